@@ -1,0 +1,188 @@
+"""Mints the committed golden vectors by running the REAL Kover reference (loaded from
+/root/reference by oracle/ref_loader.py) on the seeded inputs of cases.py.
+
+Run in the build container only:   python tests/golden/make_golden.py
+Outputs: tests/golden/*.npz (small, committed).  The GPU box has no reference tree; tests
+there compare against these files.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+
+import cases  # noqa: E402
+from oracle.ref_loader import ChunkedArray, load_reference  # noqa: E402
+
+ref = load_reference()
+
+
+def save(name, **arrays):
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **arrays)
+    print("wrote %-32s %8d bytes" % (name + ".npz", os.path.getsize(path)))
+
+
+def ref_rc(P, n, chunks):
+    return ref.rules.KmerRuleClassifications(ChunkedArray(P, chunks), n)
+
+
+# ------------------------------------------------------------------ popcount + pack (a1, a12)
+def gen_popcount():
+    rs = np.random.RandomState(100)
+    a64 = rs.randint(0, 2 ** 63, size=(4, 257), dtype=np.int64).astype(np.uint64)
+    a64 ^= rs.randint(0, 2, size=a64.shape, dtype=np.int64).astype(np.uint64) << np.uint64(63)
+    a64[rs.rand(*a64.shape) < 0.1] = 0
+    m64 = np.array([0xFFFFFFFFFFFFFFFF, 0, 0x8000000000000001, 0x00FF00FF00FF00FF], dtype=np.uint64)
+    o64 = a64.copy()
+    ref.popcount.inplace_popcount_64(o64, m64)
+    a32 = rs.randint(0, 2 ** 32, size=(3, 131), dtype=np.int64).astype(np.uint32)
+    a32[rs.rand(*a32.shape) < 0.1] = 0
+    m32 = np.array([0xFFFFFFFF, 0x80000001, 0x0F0F0F0F], dtype=np.uint32)
+    o32 = a32.copy()
+    ref.popcount.inplace_popcount_32(o32, m32)
+    save("popcount", a64=a64, m64=m64, o64=o64, a32=a32, m32=m32, o32=o32)
+
+
+def gen_pack():
+    X = cases.dense_bits(101, 130, 9, 0.5)
+    p64 = ref.utils._pack_binary_bytes_to_ints(X, 64)
+    p32 = ref.utils._pack_binary_bytes_to_ints(X, 32)
+    u64 = ref.utils._unpack_binary_bytes_from_ints(p64)
+    u32 = ref.utils._unpack_binary_bytes_from_ints(p32)
+    mins = np.array([np.dtype(ref.utils._minimum_uint_size(v)).itemsize for v in (0, 255, 256, 65535, 65536, 2 ** 32)])
+    save("pack", X=X, p64=p64, p32=p32, u64=u64, u32=u32, min_uint_itemsize=mins)
+
+
+# ------------------------------------------------------------------ sum_rows / get_columns (a3, a4, a5)
+def gen_rules():
+    for mname in ("M1", "M2", "M3", "M4"):
+        X, P, n, chunks = cases.matrix(mname)
+        k = P.shape[1]
+        out = {}
+        rc = ref_rc(P, n, chunks)
+        out["shape"] = np.array(rc.shape)
+        for rname, rows in cases.row_sets(n).items():
+            r = rc.sum_rows(rows)
+            out["sum_" + rname] = r
+        for cname, cols in cases.column_sets(k).items():
+            out["col_" + cname] = rc.get_columns(cols)
+        if mname == "M3":        # 32-bit packing (reader supports it: rules.py:123-125)
+            rc32 = ref_rc(cases.pack32_from64(P), n, chunks)
+            for rname, rows in cases.row_sets(n).items():
+                out["sum32_" + rname] = rc32.sum_rows(rows)
+            out["col32_mixed"] = rc32.get_columns(cases.column_sets(k)["mixed"])
+        if mname == "M4":        # remove_rows bookkeeping (rules.py:173-194)
+            rc2 = ref_rc(P, n, chunks)
+            rc2.remove_rows([3, 10])
+            rc2.remove_rows([0])
+            out["rm_shape"] = np.array(rc2.shape)
+            out["rm_sum"] = rc2.sum_rows(np.array([0, 1, 2, 9, 40, 61]))
+            out["rm_col"] = rc2.get_columns([1, k + 2])
+        save("rules_" + mname, **out)
+
+
+# ------------------------------------------------------------------ SCM utility scan (a6)
+def gen_utility():
+    for case in cases.UTILITY_CASES:
+        P, n, chunks, pos, neg, p, blacklist, ubs = cases.utility_inputs(case)
+        ref.scm.UTIL_BLOCK_SIZE = ubs
+        m = ref.scm.SetCoveringMachine(model_type=ref.models.conjunction, p=p, max_rules=10)
+        bu, bi, bp, bn = m._get_best_utility_rules(ref_rc(P, n, chunks), pos, neg, rule_blacklist=blacklist)
+        save(case[0], best_utility=np.float64(bu), best_idx=np.asarray(bi, dtype=np.int64),
+             best_pos_err=np.asarray(bp, dtype=np.int64), best_neg_cover=np.asarray(bn, dtype=np.int64))
+    ref.scm.UTIL_BLOCK_SIZE = 1000000
+
+
+# ------------------------------------------------------------------ SCM fit (a7, a8)
+def gen_scm():
+    for case in cases.SCM_CASES:
+        name, mname, lname, model_type, p, max_rules, tb, blacklist, ubs = case
+        X, P, n, chunks = cases.matrix(mname)
+        y = cases.labels(lname)
+        k = P.shape[1]
+        ref.scm.UTIL_BLOCK_SIZE = ubs
+        rc = ref_rc(P, n, chunks)
+        rules = ref.rules.LazyKmerRuleList(["K%d" % i for i in range(k)], np.arange(k))
+        risks = cases.rule_risks(2 * k)
+
+        def tiebreaker(idx):                      # experiment_scm.py:122-130
+            if tb == "identity":
+                return idx
+            tie = risks[idx]
+            if model_type == "conjunction":
+                return idx[np.isclose(tie, tie.min())]
+            return idx[np.isclose(tie, tie.max())]
+
+        infos = []
+        m = ref.scm.SetCoveringMachine(model_type=model_type, p=p, max_rules=max_rules)
+        m.fit(rules, rc, np.where(y == 1)[0], np.where(y == 0)[0], rule_blacklist=blacklist,
+              tiebreaker=tiebreaker, iteration_callback=lambda i: infos.append(dict(i)),
+              iteration_rule_importances=True)
+        out = {"n_iterations": np.array(len(infos)),
+               "model_str": np.array(str(m.model)),
+               "rule_importances": np.asarray(m.rule_importances, dtype=np.float64)}
+        for t, info in enumerate(infos):
+            out["it%d_utility_max" % t] = np.float64(info["utility_max"])
+            out["it%d_utility_argmax" % t] = np.asarray(info["utility_argmax"], dtype=np.int64)
+            out["it%d_equivalent" % t] = np.asarray(info["equivalent_rules_idx"], dtype=np.int64)
+            out["it%d_selected" % t] = np.array(str(info["selected_rule"]))
+            out["it%d_importances" % t] = np.asarray(info["rule_importances"], dtype=np.float64)
+        save(name, **out)
+    ref.scm.UTIL_BLOCK_SIZE = 1000000
+
+
+# ------------------------------------------------------------------ CART fit (a9, a11)
+def tree_to_dict(node):
+    d = {"depth": node.depth, "criterion_value": float(node.criterion_value),
+         "n_by_class": {int(c): int(len(v)) for c, v in node.class_examples_idx.items()}}
+    if node.rule is not None:
+        d["rule_idx"] = int(node.rule.kmer_index)
+        d["equivalent_rules_idx"] = [int(x) for x in node.rule.equivalent_rules_idx]
+        d["importance"] = float(node.rule.importance)
+        d["left"] = tree_to_dict(node.left_child)
+        d["right"] = tree_to_dict(node.right_child)
+    return d
+
+
+def gen_cart():
+    for case in cases.CART_CASES:
+        name, mname, lname, max_depth, mss, class_importance, tb, subset_seed = case
+        X, P, n, chunks = cases.matrix(mname)
+        y = cases.labels(lname)
+        k = P.shape[1]
+        rc = ref_rc(P, n, chunks)
+        rules = ref.rules.LazyKmerRuleList(["K%d" % i for i in range(k)], np.arange(k))
+        train = cases.train_subset(n, subset_seed)
+        example_idx = {c: train[y[train] == c] for c in sorted(class_importance.keys())}
+        if tb == "occurrence":                    # experiment_cart.py:82-94, 264
+            occ = rc.sum_rows(train)
+            tiebreaker = lambda idx: idx[np.isclose(occ[idx], occ[idx].max())]
+        else:
+            tiebreaker = None
+
+        def split_cb(node, equiv):                # experiment_cart.py:97-106
+            node.rule.equivalent_rules_idx = equiv
+
+        t = ref.cart.DecisionTreeClassifier("gini", max_depth, mss, class_importance)
+        t.fit(rules, rc, example_idx, rule_blacklist=[], tiebreaker=tiebreaker, split_callback=split_cb)
+        d = tree_to_dict(t.decision_tree)
+        # also the raw root scores, to pin the float64 operation order of _gini_rule_score
+        save(name, tree_json=np.array(json.dumps(d)))
+    # raw root gini scores for two cases (cart.py:112-161 is a closure: re-run it via a tiny fit that
+    # captures rules_criterion through the tiebreaker's candidate set is not possible; instead pin the
+    # scores through `candidates == where(score == min)` at every node, which tree_json already holds)
+
+
+if __name__ == "__main__":
+    gen_popcount()
+    gen_pack()
+    gen_rules()
+    gen_utility()
+    gen_scm()
+    gen_cart()
