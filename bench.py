@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""bench.py -- k-mer rules scored per second per SCM iteration (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One STEP = one SCM iteration scan (`_get_best_utility_rules`, reference scm.py:238-288) over the
+whole HBM-resident packed matrix: 2*K rules scored (presence + absence), the p value and the
+(fold, model-type) example masks cycling through config 2's hyper-parameter grid.
+
+N = 1 workload: BASELINE.json configs[1] -- 2 000 genomes x 10 000 000 k-mers (W = 32 packed rows,
+2.56 GB), synthetic (hash-generated on the device, kover_b200/synthetic.py), genomes sorted by label
+as the reference's dataset builder does (create.py:190-194).  N > 1: weak scaling, every rank holds
+a 2 000 x 10 000 000 column shard of a 2 000 x (N * 10 M) matrix; the only exchange per step is the
+per-utility-block maxima + tie lists (sharding.ShardGroup over NCCL).
+
+value     rules/s, K steps timed with CUDA events on the shard's stream (inputs resident in HBM)
+roofline  algorithmic bytes of the scan kernel (8 * W_active * K_local per launch) / its own
+          CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs
+e2e       the same steps through the reference-shaped Python API with HOST index arrays in and
+          host result arrays out (wall clock, synchronised both sides)
+cpu_baseline / --impl reference: the CPU restatement of the reference path (oracle/), driven with
+          the reference's own compiled popcount kernel when oracle/_ref holds it.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_GENOMES = 2000
+N_KMERS_PER_GPU = 10_000_000
+SEED = 72
+P_GRID = [0.1, 0.5, 1.0, 2.0, 5.0, 10.0]
+N_FOLDS = 5
+UTIL_BLOCK_SIZE = 1000000
+CPU_SAMPLE_COLS = 1_000_000
+
+
+# ------------------------------------------------------------------------------------------ workload
+def step_inputs(n_genomes, seed, sorted_by_label=True):
+    """The (p, pos_idx, neg_idx) of every step in the cycle: p grid x {conjunction, disjunction} x
+    {full training set, 5 CV folds} -- the fits config 2 runs (experiment_scm.py:196-248)."""
+    from kover_b200.synthetic import synthetic_labels, train_split
+    y = synthetic_labels(seed, n_genomes, sorted_by_label=sorted_by_label)
+    train = train_split(seed, n_genomes)
+    rs = np.random.RandomState(seed)
+    fold_of = rs.randint(0, N_FOLDS, size=train.shape[0])
+    subsets = [train] + [train[fold_of != f] for f in range(N_FOLDS)]
+    steps = []
+    for sub in subsets:
+        pos, neg = sub[y[sub] == 1], sub[y[sub] == 0]
+        for model_type in ("conjunction", "disjunction"):
+            for p in P_GRID:
+                steps.append((p, pos, neg) if model_type == "conjunction" else (p, neg, pos))
+    return steps
+
+
+def active_words(pos, neg, n_genomes):
+    w = np.zeros((n_genomes + 63) // 64, dtype=bool)
+    w[np.asarray(pos) // 64] = True
+    w[np.asarray(neg) // 64] = True
+    return int(w.sum())
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler(object):
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.samples, self._stop, self._t = device, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 6:
+                    self.samples.append(f)
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=10)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+_CPU = {}
+
+
+def _cpu_init(n_genomes, seed, c0, n_cols, use_ref_kernel):
+    from kover_b200.synthetic import synthetic_block
+    from oracle import kover_oracle as ko
+    P = synthetic_block(seed, n_genomes, c0, n_cols)
+
+    class Chunked(np.ndarray):
+        chunks = None
+    d = P.view(Chunked)
+    d.chunks = (1, 100000)                       # the HDF5 chunk shape the reference iterates (create.py:230)
+    rc = ko.OracleKmerRuleClassifications(d, n_genomes, fast=False)
+    kind = "port"
+    if use_ref_kernel:
+        try:
+            from oracle import ref_loader
+            pc = ref_loader.load_reference_popcount()
+            rc.inplace_popcount = pc.inplace_popcount_64      # the reference's own compiled popcount.pyx
+            kind = "reference-kernel"
+        except Exception:  # noqa: BLE001
+            pass
+    _CPU["rc"], _CPU["ko"], _CPU["kind"] = rc, ko, kind
+
+
+def _cpu_step(args):
+    p, pos, neg = args
+    rc, ko = _CPU["rc"], _CPU["ko"]
+    t0 = time.perf_counter()
+    out = ko.best_utility_rules(rc, p, pos, neg)
+    return time.perf_counter() - t0, float(out[0]), int(len(out[1]))
+
+
+def ref_kernel_available():
+    import sysconfig
+    so = os.path.join(ROOT, "oracle", "_ref", "popcount" + sysconfig.get_config_var("EXT_SUFFIX"))
+    return os.path.isfile(so) or os.path.isdir("/root/reference")
+
+
+def cpu_baseline(n_genomes, seed, steps, n_steps=4):
+    """1 core (the reference hot path is single-threaded), bounded sample: CPU_SAMPLE_COLS columns."""
+    _cpu_init(n_genomes, seed, 0, CPU_SAMPLE_COLS, ref_kernel_available())
+    times = [_cpu_step(steps[i % len(steps)])[0] for i in range(n_steps)]
+    best = min(times)
+    return {"value": 2.0 * CPU_SAMPLE_COLS / best, "unit": "rules/s", "cores": 1,
+            "kind": "port", "native_kernel": _CPU["kind"],
+            "sample": "%d of %d k-mer columns x all %d genomes (in RAM, no HDF5/gzip), best of %d scans of "
+                      "oracle.best_utility_rules (2 sum_rows block loops + utility merge); scales linearly in columns"
+                      % (CPU_SAMPLE_COLS, N_KMERS_PER_GPU, n_genomes, n_steps)}
+
+
+def run_reference_arm(args):
+    """The reference's CPU implementation of the path on all host cores: the reference parallelises over
+    hyper-parameter combinations with a fork pool (experiment_scm.py:217), so every worker runs an
+    independent scan (its own p / masks) over the same bounded sample of the matrix."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    steps = step_inputs(N_GENOMES, SEED)
+    use_ref = ref_kernel_available()
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores, initializer=_cpu_init, initargs=(N_GENOMES, SEED, 0, CPU_SAMPLE_COLS, use_ref)) as pool:
+        batch = lambda i: [steps[(i * cores + j) % len(steps)] for j in range(cores)]
+        for w in range(args.warmup):
+            pool.map(_cpu_step, batch(w))
+        t0 = time.perf_counter()
+        for s in range(args.steps):
+            pool.map(_cpu_step, batch(args.warmup + s))
+        dt = time.perf_counter() - t0
+    _cpu_init(N_GENOMES, SEED, 0, 1024, use_ref)
+    rules = 2.0 * CPU_SAMPLE_COLS * cores * args.steps
+    value = rules / dt
+    sample = ("each step = %d concurrent scans (one per host core, the reference's Pool-over-HP parallelism) of "
+              "%d of %d k-mer columns x %d genomes held in RAM (no HDF5/gzip)" %
+              (cores, CPU_SAMPLE_COLS, N_KMERS_PER_GPU * args.gpus, N_GENOMES))
+    line = {
+        "impl": "reference", "metric": "kmer_rules_scored_per_sec_per_scm_iteration", "value": value,
+        "unit": "rules/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u64 popcount + f64 utility", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": "rules/s", "cores": cores, "kind": "port",
+                         "native_kernel": _CPU["kind"], "sample": sample},
+        "e2e": {"value": value, "unit": "rules/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_config(n_gpus):
+    return {"workload": "BASELINE configs[1]: SCM utility scan, 2000 genomes x 10M k-mers per GPU (W=32 packed rows, "
+                        "2.56 GB per GPU), p grid {0.1,0.5,1,2,5,10} x {conjunction,disjunction} x {train, 5 CV folds}",
+            "n_genomes": N_GENOMES, "n_kmers_per_gpu": N_KMERS_PER_GPU, "n_kmers_total": N_KMERS_PER_GPU * n_gpus,
+            "rules_per_step": 2 * N_KMERS_PER_GPU * n_gpus, "util_block_size": UTIL_BLOCK_SIZE,
+            "labels": "genomes sorted by label (create.py:190-194)", "sharding": "k-mer columns, %d shard(s)" % n_gpus,
+            "l2": "inputs (2.56 GB/GPU) are 20x larger than the 126 MB L2; no flush needed"}
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def run_ours(args):
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus %d needs torchrun (one process per GPU)" % args.gpus)
+    import torch
+    from kover_b200 import _native
+    from kover_b200.learning.common.rules import KmerRuleClassifications
+    from kover_b200.sharding import Comm, ShardGroup
+
+    torch.cuda.set_device(local_rank)
+    comm = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        comm = Comm()
+
+    k_local, k_total = N_KMERS_PER_GPU, N_KMERS_PER_GPU * world
+    col0 = rank * k_local
+    shard = _native.Shard(local_rank, N_GENOMES, k_total, col0, k_local)
+    t0 = time.perf_counter()
+    shard.generate_synthetic(SEED)
+    gen_s = time.perf_counter() - t0
+    slices = [(r * k_local, k_local) for r in range(world)]
+    group = ShardGroup([shard], N_GENOMES, k_total, comm=comm, rank_slices=slices)
+
+    class Meta(object):
+        shape = ((N_GENOMES + 63) // 64, k_total)
+        dtype = np.dtype(np.uint64)
+        chunks = (1, 100000)
+    rc = KmerRuleClassifications(Meta(), N_GENOMES, shard_group=group)
+
+    steps = step_inputs(N_GENOMES, SEED)
+    info0 = shard.info()
+
+    def one_step(i):
+        p, pos, neg = steps[i % len(steps)]
+        return rc.best_utility_rules(p, pos, neg, util_block_size=UTIL_BLOCK_SIZE)
+
+    def sync_all():
+        if comm is not None:
+            torch.cuda.synchronize()
+            comm.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        one_step(i)
+
+    # ---- timed region 1: device time of K steps (CUDA events on the shard's stream), inputs resident
+    kernel_ms, alg_bytes, d2h, h2d = [], [], 0, 0
+    with ClockSampler(local_rank) as clocks:
+        sync_all()
+        launches0 = shard.info().total_launches
+        shard.timer_start()
+        wall0 = time.perf_counter()
+        for i in range(args.steps):
+            p, pos, neg = steps[(args.warmup + i) % len(steps)]
+            out = rc.best_utility_rules(p, pos, neg, util_block_size=UTIL_BLOCK_SIZE)
+            kernel_ms.append(shard.info().last_kernel_ms)
+            wa = active_words(pos, neg, N_GENOMES)
+            alg_bytes.append(8.0 * wa * k_local)
+            h2d += wa * 20
+            d2h += _native.n_utility_blocks(k_total, UTIL_BLOCK_SIZE) * 8 + 8 + 16 * len(out[1])
+        dev_ms = shard.timer_stop()
+        sync_all()
+        wall_s = time.perf_counter() - wall0
+        launches = shard.info().total_launches - launches0
+        # keep the sampler alive for at least a few samples on very short runs
+        if wall_s < 0.5:
+            for i in range(int(0.5 / max(wall_s / args.steps, 1e-4))):
+                one_step(i)
+    if comm is not None:
+        dev_ms = float(comm.allreduce_max(np.array([dev_ms]))[0])
+        wall_s = float(comm.allreduce_max(np.array([wall_s]))[0])
+        launches = int(comm.allreduce_sum(np.array([launches], dtype=np.int64))[0])
+
+    # ---- timed region 2: end to end through the reference-shaped API, host arrays in and out
+    from kover_b200.learning.learners.scm import SetCoveringMachine
+    learners = {p: SetCoveringMachine(p=p) for p in P_GRID}
+    sync_all()
+    e0 = time.perf_counter()
+    for i in range(args.steps):
+        p, pos, neg = steps[(args.warmup + i) % len(steps)]
+        res = learners[p]._get_best_utility_rules(rc, pos, neg, rule_blacklist=[])
+        assert isinstance(res[1], np.ndarray)
+    sync_all()
+    e2e_s = time.perf_counter() - e0
+    if comm is not None:
+        e2e_s = float(comm.allreduce_max(np.array([e2e_s]))[0])
+
+    rules_per_step = 2.0 * k_total
+    value = rules_per_step * args.steps / (dev_ms * 1e-3)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy)"
+    else:
+        peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+    achieved = float(np.sum(alg_bytes) / (np.sum(kernel_ms) * 1e-3) / 1e9)
+    line = {
+        "metric": "kmer_rules_scored_per_sec_per_scm_iteration", "value": value, "unit": "rules/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u64 popcount + f64 utility", "data": "synthetic (hash-generated on device, seed %d)" % SEED,
+        "config": workload_config(world),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "kernel": "k_scan2<EPI_SCM>", "peak_source": peak_src,
+                     "bytes_per_launch": float(np.mean(alg_bytes)), "kernel_ms": float(np.mean(kernel_ms)),
+                     "kernel_share_of_step": float(np.sum(kernel_ms) / dev_ms)},
+        "e2e": {"value": rules_per_step * args.steps / e2e_s, "unit": "rules/s",
+                "h2d_bytes_per_step": int(h2d / args.steps), "d2h_bytes_per_step": int(d2h / args.steps),
+                "ms_per_step": 1e3 * e2e_s / args.steps,
+                "api": "SetCoveringMachine._get_best_utility_rules(rule_classifications, pos_idx, neg_idx) with host "
+                       "index arrays in, host tie arrays out; matrix resident (uploaded once per dataset)"},
+        "gpu_launches": int(launches),
+        "clocks": clocks.summary(),
+        "wall_ms_per_step": 1e3 * wall_s / args.steps,
+        "generate_s": gen_s,
+    }
+    if rank == 0 and world == 1:
+        line["cpu_baseline"] = cpu_baseline(N_GENOMES, SEED, steps)
+    if rank == 0:
+        print(json.dumps(line))
+    rc.close()
+    if comm is not None:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=72)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,158 @@
+/* kover_b200.h -- C ABI of libkoverb200.so: Kover's rule-scoring hot path on B200 (sm_100a).
+ *
+ * This is the native boundary a Kover maintainer binds (ctypes stub: INTEGRATION.md).  It sits
+ * where the reference's Cython module `kover.learning.common.popcount` sits today, but one level
+ * up -- at `KmerRuleClassifications.sum_rows` granularity -- because a call per 800 KB host block
+ * (reference rules.py:247-262) cannot feed a GPU.  Each entry point cites the reference interface
+ * it replaces (paths relative to /root/reference/core/kover).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every array is caller-owned, contiguous, host memory and is
+ *     not retained after the call returns;
+ *   - every function returns 0 on success, a negative KV_E_* code otherwise; the message is in
+ *     kv_last_error() (thread-local);
+ *   - one kv_shard = one contiguous k-mer-column slice of the packed matrix resident in the HBM of
+ *     one GPU.  A single-GPU job has one shard covering all columns; a multi-GPU job has one per
+ *     rank (one process per GPU) or one per device (single process);
+ *   - calls on a shard are synchronous at the ABI and must come from one host thread at a time;
+ *   - no CPU fallback: without a usable CUDA device kv_create() fails.
+ *
+ * Packed layout (the HDF5 `kmer_matrix` contract, utils.py:133-156, create.py:224-230):
+ *   uint64 [W = ceil(n_examples/64), K] row-major; example i is bit 63-(i%64) of word i/64 of its
+ *   column; padding bits of the last word are zero.  Row masks use the same bit order
+ *   (rules.py:210-222).  Rule index r in [0,K) = presence of k-mer r, r in [K,2K) = absence of
+ *   k-mer r-K (rules.py:57-79).
+ */
+#ifndef KOVER_B200_H
+#define KOVER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KV_OK 0
+#define KV_E_INVALID (-1)   /* bad argument (Python shim raises ValueError)            */
+#define KV_E_CUDA (-2)      /* CUDA runtime error / no device (RuntimeError)             */
+#define KV_E_NOMEM (-3)     /* device or pinned allocation failed (MemoryError)          */
+#define KV_E_OVERFLOW (-4)  /* caller's tie buffer too small; *n_found holds the need    */
+
+typedef struct kv_shard kv_shard;
+
+typedef struct kv_shard_info {
+    int32_t device;          /* CUDA ordinal                                             */
+    int32_t sm_count;        /* multiprocessors (148 on B200)                            */
+    int64_t n_examples;      /* genomes                                                  */
+    int64_t n_words;         /* W = ceil(n_examples / 64)                                */
+    int64_t n_kmers_total;   /* K of the whole dataset                                   */
+    int64_t col0;            /* first global column held by this shard                   */
+    int64_t n_cols;          /* columns held                                             */
+    int64_t ld;              /* device row pitch in 64-bit words                         */
+    int64_t matrix_bytes;    /* bytes of HBM behind the packed image                     */
+    double last_kernel_ms;   /* CUDA-event time of the scan kernel of the last scan call */
+    int64_t last_launches;   /* kernels launched by the last call                        */
+    int64_t total_launches;  /* kernels launched since kv_create                         */
+} kv_shard_info;
+
+const char *kv_last_error(void);
+int kv_abi_version(void);
+int kv_device_count(int *n_devices);
+
+/* ---- lifecycle ---------------------------------------------------------------------------
+ * Replaces KmerRuleClassifications.__init__ binding an h5py dataset (rules.py:104-133): the
+ * shard owns a zero-initialised [W, n_cols] packed image in HBM. */
+int kv_create(int device, int64_t n_examples, int64_t n_kmers_total, int64_t col0, int64_t n_cols,
+              kv_shard **out);
+int kv_destroy(kv_shard *s);
+int kv_get_info(kv_shard *s, kv_shard_info *out);
+
+/* ---- upload ------------------------------------------------------------------------------
+ * Replaces the per-call h5py chunk reads `dataset[rows, c0:c1]` (rules.py:253): every HDF5 chunk
+ * (1 x <=100000, create.py:230) is pushed once.  `host` is a [n_rows, n_cols] block with row pitch
+ * `ld_elems` elements of the packed matrix starting at packed row `row0` and GLOBAL column
+ * `gcol0`; columns outside the shard are skipped.  pack_bits = 64 or 32 (rules.py:123-128); 32-bit
+ * rows 2w, 2w+1 become the high / low halves of 64-bit row w. */
+int kv_upload_block(kv_shard *s, int pack_bits, int64_t row0, int64_t n_rows, int64_t gcol0,
+                    int64_t n_cols, const void *host, int64_t ld_elems);
+/* Fill the shard with the deterministic synthetic matrix of kover_b200/synthetic.py (bench and
+ * full-size parity tests; the CPU twin regenerates any column slice). */
+int kv_generate_synthetic(kv_shard *s, uint64_t seed);
+
+/* Read back a [n_rows, n_cols] block of 64-bit packed rows starting at packed row `row0` and LOCAL
+ * column `lcol0` (upload round-trip checks; bench staging). */
+int kv_read_block(kv_shard *s, int64_t row0, int64_t n_rows, int64_t lcol0, int64_t n_cols, uint64_t *host,
+                  int64_t ld_elems);
+
+/* ---- timing ------------------------------------------------------------------------------
+ * CUDA events on the shard's own stream (torch.cuda.Event cannot see it): start, run any number of
+ * calls, stop -> device milliseconds between the two marks. */
+int kv_timer_start(kv_shard *s);
+int kv_timer_stop(kv_shard *s, double *elapsed_ms);
+
+/* ---- a1: popcount.pyx:52-67, 97-112 -------------------------------------------------------
+ * arr[i,j] <- popcount(arr[i,j] & row_mask[i]) for arr[i,j] != 0, in place, [m,n] C-contiguous
+ * host block.  Stateless (uploads, runs, downloads) -- kept for drop-in completeness. */
+int kv_inplace_popcount_64(int device, uint64_t *arr, int64_t m, int64_t n, const uint64_t *row_mask);
+int kv_inplace_popcount_32(int device, uint32_t *arr, int64_t m, int64_t n, const uint32_t *row_mask);
+
+/* ---- a3: KmerRuleClassifications.sum_rows (rules.py:201-267) ------------------------------
+ * mask: W words built as rules.py:210-222.  out[n_cols] = per local column, the number of masked
+ * examples having the k-mer, stored with out_itemsize = 1, 2, 4 or 8 bytes (the reference's
+ * _minimum_uint_size dtype, utils.py:117-130).  The absence half is len(rows) - out (rules.py:265)
+ * and is left to the caller. */
+int kv_sum_rows(kv_shard *s, const uint64_t *mask, void *out, int out_itemsize);
+/* Several masks in one pass over the matrix (the reference's own TODO, rules.py:200).
+ * masks: [n_masks, W]; out: [n_masks, n_cols] uint32. */
+int kv_sum_rows_multi(kv_shard *s, int n_masks, const uint64_t *masks, uint32_t *out);
+
+/* ---- a4: KmerRuleClassifications.get_columns (rules.py:135-171) ---------------------------
+ * cols: n LOCAL presence-column indices.  out: [n, W] packed words (column j's W words are
+ * contiguous).  Unpacking / inversion for absence rules is host work on W words. */
+int kv_get_columns(kv_shard *s, const int64_t *cols, int64_t n, uint64_t *out);
+
+/* ---- a6: SetCoveringMachine._get_best_utility_rules (scm.py:238-288) ----------------------
+ * Blacklist: GLOBAL rule indices in [0, 2K); entries outside the shard are ignored; n = 0 clears
+ * (scm.py:239-240, 267). */
+int kv_set_blacklist(kv_shard *s, const int64_t *rule_idx, int64_t n);
+/* Number of utility blocks of `util_block_size` rules over the 2K rule space (scm.py:262). */
+int64_t kv_scm_n_blocks(int64_t n_kmers_total, int64_t util_block_size);
+/* Phase 1: one pass over the shard.  Counts for both masks, utility
+ * u = neg_cover - p * pos_err (two rounded fp64 ops, scm.py:263-264), blacklisted -> -inf, and the
+ * maximum of every utility block this shard touches.  block_max[n_blocks] receives -inf for
+ * untouched blocks, so shards merge with an element-wise max. */
+int kv_scm_scan(kv_shard *s, const uint64_t *pos_mask, const uint64_t *neg_mask, int64_t n_pos,
+                int64_t n_neg, double p, int64_t util_block_size, double *block_max, int64_t n_blocks);
+/* Host-only replay of the sequential block merge (scm.py:270-286) over the MERGED block maxima:
+ * selected[b] = 1 for blocks whose ties survive; *best_utility as the reference returns it. */
+int kv_scm_select_blocks(const double *block_max, int64_t n_blocks, double *best_utility,
+                         uint8_t *selected);
+/* Phase 2: rules of the selected blocks with isclose(u, block_max[b]) (scm.py:273), GLOBAL rule
+ * indices ascending, with their pos_err / neg_cover counts.  Uses the counts left on the device by
+ * the last kv_scm_scan.  Returns KV_E_OVERFLOW (and the needed size in *n_found) when capacity is
+ * too small. */
+int kv_scm_ties(kv_shard *s, const double *block_max, const uint8_t *selected, int64_t n_blocks,
+                int64_t capacity, int64_t *rule_idx, int64_t *pos_err, int64_t *neg_cover,
+                int64_t *n_found);
+/* Single-shard convenience: scan + select + ties in one call. */
+int kv_scm_best_rules(kv_shard *s, const uint64_t *pos_mask, const uint64_t *neg_mask, int64_t n_pos,
+                      int64_t n_neg, double p, int64_t util_block_size, double *best_utility,
+                      int64_t capacity, int64_t *rule_idx, int64_t *pos_err, int64_t *neg_cover,
+                      int64_t *n_found);
+
+/* ---- a9 / a11: DecisionTreeClassifier _gini_rule_score + _find_best_split (cart.py:112-161,
+ * 219-250) --------------------------------------------------------------------------------
+ * class_masks: [n_classes, W] masks of the node's examples per class, in the caller's dict order;
+ * altered_prior, n_total (cart.py:71-77), n_node = len(example_idx[c]).  Phase 1 returns the
+ * minimum split score over the shard's presence rules (blacklisted / empty-child -> +inf). */
+int kv_gini_scan(kv_shard *s, int n_classes, const uint64_t *class_masks, const double *altered_prior,
+                 const double *n_total, const int64_t *n_node, double *min_score);
+/* Phase 2: rules with score == min_score exactly (cart.py:238), GLOBAL indices ascending. */
+int kv_gini_ties(kv_shard *s, double min_score, int64_t capacity, int64_t *rule_idx, int64_t *n_found);
+/* The split scores themselves (testing / callers that want rules_criterion): out[n_cols]. */
+int kv_gini_scores(kv_shard *s, double *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KOVER_B200_H */

@@ -1,0 +1,319 @@
+"""ctypes binding of libkoverb200.so (C ABI: include/kover_b200.h).
+
+Nothing here computes: every function forwards to the CUDA library and turns its integer status
+into the exception type the reference raises for the same mistake (ValueError for bad arguments,
+RuntimeError otherwise).  If the library is missing it is built once with nvcc; if that is not
+possible, or no GPU is usable, calls fail loudly -- there is no CPU fallback.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+from . import build as _build
+
+KV_OK, KV_E_INVALID, KV_E_CUDA, KV_E_NOMEM, KV_E_OVERFLOW = 0, -1, -2, -3, -4
+
+_c_i64 = ctypes.c_int64
+_c_p = ctypes.c_void_p
+
+
+class ShardInfo(ctypes.Structure):
+    _fields_ = [("device", ctypes.c_int32), ("sm_count", ctypes.c_int32), ("n_examples", _c_i64),
+                ("n_words", _c_i64), ("n_kmers_total", _c_i64), ("col0", _c_i64), ("n_cols", _c_i64),
+                ("ld", _c_i64), ("matrix_bytes", _c_i64), ("last_kernel_ms", ctypes.c_double),
+                ("last_launches", _c_i64), ("total_launches", _c_i64)]
+
+
+# every exported symbol with (restype, argtypes); tests/test_abi.py checks this table against the header
+SYMBOLS = {
+    "kv_last_error": (ctypes.c_char_p, []),
+    "kv_abi_version": (ctypes.c_int, []),
+    "kv_device_count": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int)]),
+    "kv_create": (ctypes.c_int, [ctypes.c_int, _c_i64, _c_i64, _c_i64, _c_i64, ctypes.POINTER(_c_p)]),
+    "kv_destroy": (ctypes.c_int, [_c_p]),
+    "kv_get_info": (ctypes.c_int, [_c_p, ctypes.POINTER(ShardInfo)]),
+    "kv_upload_block": (ctypes.c_int, [_c_p, ctypes.c_int, _c_i64, _c_i64, _c_i64, _c_i64, _c_p, _c_i64]),
+    "kv_generate_synthetic": (ctypes.c_int, [_c_p, ctypes.c_uint64]),
+    "kv_read_block": (ctypes.c_int, [_c_p, _c_i64, _c_i64, _c_i64, _c_i64, _c_p, _c_i64]),
+    "kv_timer_start": (ctypes.c_int, [_c_p]),
+    "kv_timer_stop": (ctypes.c_int, [_c_p, ctypes.POINTER(ctypes.c_double)]),
+    "kv_inplace_popcount_64": (ctypes.c_int, [ctypes.c_int, _c_p, _c_i64, _c_i64, _c_p]),
+    "kv_inplace_popcount_32": (ctypes.c_int, [ctypes.c_int, _c_p, _c_i64, _c_i64, _c_p]),
+    "kv_sum_rows": (ctypes.c_int, [_c_p, _c_p, _c_p, ctypes.c_int]),
+    "kv_sum_rows_multi": (ctypes.c_int, [_c_p, ctypes.c_int, _c_p, _c_p]),
+    "kv_get_columns": (ctypes.c_int, [_c_p, _c_p, _c_i64, _c_p]),
+    "kv_set_blacklist": (ctypes.c_int, [_c_p, _c_p, _c_i64]),
+    "kv_scm_n_blocks": (_c_i64, [_c_i64, _c_i64]),
+    "kv_scm_scan": (ctypes.c_int, [_c_p, _c_p, _c_p, _c_i64, _c_i64, ctypes.c_double, _c_i64, _c_p, _c_i64]),
+    "kv_scm_select_blocks": (ctypes.c_int, [_c_p, _c_i64, ctypes.POINTER(ctypes.c_double), _c_p]),
+    "kv_scm_ties": (ctypes.c_int, [_c_p, _c_p, _c_p, _c_i64, _c_i64, _c_p, _c_p, _c_p, ctypes.POINTER(_c_i64)]),
+    "kv_scm_best_rules": (ctypes.c_int, [_c_p, _c_p, _c_p, _c_i64, _c_i64, ctypes.c_double, _c_i64,
+                                         ctypes.POINTER(ctypes.c_double), _c_i64, _c_p, _c_p, _c_p,
+                                         ctypes.POINTER(_c_i64)]),
+    "kv_gini_scan": (ctypes.c_int, [_c_p, ctypes.c_int, _c_p, _c_p, _c_p, _c_p, ctypes.POINTER(ctypes.c_double)]),
+    "kv_gini_ties": (ctypes.c_int, [_c_p, ctypes.c_double, _c_i64, _c_p, ctypes.POINTER(_c_i64)]),
+    "kv_gini_scores": (ctypes.c_int, [_c_p, _c_p]),
+}
+
+_lib = None
+
+
+def library_path():
+    return _build.LIB
+
+
+def load():
+    """The loaded library (built on first use if absent).  Raises RuntimeError if unavailable."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB
+    if not os.path.isfile(path):
+        try:
+            _build.build_native()
+        except Exception as e:  # noqa: BLE001
+            raise RuntimeError("libkoverb200.so is missing and could not be built with nvcc (%s). kover_b200 has "
+                               "no CPU fallback: build it with `python -m kover_b200.build`." % e)
+    lib = ctypes.CDLL(path)
+    for name, (res, args) in SYMBOLS.items():
+        f = getattr(lib, name)
+        f.restype = res
+        f.argtypes = args
+    _lib = lib
+    return lib
+
+
+def last_error():
+    return load().kv_last_error().decode("utf-8", "replace")
+
+
+def check(rc):
+    if rc == KV_OK:
+        return
+    msg = last_error()
+    if rc == KV_E_INVALID:
+        raise ValueError(msg)
+    if rc == KV_E_NOMEM:
+        raise MemoryError(msg)
+    raise RuntimeError(msg)
+
+
+def ptr(a):
+    """Data pointer of a C-contiguous numpy array (or None)."""
+    if a is None:
+        return None
+    assert a.flags.c_contiguous
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def device_count():
+    n = ctypes.c_int(0)
+    check(load().kv_device_count(ctypes.byref(n)))
+    return n.value
+
+
+class Shard(object):
+    """One contiguous k-mer-column slice of the packed matrix resident in the HBM of one GPU."""
+
+    def __init__(self, device, n_examples, n_kmers_total, col0=0, n_cols=None):
+        self._lib = load()
+        self._h = _c_p()
+        if n_cols is None:
+            n_cols = n_kmers_total - col0
+        check(self._lib.kv_create(int(device), int(n_examples), int(n_kmers_total), int(col0), int(n_cols),
+                                  ctypes.byref(self._h)))
+        self.device = int(device)
+        self.n_examples = int(n_examples)
+        self.n_words = (self.n_examples + 63) // 64
+        self.n_kmers_total = int(n_kmers_total)
+        self.col0 = int(col0)
+        self.n_cols = int(n_cols)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.kv_destroy(self._h)
+            self._h = _c_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    def info(self):
+        i = ShardInfo()
+        check(self._lib.kv_get_info(self._h, ctypes.byref(i)))
+        return i
+
+    # -- upload
+    def upload_block(self, block, row0, gcol0):
+        block = np.asarray(block)
+        if block.dtype == np.uint64:
+            bits = 64
+        elif block.dtype == np.uint32:
+            bits = 32
+        else:
+            raise ValueError("Unsupported data type for packed attribute classifications array. The supported data"
+                             " types are np.uint32 and np.uint64.")
+        if block.ndim == 1:
+            block = block.reshape(1, -1)
+        if block.strides[1] != block.itemsize or block.strides[0] % block.itemsize or block.strides[0] < 0:
+            block = np.ascontiguousarray(block)
+        ld = block.strides[0] // block.itemsize if block.shape[0] > 1 else max(block.shape[1], 1)
+        check(self._lib.kv_upload_block(self._h, bits, int(row0), block.shape[0], int(gcol0), block.shape[1],
+                                        ctypes.c_void_p(block.ctypes.data), int(ld)))
+
+    def generate_synthetic(self, seed):
+        check(self._lib.kv_generate_synthetic(self._h, ctypes.c_uint64(int(seed))))
+
+    def read_block(self, row0, n_rows, lcol0, n_cols, out=None):
+        if out is None:
+            out = np.empty((n_rows, n_cols), dtype=np.uint64)
+        assert out.dtype == np.uint64 and out.shape == (n_rows, n_cols) and out.flags.c_contiguous
+        check(self._lib.kv_read_block(self._h, int(row0), int(n_rows), int(lcol0), int(n_cols), ptr(out), int(n_cols)))
+        return out
+
+    def timer_start(self):
+        check(self._lib.kv_timer_start(self._h))
+
+    def timer_stop(self):
+        ms = ctypes.c_double(0.0)
+        check(self._lib.kv_timer_stop(self._h, ctypes.byref(ms)))
+        return ms.value
+
+    # -- a3
+    def sum_rows(self, mask, out):
+        mask = np.ascontiguousarray(mask, dtype=np.uint64)
+        assert mask.shape == (self.n_words,) and out.shape == (self.n_cols,)
+        check(self._lib.kv_sum_rows(self._h, ptr(mask), ptr(out), out.itemsize))
+        return out
+
+    def sum_rows_multi(self, masks):
+        masks = np.ascontiguousarray(masks, dtype=np.uint64)
+        assert masks.ndim == 2 and masks.shape[1] == self.n_words
+        out = np.empty((masks.shape[0], self.n_cols), dtype=np.uint32)
+        check(self._lib.kv_sum_rows_multi(self._h, masks.shape[0], ptr(masks), ptr(out)))
+        return out
+
+    # -- a4
+    def get_columns(self, local_cols):
+        cols = np.ascontiguousarray(local_cols, dtype=np.int64)
+        out = np.empty((cols.shape[0], self.n_words), dtype=np.uint64)
+        check(self._lib.kv_get_columns(self._h, ptr(cols), cols.shape[0], ptr(out)))
+        return out
+
+    # -- a6
+    def set_blacklist(self, rule_idx):
+        idx = np.ascontiguousarray(rule_idx, dtype=np.int64)
+        check(self._lib.kv_set_blacklist(self._h, ptr(idx), idx.shape[0]))
+
+    def scm_scan(self, pos_mask, neg_mask, n_pos, n_neg, p, util_block_size):
+        nb = n_utility_blocks(self.n_kmers_total, util_block_size)
+        bm = np.empty(nb, dtype=np.float64)
+        pos_mask = np.ascontiguousarray(pos_mask, dtype=np.uint64)
+        neg_mask = np.ascontiguousarray(neg_mask, dtype=np.uint64)
+        assert pos_mask.shape == (self.n_words,) and neg_mask.shape == (self.n_words,)
+        check(self._lib.kv_scm_scan(self._h, ptr(pos_mask), ptr(neg_mask), int(n_pos), int(n_neg), float(p),
+                                    int(util_block_size), ptr(bm), nb))
+        return bm
+
+    def scm_ties(self, block_max, selected, capacity=4096):
+        bm = np.ascontiguousarray(block_max, dtype=np.float64)
+        sel = np.ascontiguousarray(selected, dtype=np.uint8)
+        while True:
+            idx = np.empty(capacity, dtype=np.int64)
+            pe = np.empty(capacity, dtype=np.int64)
+            nc = np.empty(capacity, dtype=np.int64)
+            n = _c_i64(0)
+            rc = self._lib.kv_scm_ties(self._h, ptr(bm), ptr(sel), bm.shape[0], capacity, ptr(idx), ptr(pe), ptr(nc),
+                                       ctypes.byref(n))
+            if rc == KV_E_OVERFLOW:
+                capacity = int(n.value)
+                continue
+            check(rc)
+            return idx[:n.value], pe[:n.value], nc[:n.value]
+
+    def scm_best_rules(self, pos_mask, neg_mask, n_pos, n_neg, p, util_block_size, capacity=4096):
+        pos_mask = np.ascontiguousarray(pos_mask, dtype=np.uint64)
+        neg_mask = np.ascontiguousarray(neg_mask, dtype=np.uint64)
+        assert pos_mask.shape == (self.n_words,) and neg_mask.shape == (self.n_words,)
+        best = ctypes.c_double(0.0)
+        idx = np.empty(capacity, dtype=np.int64)
+        pe = np.empty(capacity, dtype=np.int64)
+        nc = np.empty(capacity, dtype=np.int64)
+        n = _c_i64(0)
+        rc = self._lib.kv_scm_best_rules(self._h, ptr(pos_mask), ptr(neg_mask), int(n_pos), int(n_neg), float(p),
+                                         int(util_block_size), ctypes.byref(best), capacity, ptr(idx), ptr(pe),
+                                         ptr(nc), ctypes.byref(n))
+        if rc == KV_E_OVERFLOW:
+            # rare (huge equivalent-rule set): redo through the three-phase path with a buffer of the right size
+            bm = self.scm_scan(pos_mask, neg_mask, n_pos, n_neg, p, util_block_size)
+            best_v, sel = select_blocks(bm)
+            idx, pe, nc = self.scm_ties(bm, sel, int(n.value))
+            return best_v, idx, pe, nc
+        check(rc)
+        return best.value, idx[:n.value], pe[:n.value], nc[:n.value]
+
+    # -- a9 / a11
+    def gini_scan(self, class_masks, altered_prior, n_total, n_node):
+        masks = np.ascontiguousarray(class_masks, dtype=np.uint64)
+        assert masks.ndim == 2 and masks.shape[1] == self.n_words
+        pri = np.ascontiguousarray(altered_prior, dtype=np.float64)
+        tot = np.ascontiguousarray(n_total, dtype=np.float64)
+        nn = np.ascontiguousarray(n_node, dtype=np.int64)
+        assert pri.shape[0] == tot.shape[0] == nn.shape[0] == masks.shape[0]
+        out = ctypes.c_double(0.0)
+        check(self._lib.kv_gini_scan(self._h, masks.shape[0], ptr(masks), ptr(pri), ptr(tot), ptr(nn),
+                                     ctypes.byref(out)))
+        return out.value
+
+    def gini_ties(self, min_score, capacity=4096):
+        while True:
+            idx = np.empty(capacity, dtype=np.int64)
+            n = _c_i64(0)
+            rc = self._lib.kv_gini_ties(self._h, float(min_score), capacity, ptr(idx), ctypes.byref(n))
+            if rc == KV_E_OVERFLOW:
+                capacity = int(n.value)
+                continue
+            check(rc)
+            return idx[:n.value]
+
+    def gini_scores(self):
+        out = np.empty(self.n_cols, dtype=np.float64)
+        check(self._lib.kv_gini_scores(self._h, ptr(out)))
+        return out
+
+
+def n_utility_blocks(n_kmers_total, util_block_size):
+    return int(load().kv_scm_n_blocks(int(n_kmers_total), int(util_block_size)))
+
+
+def select_blocks(block_max):
+    """Replay of the reference's sequential utility-block merge (scm.py:270-286) -> (best, selected)."""
+    bm = np.ascontiguousarray(block_max, dtype=np.float64)
+    sel = np.zeros(bm.shape[0], dtype=np.uint8)
+    best = ctypes.c_double(0.0)
+    check(load().kv_scm_select_blocks(ptr(bm), bm.shape[0], ctypes.byref(best), ptr(sel)))
+    return best.value, sel
+
+
+def inplace_popcount(arr, row_mask, device=0):
+    lib = load()
+    if arr.dtype == np.uint64:
+        fn, t = lib.kv_inplace_popcount_64, np.uint64
+    elif arr.dtype == np.uint32:
+        fn, t = lib.kv_inplace_popcount_32, np.uint32
+    else:
+        raise ValueError("Buffer dtype mismatch: expected uint32 or uint64")
+    if arr.ndim != 2:
+        raise ValueError("Buffer has wrong number of dimensions (expected 2, got %d)" % arr.ndim)
+    mask = np.ascontiguousarray(row_mask, dtype=t)
+    if mask.ndim != 1 or mask.shape[0] < arr.shape[0]:
+        raise ValueError("row_mask must have one entry per row of arr")
+    if arr.flags.c_contiguous:
+        check(fn(int(device), ptr(arr), arr.shape[0], arr.shape[1], ptr(mask)))
+    else:  # typed memoryviews accept strided buffers; round-trip through a contiguous copy
+        tmp = np.ascontiguousarray(arr)
+        check(fn(int(device), ptr(tmp), tmp.shape[0], tmp.shape[1], ptr(mask)))
+        arr[...] = tmp

@@ -1,0 +1,1507 @@
+// libkoverb200 -- Kover's rule-scoring hot path as hand-written CUDA for B200 (sm_100a).
+//
+// What the kernels compute and which reference lines they restate (paths relative to
+// /root/reference/core/kover):
+//   k_scan2        rules.py:201-267 (sum_rows for two row masks in ONE pass over the packed matrix:
+//                  popcount(word & mask), popcount.pyx:76-95) fused with the SCM utility and the
+//                  per-utility-block maximum of scm.py:262-270
+//   k_scm_ties     scm.py:273 (isclose tie set against the block maximum)
+//   k_count_multi  rules.py:201-267 for up to 8 masks per pass (CART classes, batched sum_rows)
+//   k_gini         cart.py:85-161 (_gini_impurity / _gini_rule_score), min + exact ties cart.py:238
+//   k_gather_cols  rules.py:164 (dataset[:, cols])
+//   k_popc_inplace popcount.pyx:31-50, 76-95
+// Layout in HBM: uint64 [W, ld] row-major, ld = n_cols rounded up to 512 words so that every
+// 512-column tile row is a 4 KB aligned segment; padding columns are zero and masked out of every
+// reduction.  The path is a bitwise reduction bound by HBM bandwidth: no tensor cores.
+//
+// No CPU fallback lives here: every entry point either runs on the GPU or returns an error.
+#include "kover_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <numeric>
+#include <string>
+#include <vector>
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess) {                                                                  \
+            char b__[512];                                                                         \
+            snprintf(b__, sizeof b__, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__),     \
+                     __FILE__, __LINE__);                                                          \
+            return fail(e__ == cudaErrorMemoryAllocation ? KV_E_NOMEM : KV_E_CUDA, b__);           \
+        }                                                                                          \
+    } while (0)
+
+#define KV_TRY(call)                                                                               \
+    do {                                                                                           \
+        int r__ = (call);                                                                          \
+        if (r__ != KV_OK) return r__;                                                              \
+    } while (0)
+
+extern "C" const char *kv_last_error(void) { return g_err.c_str(); }
+extern "C" int kv_abi_version(void) { return 1; }
+
+extern "C" int kv_device_count(int *n) {
+    if (!n) return fail(KV_E_INVALID, "kv_device_count: null pointer");
+    CU(cudaGetDeviceCount(n));
+    return KV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// constants
+// ------------------------------------------------------------------------------------------------
+static constexpr int TILE_COLS = 512;    // columns per tile: 256 threads x one 128-bit load
+static constexpr int SCAN_THREADS = 256;
+static constexpr int MAX_MULTI = 8;      // masks per pass of k_count_multi
+static constexpr int MAX_CLASSES = 64;
+
+// ------------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------------
+// Streaming 128-bit load: read-only path, no L1 allocation (every matrix word is used exactly once
+// per scan).
+__device__ __forceinline__ ulonglong2 ldg_stream(const uint64_t *p) {
+    ulonglong2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p));
+    return v;
+}
+
+// Order-preserving map double -> uint64 so that atomicMax / atomicMin on integers order doubles.
+// The smallest image of any double (that of -inf) is 0x000F..F > 0, so a zeroed slot decodes as
+// "nothing seen" = -inf (max) and an all-ones slot as +inf (min).
+__device__ __host__ __forceinline__ unsigned long long enc_f64(double d) {
+    unsigned long long b;
+#ifdef __CUDA_ARCH__
+    b = (unsigned long long)__double_as_longlong(d);
+#else
+    memcpy(&b, &d, 8);
+#endif
+    return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+static inline double dec_f64_max(unsigned long long v) {
+    if (v == 0ull) return -std::numeric_limits<double>::infinity();
+    unsigned long long b = (v & 0x8000000000000000ull) ? (v & 0x7FFFFFFFFFFFFFFFull) : ~v;
+    double d;
+    memcpy(&d, &b, 8);
+    return d;
+}
+static inline double dec_f64_min(unsigned long long v) {
+    if (v == ~0ull) return std::numeric_limits<double>::infinity();
+    return dec_f64_max(v);
+}
+
+// scm.py:263-264 -- float64(neg_cover) - float64(p) * float64(pos_err): one rounded multiply, one
+// rounded subtract.  A fused multiply-add changes results, hence the _rn
+// intrinsics, which the compiler never contracts.
+__device__ __forceinline__ double scm_utility(uint32_t neg_cover, uint32_t pos_err, double p) {
+    return __dsub_rn((double)neg_cover, __dmul_rn(p, (double)pos_err));
+}
+
+// floor(r / d) for 0 <= r < 2^52 using a double reciprocal and one correction step.
+__device__ __forceinline__ long long fast_div(long long r, long long d, double inv) {
+    long long q = (long long)((double)r * inv);
+    long long rem = r - q * d;
+    if (rem < 0) --q;
+    else if (rem >= d) ++q;
+    return q;
+}
+
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_scan2: the hot kernel
+// ------------------------------------------------------------------------------------------------
+struct Scan2Params {
+    const uint64_t *mat;
+    long long ld, n_cols, col0, k_total, n_tiles;
+    // active packed rows (mask word != 0, rules.py:244), grouped: nA rows where only mask 0 is
+    // non-zero, then nB rows where only mask 1 is, then nC rows where both are.
+    const uint32_t *rec_row;
+    const uint64_t *rec_m0, *rec_m1;
+    int nA, nB, nC;
+    uint32_t *cnt0, *cnt1;            // [ld] each; cnt1 may be null (single-mask scan)
+    // SCM epilogue
+    double p;
+    uint32_t n_pos, n_neg;
+    long long ubs;
+    const uint32_t *black_pres, *black_abs;   // bitmaps over local columns or null
+    unsigned long long *blockmax;             // enc_f64 per utility block
+};
+
+enum { EPI_COUNTS = 0, EPI_SCM = 1 };
+
+template <int MODE>   // 0: mask 0 only, 1: mask 1 only, 2: both
+__device__ __forceinline__ void accum_rows(const uint64_t *__restrict__ base, long long ld,
+                                           const uint32_t *rows, const uint64_t *m0, const uint64_t *m1, int n,
+                                           uint32_t &c0x, uint32_t &c0y, uint32_t &c1x, uint32_t &c1y) {
+    constexpr int UN = 8;
+    int i = 0;
+#pragma unroll 1
+    for (; i + UN <= n; i += UN) {
+        ulonglong2 v[UN];
+#pragma unroll
+        for (int j = 0; j < UN; ++j) v[j] = ldg_stream(base + (long long)rows[i + j] * ld);
+#pragma unroll
+        for (int j = 0; j < UN; ++j) {
+            if (MODE != 1) {
+                const uint64_t m = m0[i + j];
+                c0x += __popcll(v[j].x & m);
+                c0y += __popcll(v[j].y & m);
+            }
+            if (MODE != 0) {
+                const uint64_t m = m1[i + j];
+                c1x += __popcll(v[j].x & m);
+                c1y += __popcll(v[j].y & m);
+            }
+        }
+    }
+#pragma unroll 1
+    for (; i < n; ++i) {
+        const ulonglong2 v = ldg_stream(base + (long long)rows[i] * ld);
+        if (MODE != 1) {
+            const uint64_t m = m0[i];
+            c0x += __popcll(v.x & m);
+            c0y += __popcll(v.y & m);
+        }
+        if (MODE != 0) {
+            const uint64_t m = m1[i];
+            c1x += __popcll(v.x & m);
+            c1y += __popcll(v.y & m);
+        }
+    }
+}
+
+// Running maximum of one half (presence / absence) of the rule space, kept per thread while the
+// CTA's tiles stay inside one utility block; reduced and pushed with ONE atomic when they leave it.
+struct RunMax {
+    long long lo, hi, bid;
+    double mx;
+};
+
+__device__ __forceinline__ void runmax_flush(RunMax &r, unsigned long long *blockmax, double *s_red) {
+    // CTA-uniform call
+    if (r.bid >= 0) {
+        double v = warp_max(r.mx);
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        __syncthreads();
+        if (lane == 0) s_red[wid] = v;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double m = s_red[0];
+            for (int w = 1; w < SCAN_THREADS / 32; ++w) m = fmax(m, s_red[w]);
+            atomicMax(blockmax + r.bid, enc_f64(m));
+        }
+    }
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(SCAN_THREADS, 4) k_scan2(const Scan2Params P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ double s_red[SCAN_THREADS / 32];
+    const int n_act = P.nA + P.nB + P.nC;
+    uint64_t *s_m0 = reinterpret_cast<uint64_t *>(smem_raw);
+    uint64_t *s_m1 = s_m0 + n_act;
+    uint32_t *s_row = reinterpret_cast<uint32_t *>(s_m1 + n_act);
+    for (int i = threadIdx.x; i < n_act; i += SCAN_THREADS) {
+        s_m0[i] = P.rec_m0[i];
+        s_m1[i] = P.rec_m1[i];
+        s_row[i] = P.rec_row[i];
+    }
+    __syncthreads();
+
+    // contiguous tile range per CTA: a CTA's rules stay inside one or two utility blocks
+    const long long t0 = (P.n_tiles * (long long)blockIdx.x) / gridDim.x;
+    const long long t1 = (P.n_tiles * (long long)(blockIdx.x + 1)) / gridDim.x;
+
+    RunMax run[2];
+    run[0].lo = run[1].lo = 1; run[0].hi = run[1].hi = 0; run[0].bid = run[1].bid = -1;
+    run[0].mx = run[1].mx = -INFINITY;
+    const double neg_inf = -INFINITY;
+
+    for (long long tile = t0; tile < t1; ++tile) {
+        const long long col = tile * TILE_COLS + 2 * (long long)threadIdx.x;
+        const uint64_t *base = P.mat + col;
+        uint32_t c0x = 0, c0y = 0, c1x = 0, c1y = 0;
+        accum_rows<0>(base, P.ld, s_row, s_m0, s_m1, P.nA, c0x, c0y, c1x, c1y);
+        accum_rows<1>(base, P.ld, s_row + P.nA, s_m0 + P.nA, s_m1 + P.nA, P.nB, c0x, c0y, c1x, c1y);
+        accum_rows<2>(base, P.ld, s_row + P.nA + P.nB, s_m0 + P.nA + P.nB, s_m1 + P.nA + P.nB, P.nC,
+                      c0x, c0y, c1x, c1y);
+        *reinterpret_cast<uint2 *>(P.cnt0 + col) = make_uint2(c0x, c0y);
+        if (P.cnt1) *reinterpret_cast<uint2 *>(P.cnt1 + col) = make_uint2(c1x, c1y);
+
+        if (EPI == EPI_SCM) {
+            const bool vx = col < P.n_cols, vy = col + 1 < P.n_cols;
+            uint32_t bp = 0, ba = 0;
+            if (P.black_pres) {
+                bp = P.black_pres[col >> 5] >> (col & 31);
+                ba = P.black_abs[col >> 5] >> (col & 31);
+            }
+            // presence rule k: covers the negatives WITHOUT the k-mer, errs on the positives
+            // without it; absence rule K+k: the complements (rules.py:265, scm.py:245-251)
+            double u[2][2];
+            u[0][0] = (bp & 1u) ? neg_inf : scm_utility(P.n_neg - c1x, P.n_pos - c0x, P.p);
+            u[0][1] = (bp & 2u) ? neg_inf : scm_utility(P.n_neg - c1y, P.n_pos - c0y, P.p);
+            u[1][0] = (ba & 1u) ? neg_inf : scm_utility(c1x, c0x, P.p);
+            u[1][1] = (ba & 2u) ? neg_inf : scm_utility(c1y, c0y, P.p);
+            const long long tile_c0 = tile * TILE_COLS;
+            const long long tile_n = min((long long)TILE_COLS, P.n_cols - tile_c0);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                RunMax &r = run[h];
+                const long long r0 = (long long)h * P.k_total + P.col0 + tile_c0;
+                const long long r1 = r0 + tile_n - 1;
+                bool fast = (r0 >= r.lo) && (r1 < r.hi);
+                if (!fast) {                                   // CTA-uniform: depends on the tile only
+                    runmax_flush(r, P.blockmax, s_red);
+                    const long long b0 = r0 / P.ubs, b1 = r1 / P.ubs;
+                    if (b0 == b1) {
+                        r.bid = b0; r.lo = b0 * P.ubs; r.hi = r.lo + P.ubs; r.mx = neg_inf;
+                        fast = true;
+                    } else {
+                        r.bid = -1; r.lo = 1; r.hi = 0; r.mx = neg_inf;
+                    }
+                }
+                if (fast) {
+                    if (vx) r.mx = fmax(r.mx, u[h][0]);
+                    if (vy) r.mx = fmax(r.mx, u[h][1]);
+                } else {                                       // tile straddles a block boundary
+                    const long long rx = r0 + 2 * (long long)threadIdx.x;
+                    if (vx) atomicMax(P.blockmax + rx / P.ubs, enc_f64(u[h][0]));
+                    if (vy) atomicMax(P.blockmax + (rx + 1) / P.ubs, enc_f64(u[h][1]));
+                }
+            }
+        }
+    }
+    if (EPI == EPI_SCM) {
+        runmax_flush(run[0], P.blockmax, s_red);
+        runmax_flush(run[1], P.blockmax, s_red);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_scm_ties: rules of the selected utility blocks whose utility is isclose to the block maximum
+// ------------------------------------------------------------------------------------------------
+struct TieParams {
+    const uint32_t *cnt0, *cnt1;
+    long long n_cols, col0, k_total, ubs;
+    double inv_ubs, p;
+    uint32_t n_pos, n_neg;
+    const uint32_t *black_pres, *black_abs;
+    const double *bm, *tol;        // per utility block: maximum and atol + rtol * |maximum|
+    const uint8_t *sel;            // 1 = collect, 0 = skip
+    long long *out_idx;
+    uint32_t *out_pe, *out_nc;
+    unsigned long long *counter;
+    long long cap;
+};
+
+__device__ __forceinline__ void tie_emit(const TieParams &P, long long rule, double u, uint32_t pe, uint32_t nc) {
+    const long long b = fast_div(rule, P.ubs, P.inv_ubs);
+    if (!P.sel[b]) return;
+    const double m = P.bm[b];
+    // numpy isclose(u, m): |u - m| <= atol + rtol*|m| and isfinite(m), or u == m
+    const bool close = (u == m) || (isfinite(m) && fabs(__dsub_rn(u, m)) <= P.tol[b]);
+    if (close) {
+        const unsigned long long slot = atomicAdd(P.counter, 1ull);
+        if ((long long)slot < P.cap) {
+            P.out_idx[slot] = rule;
+            P.out_pe[slot] = pe;
+            P.out_nc[slot] = nc;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_scm_ties(const TieParams P) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long col = (long long)blockIdx.x * blockDim.x + threadIdx.x; col < P.n_cols; col += stride) {
+        const uint32_t c0 = P.cnt0[col], c1 = P.cnt1[col];
+        bool bp = false, ba = false;
+        if (P.black_pres) {
+            bp = (P.black_pres[col >> 5] >> (col & 31)) & 1u;
+            ba = (P.black_abs[col >> 5] >> (col & 31)) & 1u;
+        }
+        const uint32_t pe_p = P.n_pos - c0, nc_p = P.n_neg - c1;
+        const double up = bp ? -INFINITY : scm_utility(nc_p, pe_p, P.p);
+        const double ua = ba ? -INFINITY : scm_utility(c1, c0, P.p);
+        tie_emit(P, P.col0 + col, up, pe_p, nc_p);
+        tie_emit(P, P.k_total + P.col0 + col, ua, c0, c1);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_count_multi: NM masks per pass (CART classes / batched sum_rows)
+// ------------------------------------------------------------------------------------------------
+struct MultiParams {
+    const uint64_t *mat;
+    long long ld, n_tiles;
+    const uint32_t *rec_row;      // active rows (any mask non-zero)
+    const uint64_t *rec_m;        // [n_act][NM]
+    int n_act;
+    uint32_t *cnt[MAX_MULTI];     // [ld] each
+};
+
+template <int NM>
+__global__ void __launch_bounds__(SCAN_THREADS, 4) k_count_multi(const MultiParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t *s_m = reinterpret_cast<uint64_t *>(smem_raw);
+    uint32_t *s_row = reinterpret_cast<uint32_t *>(s_m + (size_t)P.n_act * NM);
+    for (int i = threadIdx.x; i < P.n_act * NM; i += SCAN_THREADS) s_m[i] = P.rec_m[i];
+    for (int i = threadIdx.x; i < P.n_act; i += SCAN_THREADS) s_row[i] = P.rec_row[i];
+    __syncthreads();
+    const long long t0 = (P.n_tiles * (long long)blockIdx.x) / gridDim.x;
+    const long long t1 = (P.n_tiles * (long long)(blockIdx.x + 1)) / gridDim.x;
+    constexpr int UN = 4;
+    for (long long tile = t0; tile < t1; ++tile) {
+        const long long col = tile * TILE_COLS + 2 * (long long)threadIdx.x;
+        const uint64_t *base = P.mat + col;
+        uint32_t cx[NM], cy[NM];
+#pragma unroll
+        for (int m = 0; m < NM; ++m) cx[m] = cy[m] = 0;
+        int i = 0;
+#pragma unroll 1
+        for (; i + UN <= P.n_act; i += UN) {
+            ulonglong2 v[UN];
+#pragma unroll
+            for (int j = 0; j < UN; ++j) v[j] = ldg_stream(base + (long long)s_row[i + j] * P.ld);
+#pragma unroll
+            for (int j = 0; j < UN; ++j) {
+#pragma unroll
+                for (int m = 0; m < NM; ++m) {
+                    const uint64_t mk = s_m[(i + j) * NM + m];
+                    if (mk) {                                   // warp-uniform
+                        cx[m] += __popcll(v[j].x & mk);
+                        cy[m] += __popcll(v[j].y & mk);
+                    }
+                }
+            }
+        }
+#pragma unroll 1
+        for (; i < P.n_act; ++i) {
+            const ulonglong2 v = ldg_stream(base + (long long)s_row[i] * P.ld);
+#pragma unroll
+            for (int m = 0; m < NM; ++m) {
+                const uint64_t mk = s_m[i * NM + m];
+                cx[m] += __popcll(v.x & mk);
+                cy[m] += __popcll(v.y & mk);
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < NM; ++m) *reinterpret_cast<uint2 *>(P.cnt[m] + col) = make_uint2(cx[m], cy[m]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_gini: split score of every presence rule from the per-class counts (cart.py:85-161)
+// ------------------------------------------------------------------------------------------------
+struct GiniParams {
+    const uint32_t *cnt[MAX_CLASSES];
+    double prior[MAX_CLASSES], n_total[MAX_CLASSES], n_node[MAX_CLASSES];
+    int n_classes;
+    long long n_cols, col0;
+    const uint32_t *black_pres;
+    unsigned long long *min_enc;    // MODE_MIN
+    double min_score;               // MODE_TIES
+    long long *out_idx;
+    unsigned long long *counter;
+    long long cap;
+    double *scores;                 // MODE_SCORES
+};
+enum { GINI_MIN = 0, GINI_TIES = 1, GINI_SCORES = 2 };
+
+// _gini_impurity(n, multiply_by_node_proba=True), cart.py:99-110, in numpy's operation order:
+//   p_j_t = ((1.0 * prior) * n) / N ; p_t = 0 + p_0 + p_1 ... ; q_j = p_j_t / p_t ;
+//   div = 0 + sum_{i != j} q_i * q_j (i outer, j inner) ; result = div * p_t
+template <int NC>
+__device__ __forceinline__ double gini_child(const double *n, const GiniParams &P, int nc_rt) {
+    const int nc = NC > 0 ? NC : nc_rt;
+    double q[NC > 0 ? NC : MAX_CLASSES];
+    double pt = 0.0;
+#pragma unroll
+    for (int c = 0; c < nc; ++c) {
+        q[c] = __ddiv_rn(__dmul_rn(P.prior[c], n[c]), P.n_total[c]);
+        pt = (c == 0) ? q[c] : __dadd_rn(pt, q[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < nc; ++c) q[c] = __ddiv_rn(q[c], pt);
+    double div = 0.0;
+    bool first = true;
+#pragma unroll
+    for (int i = 0; i < nc; ++i) {
+#pragma unroll
+        for (int j = 0; j < nc; ++j) {
+            if (i == j) continue;
+            const double t = __dmul_rn(q[i], q[j]);
+            div = first ? t : __dadd_rn(div, t);
+            first = false;
+        }
+    }
+    return __dmul_rn(div, pt);
+}
+
+template <int NC>
+__device__ __forceinline__ double gini_score(long long col, const GiniParams &P) {
+    const int nc = NC > 0 ? NC : P.n_classes;
+    double l[NC > 0 ? NC : MAX_CLASSES], r[NC > 0 ? NC : MAX_CLASSES];
+    double suml = 0.0, sumr = 0.0;
+#pragma unroll
+    for (int c = 0; c < nc; ++c) {
+        l[c] = (double)P.cnt[c][col];                  // examples WITH the k-mer (cart.py:129-131)
+        r[c] = P.n_node[c] - l[c];                     // exact (integers)
+        suml += l[c];
+        sumr += r[c];
+    }
+    if (P.black_pres && ((P.black_pres[col >> 5] >> (col & 31)) & 1u)) return INFINITY;   // cart.py:231
+    if (suml == 0.0 || sumr == 0.0) return INFINITY;                                      // cart.py:158-159
+    return __dadd_rn(gini_child<NC>(l, P, nc), gini_child<NC>(r, P, nc));
+}
+
+template <int NC, int MODE>
+__global__ void __launch_bounds__(256) k_gini(const GiniParams P) {
+    __shared__ double s_red[8];
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    double mn = INFINITY;
+    for (long long col = (long long)blockIdx.x * blockDim.x + threadIdx.x; col < P.n_cols; col += stride) {
+        const double s = gini_score<NC>(col, P);
+        if (MODE == GINI_MIN) {
+            mn = fmin(mn, s);      // NaN-ignoring; the reference's scores hold no NaN for valid priors
+        } else if (MODE == GINI_TIES) {
+            if (s == P.min_score) {
+                const unsigned long long slot = atomicAdd(P.counter, 1ull);
+                if ((long long)slot < P.cap) P.out_idx[slot] = P.col0 + col;
+            }
+        } else {
+            P.scores[col] = s;
+        }
+    }
+    if (MODE == GINI_MIN) {
+        mn = warp_min(mn);
+        if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = mn;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < 8; ++w) mn = fmin(mn, s_red[w]);
+            atomicMin(P.min_enc, enc_f64(mn));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// small kernels
+// ------------------------------------------------------------------------------------------------
+__global__ void k_gather_cols(const uint64_t *mat, long long ld, long long n_words, const long long *cols,
+                              long long n, uint64_t *out) {
+    const long long j = blockIdx.x;
+    for (long long w = threadIdx.x; w < n_words; w += blockDim.x) out[j * n_words + w] = mat[w * ld + cols[j]];
+}
+
+// 32-bit packed rows -> halves of the 64-bit image (rules.py:123-125): row 2w is the high half
+__global__ void k_merge32(uint64_t *mat, long long ld, long long lcol0, long long row0_32, long long n_rows,
+                          long long n_cols, const uint32_t *src, long long src_ld) {
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_cols) return;
+    for (long long r = 0; r < n_rows; ++r) {
+        const long long r32 = row0_32 + r;
+        const uint64_t v = (uint64_t)src[r * src_ld + c] << ((r32 & 1) ? 0 : 32);
+        uint64_t *dst = mat + (r32 >> 1) * ld + lcol0 + c;
+        const uint64_t keep = (r32 & 1) ? 0xFFFFFFFF00000000ull : 0x00000000FFFFFFFFull;
+        *dst = (*dst & keep) | v;
+    }
+}
+
+template <typename T>
+__global__ void k_popc_inplace(T *arr, long long m, long long n, const T *mask) {
+    const long long total = m * n;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const T v = arr[i];
+        if (v != 0) {                                            // popcount.pyx:47-48 / 93-94
+            const T x = v & mask[i / n];
+            arr[i] = sizeof(T) == 8 ? (T)__popcll((unsigned long long)x) : (T)__popc((unsigned int)x);
+        }
+    }
+}
+
+template <typename T>
+__global__ void k_narrow(const uint32_t *src, T *dst, long long n) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = (T)src[i];
+}
+
+// Synthetic matrix: see kover_b200/synthetic.py (numpy twin of exactly this function).
+__device__ __host__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    uint64_t z = x;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__device__ __forceinline__ uint64_t synth_word(uint64_t seed, uint64_t gcol, uint64_t w) {
+    const unsigned level = (unsigned)(splitmix64(seed ^ (gcol * 0xD6E8FEB86659FD93ull)) & 7ull);
+    const uint64_t base = seed + ((gcol << 13) + w) * 4ull;
+    const uint64_t r1 = splitmix64(base), r2 = splitmix64(base + 1), r3 = splitmix64(base + 2);
+    switch (level) {
+        case 0: return r1 & r2 & r3;                       // 1/8
+        case 1: return r1 & r2;                            // 1/4
+        case 2: return r1 & (r2 | r3);                     // 3/8
+        case 3: return r1;                                 // 1/2
+        case 4: return r1 | (r2 & r3);                     // 5/8
+        case 5: return r1 | r2;                            // 3/4
+        case 6: return r1 | r2 | r3;                       // 7/8
+        default: return r1 & r2 & r3 & splitmix64(base + 3);   // 1/16
+    }
+}
+__global__ void k_generate(uint64_t *mat, long long ld, long long n_words, long long n_cols, long long col0,
+                           uint64_t seed, uint64_t last_word_mask) {
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long w = blockIdx.y;
+    if (c >= n_cols) return;
+    uint64_t v = synth_word(seed, (uint64_t)(col0 + c), (uint64_t)w);
+    if (w == n_words - 1) v &= last_word_mask;
+    mat[w * ld + c] = v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// shard
+// ------------------------------------------------------------------------------------------------
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+};
+
+struct kv_shard {
+    int device = 0, sm_count = 0;
+    long long n_examples = 0, W = 0, k_total = 0, col0 = 0, n_cols = 0, ld = 0, n_tiles = 0;
+    uint64_t *d_mat = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+    int scan_ctas_per_sm = 4;
+
+    std::vector<uint32_t *> d_cnt;            // count arrays, [ld] each
+    DevBuf d_rec, d_misc, d_ties, d_stage;
+    void *h_pin = nullptr;                    // pinned staging (records, block tables, small results)
+    size_t h_pin_bytes = 0;
+    void *h_up[2] = {nullptr, nullptr};       // pinned upload ring
+    cudaEvent_t ev_up[2] = {nullptr, nullptr};
+    size_t h_up_bytes = 0;
+    int up_slot = 0;
+
+    uint32_t *d_black_pres = nullptr, *d_black_abs = nullptr;
+    bool have_black = false;
+
+    // state left by the last scan for phase 2
+    bool scm_valid = false;
+    long long scm_n_pos = 0, scm_n_neg = 0, scm_ubs = 0;
+    double scm_p = 0.0;
+    bool gini_valid = false;
+    GiniParams gini;
+
+    double last_kernel_ms = 0.0;
+    long long last_launches = 0, total_launches = 0;
+};
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+static int ensure(DevBuf &b, size_t bytes) {
+    if (b.bytes >= bytes) return KV_OK;
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.bytes = 0;
+    size_t want = std::max(bytes, (size_t)4096);
+    CU(cudaMalloc(&b.p, want));
+    b.bytes = want;
+    return KV_OK;
+}
+
+static int ensure_pinned(kv_shard *s, size_t bytes) {
+    if (s->h_pin_bytes >= bytes) return KV_OK;
+    if (s->h_pin) cudaFreeHost(s->h_pin);
+    s->h_pin = nullptr;
+    s->h_pin_bytes = 0;
+    size_t want = std::max(bytes, (size_t)1 << 16);
+    CU(cudaMallocHost(&s->h_pin, want));
+    s->h_pin_bytes = want;
+    return KV_OK;
+}
+
+static int ensure_counts(kv_shard *s, int n) {
+    while ((int)s->d_cnt.size() < n) {
+        uint32_t *p = nullptr;
+        CU(cudaMalloc(&p, (size_t)s->ld * sizeof(uint32_t)));
+        s->d_cnt.push_back(p);
+    }
+    return KV_OK;
+}
+
+static inline void count_launch(kv_shard *s, int n = 1) {
+    s->last_launches += n;
+    s->total_launches += n;
+}
+
+static int scan_grid(kv_shard *s) {
+    long long g = (long long)s->sm_count * s->scan_ctas_per_sm;
+    return (int)std::max(1ll, std::min(g, s->n_tiles));
+}
+
+extern "C" int kv_create(int device, int64_t n_examples, int64_t n_kmers_total, int64_t col0, int64_t n_cols,
+                         kv_shard **out) {
+    if (!out) return fail(KV_E_INVALID, "kv_create: null out pointer");
+    *out = nullptr;
+    if (n_examples <= 0 || n_kmers_total <= 0 || n_cols <= 0 || col0 < 0 || col0 + n_cols > n_kmers_total)
+        return fail(KV_E_INVALID, "kv_create: bad shape (n_examples, n_kmers, col0, n_cols)");
+    if (2 * n_kmers_total >= (1ll << 52)) return fail(KV_E_INVALID, "kv_create: too many k-mers");
+    if (n_examples > 0xFFFFFFFFll) return fail(KV_E_INVALID, "kv_create: too many examples");
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0)
+        return fail(KV_E_CUDA, std::string("kv_create: no usable CUDA device (no CPU fallback exists): ") +
+                                   cudaGetErrorString(e));
+    if (device < 0 || device >= n_dev) return fail(KV_E_INVALID, "kv_create: device ordinal out of range");
+    DeviceGuard g(device);
+    if (!g.ok) return fail(KV_E_CUDA, "kv_create: cudaSetDevice failed");
+    kv_shard *s = new kv_shard();
+    s->device = device;
+    s->n_examples = n_examples;
+    s->W = (n_examples + 63) / 64;
+    s->k_total = n_kmers_total;
+    s->col0 = col0;
+    s->n_cols = n_cols;
+    s->n_tiles = (n_cols + TILE_COLS - 1) / TILE_COLS;
+    s->ld = s->n_tiles * TILE_COLS;
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    s->sm_count = prop.multiProcessorCount;
+    const size_t bytes = (size_t)s->W * (size_t)s->ld * 8;
+    if (cudaMalloc(&s->d_mat, bytes) != cudaSuccess) {
+        delete s;
+        char b[256];
+        snprintf(b, sizeof b, "kv_create: cannot allocate %.2f GB of HBM for the packed matrix", bytes / 1e9);
+        return fail(KV_E_NOMEM, b);
+    }
+    CU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&s->ev0));
+    CU(cudaEventCreate(&s->ev1));
+    CU(cudaEventCreate(&s->ev_t0));
+    CU(cudaEventCreate(&s->ev_t1));
+    CU(cudaMemsetAsync(s->d_mat, 0, bytes, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    // the scan kernels stage up to ~20 B per active packed row in shared memory
+    CU(cudaFuncSetAttribute(k_scan2<EPI_COUNTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CU(cudaFuncSetAttribute(k_scan2<EPI_SCM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    *out = s;
+    return KV_OK;
+}
+
+extern "C" int kv_destroy(kv_shard *s) {
+    if (!s) return KV_OK;
+    DeviceGuard g(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    cudaFree(s->d_mat);
+    for (auto p : s->d_cnt) cudaFree(p);
+    for (DevBuf *b : {&s->d_rec, &s->d_misc, &s->d_ties, &s->d_stage})
+        if (b->p) cudaFree(b->p);
+    if (s->d_black_pres) cudaFree(s->d_black_pres);
+    if (s->d_black_abs) cudaFree(s->d_black_abs);
+    if (s->h_pin) cudaFreeHost(s->h_pin);
+    for (int i = 0; i < 2; ++i) {
+        if (s->h_up[i]) cudaFreeHost(s->h_up[i]);
+        if (s->ev_up[i]) cudaEventDestroy(s->ev_up[i]);
+    }
+    if (s->ev0) cudaEventDestroy(s->ev0);
+    if (s->ev1) cudaEventDestroy(s->ev1);
+    if (s->ev_t0) cudaEventDestroy(s->ev_t0);
+    if (s->ev_t1) cudaEventDestroy(s->ev_t1);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+    return KV_OK;
+}
+
+extern "C" int kv_get_info(kv_shard *s, kv_shard_info *o) {
+    if (!s || !o) return fail(KV_E_INVALID, "kv_get_info: null pointer");
+    o->device = s->device;
+    o->sm_count = s->sm_count;
+    o->n_examples = s->n_examples;
+    o->n_words = s->W;
+    o->n_kmers_total = s->k_total;
+    o->col0 = s->col0;
+    o->n_cols = s->n_cols;
+    o->ld = s->ld;
+    o->matrix_bytes = (int64_t)((size_t)s->W * (size_t)s->ld * 8);
+    o->last_kernel_ms = s->last_kernel_ms;
+    o->last_launches = s->last_launches;
+    o->total_launches = s->total_launches;
+    return KV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// upload
+// ------------------------------------------------------------------------------------------------
+static int ensure_upload_ring(kv_shard *s) {
+    if (s->h_up[0]) return KV_OK;
+    s->h_up_bytes = (size_t)32 << 20;
+    for (int i = 0; i < 2; ++i) {
+        CU(cudaMallocHost(&s->h_up[i], s->h_up_bytes));
+        CU(cudaEventCreateWithFlags(&s->ev_up[i], cudaEventDisableTiming));
+    }
+    return KV_OK;
+}
+
+extern "C" int kv_upload_block(kv_shard *s, int pack_bits, int64_t row0, int64_t n_rows, int64_t gcol0,
+                               int64_t n_cols, const void *host, int64_t ld_elems) {
+    if (!s || !host) return fail(KV_E_INVALID, "kv_upload_block: null pointer");
+    if (pack_bits != 64 && pack_bits != 32)
+        return fail(KV_E_INVALID, "Unsupported data type for packed attribute classifications array. The supported "
+                                  "data types are np.uint32 and np.uint64.");
+    const long long max_rows = pack_bits == 64 ? s->W : (s->n_examples + 31) / 32;
+    if (row0 < 0 || n_rows < 0 || row0 + n_rows > max_rows || gcol0 < 0 || n_cols < 0 ||
+        gcol0 + n_cols > s->k_total || ld_elems < n_cols)
+        return fail(KV_E_INVALID, "kv_upload_block: block outside the packed matrix");
+    // intersect with the shard's columns
+    const long long a = std::max<long long>(gcol0, s->col0), b = std::min<long long>(gcol0 + n_cols, s->col0 + s->n_cols);
+    if (a >= b || n_rows == 0) return KV_OK;
+    const long long nc = b - a, src_off = a - gcol0, lcol0 = a - s->col0;
+    DeviceGuard g(s->device);
+    KV_TRY(ensure_upload_ring(s));
+    s->last_launches = 0;
+    const size_t esz = pack_bits / 8;
+    // stream the block through the pinned ring in row groups
+    const long long rows_per_slot = std::max<long long>(1, (long long)(s->h_up_bytes / ((size_t)nc * esz)));
+    if ((size_t)nc * esz > s->h_up_bytes) {
+        // a single row wider than a slot: split by columns recursively
+        const long long half = nc / 2;
+        KV_TRY(kv_upload_block(s, pack_bits, row0, n_rows, a, half, (const char *)host + src_off * esz, ld_elems));
+        return kv_upload_block(s, pack_bits, row0, n_rows, a + half, nc - half,
+                               (const char *)host + (src_off + half) * esz, ld_elems);
+    }
+    for (long long r = 0; r < n_rows; r += rows_per_slot) {
+        const long long nr = std::min(rows_per_slot, n_rows - r);
+        const int slot = s->up_slot;
+        s->up_slot ^= 1;
+        CU(cudaEventSynchronize(s->ev_up[slot]));
+        char *pin = (char *)s->h_up[slot];
+        for (long long i = 0; i < nr; ++i)
+            memcpy(pin + (size_t)i * nc * esz, (const char *)host + ((size_t)(r + i) * ld_elems + src_off) * esz,
+                   (size_t)nc * esz);
+        if (pack_bits == 64) {
+            CU(cudaMemcpy2DAsync(s->d_mat + (row0 + r) * s->ld + lcol0, (size_t)s->ld * 8, pin, (size_t)nc * 8,
+                                 (size_t)nc * 8, (size_t)nr, cudaMemcpyHostToDevice, s->stream));
+        } else {
+            KV_TRY(ensure(s->d_stage, s->h_up_bytes));
+            CU(cudaMemcpyAsync(s->d_stage.p, pin, (size_t)nr * nc * 4, cudaMemcpyHostToDevice, s->stream));
+            k_merge32<<<(unsigned)((nc + 255) / 256), 256, 0, s->stream>>>(s->d_mat, s->ld, lcol0, row0 + r, nr, nc,
+                                                                            (const uint32_t *)s->d_stage.p, nc);
+            count_launch(s);
+        }
+        CU(cudaEventRecord(s->ev_up[slot], s->stream));
+    }
+    CU(cudaStreamSynchronize(s->stream));
+    CU(cudaGetLastError());
+    s->scm_valid = s->gini_valid = false;
+    return KV_OK;
+}
+
+extern "C" int kv_generate_synthetic(kv_shard *s, uint64_t seed) {
+    if (!s) return fail(KV_E_INVALID, "kv_generate_synthetic: null shard");
+    if (s->W > 8192) return fail(KV_E_INVALID, "kv_generate_synthetic: more than 8192 packed rows");
+    DeviceGuard g(s->device);
+    s->last_launches = 0;
+    const int rem = (int)(s->n_examples % 64);
+    const uint64_t last_mask = rem ? (~0ull << (64 - rem)) : ~0ull;
+    dim3 grid((unsigned)((s->n_cols + 255) / 256), (unsigned)s->W);
+    k_generate<<<grid, 256, 0, s->stream>>>(s->d_mat, s->ld, s->W, s->n_cols, s->col0, seed, last_mask);
+    count_launch(s);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(s->stream));
+    s->scm_valid = s->gini_valid = false;
+    return KV_OK;
+}
+
+extern "C" int kv_read_block(kv_shard *s, int64_t row0, int64_t n_rows, int64_t lcol0, int64_t n_cols,
+                             uint64_t *host, int64_t ld_elems) {
+    if (!s || !host) return fail(KV_E_INVALID, "kv_read_block: null pointer");
+    if (row0 < 0 || n_rows < 0 || row0 + n_rows > s->W || lcol0 < 0 || n_cols < 0 || lcol0 + n_cols > s->n_cols ||
+        ld_elems < n_cols)
+        return fail(KV_E_INVALID, "kv_read_block: block outside the shard");
+    if (n_rows == 0 || n_cols == 0) return KV_OK;
+    DeviceGuard g(s->device);
+    CU(cudaMemcpy2DAsync(host, (size_t)ld_elems * 8, s->d_mat + row0 * s->ld + lcol0, (size_t)s->ld * 8,
+                         (size_t)n_cols * 8, (size_t)n_rows, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return KV_OK;
+}
+
+extern "C" int kv_timer_start(kv_shard *s) {
+    if (!s) return fail(KV_E_INVALID, "kv_timer_start: null shard");
+    DeviceGuard g(s->device);
+    CU(cudaStreamSynchronize(s->stream));
+    CU(cudaEventRecord(s->ev_t0, s->stream));
+    return KV_OK;
+}
+extern "C" int kv_timer_stop(kv_shard *s, double *elapsed_ms) {
+    if (!s || !elapsed_ms) return fail(KV_E_INVALID, "kv_timer_stop: null pointer");
+    DeviceGuard g(s->device);
+    CU(cudaEventRecord(s->ev_t1, s->stream));
+    CU(cudaEventSynchronize(s->ev_t1));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, s->ev_t0, s->ev_t1));
+    *elapsed_ms = ms;
+    return KV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// a1: in-place popcount of a host block
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+static int popc_inplace_host(int device, T *arr, int64_t m, int64_t n, const T *mask) {
+    if (m < 0 || n < 0) return fail(KV_E_INVALID, "inplace_popcount: negative shape");
+    if (m == 0 || n == 0) return KV_OK;
+    if (!arr || !mask) return fail(KV_E_INVALID, "inplace_popcount: null pointer");
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || device < 0 || device >= n_dev)
+        return fail(KV_E_CUDA, "inplace_popcount: no usable CUDA device (no CPU fallback exists)");
+    DeviceGuard g(device);
+    T *d_arr = nullptr, *d_mask = nullptr;
+    const size_t bytes = (size_t)m * n * sizeof(T);
+    CU(cudaMalloc(&d_arr, bytes));
+    if (cudaMalloc(&d_mask, (size_t)m * sizeof(T)) != cudaSuccess) {
+        cudaFree(d_arr);
+        return fail(KV_E_NOMEM, "inplace_popcount: cudaMalloc failed");
+    }
+    int rc = KV_OK;
+    do {
+        if (cudaMemcpy(d_arr, arr, bytes, cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMemcpy(d_mask, mask, (size_t)m * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) {
+            rc = fail(KV_E_CUDA, "inplace_popcount: host to device copy failed");
+            break;
+        }
+        const long long total = (long long)m * n;
+        const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 148 * 16);
+        k_popc_inplace<T><<<grid, 256>>>(d_arr, m, n, d_mask);
+        if (cudaGetLastError() != cudaSuccess || cudaMemcpy(arr, d_arr, bytes, cudaMemcpyDeviceToHost) != cudaSuccess)
+            rc = fail(KV_E_CUDA, "inplace_popcount: kernel or device to host copy failed");
+    } while (0);
+    cudaFree(d_arr);
+    cudaFree(d_mask);
+    return rc;
+}
+extern "C" int kv_inplace_popcount_64(int device, uint64_t *arr, int64_t m, int64_t n, const uint64_t *row_mask) {
+    return popc_inplace_host<uint64_t>(device, arr, m, n, row_mask);
+}
+extern "C" int kv_inplace_popcount_32(int device, uint32_t *arr, int64_t m, int64_t n, const uint32_t *row_mask) {
+    return popc_inplace_host<uint32_t>(device, arr, m, n, row_mask);
+}
+
+// ------------------------------------------------------------------------------------------------
+// row records
+// ------------------------------------------------------------------------------------------------
+// Build the grouped active-row records for a mask pair in pinned memory and push them.
+// Layout in d_rec: m0[n_act] | m1[n_act] | row[n_act].
+static int push_records2(kv_shard *s, const uint64_t *m0, const uint64_t *m1, int &nA, int &nB, int &nC) {
+    const long long W = s->W;
+    KV_TRY(ensure_pinned(s, (size_t)W * 20 + 64));
+    nA = nB = nC = 0;
+    for (long long w = 0; w < W; ++w) {
+        const bool a = m0[w] != 0, b = m1 && m1[w] != 0;
+        if (a && b) ++nC;
+        else if (a) ++nA;
+        else if (b) ++nB;
+    }
+    const int n_act = nA + nB + nC;
+    uint64_t *pm0 = (uint64_t *)s->h_pin, *pm1 = pm0 + n_act;
+    uint32_t *prow = (uint32_t *)(pm1 + n_act);
+    int iA = 0, iB = nA, iC = nA + nB;
+    for (long long w = 0; w < W; ++w) {
+        const bool a = m0[w] != 0, b = m1 && m1[w] != 0;
+        int i;
+        if (a && b) i = iC++;
+        else if (a) i = iA++;
+        else if (b) i = iB++;
+        else continue;
+        pm0[i] = m0[w];
+        pm1[i] = m1 ? m1[w] : 0;
+        prow[i] = (uint32_t)w;
+    }
+    KV_TRY(ensure(s->d_rec, (size_t)n_act * 20 + 64));
+    if (n_act) CU(cudaMemcpyAsync(s->d_rec.p, s->h_pin, (size_t)n_act * 20, cudaMemcpyHostToDevice, s->stream));
+    return KV_OK;
+}
+
+static void fill_scan2(kv_shard *s, Scan2Params &P, int nA, int nB, int nC) {
+    const int n_act = nA + nB + nC;
+    memset(&P, 0, sizeof P);
+    P.mat = s->d_mat;
+    P.ld = s->ld;
+    P.n_cols = s->n_cols;
+    P.col0 = s->col0;
+    P.k_total = s->k_total;
+    P.n_tiles = s->n_tiles;
+    P.rec_m0 = (const uint64_t *)s->d_rec.p;
+    P.rec_m1 = P.rec_m0 + n_act;
+    P.rec_row = (const uint32_t *)(P.rec_m1 + n_act);
+    P.nA = nA;
+    P.nB = nB;
+    P.nC = nC;
+}
+
+static int check_smem(size_t bytes) {
+    if (bytes > 200 * 1024)
+        return fail(KV_E_INVALID, "too many active packed rows for one scan (shared-memory staging limit)");
+    return KV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// a3: sum_rows
+// ------------------------------------------------------------------------------------------------
+extern "C" int kv_sum_rows(kv_shard *s, const uint64_t *mask, void *out, int out_itemsize) {
+    if (!s || !mask || !out) return fail(KV_E_INVALID, "kv_sum_rows: null pointer");
+    if (out_itemsize != 1 && out_itemsize != 2 && out_itemsize != 4 && out_itemsize != 8)
+        return fail(KV_E_INVALID, "kv_sum_rows: out_itemsize must be 1, 2, 4 or 8");
+    DeviceGuard g(s->device);
+    s->last_launches = 0;
+    KV_TRY(ensure_counts(s, 1));
+    int nA, nB, nC;
+    KV_TRY(push_records2(s, mask, nullptr, nA, nB, nC));
+    Scan2Params P;
+    fill_scan2(s, P, nA, nB, nC);
+    P.cnt0 = s->d_cnt[0];
+    P.cnt1 = nullptr;
+    const size_t smem = (size_t)(nA + nB + nC) * 20 + 16;
+    KV_TRY(check_smem(smem));
+    CU(cudaEventRecord(s->ev0, s->stream));
+    k_scan2<EPI_COUNTS><<<scan_grid(s), SCAN_THREADS, smem, s->stream>>>(P);
+    count_launch(s);
+    CU(cudaEventRecord(s->ev1, s->stream));
+    s->scm_valid = s->gini_valid = false;
+    if (out_itemsize == 4) {
+        CU(cudaMemcpyAsync(out, s->d_cnt[0], (size_t)s->n_cols * 4, cudaMemcpyDeviceToHost, s->stream));
+    } else {
+        KV_TRY(ensure(s->d_stage, (size_t)s->n_cols * out_itemsize));
+        const unsigned grid = (unsigned)std::min<long long>((s->n_cols + 255) / 256, (long long)s->sm_count * 8);
+        if (out_itemsize == 1) k_narrow<uint8_t><<<grid, 256, 0, s->stream>>>(s->d_cnt[0], (uint8_t *)s->d_stage.p, s->n_cols);
+        else if (out_itemsize == 2) k_narrow<uint16_t><<<grid, 256, 0, s->stream>>>(s->d_cnt[0], (uint16_t *)s->d_stage.p, s->n_cols);
+        else k_narrow<uint64_t><<<grid, 256, 0, s->stream>>>(s->d_cnt[0], (uint64_t *)s->d_stage.p, s->n_cols);
+        count_launch(s);
+        CU(cudaMemcpyAsync(out, s->d_stage.p, (size_t)s->n_cols * out_itemsize, cudaMemcpyDeviceToHost, s->stream));
+    }
+    CU(cudaStreamSynchronize(s->stream));
+    CU(cudaGetLastError());
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+    s->last_kernel_ms = ms;
+    return KV_OK;
+}
+
+// counts of n_masks masks into d_cnt[first .. first+n_masks) (device resident)
+static int count_masks(kv_shard *s, int n_masks, const uint64_t *masks, int first) {
+    const long long W = s->W;
+    KV_TRY(ensure_counts(s, first + n_masks));
+    float total_ms = 0;
+    for (int m0 = 0; m0 < n_masks; m0 += MAX_MULTI) {
+        const int nm = std::min(MAX_MULTI, n_masks - m0);
+        KV_TRY(ensure_pinned(s, (size_t)W * (8 * nm + 4) + 64));
+        // an in-flight H2D may still read h_pin from the previous group
+        CU(cudaStreamSynchronize(s->stream));
+        int n_act = 0;
+        for (long long w = 0; w < W; ++w) {
+            bool any = false;
+            for (int m = 0; m < nm; ++m) any |= masks[(size_t)(m0 + m) * W + w] != 0;
+            n_act += any;
+        }
+        uint64_t *pm = (uint64_t *)s->h_pin;
+        uint32_t *prow = (uint32_t *)(pm + (size_t)n_act * nm);
+        int i = 0;
+        for (long long w = 0; w < W; ++w) {
+            bool any = false;
+            for (int m = 0; m < nm; ++m) any |= masks[(size_t)(m0 + m) * W + w] != 0;
+            if (!any) continue;
+            for (int m = 0; m < nm; ++m) pm[(size_t)i * nm + m] = masks[(size_t)(m0 + m) * W + w];
+            prow[i++] = (uint32_t)w;
+        }
+        const size_t rec_bytes = (size_t)n_act * (8 * nm + 4);
+        KV_TRY(ensure(s->d_rec, rec_bytes + 64));
+        if (n_act) CU(cudaMemcpyAsync(s->d_rec.p, s->h_pin, rec_bytes, cudaMemcpyHostToDevice, s->stream));
+        MultiParams P;
+        memset(&P, 0, sizeof P);
+        P.mat = s->d_mat;
+        P.ld = s->ld;
+        P.n_tiles = s->n_tiles;
+        P.rec_m = (const uint64_t *)s->d_rec.p;
+        P.rec_row = (const uint32_t *)(P.rec_m + (size_t)n_act * nm);
+        P.n_act = n_act;
+        for (int m = 0; m < nm; ++m) P.cnt[m] = s->d_cnt[first + m0 + m];
+        const size_t smem = rec_bytes + 16;
+        KV_TRY(check_smem(smem));
+        const int grid = scan_grid(s);
+        CU(cudaEventRecord(s->ev0, s->stream));
+#define LAUNCH_MULTI(NM)                                                                                      \
+    case NM:                                                                                                  \
+        CU(cudaFuncSetAttribute(k_count_multi<NM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
+        k_count_multi<NM><<<grid, SCAN_THREADS, smem, s->stream>>>(P);                                        \
+        break;
+        switch (nm) {
+            LAUNCH_MULTI(1) LAUNCH_MULTI(2) LAUNCH_MULTI(3) LAUNCH_MULTI(4)
+            LAUNCH_MULTI(5) LAUNCH_MULTI(6) LAUNCH_MULTI(7) LAUNCH_MULTI(8)
+        }
+#undef LAUNCH_MULTI
+        count_launch(s);
+        CU(cudaEventRecord(s->ev1, s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+        CU(cudaGetLastError());
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+        total_ms += ms;
+    }
+    s->last_kernel_ms = total_ms;
+    return KV_OK;
+}
+
+extern "C" int kv_sum_rows_multi(kv_shard *s, int n_masks, const uint64_t *masks, uint32_t *out) {
+    if (!s || !masks || !out) return fail(KV_E_INVALID, "kv_sum_rows_multi: null pointer");
+    if (n_masks <= 0 || n_masks > 4096) return fail(KV_E_INVALID, "kv_sum_rows_multi: n_masks out of range");
+    DeviceGuard g(s->device);
+    s->last_launches = 0;
+    s->scm_valid = s->gini_valid = false;
+    KV_TRY(count_masks(s, n_masks, masks, 0));
+    for (int m = 0; m < n_masks; ++m)
+        CU(cudaMemcpyAsync(out + (size_t)m * s->n_cols, s->d_cnt[m], (size_t)s->n_cols * 4, cudaMemcpyDeviceToHost,
+                           s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return KV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// a4: get_columns
+// ------------------------------------------------------------------------------------------------
+extern "C" int kv_get_columns(kv_shard *s, const int64_t *cols, int64_t n, uint64_t *out) {
+    if (!s || (n > 0 && (!cols || !out))) return fail(KV_E_INVALID, "kv_get_columns: null pointer");
+    if (n < 0) return fail(KV_E_INVALID, "kv_get_columns: negative count");
+    if (n == 0) return KV_OK;
+    for (int64_t i = 0; i < n; ++i)
+        if (cols[i] < 0 || cols[i] >= s->n_cols) return fail(KV_E_INVALID, "kv_get_columns: column outside the shard");
+    DeviceGuard g(s->device);
+    s->last_launches = 0;
+    const size_t out_bytes = (size_t)n * s->W * 8, idx_bytes = (size_t)n * 8;
+    KV_TRY(ensure(s->d_stage, out_bytes + idx_bytes));
+    long long *d_cols = (long long *)((char *)s->d_stage.p + out_bytes);
+    CU(cudaMemcpyAsync(d_cols, cols, idx_bytes, cudaMemcpyHostToDevice, s->stream));
+    const int threads = (int)std::min<long long>(256, std::max<long long>(32, s->W));
+    k_gather_cols<<<(unsigned)n, threads, 0, s->stream>>>(s->d_mat, s->ld, s->W, d_cols, n, (uint64_t *)s->d_stage.p);
+    count_launch(s);
+    CU(cudaMemcpyAsync(out, s->d_stage.p, out_bytes, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    CU(cudaGetLastError());
+    return KV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// a6: SCM scan
+// ------------------------------------------------------------------------------------------------
+extern "C" int kv_set_blacklist(kv_shard *s, const int64_t *rule_idx, int64_t n) {
+    if (!s || (n > 0 && !rule_idx)) return fail(KV_E_INVALID, "kv_set_blacklist: null pointer");
+    DeviceGuard g(s->device);
+    s->scm_valid = s->gini_valid = false;
+    if (n <= 0) {
+        s->have_black = false;
+        return KV_OK;
+    }
+    const size_t words = (size_t)s->ld / 32;
+    std::vector<uint32_t> bp(words, 0), ba(words, 0);
+    for (int64_t i = 0; i < n; ++i) {
+        int64_t r = rule_idx[i];
+        if (r < 0) r += 2 * s->k_total;                       // numpy negative indexing (scm.py:240)
+        if (r < 0 || r >= 2 * s->k_total) return fail(KV_E_INVALID, "kv_set_blacklist: rule index out of range");
+        const bool absence = r >= s->k_total;
+        const int64_t c = (absence ? r - s->k_total : r) - s->col0;
+        if (c < 0 || c >= s->n_cols) continue;
+        (absence ? ba : bp)[c >> 5] |= 1u << (c & 31);
+    }
+    if (!s->d_black_pres) {
+        CU(cudaMalloc(&s->d_black_pres, words * 4));
+        CU(cudaMalloc(&s->d_black_abs, words * 4));
+    }
+    CU(cudaMemcpyAsync(s->d_black_pres, bp.data(), words * 4, cudaMemcpyHostToDevice, s->stream));
+    CU(cudaMemcpyAsync(s->d_black_abs, ba.data(), words * 4, cudaMemcpyHostToDevice, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    s->have_black = true;
+    return KV_OK;
+}
+
+extern "C" int64_t kv_scm_n_blocks(int64_t n_kmers_total, int64_t util_block_size) {
+    if (n_kmers_total <= 0 || util_block_size <= 0) return 0;
+    return (2 * n_kmers_total + util_block_size - 1) / util_block_size;
+}
+
+// d_misc layout: blockmax enc [n_blocks] | bm f64 [n_blocks] | tol f64 [n_blocks] | sel u8 [n_blocks] | counter
+struct MiscLayout {
+    unsigned long long *blockmax;
+    double *bm, *tol;
+    uint8_t *sel;
+    unsigned long long *counter;
+    size_t bytes;
+};
+static MiscLayout misc_layout(void *base, long long n_blocks) {
+    MiscLayout L;
+    char *p = (char *)base;
+    L.blockmax = (unsigned long long *)p; p += (size_t)n_blocks * 8;
+    L.bm = (double *)p; p += (size_t)n_blocks * 8;
+    L.tol = (double *)p; p += (size_t)n_blocks * 8;
+    L.counter = (unsigned long long *)p; p += 16;
+    L.sel = (uint8_t *)p; p += ((size_t)n_blocks + 15) / 16 * 16;
+    L.bytes = (size_t)(p - (char *)base);
+    return L;
+}
+
+static int scm_scan_async(kv_shard *s, const uint64_t *pos_mask, const uint64_t *neg_mask, int64_t n_pos, int64_t n_neg,
+                          double p, int64_t ubs, int64_t n_blocks) {
+    if (n_pos < 0 || n_neg < 0 || n_pos > s->n_examples || n_neg > s->n_examples)
+        return fail(KV_E_INVALID, "kv_scm_scan: n_pos / n_neg out of range");
+    if (ubs <= 0) return fail(KV_E_INVALID, "kv_scm_scan: util_block_size must be positive");
+    if (n_blocks != kv_scm_n_blocks(s->k_total, ubs)) return fail(KV_E_INVALID, "kv_scm_scan: wrong n_blocks");
+    KV_TRY(ensure_counts(s, 2));
+    int nA, nB, nC;
+    KV_TRY(push_records2(s, pos_mask, neg_mask, nA, nB, nC));
+    MiscLayout L0 = misc_layout(nullptr, n_blocks);
+    KV_TRY(ensure(s->d_misc, L0.bytes));
+    MiscLayout L = misc_layout(s->d_misc.p, n_blocks);
+    CU(cudaMemsetAsync(L.blockmax, 0, (size_t)n_blocks * 8, s->stream));
+    Scan2Params P;
+    fill_scan2(s, P, nA, nB, nC);
+    P.cnt0 = s->d_cnt[0];
+    P.cnt1 = s->d_cnt[1];
+    P.p = p;
+    P.n_pos = (uint32_t)n_pos;
+    P.n_neg = (uint32_t)n_neg;
+    P.ubs = ubs;
+    P.black_pres = s->have_black ? s->d_black_pres : nullptr;
+    P.black_abs = s->have_black ? s->d_black_abs : nullptr;
+    P.blockmax = L.blockmax;
+    const size_t smem = (size_t)(nA + nB + nC) * 20 + 16;
+    KV_TRY(check_smem(smem));
+    CU(cudaEventRecord(s->ev0, s->stream));
+    k_scan2<EPI_SCM><<<scan_grid(s), SCAN_THREADS, smem, s->stream>>>(P);
+    count_launch(s);
+    CU(cudaEventRecord(s->ev1, s->stream));
+    s->scm_valid = true;
+    s->gini_valid = false;
+    s->scm_n_pos = n_pos;
+    s->scm_n_neg = n_neg;
+    s->scm_ubs = ubs;
+    s->scm_p = p;
+    return KV_OK;
+}
+
+extern "C" int kv_scm_scan(kv_shard *s, const uint64_t *pos_mask, const uint64_t *neg_mask, int64_t n_pos,
+                           int64_t n_neg, double p, int64_t util_block_size, double *block_max, int64_t n_blocks) {
+    if (!s || !pos_mask || !neg_mask || !block_max) return fail(KV_E_INVALID, "kv_scm_scan: null pointer");
+    DeviceGuard g(s->device);
+    s->last_launches = 0;
+    KV_TRY(scm_scan_async(s, pos_mask, neg_mask, n_pos, n_neg, p, util_block_size, n_blocks));
+    KV_TRY(ensure_pinned(s, (size_t)n_blocks * 8));
+    MiscLayout L = misc_layout(s->d_misc.p, n_blocks);
+    CU(cudaMemcpyAsync(s->h_pin, L.blockmax, (size_t)n_blocks * 8, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    CU(cudaGetLastError());
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+    s->last_kernel_ms = ms;
+    const unsigned long long *enc = (const unsigned long long *)s->h_pin;
+    for (int64_t b = 0; b < n_blocks; ++b) block_max[b] = dec_f64_max(enc[b]);
+    return KV_OK;
+}
+
+// numpy.isclose(a, b) for scalars, rtol=1e-5, atol=1e-8 (numpy 2.3: |a-b| <= atol + rtol*|b| and
+// isfinite(b), or a == b).  Compiled with -ffp-contract=off: one rounded multiply, one rounded add.
+static inline bool np_isclose(double a, double b) {
+    if (a == b) return true;
+    if (!std::isfinite(b)) return false;
+    volatile double t = 1e-5 * std::fabs(b);
+    volatile double tol = 1e-8 + t;
+    return std::fabs(a - b) <= tol;
+}
+
+extern "C" int kv_scm_select_blocks(const double *block_max, int64_t n_blocks, double *best_utility,
+                                    uint8_t *selected) {
+    if (!block_max || !best_utility || !selected || n_blocks <= 0)
+        return fail(KV_E_INVALID, "kv_scm_select_blocks: bad arguments");
+    double best = -std::numeric_limits<double>::infinity();
+    memset(selected, 0, (size_t)n_blocks);
+    for (int64_t b = 0; b < n_blocks; ++b) {
+        const double m = block_max[b];
+        if (m > best || np_isclose(best, m)) {          // scm.py:271
+            if (np_isclose(m, best)) {                  // scm.py:276: append, best_utility unchanged
+                selected[b] = 1;
+            } else {                                    // scm.py:282-286: replace
+                best = m;
+                memset(selected, 0, (size_t)n_blocks);
+                selected[b] = 1;
+            }
+        }
+    }
+    *best_utility = best;
+    return KV_OK;
+}
+
+struct TieRec {
+    long long idx;
+    uint32_t pe, nc;
+};
+
+static int scm_ties_impl(kv_shard *s, const double *block_max, const uint8_t *selected, int64_t n_blocks,
+                         int64_t capacity, int64_t *rule_idx, int64_t *pos_err, int64_t *neg_cover, int64_t *n_found) {
+    if (!s->scm_valid) return fail(KV_E_INVALID, "kv_scm_ties: no SCM scan result on the device");
+    if (n_blocks != kv_scm_n_blocks(s->k_total, s->scm_ubs)) return fail(KV_E_INVALID, "kv_scm_ties: wrong n_blocks");
+    if (capacity < 0) return fail(KV_E_INVALID, "kv_scm_ties: negative capacity");
+    MiscLayout L = misc_layout(s->d_misc.p, n_blocks);
+    // block table -> pinned -> device
+    const size_t tab_bytes = (size_t)n_blocks * 16 + 16 + ((size_t)n_blocks + 15) / 16 * 16;
+    KV_TRY(ensure_pinned(s, tab_bytes));
+    {
+        double *bm = (double *)s->h_pin, *tol = bm + n_blocks;
+        unsigned long long *cnt = (unsigned long long *)(tol + n_blocks);
+        uint8_t *sel = (uint8_t *)(cnt + 2);
+        for (int64_t b = 0; b < n_blocks; ++b) {
+            bm[b] = block_max[b];
+            volatile double t = 1e-5 * std::fabs(block_max[b]);
+            volatile double tl = 1e-8 + t;
+            tol[b] = tl;
+            sel[b] = selected[b];
+        }
+        cnt[0] = cnt[1] = 0;
+        CU(cudaMemcpyAsync(L.bm, s->h_pin, tab_bytes, cudaMemcpyHostToDevice, s->stream));
+    }
+    const long long cap = std::max<long long>(capacity, 1);
+    KV_TRY(ensure(s->d_ties, (size_t)cap * 16));
+    TieParams T;
+    memset(&T, 0, sizeof T);
+    T.cnt0 = s->d_cnt[0];
+    T.cnt1 = s->d_cnt[1];
+    T.n_cols = s->n_cols;
+    T.col0 = s->col0;
+    T.k_total = s->k_total;
+    T.ubs = s->scm_ubs;
+    T.inv_ubs = 1.0 / (double)s->scm_ubs;
+    T.p = s->scm_p;
+    T.n_pos = (uint32_t)s->scm_n_pos;
+    T.n_neg = (uint32_t)s->scm_n_neg;
+    T.black_pres = s->have_black ? s->d_black_pres : nullptr;
+    T.black_abs = s->have_black ? s->d_black_abs : nullptr;
+    T.bm = L.bm;
+    T.tol = L.tol;
+    T.sel = L.sel;
+    T.out_idx = (long long *)s->d_ties.p;
+    T.out_pe = (uint32_t *)((char *)s->d_ties.p + (size_t)cap * 8);
+    T.out_nc = T.out_pe + cap;
+    T.counter = L.counter;
+    T.cap = capacity;
+    const unsigned grid = (unsigned)std::min<long long>((s->n_cols + 255) / 256, (long long)s->sm_count * 8);
+    k_scm_ties<<<grid, 256, 0, s->stream>>>(T);
+    count_launch(s);
+    // counter + (optimistically) the first few ties in one round trip
+    CU(cudaMemcpyAsync(s->h_pin, L.counter, 8, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    CU(cudaGetLastError());
+    const long long found = (long long)*(unsigned long long *)s->h_pin;
+    *n_found = found;
+    if (found > capacity) return fail(KV_E_OVERFLOW, "kv_scm_ties: tie buffer too small");
+    if (found == 0) return KV_OK;
+    KV_TRY(ensure_pinned(s, (size_t)found * 16));
+    char *hp = (char *)s->h_pin;
+    CU(cudaMemcpyAsync(hp, T.out_idx, (size_t)found * 8, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaMemcpyAsync(hp + (size_t)found * 8, T.out_pe, (size_t)found * 4, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaMemcpyAsync(hp + (size_t)found * 12, T.out_nc, (size_t)found * 4, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    const long long *h_idx = (const long long *)hp;
+    const uint32_t *h_pe = (const uint32_t *)(hp + (size_t)found * 8), *h_nc = h_pe + found;
+    std::vector<TieRec> recs((size_t)found);
+    for (long long i = 0; i < found; ++i) recs[i] = {h_idx[i], h_pe[i], h_nc[i]};
+    std::sort(recs.begin(), recs.end(), [](const TieRec &a, const TieRec &b) { return a.idx < b.idx; });
+    for (long long i = 0; i < found; ++i) {
+        rule_idx[i] = recs[i].idx;
+        pos_err[i] = recs[i].pe;
+        neg_cover[i] = recs[i].nc;
+    }
+    return KV_OK;
+}
+
+extern "C" int kv_scm_ties(kv_shard *s, const double *block_max, const uint8_t *selected, int64_t n_blocks,
+                           int64_t capacity, int64_t *rule_idx, int64_t *pos_err, int64_t *neg_cover,
+                           int64_t *n_found) {
+    if (!s || !block_max || !selected || !n_found || (capacity > 0 && (!rule_idx || !pos_err || !neg_cover)))
+        return fail(KV_E_INVALID, "kv_scm_ties: null pointer");
+    DeviceGuard g(s->device);
+    s->last_launches = 0;
+    return scm_ties_impl(s, block_max, selected, n_blocks, capacity, rule_idx, pos_err, neg_cover, n_found);
+}
+
+extern "C" int kv_scm_best_rules(kv_shard *s, const uint64_t *pos_mask, const uint64_t *neg_mask, int64_t n_pos,
+                                 int64_t n_neg, double p, int64_t util_block_size, double *best_utility,
+                                 int64_t capacity, int64_t *rule_idx, int64_t *pos_err, int64_t *neg_cover,
+                                 int64_t *n_found) {
+    if (!s || !pos_mask || !neg_mask || !best_utility || !n_found) return fail(KV_E_INVALID, "kv_scm_best_rules: null pointer");
+    if (s->col0 != 0 || s->n_cols != s->k_total)
+        return fail(KV_E_INVALID, "kv_scm_best_rules: single-shard call on a partial shard; use scan/select/ties");
+    const int64_t n_blocks = kv_scm_n_blocks(s->k_total, util_block_size);
+    if (n_blocks <= 0) return fail(KV_E_INVALID, "kv_scm_best_rules: util_block_size must be positive");
+    std::vector<double> bm((size_t)n_blocks);
+    std::vector<uint8_t> sel((size_t)n_blocks);
+    KV_TRY(kv_scm_scan(s, pos_mask, neg_mask, n_pos, n_neg, p, util_block_size, bm.data(), n_blocks));
+    const double scan_ms = s->last_kernel_ms;
+    const long long scan_launches = s->last_launches;
+    KV_TRY(kv_scm_select_blocks(bm.data(), n_blocks, best_utility, sel.data()));
+    DeviceGuard g(s->device);
+    int rc = scm_ties_impl(s, bm.data(), sel.data(), n_blocks, capacity, rule_idx, pos_err, neg_cover, n_found);
+    s->last_kernel_ms = scan_ms;
+    (void)scan_launches;
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// a9 / a11: Gini split scan
+// ------------------------------------------------------------------------------------------------
+template <int MODE>
+static void launch_gini(kv_shard *s, const GiniParams &G) {
+    const unsigned grid = (unsigned)std::min<long long>((s->n_cols + 255) / 256, (long long)s->sm_count * 8);
+    switch (G.n_classes) {
+        case 2: k_gini<2, MODE><<<grid, 256, 0, s->stream>>>(G); break;
+        case 3: k_gini<3, MODE><<<grid, 256, 0, s->stream>>>(G); break;
+        case 4: k_gini<4, MODE><<<grid, 256, 0, s->stream>>>(G); break;
+        default: k_gini<0, MODE><<<grid, 256, 0, s->stream>>>(G); break;
+    }
+    count_launch(s);
+}
+
+extern "C" int kv_gini_scan(kv_shard *s, int n_classes, const uint64_t *class_masks, const double *altered_prior,
+                            const double *n_total, const int64_t *n_node, double *min_score) {
+    if (!s || !class_masks || !altered_prior || !n_total || !n_node || !min_score)
+        return fail(KV_E_INVALID, "kv_gini_scan: null pointer");
+    if (n_classes < 1 || n_classes > MAX_CLASSES) return fail(KV_E_INVALID, "kv_gini_scan: 1..64 classes supported");
+    DeviceGuard g(s->device);
+    s->last_launches = 0;
+    s->scm_valid = false;
+    s->gini_valid = false;
+    if (n_classes == 2) {
+        // two disjoint class masks: the grouped two-mask scan reads each packed row once
+        KV_TRY(ensure_counts(s, 2));
+        int nA, nB, nC;
+        KV_TRY(push_records2(s, class_masks, class_masks + s->W, nA, nB, nC));
+        Scan2Params P;
+        fill_scan2(s, P, nA, nB, nC);
+        P.cnt0 = s->d_cnt[0];
+        P.cnt1 = s->d_cnt[1];
+        const size_t smem = (size_t)(nA + nB + nC) * 20 + 16;
+        KV_TRY(check_smem(smem));
+        CU(cudaEventRecord(s->ev0, s->stream));
+        k_scan2<EPI_COUNTS><<<scan_grid(s), SCAN_THREADS, smem, s->stream>>>(P);
+        count_launch(s);
+        CU(cudaEventRecord(s->ev1, s->stream));
+    } else {
+        KV_TRY(count_masks(s, n_classes, class_masks, 0));
+    }
+    GiniParams &G = s->gini;
+    memset(&G, 0, sizeof G);
+    G.n_classes = n_classes;
+    for (int c = 0; c < n_classes; ++c) {
+        G.cnt[c] = s->d_cnt[c];
+        G.prior[c] = altered_prior[c];
+        G.n_total[c] = n_total[c];
+        G.n_node[c] = (double)n_node[c];
+    }
+    G.n_cols = s->n_cols;
+    G.col0 = s->col0;
+    G.black_pres = s->have_black ? s->d_black_pres : nullptr;
+    KV_TRY(ensure(s->d_misc, 64));
+    G.min_enc = (unsigned long long *)s->d_misc.p;
+    G.counter = G.min_enc + 1;
+    CU(cudaMemsetAsync(G.min_enc, 0xFF, 8, s->stream));
+    launch_gini<GINI_MIN>(s, G);
+    KV_TRY(ensure_pinned(s, 64));
+    CU(cudaMemcpyAsync(s->h_pin, G.min_enc, 8, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    CU(cudaGetLastError());
+    if (n_classes == 2) {
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+        s->last_kernel_ms = ms;
+    }
+    *min_score = dec_f64_min(*(unsigned long long *)s->h_pin);
+    s->gini_valid = true;
+    return KV_OK;
+}
+
+extern "C" int kv_gini_ties(kv_shard *s, double min_score, int64_t capacity, int64_t *rule_idx, int64_t *n_found) {
+    if (!s || !n_found || (capacity > 0 && !rule_idx)) return fail(KV_E_INVALID, "kv_gini_ties: null pointer");
+    if (!s->gini_valid) return fail(KV_E_INVALID, "kv_gini_ties: no Gini scan result on the device");
+    if (capacity < 0) return fail(KV_E_INVALID, "kv_gini_ties: negative capacity");
+    DeviceGuard g(s->device);
+    s->last_launches = 0;
+    const long long cap = std::max<long long>(capacity, 1);
+    KV_TRY(ensure(s->d_ties, (size_t)cap * 8));
+    GiniParams G = s->gini;
+    G.min_score = min_score;
+    G.out_idx = (long long *)s->d_ties.p;
+    G.cap = capacity;
+    CU(cudaMemsetAsync(G.counter, 0, 8, s->stream));
+    launch_gini<GINI_TIES>(s, G);
+    CU(cudaMemcpyAsync(s->h_pin, G.counter, 8, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    CU(cudaGetLastError());
+    const long long found = (long long)*(unsigned long long *)s->h_pin;
+    *n_found = found;
+    if (found > capacity) return fail(KV_E_OVERFLOW, "kv_gini_ties: tie buffer too small");
+    if (found == 0) return KV_OK;
+    CU(cudaMemcpyAsync(rule_idx, G.out_idx, (size_t)found * 8, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    std::sort(rule_idx, rule_idx + found);
+    return KV_OK;
+}
+
+extern "C" int kv_gini_scores(kv_shard *s, double *out) {
+    if (!s || !out) return fail(KV_E_INVALID, "kv_gini_scores: null pointer");
+    if (!s->gini_valid) return fail(KV_E_INVALID, "kv_gini_scores: no Gini scan result on the device");
+    DeviceGuard g(s->device);
+    s->last_launches = 0;
+    KV_TRY(ensure(s->d_stage, (size_t)s->n_cols * 8));
+    GiniParams G = s->gini;
+    G.scores = (double *)s->d_stage.p;
+    launch_gini<GINI_SCORES>(s, G);
+    CU(cudaMemcpyAsync(out, G.scores, (size_t)s->n_cols * 8, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    CU(cudaGetLastError());
+    return KV_OK;
+}

@@ -1,0 +1,294 @@
+"""Rule objects and the device-resident ``KmerRuleClassifications``.
+
+Mirrors reference kover/learning/common/rules.py: same class names, constructor signature,
+methods (``get_columns``, ``remove_rows``, ``shape``, ``sum_rows``), return dtypes and exceptions
+(rules.py:27-267).  What changes is where the matrix lives: the constructor streams the packed
+``kmer_matrix`` into HBM once (column-sharded over the visible GPUs) and every later call is a
+kernel over that resident image instead of a loop of h5py chunk reads + Cython popcount
+(rules.py:247-262).
+
+Additions the learners of this package use (not in the reference): ``best_utility_rules`` (the
+fused SCM scan, scm.py:238-288) and ``gini_best_split`` (cart.py:112-161, 231-238).
+"""
+import os
+
+import numpy as np
+
+from ... import _native
+from ...sharding import Comm, ShardGroup, partition_columns
+from ...utils import _minimum_uint_size, _unpack_binary_bytes_from_ints, build_row_mask
+
+
+class KmerRule(object):
+    def __init__(self, kmer_index, kmer_sequence, type):
+        """A k-mer presence ("presence") or absence ("absence") rule (rules.py:27-54)."""
+        self.kmer_index = kmer_index
+        self.kmer_sequence = kmer_sequence
+        self.type = type
+
+    def classify(self, X):
+        if self.type == "absence":
+            return (X[:, self.kmer_index] == 0).astype(np.uint8)
+        else:
+            return (X[:, self.kmer_index] == 1).astype(np.uint8)
+
+    def inverse(self):
+        return KmerRule(kmer_index=self.kmer_index, kmer_sequence=self.kmer_sequence,
+                        type="absence" if self.type == "presence" else "presence")
+
+    def __str__(self):
+        return ("Absence(" if self.type == "absence" else "Presence(") + str(self.kmer_sequence) + ")"
+
+
+class LazyKmerRuleList(object):
+    """First half: presence rules; second half: absence rules in the same order (rules.py:57-79)."""
+
+    def __init__(self, kmer_sequences, kmer_by_rule):
+        self.n_rules = kmer_by_rule.shape[0] * 2
+        self.kmer_sequences = kmer_sequences
+        self.kmer_by_rule = kmer_by_rule
+
+    def __getitem__(self, idx):
+        if idx >= self.n_rules:
+            raise ValueError("Index %d is out of range for list of size %d" % (idx, self.n_rules))
+        if idx >= len(self.kmer_sequences):
+            type = "absence"
+            kmer_idx = self.kmer_by_rule[idx % len(self.kmer_sequences)]
+        else:
+            type = "presence"
+            kmer_idx = self.kmer_by_rule[idx]
+        return KmerRule(idx % len(self.kmer_sequences), self.kmer_sequences[kmer_idx], type)
+
+    def __len__(self):
+        return self.n_rules
+
+
+class BaseRuleClassifications(object):
+    def __init__(self):
+        pass
+
+    def get_columns(self, columns):
+        raise NotImplementedError()
+
+    def remove_rows(self, rows):
+        raise NotImplementedError()
+
+    @property
+    def shape(self):
+        raise NotImplementedError()
+
+    def sum_rows(self, rows):
+        raise NotImplementedError()
+
+
+def _default_devices():
+    env = os.environ.get("KOVER_B200_DEVICES")
+    if env:
+        return [int(x) for x in env.split(",") if x.strip() != ""]
+    return [int(os.environ.get("LOCAL_RANK", "0"))]
+
+
+class KmerRuleClassifications(BaseRuleClassifications):
+    """Methods involving columns account for presence and absence rules.
+
+    dataset: the packed ``kmer_matrix`` -- anything with ``shape``, ``dtype``, numpy-style
+        ``__getitem__`` and optionally ``chunks`` (an h5py dataset, a numpy array or memmap).
+    n_rows: the number of genomes.
+    block_size: kept for signature compatibility (rules.py:104); it sizes the upload slabs only.
+
+    Keyword-only extras: ``devices`` (CUDA ordinals; default $KOVER_B200_DEVICES, else $LOCAL_RANK,
+    else 0), ``comm`` (a sharding.Comm: this process holds rank ``comm.rank``'s column slice),
+    ``shard_group`` (adopt an existing, already filled group).
+    """
+
+    def __init__(self, dataset, n_rows, block_size=None, devices=None, comm=None, shard_group=None):
+        self.dataset = dataset
+        self.dataset_initial_n_rows = n_rows
+        self.dataset_n_rows = n_rows
+        self.dataset_removed_rows = []
+        self.dataset_removed_rows_mask = np.zeros(self.dataset_initial_n_rows, dtype=bool)
+        self.block_size = (None, None)
+
+        if block_size is None:
+            chunks = getattr(self.dataset, "chunks", None)
+            if chunks is None:
+                self.block_size = (1, self.dataset.shape[1])
+            else:
+                self.block_size = chunks
+        else:
+            if len(block_size) != 2 or not isinstance(block_size[0], int) or not isinstance(block_size[1], int):
+                raise ValueError("The block size must be a tuple of 2 integers.")
+            self.block_size = block_size
+
+        # Get the size of the ints used to store the data
+        if self.dataset.dtype == np.uint32:
+            self.dataset_pack_size = 32
+        elif self.dataset.dtype == np.uint64:
+            self.dataset_pack_size = 64
+        else:
+            raise ValueError("Unsupported data type for packed attribute classifications array. The supported data" +
+                             " types are np.uint32 and np.uint64.")
+
+        self._n_kmers = int(self.dataset.shape[1])
+        self._blacklist_key = None
+        if shard_group is not None:
+            self._group = shard_group
+        else:
+            self._group = self._build_group(devices, comm)
+            self._upload()
+        super(BaseRuleClassifications, self).__init__()
+
+    # ------------------------------------------------------------------ device image
+    def _build_group(self, devices, comm):
+        n, k = int(self.dataset_initial_n_rows), self._n_kmers
+        if n > self.dataset.shape[0] * self.dataset_pack_size:
+            raise ValueError("n_rows exceeds the number of examples the packed matrix can hold.")
+        devices = list(devices) if devices is not None else _default_devices()
+        if comm is not None:
+            slices = partition_columns(k, comm.world_size)
+            col0, n_cols = slices[comm.rank]
+            if n_cols == 0:
+                raise ValueError("more ranks than 512-column tiles")
+            return ShardGroup([_native.Shard(devices[0], n, k, col0, n_cols)], n, k, comm=comm, rank_slices=slices)
+        slices = [s for s in partition_columns(k, len(devices)) if s[1] > 0]
+        return ShardGroup([_native.Shard(d, n, k, c0, nc) for d, (c0, nc) in zip(devices, slices)], n, k)
+
+    def _upload(self, slab_bytes=128 << 20):
+        """Stream the packed matrix into HBM: row slabs x the column span of the local shards."""
+        ds = self.dataset
+        itemsize = np.dtype(ds.dtype).itemsize
+        n_packed_rows = int(ds.shape[0])
+        needed_rows = -(-int(self.dataset_initial_n_rows) // self.dataset_pack_size)
+        for s in self._group.shards:
+            c0, c1 = s.col0, s.col0 + s.n_cols
+            rows_per_slab = max(1, min(needed_rows, slab_bytes // max(1, s.n_cols * itemsize)))
+            for r0 in range(0, min(needed_rows, n_packed_rows), rows_per_slab):
+                r1 = min(r0 + rows_per_slab, needed_rows, n_packed_rows)
+                block = np.asarray(ds[r0:r1, c0:c1])
+                s.upload_block(block, r0, c0)
+
+    def close(self):
+        self._group.close()
+
+    # ------------------------------------------------------------------ reference interface
+    def get_columns(self, columns):
+        """
+        Columns can be an integer (or any object that implements __index__) or a sorted list/ndarray.
+        """
+        columns_is_int = False
+        if hasattr(columns, "__index__"):  # All int types implement the __index__ method (PEP 357)
+            columns = [columns.__index__()]
+            columns_is_int = True
+        elif isinstance(columns, np.ndarray):
+            columns = columns.tolist()
+        elif isinstance(columns, list):
+            pass
+        else:
+            columns = list(columns)
+
+        n_kmers = self._n_kmers
+        # Detect where an inversion is needed (columns corresponding to absence rules)
+        invert_result = np.array([c >= n_kmers for c in columns], dtype=bool)
+        columns = [(c if c < n_kmers else c % n_kmers) for c in columns]
+
+        # Don't return rows that have been deleted
+        row_mask = np.ones(self.dataset.shape[0] * self.dataset_pack_size, dtype=bool)
+        row_mask[self.dataset_initial_n_rows:] = False
+        row_mask[self.dataset_removed_rows] = False
+
+        unique, inverse = np.unique(columns, return_inverse=True)
+        if unique.size and (unique[0] < -n_kmers or unique[-1] >= n_kmers):
+            raise IndexError("column index out of range")
+        unique = np.where(unique < 0, unique + n_kmers, unique)
+        packed = self._group.get_packed_columns(unique)                       # [n_unique, W64]
+        result = _unpack_binary_bytes_from_ints(np.ascontiguousarray(packed.T))   # [W64 * 64, n_unique]
+        n_unpacked = min(row_mask.shape[0], result.shape[0])   # rows past n_rows are masked out anyway
+        result = result[:n_unpacked][row_mask[:n_unpacked]]
+        result = result[:, inverse]
+        result[:, invert_result] = 1 - result[:, invert_result]
+
+        if columns_is_int:
+            return result.reshape(-1)
+        else:
+            return result
+
+    def _dataset_relative_rows(self, rows):
+        """The (r+1)-th row that has not been removed, for each r (rules.py:177-184, 227-236)."""
+        rows = np.asarray(rows, dtype=np.int64).reshape(-1)
+        if len(self.dataset_removed_rows) == 0:
+            if rows.size and (rows.min() < 0 or rows.max() >= self.dataset_initial_n_rows):
+                raise IndexError("index out of bounds")
+            return rows
+        alive = np.flatnonzero(~self.dataset_removed_rows_mask)
+        return alive[rows]
+
+    def remove_rows(self, rows):
+        dataset_removed_rows = self._dataset_relative_rows(rows).tolist()
+        if len(dataset_removed_rows) > 0:
+            self.dataset_removed_rows = sorted(set(self.dataset_removed_rows + dataset_removed_rows))
+            self.dataset_removed_rows_mask = np.zeros(self.dataset_initial_n_rows, dtype=bool)
+            self.dataset_removed_rows_mask[self.dataset_removed_rows] = True
+            self.dataset_n_rows = self.dataset_initial_n_rows - len(self.dataset_removed_rows)
+
+    @property
+    def shape(self):
+        return self.dataset_n_rows, self._n_kmers * 2
+
+    def row_mask(self, rows):
+        """64-bit row mask over the packed rows for example indices ``rows`` (rules.py:210-239)."""
+        return build_row_mask(self._dataset_relative_rows(np.sort(np.asarray(rows))),
+                              self.dataset_initial_n_rows, 64)
+
+    def sum_rows(self, rows):
+        """
+        Note: Assumes that the rows argument does not contain duplicate elements. Rows will not be considered more than once.
+        """
+        rows = np.asarray(rows)
+        result_dtype = _minimum_uint_size(rows.shape[0])
+        n_kmers = self._n_kmers
+        result = np.zeros(n_kmers * 2, dtype=result_dtype)
+        mask = self.row_mask(rows)
+        self._group.sum_rows_into(mask, result[:n_kmers])
+        # Compute the sum for absence rules
+        result[n_kmers:] = len(rows) - result[:n_kmers]
+        return result
+
+    # ------------------------------------------------------------------ fused scans (this package's learners)
+    def set_rule_blacklist(self, rule_blacklist):
+        bl = np.asarray(rule_blacklist, dtype=np.int64).reshape(-1)
+        key = bl.tobytes()
+        if key != self._blacklist_key:
+            self._group.set_blacklist(bl)
+            self._blacklist_key = key
+
+    def best_utility_rules(self, p, positive_example_idx, negative_example_idx, rule_blacklist=(),
+                           util_block_size=1000000):
+        """scm.py:238-288 in one pass over the matrix.  -> (best_utility, rule idx ascending,
+        pos_error_counts, neg_cover_counts) for the rules whose utility ties the maximum."""
+        positive_example_idx = np.asarray(positive_example_idx)
+        negative_example_idx = np.asarray(negative_example_idx)
+        self.set_rule_blacklist(rule_blacklist)
+        pos_mask = self.row_mask(positive_example_idx)
+        neg_mask = self.row_mask(negative_example_idx)
+        return self._group.scm_best_rules(pos_mask, neg_mask, positive_example_idx.shape[0],
+                                          negative_example_idx.shape[0], float(p), int(util_block_size))
+
+    def gini_best_split(self, example_idx, altered_priors, n_total_class_examples, rule_blacklist=()):
+        """cart.py:112-161 + 231-238.  example_idx: dict class -> example indices of the node, iterated in
+        dict order like the reference.  -> (min score, presence-rule indices achieving it, ascending)."""
+        self.set_rule_blacklist(rule_blacklist)
+        classes = list(example_idx.keys())
+        masks = np.stack([self.row_mask(example_idx[c]) for c in classes])
+        prior = np.array([altered_priors[c] for c in classes], dtype=np.float64)
+        total = np.array([n_total_class_examples[c] for c in classes], dtype=np.float64)
+        n_node = np.array([len(example_idx[c]) for c in classes], dtype=np.int64)
+        return self._group.gini_best_split(masks, prior, total, n_node)
+
+    def gini_scores(self):
+        """rules_criterion of the last gini_best_split call (cart.py:228-231), float64 [n_kmers]."""
+        return self._group.gini_scores()
+
+    def sum_rows_multi(self, row_sets):
+        """Presence counts for several row sets in one pass (the reference's TODO at rules.py:200).
+        -> uint32 [len(row_sets), n_kmers]."""
+        return self._group.sum_rows_multi(np.stack([self.row_mask(r) for r in row_sets]))

@@ -1,0 +1,199 @@
+"""Column sharding of the packed matrix and the small per-scan merge.
+
+K-mer columns are independent units: every shard holds all W packed rows of a contiguous column
+slice, scans it alone, and only tiny results cross shards -- per-utility-block maxima (one double
+per 10^6 rules), tie lists, one selected column.  ``ShardGroup`` runs that protocol over
+
+  * the shards this process owns (one per local GPU; usually exactly one), and
+  * optionally a ``Comm`` over torch.distributed (one process per GPU, NCCL on the GPU box, gloo in
+    the CPU tests) for the shards other ranks own.
+
+The group is written against a small shard interface (scm_scan / scm_ties / gini_scan / gini_ties /
+sum_rows / get_columns / set_blacklist, see _native.Shard) so the host-side merge logic can be
+exercised without a GPU by the world_size-2 gloo tests, which plug in a checker-backed shard.
+"""
+import numpy as np
+
+from . import _native
+
+TILE_COLS = 512
+
+
+def partition_columns(n_kmers, n_parts):
+    """Contiguous column slices [(col0, n_cols)] of near-equal size, boundaries on 512-column tiles.
+    Parts may be empty only when n_kmers < n_parts * 512; empty parts are dropped by the callers."""
+    n_tiles = (n_kmers + TILE_COLS - 1) // TILE_COLS
+    bounds = [min(n_kmers, ((n_tiles * i) // n_parts) * TILE_COLS) for i in range(n_parts)] + [n_kmers]
+    return [(bounds[i], bounds[i + 1] - bounds[i]) for i in range(n_parts)]
+
+
+class Comm(object):
+    """Numpy-level collectives over a torch.distributed process group (NCCL or gloo)."""
+
+    def __init__(self, group=None, device=None):
+        import torch
+        import torch.distributed as dist
+        self._torch, self._dist, self.group = torch, dist, group
+        self.rank = dist.get_rank(group)
+        self.world_size = dist.get_world_size(group)
+        backend = dist.get_backend(group)
+        self.device = device if device is not None else (
+            torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu"))
+
+    def _t(self, a):
+        return self._torch.from_numpy(np.ascontiguousarray(a)).to(self.device)
+
+    def allreduce_max(self, a):
+        t = self._t(a)
+        self._dist.all_reduce(t, op=self._dist.ReduceOp.MAX, group=self.group)
+        return t.cpu().numpy()
+
+    def allreduce_sum(self, a):
+        t = self._t(a)
+        self._dist.all_reduce(t, op=self._dist.ReduceOp.SUM, group=self.group)
+        return t.cpu().numpy()
+
+    def allreduce_min(self, a):
+        t = self._t(a)
+        self._dist.all_reduce(t, op=self._dist.ReduceOp.MIN, group=self.group)
+        return t.cpu().numpy()
+
+    def allgather_concat(self, a):
+        """Concatenate 1-D int64 arrays of different lengths from every rank, in rank order."""
+        a = np.ascontiguousarray(a, dtype=np.int64)
+        n = self._t(np.array([a.shape[0]], dtype=np.int64))
+        sizes = [self._torch.zeros_like(n) for _ in range(self.world_size)]
+        self._dist.all_gather(sizes, n, group=self.group)
+        sizes = [int(s.item()) for s in sizes]
+        m = max(sizes)
+        if m == 0:
+            return np.zeros(0, dtype=np.int64)
+        pad = np.zeros(m, dtype=np.int64)
+        pad[:a.shape[0]] = a
+        t = self._t(pad)
+        out = [self._torch.zeros_like(t) for _ in range(self.world_size)]
+        self._dist.all_gather(out, t, group=self.group)
+        return np.concatenate([o.cpu().numpy()[:s] for o, s in zip(out, sizes)])
+
+    def broadcast(self, a, src):
+        t = self._t(a)
+        self._dist.broadcast(t, src=self._dist.get_global_rank(self.group, src) if self.group is not None else src,
+                             group=self.group)
+        return t.cpu().numpy()
+
+    def barrier(self):
+        self._dist.barrier(group=self.group)
+
+
+class ShardGroup(object):
+    """Shards owned by this process (+ optional Comm to the other ranks) acting as one matrix."""
+
+    def __init__(self, shards, n_examples, n_kmers, comm=None, rank_slices=None):
+        self.shards = list(shards)
+        self.n_examples = int(n_examples)
+        self.n_words = (self.n_examples + 63) // 64
+        self.n_kmers = int(n_kmers)
+        self.comm = comm
+        # rank_slices[r] = (col0, n_cols) of rank r (to find the owner of a column)
+        self.rank_slices = rank_slices
+        if comm is None:
+            covered = sum(s.n_cols for s in self.shards)
+            if covered != self.n_kmers:
+                raise ValueError("local shards cover %d of %d columns" % (covered, self.n_kmers))
+        self._single = comm is None and len(self.shards) == 1
+
+    # ------------------------------------------------------------------ upload
+    def upload_block(self, block, row0, gcol0):
+        for s in self.shards:
+            s.upload_block(block, row0, gcol0)
+
+    # ------------------------------------------------------------------ a3
+    def sum_rows_into(self, mask, out):
+        """Presence counts of the LOCAL shards into out[col0:col0+n_cols] (out spans all K columns)."""
+        for s in self.shards:
+            s.sum_rows(mask, out[s.col0:s.col0 + s.n_cols])
+        if self.comm is not None:
+            # every rank needs the full vector to honour the reference's return value
+            lo = min(s.col0 for s in self.shards)
+            hi = max(s.col0 + s.n_cols for s in self.shards)
+            full = self.comm.allgather_concat(out[lo:hi].astype(np.int64))
+            out[:] = full.astype(out.dtype)
+        return out
+
+    # ------------------------------------------------------------------ a4
+    def get_packed_columns(self, cols):
+        """cols: presence-column indices (global).  -> uint64 [len(cols), W]."""
+        cols = np.asarray(cols, dtype=np.int64)
+        out = np.zeros((cols.shape[0], self.n_words), dtype=np.uint64)
+        for s in self.shards:
+            sel = np.flatnonzero((cols >= s.col0) & (cols < s.col0 + s.n_cols))
+            if sel.size:
+                out[sel] = s.get_columns(cols[sel] - s.col0)
+        if self.comm is not None:
+            # exactly one rank owns each column and the others hold zeros: a sum-reduce is a broadcast
+            out = self.comm.allreduce_sum(out.view(np.int64)).view(np.uint64)
+        return out
+
+    # ------------------------------------------------------------------ a6
+    def set_blacklist(self, rule_idx):
+        for s in self.shards:
+            s.set_blacklist(rule_idx)
+
+    def scm_best_rules(self, pos_mask, neg_mask, n_pos, n_neg, p, util_block_size):
+        """-> (best_utility, rule_idx ascending int64, pos_err int64, neg_cover int64); scm.py:238-288."""
+        if self._single:
+            return self.shards[0].scm_best_rules(pos_mask, neg_mask, n_pos, n_neg, p, util_block_size)
+        bm = None
+        for s in self.shards:
+            b = s.scm_scan(pos_mask, neg_mask, n_pos, n_neg, p, util_block_size)
+            bm = b if bm is None else np.maximum(bm, b)
+        if self.comm is not None:
+            bm = self.comm.allreduce_max(bm)
+        best, sel = _native.select_blocks(bm)
+        parts = [s.scm_ties(bm, sel) for s in self.shards]
+        idx = np.concatenate([q[0] for q in parts])
+        pe = np.concatenate([q[1] for q in parts])
+        nc = np.concatenate([q[2] for q in parts])
+        if self.comm is not None:
+            flat = self.comm.allgather_concat(np.stack([idx, pe, nc], axis=1).reshape(-1)).reshape(-1, 3)
+            idx, pe, nc = flat[:, 0], flat[:, 1], flat[:, 2]
+        order = np.argsort(idx, kind="stable")
+        return best, idx[order], pe[order], nc[order]
+
+    # ------------------------------------------------------------------ a9 / a11
+    def gini_best_split(self, class_masks, altered_prior, n_total, n_node):
+        """-> (min_score, presence-rule indices with score == min_score, ascending); cart.py:112-161, 231-238."""
+        mins = [s.gini_scan(class_masks, altered_prior, n_total, n_node) for s in self.shards]
+        m = min(mins)
+        if self.comm is not None:
+            m = float(self.comm.allreduce_min(np.array([m], dtype=np.float64))[0])
+        if m == np.inf:
+            return m, np.zeros(0, dtype=np.int64)
+        idx = np.concatenate([s.gini_ties(m) if mn == m else np.zeros(0, dtype=np.int64)
+                              for s, mn in zip(self.shards, mins)])
+        if self.comm is not None:
+            idx = self.comm.allgather_concat(idx)
+        return m, np.sort(idx)
+
+    def gini_scores(self):
+        if self.comm is not None:
+            raise NotImplementedError("gini_scores is a single-process debugging aid")
+        out = np.empty(self.n_kmers, dtype=np.float64)
+        for s in self.shards:
+            out[s.col0:s.col0 + s.n_cols] = s.gini_scores()
+        return out
+
+    def sum_rows_multi(self, masks):
+        """uint32 [n_masks, K] presence counts of several masks in one pass (local shards only)."""
+        if self.comm is not None:
+            raise NotImplementedError("sum_rows_multi is per-process")
+        masks = np.ascontiguousarray(masks, dtype=np.uint64)
+        out = np.empty((masks.shape[0], self.n_kmers), dtype=np.uint32)
+        for s in self.shards:
+            out[:, s.col0:s.col0 + s.n_cols] = s.sum_rows_multi(masks)
+        return out
+
+    def close(self):
+        for s in self.shards:
+            s.close()
+        self.shards = []

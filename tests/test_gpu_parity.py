@@ -1,0 +1,347 @@
+"""GPU: the CUDA path (through the C ABI, via the reference-shaped Python classes) against
+  (1) the golden vectors minted from the REAL reference (tests/golden/*.npz),
+  (2) the CPU checker (oracle/) on seeded inputs at sizes it finishes in seconds,
+  (3) size-independent properties at BASELINE.json's config-2 size (2k genomes x 10M k-mers).
+Everything is bit-exact: integer counts and index sets with array_equal, float64 utilities / Gini
+scores with ==."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import cases
+from kover_b200 import _native
+from kover_b200.learning.common import popcount as kpop
+from kover_b200.learning.common.rules import KmerRuleClassifications, LazyKmerRuleList
+from kover_b200.learning.learners import cart as kcart
+from kover_b200.learning.learners import scm as kscm
+from kover_b200.synthetic import synthetic_block, synthetic_labels, train_split
+from oracle import kover_oracle as ko
+
+pytestmark = pytest.mark.gpu
+
+
+def load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name + ".npz"))
+
+
+class Chunked(np.ndarray):
+    chunks = None
+
+
+def as_dataset(P, chunks):
+    d = P.view(Chunked)
+    d.chunks = chunks
+    return d
+
+
+def rule_list(k):
+    return LazyKmerRuleList(["K%d" % i for i in range(k)], np.arange(k))
+
+
+# ---------------------------------------------------------------------------------- a1
+def test_popcount_kernel_golden(golden_dir):
+    g = load(golden_dir, "popcount")
+    a = g["a64"].copy()
+    kpop.inplace_popcount_64(a, g["m64"])
+    assert np.array_equal(a, g["o64"])
+    b = g["a32"].copy()
+    kpop.inplace_popcount_32(b, g["m32"])
+    assert np.array_equal(b, g["o32"])
+    with pytest.raises(ValueError):
+        kpop.inplace_popcount_64(g["a32"].copy(), g["m32"])
+
+
+# ---------------------------------------------------------------------------------- a3 / a4 / a5
+@pytest.mark.parametrize("mname", ["M1", "M2", "M3", "M4"])
+@pytest.mark.parametrize("devices", [[0], [0, 0, 0]], ids=["1shard", "3shards"])
+def test_sum_rows_get_columns_golden(golden_dir, mname, devices):
+    g = load(golden_dir, "rules_" + mname)
+    X, P, n, chunks = cases.matrix(mname)
+    k = P.shape[1]
+    rc = KmerRuleClassifications(as_dataset(P, chunks), n, devices=devices)
+    assert list(rc.shape) == g["shape"].tolist()
+    for rname, rows in cases.row_sets(n).items():
+        got = rc.sum_rows(rows)
+        want = g["sum_" + rname]
+        assert got.dtype == want.dtype, rname
+        assert np.array_equal(got, want), rname
+    for cname, cols in cases.column_sets(k).items():
+        got = rc.get_columns(cols)
+        want = g["col_" + cname]
+        assert got.shape == want.shape and got.dtype == want.dtype and np.array_equal(got, want), cname
+    if mname == "M3":
+        rc32 = KmerRuleClassifications(as_dataset(cases.pack32_from64(P), chunks), n, devices=devices)
+        for rname, rows in cases.row_sets(n).items():
+            assert np.array_equal(rc32.sum_rows(rows), g["sum32_" + rname]), rname
+        assert np.array_equal(rc32.get_columns(cases.column_sets(k)["mixed"]), g["col32_mixed"])
+    if mname == "M4":
+        rc2 = KmerRuleClassifications(as_dataset(P, chunks), n, devices=devices)
+        rc2.remove_rows([3, 10])
+        rc2.remove_rows([0])
+        assert list(rc2.shape) == g["rm_shape"].tolist()
+        assert np.array_equal(rc2.sum_rows(np.array([0, 1, 2, 9, 40, 61])), g["rm_sum"])
+        assert np.array_equal(rc2.get_columns([1, k + 2]), g["rm_col"])
+        with pytest.raises(TypeError):
+            rc2.get_columns(np.array([1, 2]))
+
+
+def test_sum_rows_multi_matches_single():
+    X, P, n, chunks = cases.matrix("M2")
+    rc = KmerRuleClassifications(P, n, devices=[0, 0])
+    sets = list(cases.row_sets(n).values()) + [np.arange(0, n, 3), np.arange(1, n, 7), np.arange(n - 70, n)] * 3
+    multi = rc.sum_rows_multi(sets)        # 17 masks: two passes of k_count_multi
+    for i, rows in enumerate(sets):
+        assert np.array_equal(multi[i], rc.sum_rows(rows)[:P.shape[1]].astype(np.uint32)), i
+
+
+# ---------------------------------------------------------------------------------- a6
+@pytest.mark.parametrize("case", cases.UTILITY_CASES, ids=[c[0] for c in cases.UTILITY_CASES])
+@pytest.mark.parametrize("devices", [[0], [0, 0]], ids=["1shard", "2shards"])
+def test_best_utility_rules_golden(golden_dir, case, devices):
+    g = load(golden_dir, case[0])
+    P, n, chunks, pos, neg, p, blacklist, ubs = cases.utility_inputs(case)
+    rc = KmerRuleClassifications(as_dataset(P, chunks), n, devices=devices)
+    bu, bi, bp, bn = rc.best_utility_rules(p, pos, neg, rule_blacklist=blacklist, util_block_size=ubs)
+    assert bu == float(g["best_utility"])
+    assert np.array_equal(bi, g["best_idx"])
+    assert np.array_equal(bp, g["best_pos_err"])
+    assert np.array_equal(bn, g["best_neg_cover"])
+
+
+def test_best_utility_no_positives_left():
+    # scm.py:250-253: with no positive example left the error counts are all zero
+    X, P, n, chunks = cases.matrix("M1")
+    rc = KmerRuleClassifications(P, n, devices=[0])
+    neg = np.arange(0, n, 2)
+    bu, bi, bp, bn = rc.best_utility_rules(1.0, np.array([], dtype=np.int64), neg, util_block_size=1000)
+    orc = ko.OracleKmerRuleClassifications(P, n, fast=True)
+    wu, wi, wp, wn = ko.merge_utility_blocks(len(neg) - orc.sum_rows(neg), np.zeros(2 * P.shape[1], dtype=np.uint8),
+                                             1.0, np.zeros(2 * P.shape[1], dtype=bool), block_size=1000)
+    assert bu == wu and np.array_equal(bi, np.asarray(wi, dtype=np.int64)) and not bp.any()
+    assert np.array_equal(bn, wn)
+
+
+def test_tie_buffer_overflow_regrows():
+    # every rule of an all-zero matrix ties: 2K ties must come back complete and ascending
+    n, k = 70, 3000
+    P = np.zeros((2, k), dtype=np.uint64)
+    rc = KmerRuleClassifications(P, n, devices=[0])
+    pos, neg = np.arange(0, 30), np.arange(30, 70)
+    shard = rc._group.shards[0]
+    bu, bi, bp, bn = shard.scm_best_rules(rc.row_mask(pos), rc.row_mask(neg), 30, 40, 1.0, 1000, capacity=16)
+    assert bu == 10.0 and np.array_equal(bi, np.arange(k))      # presence rules: 40 covered - 1.0 * 30 errors
+    assert bp.tolist() == [30] * k and bn.tolist() == [40] * k
+
+
+@pytest.mark.parametrize("seed,n,k,p,ubs", [(1, 1000, 70000, 1.0, 1000000), (2, 2500, 30011, 0.316, 9973),
+                                            (3, 129, 100001, 999999.0, 50000), (4, 640, 51200, 2.0, 512)])
+@pytest.mark.parametrize("sorted_labels", [True, False])
+def test_best_utility_rules_vs_checker(seed, n, k, p, ubs, sorted_labels):
+    P = synthetic_block(seed, n, 0, k)
+    y = synthetic_labels(seed, n, sorted_by_label=sorted_labels)
+    train = train_split(seed, n)
+    pos, neg = train[y[train] == 1], train[y[train] == 0]
+    blacklist = np.unique(np.random.RandomState(seed).randint(0, 2 * k, size=50))
+    orc = ko.OracleKmerRuleClassifications(P, n, fast=True)
+    bl = np.zeros(2 * k, dtype=bool)
+    bl[blacklist] = True
+    wu, wi, wp, wn = ko.merge_utility_blocks(len(neg) - orc.sum_rows(neg), len(pos) - orc.sum_rows(pos), p, bl,
+                                             block_size=ubs)
+    for devices in ([0], [0, 0, 0]):
+        rc = KmerRuleClassifications(P, n, devices=devices)
+        bu, bi, bp, bn = rc.best_utility_rules(p, pos, neg, rule_blacklist=blacklist, util_block_size=ubs)
+        assert bu == wu
+        assert np.array_equal(bi, np.asarray(wi, dtype=np.int64))
+        assert np.array_equal(bp, wp) and np.array_equal(bn, wn)
+        rc.close()
+
+
+# ---------------------------------------------------------------------------------- a7 / a8
+@pytest.mark.parametrize("case", cases.SCM_CASES, ids=[c[0] for c in cases.SCM_CASES])
+def test_scm_fit_golden(golden_dir, case, monkeypatch):
+    name, mname, lname, model_type, p, max_rules, tb, blacklist, ubs = case
+    g = load(golden_dir, name)
+    X, P, n, chunks = cases.matrix(mname)
+    y = cases.labels(lname)
+    k = P.shape[1]
+    monkeypatch.setattr(kscm, "UTIL_BLOCK_SIZE", ubs)
+    rc = KmerRuleClassifications(as_dataset(P, chunks), n, devices=[0, 0])
+    risks = cases.rule_risks(2 * k)
+
+    def tiebreaker(idx):
+        if tb == "identity":
+            return idx
+        return ko.scm_tiebreaker(idx, risks, model_type)
+
+    infos = []
+    m = kscm.SetCoveringMachine(model_type=model_type, p=p, max_rules=max_rules)
+    m.fit(rule_list(k), rc, np.where(y == 1)[0], np.where(y == 0)[0], rule_blacklist=blacklist,
+          tiebreaker=tiebreaker, iteration_callback=lambda i: infos.append(dict(i)), iteration_rule_importances=True)
+    assert len(infos) == int(g["n_iterations"])
+    assert str(m.model) == str(g["model_str"])
+    for t, info in enumerate(infos):
+        assert info["utility_max"] == float(g["it%d_utility_max" % t])
+        assert np.array_equal(np.asarray(info["utility_argmax"], dtype=np.int64), g["it%d_utility_argmax" % t])
+        assert np.array_equal(np.asarray(info["equivalent_rules_idx"], dtype=np.int64), g["it%d_equivalent" % t])
+        assert str(info["selected_rule"]) == str(g["it%d_selected" % t])
+        assert np.array_equal(info["rule_importances"], g["it%d_importances" % t])
+    assert np.array_equal(np.asarray(m.rule_importances, dtype=np.float64), g["rule_importances"])
+    # predictions of the learnt model on the unpacked matrix (models.py:155-182)
+    if X is not None:
+        pred = m.predict(X)
+        cls = np.stack([r.classify(X) for r in m.model.rules], axis=1)
+        want = cls.all(axis=1) if model_type == "conjunction" else cls.any(axis=1)
+        assert np.array_equal(pred, want.astype(np.uint8))
+
+
+# ---------------------------------------------------------------------------------- a9 / a11
+def tree_to_dict(node):
+    d = {"depth": node.depth, "criterion_value": float(node.criterion_value),
+         "n_by_class": {int(c): int(len(v)) for c, v in node.class_examples_idx.items()}}
+    if node.rule is not None:
+        d["rule_idx"] = int(node.rule.kmer_index)
+        d["equivalent_rules_idx"] = [int(x) for x in node.equivalent_rules_idx]
+        d["importance"] = float(node.rule.importance)
+        d["left"] = tree_to_dict(node.left_child)
+        d["right"] = tree_to_dict(node.right_child)
+    return d
+
+
+def tree_equal(got, want, path="root"):
+    assert got["depth"] == want["depth"], path
+    assert got["n_by_class"] == {int(c): v for c, v in want["n_by_class"].items()}, path
+    assert got["criterion_value"] == want["criterion_value"], path
+    assert ("rule_idx" in got) == ("rule_idx" in want), path
+    if "rule_idx" in want:
+        assert got["rule_idx"] == want["rule_idx"], path
+        assert got["equivalent_rules_idx"] == want["equivalent_rules_idx"], path
+        assert got["importance"] == want["importance"], path
+        tree_equal(got["left"], want["left"], path + ".L")
+        tree_equal(got["right"], want["right"], path + ".R")
+
+
+@pytest.mark.parametrize("case", cases.CART_CASES, ids=[c[0] for c in cases.CART_CASES])
+@pytest.mark.parametrize("devices", [[0], [0, 0]], ids=["1shard", "2shards"])
+def test_cart_fit_golden(golden_dir, case, devices):
+    name, mname, lname, max_depth, mss, class_importance, tb, subset_seed = case
+    g = load(golden_dir, name)
+    want = json.loads(str(g["tree_json"]))
+    X, P, n, chunks = cases.matrix(mname)
+    y = cases.labels(lname)
+    k = P.shape[1]
+    rc = KmerRuleClassifications(as_dataset(P, chunks), n, devices=devices)
+    train = cases.train_subset(n, subset_seed)
+    example_idx = {c: train[y[train] == c] for c in sorted(class_importance.keys())}
+    tiebreaker = None
+    if tb == "occurrence":
+        occ = rc.sum_rows(train)
+        tiebreaker = lambda idx: ko.cart_tiebreaker(idx, occ)
+    t = kcart.DecisionTreeClassifier("gini", max_depth, mss, class_importance)
+    t.fit(rule_list(k), rc, example_idx, rule_blacklist=[], tiebreaker=tiebreaker)
+    tree_equal(tree_to_dict(t.decision_tree), want)
+
+
+@pytest.mark.parametrize("n_classes", [2, 3, 5])
+def test_gini_scores_vs_checker(n_classes):
+    seed, n, k = 11, 700, 40000
+    P = synthetic_block(seed, n, 0, k)
+    rs = np.random.RandomState(seed)
+    y = rs.randint(0, n_classes, size=n)
+    node = np.sort(rs.choice(n, 400, replace=False))          # a node deeper in the tree: a subset of examples
+    ex_all = {c: np.where(y == c)[0] for c in range(n_classes)}
+    ex_node = {c: node[y[node] == c] for c in range(n_classes)}
+    importance = {c: 1.0 + 0.37 * c for c in range(n_classes)}
+    n_total, altered = ko.cart_altered_priors(ex_all, importance)
+    orc = ko.OracleKmerRuleClassifications(P, n, fast=True)
+    want = ko.gini_rule_score(orc, ex_node, altered, n_total)
+    blacklist = [5, 17, 39999]
+    want[blacklist] = np.inf
+    rc = KmerRuleClassifications(P, n, devices=[0, 0])
+    m, cand = rc.gini_best_split(ex_node, altered, n_total, rule_blacklist=blacklist)
+    got = rc.gini_scores()
+    assert np.array_equal(got, want)                           # bit-exact float64, inf included
+    assert m == want.min() and np.array_equal(cand, np.where(want == want.min())[0])
+
+
+def test_cross_entropy_fit_matches_checker_counts():
+    # cross-entropy: device counts + the reference's numpy formula on the host (cart.py:167-207)
+    X, P, n, chunks = cases.matrix("M2")
+    y = cases.labels("M2_planted")
+    k = P.shape[1]
+    rc = KmerRuleClassifications(P, n, devices=[0])
+    t = kcart.DecisionTreeClassifier("cross-entropy", 3, 2, {0: 1.0, 1: 1.0})
+    t.fit(rule_list(k), rc, {0: np.where(y == 0)[0], 1: np.where(y == 1)[0]})
+    assert sorted(r.kmer_index for r in t.decision_tree.rules) == [3, 9, 20]
+
+
+# ---------------------------------------------------------------------------------- full-size properties (config 2)
+@pytest.fixture(scope="module")
+def config2():
+    n, k, seed = 2000, 10_000_000, 72
+    shard = _native.Shard(0, n, k)
+    shard.generate_synthetic(seed)
+    from kover_b200.sharding import ShardGroup
+
+    class Meta(object):
+        shape = (32, k)
+        dtype = np.dtype(np.uint64)
+        chunks = (1, 100000)
+
+    rc = KmerRuleClassifications(Meta(), n, shard_group=ShardGroup([shard], n, k))
+    yield rc, n, k, seed
+    rc.close()
+
+
+def test_config2_slices_match_checker(config2):
+    rc, n, k, seed = config2
+    y = synthetic_labels(seed, n)
+    train = train_split(seed, n)
+    pos, neg = train[y[train] == 1], train[y[train] == 0]
+    sp, sn = rc.sum_rows(pos), rc.sum_rows(neg)
+    assert sp.dtype == np.uint16 and sp.shape == (2 * k,)
+    for c0 in (0, 4_999_680, k - 100_000):
+        P = synthetic_block(seed, n, c0, 100_000)
+        orc = ko.OracleKmerRuleClassifications(P, n, fast=True)
+        assert np.array_equal(sp[c0:c0 + 100_000], orc.sum_rows(pos)[:100_000])
+        assert np.array_equal(sn[k + c0:k + c0 + 100_000], orc.sum_rows(neg)[100_000:])
+        cols = [c0, c0 + 77_777, k + c0 + 99_999]
+        local = [0, 77_777, 100_000 + 99_999]
+        assert np.array_equal(rc.get_columns(cols), orc.get_columns(local))
+
+
+def test_config2_scan_properties(config2):
+    rc, n, k, seed = config2
+    y = synthetic_labels(seed, n)
+    train = train_split(seed, n)
+    pos, neg = train[y[train] == 1], train[y[train] == 0]
+    sp, sn = rc.sum_rows(pos), rc.sum_rows(neg)
+    # presence + absence = |rows| for every k-mer; linearity over a disjoint union
+    assert np.array_equal(sp[:k].astype(np.int64) + sp[k:], np.full(k, len(pos)))
+    both = rc.sum_rows(train)
+    assert np.array_equal(both[:k].astype(np.int64), sp[:k].astype(np.int64) + sn[:k])
+    for p in (1.0, 0.1, 999999.0):
+        neg_cover = (len(neg) - sn).astype(np.float64)
+        pos_err = (len(pos) - sp).astype(np.float64)
+        bu, bi, bp, bn = rc.best_utility_rules(p, pos, neg)
+        wu, wi, wp, wn = ko.merge_utility_blocks(len(neg) - sn, len(pos) - sp, p, np.zeros(2 * k, dtype=bool))
+        assert bu == wu and np.array_equal(bi, np.asarray(wi, dtype=np.int64))
+        assert np.array_equal(bp, wp) and np.array_equal(bn, wn)
+        u = neg_cover - p * pos_err
+        assert bu <= u.max() and np.all(np.isclose(u[bi], u[bi].max(), rtol=2e-5))
+
+
+def test_config2_gini_properties(config2):
+    rc, n, k, seed = config2
+    y = synthetic_labels(seed, n)
+    train = train_split(seed, n)
+    ex = {0: train[y[train] == 0], 1: train[y[train] == 1]}
+    n_total, altered = ko.cart_altered_priors(ex, {0: 1.0, 1: 1.0})
+    m, cand = rc.gini_best_split(ex, altered, n_total)
+    scores = rc.gini_scores()
+    assert m == scores.min() and np.array_equal(cand, np.where(scores == m)[0])
+    c0 = 1_234_944
+    P = synthetic_block(seed, n, c0, 50_000)
+    want = ko.gini_rule_score(ko.OracleKmerRuleClassifications(P, n, fast=True), ex, altered, n_total)
+    assert np.array_equal(scores[c0:c0 + 50_000], want)
