@@ -318,7 +318,7 @@ def run_ours(args):
         "dtype": "u64 popcount + f64 utility", "data": "synthetic (hash-generated on device, seed %d)" % SEED,
         "config": workload_config(world),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "k_scan2<EPI_SCM>", "peak_source": peak_src,
+                     "traffic": None, "kernel": "k_scan_tma<EPI_SCM>", "peak_source": peak_src,
                      "bytes_per_launch": float(np.mean(alg_bytes)), "kernel_ms": float(np.mean(kernel_ms)),
                      "kernel_share_of_step": float(np.sum(kernel_ms) / dev_ms)},
         "e2e": {"value": rules_per_step * args.steps / e2e_s, "unit": "rules/s",

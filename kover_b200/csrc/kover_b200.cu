@@ -2,16 +2,17 @@
 //
 // What the kernels compute and which reference lines they restate (paths relative to
 // /root/reference/core/kover):
-//   k_scan2        rules.py:201-267 (sum_rows for two row masks in ONE pass over the packed matrix:
+//   k_scan_tma     rules.py:201-267 (sum_rows for two row masks in ONE pass over the packed matrix:
 //                  popcount(word & mask), popcount.pyx:76-95) fused with the SCM utility and the
-//                  per-utility-block maximum of scm.py:262-270
+//                  per-utility-block maximum of scm.py:262-270; TMA bulk copies + mbarrier ring
+//   k_scm_select   scm.py:270-286 (sequential merge of the block maxima), on the device
 //   k_scm_ties     scm.py:273 (isclose tie set against the block maximum)
 //   k_count_multi  rules.py:201-267 for up to 8 masks per pass (CART classes, batched sum_rows)
 //   k_gini         cart.py:85-161 (_gini_impurity / _gini_rule_score), min + exact ties cart.py:238
 //   k_gather_cols  rules.py:164 (dataset[:, cols])
 //   k_popc_inplace popcount.pyx:31-50, 76-95
-// Layout in HBM: uint64 [W, ld] row-major, ld = n_cols rounded up to 512 words so that every
-// 512-column tile row is a 4 KB aligned segment; padding columns are zero and masked out of every
+// Layout in HBM: uint64 [W, ld] row-major, ld = n_cols rounded up to 1024 words so that every
+// tile row (512 or 1024 columns) is a 4 / 8 KB aligned segment; padding columns are zero and masked out of every
 // reduction.  The path is a bitwise reduction bound by HBM bandwidth: no tensor cores.
 //
 // No CPU fallback lives here: every entry point either runs on the GPU or returns an error.
@@ -68,7 +69,8 @@ extern "C" int kv_device_count(int *n) {
 // ------------------------------------------------------------------------------------------------
 // constants
 // ------------------------------------------------------------------------------------------------
-static constexpr int TILE_COLS = 512;    // columns per tile: 256 threads x one 128-bit load
+static constexpr int TILE_COLS = 512;    // columns per tile of the direct-load kernels: 256 threads x one 128-bit load
+static constexpr int LD_ALIGN = 3072;    // row pitch granularity: a multiple of every tile width (256/512/768/1024)
 static constexpr int SCAN_THREADS = 256;
 static constexpr int MAX_MULTI = 8;      // masks per pass of k_count_multi
 static constexpr int MAX_CLASSES = 64;
@@ -136,16 +138,25 @@ __device__ __forceinline__ double warp_min(double v) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_scan2: the hot kernel
+// k_scan_tma: the hot kernel
 // ------------------------------------------------------------------------------------------------
+// One pass over the shard for a pair of row masks.  Warp-specialised, persistent, one CTA per SM:
+//   * producer warp: one elected lane walks the CTA's tiles x active packed rows and issues one TMA
+//     bulk copy (cp.async.bulk, global -> shared, completion on an mbarrier) per (row, tile) segment
+//     of CW*512 contiguous bytes into a ring of S stages x R rows;
+//   * CW consumer warps: wait for a stage, read their two 64-bit columns of each row from shared
+//     memory with one 128-bit load, AND with the row's mask words (staged in shared memory once per
+//     CTA) and popcount; release the stage; after the last row of a tile run the epilogue.
+// The ring keeps ~128 KB of reads in flight per SM without holding registers, which the sweep in
+// tools/scan_sweep.cu measured at 96-98 % of the copy-bandwidth peak against 84-95 % for direct
+// loads (profiles/README.md).
 struct Scan2Params {
     const uint64_t *mat;
-    long long ld, n_cols, col0, k_total, n_tiles;
-    // active packed rows (mask word != 0, rules.py:244), grouped: nA rows where only mask 0 is
-    // non-zero, then nB rows where only mask 1 is, then nC rows where both are.
+    long long ld, n_cols, col0, k_total;
+    // active packed rows (mask word != 0, rules.py:244): rows with only mask 0, then only mask 1, then both
     const uint32_t *rec_row;
     const uint64_t *rec_m0, *rec_m1;
-    int nA, nB, nC;
+    int n_act;
     uint32_t *cnt0, *cnt1;            // [ld] each; cnt1 may be null (single-mask scan)
     // SCM epilogue
     double p;
@@ -153,49 +164,48 @@ struct Scan2Params {
     long long ubs;
     const uint32_t *black_pres, *black_abs;   // bitmaps over local columns or null
     unsigned long long *blockmax;             // enc_f64 per utility block
+    unsigned long long *segmax;               // enc_f64 per 64-column segment: [2][ld / 64] (presence, absence)
 };
 
 enum { EPI_COUNTS = 0, EPI_SCM = 1 };
 
-template <int MODE>   // 0: mask 0 only, 1: mask 1 only, 2: both
-__device__ __forceinline__ void accum_rows(const uint64_t *__restrict__ base, long long ld,
-                                           const uint32_t *rows, const uint64_t *m0, const uint64_t *m1, int n,
-                                           uint32_t &c0x, uint32_t &c0y, uint32_t &c1x, uint32_t &c1y) {
-    constexpr int UN = 8;
-    int i = 0;
-#pragma unroll 1
-    for (; i + UN <= n; i += UN) {
-        ulonglong2 v[UN];
-#pragma unroll
-        for (int j = 0; j < UN; ++j) v[j] = ldg_stream(base + (long long)rows[i + j] * ld);
-#pragma unroll
-        for (int j = 0; j < UN; ++j) {
-            if (MODE != 1) {
-                const uint64_t m = m0[i + j];
-                c0x += __popcll(v[j].x & m);
-                c0y += __popcll(v[j].y & m);
-            }
-            if (MODE != 0) {
-                const uint64_t m = m1[i + j];
-                c1x += __popcll(v[j].x & m);
-                c1y += __popcll(v[j].y & m);
-            }
-        }
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok = 0;
+    const uint32_t a = smem_u32(bar);
+    while (!ok) {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok)
+                     : "r"(a), "r"(parity)
+                     : "memory");
     }
-#pragma unroll 1
-    for (; i < n; ++i) {
-        const ulonglong2 v = ldg_stream(base + (long long)rows[i] * ld);
-        if (MODE != 1) {
-            const uint64_t m = m0[i];
-            c0x += __popcll(v.x & m);
-            c0y += __popcll(v.y & m);
-        }
-        if (MODE != 0) {
-            const uint64_t m = m1[i];
-            c1x += __popcll(v.x & m);
-            c1y += __popcll(v.y & m);
-        }
-    }
+}
+// TMA bulk copy global -> shared (1-D), completion signalled as transaction bytes on `bar`
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void consumer_bar(int n_threads) {
+    asm volatile("bar.sync 1, %0;" ::"r"(n_threads) : "memory");
+}
+
+// max over the warp of an enc_f64 image: two redux.sync on the 32-bit halves
+__device__ __forceinline__ unsigned long long warp_max_enc(unsigned long long e) {
+    const uint32_t hi = (uint32_t)(e >> 32), lo = (uint32_t)e;
+    const uint32_t mh = __reduce_max_sync(0xffffffffu, hi);
+    const uint32_t ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+    return ((unsigned long long)mh << 32) | ml;
 }
 
 // Running maximum of one half (presence / absence) of the rule space, kept per thread while the
@@ -205,54 +215,123 @@ struct RunMax {
     double mx;
 };
 
-__device__ __forceinline__ void runmax_flush(RunMax &r, unsigned long long *blockmax, double *s_red) {
-    // CTA-uniform call
+template <int CW>
+__device__ __forceinline__ void runmax_flush(RunMax &r, unsigned long long *blockmax, unsigned long long *s_red) {
+    // called by all consumer threads with CTA-uniform arguments
     if (r.bid >= 0) {
-        double v = warp_max(r.mx);
+        const unsigned long long v = warp_max_enc(enc_f64(r.mx));
         const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-        __syncthreads();
+        consumer_bar(CW * 32);
         if (lane == 0) s_red[wid] = v;
-        __syncthreads();
+        consumer_bar(CW * 32);
         if (threadIdx.x == 0) {
-            double m = s_red[0];
-            for (int w = 1; w < SCAN_THREADS / 32; ++w) m = fmax(m, s_red[w]);
-            atomicMax(blockmax + r.bid, enc_f64(m));
+            unsigned long long m = s_red[0];
+            for (int w = 1; w < CW; ++w) m = s_red[w] > m ? s_red[w] : m;
+            atomicMax(blockmax + r.bid, m);
         }
     }
 }
 
-template <int EPI>
-__global__ void __launch_bounds__(SCAN_THREADS, 4) k_scan2(const Scan2Params P) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ double s_red[SCAN_THREADS / 32];
-    const int n_act = P.nA + P.nB + P.nC;
-    uint64_t *s_m0 = reinterpret_cast<uint64_t *>(smem_raw);
+__device__ __forceinline__ void accum_word(const unsigned char *p, uint64_t a, uint64_t m, uint32_t &c0x, uint32_t &c0y,
+                                           uint32_t &c1x, uint32_t &c1y) {
+    const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(p);
+    if (a) {                                   // warp-uniform: the mask words are per row
+        c0x += __popcll(v.x & a);
+        c0y += __popcll(v.y & a);
+    }
+    if (m) {
+        c1x += __popcll(v.x & m);
+        c1y += __popcll(v.y & m);
+    }
+}
+
+template <int EPI, int CW, int R, int S, int MINB>
+__global__ void __launch_bounds__((CW + 1) * 32, MINB) k_scan_tma(const Scan2Params P) {
+    extern __shared__ __align__(128) unsigned char smem_tma[];
+    constexpr int ROW_BYTES = CW * 32 * 16;
+    constexpr int TC = CW * 64;                          // columns per tile
+    __shared__ unsigned long long s_red[CW];
+    const int n_act = P.n_act;
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_tma);
+    uint64_t *empty = full + S;
+    uint64_t *s_m0 = empty + S;
     uint64_t *s_m1 = s_m0 + n_act;
     uint32_t *s_row = reinterpret_cast<uint32_t *>(s_m1 + n_act);
-    for (int i = threadIdx.x; i < n_act; i += SCAN_THREADS) {
+    unsigned char *ring = smem_tma + ((size_t)(2 * S) * 8 + (size_t)n_act * 20 + 127) / 128 * 128;
+    for (int i = threadIdx.x; i < n_act; i += blockDim.x) {
         s_m0[i] = P.rec_m0[i];
         s_m1[i] = P.rec_m1[i];
         s_row[i] = P.rec_row[i];
     }
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(full + s, 1);
+            mbar_init(empty + s, CW);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
 
     // contiguous tile range per CTA: a CTA's rules stay inside one or two utility blocks
-    const long long t0 = (P.n_tiles * (long long)blockIdx.x) / gridDim.x;
-    const long long t1 = (P.n_tiles * (long long)(blockIdx.x + 1)) / gridDim.x;
+    const long long n_tiles = P.ld / TC;
+    const long long t0 = (n_tiles * (long long)blockIdx.x) / gridDim.x;
+    const long long t1 = (n_tiles * (long long)(blockIdx.x + 1)) / gridDim.x;
+    const int nb = (n_act + R - 1) / R;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+    if (warp == CW) {
+        // ------------------------------------------------------------------ producer
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            for (long long tile = t0; tile < t1; ++tile) {
+                const uint64_t *src = P.mat + tile * TC;
+                for (int b = 0; b < nb; ++b) {
+                    const int rows_here = min(R, n_act - b * R);
+                    mbar_wait(empty + s, ph ^ 1);
+                    mbar_expect_tx(full + s, (uint32_t)rows_here * ROW_BYTES);
+                    unsigned char *dst = ring + (size_t)s * R * ROW_BYTES;
+                    if (rows_here == R) {
+#pragma unroll
+                        for (int r = 0; r < R; ++r)
+                            tma_bulk_g2s(dst + r * ROW_BYTES, src + (long long)s_row[b * R + r] * P.ld, ROW_BYTES, full + s);
+                    } else {
+                        for (int r = 0; r < rows_here; ++r)
+                            tma_bulk_g2s(dst + r * ROW_BYTES, src + (long long)s_row[b * R + r] * P.ld, ROW_BYTES, full + s);
+                    }
+                    if (++s == S) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+        return;
+    }
+
+    // ---------------------------------------------------------------------- consumers
     RunMax run[2];
     run[0].lo = run[1].lo = 1; run[0].hi = run[1].hi = 0; run[0].bid = run[1].bid = -1;
     run[0].mx = run[1].mx = -INFINITY;
     const double neg_inf = -INFINITY;
-
+    int s = 0;
+    uint32_t ph = 0;
     for (long long tile = t0; tile < t1; ++tile) {
-        const long long col = tile * TILE_COLS + 2 * (long long)threadIdx.x;
-        const uint64_t *base = P.mat + col;
         uint32_t c0x = 0, c0y = 0, c1x = 0, c1y = 0;
-        accum_rows<0>(base, P.ld, s_row, s_m0, s_m1, P.nA, c0x, c0y, c1x, c1y);
-        accum_rows<1>(base, P.ld, s_row + P.nA, s_m0 + P.nA, s_m1 + P.nA, P.nB, c0x, c0y, c1x, c1y);
-        accum_rows<2>(base, P.ld, s_row + P.nA + P.nB, s_m0 + P.nA + P.nB, s_m1 + P.nA + P.nB, P.nC,
-                      c0x, c0y, c1x, c1y);
+        for (int b = 0; b < nb; ++b) {
+            const int rows_here = min(R, n_act - b * R);
+            mbar_wait(full + s, ph);
+            const unsigned char *st = ring + (size_t)s * R * ROW_BYTES + threadIdx.x * 16;
+            if (rows_here == R) {
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+                    accum_word(st + r * ROW_BYTES, s_m0[b * R + r], s_m1[b * R + r], c0x, c0y, c1x, c1y);
+            } else {
+                for (int r = 0; r < rows_here; ++r)
+                    accum_word(st + r * ROW_BYTES, s_m0[b * R + r], s_m1[b * R + r], c0x, c0y, c1x, c1y);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty + s);
+            if (++s == S) { s = 0; ph ^= 1; }
+        }
+        const long long col = tile * TC + 2 * (long long)threadIdx.x;
         *reinterpret_cast<uint2 *>(P.cnt0 + col) = make_uint2(c0x, c0y);
         if (P.cnt1) *reinterpret_cast<uint2 *>(P.cnt1 + col) = make_uint2(c1x, c1y);
 
@@ -264,22 +343,28 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k_scan2(const Scan2Params P) 
                 ba = P.black_abs[col >> 5] >> (col & 31);
             }
             // presence rule k: covers the negatives WITHOUT the k-mer, errs on the positives
-            // without it; absence rule K+k: the complements (rules.py:265, scm.py:245-251)
-            double u[2][2];
-            u[0][0] = (bp & 1u) ? neg_inf : scm_utility(P.n_neg - c1x, P.n_pos - c0x, P.p);
-            u[0][1] = (bp & 2u) ? neg_inf : scm_utility(P.n_neg - c1y, P.n_pos - c0y, P.p);
-            u[1][0] = (ba & 1u) ? neg_inf : scm_utility(c1x, c0x, P.p);
-            u[1][1] = (ba & 2u) ? neg_inf : scm_utility(c1y, c0y, P.p);
-            const long long tile_c0 = tile * TILE_COLS;
-            const long long tile_n = min((long long)TILE_COLS, P.n_cols - tile_c0);
+            // without it; absence rule K+k: the complements (rules.py:265, scm.py:245-251).
+            // Padding columns and blacklisted rules (scm.py:267) score -inf.
+            double ux[2], uy[2];
+            ux[0] = (!vx || (bp & 1u)) ? neg_inf : scm_utility(P.n_neg - c1x, P.n_pos - c0x, P.p);
+            uy[0] = (!vy || (bp & 2u)) ? neg_inf : scm_utility(P.n_neg - c1y, P.n_pos - c0y, P.p);
+            ux[1] = (!vx || (ba & 1u)) ? neg_inf : scm_utility(c1x, c0x, P.p);
+            uy[1] = (!vy || (ba & 2u)) ? neg_inf : scm_utility(c1y, c0y, P.p);
+            const long long tile_c0 = tile * TC;
+            const long long tile_n = min((long long)TC, P.n_cols - tile_c0);     // <= 0 for pure padding tiles
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
+                const double um = fmax(ux[h], uy[h]);
+                // per-64-column segment maximum: lets k_scm_ties skip segments that cannot hold a tie
+                const unsigned long long seg = warp_max_enc(enc_f64(um));
+                if (lane == 0) P.segmax[(size_t)h * (P.ld >> 6) + (col >> 6)] = seg;
+                if (tile_n <= 0) continue;
                 RunMax &r = run[h];
                 const long long r0 = (long long)h * P.k_total + P.col0 + tile_c0;
                 const long long r1 = r0 + tile_n - 1;
                 bool fast = (r0 >= r.lo) && (r1 < r.hi);
                 if (!fast) {                                   // CTA-uniform: depends on the tile only
-                    runmax_flush(r, P.blockmax, s_red);
+                    runmax_flush<CW>(r, P.blockmax, s_red);
                     const long long b0 = r0 / P.ubs, b1 = r1 / P.ubs;
                     if (b0 == b1) {
                         r.bid = b0; r.lo = b0 * P.ubs; r.hi = r.lo + P.ubs; r.mx = neg_inf;
@@ -289,20 +374,72 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k_scan2(const Scan2Params P) 
                     }
                 }
                 if (fast) {
-                    if (vx) r.mx = fmax(r.mx, u[h][0]);
-                    if (vy) r.mx = fmax(r.mx, u[h][1]);
+                    r.mx = fmax(r.mx, um);
                 } else {                                       // tile straddles a block boundary
                     const long long rx = r0 + 2 * (long long)threadIdx.x;
-                    if (vx) atomicMax(P.blockmax + rx / P.ubs, enc_f64(u[h][0]));
-                    if (vy) atomicMax(P.blockmax + (rx + 1) / P.ubs, enc_f64(u[h][1]));
+                    if (vx) atomicMax(P.blockmax + rx / P.ubs, enc_f64(ux[h]));
+                    if (vy) atomicMax(P.blockmax + (rx + 1) / P.ubs, enc_f64(uy[h]));
                 }
             }
         }
     }
     if (EPI == EPI_SCM) {
-        runmax_flush(run[0], P.blockmax, s_red);
-        runmax_flush(run[1], P.blockmax, s_red);
+        runmax_flush<CW>(run[0], P.blockmax, s_red);
+        runmax_flush<CW>(run[1], P.blockmax, s_red);
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_scm_select: device replay of the sequential utility-block merge (scm.py:270-286), one thread.
+// Same arithmetic as kv_scm_select_blocks / numpy.isclose: |a-b| <= atol + rtol*|b| and isfinite(b),
+// or a == b, every operation rounded separately.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double dec_f64_max_dev(unsigned long long v) {
+    if (v == 0ull) return -INFINITY;
+    const unsigned long long b = (v & 0x8000000000000000ull) ? (v & 0x7FFFFFFFFFFFFFFFull) : ~v;
+    return __longlong_as_double((long long)b);
+}
+__device__ __forceinline__ double np_tol_dev(double b) { return __dadd_rn(1e-8, __dmul_rn(1e-5, fabs(b))); }
+__device__ __forceinline__ bool np_isclose_dev(double a, double b) {
+    if (a == b) return true;
+    if (!isfinite(b)) return false;
+    return fabs(__dsub_rn(a, b)) <= np_tol_dev(b);
+}
+
+struct TieHeader {               // first 32 bytes of d_ties
+    double best_utility;
+    unsigned long long count;
+    unsigned long long pad[2];
+};
+struct TieRec {
+    long long idx;
+    uint32_t pe, nc;
+};
+
+__global__ void k_scm_select(const unsigned long long *blockmax, long long n_blocks, double *bm, double *tol,
+                             uint8_t *sel, TieHeader *hdr) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    double best = -INFINITY;
+    long long first = 0;                       // blocks before `first` are deselected
+    for (long long b = 0; b < n_blocks; ++b) {
+        const double m = dec_f64_max_dev(blockmax[b]);
+        bm[b] = m;
+        tol[b] = np_tol_dev(m);
+        uint8_t keep = 0;
+        if (m > best || np_isclose_dev(best, m)) {
+            if (np_isclose_dev(m, best)) {
+                keep = 1;
+            } else {
+                best = m;
+                for (long long q = first; q < b; ++q) sel[q] = 0;
+                first = b;
+                keep = 1;
+            }
+        }
+        sel[b] = keep;
+    }
+    hdr->best_utility = best;
+    hdr->count = 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -310,48 +447,82 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k_scan2(const Scan2Params P) 
 // ------------------------------------------------------------------------------------------------
 struct TieParams {
     const uint32_t *cnt0, *cnt1;
-    long long n_cols, col0, k_total, ubs;
+    const unsigned long long *segmax;   // [2][ld / 64]
+    long long n_cols, ld, col0, k_total, ubs;
     double inv_ubs, p;
     uint32_t n_pos, n_neg;
     const uint32_t *black_pres, *black_abs;
     const double *bm, *tol;        // per utility block: maximum and atol + rtol * |maximum|
     const uint8_t *sel;            // 1 = collect, 0 = skip
-    long long *out_idx;
-    uint32_t *out_pe, *out_nc;
-    unsigned long long *counter;
+    TieHeader *hdr;
+    TieRec *out;
     long long cap;
 };
+
+__device__ __forceinline__ bool tie_close(double u, double m, double tol) {
+    // numpy isclose(u, m): |u - m| <= atol + rtol*|m| and isfinite(m), or u == m
+    return (u == m) || (isfinite(m) && fabs(__dsub_rn(u, m)) <= tol);
+}
+
+// can the 64-column segment hold a tie?  If all its rules sit in one block: only if the block is
+// selected and the segment maximum itself is close to the block maximum (u <= segmax <= m and rounding
+// is monotonic, so no smaller u can be close when segmax is not).  Straddling segments are scanned.
+__device__ __forceinline__ bool seg_candidate(const TieParams &P, long long r0, long long r1, double smax) {
+    const long long b0 = fast_div(r0, P.ubs, P.inv_ubs), b1 = fast_div(r1, P.ubs, P.inv_ubs);
+    if (b0 != b1) return true;
+    return P.sel[b0] && tie_close(smax, P.bm[b0], P.tol[b0]);
+}
 
 __device__ __forceinline__ void tie_emit(const TieParams &P, long long rule, double u, uint32_t pe, uint32_t nc) {
     const long long b = fast_div(rule, P.ubs, P.inv_ubs);
     if (!P.sel[b]) return;
-    const double m = P.bm[b];
-    // numpy isclose(u, m): |u - m| <= atol + rtol*|m| and isfinite(m), or u == m
-    const bool close = (u == m) || (isfinite(m) && fabs(__dsub_rn(u, m)) <= P.tol[b]);
-    if (close) {
-        const unsigned long long slot = atomicAdd(P.counter, 1ull);
+    if (tie_close(u, P.bm[b], P.tol[b])) {
+        const unsigned long long slot = atomicAdd(&P.hdr->count, 1ull);
         if ((long long)slot < P.cap) {
-            P.out_idx[slot] = rule;
-            P.out_pe[slot] = pe;
-            P.out_nc[slot] = nc;
+            TieRec r;
+            r.idx = rule; r.pe = pe; r.nc = nc;
+            P.out[slot] = r;
         }
     }
 }
 
 __global__ void __launch_bounds__(256) k_scm_ties(const TieParams P) {
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long col = (long long)blockIdx.x * blockDim.x + threadIdx.x; col < P.n_cols; col += stride) {
-        const uint32_t c0 = P.cnt0[col], c1 = P.cnt1[col];
-        bool bp = false, ba = false;
-        if (P.black_pres) {
-            bp = (P.black_pres[col >> 5] >> (col & 31)) & 1u;
-            ba = (P.black_abs[col >> 5] >> (col & 31)) & 1u;
+    const int lane = threadIdx.x & 31;
+    const long long n_seg = (P.n_cols + 63) >> 6;
+    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long sb = warp0 * 32; sb < n_seg; sb += n_warps * 32) {
+        // each lane screens one segment; the warp then scans the candidates together
+        const long long g = sb + lane;
+        unsigned cand = 0;
+        if (g < n_seg) {
+            const long long c0 = g << 6, c1 = min(c0 + 63, P.n_cols - 1);
+            const double sp = dec_f64_max_dev(P.segmax[g]);
+            const double sa = dec_f64_max_dev(P.segmax[(P.ld >> 6) + g]);
+            if (seg_candidate(P, P.col0 + c0, P.col0 + c1, sp)) cand |= 1u;
+            if (seg_candidate(P, P.k_total + P.col0 + c0, P.k_total + P.col0 + c1, sa)) cand |= 2u;
         }
-        const uint32_t pe_p = P.n_pos - c0, nc_p = P.n_neg - c1;
-        const double up = bp ? -INFINITY : scm_utility(nc_p, pe_p, P.p);
-        const double ua = ba ? -INFINITY : scm_utility(c1, c0, P.p);
-        tie_emit(P, P.col0 + col, up, pe_p, nc_p);
-        tie_emit(P, P.k_total + P.col0 + col, ua, c0, c1);
+        unsigned todo = __ballot_sync(0xffffffffu, cand != 0);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const unsigned which = __shfl_sync(0xffffffffu, cand, src);
+            const long long cbase = (sb + src) << 6;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const long long col = cbase + lane + 32 * j;
+                if (col >= P.n_cols) continue;
+                const uint32_t c0 = P.cnt0[col], c1 = P.cnt1[col];
+                bool bp = false, ba = false;
+                if (P.black_pres) {
+                    bp = (P.black_pres[col >> 5] >> (col & 31)) & 1u;
+                    ba = (P.black_abs[col >> 5] >> (col & 31)) & 1u;
+                }
+                const uint32_t pe_p = P.n_pos - c0, nc_p = P.n_neg - c1;
+                if (which & 1u) tie_emit(P, P.col0 + col, bp ? -INFINITY : scm_utility(nc_p, pe_p, P.p), pe_p, nc_p);
+                if (which & 2u) tie_emit(P, P.k_total + P.col0 + col, ba ? -INFINITY : scm_utility(c1, c0, P.p), c0, c1);
+            }
+        }
     }
 }
 
@@ -601,6 +772,7 @@ struct kv_shard {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
     int scan_ctas_per_sm = 4;
+    int scan_variant = -1;                    // -1: choose per call; >= 0: forced (KOVER_B200_SCAN_VARIANT)
 
     std::vector<uint32_t *> d_cnt;            // count arrays, [ld] each
     DevBuf d_rec, d_misc, d_ties, d_stage;
@@ -612,6 +784,7 @@ struct kv_shard {
     int up_slot = 0;
 
     uint32_t *d_black_pres = nullptr, *d_black_abs = nullptr;
+    unsigned long long *d_segmax = nullptr;   // [2][ld / 64] segment maxima left by the last SCM scan
     bool have_black = false;
 
     // state left by the last scan for phase 2
@@ -701,8 +874,9 @@ extern "C" int kv_create(int device, int64_t n_examples, int64_t n_kmers_total, 
     s->k_total = n_kmers_total;
     s->col0 = col0;
     s->n_cols = n_cols;
-    s->n_tiles = (n_cols + TILE_COLS - 1) / TILE_COLS;
-    s->ld = s->n_tiles * TILE_COLS;
+    s->ld = (n_cols + LD_ALIGN - 1) / LD_ALIGN * LD_ALIGN;
+    s->n_tiles = s->ld / TILE_COLS;
+    if (const char *v = getenv("KOVER_B200_SCAN_VARIANT")) s->scan_variant = atoi(v);
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
     s->sm_count = prop.multiProcessorCount;
@@ -720,9 +894,6 @@ extern "C" int kv_create(int device, int64_t n_examples, int64_t n_kmers_total, 
     CU(cudaEventCreate(&s->ev_t1));
     CU(cudaMemsetAsync(s->d_mat, 0, bytes, s->stream));
     CU(cudaStreamSynchronize(s->stream));
-    // the scan kernels stage up to ~20 B per active packed row in shared memory
-    CU(cudaFuncSetAttribute(k_scan2<EPI_COUNTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    CU(cudaFuncSetAttribute(k_scan2<EPI_SCM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     *out = s;
     return KV_OK;
 }
@@ -737,6 +908,7 @@ extern "C" int kv_destroy(kv_shard *s) {
         if (b->p) cudaFree(b->p);
     if (s->d_black_pres) cudaFree(s->d_black_pres);
     if (s->d_black_abs) cudaFree(s->d_black_abs);
+    if (s->d_segmax) cudaFree(s->d_segmax);
     if (s->h_pin) cudaFreeHost(s->h_pin);
     for (int i = 0; i < 2; ++i) {
         if (s->h_up[i]) cudaFreeHost(s->h_up[i]);
@@ -930,19 +1102,21 @@ extern "C" int kv_inplace_popcount_32(int device, uint32_t *arr, int64_t m, int6
 // ------------------------------------------------------------------------------------------------
 // row records
 // ------------------------------------------------------------------------------------------------
-// Build the grouped active-row records for a mask pair in pinned memory and push them.
+// Build the active-row records for a mask pair in pinned memory and push them.  Rows are grouped
+// (only mask 0, only mask 1, both) so that consecutive rows of a stage take the same branches.
 // Layout in d_rec: m0[n_act] | m1[n_act] | row[n_act].
-static int push_records2(kv_shard *s, const uint64_t *m0, const uint64_t *m1, int &nA, int &nB, int &nC) {
+static int push_records2(kv_shard *s, const uint64_t *m0, const uint64_t *m1, int &n_act, int &n_both) {
     const long long W = s->W;
     KV_TRY(ensure_pinned(s, (size_t)W * 20 + 64));
-    nA = nB = nC = 0;
+    int nA = 0, nB = 0, nC = 0;
     for (long long w = 0; w < W; ++w) {
         const bool a = m0[w] != 0, b = m1 && m1[w] != 0;
         if (a && b) ++nC;
         else if (a) ++nA;
         else if (b) ++nB;
     }
-    const int n_act = nA + nB + nC;
+    n_act = nA + nB + nC;
+    n_both = nC;
     uint64_t *pm0 = (uint64_t *)s->h_pin, *pm1 = pm0 + n_act;
     uint32_t *prow = (uint32_t *)(pm1 + n_act);
     int iA = 0, iB = nA, iC = nA + nB;
@@ -962,26 +1136,89 @@ static int push_records2(kv_shard *s, const uint64_t *m0, const uint64_t *m1, in
     return KV_OK;
 }
 
-static void fill_scan2(kv_shard *s, Scan2Params &P, int nA, int nB, int nC) {
-    const int n_act = nA + nB + nC;
+static void fill_scan2(kv_shard *s, Scan2Params &P, int n_act) {
     memset(&P, 0, sizeof P);
     P.mat = s->d_mat;
     P.ld = s->ld;
     P.n_cols = s->n_cols;
     P.col0 = s->col0;
     P.k_total = s->k_total;
-    P.n_tiles = s->n_tiles;
     P.rec_m0 = (const uint64_t *)s->d_rec.p;
     P.rec_m1 = P.rec_m0 + n_act;
     P.rec_row = (const uint32_t *)(P.rec_m1 + n_act);
-    P.nA = nA;
-    P.nB = nB;
-    P.nC = nC;
+    P.n_act = n_act;
+    P.ubs = 1;
 }
 
 static int check_smem(size_t bytes) {
     if (bytes > 200 * 1024)
         return fail(KV_E_INVALID, "too many active packed rows for one scan (shared-memory staging limit)");
+    return KV_OK;
+}
+
+// Scan-kernel variants <consumer warps, rows per stage, stages, CTAs per SM>, measured on B200 by
+// tools/scan_sweep.cu (profiles/README.md): variant 0 is best when each packed row carries one
+// non-zero mask word (label-sorted datasets: 2 popc per streamed word), variant 1 when most rows
+// carry both (4 popc per word: more consumer warps to issue them).
+// X(id, consumer warps, rows per stage, stages, CTAs per SM)
+#define KV_SCAN_VARIANTS(X) \
+    X(0, 8, 4, 4, 2)        \
+    X(1, 16, 8, 3, 1)       \
+    X(2, 8, 4, 3, 3)        \
+    X(3, 8, 2, 8, 2)        \
+    X(4, 16, 4, 3, 2)       \
+    X(5, 16, 2, 4, 2)       \
+    X(6, 8, 8, 2, 2)        \
+    X(7, 8, 4, 6, 2)        \
+    X(8, 4, 4, 4, 4)        \
+    X(9, 16, 4, 6, 1)       \
+    X(10, 16, 4, 4, 1)      \
+    X(11, 8, 4, 2, 4)       \
+    X(12, 8, 4, 8, 1)       \
+    X(13, 12, 4, 4, 2)      \
+    X(14, 16, 8, 2, 2)      \
+    X(15, 8, 8, 3, 2)
+static constexpr int kNumScanVariants = 16;
+
+template <int EPI, int CW, int R, int S, int MINB>
+static int launch_scan_variant(kv_shard *s, const Scan2Params &P) {
+    const size_t smem = ((size_t)(2 * S) * 8 + (size_t)P.n_act * 20 + 127) / 128 * 128 + (size_t)S * R * CW * 512;
+    if (smem + 2048 > 227 * 1024)      // opt-in limit per CTA, minus static + driver-reserved shared memory
+        return fail(KV_E_INVALID, "too many active packed rows for one scan (shared-memory staging limit)");
+    static thread_local int attr_device = -1;
+    static thread_local size_t attr_bytes = 0;
+    if (attr_device != s->device || attr_bytes < smem) {   // per (instantiation, device)
+        CU(cudaFuncSetAttribute(k_scan_tma<EPI, CW, R, S, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_device = s->device;
+        attr_bytes = smem;
+    }
+    const long long n_tiles = s->ld / (CW * 64);
+    const int grid = (int)std::max(1ll, std::min<long long>((long long)s->sm_count * MINB, n_tiles));
+    k_scan_tma<EPI, CW, R, S, MINB><<<grid, (CW + 1) * 32, smem, s->stream>>>(P);
+    return KV_OK;
+}
+
+template <int EPI>
+static int launch_scan(kv_shard *s, const Scan2Params &P, int n_both) {
+    // Default: variant 1 (16 consumer warps, 8 rows x 8 KB per stage, 3 stages = 192 KB in flight per SM) --
+    // within 1 % of the best variant for label-sorted masks and the best when both masks hit every
+    // row (profiles/README.md).  With more than ~1500 active packed rows the mask staging no longer fits
+    // beside that ring: variant 10 (128 KB ring).
+    (void)n_both;
+    int v = s->scan_variant;
+    if (v < 0 || v >= kNumScanVariants) v = ((size_t)P.n_act * 20 > 30 * 1024) ? 10 : 1;
+    CU(cudaEventRecord(s->ev0, s->stream));
+    int rc = KV_OK;
+    switch (v) {
+#define KV_CASE(ID, CW_, R_, S_, MINB_) \
+    case ID: rc = launch_scan_variant<EPI, CW_, R_, S_, MINB_>(s, P); break;
+        KV_SCAN_VARIANTS(KV_CASE)
+#undef KV_CASE
+        default: return fail(KV_E_INVALID, "unknown scan variant");
+    }
+    KV_TRY(rc);
+    count_launch(s);
+    CU(cudaEventRecord(s->ev1, s->stream));
     return KV_OK;
 }
 
@@ -995,18 +1232,13 @@ extern "C" int kv_sum_rows(kv_shard *s, const uint64_t *mask, void *out, int out
     DeviceGuard g(s->device);
     s->last_launches = 0;
     KV_TRY(ensure_counts(s, 1));
-    int nA, nB, nC;
-    KV_TRY(push_records2(s, mask, nullptr, nA, nB, nC));
+    int n_act, n_both;
+    KV_TRY(push_records2(s, mask, nullptr, n_act, n_both));
     Scan2Params P;
-    fill_scan2(s, P, nA, nB, nC);
+    fill_scan2(s, P, n_act);
     P.cnt0 = s->d_cnt[0];
     P.cnt1 = nullptr;
-    const size_t smem = (size_t)(nA + nB + nC) * 20 + 16;
-    KV_TRY(check_smem(smem));
-    CU(cudaEventRecord(s->ev0, s->stream));
-    k_scan2<EPI_COUNTS><<<scan_grid(s), SCAN_THREADS, smem, s->stream>>>(P);
-    count_launch(s);
-    CU(cudaEventRecord(s->ev1, s->stream));
+    KV_TRY(launch_scan<EPI_COUNTS>(s, P, n_both));
     s->scm_valid = s->gini_valid = false;
     if (out_itemsize == 4) {
         CU(cudaMemcpyAsync(out, s->d_cnt[0], (size_t)s->n_cols * 4, cudaMemcpyDeviceToHost, s->stream));
@@ -1167,12 +1399,11 @@ extern "C" int64_t kv_scm_n_blocks(int64_t n_kmers_total, int64_t util_block_siz
     return (2 * n_kmers_total + util_block_size - 1) / util_block_size;
 }
 
-// d_misc layout: blockmax enc [n_blocks] | bm f64 [n_blocks] | tol f64 [n_blocks] | sel u8 [n_blocks] | counter
+// d_misc layout: blockmax enc [n_blocks] | bm f64 [n_blocks] | tol f64 [n_blocks] | sel u8 [n_blocks]
 struct MiscLayout {
     unsigned long long *blockmax;
     double *bm, *tol;
     uint8_t *sel;
-    unsigned long long *counter;
     size_t bytes;
 };
 static MiscLayout misc_layout(void *base, long long n_blocks) {
@@ -1181,10 +1412,15 @@ static MiscLayout misc_layout(void *base, long long n_blocks) {
     L.blockmax = (unsigned long long *)p; p += (size_t)n_blocks * 8;
     L.bm = (double *)p; p += (size_t)n_blocks * 8;
     L.tol = (double *)p; p += (size_t)n_blocks * 8;
-    L.counter = (unsigned long long *)p; p += 16;
     L.sel = (uint8_t *)p; p += ((size_t)n_blocks + 15) / 16 * 16;
     L.bytes = (size_t)(p - (char *)base);
     return L;
+}
+
+static constexpr long long kTieFirstBatch = 2048;   // tie records fetched together with the header
+
+static int ensure_ties(kv_shard *s, long long cap) {
+    return ensure(s->d_ties, sizeof(TieHeader) + (size_t)std::max<long long>(cap, kTieFirstBatch) * sizeof(TieRec));
 }
 
 static int scm_scan_async(kv_shard *s, const uint64_t *pos_mask, const uint64_t *neg_mask, int64_t n_pos, int64_t n_neg,
@@ -1194,14 +1430,15 @@ static int scm_scan_async(kv_shard *s, const uint64_t *pos_mask, const uint64_t 
     if (ubs <= 0) return fail(KV_E_INVALID, "kv_scm_scan: util_block_size must be positive");
     if (n_blocks != kv_scm_n_blocks(s->k_total, ubs)) return fail(KV_E_INVALID, "kv_scm_scan: wrong n_blocks");
     KV_TRY(ensure_counts(s, 2));
-    int nA, nB, nC;
-    KV_TRY(push_records2(s, pos_mask, neg_mask, nA, nB, nC));
+    if (!s->d_segmax) CU(cudaMalloc(&s->d_segmax, (size_t)(s->ld / 64) * 2 * 8));
+    int n_act, n_both;
+    KV_TRY(push_records2(s, pos_mask, neg_mask, n_act, n_both));
     MiscLayout L0 = misc_layout(nullptr, n_blocks);
     KV_TRY(ensure(s->d_misc, L0.bytes));
     MiscLayout L = misc_layout(s->d_misc.p, n_blocks);
     CU(cudaMemsetAsync(L.blockmax, 0, (size_t)n_blocks * 8, s->stream));
     Scan2Params P;
-    fill_scan2(s, P, nA, nB, nC);
+    fill_scan2(s, P, n_act);
     P.cnt0 = s->d_cnt[0];
     P.cnt1 = s->d_cnt[1];
     P.p = p;
@@ -1211,12 +1448,8 @@ static int scm_scan_async(kv_shard *s, const uint64_t *pos_mask, const uint64_t 
     P.black_pres = s->have_black ? s->d_black_pres : nullptr;
     P.black_abs = s->have_black ? s->d_black_abs : nullptr;
     P.blockmax = L.blockmax;
-    const size_t smem = (size_t)(nA + nB + nC) * 20 + 16;
-    KV_TRY(check_smem(smem));
-    CU(cudaEventRecord(s->ev0, s->stream));
-    k_scan2<EPI_SCM><<<scan_grid(s), SCAN_THREADS, smem, s->stream>>>(P);
-    count_launch(s);
-    CU(cudaEventRecord(s->ev1, s->stream));
+    P.segmax = s->d_segmax;
+    KV_TRY(launch_scan<EPI_SCM>(s, P, n_both));
     s->scm_valid = true;
     s->gini_valid = false;
     s->scm_n_pos = n_pos;
@@ -1247,12 +1480,15 @@ extern "C" int kv_scm_scan(kv_shard *s, const uint64_t *pos_mask, const uint64_t
 
 // numpy.isclose(a, b) for scalars, rtol=1e-5, atol=1e-8 (numpy 2.3: |a-b| <= atol + rtol*|b| and
 // isfinite(b), or a == b).  Compiled with -ffp-contract=off: one rounded multiply, one rounded add.
+static inline double np_tol(double b) {
+    volatile double t = 1e-5 * std::fabs(b);
+    volatile double tol = 1e-8 + t;
+    return tol;
+}
 static inline bool np_isclose(double a, double b) {
     if (a == b) return true;
     if (!std::isfinite(b)) return false;
-    volatile double t = 1e-5 * std::fabs(b);
-    volatile double tol = 1e-8 + t;
-    return std::fabs(a - b) <= tol;
+    return std::fabs(a - b) <= np_tol(b);
 }
 
 extern "C" int kv_scm_select_blocks(const double *block_max, int64_t n_blocks, double *best_utility,
@@ -1277,41 +1513,21 @@ extern "C" int kv_scm_select_blocks(const double *block_max, int64_t n_blocks, d
     return KV_OK;
 }
 
-struct TieRec {
-    long long idx;
-    uint32_t pe, nc;
-};
-
-static int scm_ties_impl(kv_shard *s, const double *block_max, const uint8_t *selected, int64_t n_blocks,
-                         int64_t capacity, int64_t *rule_idx, int64_t *pos_err, int64_t *neg_cover, int64_t *n_found) {
-    if (!s->scm_valid) return fail(KV_E_INVALID, "kv_scm_ties: no SCM scan result on the device");
-    if (n_blocks != kv_scm_n_blocks(s->k_total, s->scm_ubs)) return fail(KV_E_INVALID, "kv_scm_ties: wrong n_blocks");
-    if (capacity < 0) return fail(KV_E_INVALID, "kv_scm_ties: negative capacity");
+// Launch k_scm_ties on the block tables already in d_misc, then bring header + records back with as
+// few round trips as possible and sort by rule index (the kernel appends in arbitrary order; the
+// reference's order is ascending rule index, scm.py:273-280).
+static int scm_collect_ties(kv_shard *s, int64_t n_blocks, int64_t capacity, double *best_utility, int64_t *rule_idx,
+                            int64_t *pos_err, int64_t *neg_cover, int64_t *n_found) {
     MiscLayout L = misc_layout(s->d_misc.p, n_blocks);
-    // block table -> pinned -> device
-    const size_t tab_bytes = (size_t)n_blocks * 16 + 16 + ((size_t)n_blocks + 15) / 16 * 16;
-    KV_TRY(ensure_pinned(s, tab_bytes));
-    {
-        double *bm = (double *)s->h_pin, *tol = bm + n_blocks;
-        unsigned long long *cnt = (unsigned long long *)(tol + n_blocks);
-        uint8_t *sel = (uint8_t *)(cnt + 2);
-        for (int64_t b = 0; b < n_blocks; ++b) {
-            bm[b] = block_max[b];
-            volatile double t = 1e-5 * std::fabs(block_max[b]);
-            volatile double tl = 1e-8 + t;
-            tol[b] = tl;
-            sel[b] = selected[b];
-        }
-        cnt[0] = cnt[1] = 0;
-        CU(cudaMemcpyAsync(L.bm, s->h_pin, tab_bytes, cudaMemcpyHostToDevice, s->stream));
-    }
-    const long long cap = std::max<long long>(capacity, 1);
-    KV_TRY(ensure(s->d_ties, (size_t)cap * 16));
+    TieHeader *d_hdr = (TieHeader *)s->d_ties.p;
+    TieRec *d_rec = (TieRec *)(d_hdr + 1);
     TieParams T;
     memset(&T, 0, sizeof T);
     T.cnt0 = s->d_cnt[0];
     T.cnt1 = s->d_cnt[1];
+    T.segmax = s->d_segmax;
     T.n_cols = s->n_cols;
+    T.ld = s->ld;
     T.col0 = s->col0;
     T.k_total = s->k_total;
     T.ubs = s->scm_ubs;
@@ -1324,33 +1540,32 @@ static int scm_ties_impl(kv_shard *s, const double *block_max, const uint8_t *se
     T.bm = L.bm;
     T.tol = L.tol;
     T.sel = L.sel;
-    T.out_idx = (long long *)s->d_ties.p;
-    T.out_pe = (uint32_t *)((char *)s->d_ties.p + (size_t)cap * 8);
-    T.out_nc = T.out_pe + cap;
-    T.counter = L.counter;
-    T.cap = capacity;
-    const unsigned grid = (unsigned)std::min<long long>((s->n_cols + 255) / 256, (long long)s->sm_count * 8);
+    T.hdr = d_hdr;
+    T.out = d_rec;
+    T.cap = std::max<long long>(capacity, kTieFirstBatch);     // device buffer holds at least the first batch
+    const long long n_seg = (s->n_cols + 63) / 64;
+    const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((n_seg + 255) / 256, (long long)s->sm_count * 4));
     k_scm_ties<<<grid, 256, 0, s->stream>>>(T);
     count_launch(s);
-    // counter + (optimistically) the first few ties in one round trip
-    CU(cudaMemcpyAsync(s->h_pin, L.counter, 8, cudaMemcpyDeviceToHost, s->stream));
+    const size_t first_bytes = sizeof(TieHeader) + (size_t)kTieFirstBatch * sizeof(TieRec);
+    KV_TRY(ensure_pinned(s, first_bytes));
+    CU(cudaMemcpyAsync(s->h_pin, d_hdr, first_bytes, cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
     CU(cudaGetLastError());
-    const long long found = (long long)*(unsigned long long *)s->h_pin;
+    const TieHeader hdr = *(const TieHeader *)s->h_pin;
+    const long long found = (long long)hdr.count;
     *n_found = found;
-    if (found > capacity) return fail(KV_E_OVERFLOW, "kv_scm_ties: tie buffer too small");
+    if (best_utility) *best_utility = hdr.best_utility;
+    if (found > capacity) return fail(KV_E_OVERFLOW, "tie buffer too small");
     if (found == 0) return KV_OK;
-    KV_TRY(ensure_pinned(s, (size_t)found * 16));
-    char *hp = (char *)s->h_pin;
-    CU(cudaMemcpyAsync(hp, T.out_idx, (size_t)found * 8, cudaMemcpyDeviceToHost, s->stream));
-    CU(cudaMemcpyAsync(hp + (size_t)found * 8, T.out_pe, (size_t)found * 4, cudaMemcpyDeviceToHost, s->stream));
-    CU(cudaMemcpyAsync(hp + (size_t)found * 12, T.out_nc, (size_t)found * 4, cudaMemcpyDeviceToHost, s->stream));
-    CU(cudaStreamSynchronize(s->stream));
-    const long long *h_idx = (const long long *)hp;
-    const uint32_t *h_pe = (const uint32_t *)(hp + (size_t)found * 8), *h_nc = h_pe + found;
-    std::vector<TieRec> recs((size_t)found);
-    for (long long i = 0; i < found; ++i) recs[i] = {h_idx[i], h_pe[i], h_nc[i]};
-    std::sort(recs.begin(), recs.end(), [](const TieRec &a, const TieRec &b) { return a.idx < b.idx; });
+    if (found > kTieFirstBatch) {
+        KV_TRY(ensure_pinned(s, sizeof(TieHeader) + (size_t)found * sizeof(TieRec)));
+        CU(cudaMemcpyAsync(s->h_pin, d_hdr, sizeof(TieHeader) + (size_t)found * sizeof(TieRec), cudaMemcpyDeviceToHost,
+                           s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+    }
+    TieRec *recs = (TieRec *)((TieHeader *)s->h_pin + 1);
+    std::sort(recs, recs + found, [](const TieRec &a, const TieRec &b) { return a.idx < b.idx; });
     for (long long i = 0; i < found; ++i) {
         rule_idx[i] = recs[i].idx;
         pos_err[i] = recs[i].pe;
@@ -1364,30 +1579,55 @@ extern "C" int kv_scm_ties(kv_shard *s, const double *block_max, const uint8_t *
                            int64_t *n_found) {
     if (!s || !block_max || !selected || !n_found || (capacity > 0 && (!rule_idx || !pos_err || !neg_cover)))
         return fail(KV_E_INVALID, "kv_scm_ties: null pointer");
+    if (!s->scm_valid) return fail(KV_E_INVALID, "kv_scm_ties: no SCM scan result on the device");
+    if (n_blocks != kv_scm_n_blocks(s->k_total, s->scm_ubs)) return fail(KV_E_INVALID, "kv_scm_ties: wrong n_blocks");
+    if (capacity < 0) return fail(KV_E_INVALID, "kv_scm_ties: negative capacity");
     DeviceGuard g(s->device);
     s->last_launches = 0;
-    return scm_ties_impl(s, block_max, selected, n_blocks, capacity, rule_idx, pos_err, neg_cover, n_found);
+    // merged block table (host) -> pinned -> device: bm | tol | sel are contiguous in d_misc
+    MiscLayout L = misc_layout(s->d_misc.p, n_blocks);
+    const size_t tab_bytes = (size_t)n_blocks * 16 + ((size_t)n_blocks + 15) / 16 * 16;
+    KV_TRY(ensure_pinned(s, tab_bytes + sizeof(TieHeader)));
+    double *bm = (double *)s->h_pin, *tol = bm + n_blocks;
+    uint8_t *sel = (uint8_t *)(tol + n_blocks);
+    for (int64_t b = 0; b < n_blocks; ++b) {
+        bm[b] = block_max[b];
+        tol[b] = np_tol(block_max[b]);
+        sel[b] = selected[b];
+    }
+    TieHeader *h_hdr = (TieHeader *)((char *)s->h_pin + tab_bytes);
+    memset(h_hdr, 0, sizeof(TieHeader));
+    KV_TRY(ensure_ties(s, capacity));
+    CU(cudaMemcpyAsync(L.bm, s->h_pin, tab_bytes, cudaMemcpyHostToDevice, s->stream));
+    CU(cudaMemcpyAsync(s->d_ties.p, h_hdr, sizeof(TieHeader), cudaMemcpyHostToDevice, s->stream));
+    // the pinned buffer is reused for the results below
+    CU(cudaStreamSynchronize(s->stream));
+    return scm_collect_ties(s, n_blocks, capacity, nullptr, rule_idx, pos_err, neg_cover, n_found);
 }
 
 extern "C" int kv_scm_best_rules(kv_shard *s, const uint64_t *pos_mask, const uint64_t *neg_mask, int64_t n_pos,
                                  int64_t n_neg, double p, int64_t util_block_size, double *best_utility,
                                  int64_t capacity, int64_t *rule_idx, int64_t *pos_err, int64_t *neg_cover,
                                  int64_t *n_found) {
-    if (!s || !pos_mask || !neg_mask || !best_utility || !n_found) return fail(KV_E_INVALID, "kv_scm_best_rules: null pointer");
+    if (!s || !pos_mask || !neg_mask || !best_utility || !n_found ||
+        (capacity > 0 && (!rule_idx || !pos_err || !neg_cover)))
+        return fail(KV_E_INVALID, "kv_scm_best_rules: null pointer");
     if (s->col0 != 0 || s->n_cols != s->k_total)
         return fail(KV_E_INVALID, "kv_scm_best_rules: single-shard call on a partial shard; use scan/select/ties");
+    if (capacity < 0) return fail(KV_E_INVALID, "kv_scm_best_rules: negative capacity");
     const int64_t n_blocks = kv_scm_n_blocks(s->k_total, util_block_size);
     if (n_blocks <= 0) return fail(KV_E_INVALID, "kv_scm_best_rules: util_block_size must be positive");
-    std::vector<double> bm((size_t)n_blocks);
-    std::vector<uint8_t> sel((size_t)n_blocks);
-    KV_TRY(kv_scm_scan(s, pos_mask, neg_mask, n_pos, n_neg, p, util_block_size, bm.data(), n_blocks));
-    const double scan_ms = s->last_kernel_ms;
-    const long long scan_launches = s->last_launches;
-    KV_TRY(kv_scm_select_blocks(bm.data(), n_blocks, best_utility, sel.data()));
     DeviceGuard g(s->device);
-    int rc = scm_ties_impl(s, bm.data(), sel.data(), n_blocks, capacity, rule_idx, pos_err, neg_cover, n_found);
-    s->last_kernel_ms = scan_ms;
-    (void)scan_launches;
+    s->last_launches = 0;
+    // scan -> device-side block merge -> tie collection, one host synchronisation for the whole call
+    KV_TRY(ensure_ties(s, capacity));
+    KV_TRY(scm_scan_async(s, pos_mask, neg_mask, n_pos, n_neg, p, util_block_size, n_blocks));
+    MiscLayout L = misc_layout(s->d_misc.p, n_blocks);
+    k_scm_select<<<1, 32, 0, s->stream>>>(L.blockmax, n_blocks, L.bm, L.tol, L.sel, (TieHeader *)s->d_ties.p);
+    count_launch(s);
+    const int rc = scm_collect_ties(s, n_blocks, capacity, best_utility, rule_idx, pos_err, neg_cover, n_found);
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, s->ev0, s->ev1) == cudaSuccess) s->last_kernel_ms = ms;
     return rc;
 }
 
@@ -1418,18 +1658,13 @@ extern "C" int kv_gini_scan(kv_shard *s, int n_classes, const uint64_t *class_ma
     if (n_classes == 2) {
         // two disjoint class masks: the grouped two-mask scan reads each packed row once
         KV_TRY(ensure_counts(s, 2));
-        int nA, nB, nC;
-        KV_TRY(push_records2(s, class_masks, class_masks + s->W, nA, nB, nC));
+        int n_act, n_both;
+        KV_TRY(push_records2(s, class_masks, class_masks + s->W, n_act, n_both));
         Scan2Params P;
-        fill_scan2(s, P, nA, nB, nC);
+        fill_scan2(s, P, n_act);
         P.cnt0 = s->d_cnt[0];
         P.cnt1 = s->d_cnt[1];
-        const size_t smem = (size_t)(nA + nB + nC) * 20 + 16;
-        KV_TRY(check_smem(smem));
-        CU(cudaEventRecord(s->ev0, s->stream));
-        k_scan2<EPI_COUNTS><<<scan_grid(s), SCAN_THREADS, smem, s->stream>>>(P);
-        count_launch(s);
-        CU(cudaEventRecord(s->ev1, s->stream));
+        KV_TRY(launch_scan<EPI_COUNTS>(s, P, n_both));
     } else {
         KV_TRY(count_masks(s, n_classes, class_masks, 0));
     }

@@ -236,8 +236,8 @@ class KmerRuleClassifications(BaseRuleClassifications):
 
     def row_mask(self, rows):
         """64-bit row mask over the packed rows for example indices ``rows`` (rules.py:210-239)."""
-        return build_row_mask(self._dataset_relative_rows(np.sort(np.asarray(rows))),
-                              self.dataset_initial_n_rows, 64)
+        # (the reference sorts `rows` first, rules.py:225; the mask does not depend on the order)
+        return build_row_mask(self._dataset_relative_rows(rows), self.dataset_initial_n_rows, 64)
 
     def sum_rows(self, rows):
         """

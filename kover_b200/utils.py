@@ -70,14 +70,14 @@ def build_row_mask(example_idx, n_examples, mask_n_bits):
         raise ValueError("Unsupported mask format. Use 8, 16, 32, 64 or 128 bits.")
     if mask_n_bits == 128:
         raise ValueError("128-bit masks have no numpy dtype.")
-    t = np.dtype("u%d" % (mask_n_bits // 8)).type
+    nbytes = mask_n_bits // 8
     n_masks = int(ceil(float(n_examples) / mask_n_bits))
-    masks = np.zeros(n_masks, dtype=t)
     idx = np.asarray(example_idx, dtype=np.int64).reshape(-1)
+    bits = np.zeros(n_masks * mask_n_bits, dtype=np.uint8)
     if idx.size:
-        if idx.min() < 0 or idx.max() >= n_masks * mask_n_bits:
+        if idx.min() < 0 or idx.max() >= bits.shape[0]:
             raise IndexError("list index out of range")
-        words = idx // mask_n_bits
-        bits = np.left_shift(t(1), (mask_n_bits - 1 - (idx - words * mask_n_bits)).astype(t))
-        np.bitwise_or.at(masks, words, bits)
+        bits[idx] = 1
+    # packbits is MSB-first, so example i lands on bit mask_n_bits-1-(i % mask_n_bits) of word i // mask_n_bits
+    masks = np.packbits(bits).view(">u%d" % nbytes).astype("u%d" % nbytes)
     return masks
