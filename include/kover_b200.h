@@ -53,6 +53,8 @@ typedef struct kv_shard_info {
     double last_kernel_ms;   /* CUDA-event time of the scan kernel of the last scan call */
     int64_t last_launches;   /* kernels launched by the last call                        */
     int64_t total_launches;  /* kernels launched since kv_create                         */
+    double scan_ms_total;    /* sum of the scan kernels' CUDA-event times since kv_create */
+    int64_t scan_calls;      /* SCM scans since kv_create                                */
 } kv_shard_info;
 
 const char *kv_last_error(void);
@@ -134,6 +136,19 @@ int kv_scm_select_blocks(const double *block_max, int64_t n_blocks, double *best
 int kv_scm_ties(kv_shard *s, const double *block_max, const uint8_t *selected, int64_t n_blocks,
                 int64_t capacity, int64_t *rule_idx, int64_t *pos_err, int64_t *neg_cover,
                 int64_t *n_found);
+/* Multi-rank, one exchange per scan: phase 1 plus a LOCAL superset of the ties, written as one packet
+ *   double block_max[n_blocks] | uint64 count | double threshold | {int64 rule, uint32 pos_err,
+ *   uint32 neg_cover} records[capacity]
+ * (records of blacklisted rules carry bit 62 of `rule`).  Every rule that can survive the merge over
+ * ranks has u >= local_max - 5 * (1e-8 + 1e-5 * |local_max|), so the ranks all-gather their packets
+ * once and finish on the host (max-merge, kv_scm_select_blocks, exact isclose filter).  count >
+ * capacity means the packet is truncated: fall back to kv_scm_scan / kv_scm_ties.  `packet` is host
+ * memory, or -- packet_on_device = 1, the one device pointer in this ABI -- memory on the shard's
+ * GPU (e.g. the torch tensor handed to NCCL); the call returns after the stream has drained. */
+int64_t kv_scm_packet_bytes(int64_t n_blocks, int64_t capacity);
+int kv_scm_scan_packet(kv_shard *s, const uint64_t *pos_mask, const uint64_t *neg_mask, int64_t n_pos,
+                       int64_t n_neg, double p, int64_t util_block_size, int64_t n_blocks, int64_t capacity,
+                       void *packet, int packet_on_device);
 /* Single-shard convenience: scan + select + ties in one call. */
 int kv_scm_best_rules(kv_shard *s, const uint64_t *pos_mask, const uint64_t *neg_mask, int64_t n_pos,
                       int64_t n_neg, double p, int64_t util_block_size, double *best_utility,

@@ -22,7 +22,8 @@ class ShardInfo(ctypes.Structure):
     _fields_ = [("device", ctypes.c_int32), ("sm_count", ctypes.c_int32), ("n_examples", _c_i64),
                 ("n_words", _c_i64), ("n_kmers_total", _c_i64), ("col0", _c_i64), ("n_cols", _c_i64),
                 ("ld", _c_i64), ("matrix_bytes", _c_i64), ("last_kernel_ms", ctypes.c_double),
-                ("last_launches", _c_i64), ("total_launches", _c_i64)]
+                ("last_launches", _c_i64), ("total_launches", _c_i64), ("scan_ms_total", ctypes.c_double),
+                ("scan_calls", _c_i64)]
 
 
 # every exported symbol with (restype, argtypes); tests/test_abi.py checks this table against the header
@@ -48,6 +49,9 @@ SYMBOLS = {
     "kv_scm_scan": (ctypes.c_int, [_c_p, _c_p, _c_p, _c_i64, _c_i64, ctypes.c_double, _c_i64, _c_p, _c_i64]),
     "kv_scm_select_blocks": (ctypes.c_int, [_c_p, _c_i64, ctypes.POINTER(ctypes.c_double), _c_p]),
     "kv_scm_ties": (ctypes.c_int, [_c_p, _c_p, _c_p, _c_i64, _c_i64, _c_p, _c_p, _c_p, ctypes.POINTER(_c_i64)]),
+    "kv_scm_packet_bytes": (_c_i64, [_c_i64, _c_i64]),
+    "kv_scm_scan_packet": (ctypes.c_int, [_c_p, _c_p, _c_p, _c_i64, _c_i64, ctypes.c_double, _c_i64, _c_i64, _c_i64,
+                                          _c_p, ctypes.c_int]),
     "kv_scm_best_rules": (ctypes.c_int, [_c_p, _c_p, _c_p, _c_i64, _c_i64, ctypes.c_double, _c_i64,
                                          ctypes.POINTER(ctypes.c_double), _c_i64, _c_p, _c_p, _c_p,
                                          ctypes.POINTER(_c_i64)]),
@@ -234,6 +238,22 @@ class Shard(object):
             check(rc)
             return idx[:n.value], pe[:n.value], nc[:n.value]
 
+    def scm_scan_packet(self, pos_mask, neg_mask, n_pos, n_neg, p, util_block_size, capacity, packet):
+        """Fill ``packet`` (a torch uint8 tensor on this shard's GPU, or a host numpy uint8 array) with the block
+        maxima + local tie candidates of one scan (kv_scm_scan_packet)."""
+        pos_mask = np.ascontiguousarray(pos_mask, dtype=np.uint64)
+        neg_mask = np.ascontiguousarray(neg_mask, dtype=np.uint64)
+        nb = n_utility_blocks(self.n_kmers_total, util_block_size)
+        need = packet_bytes(nb, capacity)
+        if isinstance(packet, np.ndarray):
+            assert packet.dtype == np.uint8 and packet.size >= need and packet.flags.c_contiguous
+            addr, on_device = packet.ctypes.data, 0
+        else:
+            assert packet.numel() * packet.element_size() >= need and packet.is_contiguous()
+            addr, on_device = packet.data_ptr(), int(packet.is_cuda)
+        check(self._lib.kv_scm_scan_packet(self._h, ptr(pos_mask), ptr(neg_mask), int(n_pos), int(n_neg), float(p),
+                                           int(util_block_size), nb, int(capacity), ctypes.c_void_p(addr), on_device))
+
     def scm_best_rules(self, pos_mask, neg_mask, n_pos, n_neg, p, util_block_size, capacity=4096):
         pos_mask = np.ascontiguousarray(pos_mask, dtype=np.uint64)
         neg_mask = np.ascontiguousarray(neg_mask, dtype=np.uint64)
@@ -287,6 +307,23 @@ class Shard(object):
 
 def n_utility_blocks(n_kmers_total, util_block_size):
     return int(load().kv_scm_n_blocks(int(n_kmers_total), int(util_block_size)))
+
+
+def packet_bytes(n_blocks, capacity):
+    return int(load().kv_scm_packet_bytes(int(n_blocks), int(capacity)))
+
+
+TIE_FLAG_NEG_INF = 1 << 62
+PACKET_REC_DTYPE = np.dtype([("idx", "<i8"), ("pe", "<u4"), ("nc", "<u4")])
+
+
+def parse_packet(buf, n_blocks, capacity):
+    """buf: uint8 [packet_bytes] -> (block_max f64[n_blocks], count, threshold, records[min(count, capacity)])."""
+    bm = buf[:8 * n_blocks].view(np.float64)
+    count = int(buf[8 * n_blocks:8 * n_blocks + 8].view(np.uint64)[0])
+    thr = float(buf[8 * n_blocks + 8:8 * n_blocks + 16].view(np.float64)[0])
+    recs = buf[8 * n_blocks + 16:8 * n_blocks + 16 + 16 * capacity].view(PACKET_REC_DTYPE)
+    return bm, count, thr, recs[:min(count, capacity)]
 
 
 def select_blocks(block_max):

@@ -416,14 +416,32 @@ struct TieRec {
     uint32_t pe, nc;
 };
 
-__global__ void k_scm_select(const unsigned long long *blockmax, long long n_blocks, double *bm, double *tol,
-                             uint8_t *sel, TieHeader *hdr) {
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+// Both select kernels run as ONE warp: the lanes fetch + decode the block maxima in parallel (and zero
+// the accumulators for the next scan), lane 0 then walks them in shared memory.
+static constexpr int SELECT_SMEM_BLOCKS = 2048;
+
+__device__ __forceinline__ const double *select_prologue(unsigned long long *blockmax, long long n_blocks, double *bm,
+                                                         double *s_bm) {
+    const bool in_smem = n_blocks <= SELECT_SMEM_BLOCKS;
+    for (long long b = threadIdx.x; b < n_blocks; b += 32) {
+        const double m = dec_f64_max_dev(blockmax[b]);
+        blockmax[b] = 0ull;
+        bm[b] = m;
+        if (in_smem) s_bm[b] = m;
+    }
+    __syncwarp();
+    return in_smem ? s_bm : bm;
+}
+
+__global__ void __launch_bounds__(32) k_scm_select(unsigned long long *blockmax, long long n_blocks, double *bm,
+                                                   double *tol, uint8_t *sel, TieHeader *hdr) {
+    __shared__ double s_bm[SELECT_SMEM_BLOCKS];
+    const double *v = select_prologue(blockmax, n_blocks, bm, s_bm);
+    if (threadIdx.x != 0) return;
     double best = -INFINITY;
     long long first = 0;                       // blocks before `first` are deselected
     for (long long b = 0; b < n_blocks; ++b) {
-        const double m = dec_f64_max_dev(blockmax[b]);
-        bm[b] = m;
+        const double m = v[b];
         tol[b] = np_tol_dev(m);
         uint8_t keep = 0;
         if (m > best || np_isclose_dev(best, m)) {
@@ -442,6 +460,25 @@ __global__ void k_scm_select(const unsigned long long *blockmax, long long n_blo
     hdr->count = 0;
 }
 
+// Multi-rank variant: this rank only knows ITS block maxima.  Every rule that can survive the global
+// merge has u >= Gmax - ~3*T(Gmax) with T(x) = 1e-8 + 1e-5*|x| and Gmax >= Lmax (the local maximum),
+// and x - c*T(x) is increasing, so u >= Lmax - 5*T(Lmax) is a superset criterion that needs no
+// exchange.  The exact filter runs on the host after the gather.
+struct PacketHeader {            // follows the n_blocks doubles in the packet
+    unsigned long long count;
+    double threshold;
+};
+__global__ void __launch_bounds__(32) k_scm_select_local(unsigned long long *blockmax, long long n_blocks,
+                                                         double *packet_bm, PacketHeader *hdr) {
+    __shared__ double s_bm[SELECT_SMEM_BLOCKS];
+    const double *v = select_prologue(blockmax, n_blocks, packet_bm, s_bm);
+    if (threadIdx.x != 0) return;
+    double lmax = -INFINITY;
+    for (long long b = 0; b < n_blocks; ++b) lmax = fmax(lmax, v[b]);
+    hdr->count = 0;
+    hdr->threshold = isfinite(lmax) ? lmax - 5.0 * np_tol_dev(lmax) : -INFINITY;
+}
+
 // ------------------------------------------------------------------------------------------------
 // k_scm_ties: rules of the selected utility blocks whose utility is isclose to the block maximum
 // ------------------------------------------------------------------------------------------------
@@ -454,10 +491,12 @@ struct TieParams {
     const uint32_t *black_pres, *black_abs;
     const double *bm, *tol;        // per utility block: maximum and atol + rtol * |maximum|
     const uint8_t *sel;            // 1 = collect, 0 = skip
-    TieHeader *hdr;
+    unsigned long long *count;     // tie counter (TieHeader::count or PacketHeader::count)
+    const double *threshold;       // candidate mode (multi-rank): emit every rule with u >= *threshold
     TieRec *out;
     long long cap;
 };
+static constexpr long long TIE_FLAG_NEG_INF = 1ll << 62;   // candidate record of a blacklisted rule (u = -inf)
 
 __device__ __forceinline__ bool tie_close(double u, double m, double tol) {
     // numpy isclose(u, m): |u - m| <= atol + rtol*|m| and isfinite(m), or u == m
@@ -468,21 +507,25 @@ __device__ __forceinline__ bool tie_close(double u, double m, double tol) {
 // selected and the segment maximum itself is close to the block maximum (u <= segmax <= m and rounding
 // is monotonic, so no smaller u can be close when segmax is not).  Straddling segments are scanned.
 __device__ __forceinline__ bool seg_candidate(const TieParams &P, long long r0, long long r1, double smax) {
+    if (P.threshold) return smax >= *P.threshold;
     const long long b0 = fast_div(r0, P.ubs, P.inv_ubs), b1 = fast_div(r1, P.ubs, P.inv_ubs);
     if (b0 != b1) return true;
     return P.sel[b0] && tie_close(smax, P.bm[b0], P.tol[b0]);
 }
 
 __device__ __forceinline__ void tie_emit(const TieParams &P, long long rule, double u, uint32_t pe, uint32_t nc) {
-    const long long b = fast_div(rule, P.ubs, P.inv_ubs);
-    if (!P.sel[b]) return;
-    if (tie_close(u, P.bm[b], P.tol[b])) {
-        const unsigned long long slot = atomicAdd(&P.hdr->count, 1ull);
-        if ((long long)slot < P.cap) {
-            TieRec r;
-            r.idx = rule; r.pe = pe; r.nc = nc;
-            P.out[slot] = r;
-        }
+    if (P.threshold) {
+        if (!(u >= *P.threshold)) return;
+        if (u == -INFINITY) rule |= TIE_FLAG_NEG_INF;
+    } else {
+        const long long b = fast_div(rule, P.ubs, P.inv_ubs);
+        if (!P.sel[b] || !tie_close(u, P.bm[b], P.tol[b])) return;
+    }
+    const unsigned long long slot = atomicAdd(P.count, 1ull);
+    if ((long long)slot < P.cap) {
+        TieRec r;
+        r.idx = rule; r.pe = pe; r.nc = nc;
+        P.out[slot] = r;
     }
 }
 
@@ -794,8 +837,8 @@ struct kv_shard {
     bool gini_valid = false;
     GiniParams gini;
 
-    double last_kernel_ms = 0.0;
-    long long last_launches = 0, total_launches = 0;
+    double last_kernel_ms = 0.0, scan_ms_total = 0.0;
+    long long last_launches = 0, total_launches = 0, scan_calls = 0;
 };
 
 struct DeviceGuard {
@@ -817,6 +860,7 @@ static int ensure(DevBuf &b, size_t bytes) {
     b.bytes = 0;
     size_t want = std::max(bytes, (size_t)4096);
     CU(cudaMalloc(&b.p, want));
+    CU(cudaMemset(b.p, 0, want));          // the block-maxima accumulators rely on starting zeroed
     b.bytes = want;
     return KV_OK;
 }
@@ -937,6 +981,8 @@ extern "C" int kv_get_info(kv_shard *s, kv_shard_info *o) {
     o->last_kernel_ms = s->last_kernel_ms;
     o->last_launches = s->last_launches;
     o->total_launches = s->total_launches;
+    o->scan_ms_total = s->scan_ms_total;
+    o->scan_calls = s->scan_calls;
     return KV_OK;
 }
 
@@ -1436,7 +1482,7 @@ static int scm_scan_async(kv_shard *s, const uint64_t *pos_mask, const uint64_t 
     MiscLayout L0 = misc_layout(nullptr, n_blocks);
     KV_TRY(ensure(s->d_misc, L0.bytes));
     MiscLayout L = misc_layout(s->d_misc.p, n_blocks);
-    CU(cudaMemsetAsync(L.blockmax, 0, (size_t)n_blocks * 8, s->stream));
+    // L.blockmax is all-zero here: zeroed at allocation and re-zeroed by whoever consumed it last
     Scan2Params P;
     fill_scan2(s, P, n_act);
     P.cnt0 = s->d_cnt[0];
@@ -1456,6 +1502,7 @@ static int scm_scan_async(kv_shard *s, const uint64_t *pos_mask, const uint64_t 
     s->scm_n_neg = n_neg;
     s->scm_ubs = ubs;
     s->scm_p = p;
+    s->scan_calls += 1;
     return KV_OK;
 }
 
@@ -1468,11 +1515,13 @@ extern "C" int kv_scm_scan(kv_shard *s, const uint64_t *pos_mask, const uint64_t
     KV_TRY(ensure_pinned(s, (size_t)n_blocks * 8));
     MiscLayout L = misc_layout(s->d_misc.p, n_blocks);
     CU(cudaMemcpyAsync(s->h_pin, L.blockmax, (size_t)n_blocks * 8, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaMemsetAsync(L.blockmax, 0, (size_t)n_blocks * 8, s->stream));
     CU(cudaStreamSynchronize(s->stream));
     CU(cudaGetLastError());
     float ms = 0;
     CU(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
     s->last_kernel_ms = ms;
+    s->scan_ms_total += ms;
     const unsigned long long *enc = (const unsigned long long *)s->h_pin;
     for (int64_t b = 0; b < n_blocks; ++b) block_max[b] = dec_f64_max(enc[b]);
     return KV_OK;
@@ -1540,7 +1589,8 @@ static int scm_collect_ties(kv_shard *s, int64_t n_blocks, int64_t capacity, dou
     T.bm = L.bm;
     T.tol = L.tol;
     T.sel = L.sel;
-    T.hdr = d_hdr;
+    T.count = &d_hdr->count;
+    T.threshold = nullptr;
     T.out = d_rec;
     T.cap = std::max<long long>(capacity, kTieFirstBatch);     // device buffer holds at least the first batch
     const long long n_seg = (s->n_cols + 63) / 64;
@@ -1627,8 +1677,68 @@ extern "C" int kv_scm_best_rules(kv_shard *s, const uint64_t *pos_mask, const ui
     count_launch(s);
     const int rc = scm_collect_ties(s, n_blocks, capacity, best_utility, rule_idx, pos_err, neg_cover, n_found);
     float ms = 0;
-    if (cudaEventElapsedTime(&ms, s->ev0, s->ev1) == cudaSuccess) s->last_kernel_ms = ms;
+    if (cudaEventElapsedTime(&ms, s->ev0, s->ev1) == cudaSuccess) {
+        s->last_kernel_ms = ms;
+        s->scan_ms_total += ms;
+    }
     return rc;
+}
+
+extern "C" int64_t kv_scm_packet_bytes(int64_t n_blocks, int64_t capacity) {
+    if (n_blocks <= 0 || capacity < 0) return 0;
+    return n_blocks * 8 + (int64_t)sizeof(PacketHeader) + capacity * (int64_t)sizeof(TieRec);
+}
+
+extern "C" int kv_scm_scan_packet(kv_shard *s, const uint64_t *pos_mask, const uint64_t *neg_mask, int64_t n_pos,
+                                  int64_t n_neg, double p, int64_t util_block_size, int64_t n_blocks, int64_t capacity,
+                                  void *packet, int packet_on_device) {
+    if (!s || !pos_mask || !neg_mask || !packet) return fail(KV_E_INVALID, "kv_scm_scan_packet: null pointer");
+    if (capacity < 0) return fail(KV_E_INVALID, "kv_scm_scan_packet: negative capacity");
+    DeviceGuard g(s->device);
+    s->last_launches = 0;
+    KV_TRY(scm_scan_async(s, pos_mask, neg_mask, n_pos, n_neg, p, util_block_size, n_blocks));
+    const size_t bytes = (size_t)kv_scm_packet_bytes(n_blocks, capacity);
+    char *d_packet = (char *)packet;
+    if (!packet_on_device) {
+        KV_TRY(ensure(s->d_ties, bytes));
+        d_packet = (char *)s->d_ties.p;
+    }
+    MiscLayout L = misc_layout(s->d_misc.p, n_blocks);
+    PacketHeader *d_hdr = (PacketHeader *)(d_packet + (size_t)n_blocks * 8);
+    k_scm_select_local<<<1, 32, 0, s->stream>>>(L.blockmax, n_blocks, (double *)d_packet, d_hdr);
+    count_launch(s);
+    TieParams T;
+    memset(&T, 0, sizeof T);
+    T.cnt0 = s->d_cnt[0];
+    T.cnt1 = s->d_cnt[1];
+    T.segmax = s->d_segmax;
+    T.n_cols = s->n_cols;
+    T.ld = s->ld;
+    T.col0 = s->col0;
+    T.k_total = s->k_total;
+    T.ubs = s->scm_ubs;
+    T.inv_ubs = 1.0 / (double)s->scm_ubs;
+    T.p = s->scm_p;
+    T.n_pos = (uint32_t)s->scm_n_pos;
+    T.n_neg = (uint32_t)s->scm_n_neg;
+    T.black_pres = s->have_black ? s->d_black_pres : nullptr;
+    T.black_abs = s->have_black ? s->d_black_abs : nullptr;
+    T.count = &d_hdr->count;
+    T.threshold = &d_hdr->threshold;
+    T.out = (TieRec *)(d_hdr + 1);
+    T.cap = capacity;
+    const long long n_seg = (s->n_cols + 63) / 64;
+    const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((n_seg + 255) / 256, (long long)s->sm_count * 4));
+    k_scm_ties<<<grid, 256, 0, s->stream>>>(T);
+    count_launch(s);
+    if (!packet_on_device) CU(cudaMemcpyAsync(packet, d_packet, bytes, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    CU(cudaGetLastError());
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+    s->last_kernel_ms = ms;
+    s->scan_ms_total += ms;
+    return KV_OK;
 }
 
 // ------------------------------------------------------------------------------------------------

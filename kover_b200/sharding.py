@@ -75,6 +75,19 @@ class Comm(object):
         self._dist.all_gather(out, t, group=self.group)
         return np.concatenate([o.cpu().numpy()[:s] for o, s in zip(out, sizes)])
 
+    def byte_buffers(self, nbytes):
+        """(local [nbytes], gathered [world, nbytes]) uint8 tensors on the collective's device, cached by size."""
+        cache = self.__dict__.setdefault("_byte_buffers", {})
+        if nbytes not in cache:
+            cache[nbytes] = (self._torch.zeros(nbytes, dtype=self._torch.uint8, device=self.device),
+                             self._torch.zeros((self.world_size, nbytes), dtype=self._torch.uint8, device=self.device))
+        return cache[nbytes]
+
+    def allgather_bytes(self, local, gathered):
+        """One fixed-size all-gather; returns the gathered bytes as a host numpy array [world, nbytes]."""
+        self._dist.all_gather(list(gathered.unbind(0)), local, group=self.group)
+        return gathered.cpu().numpy()
+
     def broadcast(self, a, src):
         t = self._t(a)
         self._dist.broadcast(t, src=self._dist.get_global_rank(self.group, src) if self.group is not None else src,
@@ -101,6 +114,7 @@ class ShardGroup(object):
             if covered != self.n_kmers:
                 raise ValueError("local shards cover %d of %d columns" % (covered, self.n_kmers))
         self._single = comm is None and len(self.shards) == 1
+        self.exchange_stats = {"one_exchange": 0, "two_phase_fallback": 0}
 
     # ------------------------------------------------------------------ upload
     def upload_block(self, block, row0, gcol0):
@@ -139,10 +153,48 @@ class ShardGroup(object):
         for s in self.shards:
             s.set_blacklist(rule_idx)
 
+    PACKET_CAPACITY = 256      # tie candidates per rank that travel with the block maxima
+
+    def _scm_best_rules_one_exchange(self, pos_mask, neg_mask, n_pos, n_neg, p, util_block_size):
+        """Multi-rank scan with ONE collective: every rank all-gathers {its block maxima, a local superset of
+        the ties}; the merge (scm.py:270-286) and the exact isclose filter (scm.py:273) then run redundantly
+        on every host.  Returns None when some rank's candidates overflowed the packet."""
+        shard, cap = self.shards[0], self.PACKET_CAPACITY
+        nb = _native.n_utility_blocks(self.n_kmers, util_block_size)
+        local, gathered = self.comm.byte_buffers(_native.packet_bytes(nb, cap))
+        shard.scm_scan_packet(pos_mask, neg_mask, n_pos, n_neg, p, util_block_size, cap, local)
+        packets = [_native.parse_packet(row, nb, cap) for row in self.comm.allgather_bytes(local, gathered)]
+        bm = np.maximum.reduce([q[0] for q in packets])
+        best, sel = _native.select_blocks(bm)
+        if any(q[1] > cap for q in packets):
+            return None, bm, best, sel
+        recs = np.concatenate([q[3] for q in packets])
+        neg_inf = (recs["idx"] & _native.TIE_FLAG_NEG_INF) != 0
+        idx = recs["idx"] & ~np.int64(_native.TIE_FLAG_NEG_INF)
+        pe, nc = recs["pe"].astype(np.int64), recs["nc"].astype(np.int64)
+        u = nc.astype(np.float64) - float(p) * pe.astype(np.float64)     # scm.py:263-264, same two rounded ops
+        u[neg_inf] = -np.inf
+        blk = idx // int(util_block_size)
+        keep = sel[blk].astype(bool) & np.isclose(u, bm[blk])
+        order = np.argsort(idx[keep], kind="stable")
+        return (best, idx[keep][order], pe[keep][order], nc[keep][order]), bm, best, sel
+
     def scm_best_rules(self, pos_mask, neg_mask, n_pos, n_neg, p, util_block_size):
         """-> (best_utility, rule_idx ascending int64, pos_err int64, neg_cover int64); scm.py:238-288."""
         if self._single:
             return self.shards[0].scm_best_rules(pos_mask, neg_mask, n_pos, n_neg, p, util_block_size)
+        if self.comm is not None and len(self.shards) == 1 and hasattr(self.shards[0], "scm_scan_packet"):
+            out, bm, best, sel = self._scm_best_rules_one_exchange(pos_mask, neg_mask, n_pos, n_neg, p,
+                                                                   util_block_size)
+            if out is not None:
+                self.exchange_stats["one_exchange"] += 1
+                return out
+            self.exchange_stats["two_phase_fallback"] += 1
+            # a huge equivalent-rule set: the counts are still on the device, collect exactly in a second exchange
+            idx, pe, nc = self.shards[0].scm_ties(bm, sel)
+            flat = self.comm.allgather_concat(np.stack([idx, pe, nc], axis=1).reshape(-1)).reshape(-1, 3)
+            order = np.argsort(flat[:, 0], kind="stable")
+            return best, flat[order, 0], flat[order, 1], flat[order, 2]
         bm = None
         for s in self.shards:
             b = s.scm_scan(pos_mask, neg_mask, n_pos, n_neg, p, util_block_size)

@@ -19,11 +19,16 @@ from oracle import kover_oracle as ko  # noqa: E402
 from oracle_shard import OracleShard  # noqa: E402
 
 
+STATS = {"one_exchange": 0, "two_phase_fallback": 0}
+GROUPS = []
+
+
 def make_rc(P, n, comm):
     k = P.shape[1]
     slices = partition_columns(k, comm.world_size)
     c0, nc = slices[comm.rank]
     group = ShardGroup([OracleShard(P, n, c0, nc)], n, k, comm=comm, rank_slices=slices)
+    GROUPS.append(group)
     return KmerRuleClassifications(P, n, shard_group=group)
 
 
@@ -112,6 +117,11 @@ def main():
         walk(t.decision_tree, want)
         out["checks"] += 1
 
+    for g_ in GROUPS:
+        for key in STATS:
+            STATS[key] += g_.exchange_stats[key]
+    out.update(STATS)
+    assert STATS["one_exchange"] > 0 and STATS["two_phase_fallback"] > 0, STATS   # both protocols exercised
     comm.barrier()
     with open(os.path.join(os.environ["KV_TEST_OUT"], "rank%d.json" % comm.rank), "w") as f:
         json.dump(out, f)

@@ -51,6 +51,25 @@ class OracleShard(object):
         np.maximum.at(bm, rules // util_block_size, u)
         return bm
 
+    def scm_scan_packet(self, pos_mask, neg_mask, n_pos, n_neg, p, util_block_size, capacity, packet):
+        """The packet kv_scm_scan_packet writes (include/kover_b200.h), into a CPU torch tensor / numpy array."""
+        from kover_b200 import _native
+        bm = self.scm_scan(pos_mask, neg_mask, n_pos, n_neg, p, util_block_size)
+        rules, u, pe, nc = self._utilities()
+        lmax = bm.max()
+        thr = lmax - 5.0 * (1e-8 + 1e-5 * abs(lmax)) if np.isfinite(lmax) else -np.inf
+        keep = u >= thr
+        nb = bm.shape[0]
+        buf = packet if isinstance(packet, np.ndarray) else packet.numpy()
+        buf[:8 * nb] = bm.view(np.uint8)
+        buf[8 * nb:8 * nb + 8] = np.array([keep.sum()], dtype=np.uint64).view(np.uint8)
+        buf[8 * nb + 8:8 * nb + 16] = np.array([thr], dtype=np.float64).view(np.uint8)
+        recs = np.zeros(min(int(keep.sum()), capacity), dtype=_native.PACKET_REC_DTYPE)
+        m = recs.shape[0]
+        flagged = rules[keep] | np.where(np.isneginf(u[keep]), np.int64(_native.TIE_FLAG_NEG_INF), np.int64(0))
+        recs["idx"], recs["pe"], recs["nc"] = flagged[:m], pe[keep][:m], nc[keep][:m]
+        buf[8 * nb + 16:8 * nb + 16 + 16 * m] = recs.view(np.uint8)
+
     def scm_ties(self, block_max, selected, capacity=4096):
         rules, u, pe, nc = self._utilities()
         b = rules // self._ubs
