@@ -51,12 +51,13 @@ def main():
         out["checks"] += 1
 
     # utility scan: block maxima merged over ranks, ties concatenated
-    for case in cases.UTILITY_CASES:
+    for case, cap in [(c, cap) for cap in (256, 2) for c in cases.UTILITY_CASES]:
         if case[1] == "MW":
             continue
         gg = np.load(os.path.join(golden, case[0] + ".npz"))
         P, n, chunks, pos, neg, p, blacklist, ubs = cases.utility_inputs(case)
         rc = make_rc(P, n, comm)
+        rc._group.PACKET_CAPACITY = cap       # cap = 2 forces the two-phase fallback on every rank
         bu, bi, bp, bn = rc.best_utility_rules(p, pos, neg, rule_blacklist=blacklist, util_block_size=ubs)
         assert bu == float(gg["best_utility"]), case[0]
         assert np.array_equal(bi, gg["best_idx"]) and np.array_equal(bp, gg["best_pos_err"]), case[0]
