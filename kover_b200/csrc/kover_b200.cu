@@ -861,6 +861,7 @@ static int ensure(DevBuf &b, size_t bytes) {
     size_t want = std::max(bytes, (size_t)4096);
     CU(cudaMalloc(&b.p, want));
     CU(cudaMemset(b.p, 0, want));          // the block-maxima accumulators rely on starting zeroed
+    CU(cudaDeviceSynchronize());           // (re)allocation is rare; the memset must not race the shard's stream
     b.bytes = want;
     return KV_OK;
 }

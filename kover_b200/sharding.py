@@ -98,6 +98,27 @@ class Comm(object):
         self._dist.barrier(group=self.group)
 
 
+def merge_packets(rows, n_blocks, capacity, p, util_block_size):
+    """rows: uint8 [n_shards, packet_bytes] of kv_scm_scan_packet packets.  Max-merge of the block maxima, the
+    reference's sequential block merge (scm.py:270-286) and the exact isclose filter (scm.py:273) on the
+    gathered candidates.  -> ((best, idx, pos_err, neg_cover) or None if a packet overflowed, bm, best, sel)."""
+    packets = [_native.parse_packet(row, n_blocks, capacity) for row in rows]
+    bm = np.maximum.reduce([q[0] for q in packets])
+    best, sel = _native.select_blocks(bm)
+    if any(q[1] > capacity for q in packets):
+        return None, bm, best, sel
+    recs = np.concatenate([q[3] for q in packets])
+    neg_inf = (recs["idx"] & _native.TIE_FLAG_NEG_INF) != 0
+    idx = recs["idx"] & ~np.int64(_native.TIE_FLAG_NEG_INF)
+    pe, nc = recs["pe"].astype(np.int64), recs["nc"].astype(np.int64)
+    u = nc.astype(np.float64) - float(p) * pe.astype(np.float64)     # scm.py:263-264, the same two rounded ops
+    u[neg_inf] = -np.inf
+    blk = idx // int(util_block_size)
+    keep = sel[blk].astype(bool) & np.isclose(u, bm[blk])
+    order = np.argsort(idx[keep], kind="stable")
+    return (best, idx[keep][order], pe[keep][order], nc[keep][order]), bm, best, sel
+
+
 class ShardGroup(object):
     """Shards owned by this process (+ optional Comm to the other ranks) acting as one matrix."""
 
@@ -163,21 +184,7 @@ class ShardGroup(object):
         nb = _native.n_utility_blocks(self.n_kmers, util_block_size)
         local, gathered = self.comm.byte_buffers(_native.packet_bytes(nb, cap))
         shard.scm_scan_packet(pos_mask, neg_mask, n_pos, n_neg, p, util_block_size, cap, local)
-        packets = [_native.parse_packet(row, nb, cap) for row in self.comm.allgather_bytes(local, gathered)]
-        bm = np.maximum.reduce([q[0] for q in packets])
-        best, sel = _native.select_blocks(bm)
-        if any(q[1] > cap for q in packets):
-            return None, bm, best, sel
-        recs = np.concatenate([q[3] for q in packets])
-        neg_inf = (recs["idx"] & _native.TIE_FLAG_NEG_INF) != 0
-        idx = recs["idx"] & ~np.int64(_native.TIE_FLAG_NEG_INF)
-        pe, nc = recs["pe"].astype(np.int64), recs["nc"].astype(np.int64)
-        u = nc.astype(np.float64) - float(p) * pe.astype(np.float64)     # scm.py:263-264, same two rounded ops
-        u[neg_inf] = -np.inf
-        blk = idx // int(util_block_size)
-        keep = sel[blk].astype(bool) & np.isclose(u, bm[blk])
-        order = np.argsort(idx[keep], kind="stable")
-        return (best, idx[keep][order], pe[keep][order], nc[keep][order]), bm, best, sel
+        return merge_packets(self.comm.allgather_bytes(local, gathered), nb, cap, p, util_block_size)
 
     def scm_best_rules(self, pos_mask, neg_mask, n_pos, n_neg, p, util_block_size):
         """-> (best_utility, rule_idx ascending int64, pos_err int64, neg_cover int64); scm.py:238-288."""

@@ -110,6 +110,32 @@ def test_best_utility_rules_golden(golden_dir, case, devices):
     assert np.array_equal(bn, g["best_neg_cover"])
 
 
+@pytest.mark.parametrize("case", cases.UTILITY_CASES, ids=[c[0] for c in cases.UTILITY_CASES])
+def test_one_exchange_packets_golden(golden_dir, case):
+    """The multi-rank protocol (kv_scm_scan_packet + sharding.merge_packets) with three shards on one GPU
+    standing in for three ranks: identical to the reference's result whenever no packet overflows."""
+    from kover_b200.sharding import merge_packets
+    g = load(golden_dir, case[0])
+    P, n, chunks, pos, neg, p, blacklist, ubs = cases.utility_inputs(case)
+    rc = KmerRuleClassifications(as_dataset(P, chunks), n, devices=[0, 0, 0])
+    rc.set_rule_blacklist(blacklist)
+    nb = _native.n_utility_blocks(P.shape[1], ubs)
+    for cap in (4096, 3):
+        rows = np.zeros((3, _native.packet_bytes(nb, cap)), dtype=np.uint8)
+        for i, shard in enumerate(rc._group.shards):
+            shard.scm_scan_packet(rc.row_mask(pos), rc.row_mask(neg), len(pos), len(neg), p, ubs, cap, rows[i])
+        out, bm, best, sel = merge_packets(rows, nb, cap, p, ubs)
+        assert best == float(g["best_utility"])
+        if out is None:                      # overflow: the caller falls back to kv_scm_ties on the merged tables
+            assert cap == 3
+            parts = [shard.scm_ties(bm, sel) for shard in rc._group.shards]
+            idx = np.sort(np.concatenate([q[0] for q in parts]))
+            assert np.array_equal(idx, g["best_idx"])
+        else:
+            assert np.array_equal(out[1], g["best_idx"]) and np.array_equal(out[2], g["best_pos_err"])
+            assert np.array_equal(out[3], g["best_neg_cover"])
+
+
 def test_best_utility_no_positives_left():
     # scm.py:250-253: with no positive example left the error counts are all zero
     X, P, n, chunks = cases.matrix("M1")
