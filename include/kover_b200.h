@@ -149,6 +149,27 @@ int64_t kv_scm_packet_bytes(int64_t n_blocks, int64_t capacity);
 int kv_scm_scan_packet(kv_shard *s, const uint64_t *pos_mask, const uint64_t *neg_mask, int64_t n_pos,
                        int64_t n_neg, double p, int64_t util_block_size, int64_t n_blocks, int64_t capacity,
                        void *packet, int packet_on_device);
+/* Host-only merge of n_packets gathered packets [n_packets][kv_scm_packet_bytes(n_blocks, packet_capacity)]:
+ * element-wise max of the block maxima (-> merged_block_max[n_blocks]), kv_scm_select_blocks (-> selected[n_blocks],
+ * *best_utility) and the exact isclose filter (scm.py:273) over the candidates, ascending rule index.
+ * *overflowed = 1 (and no ties) when some packet was truncated. */
+int kv_scm_merge_packets(const void *rows, int64_t n_packets, int64_t n_blocks, int64_t packet_capacity, double p,
+                         int64_t util_block_size, double *best_utility, int64_t capacity, int64_t *rule_idx,
+                         int64_t *pos_err, int64_t *neg_cover, int64_t *n_found, double *merged_block_max,
+                         uint8_t *selected, int *overflowed);
+/* Peer mailbox (one process per GPU, all GPUs of one node): the packets are all-gathered by remote stores
+ * over NVLink into every peer's mailbox from the same kernel that waits for the peers' packets, so a
+ * multi-rank step costs one host synchronisation and no NCCL call.  kv_p2p_create returns this rank's
+ * 64-byte CUDA IPC handle; exchange the handles out of band (torch.distributed all_gather) and pass all
+ * `world` of them, rank order, to kv_p2p_connect.  Every rank must then call kv_scm_best_rules_p2p in the
+ * same order; outputs as kv_scm_merge_packets. */
+int kv_p2p_create(kv_shard *s, int rank, int world, int64_t slot_bytes, void *ipc_handle_out);
+int kv_p2p_connect(kv_shard *s, const void *all_handles);
+int kv_scm_best_rules_p2p(kv_shard *s, const uint64_t *pos_mask, const uint64_t *neg_mask, int64_t n_pos,
+                          int64_t n_neg, double p, int64_t util_block_size, int64_t packet_capacity,
+                          double *best_utility, int64_t capacity, int64_t *rule_idx, int64_t *pos_err,
+                          int64_t *neg_cover, int64_t *n_found, double *merged_block_max, uint8_t *selected,
+                          int *overflowed);
 /* Single-shard convenience: scan + select + ties in one call. */
 int kv_scm_best_rules(kv_shard *s, const uint64_t *pos_mask, const uint64_t *neg_mask, int64_t n_pos,
                       int64_t n_neg, double p, int64_t util_block_size, double *best_utility,

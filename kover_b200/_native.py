@@ -52,6 +52,14 @@ SYMBOLS = {
     "kv_scm_packet_bytes": (_c_i64, [_c_i64, _c_i64]),
     "kv_scm_scan_packet": (ctypes.c_int, [_c_p, _c_p, _c_p, _c_i64, _c_i64, ctypes.c_double, _c_i64, _c_i64, _c_i64,
                                           _c_p, ctypes.c_int]),
+    "kv_scm_merge_packets": (ctypes.c_int, [_c_p, _c_i64, _c_i64, _c_i64, ctypes.c_double, _c_i64,
+                                            ctypes.POINTER(ctypes.c_double), _c_i64, _c_p, _c_p, _c_p,
+                                            ctypes.POINTER(_c_i64), _c_p, _c_p, ctypes.POINTER(ctypes.c_int)]),
+    "kv_p2p_create": (ctypes.c_int, [_c_p, ctypes.c_int, ctypes.c_int, _c_i64, _c_p]),
+    "kv_p2p_connect": (ctypes.c_int, [_c_p, _c_p]),
+    "kv_scm_best_rules_p2p": (ctypes.c_int, [_c_p, _c_p, _c_p, _c_i64, _c_i64, ctypes.c_double, _c_i64, _c_i64,
+                                             ctypes.POINTER(ctypes.c_double), _c_i64, _c_p, _c_p, _c_p,
+                                             ctypes.POINTER(_c_i64), _c_p, _c_p, ctypes.POINTER(ctypes.c_int)]),
     "kv_scm_best_rules": (ctypes.c_int, [_c_p, _c_p, _c_p, _c_i64, _c_i64, ctypes.c_double, _c_i64,
                                          ctypes.POINTER(ctypes.c_double), _c_i64, _c_p, _c_p, _c_p,
                                          ctypes.POINTER(_c_i64)]),
@@ -254,6 +262,37 @@ class Shard(object):
         check(self._lib.kv_scm_scan_packet(self._h, ptr(pos_mask), ptr(neg_mask), int(n_pos), int(n_neg), float(p),
                                            int(util_block_size), nb, int(capacity), ctypes.c_void_p(addr), on_device))
 
+    # -- peer mailbox (multi-rank, one process per GPU)
+    def p2p_create(self, rank, world, slot_bytes):
+        handle = np.zeros(64, dtype=np.uint8)
+        check(self._lib.kv_p2p_create(self._h, int(rank), int(world), int(slot_bytes), ptr(handle)))
+        return handle
+
+    def p2p_connect(self, all_handles):
+        h = np.ascontiguousarray(all_handles, dtype=np.uint8)
+        check(self._lib.kv_p2p_connect(self._h, ptr(h)))
+
+    def scm_best_rules_p2p(self, pos_mask, neg_mask, n_pos, n_neg, p, util_block_size, packet_capacity,
+                           capacity=4096):
+        """-> ((best, idx, pos_err, neg_cover) or None on packet overflow, merged block maxima, best, selected)."""
+        pos_mask = np.ascontiguousarray(pos_mask, dtype=np.uint64)
+        neg_mask = np.ascontiguousarray(neg_mask, dtype=np.uint64)
+        nb = n_utility_blocks(self.n_kmers_total, util_block_size)
+        bm, sel = np.empty(nb, dtype=np.float64), np.empty(nb, dtype=np.uint8)
+        idx, pe, nc = (np.empty(capacity, dtype=np.int64) for _ in range(3))
+        best, n, over = ctypes.c_double(0.0), _c_i64(0), ctypes.c_int(0)
+        rc = self._lib.kv_scm_best_rules_p2p(self._h, ptr(pos_mask), ptr(neg_mask), int(n_pos), int(n_neg), float(p),
+                                             int(util_block_size), int(packet_capacity), ctypes.byref(best), capacity,
+                                             ptr(idx), ptr(pe), ptr(nc), ctypes.byref(n), ptr(bm), ptr(sel),
+                                             ctypes.byref(over))
+        if rc == KV_E_OVERFLOW:       # more exact ties than `capacity` (cannot exceed world * packet_capacity)
+            over.value = 1
+        else:
+            check(rc)
+        if over.value:
+            return None, bm, best.value, sel
+        return (best.value, idx[:n.value], pe[:n.value], nc[:n.value]), bm, best.value, sel
+
     def scm_best_rules(self, pos_mask, neg_mask, n_pos, n_neg, p, util_block_size, capacity=4096):
         pos_mask = np.ascontiguousarray(pos_mask, dtype=np.uint64)
         neg_mask = np.ascontiguousarray(neg_mask, dtype=np.uint64)
@@ -324,6 +363,23 @@ def parse_packet(buf, n_blocks, capacity):
     thr = float(buf[8 * n_blocks + 8:8 * n_blocks + 16].view(np.float64)[0])
     recs = buf[8 * n_blocks + 16:8 * n_blocks + 16 + 16 * capacity].view(PACKET_REC_DTYPE)
     return bm, count, thr, recs[:min(count, capacity)]
+
+
+def merge_packets(rows, n_blocks, packet_capacity, p, util_block_size):
+    """kv_scm_merge_packets over uint8 [n_packets, packet_bytes].
+    -> ((best, idx, pos_err, neg_cover) or None on packet overflow, merged block maxima, best, selected)."""
+    rows = np.ascontiguousarray(rows, dtype=np.uint8)
+    assert rows.ndim == 2 and rows.shape[1] == packet_bytes(n_blocks, packet_capacity)
+    capacity = max(1, rows.shape[0] * packet_capacity)
+    bm, sel = np.empty(n_blocks, dtype=np.float64), np.empty(n_blocks, dtype=np.uint8)
+    idx, pe, nc = (np.empty(capacity, dtype=np.int64) for _ in range(3))
+    best, n, over = ctypes.c_double(0.0), _c_i64(0), ctypes.c_int(0)
+    check(load().kv_scm_merge_packets(ptr(rows), rows.shape[0], int(n_blocks), int(packet_capacity), float(p),
+                                      int(util_block_size), ctypes.byref(best), capacity, ptr(idx), ptr(pe), ptr(nc),
+                                      ctypes.byref(n), ptr(bm), ptr(sel), ctypes.byref(over)))
+    if over.value:
+        return None, bm, best.value, sel
+    return (best.value, idx[:n.value], pe[:n.value], nc[:n.value]), bm, best.value, sel
 
 
 def select_blocks(block_max):

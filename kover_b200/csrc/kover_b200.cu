@@ -808,7 +808,11 @@ struct DevBuf {
     size_t bytes = 0;
 };
 
+struct kv_p2p;
+static void p2p_destroy(kv_p2p *m);
+
 struct kv_shard {
+    kv_p2p *p2p = nullptr;                    // peer mailbox (multi-rank), optional
     int device = 0, sm_count = 0;
     long long n_examples = 0, W = 0, k_total = 0, col0 = 0, n_cols = 0, ld = 0, n_tiles = 0;
     uint64_t *d_mat = nullptr;
@@ -947,6 +951,7 @@ extern "C" int kv_destroy(kv_shard *s) {
     if (!s) return KV_OK;
     DeviceGuard g(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
+    p2p_destroy(s->p2p);
     cudaFree(s->d_mat);
     for (auto p : s->d_cnt) cudaFree(p);
     for (DevBuf *b : {&s->d_rec, &s->d_misc, &s->d_ties, &s->d_stage})
@@ -1690,20 +1695,11 @@ extern "C" int64_t kv_scm_packet_bytes(int64_t n_blocks, int64_t capacity) {
     return n_blocks * 8 + (int64_t)sizeof(PacketHeader) + capacity * (int64_t)sizeof(TieRec);
 }
 
-extern "C" int kv_scm_scan_packet(kv_shard *s, const uint64_t *pos_mask, const uint64_t *neg_mask, int64_t n_pos,
-                                  int64_t n_neg, double p, int64_t util_block_size, int64_t n_blocks, int64_t capacity,
-                                  void *packet, int packet_on_device) {
-    if (!s || !pos_mask || !neg_mask || !packet) return fail(KV_E_INVALID, "kv_scm_scan_packet: null pointer");
-    if (capacity < 0) return fail(KV_E_INVALID, "kv_scm_scan_packet: negative capacity");
-    DeviceGuard g(s->device);
-    s->last_launches = 0;
+// scan + local select + candidate collection into a packet in DEVICE memory; nothing is synchronised
+static int scm_packet_async(kv_shard *s, const uint64_t *pos_mask, const uint64_t *neg_mask, int64_t n_pos,
+                            int64_t n_neg, double p, int64_t util_block_size, int64_t n_blocks, int64_t capacity,
+                            char *d_packet) {
     KV_TRY(scm_scan_async(s, pos_mask, neg_mask, n_pos, n_neg, p, util_block_size, n_blocks));
-    const size_t bytes = (size_t)kv_scm_packet_bytes(n_blocks, capacity);
-    char *d_packet = (char *)packet;
-    if (!packet_on_device) {
-        KV_TRY(ensure(s->d_ties, bytes));
-        d_packet = (char *)s->d_ties.p;
-    }
     MiscLayout L = misc_layout(s->d_misc.p, n_blocks);
     PacketHeader *d_hdr = (PacketHeader *)(d_packet + (size_t)n_blocks * 8);
     k_scm_select_local<<<1, 32, 0, s->stream>>>(L.blockmax, n_blocks, (double *)d_packet, d_hdr);
@@ -1732,14 +1728,270 @@ extern "C" int kv_scm_scan_packet(kv_shard *s, const uint64_t *pos_mask, const u
     const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((n_seg + 255) / 256, (long long)s->sm_count * 4));
     k_scm_ties<<<grid, 256, 0, s->stream>>>(T);
     count_launch(s);
-    if (!packet_on_device) CU(cudaMemcpyAsync(packet, d_packet, bytes, cudaMemcpyDeviceToHost, s->stream));
-    CU(cudaStreamSynchronize(s->stream));
-    CU(cudaGetLastError());
+    return KV_OK;
+}
+
+static int finish_scan_timing(kv_shard *s) {
     float ms = 0;
     CU(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
     s->last_kernel_ms = ms;
     s->scan_ms_total += ms;
     return KV_OK;
+}
+
+extern "C" int kv_scm_scan_packet(kv_shard *s, const uint64_t *pos_mask, const uint64_t *neg_mask, int64_t n_pos,
+                                  int64_t n_neg, double p, int64_t util_block_size, int64_t n_blocks, int64_t capacity,
+                                  void *packet, int packet_on_device) {
+    if (!s || !pos_mask || !neg_mask || !packet) return fail(KV_E_INVALID, "kv_scm_scan_packet: null pointer");
+    if (capacity < 0) return fail(KV_E_INVALID, "kv_scm_scan_packet: negative capacity");
+    DeviceGuard g(s->device);
+    s->last_launches = 0;
+    const size_t bytes = (size_t)kv_scm_packet_bytes(n_blocks, capacity);
+    char *d_packet = (char *)packet;
+    if (!packet_on_device) {
+        KV_TRY(ensure(s->d_ties, bytes));
+        d_packet = (char *)s->d_ties.p;
+    }
+    KV_TRY(scm_packet_async(s, pos_mask, neg_mask, n_pos, n_neg, p, util_block_size, n_blocks, capacity, d_packet));
+    if (!packet_on_device) CU(cudaMemcpyAsync(packet, d_packet, bytes, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    CU(cudaGetLastError());
+    return finish_scan_timing(s);
+}
+
+// Host-only: merge of the gathered packets (max of the block maxima, scm.py:270-286 replay, exact
+// isclose filter of the candidates with u recomputed as scm.py:263-264 does).
+extern "C" int kv_scm_merge_packets(const void *rows, int64_t n_packets, int64_t n_blocks, int64_t packet_capacity,
+                                    double p, int64_t util_block_size, double *best_utility, int64_t capacity,
+                                    int64_t *rule_idx, int64_t *pos_err, int64_t *neg_cover, int64_t *n_found,
+                                    double *merged_block_max, uint8_t *selected, int *overflowed) {
+    if (!rows || !best_utility || !n_found || !merged_block_max || !selected || !overflowed ||
+        (capacity > 0 && (!rule_idx || !pos_err || !neg_cover)))
+        return fail(KV_E_INVALID, "kv_scm_merge_packets: null pointer");
+    if (n_packets <= 0 || n_blocks <= 0 || packet_capacity < 0 || util_block_size <= 0 || capacity < 0)
+        return fail(KV_E_INVALID, "kv_scm_merge_packets: bad sizes");
+    const size_t stride = (size_t)kv_scm_packet_bytes(n_blocks, packet_capacity);
+    const char *base = (const char *)rows;
+    const double ninf = -std::numeric_limits<double>::infinity();
+    for (int64_t b = 0; b < n_blocks; ++b) merged_block_max[b] = ninf;
+    *overflowed = 0;
+    for (int64_t r = 0; r < n_packets; ++r) {
+        const double *bm = (const double *)(base + r * stride);
+        for (int64_t b = 0; b < n_blocks; ++b) merged_block_max[b] = std::max(merged_block_max[b], bm[b]);
+        const PacketHeader *h = (const PacketHeader *)(bm + n_blocks);
+        if ((int64_t)h->count > packet_capacity) *overflowed = 1;
+    }
+    KV_TRY(kv_scm_select_blocks(merged_block_max, n_blocks, best_utility, selected));
+    *n_found = 0;
+    if (*overflowed) return KV_OK;
+    std::vector<TieRec> keep;
+    for (int64_t r = 0; r < n_packets; ++r) {
+        const double *bm = (const double *)(base + r * stride);
+        const PacketHeader *h = (const PacketHeader *)(bm + n_blocks);
+        const TieRec *recs = (const TieRec *)(h + 1);
+        for (unsigned long long i = 0; i < h->count; ++i) {
+            TieRec t = recs[i];
+            const bool neg_inf = (t.idx & TIE_FLAG_NEG_INF) != 0;
+            t.idx &= ~TIE_FLAG_NEG_INF;
+            const int64_t b = t.idx / util_block_size;
+            if (b < 0 || b >= n_blocks) return fail(KV_E_INVALID, "kv_scm_merge_packets: corrupt packet");
+            if (!selected[b]) continue;
+            volatile double prod = p * (double)t.pe;              // one rounded multiply ...
+            volatile double u = (double)t.nc - prod;              // ... one rounded subtract (scm.py:263-264)
+            if (np_isclose(neg_inf ? ninf : (double)u, merged_block_max[b])) keep.push_back(t);
+        }
+    }
+    std::sort(keep.begin(), keep.end(), [](const TieRec &a, const TieRec &b) { return a.idx < b.idx; });
+    *n_found = (int64_t)keep.size();
+    if ((int64_t)keep.size() > capacity) return fail(KV_E_OVERFLOW, "kv_scm_merge_packets: tie buffer too small");
+    for (size_t i = 0; i < keep.size(); ++i) {
+        rule_idx[i] = keep[i].idx;
+        pos_err[i] = keep[i].pe;
+        neg_cover[i] = keep[i].nc;
+    }
+    return KV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Peer mailbox: the all-gather of the packets over NVLink peer memory, fused behind the tie kernel.
+// Every rank owns a mailbox [2 parities][world slots][slot_bytes] + flags[world]; after its candidates
+// are complete a rank STORES its packet into slot[parity][rank] of every peer's mailbox (remote stores
+// over NVLink/NVSwitch, fire and forget), fences, and writes the step's sequence number into
+// flags[rank] of every peer; then it waits until its own flags show every peer's sequence number.  One
+// kernel does both, so the host synchronises once per step and no NCCL call sits on the step's path.
+// (Ranks run on different GPUs; never use this with several ranks time-slicing one GPU.)
+// ------------------------------------------------------------------------------------------------
+static constexpr int P2P_MAX_WORLD = 64;
+struct P2PParams {
+    char *peer_box[P2P_MAX_WORLD];        // mailbox base of every rank, mapped into this process
+    unsigned long long *peer_flags[P2P_MAX_WORLD];
+    int rank, world;
+    unsigned long long seq;
+    size_t slot_bytes, n_blocks_bytes;
+    const char *packet;                   // local packet (device)
+    long long packet_capacity;
+    int *error;                           // device int: 1 = timed out waiting for a peer
+    unsigned long long timeout_ns;
+};
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+__global__ void __launch_bounds__(256) k_p2p_publish_wait(const P2PParams P) {
+    // bytes worth sending: block maxima + header + the records actually present
+    const PacketHeader *hdr = (const PacketHeader *)(P.packet + P.n_blocks_bytes);
+    const long long n_rec = min((long long)hdr->count, P.packet_capacity);
+    const size_t bytes = P.n_blocks_bytes + sizeof(PacketHeader) + (size_t)n_rec * sizeof(TieRec);
+    const size_t n16 = (bytes + 15) / 16;
+    const int parity = (int)(P.seq & 1ull);
+    const uint4 *src = (const uint4 *)P.packet;
+    for (int r = 0; r < P.world; ++r) {
+        uint4 *dst = (uint4 *)(P.peer_box[r] + ((size_t)parity * P.world + P.rank) * P.slot_bytes);
+        for (size_t i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = src[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < P.world) {
+        // release: the packet stores above are visible before the flag
+        unsigned long long *f = P.peer_flags[threadIdx.x] + P.rank;
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(P.seq) : "memory");
+        // wait for peer threadIdx.x's flag in MY mailbox
+        const unsigned long long *mine = P.peer_flags[P.rank] + threadIdx.x;
+        const unsigned long long t0 = globaltimer_ns();
+        unsigned long long v = 0;
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
+            if (v >= P.seq) break;
+            if (globaltimer_ns() - t0 > P.timeout_ns) {
+                *P.error = 1;
+                break;
+            }
+            __nanosleep(200);
+        }
+    }
+    __threadfence_system();
+}
+
+struct kv_p2p {
+    int rank = 0, world = 0;
+    size_t slot_bytes = 0;
+    char *box = nullptr;                   // own mailbox: [2][world][slot_bytes] then flags[world] (256-aligned)
+    size_t flags_off = 0, total_bytes = 0;
+    char *peer_box[P2P_MAX_WORLD] = {nullptr};
+    bool opened[P2P_MAX_WORLD] = {false};
+    char *d_packet = nullptr;              // local packet staging
+    int *d_error = nullptr;
+    unsigned long long seq = 0;
+    void *h_rows = nullptr;                // pinned: gathered rows of one parity
+};
+
+extern "C" int kv_p2p_create(kv_shard *s, int rank, int world, int64_t slot_bytes, void *ipc_handle_out) {
+    if (!s || !ipc_handle_out) return fail(KV_E_INVALID, "kv_p2p_create: null pointer");
+    if (world < 1 || world > P2P_MAX_WORLD || rank < 0 || rank >= world || slot_bytes <= 0)
+        return fail(KV_E_INVALID, "kv_p2p_create: bad rank / world / slot size");
+    DeviceGuard g(s->device);
+    if (s->p2p) return fail(KV_E_INVALID, "kv_p2p_create: mailbox already exists");
+    kv_p2p *m = new kv_p2p();
+    m->rank = rank;
+    m->world = world;
+    m->slot_bytes = ((size_t)slot_bytes + 255) / 256 * 256;
+    m->flags_off = 2 * (size_t)world * m->slot_bytes;
+    m->total_bytes = m->flags_off + 256 + (size_t)world * 8;
+    if (cudaMalloc(&m->box, m->total_bytes) != cudaSuccess || cudaMalloc(&m->d_packet, m->slot_bytes) != cudaSuccess ||
+        cudaMalloc(&m->d_error, 4) != cudaSuccess ||
+        cudaMallocHost(&m->h_rows, (size_t)world * m->slot_bytes) != cudaSuccess) {
+        delete m;
+        return fail(KV_E_NOMEM, "kv_p2p_create: allocation failed");
+    }
+    CU(cudaMemset(m->box, 0, m->total_bytes));
+    CU(cudaMemset(m->d_error, 0, 4));
+    CU(cudaDeviceSynchronize());
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, m->box));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    memcpy(ipc_handle_out, &h, 64);
+    m->peer_box[rank] = m->box;
+    s->p2p = m;
+    return KV_OK;
+}
+
+extern "C" int kv_p2p_connect(kv_shard *s, const void *all_handles) {
+    if (!s || !all_handles || !s->p2p) return fail(KV_E_INVALID, "kv_p2p_connect: no mailbox");
+    DeviceGuard g(s->device);
+    kv_p2p *m = s->p2p;
+    for (int r = 0; r < m->world; ++r) {
+        if (r == m->rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char *)all_handles + (size_t)r * 64, 64);
+        void *ptr = nullptr;
+        CU(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        m->peer_box[r] = (char *)ptr;
+        m->opened[r] = true;
+    }
+    return KV_OK;
+}
+
+static void p2p_destroy(kv_p2p *m) {
+    if (!m) return;
+    for (int r = 0; r < m->world; ++r)
+        if (m->opened[r]) cudaIpcCloseMemHandle(m->peer_box[r]);
+    cudaFree(m->box);
+    cudaFree(m->d_packet);
+    cudaFree(m->d_error);
+    if (m->h_rows) cudaFreeHost(m->h_rows);
+    delete m;
+}
+
+// One multi-rank SCM step: scan, local candidates, publish to every peer + wait for theirs (one kernel),
+// read back the gathered packets, merge on the host.  All ranks must call it in the same order.
+extern "C" int kv_scm_best_rules_p2p(kv_shard *s, const uint64_t *pos_mask, const uint64_t *neg_mask, int64_t n_pos,
+                                     int64_t n_neg, double p, int64_t util_block_size, int64_t packet_capacity,
+                                     double *best_utility, int64_t capacity, int64_t *rule_idx, int64_t *pos_err,
+                                     int64_t *neg_cover, int64_t *n_found, double *merged_block_max,
+                                     uint8_t *selected, int *overflowed) {
+    if (!s || !s->p2p || !pos_mask || !neg_mask) return fail(KV_E_INVALID, "kv_scm_best_rules_p2p: no mailbox / null pointer");
+    kv_p2p *m = s->p2p;
+    const int64_t n_blocks = kv_scm_n_blocks(s->k_total, util_block_size);
+    if (n_blocks <= 0) return fail(KV_E_INVALID, "kv_scm_best_rules_p2p: util_block_size must be positive");
+    const size_t bytes = (size_t)kv_scm_packet_bytes(n_blocks, packet_capacity);
+    if (bytes > m->slot_bytes) return fail(KV_E_INVALID, "kv_scm_best_rules_p2p: packet larger than the mailbox slot");
+    DeviceGuard g(s->device);
+    s->last_launches = 0;
+    KV_TRY(scm_packet_async(s, pos_mask, neg_mask, n_pos, n_neg, p, util_block_size, n_blocks, packet_capacity,
+                            m->d_packet));
+    P2PParams P;
+    memset(&P, 0, sizeof P);
+    for (int r = 0; r < m->world; ++r) {
+        P.peer_box[r] = m->peer_box[r];
+        P.peer_flags[r] = (unsigned long long *)(m->peer_box[r] + m->flags_off + 256);
+    }
+    P.rank = m->rank;
+    P.world = m->world;
+    P.seq = ++m->seq;
+    P.slot_bytes = m->slot_bytes;
+    P.n_blocks_bytes = (size_t)n_blocks * 8;
+    P.packet = m->d_packet;
+    P.packet_capacity = packet_capacity;
+    P.error = m->d_error;
+    P.timeout_ns = 20ull * 1000 * 1000 * 1000;
+    k_p2p_publish_wait<<<1, 256, 0, s->stream>>>(P);
+    count_launch(s);
+    const int parity = (int)(P.seq & 1ull);
+    // gathered rows of this parity, at the packet stride the merge expects, + the error word
+    CU(cudaMemcpy2DAsync(m->h_rows, bytes, m->box + (size_t)parity * m->world * m->slot_bytes, m->slot_bytes, bytes,
+                         (size_t)m->world, cudaMemcpyDeviceToHost, s->stream));
+    KV_TRY(ensure_pinned(s, 64));
+    CU(cudaMemcpyAsync(s->h_pin, m->d_error, 4, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    CU(cudaGetLastError());
+    KV_TRY(finish_scan_timing(s));
+    if (*(int *)s->h_pin != 0) return fail(KV_E_CUDA, "kv_scm_best_rules_p2p: timed out waiting for a peer rank's packet");
+    return kv_scm_merge_packets(m->h_rows, m->world, n_blocks, packet_capacity, p, util_block_size, best_utility,
+                                capacity, rule_idx, pos_err, neg_cover, n_found, merged_block_max, selected,
+                                overflowed);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -101,22 +101,9 @@ class Comm(object):
 def merge_packets(rows, n_blocks, capacity, p, util_block_size):
     """rows: uint8 [n_shards, packet_bytes] of kv_scm_scan_packet packets.  Max-merge of the block maxima, the
     reference's sequential block merge (scm.py:270-286) and the exact isclose filter (scm.py:273) on the
-    gathered candidates.  -> ((best, idx, pos_err, neg_cover) or None if a packet overflowed, bm, best, sel)."""
-    packets = [_native.parse_packet(row, n_blocks, capacity) for row in rows]
-    bm = np.maximum.reduce([q[0] for q in packets])
-    best, sel = _native.select_blocks(bm)
-    if any(q[1] > capacity for q in packets):
-        return None, bm, best, sel
-    recs = np.concatenate([q[3] for q in packets])
-    neg_inf = (recs["idx"] & _native.TIE_FLAG_NEG_INF) != 0
-    idx = recs["idx"] & ~np.int64(_native.TIE_FLAG_NEG_INF)
-    pe, nc = recs["pe"].astype(np.int64), recs["nc"].astype(np.int64)
-    u = nc.astype(np.float64) - float(p) * pe.astype(np.float64)     # scm.py:263-264, the same two rounded ops
-    u[neg_inf] = -np.inf
-    blk = idx // int(util_block_size)
-    keep = sel[blk].astype(bool) & np.isclose(u, bm[blk])
-    order = np.argsort(idx[keep], kind="stable")
-    return (best, idx[keep][order], pe[keep][order], nc[keep][order]), bm, best, sel
+    gathered candidates, all in the library's host code (kv_scm_merge_packets).
+    -> ((best, idx, pos_err, neg_cover) or None if a packet overflowed, bm, best, sel)."""
+    return _native.merge_packets(rows, n_blocks, capacity, p, util_block_size)
 
 
 class ShardGroup(object):
@@ -136,6 +123,36 @@ class ShardGroup(object):
                 raise ValueError("local shards cover %d of %d columns" % (covered, self.n_kmers))
         self._single = comm is None and len(self.shards) == 1
         self.exchange_stats = {"one_exchange": 0, "two_phase_fallback": 0}
+        self.p2p_slot_bytes = 0
+        if comm is not None and len(self.shards) == 1 and comm.world_size > 1:
+            self._try_p2p()
+
+    def _try_p2p(self):
+        """Peer mailbox over CUDA IPC / NVLink (kv_p2p_*): used when every rank could map every peer.  Disabled
+        with KOVER_B200_P2P=0 or when the shards are not device shards; any failure on any rank falls back
+        to the NCCL all-gather for all ranks."""
+        import os
+        shard = self.shards[0]
+        ok = int(hasattr(shard, "p2p_create") and os.environ.get("KOVER_B200_P2P", "1") != "0"
+                 and str(self.comm.device).startswith("cuda"))
+        slot = _native.packet_bytes(max(1, _native.n_utility_blocks(self.n_kmers, 1000000)), self.PACKET_CAPACITY)
+        handle = np.zeros(64, dtype=np.uint8)
+        if ok:
+            try:
+                handle = shard.p2p_create(self.comm.rank, self.comm.world_size, slot)
+            except Exception:  # noqa: BLE001
+                ok = 0
+        if int(self.comm.allreduce_min(np.array([ok], dtype=np.int64))[0]) == 0:
+            return
+        local, gathered = self.comm.byte_buffers(64)
+        local.copy_(local.new_tensor(handle))
+        handles = self.comm.allgather_bytes(local, gathered)
+        try:
+            shard.p2p_connect(handles)
+        except Exception:  # noqa: BLE001
+            ok = 0
+        if int(self.comm.allreduce_min(np.array([ok], dtype=np.int64))[0]) == 1:
+            self.p2p_slot_bytes = slot
 
     # ------------------------------------------------------------------ upload
     def upload_block(self, block, row0, gcol0):
@@ -191,8 +208,13 @@ class ShardGroup(object):
         if self._single:
             return self.shards[0].scm_best_rules(pos_mask, neg_mask, n_pos, n_neg, p, util_block_size)
         if self.comm is not None and len(self.shards) == 1 and hasattr(self.shards[0], "scm_scan_packet"):
-            out, bm, best, sel = self._scm_best_rules_one_exchange(pos_mask, neg_mask, n_pos, n_neg, p,
-                                                                   util_block_size)
+            nb = _native.n_utility_blocks(self.n_kmers, util_block_size)
+            if self.p2p_slot_bytes >= _native.packet_bytes(nb, self.PACKET_CAPACITY):
+                out, bm, best, sel = self.shards[0].scm_best_rules_p2p(pos_mask, neg_mask, n_pos, n_neg, p,
+                                                                        util_block_size, self.PACKET_CAPACITY)
+            else:
+                out, bm, best, sel = self._scm_best_rules_one_exchange(pos_mask, neg_mask, n_pos, n_neg, p,
+                                                                       util_block_size)
             if out is not None:
                 self.exchange_stats["one_exchange"] += 1
                 return out

@@ -1,0 +1,78 @@
+"""Worker of tests/test_multigpu_nccl.py: one rank per GPU (NCCL).  Each rank holds a column shard on its own
+GPU; the sharded learners must reproduce the CPU checker bit for bit through BOTH exchange paths (peer
+mailbox over NVLink, NCCL all-gather)."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "golden")]
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+from kover_b200.learning.common.rules import KmerRuleClassifications, LazyKmerRuleList  # noqa: E402
+from kover_b200.learning.learners import cart as kcart, scm as kscm  # noqa: E402
+from kover_b200.sharding import Comm  # noqa: E402
+from kover_b200.synthetic import synthetic_block, synthetic_labels, train_split  # noqa: E402
+from oracle import kover_oracle as ko  # noqa: E402
+
+
+def main():
+    lr = int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(lr)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+    comm = Comm()
+    seed, n, k = 5, 900, 300000
+    P = synthetic_block(seed, n, 0, k)
+    y = synthetic_labels(seed, n, sorted_by_label=False)
+    train = train_split(seed, n)
+    pos, neg = train[y[train] == 1], train[y[train] == 0]
+    orc = ko.OracleKmerRuleClassifications(P, n, fast=True)
+    blacklist = [3, k + 7, 2 * k - 1]
+    bl = np.zeros(2 * k, dtype=bool)
+    bl[blacklist] = True
+    used = {}
+    for p2p in ("1", "0"):
+        os.environ["KOVER_B200_P2P"] = p2p
+        rc = KmerRuleClassifications(P, n, devices=[lr], comm=comm)
+        used[p2p] = rc._group.p2p_slot_bytes > 0
+        got = rc.sum_rows(pos)
+        assert np.array_equal(got, orc.sum_rows(pos))
+        for p, ubs in ((1.0, 1000000), (0.316, 99991), (999999.0, 1000000), (2.0, 4096)):
+            wu, wi, wp, wn = ko.merge_utility_blocks(len(neg) - orc.sum_rows(neg), len(pos) - orc.sum_rows(pos), p, bl,
+                                                     block_size=ubs)
+            for rep in range(3):            # consecutive steps alternate the mailbox parity
+                bu, bi, bp, bn = rc.best_utility_rules(p, pos, neg, rule_blacklist=blacklist, util_block_size=ubs)
+                assert bu == wu and np.array_equal(bi, np.asarray(wi, dtype=np.int64)), (p2p, p, ubs)
+                assert np.array_equal(bp, wp) and np.array_equal(bn, wn)
+        # a full fit and a tree
+        rules = LazyKmerRuleList(["K%d" % i for i in range(k)], np.arange(k))
+        m = kscm.SetCoveringMachine(model_type="conjunction", p=1.0, max_rules=4)
+        m.fit(rules, rc, pos, neg, tiebreaker=lambda idx: idx)
+        want_model, _, want_imp = ko.scm_fit(orc, "conjunction", 1.0, 4, pos, neg, tiebreaker=lambda idx: idx)
+        assert [int(r.kmer_index) + (k if r.type == "absence" else 0) for r in m.model.rules] == want_model
+        assert np.array_equal(np.asarray(m.rule_importances), np.asarray(want_imp))
+        ex = {0: neg, 1: pos}
+        t = kcart.DecisionTreeClassifier("gini", 3, 2, {0: 1.0, 1: 1.0})
+        t.fit(rules, rc, ex)
+        root = ko.cart_fit(orc, ex, "gini", 3, 2, {0: 1.0, 1: 1.0})
+
+        def walk(a, b):
+            assert (a.rule is None) == b.is_leaf
+            if a.rule is not None:
+                assert int(a.rule_idx) == int(b.rule_idx) and float(a.criterion_value) == float(b.criterion_value)
+                walk(a.left_child, b.left_child)
+                walk(a.right_child, b.right_child)
+        walk(t.decision_tree, root)
+        stats = dict(rc._group.exchange_stats)
+        rc.close()
+    comm.barrier()
+    if comm.rank == 0:
+        print("NCCL_WORKER_OK p2p_used=%s nccl_used=%s stats=%s" % (used["1"], not used["0"], stats))
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
