@@ -104,6 +104,10 @@ int kv_inplace_popcount_32(int device, uint32_t *arr, int64_t m, int64_t n, cons
  * _minimum_uint_size dtype, utils.py:117-130).  The absence half is len(rows) - out (rules.py:265)
  * and is left to the caller. */
 int kv_sum_rows(kv_shard *s, const uint64_t *mask, void *out, int out_itemsize);
+/* Both halves of the reference's return value: out_presence[n_cols] as kv_sum_rows, out_absence[n_cols] =
+ * n_rows - presence evaluated in the output dtype (rules.py:265). */
+int kv_sum_rows_full(kv_shard *s, const uint64_t *mask, int64_t n_rows, void *out_presence, void *out_absence,
+                     int out_itemsize);
 /* Several masks in one pass over the matrix (the reference's own TODO, rules.py:200).
  * masks: [n_masks, W]; out: [n_masks, n_cols] uint32. */
 int kv_sum_rows_multi(kv_shard *s, int n_masks, const uint64_t *masks, uint32_t *out);
@@ -185,6 +189,10 @@ int kv_gini_scan(kv_shard *s, int n_classes, const uint64_t *class_masks, const 
                  const double *n_total, const int64_t *n_node, double *min_score);
 /* Phase 2: rules with score == min_score exactly (cart.py:238), GLOBAL indices ascending. */
 int kv_gini_ties(kv_shard *s, double min_score, int64_t capacity, int64_t *rule_idx, int64_t *n_found);
+/* Single-shard convenience: both phases in one call with one host synchronisation. */
+int kv_gini_best_split(kv_shard *s, int n_classes, const uint64_t *class_masks, const double *altered_prior,
+                       const double *n_total, const int64_t *n_node, double *min_score, int64_t capacity,
+                       int64_t *rule_idx, int64_t *n_found);
 /* The split scores themselves (testing / callers that want rules_criterion): out[n_cols]. */
 int kv_gini_scores(kv_shard *s, double *out);
 

@@ -42,6 +42,7 @@ SYMBOLS = {
     "kv_inplace_popcount_64": (ctypes.c_int, [ctypes.c_int, _c_p, _c_i64, _c_i64, _c_p]),
     "kv_inplace_popcount_32": (ctypes.c_int, [ctypes.c_int, _c_p, _c_i64, _c_i64, _c_p]),
     "kv_sum_rows": (ctypes.c_int, [_c_p, _c_p, _c_p, ctypes.c_int]),
+    "kv_sum_rows_full": (ctypes.c_int, [_c_p, _c_p, _c_i64, _c_p, _c_p, ctypes.c_int]),
     "kv_sum_rows_multi": (ctypes.c_int, [_c_p, ctypes.c_int, _c_p, _c_p]),
     "kv_get_columns": (ctypes.c_int, [_c_p, _c_p, _c_i64, _c_p]),
     "kv_set_blacklist": (ctypes.c_int, [_c_p, _c_p, _c_i64]),
@@ -64,6 +65,8 @@ SYMBOLS = {
                                          ctypes.POINTER(ctypes.c_double), _c_i64, _c_p, _c_p, _c_p,
                                          ctypes.POINTER(_c_i64)]),
     "kv_gini_scan": (ctypes.c_int, [_c_p, ctypes.c_int, _c_p, _c_p, _c_p, _c_p, ctypes.POINTER(ctypes.c_double)]),
+    "kv_gini_best_split": (ctypes.c_int, [_c_p, ctypes.c_int, _c_p, _c_p, _c_p, _c_p, ctypes.POINTER(ctypes.c_double),
+                                          _c_i64, _c_p, ctypes.POINTER(_c_i64)]),
     "kv_gini_ties": (ctypes.c_int, [_c_p, ctypes.c_double, _c_i64, _c_p, ctypes.POINTER(_c_i64)]),
     "kv_gini_scores": (ctypes.c_int, [_c_p, _c_p]),
 }
@@ -201,6 +204,13 @@ class Shard(object):
         check(self._lib.kv_sum_rows(self._h, ptr(mask), ptr(out), out.itemsize))
         return out
 
+    def sum_rows_full(self, mask, n_rows, out_presence, out_absence):
+        mask = np.ascontiguousarray(mask, dtype=np.uint64)
+        assert mask.shape == (self.n_words,) and out_presence.shape == out_absence.shape == (self.n_cols,)
+        assert out_presence.dtype == out_absence.dtype
+        check(self._lib.kv_sum_rows_full(self._h, ptr(mask), int(n_rows), ptr(out_presence), ptr(out_absence),
+                                         out_presence.itemsize))
+
     def sum_rows_multi(self, masks):
         masks = np.ascontiguousarray(masks, dtype=np.uint64)
         assert masks.ndim == 2 and masks.shape[1] == self.n_words
@@ -326,6 +336,22 @@ class Shard(object):
         check(self._lib.kv_gini_scan(self._h, masks.shape[0], ptr(masks), ptr(pri), ptr(tot), ptr(nn),
                                      ctypes.byref(out)))
         return out.value
+
+    def gini_best_split(self, class_masks, altered_prior, n_total, n_node, capacity=4096):
+        """Single-shard fused call -> (min score, rule indices achieving it, ascending)."""
+        masks = np.ascontiguousarray(class_masks, dtype=np.uint64)
+        assert masks.ndim == 2 and masks.shape[1] == self.n_words
+        pri = np.ascontiguousarray(altered_prior, dtype=np.float64)
+        tot = np.ascontiguousarray(n_total, dtype=np.float64)
+        nn = np.ascontiguousarray(n_node, dtype=np.int64)
+        idx = np.empty(capacity, dtype=np.int64)
+        m, n = ctypes.c_double(0.0), _c_i64(0)
+        rc = self._lib.kv_gini_best_split(self._h, masks.shape[0], ptr(masks), ptr(pri), ptr(tot), ptr(nn),
+                                          ctypes.byref(m), capacity, ptr(idx), ctypes.byref(n))
+        if rc == KV_E_OVERFLOW:      # the counts and the minimum are still on the device
+            return m.value, self.gini_ties(m.value, int(n.value))
+        check(rc)
+        return m.value, idx[:n.value]
 
     def gini_ties(self, min_score, capacity=4096):
         while True:

@@ -70,7 +70,7 @@ extern "C" int kv_device_count(int *n) {
 // constants
 // ------------------------------------------------------------------------------------------------
 static constexpr int TILE_COLS = 512;    // columns per tile of the direct-load kernels: 256 threads x one 128-bit load
-static constexpr int LD_ALIGN = 3072;    // row pitch granularity: a multiple of every tile width (256/512/768/1024)
+static constexpr int LD_ALIGN = 1024;    // row pitch granularity: a multiple of every tile width (512 / 1024 columns)
 static constexpr int SCAN_THREADS = 256;
 static constexpr int MAX_MULTI = 8;      // masks per pass of k_count_multi
 static constexpr int MAX_CLASSES = 64;
@@ -165,9 +165,31 @@ struct Scan2Params {
     const uint32_t *black_pres, *black_abs;   // bitmaps over local columns or null
     unsigned long long *blockmax;             // enc_f64 per utility block
     unsigned long long *segmax;               // enc_f64 per 64-column segment: [2][ld / 64] (presence, absence)
+    // Gini epilogue (two classes = the two masks, in the caller's dict order): cart.py:71-77, 99-110
+    double g_prior[2], g_ntot[2], g_nnode[2];
+    unsigned long long *gmin;                 // enc_f64 of the minimum split score; segmax[0..ld/64) holds segment minima
 };
 
-enum { EPI_COUNTS = 0, EPI_SCM = 1 };
+enum { EPI_COUNTS = 0, EPI_SCM = 1, EPI_GINI2 = 2 };
+
+// _gini_rule_score for two classes (cart.py:112-161) in numpy's operation order; l0/l1 = examples of
+// class 0/1 WITH the k-mer.  Identical arithmetic to gini_score<2> below (k_gini), kept separate so the
+// scan kernel does not carry the 64-class parameter block.
+__device__ __forceinline__ double gini2_child(double n0, double n1, const Scan2Params &P) {
+    double q0 = __ddiv_rn(__dmul_rn(P.g_prior[0], n0), P.g_ntot[0]);
+    double q1 = __ddiv_rn(__dmul_rn(P.g_prior[1], n1), P.g_ntot[1]);
+    const double pt = __dadd_rn(q0, q1);
+    q0 = __ddiv_rn(q0, pt);
+    q1 = __ddiv_rn(q1, pt);
+    const double div = __dadd_rn(__dmul_rn(q0, q1), __dmul_rn(q1, q0));
+    return __dmul_rn(div, pt);
+}
+__device__ __forceinline__ double gini2_score(uint32_t c0, uint32_t c1, bool blacklisted, const Scan2Params &P) {
+    const double l0 = (double)c0, l1 = (double)c1;
+    const double r0 = P.g_nnode[0] - l0, r1 = P.g_nnode[1] - l1;
+    if (blacklisted || l0 + l1 == 0.0 || r0 + r1 == 0.0) return INFINITY;       // cart.py:231, 158-159
+    return __dadd_rn(gini2_child(l0, l1, P), gini2_child(r0, r1, P));
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
@@ -205,6 +227,13 @@ __device__ __forceinline__ unsigned long long warp_max_enc(unsigned long long e)
     const uint32_t hi = (uint32_t)(e >> 32), lo = (uint32_t)e;
     const uint32_t mh = __reduce_max_sync(0xffffffffu, hi);
     const uint32_t ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+    return ((unsigned long long)mh << 32) | ml;
+}
+
+__device__ __forceinline__ unsigned long long warp_min_enc(unsigned long long e) {
+    const uint32_t hi = (uint32_t)(e >> 32), lo = (uint32_t)e;
+    const uint32_t mh = __reduce_min_sync(0xffffffffu, hi);
+    const uint32_t ml = __reduce_min_sync(0xffffffffu, hi == mh ? lo : 0xffffffffu);
     return ((unsigned long long)mh << 32) | ml;
 }
 
@@ -311,6 +340,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) k_scan_tma(const Scan2Par
     run[0].lo = run[1].lo = 1; run[0].hi = run[1].hi = 0; run[0].bid = run[1].bid = -1;
     run[0].mx = run[1].mx = -INFINITY;
     const double neg_inf = -INFINITY;
+    double gini_min = INFINITY;
     int s = 0;
     uint32_t ph = 0;
     for (long long tile = t0; tile < t1; ++tile) {
@@ -335,6 +365,17 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) k_scan_tma(const Scan2Par
         *reinterpret_cast<uint2 *>(P.cnt0 + col) = make_uint2(c0x, c0y);
         if (P.cnt1) *reinterpret_cast<uint2 *>(P.cnt1 + col) = make_uint2(c1x, c1y);
 
+        if (EPI == EPI_GINI2) {
+            const bool vx = col < P.n_cols, vy = col + 1 < P.n_cols;
+            uint32_t bp = 0;
+            if (P.black_pres) bp = P.black_pres[col >> 5] >> (col & 31);
+            const double sx = vx ? gini2_score(c0x, c1x, bp & 1u, P) : INFINITY;
+            const double sy = vy ? gini2_score(c0y, c1y, bp & 2u, P) : INFINITY;
+            const double sm = fmin(sx, sy);
+            const unsigned long long seg = warp_min_enc(enc_f64(sm));
+            if (lane == 0) P.segmax[col >> 6] = seg;
+            gini_min = fmin(gini_min, sm);
+        }
         if (EPI == EPI_SCM) {
             const bool vx = col < P.n_cols, vy = col + 1 < P.n_cols;
             uint32_t bp = 0, ba = 0;
@@ -386,6 +427,17 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) k_scan_tma(const Scan2Par
     if (EPI == EPI_SCM) {
         runmax_flush<CW>(run[0], P.blockmax, s_red);
         runmax_flush<CW>(run[1], P.blockmax, s_red);
+    }
+    if (EPI == EPI_GINI2) {
+        const unsigned long long v = warp_min_enc(enc_f64(gini_min));
+        consumer_bar(CW * 32);
+        if (lane == 0) s_red[warp] = v;
+        consumer_bar(CW * 32);
+        if (threadIdx.x == 0) {
+            unsigned long long m = s_red[0];
+            for (int w = 1; w < CW; ++w) m = s_red[w] < m ? s_red[w] : m;
+            atomicMin(P.gmin, m);
+        }
     }
 }
 
@@ -642,6 +694,8 @@ struct GiniParams {
     const uint32_t *black_pres;
     unsigned long long *min_enc;    // MODE_MIN
     double min_score;               // MODE_TIES
+    const double *min_ptr;          // MODE_TIES: read the minimum from device memory instead (fused call)
+    const unsigned long long *segmin;   // MODE_TIES: enc_f64 minima of the 64-column segments, or null
     long long *out_idx;
     unsigned long long *counter;
     long long cap;
@@ -701,12 +755,26 @@ __global__ void __launch_bounds__(256) k_gini(const GiniParams P) {
     __shared__ double s_red[8];
     const long long stride = (long long)gridDim.x * blockDim.x;
     double mn = INFINITY;
+    double target = 0.0;
+    if (MODE == GINI_TIES) {
+        target = P.min_score;
+        if (P.min_ptr) {                                   // enc_f64 image left by the scan kernel
+            const unsigned long long v = *reinterpret_cast<const unsigned long long *>(P.min_ptr);
+            target = (v == ~0ull) ? INFINITY : dec_f64_max_dev(v);
+        }
+        if (target == INFINITY) return;                    // no admissible split: nothing ties (cart.py:234-235)
+    }
     for (long long col = (long long)blockIdx.x * blockDim.x + threadIdx.x; col < P.n_cols; col += stride) {
+        if (MODE == GINI_TIES && P.segmin) {
+            // the segment's minimum is exact, so a segment whose minimum differs holds no tie (cart.py:238)
+            const unsigned long long v = P.segmin[col >> 6];
+            if (v == ~0ull || dec_f64_max_dev(v) != target) continue;
+        }
         const double s = gini_score<NC>(col, P);
         if (MODE == GINI_MIN) {
             mn = fmin(mn, s);      // NaN-ignoring; the reference's scores hold no NaN for valid priors
         } else if (MODE == GINI_TIES) {
-            if (s == P.min_score) {
+            if (s == target) {
                 const unsigned long long slot = atomicAdd(P.counter, 1ull);
                 if ((long long)slot < P.cap) P.out_idx[slot] = P.col0 + col;
             }
@@ -721,6 +789,43 @@ __global__ void __launch_bounds__(256) k_gini(const GiniParams P) {
         if (threadIdx.x == 0) {
             for (int w = 1; w < 8; ++w) mn = fmin(mn, s_red[w]);
             atomicMin(P.min_enc, enc_f64(mn));
+        }
+    }
+}
+
+// Tie collection when the scan left exact per-segment minima: one lane screens one 64-column segment
+// (156 k segments for 10 M k-mers), the warp then rescans only the segments whose minimum IS the target.
+__global__ void __launch_bounds__(256) k_gini2_ties_seg(const GiniParams P) {
+    double target = P.min_score;
+    if (P.min_ptr) {
+        const unsigned long long v = *reinterpret_cast<const unsigned long long *>(P.min_ptr);
+        target = (v == ~0ull) ? INFINITY : dec_f64_max_dev(v);
+    }
+    if (target == INFINITY) return;
+    const int lane = threadIdx.x & 31;
+    const long long n_seg = (P.n_cols + 63) >> 6;
+    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long sb = warp0 * 32; sb < n_seg; sb += n_warps * 32) {
+        const long long g = sb + lane;
+        bool cand = false;
+        if (g < n_seg) {
+            const unsigned long long v = P.segmin[g];
+            cand = v != ~0ull && dec_f64_max_dev(v) == target;
+        }
+        unsigned todo = __ballot_sync(0xffffffffu, cand);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const long long col = ((sb + src) << 6) + lane + 32 * j;
+                if (col >= P.n_cols) continue;
+                if (gini_score<2>(col, P) == target) {
+                    const unsigned long long slot = atomicAdd(P.counter, 1ull);
+                    if ((long long)slot < P.cap) P.out_idx[slot] = P.col0 + col;
+                }
+            }
         }
     }
 }
@@ -758,6 +863,18 @@ __global__ void k_popc_inplace(T *arr, long long m, long long n, const T *mask) 
             const T x = v & mask[i / n];
             arr[i] = sizeof(T) == 8 ? (T)__popcll((unsigned long long)x) : (T)__popc((unsigned int)x);
         }
+    }
+}
+
+// presence counts -> the reference's result dtype, plus the absence half len(rows) - presence computed in
+// that dtype (rules.py:265: unsigned wrap-around included)
+template <typename T>
+__global__ void k_narrow2(const uint32_t *src, T *pres, T *absn, long long n, unsigned long long n_rows) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const T v = (T)src[i];
+        pres[i] = v;
+        absn[i] = (T)((T)n_rows - v);
     }
 }
 
@@ -810,6 +927,8 @@ struct DevBuf {
 
 struct kv_p2p;
 static void p2p_destroy(kv_p2p *m);
+struct kv_shard;
+static int finish_scan_timing(kv_shard *s);
 
 struct kv_shard {
     kv_p2p *p2p = nullptr;                    // peer mailbox (multi-rank), optional
@@ -1216,21 +1335,11 @@ static int check_smem(size_t bytes) {
 #define KV_SCAN_VARIANTS(X) \
     X(0, 8, 4, 4, 2)        \
     X(1, 16, 8, 3, 1)       \
-    X(2, 8, 4, 3, 3)        \
-    X(3, 8, 2, 8, 2)        \
-    X(4, 16, 4, 3, 2)       \
-    X(5, 16, 2, 4, 2)       \
-    X(6, 8, 8, 2, 2)        \
-    X(7, 8, 4, 6, 2)        \
-    X(8, 4, 4, 4, 4)        \
-    X(9, 16, 4, 6, 1)       \
-    X(10, 16, 4, 4, 1)      \
-    X(11, 8, 4, 2, 4)       \
-    X(12, 8, 4, 8, 1)       \
-    X(13, 12, 4, 4, 2)      \
-    X(14, 16, 8, 2, 2)      \
-    X(15, 8, 8, 3, 2)
-static constexpr int kNumScanVariants = 16;
+    X(2, 16, 4, 3, 2)       \
+    X(3, 16, 2, 4, 2)       \
+    X(4, 16, 4, 6, 1)       \
+    X(5, 16, 4, 4, 1)
+static constexpr int kNumScanVariants = 6;
 
 template <int EPI, int CW, int R, int S, int MINB>
 static int launch_scan_variant(kv_shard *s, const Scan2Params &P) {
@@ -1255,10 +1364,10 @@ static int launch_scan(kv_shard *s, const Scan2Params &P, int n_both) {
     // Default: variant 1 (16 consumer warps, 8 rows x 8 KB per stage, 3 stages = 192 KB in flight per SM) --
     // within 1 % of the best variant for label-sorted masks and the best when both masks hit every
     // row (profiles/README.md).  With more than ~1500 active packed rows the mask staging no longer fits
-    // beside that ring: variant 10 (128 KB ring).
+    // beside that ring: variant 5 (128 KB ring).
     (void)n_both;
     int v = s->scan_variant;
-    if (v < 0 || v >= kNumScanVariants) v = ((size_t)P.n_act * 20 > 30 * 1024) ? 10 : 1;
+    if (v < 0 || v >= kNumScanVariants) v = ((size_t)P.n_act * 20 > 30 * 1024) ? 5 : 1;
     CU(cudaEventRecord(s->ev0, s->stream));
     int rc = KV_OK;
     switch (v) {
@@ -1309,6 +1418,40 @@ extern "C" int kv_sum_rows(kv_shard *s, const uint64_t *mask, void *out, int out
     CU(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
     s->last_kernel_ms = ms;
     return KV_OK;
+}
+
+extern "C" int kv_sum_rows_full(kv_shard *s, const uint64_t *mask, int64_t n_rows, void *out_presence,
+                                void *out_absence, int out_itemsize) {
+    if (!s || !mask || !out_presence || !out_absence) return fail(KV_E_INVALID, "kv_sum_rows_full: null pointer");
+    if (out_itemsize != 1 && out_itemsize != 2 && out_itemsize != 4 && out_itemsize != 8)
+        return fail(KV_E_INVALID, "kv_sum_rows_full: out_itemsize must be 1, 2, 4 or 8");
+    if (n_rows < 0) return fail(KV_E_INVALID, "kv_sum_rows_full: negative n_rows");
+    DeviceGuard g(s->device);
+    s->last_launches = 0;
+    KV_TRY(ensure_counts(s, 1));
+    int n_act, n_both;
+    KV_TRY(push_records2(s, mask, nullptr, n_act, n_both));
+    Scan2Params P;
+    fill_scan2(s, P, n_act);
+    P.cnt0 = s->d_cnt[0];
+    P.cnt1 = nullptr;
+    KV_TRY(launch_scan<EPI_COUNTS>(s, P, n_both));
+    s->scm_valid = s->gini_valid = false;
+    const size_t half = (size_t)s->n_cols * out_itemsize;
+    KV_TRY(ensure(s->d_stage, 2 * half + 64));
+    char *d_p = (char *)s->d_stage.p, *d_a = d_p + (half + 15) / 16 * 16;
+    const unsigned grid = (unsigned)std::min<long long>((s->n_cols + 255) / 256, (long long)s->sm_count * 8);
+    const unsigned long long nr = (unsigned long long)n_rows;
+    if (out_itemsize == 1) k_narrow2<uint8_t><<<grid, 256, 0, s->stream>>>(s->d_cnt[0], (uint8_t *)d_p, (uint8_t *)d_a, s->n_cols, nr);
+    else if (out_itemsize == 2) k_narrow2<uint16_t><<<grid, 256, 0, s->stream>>>(s->d_cnt[0], (uint16_t *)d_p, (uint16_t *)d_a, s->n_cols, nr);
+    else if (out_itemsize == 4) k_narrow2<uint32_t><<<grid, 256, 0, s->stream>>>(s->d_cnt[0], (uint32_t *)d_p, (uint32_t *)d_a, s->n_cols, nr);
+    else k_narrow2<uint64_t><<<grid, 256, 0, s->stream>>>(s->d_cnt[0], (uint64_t *)d_p, (uint64_t *)d_a, s->n_cols, nr);
+    count_launch(s);
+    CU(cudaMemcpyAsync(out_presence, d_p, half, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaMemcpyAsync(out_absence, d_a, half, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    CU(cudaGetLastError());
+    return finish_scan_timing(s);
 }
 
 // counts of n_masks masks into d_cnt[first .. first+n_masks) (device resident)
@@ -1469,7 +1612,7 @@ static MiscLayout misc_layout(void *base, long long n_blocks) {
     return L;
 }
 
-static constexpr long long kTieFirstBatch = 2048;   // tie records fetched together with the header
+static constexpr long long kTieFirstBatch = 256;   // tie records fetched together with the header
 
 static int ensure_ties(kv_shard *s, long long cap) {
     return ensure(s->d_ties, sizeof(TieHeader) + (size_t)std::max<long long>(cap, kTieFirstBatch) * sizeof(TieRec));
@@ -2009,33 +2152,22 @@ static void launch_gini(kv_shard *s, const GiniParams &G) {
     count_launch(s);
 }
 
-extern "C" int kv_gini_scan(kv_shard *s, int n_classes, const uint64_t *class_masks, const double *altered_prior,
-                            const double *n_total, const int64_t *n_node, double *min_score) {
-    if (!s || !class_masks || !altered_prior || !n_total || !n_node || !min_score)
-        return fail(KV_E_INVALID, "kv_gini_scan: null pointer");
+// Launch the counting (+ for two classes the fused Gini minimum) of one node; nothing is synchronised.
+// d_misc: [0] minimum (enc_f64), [1] tie counter.
+static int gini_scan_async(kv_shard *s, int n_classes, const uint64_t *class_masks, const double *altered_prior,
+                           const double *n_total, const int64_t *n_node) {
     if (n_classes < 1 || n_classes > MAX_CLASSES) return fail(KV_E_INVALID, "kv_gini_scan: 1..64 classes supported");
-    DeviceGuard g(s->device);
-    s->last_launches = 0;
     s->scm_valid = false;
     s->gini_valid = false;
-    if (n_classes == 2) {
-        // two disjoint class masks: the grouped two-mask scan reads each packed row once
-        KV_TRY(ensure_counts(s, 2));
-        int n_act, n_both;
-        KV_TRY(push_records2(s, class_masks, class_masks + s->W, n_act, n_both));
-        Scan2Params P;
-        fill_scan2(s, P, n_act);
-        P.cnt0 = s->d_cnt[0];
-        P.cnt1 = s->d_cnt[1];
-        KV_TRY(launch_scan<EPI_COUNTS>(s, P, n_both));
-    } else {
-        KV_TRY(count_masks(s, n_classes, class_masks, 0));
-    }
+    KV_TRY(ensure(s->d_misc, 64));
+    unsigned long long *d_min = (unsigned long long *)s->d_misc.p;
+    // (d_misc doubles as the SCM block-maxima accumulator, which must be left zeroed: see kv_gini tail)
+    CU(cudaMemsetAsync(d_min, 0xFF, 8, s->stream));
+    CU(cudaMemsetAsync(d_min + 1, 0, 8, s->stream));
     GiniParams &G = s->gini;
     memset(&G, 0, sizeof G);
     G.n_classes = n_classes;
     for (int c = 0; c < n_classes; ++c) {
-        G.cnt[c] = s->d_cnt[c];
         G.prior[c] = altered_prior[c];
         G.n_total[c] = n_total[c];
         G.n_node[c] = (double)n_node[c];
@@ -2043,22 +2175,105 @@ extern "C" int kv_gini_scan(kv_shard *s, int n_classes, const uint64_t *class_ma
     G.n_cols = s->n_cols;
     G.col0 = s->col0;
     G.black_pres = s->have_black ? s->d_black_pres : nullptr;
-    KV_TRY(ensure(s->d_misc, 64));
-    G.min_enc = (unsigned long long *)s->d_misc.p;
-    G.counter = G.min_enc + 1;
-    CU(cudaMemsetAsync(G.min_enc, 0xFF, 8, s->stream));
-    launch_gini<GINI_MIN>(s, G);
+    G.min_enc = d_min;
+    G.counter = d_min + 1;
+    if (n_classes == 2) {
+        // two class masks: one pass of the two-mask scan with the Gini score, its minimum and the
+        // per-segment minima fused into the epilogue
+        KV_TRY(ensure_counts(s, 2));
+        if (!s->d_segmax) CU(cudaMalloc(&s->d_segmax, (size_t)(s->ld / 64) * 2 * 8));
+        int n_act, n_both;
+        KV_TRY(push_records2(s, class_masks, class_masks + s->W, n_act, n_both));
+        Scan2Params P;
+        fill_scan2(s, P, n_act);
+        P.cnt0 = s->d_cnt[0];
+        P.cnt1 = s->d_cnt[1];
+        P.black_pres = G.black_pres;
+        P.segmax = s->d_segmax;
+        P.gmin = d_min;
+        for (int c = 0; c < 2; ++c) {
+            P.g_prior[c] = G.prior[c];
+            P.g_ntot[c] = G.n_total[c];
+            P.g_nnode[c] = G.n_node[c];
+        }
+        KV_TRY(launch_scan<EPI_GINI2>(s, P, n_both));
+        G.segmin = s->d_segmax;
+    } else {
+        KV_TRY(count_masks(s, n_classes, class_masks, 0));
+    }
+    for (int c = 0; c < n_classes; ++c) G.cnt[c] = s->d_cnt[c];
+    if (n_classes != 2) launch_gini<GINI_MIN>(s, G);
+    s->gini_valid = true;
+    return KV_OK;
+}
+
+// d_misc[0..1] were used as min / counter: restore the all-zero state the SCM accumulators expect
+static int gini_restore_misc(kv_shard *s) {
+    CU(cudaMemsetAsync(s->d_misc.p, 0, 16, s->stream));
+    return KV_OK;
+}
+
+extern "C" int kv_gini_scan(kv_shard *s, int n_classes, const uint64_t *class_masks, const double *altered_prior,
+                            const double *n_total, const int64_t *n_node, double *min_score) {
+    if (!s || !class_masks || !altered_prior || !n_total || !n_node || !min_score)
+        return fail(KV_E_INVALID, "kv_gini_scan: null pointer");
+    DeviceGuard g(s->device);
+    s->last_launches = 0;
+    KV_TRY(gini_scan_async(s, n_classes, class_masks, altered_prior, n_total, n_node));
     KV_TRY(ensure_pinned(s, 64));
-    CU(cudaMemcpyAsync(s->h_pin, G.min_enc, 8, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaMemcpyAsync(s->h_pin, s->gini.min_enc, 8, cudaMemcpyDeviceToHost, s->stream));
+    KV_TRY(gini_restore_misc(s));
     CU(cudaStreamSynchronize(s->stream));
     CU(cudaGetLastError());
-    if (n_classes == 2) {
-        float ms = 0;
-        CU(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
-        s->last_kernel_ms = ms;
-    }
+    if (n_classes == 2) KV_TRY(finish_scan_timing(s));
     *min_score = dec_f64_min(*(unsigned long long *)s->h_pin);
-    s->gini_valid = true;
+    return KV_OK;
+}
+
+static constexpr long long kGiniFirstBatch = 512;
+
+// ties of the last scan: target from `min_score`, or from the device-resident minimum when from_device
+static int gini_ties_impl(kv_shard *s, bool from_device, double min_score, int64_t capacity, int64_t *rule_idx,
+                          int64_t *n_found, double *min_out) {
+    const long long cap = std::max<long long>(capacity, kGiniFirstBatch);
+    // d_ties: [0] minimum copy, [1] counter, then the indices
+    KV_TRY(ensure(s->d_ties, 16 + (size_t)cap * 8));
+    unsigned long long *d_hdr = (unsigned long long *)s->d_ties.p;
+    GiniParams G = s->gini;
+    G.min_score = min_score;
+    G.min_ptr = from_device ? (const double *)d_hdr : nullptr;
+    G.counter = d_hdr + 1;
+    G.out_idx = (long long *)(d_hdr + 2);
+    G.cap = cap;
+    if (from_device) CU(cudaMemcpyAsync(d_hdr, s->gini.min_enc, 8, cudaMemcpyDeviceToDevice, s->stream));
+    CU(cudaMemsetAsync(d_hdr + 1, 0, 8, s->stream));
+    if (G.segmin && G.n_classes == 2) {
+        const long long n_seg = (s->n_cols + 63) / 64;
+        const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((n_seg + 255) / 256, (long long)s->sm_count * 4));
+        k_gini2_ties_seg<<<grid, 256, 0, s->stream>>>(G);
+        count_launch(s);
+    } else {
+        launch_gini<GINI_TIES>(s, G);
+    }
+    const size_t first = 16 + (size_t)kGiniFirstBatch * 8;
+    KV_TRY(ensure_pinned(s, first));
+    CU(cudaMemcpyAsync(s->h_pin, d_hdr, first, cudaMemcpyDeviceToHost, s->stream));
+    if (from_device) KV_TRY(gini_restore_misc(s));
+    CU(cudaStreamSynchronize(s->stream));
+    CU(cudaGetLastError());
+    const unsigned long long *h = (const unsigned long long *)s->h_pin;
+    if (min_out) *min_out = dec_f64_min(h[0]);
+    const long long found = (long long)h[1];
+    *n_found = found;
+    if (found > capacity) return fail(KV_E_OVERFLOW, "kv_gini_ties: tie buffer too small");
+    if (found == 0) return KV_OK;
+    if (found > kGiniFirstBatch) {
+        CU(cudaMemcpyAsync(rule_idx, G.out_idx, (size_t)found * 8, cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+    } else {
+        memcpy(rule_idx, h + 2, (size_t)found * 8);
+    }
+    std::sort(rule_idx, rule_idx + found);
     return KV_OK;
 }
 
@@ -2068,25 +2283,22 @@ extern "C" int kv_gini_ties(kv_shard *s, double min_score, int64_t capacity, int
     if (capacity < 0) return fail(KV_E_INVALID, "kv_gini_ties: negative capacity");
     DeviceGuard g(s->device);
     s->last_launches = 0;
-    const long long cap = std::max<long long>(capacity, 1);
-    KV_TRY(ensure(s->d_ties, (size_t)cap * 8));
-    GiniParams G = s->gini;
-    G.min_score = min_score;
-    G.out_idx = (long long *)s->d_ties.p;
-    G.cap = capacity;
-    CU(cudaMemsetAsync(G.counter, 0, 8, s->stream));
-    launch_gini<GINI_TIES>(s, G);
-    CU(cudaMemcpyAsync(s->h_pin, G.counter, 8, cudaMemcpyDeviceToHost, s->stream));
-    CU(cudaStreamSynchronize(s->stream));
-    CU(cudaGetLastError());
-    const long long found = (long long)*(unsigned long long *)s->h_pin;
-    *n_found = found;
-    if (found > capacity) return fail(KV_E_OVERFLOW, "kv_gini_ties: tie buffer too small");
-    if (found == 0) return KV_OK;
-    CU(cudaMemcpyAsync(rule_idx, G.out_idx, (size_t)found * 8, cudaMemcpyDeviceToHost, s->stream));
-    CU(cudaStreamSynchronize(s->stream));
-    std::sort(rule_idx, rule_idx + found);
-    return KV_OK;
+    return gini_ties_impl(s, false, min_score, capacity, rule_idx, n_found, nullptr);
+}
+
+extern "C" int kv_gini_best_split(kv_shard *s, int n_classes, const uint64_t *class_masks, const double *altered_prior,
+                                  const double *n_total, const int64_t *n_node, double *min_score, int64_t capacity,
+                                  int64_t *rule_idx, int64_t *n_found) {
+    if (!s || !class_masks || !altered_prior || !n_total || !n_node || !min_score || !n_found ||
+        (capacity > 0 && !rule_idx))
+        return fail(KV_E_INVALID, "kv_gini_best_split: null pointer");
+    if (capacity < 0) return fail(KV_E_INVALID, "kv_gini_best_split: negative capacity");
+    DeviceGuard g(s->device);
+    s->last_launches = 0;
+    KV_TRY(gini_scan_async(s, n_classes, class_masks, altered_prior, n_total, n_node));
+    const int rc = gini_ties_impl(s, true, 0.0, capacity, rule_idx, n_found, min_score);
+    if (n_classes == 2 && (rc == KV_OK || rc == KV_E_OVERFLOW)) finish_scan_timing(s);
+    return rc;
 }
 
 extern "C" int kv_gini_scores(kv_shard *s, double *out) {

@@ -246,11 +246,11 @@ class KmerRuleClassifications(BaseRuleClassifications):
         rows = np.asarray(rows)
         result_dtype = _minimum_uint_size(rows.shape[0])
         n_kmers = self._n_kmers
-        result = np.zeros(n_kmers * 2, dtype=result_dtype)
+        result = np.empty(n_kmers * 2, dtype=result_dtype)
         mask = self.row_mask(rows)
-        self._group.sum_rows_into(mask, result[:n_kmers])
-        # Compute the sum for absence rules
-        result[n_kmers:] = len(rows) - result[:n_kmers]
+        # presence counts and, for the absence rules, len(rows) - presence (rules.py:265): both halves are
+        # produced on the device in the result dtype
+        self._group.sum_rows_into(mask, len(rows), result)
         return result
 
     # ------------------------------------------------------------------ fused scans (this package's learners)

@@ -160,16 +160,23 @@ class ShardGroup(object):
             s.upload_block(block, row0, gcol0)
 
     # ------------------------------------------------------------------ a3
-    def sum_rows_into(self, mask, out):
-        """Presence counts of the LOCAL shards into out[col0:col0+n_cols] (out spans all K columns)."""
+    def sum_rows_into(self, mask, n_rows, out):
+        """The reference's sum_rows result (rules.py:201-267) into out[2K]: presence counts of the masked examples
+        in out[:K], n_rows - presence in out[K:], both written by the shards in the output dtype."""
+        k = self.n_kmers
         for s in self.shards:
-            s.sum_rows(mask, out[s.col0:s.col0 + s.n_cols])
+            if hasattr(s, "sum_rows_full"):
+                s.sum_rows_full(mask, n_rows, out[s.col0:s.col0 + s.n_cols], out[k + s.col0:k + s.col0 + s.n_cols])
+            else:
+                s.sum_rows(mask, out[s.col0:s.col0 + s.n_cols])
+                out[k + s.col0:k + s.col0 + s.n_cols] = n_rows - out[s.col0:s.col0 + s.n_cols]
         if self.comm is not None:
             # every rank needs the full vector to honour the reference's return value
             lo = min(s.col0 for s in self.shards)
             hi = max(s.col0 + s.n_cols for s in self.shards)
             full = self.comm.allgather_concat(out[lo:hi].astype(np.int64))
-            out[:] = full.astype(out.dtype)
+            out[:k] = full.astype(out.dtype)
+            out[k:] = n_rows - out[:k]
         return out
 
     # ------------------------------------------------------------------ a4
@@ -244,6 +251,8 @@ class ShardGroup(object):
     # ------------------------------------------------------------------ a9 / a11
     def gini_best_split(self, class_masks, altered_prior, n_total, n_node):
         """-> (min_score, presence-rule indices with score == min_score, ascending); cart.py:112-161, 231-238."""
+        if self._single and hasattr(self.shards[0], "gini_best_split"):
+            return self.shards[0].gini_best_split(class_masks, altered_prior, n_total, n_node)
         mins = [s.gini_scan(class_masks, altered_prior, n_total, n_node) for s in self.shards]
         m = min(mins)
         if self.comm is not None:
