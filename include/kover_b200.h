@@ -54,7 +54,8 @@ typedef struct kv_shard_info {
     int64_t last_launches;   /* kernels launched by the last call                        */
     int64_t total_launches;  /* kernels launched since kv_create                         */
     double scan_ms_total;    /* sum of the scan kernels' CUDA-event times since kv_create */
-    int64_t scan_calls;      /* SCM scans since kv_create                                */
+    int64_t scan_calls;      /* SCM matrix scans since kv_create                         */
+    int64_t rescore_calls;   /* SCM scans served from resident counts (kv_scm_reuse_counts) */
 } kv_shard_info;
 
 const char *kv_last_error(void);
@@ -129,6 +130,13 @@ int64_t kv_scm_n_blocks(int64_t n_kmers_total, int64_t util_block_size);
  * untouched blocks, so shards merge with an element-wise max. */
 int kv_scm_scan(kv_shard *s, const uint64_t *pos_mask, const uint64_t *neg_mask, int64_t n_pos,
                 int64_t n_neg, double p, int64_t util_block_size, double *block_max, int64_t n_blocks);
+/* Arms the NEXT kv_scm_scan / kv_scm_scan_packet / kv_scm_best_rules / kv_scm_best_rules_p2p call on this
+ * shard to skip the matrix pass and re-score the counts the previous scan left on the device: same two
+ * example masks, another p, and -- swap_roles = 1 -- positives and negatives exchanged relative to the
+ * masks of the scan that produced the counts (the disjunction swaps the labels, scm.py:69-73).  The armed
+ * call ignores its mask arguments (they may be NULL) and reads 8 bytes per k-mer instead of 8*W: every p of
+ * the hyper-parameter grid and both model types share the first iteration's counts. */
+int kv_scm_reuse_counts(kv_shard *s, int swap_roles);
 /* Host-only replay of the sequential block merge (scm.py:270-286) over the MERGED block maxima:
  * selected[b] = 1 for blocks whose ties survive; *best_utility as the reference returns it. */
 int kv_scm_select_blocks(const double *block_max, int64_t n_blocks, double *best_utility,

@@ -23,7 +23,7 @@ class ShardInfo(ctypes.Structure):
                 ("n_words", _c_i64), ("n_kmers_total", _c_i64), ("col0", _c_i64), ("n_cols", _c_i64),
                 ("ld", _c_i64), ("matrix_bytes", _c_i64), ("last_kernel_ms", ctypes.c_double),
                 ("last_launches", _c_i64), ("total_launches", _c_i64), ("scan_ms_total", ctypes.c_double),
-                ("scan_calls", _c_i64)]
+                ("scan_calls", _c_i64), ("rescore_calls", _c_i64)]
 
 
 # every exported symbol with (restype, argtypes); tests/test_abi.py checks this table against the header
@@ -47,6 +47,7 @@ SYMBOLS = {
     "kv_get_columns": (ctypes.c_int, [_c_p, _c_p, _c_i64, _c_p]),
     "kv_set_blacklist": (ctypes.c_int, [_c_p, _c_p, _c_i64]),
     "kv_scm_n_blocks": (_c_i64, [_c_i64, _c_i64]),
+    "kv_scm_reuse_counts": (ctypes.c_int, [_c_p, ctypes.c_int]),
     "kv_scm_scan": (ctypes.c_int, [_c_p, _c_p, _c_p, _c_i64, _c_i64, ctypes.c_double, _c_i64, _c_p, _c_i64]),
     "kv_scm_select_blocks": (ctypes.c_int, [_c_p, _c_i64, ctypes.POINTER(ctypes.c_double), _c_p]),
     "kv_scm_ties": (ctypes.c_int, [_c_p, _c_p, _c_p, _c_i64, _c_i64, _c_p, _c_p, _c_p, ctypes.POINTER(_c_i64)]),
@@ -144,6 +145,9 @@ class Shard(object):
         self.n_kmers_total = int(n_kmers_total)
         self.col0 = int(col0)
         self.n_cols = int(n_cols)
+        # reusable output buffers of the per-step calls (their contents are copied out before returning)
+        self._tie_cap = 4096
+        self._tie_buf = [np.empty(self._tie_cap, dtype=np.int64) for _ in range(3)]
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
@@ -230,6 +234,10 @@ class Shard(object):
         idx = np.ascontiguousarray(rule_idx, dtype=np.int64)
         check(self._lib.kv_set_blacklist(self._h, ptr(idx), idx.shape[0]))
 
+    def scm_reuse_counts(self, swap_roles=False):
+        """Arm the next scm_* call to re-score the resident counts instead of scanning (kv_scm_reuse_counts)."""
+        check(self._lib.kv_scm_reuse_counts(self._h, int(bool(swap_roles))))
+
     def scm_scan(self, pos_mask, neg_mask, n_pos, n_neg, p, util_block_size):
         nb = n_utility_blocks(self.n_kmers_total, util_block_size)
         bm = np.empty(nb, dtype=np.float64)
@@ -303,18 +311,19 @@ class Shard(object):
             return None, bm, best.value, sel
         return (best.value, idx[:n.value], pe[:n.value], nc[:n.value]), bm, best.value, sel
 
-    def scm_best_rules(self, pos_mask, neg_mask, n_pos, n_neg, p, util_block_size, capacity=4096):
-        pos_mask = np.ascontiguousarray(pos_mask, dtype=np.uint64)
-        neg_mask = np.ascontiguousarray(neg_mask, dtype=np.uint64)
+    def scm_best_rules(self, pos_mask, neg_mask, n_pos, n_neg, p, util_block_size, capacity=None):
+        if pos_mask.dtype != np.uint64 or neg_mask.dtype != np.uint64:
+            pos_mask, neg_mask = pos_mask.astype(np.uint64), neg_mask.astype(np.uint64)
         assert pos_mask.shape == (self.n_words,) and neg_mask.shape == (self.n_words,)
+        if capacity is None:
+            capacity, (idx, pe, nc) = self._tie_cap, self._tie_buf
+        else:
+            idx, pe, nc = (np.empty(capacity, dtype=np.int64) for _ in range(3))
         best = ctypes.c_double(0.0)
-        idx = np.empty(capacity, dtype=np.int64)
-        pe = np.empty(capacity, dtype=np.int64)
-        nc = np.empty(capacity, dtype=np.int64)
         n = _c_i64(0)
-        rc = self._lib.kv_scm_best_rules(self._h, ptr(pos_mask), ptr(neg_mask), int(n_pos), int(n_neg), float(p),
-                                         int(util_block_size), ctypes.byref(best), capacity, ptr(idx), ptr(pe),
-                                         ptr(nc), ctypes.byref(n))
+        rc = self._lib.kv_scm_best_rules(self._h, pos_mask.ctypes.data, neg_mask.ctypes.data, int(n_pos), int(n_neg),
+                                         float(p), int(util_block_size), ctypes.byref(best), capacity,
+                                         idx.ctypes.data, pe.ctypes.data, nc.ctypes.data, ctypes.byref(n))
         if rc == KV_E_OVERFLOW:
             # rare (huge equivalent-rule set): redo through the three-phase path with a buffer of the right size
             bm = self.scm_scan(pos_mask, neg_mask, n_pos, n_neg, p, util_block_size)
@@ -322,7 +331,8 @@ class Shard(object):
             idx, pe, nc = self.scm_ties(bm, sel, int(n.value))
             return best_v, idx, pe, nc
         check(rc)
-        return best.value, idx[:n.value], pe[:n.value], nc[:n.value]
+        m = n.value
+        return best.value, idx[:m].copy(), pe[:m].copy(), nc[:m].copy()
 
     # -- a9 / a11
     def gini_scan(self, class_masks, altered_prior, n_total, n_node):

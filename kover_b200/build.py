@@ -14,7 +14,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo",
     "--fmad=false",                      # the utility / Gini arithmetic must never be contracted
-    "-Xcompiler", "-fPIC,-ffp-contract=off",
+    "-Xcompiler", "-fPIC,-ffp-contract=off,-pthread",
     "-shared",
 ]
 

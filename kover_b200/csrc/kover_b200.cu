@@ -28,6 +28,7 @@
 #include <limits>
 #include <numeric>
 #include <string>
+#include <thread>
 #include <vector>
 
 // ------------------------------------------------------------------------------------------------
@@ -50,6 +51,18 @@ static int fail(int code, const std::string &msg) {
             return fail(e__ == cudaErrorMemoryAllocation ? KV_E_NOMEM : KV_E_CUDA, b__);           \
         }                                                                                          \
     } while (0)
+
+// Wait for a stream by polling: the per-step calls end in a microseconds-long tail, where the wake-up
+// latency of a blocking cudaStreamSynchronize would be a visible fraction of the step.
+static inline cudaError_t stream_sync_spin(cudaStream_t st) {
+    cudaError_t e;
+    while ((e = cudaStreamQuery(st)) == cudaErrorNotReady) {
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+    }
+    return e;
+}
 
 #define KV_TRY(call)                                                                               \
     do {                                                                                           \
@@ -150,6 +163,9 @@ __device__ __forceinline__ double warp_min(double v) {
 // The ring keeps ~128 KB of reads in flight per SM without holding registers, which the sweep in
 // tools/scan_sweep.cu measured at 96-98 % of the copy-bandwidth peak against 84-95 % for direct
 // loads (profiles/README.md).
+// up to this many active packed rows (4 096 genomes) ride in the kernel parameter block: no H2D copy per scan
+static constexpr int SCAN_INLINE_ROWS = 64;
+
 struct Scan2Params {
     const uint64_t *mat;
     long long ld, n_cols, col0, k_total;
@@ -157,6 +173,9 @@ struct Scan2Params {
     const uint32_t *rec_row;
     const uint64_t *rec_m0, *rec_m1;
     int n_act;
+    int inline_rec;                   // 1: the records travel in the kernel parameters (n_act <= SCAN_INLINE_ROWS)
+    uint64_t inl_m0[SCAN_INLINE_ROWS], inl_m1[SCAN_INLINE_ROWS];
+    uint32_t inl_row[SCAN_INLINE_ROWS];
     uint32_t *cnt0, *cnt1;            // [ld] each; cnt1 may be null (single-mask scan)
     // SCM epilogue
     double p;
@@ -287,10 +306,18 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) k_scan_tma(const Scan2Par
     uint64_t *s_m1 = s_m0 + n_act;
     uint32_t *s_row = reinterpret_cast<uint32_t *>(s_m1 + n_act);
     unsigned char *ring = smem_tma + ((size_t)(2 * S) * 8 + (size_t)n_act * 20 + 127) / 128 * 128;
-    for (int i = threadIdx.x; i < n_act; i += blockDim.x) {
-        s_m0[i] = P.rec_m0[i];
-        s_m1[i] = P.rec_m1[i];
-        s_row[i] = P.rec_row[i];
+    if (P.inline_rec) {
+        for (int i = threadIdx.x; i < n_act; i += blockDim.x) {
+            s_m0[i] = P.inl_m0[i];
+            s_m1[i] = P.inl_m1[i];
+            s_row[i] = P.inl_row[i];
+        }
+    } else {
+        for (int i = threadIdx.x; i < n_act; i += blockDim.x) {
+            s_m0[i] = P.rec_m0[i];
+            s_m1[i] = P.rec_m1[i];
+            s_row[i] = P.rec_row[i];
+        }
     }
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) {
@@ -618,6 +645,88 @@ __global__ void __launch_bounds__(256) k_scm_ties(const TieParams P) {
                 if (which & 2u) tie_emit(P, P.k_total + P.col0 + col, ba ? -INFINITY : scm_utility(c1, c0, P.p), c0, c1);
             }
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_scm_rescore: phase 1 from RESIDENT counts -- another p, or the two masks' roles swapped (the
+// disjunction swaps the example labels, scm.py:69-73), without touching the matrix: 8 bytes per column
+// instead of 8*W.  Produces exactly what k_scan_tma<EPI_SCM>'s epilogue produces (block maxima, segment
+// maxima) so phase 2 is unchanged.  One CTA per 2 048 columns, one warp per 64-column segment at a time.
+// ------------------------------------------------------------------------------------------------
+struct RescoreParams {
+    const uint32_t *cnt_pos, *cnt_neg;     // presence counts under the (possibly swapped) positive / negative mask
+    long long n_cols, ld, col0, k_total, ubs;
+    double p;
+    uint32_t n_pos, n_neg;
+    const uint32_t *black_pres, *black_abs;
+    unsigned long long *blockmax, *segmax;
+};
+
+__global__ void __launch_bounds__(256) k_scm_rescore(const RescoreParams P) {
+    __shared__ unsigned long long s_red[2][8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long chunk_c0 = (long long)blockIdx.x * 2048;
+    const long long chunk_n = min(2048ll, P.n_cols - chunk_c0);
+    unsigned long long run[2] = {0ull, 0ull};          // enc_f64 images; 0 = nothing seen
+    bool uniform[2];
+    long long bid[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const long long r0 = (long long)h * P.k_total + P.col0 + chunk_c0;
+        bid[h] = r0 / P.ubs;
+        uniform[h] = chunk_n > 0 && (r0 + chunk_n - 1) / P.ubs == bid[h];
+    }
+    for (int sg = warp; sg < 32; sg += 8) {
+        const long long seg_c0 = chunk_c0 + sg * 64;
+        double um[2] = {-INFINITY, -INFINITY};
+        double u[2][2];
+        bool valid[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const long long col = seg_c0 + lane + 32 * j;
+            valid[j] = col < P.n_cols;
+            u[0][j] = u[1][j] = -INFINITY;
+            if (valid[j]) {
+                const uint32_t cp = P.cnt_pos[col], cn = P.cnt_neg[col];
+                bool bp = false, ba = false;
+                if (P.black_pres) {
+                    bp = (P.black_pres[col >> 5] >> (col & 31)) & 1u;
+                    ba = (P.black_abs[col >> 5] >> (col & 31)) & 1u;
+                }
+                if (!bp) u[0][j] = scm_utility(P.n_neg - cn, P.n_pos - cp, P.p);
+                if (!ba) u[1][j] = scm_utility(cn, cp, P.p);
+            }
+            um[0] = fmax(um[0], u[0][j]);
+            um[1] = fmax(um[1], u[1][j]);
+        }
+        if (seg_c0 < P.ld) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const unsigned long long seg = warp_max_enc(enc_f64(um[h]));
+                if (lane == 0) P.segmax[(size_t)h * (P.ld >> 6) + (seg_c0 >> 6)] = seg;
+                if (uniform[h]) {
+                    run[h] = seg > run[h] ? seg : run[h];
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 2; ++j)
+                        if (valid[j]) {
+                            const long long r = (long long)h * P.k_total + P.col0 + seg_c0 + lane + 32 * j;
+                            atomicMax(P.blockmax + r / P.ubs, enc_f64(u[h][j]));
+                        }
+                }
+            }
+        }
+    }
+    if (lane == 0) {
+        s_red[0][warp] = run[0];
+        s_red[1][warp] = run[1];
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 && uniform[threadIdx.x]) {
+        unsigned long long m = 0ull;
+        for (int w = 0; w < 8; ++w) m = s_red[threadIdx.x][w] > m ? s_red[threadIdx.x][w] : m;
+        if (m) atomicMax(P.blockmax + bid[threadIdx.x], m);
     }
 }
 
@@ -954,14 +1063,14 @@ struct kv_shard {
     bool have_black = false;
 
     // state left by the last scan for phase 2
-    bool scm_valid = false;
+    bool scm_valid = false, scm_swapped = false, reuse_armed = false, reuse_swap = false;
     long long scm_n_pos = 0, scm_n_neg = 0, scm_ubs = 0;
     double scm_p = 0.0;
     bool gini_valid = false;
     GiniParams gini;
 
     double last_kernel_ms = 0.0, scan_ms_total = 0.0;
-    long long last_launches = 0, total_launches = 0, scan_calls = 0;
+    long long last_launches = 0, total_launches = 0, scan_calls = 0, rescore_calls = 0;
 };
 
 struct DeviceGuard {
@@ -1108,6 +1217,7 @@ extern "C" int kv_get_info(kv_shard *s, kv_shard_info *o) {
     o->total_launches = s->total_launches;
     o->scan_ms_total = s->scan_ms_total;
     o->scan_calls = s->scan_calls;
+    o->rescore_calls = s->rescore_calls;
     return KV_OK;
 }
 
@@ -1122,6 +1232,33 @@ static int ensure_upload_ring(kv_shard *s) {
         CU(cudaEventCreateWithFlags(&s->ev_up[i], cudaEventDisableTiming));
     }
     return KV_OK;
+}
+
+// Pageable host rows -> the pinned slot.  One memcpy stream tops out near 5 GB/s, a fraction of what the
+// PCIe Gen5 link takes, so large slots are split over a few threads (byte ranges of the flattened slot).
+static void stage_rows(char *pin, const char *src, long long n_rows, size_t row_bytes, size_t src_pitch) {
+    const size_t total = (size_t)n_rows * row_bytes;
+    auto copy_range = [&](size_t b0, size_t b1) {
+        while (b0 < b1) {
+            const size_t row = b0 / row_bytes, off = b0 % row_bytes;
+            const size_t n = std::min(row_bytes - off, b1 - b0);
+            memcpy(pin + b0, src + row * src_pitch + off, n);
+            b0 += n;
+        }
+    };
+    const unsigned hw = std::thread::hardware_concurrency();
+    const int n_threads = total < ((size_t)4 << 20) ? 1 : (int)std::max(1u, std::min(hw ? hw : 1u, 6u));
+    if (n_threads == 1) {
+        copy_range(0, total);
+        return;
+    }
+    std::vector<std::thread> pool;
+    const size_t chunk = ((total + n_threads - 1) / n_threads + 63) / 64 * 64;
+    for (int t = 0; t < n_threads; ++t) {
+        const size_t b0 = std::min(total, (size_t)t * chunk), b1 = std::min(total, b0 + chunk);
+        if (b0 < b1) pool.emplace_back(copy_range, b0, b1);
+    }
+    for (auto &th : pool) th.join();
 }
 
 extern "C" int kv_upload_block(kv_shard *s, int pack_bits, int64_t row0, int64_t n_rows, int64_t gcol0,
@@ -1157,9 +1294,8 @@ extern "C" int kv_upload_block(kv_shard *s, int pack_bits, int64_t row0, int64_t
         s->up_slot ^= 1;
         CU(cudaEventSynchronize(s->ev_up[slot]));
         char *pin = (char *)s->h_up[slot];
-        for (long long i = 0; i < nr; ++i)
-            memcpy(pin + (size_t)i * nc * esz, (const char *)host + ((size_t)(r + i) * ld_elems + src_off) * esz,
-                   (size_t)nc * esz);
+        stage_rows(pin, (const char *)host + ((size_t)r * ld_elems + src_off) * esz, nr, (size_t)nc * esz,
+                   (size_t)ld_elems * esz);
         if (pack_bits == 64) {
             CU(cudaMemcpy2DAsync(s->d_mat + (row0 + r) * s->ld + lcol0, (size_t)s->ld * 8, pin, (size_t)nc * 8,
                                  (size_t)nc * 8, (size_t)nr, cudaMemcpyHostToDevice, s->stream));
@@ -1302,8 +1438,10 @@ static int push_records2(kv_shard *s, const uint64_t *m0, const uint64_t *m1, in
         pm1[i] = m1 ? m1[w] : 0;
         prow[i] = (uint32_t)w;
     }
-    KV_TRY(ensure(s->d_rec, (size_t)n_act * 20 + 64));
-    if (n_act) CU(cudaMemcpyAsync(s->d_rec.p, s->h_pin, (size_t)n_act * 20, cudaMemcpyHostToDevice, s->stream));
+    if (n_act > SCAN_INLINE_ROWS) {          // otherwise fill_scan2 copies them into the kernel parameters
+        KV_TRY(ensure(s->d_rec, (size_t)n_act * 20 + 64));
+        CU(cudaMemcpyAsync(s->d_rec.p, s->h_pin, (size_t)n_act * 20, cudaMemcpyHostToDevice, s->stream));
+    }
     return KV_OK;
 }
 
@@ -1314,10 +1452,19 @@ static void fill_scan2(kv_shard *s, Scan2Params &P, int n_act) {
     P.n_cols = s->n_cols;
     P.col0 = s->col0;
     P.k_total = s->k_total;
-    P.rec_m0 = (const uint64_t *)s->d_rec.p;
-    P.rec_m1 = P.rec_m0 + n_act;
-    P.rec_row = (const uint32_t *)(P.rec_m1 + n_act);
     P.n_act = n_act;
+    if (n_act <= SCAN_INLINE_ROWS) {
+        const uint64_t *pm0 = (const uint64_t *)s->h_pin, *pm1 = pm0 + n_act;
+        const uint32_t *prow = (const uint32_t *)(pm1 + n_act);
+        P.inline_rec = 1;
+        memcpy(P.inl_m0, pm0, (size_t)n_act * 8);
+        memcpy(P.inl_m1, pm1, (size_t)n_act * 8);
+        memcpy(P.inl_row, prow, (size_t)n_act * 4);
+    } else {
+        P.rec_m0 = (const uint64_t *)s->d_rec.p;
+        P.rec_m1 = P.rec_m0 + n_act;
+        P.rec_row = (const uint32_t *)(P.rec_m1 + n_act);
+    }
     P.ubs = 1;
 }
 
@@ -1620,44 +1767,85 @@ static int ensure_ties(kv_shard *s, long long cap) {
 
 static int scm_scan_async(kv_shard *s, const uint64_t *pos_mask, const uint64_t *neg_mask, int64_t n_pos, int64_t n_neg,
                           double p, int64_t ubs, int64_t n_blocks) {
-    if (n_pos < 0 || n_neg < 0 || n_pos > s->n_examples || n_neg > s->n_examples)
+    if (n_pos < 0 || n_neg < 0 || n_pos > s->n_examples || n_neg > s->n_examples) {
+        s->reuse_armed = false;
         return fail(KV_E_INVALID, "kv_scm_scan: n_pos / n_neg out of range");
+    }
     if (ubs <= 0) return fail(KV_E_INVALID, "kv_scm_scan: util_block_size must be positive");
     if (n_blocks != kv_scm_n_blocks(s->k_total, ubs)) return fail(KV_E_INVALID, "kv_scm_scan: wrong n_blocks");
     KV_TRY(ensure_counts(s, 2));
     if (!s->d_segmax) CU(cudaMalloc(&s->d_segmax, (size_t)(s->ld / 64) * 2 * 8));
-    int n_act, n_both;
-    KV_TRY(push_records2(s, pos_mask, neg_mask, n_act, n_both));
     MiscLayout L0 = misc_layout(nullptr, n_blocks);
     KV_TRY(ensure(s->d_misc, L0.bytes));
     MiscLayout L = misc_layout(s->d_misc.p, n_blocks);
     // L.blockmax is all-zero here: zeroed at allocation and re-zeroed by whoever consumed it last
-    Scan2Params P;
-    fill_scan2(s, P, n_act);
-    P.cnt0 = s->d_cnt[0];
-    P.cnt1 = s->d_cnt[1];
-    P.p = p;
-    P.n_pos = (uint32_t)n_pos;
-    P.n_neg = (uint32_t)n_neg;
-    P.ubs = ubs;
-    P.black_pres = s->have_black ? s->d_black_pres : nullptr;
-    P.black_abs = s->have_black ? s->d_black_abs : nullptr;
-    P.blockmax = L.blockmax;
-    P.segmax = s->d_segmax;
-    KV_TRY(launch_scan<EPI_SCM>(s, P, n_both));
+    if (s->reuse_armed) {
+        // kv_scm_reuse_counts: same masks as the previous scan (possibly with swapped roles) -> rescore only
+        s->reuse_armed = false;
+        if (!s->scm_valid) return fail(KV_E_INVALID, "kv_scm_reuse_counts: no SCM counts on the device");
+        const bool swapped = s->reuse_swap;      // relative to the masks of the scan that produced the counts
+        RescoreParams R;
+        memset(&R, 0, sizeof R);
+        R.cnt_pos = s->d_cnt[swapped ? 1 : 0];
+        R.cnt_neg = s->d_cnt[swapped ? 0 : 1];
+        R.n_cols = s->n_cols;
+        R.ld = s->ld;
+        R.col0 = s->col0;
+        R.k_total = s->k_total;
+        R.ubs = ubs;
+        R.p = p;
+        R.n_pos = (uint32_t)n_pos;
+        R.n_neg = (uint32_t)n_neg;
+        R.black_pres = s->have_black ? s->d_black_pres : nullptr;
+        R.black_abs = s->have_black ? s->d_black_abs : nullptr;
+        R.blockmax = L.blockmax;
+        R.segmax = s->d_segmax;
+        CU(cudaEventRecord(s->ev0, s->stream));
+        k_scm_rescore<<<(unsigned)((s->ld + 2047) / 2048), 256, 0, s->stream>>>(R);
+        count_launch(s);
+        CU(cudaEventRecord(s->ev1, s->stream));
+        s->scm_swapped = swapped;
+        s->rescore_calls += 1;
+    } else {
+        if (!pos_mask || !neg_mask) return fail(KV_E_INVALID, "kv_scm_scan: null mask");
+        int n_act, n_both;
+        KV_TRY(push_records2(s, pos_mask, neg_mask, n_act, n_both));
+        Scan2Params P;
+        fill_scan2(s, P, n_act);
+        P.cnt0 = s->d_cnt[0];
+        P.cnt1 = s->d_cnt[1];
+        P.p = p;
+        P.n_pos = (uint32_t)n_pos;
+        P.n_neg = (uint32_t)n_neg;
+        P.ubs = ubs;
+        P.black_pres = s->have_black ? s->d_black_pres : nullptr;
+        P.black_abs = s->have_black ? s->d_black_abs : nullptr;
+        P.blockmax = L.blockmax;
+        P.segmax = s->d_segmax;
+        KV_TRY(launch_scan<EPI_SCM>(s, P, n_both));
+        s->scm_swapped = false;
+        s->scan_calls += 1;
+    }
     s->scm_valid = true;
     s->gini_valid = false;
     s->scm_n_pos = n_pos;
     s->scm_n_neg = n_neg;
     s->scm_ubs = ubs;
     s->scm_p = p;
-    s->scan_calls += 1;
+    return KV_OK;
+}
+
+extern "C" int kv_scm_reuse_counts(kv_shard *s, int swap_roles) {
+    if (!s) return fail(KV_E_INVALID, "kv_scm_reuse_counts: null shard");
+    if (!s->scm_valid) return fail(KV_E_INVALID, "kv_scm_reuse_counts: no SCM counts on the device");
+    s->reuse_armed = true;
+    s->reuse_swap = swap_roles != 0;
     return KV_OK;
 }
 
 extern "C" int kv_scm_scan(kv_shard *s, const uint64_t *pos_mask, const uint64_t *neg_mask, int64_t n_pos,
                            int64_t n_neg, double p, int64_t util_block_size, double *block_max, int64_t n_blocks) {
-    if (!s || !pos_mask || !neg_mask || !block_max) return fail(KV_E_INVALID, "kv_scm_scan: null pointer");
+    if (!s || !block_max) return fail(KV_E_INVALID, "kv_scm_scan: null pointer");
     DeviceGuard g(s->device);
     s->last_launches = 0;
     KV_TRY(scm_scan_async(s, pos_mask, neg_mask, n_pos, n_neg, p, util_block_size, n_blocks));
@@ -1665,7 +1853,7 @@ extern "C" int kv_scm_scan(kv_shard *s, const uint64_t *pos_mask, const uint64_t
     MiscLayout L = misc_layout(s->d_misc.p, n_blocks);
     CU(cudaMemcpyAsync(s->h_pin, L.blockmax, (size_t)n_blocks * 8, cudaMemcpyDeviceToHost, s->stream));
     CU(cudaMemsetAsync(L.blockmax, 0, (size_t)n_blocks * 8, s->stream));
-    CU(cudaStreamSynchronize(s->stream));
+    CU(stream_sync_spin(s->stream));
     CU(cudaGetLastError());
     float ms = 0;
     CU(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
@@ -1721,8 +1909,8 @@ static int scm_collect_ties(kv_shard *s, int64_t n_blocks, int64_t capacity, dou
     TieRec *d_rec = (TieRec *)(d_hdr + 1);
     TieParams T;
     memset(&T, 0, sizeof T);
-    T.cnt0 = s->d_cnt[0];
-    T.cnt1 = s->d_cnt[1];
+    T.cnt0 = s->d_cnt[s->scm_swapped ? 1 : 0];
+    T.cnt1 = s->d_cnt[s->scm_swapped ? 0 : 1];
     T.segmax = s->d_segmax;
     T.n_cols = s->n_cols;
     T.ld = s->ld;
@@ -1749,7 +1937,7 @@ static int scm_collect_ties(kv_shard *s, int64_t n_blocks, int64_t capacity, dou
     const size_t first_bytes = sizeof(TieHeader) + (size_t)kTieFirstBatch * sizeof(TieRec);
     KV_TRY(ensure_pinned(s, first_bytes));
     CU(cudaMemcpyAsync(s->h_pin, d_hdr, first_bytes, cudaMemcpyDeviceToHost, s->stream));
-    CU(cudaStreamSynchronize(s->stream));
+    CU(stream_sync_spin(s->stream));
     CU(cudaGetLastError());
     const TieHeader hdr = *(const TieHeader *)s->h_pin;
     const long long found = (long long)hdr.count;
@@ -1761,7 +1949,7 @@ static int scm_collect_ties(kv_shard *s, int64_t n_blocks, int64_t capacity, dou
         KV_TRY(ensure_pinned(s, sizeof(TieHeader) + (size_t)found * sizeof(TieRec)));
         CU(cudaMemcpyAsync(s->h_pin, d_hdr, sizeof(TieHeader) + (size_t)found * sizeof(TieRec), cudaMemcpyDeviceToHost,
                            s->stream));
-        CU(cudaStreamSynchronize(s->stream));
+        CU(stream_sync_spin(s->stream));
     }
     TieRec *recs = (TieRec *)((TieHeader *)s->h_pin + 1);
     std::sort(recs, recs + found, [](const TieRec &a, const TieRec &b) { return a.idx < b.idx; });
@@ -1808,8 +1996,7 @@ extern "C" int kv_scm_best_rules(kv_shard *s, const uint64_t *pos_mask, const ui
                                  int64_t n_neg, double p, int64_t util_block_size, double *best_utility,
                                  int64_t capacity, int64_t *rule_idx, int64_t *pos_err, int64_t *neg_cover,
                                  int64_t *n_found) {
-    if (!s || !pos_mask || !neg_mask || !best_utility || !n_found ||
-        (capacity > 0 && (!rule_idx || !pos_err || !neg_cover)))
+    if (!s || !best_utility || !n_found || (capacity > 0 && (!rule_idx || !pos_err || !neg_cover)))
         return fail(KV_E_INVALID, "kv_scm_best_rules: null pointer");
     if (s->col0 != 0 || s->n_cols != s->k_total)
         return fail(KV_E_INVALID, "kv_scm_best_rules: single-shard call on a partial shard; use scan/select/ties");
@@ -1849,8 +2036,8 @@ static int scm_packet_async(kv_shard *s, const uint64_t *pos_mask, const uint64_
     count_launch(s);
     TieParams T;
     memset(&T, 0, sizeof T);
-    T.cnt0 = s->d_cnt[0];
-    T.cnt1 = s->d_cnt[1];
+    T.cnt0 = s->d_cnt[s->scm_swapped ? 1 : 0];
+    T.cnt1 = s->d_cnt[s->scm_swapped ? 0 : 1];
     T.segmax = s->d_segmax;
     T.n_cols = s->n_cols;
     T.ld = s->ld;
@@ -1885,7 +2072,7 @@ static int finish_scan_timing(kv_shard *s) {
 extern "C" int kv_scm_scan_packet(kv_shard *s, const uint64_t *pos_mask, const uint64_t *neg_mask, int64_t n_pos,
                                   int64_t n_neg, double p, int64_t util_block_size, int64_t n_blocks, int64_t capacity,
                                   void *packet, int packet_on_device) {
-    if (!s || !pos_mask || !neg_mask || !packet) return fail(KV_E_INVALID, "kv_scm_scan_packet: null pointer");
+    if (!s || !packet) return fail(KV_E_INVALID, "kv_scm_scan_packet: null pointer");
     if (capacity < 0) return fail(KV_E_INVALID, "kv_scm_scan_packet: negative capacity");
     DeviceGuard g(s->device);
     s->last_launches = 0;
@@ -1897,7 +2084,7 @@ extern "C" int kv_scm_scan_packet(kv_shard *s, const uint64_t *pos_mask, const u
     }
     KV_TRY(scm_packet_async(s, pos_mask, neg_mask, n_pos, n_neg, p, util_block_size, n_blocks, capacity, d_packet));
     if (!packet_on_device) CU(cudaMemcpyAsync(packet, d_packet, bytes, cudaMemcpyDeviceToHost, s->stream));
-    CU(cudaStreamSynchronize(s->stream));
+    CU(stream_sync_spin(s->stream));
     CU(cudaGetLastError());
     return finish_scan_timing(s);
 }
@@ -2095,7 +2282,7 @@ extern "C" int kv_scm_best_rules_p2p(kv_shard *s, const uint64_t *pos_mask, cons
                                      double *best_utility, int64_t capacity, int64_t *rule_idx, int64_t *pos_err,
                                      int64_t *neg_cover, int64_t *n_found, double *merged_block_max,
                                      uint8_t *selected, int *overflowed) {
-    if (!s || !s->p2p || !pos_mask || !neg_mask) return fail(KV_E_INVALID, "kv_scm_best_rules_p2p: no mailbox / null pointer");
+    if (!s || !s->p2p) return fail(KV_E_INVALID, "kv_scm_best_rules_p2p: no mailbox / null pointer");
     kv_p2p *m = s->p2p;
     const int64_t n_blocks = kv_scm_n_blocks(s->k_total, util_block_size);
     if (n_blocks <= 0) return fail(KV_E_INVALID, "kv_scm_best_rules_p2p: util_block_size must be positive");
@@ -2128,7 +2315,7 @@ extern "C" int kv_scm_best_rules_p2p(kv_shard *s, const uint64_t *pos_mask, cons
                          (size_t)m->world, cudaMemcpyDeviceToHost, s->stream));
     KV_TRY(ensure_pinned(s, 64));
     CU(cudaMemcpyAsync(s->h_pin, m->d_error, 4, cudaMemcpyDeviceToHost, s->stream));
-    CU(cudaStreamSynchronize(s->stream));
+    CU(stream_sync_spin(s->stream));
     CU(cudaGetLastError());
     KV_TRY(finish_scan_timing(s));
     if (*(int *)s->h_pin != 0) return fail(KV_E_CUDA, "kv_scm_best_rules_p2p: timed out waiting for a peer rank's packet");
@@ -2223,7 +2410,7 @@ extern "C" int kv_gini_scan(kv_shard *s, int n_classes, const uint64_t *class_ma
     KV_TRY(ensure_pinned(s, 64));
     CU(cudaMemcpyAsync(s->h_pin, s->gini.min_enc, 8, cudaMemcpyDeviceToHost, s->stream));
     KV_TRY(gini_restore_misc(s));
-    CU(cudaStreamSynchronize(s->stream));
+    CU(stream_sync_spin(s->stream));
     CU(cudaGetLastError());
     if (n_classes == 2) KV_TRY(finish_scan_timing(s));
     *min_score = dec_f64_min(*(unsigned long long *)s->h_pin);
@@ -2259,7 +2446,7 @@ static int gini_ties_impl(kv_shard *s, bool from_device, double min_score, int64
     KV_TRY(ensure_pinned(s, first));
     CU(cudaMemcpyAsync(s->h_pin, d_hdr, first, cudaMemcpyDeviceToHost, s->stream));
     if (from_device) KV_TRY(gini_restore_misc(s));
-    CU(cudaStreamSynchronize(s->stream));
+    CU(stream_sync_spin(s->stream));
     CU(cudaGetLastError());
     const unsigned long long *h = (const unsigned long long *)s->h_pin;
     if (min_out) *min_out = dec_f64_min(h[0]);
@@ -2269,7 +2456,7 @@ static int gini_ties_impl(kv_shard *s, bool from_device, double min_score, int64
     if (found == 0) return KV_OK;
     if (found > kGiniFirstBatch) {
         CU(cudaMemcpyAsync(rule_idx, G.out_idx, (size_t)found * 8, cudaMemcpyDeviceToHost, s->stream));
-        CU(cudaStreamSynchronize(s->stream));
+        CU(stream_sync_spin(s->stream));
     } else {
         memcpy(rule_idx, h + 2, (size_t)found * 8);
     }

@@ -273,6 +273,17 @@ class KmerRuleClassifications(BaseRuleClassifications):
         return self._group.scm_best_rules(pos_mask, neg_mask, positive_example_idx.shape[0],
                                           negative_example_idx.shape[0], float(p), int(util_block_size))
 
+    def best_utility_rules_grid(self, jobs, rule_blacklist=(), util_block_size=1000000):
+        """``best_utility_rules`` for several (p, positive_example_idx, negative_example_idx) jobs at once: jobs
+        whose example sets coincide (every p of a grid; conjunction and disjunction, whose labels are swapped)
+        share ONE pass over the matrix.  Returns the results in job order."""
+        self.set_rule_blacklist(rule_blacklist)
+        packed = []
+        for p, pos, neg in jobs:
+            pos, neg = np.asarray(pos), np.asarray(neg)
+            packed.append((float(p), self.row_mask(pos), self.row_mask(neg), pos.shape[0], neg.shape[0]))
+        return self._group.scm_best_rules_grid(packed, int(util_block_size))
+
     def gini_best_split(self, example_idx, altered_priors, n_total_class_examples, rule_blacklist=()):
         """cart.py:112-161 + 231-238.  example_idx: dict class -> example indices of the node, iterated in
         dict order like the reference.  -> (min score, presence-rule indices achieving it, ascending)."""

@@ -41,6 +41,24 @@ class BaseSetCoveringMachine(object):
 
     def fit(self, rules, rule_classifications, positive_example_idx, negative_example_idx, rule_blacklist=[],
             tiebreaker=None, iteration_callback=None, iteration_rule_importances=False, **kwargs):
+        """scm.py:54-159.  The greedy loop is written once, as a generator that asks for one utility scan per
+        iteration (``_fit_steps``); ``fit`` answers each request with its own scan, ``fit_many`` answers the
+        requests of many learners together so that scans over the same examples share a matrix pass."""
+        steps = self._fit_steps(rules, rule_classifications, positive_example_idx, negative_example_idx,
+                                rule_blacklist, tiebreaker, iteration_callback, iteration_rule_importances, **kwargs)
+        try:
+            request = next(steps)
+            while True:
+                pos_idx, neg_idx, blacklist, extra = request
+                request = steps.send(self._get_best_utility_rules(rule_classifications=rule_classifications,
+                                                                  positive_example_idx=pos_idx,
+                                                                  negative_example_idx=neg_idx,
+                                                                  rule_blacklist=blacklist, **extra))
+        except StopIteration:
+            pass
+
+    def _fit_steps(self, rules, rule_classifications, positive_example_idx, negative_example_idx, rule_blacklist=[],
+                   tiebreaker=None, iteration_callback=None, iteration_rule_importances=False, **kwargs):
         utility_function_additional_args = {}
         if kwargs is not None:
             for key, value in kwargs.items():
@@ -76,11 +94,7 @@ class BaseSetCoveringMachine(object):
             iteration_info = {"iteration_number": len(self.model) + 1}
 
             best_utility, best_utility_idx, best_utility_pos_error_counts, best_utility_neg_cover_counts = \
-                self._get_best_utility_rules(rule_classifications=rule_classifications,
-                                             positive_example_idx=positive_example_idx,
-                                             negative_example_idx=negative_example_idx,
-                                             rule_blacklist=rule_blacklist,
-                                             **utility_function_additional_args)
+                yield (positive_example_idx, negative_example_idx, rule_blacklist, utility_function_additional_args)
 
             iteration_info["utility_max"] = best_utility
             iteration_info["utility_argmax"] = best_utility_idx
@@ -165,6 +179,49 @@ class BaseSetCoveringMachine(object):
         if not self._flags.get("PROBABILISTIC_PREDICTIONS", False):
             raise RuntimeError("The predictor does not support probabilistic predictions.")
         return self.model.predict_proba(X)
+
+
+def fit_many(learners, fit_args, rule_classifications):
+    """Fit several SetCoveringMachine learners over the SAME rule_classifications in lock-step (the reference
+    runs them one after the other, or in forked workers: experiment_scm.py:196-248, 568-629).
+
+    learners: list of SetCoveringMachine; fit_args: one dict of ``fit`` keyword arguments per learner
+    (rules, positive_example_idx, negative_example_idx, rule_blacklist, tiebreaker, iteration_callback,
+    iteration_rule_importances).  At every greedy iteration the pending utility scans of all learners are
+    answered together by ``rule_classifications.best_utility_rules_grid``: learners whose remaining example
+    sets coincide -- every p of the grid and both model types at iteration 1, and whenever they picked the
+    same rules -- share one pass over the matrix.  Each learner ends in exactly the state its own ``fit``
+    would have produced (same scans, same order of operations per learner)."""
+    gens, pending = [], {}
+    for i, (learner, kw) in enumerate(zip(learners, fit_args)):
+        kw = dict(kw)
+        kw["rule_classifications"] = rule_classifications
+        g = learner._fit_steps(**kw)
+        gens.append(g)
+        try:
+            pending[i] = next(g)
+        except StopIteration:
+            pass
+    while pending:
+        # one grid call per distinct blacklist (the experiments use a single blacklist for all fits)
+        by_blacklist = {}
+        for i, (pos_idx, neg_idx, blacklist, extra) in pending.items():
+            if extra:
+                raise ValueError("fit_many does not support utility__ keyword arguments")
+            by_blacklist.setdefault(np.asarray(blacklist, dtype=np.int64).tobytes(), []).append(i)
+        answers = {}
+        for members in by_blacklist.values():
+            jobs = [(learners[i].p, pending[i][0], pending[i][1]) for i in members]
+            res = rule_classifications.best_utility_rules_grid(jobs, rule_blacklist=pending[members[0]][2],
+                                                               util_block_size=UTIL_BLOCK_SIZE)
+            answers.update(zip(members, res))
+        nxt = {}
+        for i, ans in answers.items():
+            try:
+                nxt[i] = gens[i].send(ans)
+            except StopIteration:
+                pass
+        pending = nxt
 
 
 class SetCoveringMachine(BaseSetCoveringMachine):

@@ -248,6 +248,31 @@ class ShardGroup(object):
         order = np.argsort(idx, kind="stable")
         return best, idx[order], pe[order], nc[order]
 
+    def scm_best_rules_grid(self, jobs, util_block_size):
+        """Several SCM scans that may share example masks (north-star item 4: the p grid x both model types x
+        the fits of a cross-validation in lock-step).  jobs: [(p, pos_mask, neg_mask, n_pos, n_neg)].  The
+        matrix is scanned once per DISTINCT unordered mask pair; every other job re-scores the counts that scan
+        left on the device (kv_scm_reuse_counts: another p, or positives and negatives exchanged as the
+        disjunction does, scm.py:69-73).  Results in job order, each as scm_best_rules returns it."""
+        groups = {}
+        for i, (p, pm, nm, n_pos, n_neg) in enumerate(jobs):
+            key = (pm.tobytes(), nm.tobytes())
+            if key in groups:
+                groups[key].append((i, False))
+            elif (key[1], key[0]) in groups:
+                groups[(key[1], key[0])].append((i, True))
+            else:
+                groups[key] = [(i, False)]
+        results = [None] * len(jobs)
+        for members in groups.values():
+            for rank_in_group, (i, swap) in enumerate(members):
+                p, pm, nm, n_pos, n_neg = jobs[i]
+                if rank_in_group > 0:
+                    for s in self.shards:
+                        s.scm_reuse_counts(swap)
+                results[i] = self.scm_best_rules(pm, nm, n_pos, n_neg, p, util_block_size)
+        return results
+
     # ------------------------------------------------------------------ a9 / a11
     def gini_best_split(self, class_masks, altered_prior, n_total, n_node):
         """-> (min_score, presence-rule indices with score == min_score, ascending); cart.py:112-161, 231-238."""

@@ -90,6 +90,33 @@ def main():
         out["checks"] += 1
     kscm.UTIL_BLOCK_SIZE = 1000000
 
+    # the same fits in lock-step (fit_many): scans over identical example sets are shared
+    groups = {}
+    for case in cases.SCM_CASES:
+        groups.setdefault((case[1], case[8], tuple(case[7])), []).append(case)
+    for (mname, ubs, blacklist), members in groups.items():
+        X, P, n, chunks = cases.matrix(mname)
+        k = P.shape[1]
+        kscm.UTIL_BLOCK_SIZE = ubs
+        rc = make_rc(P, n, comm)
+        risks = cases.rule_risks(2 * k)
+        learners, args = [], []
+        for name, _, lname, model_type, p, max_rules, tb, _, _ in members:
+            y = cases.labels(lname)
+            tiebreaker = (lambda idx: idx) if tb == "identity" else \
+                (lambda idx, mt=model_type: ko.scm_tiebreaker(idx, risks, mt))
+            learners.append(kscm.SetCoveringMachine(model_type=model_type, p=p, max_rules=max_rules))
+            args.append(dict(rules=LazyKmerRuleList(["K%d" % i for i in range(k)], np.arange(k)),
+                             positive_example_idx=np.where(y == 1)[0], negative_example_idx=np.where(y == 0)[0],
+                             rule_blacklist=list(blacklist), tiebreaker=tiebreaker))
+        kscm.fit_many(learners, args, rc)
+        for case, m in zip(members, learners):
+            gg = np.load(os.path.join(golden, case[0] + ".npz"))
+            assert str(m.model) == str(gg["model_str"]), case[0]
+            assert np.array_equal(np.asarray(m.rule_importances), gg["rule_importances"]), case[0]
+            out["checks"] += 1
+    kscm.UTIL_BLOCK_SIZE = 1000000
+
     # CART fits
     for case in cases.CART_CASES:
         name, mname, lname, max_depth, mss, class_importance, tb, subset_seed = case

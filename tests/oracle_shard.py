@@ -32,6 +32,9 @@ class OracleShard(object):
     def set_blacklist(self, rule_idx):
         self.black = np.asarray(rule_idx, dtype=np.int64)
 
+    def scm_reuse_counts(self, swap_roles=False):
+        pass          # the checker-backed shard recomputes from the masks it is given
+
     def _utilities(self):
         k, c0, n = self.n_kmers_total, self.col0, self.n_cols
         pres, absn = self._cnt

@@ -222,6 +222,75 @@ def test_scm_fit_golden(golden_dir, case, monkeypatch):
         assert np.array_equal(pred, want.astype(np.uint8))
 
 
+def check_scm_against_golden(g, m, infos):
+    assert len(infos) == int(g["n_iterations"])
+    assert str(m.model) == str(g["model_str"])
+    for t, info in enumerate(infos):
+        assert info["utility_max"] == float(g["it%d_utility_max" % t])
+        assert np.array_equal(np.asarray(info["utility_argmax"], dtype=np.int64), g["it%d_utility_argmax" % t])
+        assert np.array_equal(np.asarray(info["equivalent_rules_idx"], dtype=np.int64), g["it%d_equivalent" % t])
+        assert str(info["selected_rule"]) == str(g["it%d_selected" % t])
+        assert np.array_equal(info["rule_importances"], g["it%d_importances" % t])
+    assert np.array_equal(np.asarray(m.rule_importances, dtype=np.float64), g["rule_importances"])
+
+
+@pytest.mark.parametrize("devices", [[0], [0, 0]], ids=["1shard", "2shards"])
+def test_fit_many_lockstep_golden(golden_dir, devices, monkeypatch):
+    """north-star item 4: all fits over one matrix in lock-step, scans over identical example sets sharing a
+    matrix pass (kv_scm_reuse_counts).  Every learner must end exactly where its own fit() ends."""
+    groups = {}
+    for case in cases.SCM_CASES:
+        groups.setdefault((case[1], case[8], tuple(case[7])), []).append(case)
+    for (mname, ubs, blacklist), members in groups.items():
+        X, P, n, chunks = cases.matrix(mname)
+        k = P.shape[1]
+        monkeypatch.setattr(kscm, "UTIL_BLOCK_SIZE", ubs)
+        rc = KmerRuleClassifications(as_dataset(P, chunks), n, devices=devices)
+        risks = cases.rule_risks(2 * k)
+        learners, args, infos = [], [], []
+        for name, _, lname, model_type, p, max_rules, tb, _, _ in members:
+            y = cases.labels(lname)
+            tiebreaker = (lambda idx: idx) if tb == "identity" else \
+                (lambda idx, mt=model_type: ko.scm_tiebreaker(idx, risks, mt))
+            log = []
+            infos.append(log)
+            learners.append(kscm.SetCoveringMachine(model_type=model_type, p=p, max_rules=max_rules))
+            args.append(dict(rules=rule_list(k), positive_example_idx=np.where(y == 1)[0],
+                             negative_example_idx=np.where(y == 0)[0], rule_blacklist=list(blacklist),
+                             tiebreaker=tiebreaker, iteration_callback=lambda i, log=log: log.append(dict(i)),
+                             iteration_rule_importances=True))
+        kscm.fit_many(learners, args, rc)
+        for case, m, log in zip(members, learners, infos):
+            check_scm_against_golden(load(golden_dir, case[0]), m, log)
+        rc.close()
+
+
+def test_grid_shares_matrix_passes():
+    """12 jobs = 6 p values x {conjunction, disjunction (labels swapped)} over the same examples: ONE matrix
+    scan, 11 re-scores of the resident counts, results identical to 12 independent scans."""
+    seed, n, k = 9, 1500, 120000
+    P = synthetic_block(seed, n, 0, k)
+    y = synthetic_labels(seed, n)
+    train = train_split(seed, n)
+    pos, neg = train[y[train] == 1], train[y[train] == 0]
+    rc = KmerRuleClassifications(P, n, devices=[0])
+    shard = rc._group.shards[0]
+    jobs = [(p, a, b) for p in (0.1, 0.5, 1.0, 2.0, 5.0, 10.0) for a, b in ((pos, neg), (neg, pos))]
+    want = [rc.best_utility_rules(p, a, b, util_block_size=50000) for p, a, b in jobs]
+    before = shard.info()
+    got = rc.best_utility_rules_grid(jobs, util_block_size=50000)
+    after = shard.info()
+    assert after.scan_calls - before.scan_calls == 1 and after.rescore_calls - before.rescore_calls == 11
+    for w, g_ in zip(want, got):
+        assert w[0] == g_[0] and all(np.array_equal(a, b) for a, b in zip(w[1:], g_[1:]))
+    orc = ko.OracleKmerRuleClassifications(P, n, fast=True)
+    for (p, a, b), g_ in zip(jobs, got):
+        wu, wi, wp, wn = ko.merge_utility_blocks(len(b) - orc.sum_rows(b), len(a) - orc.sum_rows(a), p,
+                                                 np.zeros(2 * k, dtype=bool), block_size=50000)
+        assert g_[0] == wu and np.array_equal(g_[1], np.asarray(wi, dtype=np.int64))
+        assert np.array_equal(g_[2], wp) and np.array_equal(g_[3], wn)
+
+
 # ---------------------------------------------------------------------------------- a9 / a11
 def tree_to_dict(node):
     d = {"depth": node.depth, "criterion_value": float(node.criterion_value),
