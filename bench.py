@@ -232,6 +232,16 @@ def extra_measurements(rc, shard, steps, k_local, reps=12):
     kms = (shard.info().scan_ms_total - a) / (reps + 1)
     out["scm_scan_unsorted_labels"] = {"ms_per_step": ms, "rules_per_s": 2.0 * k_local / (ms * 1e-3), "scan_kernel_ms": kms,
                                        "scan_kernel_GBps": 8.0 * 32 * k_local / (kms * 1e-3) / 1e9}
+    # north-star item 4: one fold's whole hyper-parameter grid at iteration 1 = 6 p values x {conjunction,
+    # disjunction}: 12 jobs over the same examples -> one matrix scan + 11 re-scores of the resident counts
+    _, pos, neg = steps[0]
+    jobs = [(pp, a, b) for pp in P_GRID for a, b in ((pos, neg), (neg, pos))]
+    ia = shard.info()
+    ms = timed(lambda: rc.best_utility_rules_grid(jobs, util_block_size=UTIL_BLOCK_SIZE), 6)
+    ib = shard.info()
+    out["hp_grid_iteration_12_jobs"] = {"ms_per_grid": ms, "job_rules_per_s": len(jobs) * 2.0 * k_local / (ms * 1e-3),
+                                        "matrix_scans_per_grid": (ib.scan_calls - ia.scan_calls) / 7.0,
+                                        "rescores_per_grid": (ib.rescore_calls - ia.rescore_calls) / 7.0}
     # the reference's own operator API: sum_rows returns a 2K-long host array (D2H of 2K x uint16 per call)
     out["sum_rows_dropin_ms"] = timed(lambda: rc.sum_rows(steps[0][1]), 4)
     # upload path: host numpy block -> pinned ring -> HBM (kv_upload_block), on 1/8 of the matrix
