@@ -72,42 +72,74 @@ def active_words(pos, neg, n_genomes):
 
 # ------------------------------------------------------------------------------------------ clocks
 class ClockSampler(object):
+    """SM clocks and throttle reasons DURING the timed region.  NVML through pynvml (a few microseconds per
+    query); spawning nvidia-smi from inside the region measurably slows the steps it is supposed to watch
+    (8 % at N=4), so it is only the fallback.  Rank 0 samples every GPU of the job."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, device):
-        self.device, self.samples, self._stop, self._t = device, [], threading.Event(), None
+    def __init__(self, devices, enabled=True, period=0.05):
+        self.devices, self.samples, self._stop, self._t = list(devices), [], threading.Event(), None
+        self.enabled, self.period, self.source = enabled, period, None
+        self._nvml = None
+        if enabled:
+            try:
+                import pynvml
+                pynvml.nvmlInit()
+                self._handles = [pynvml.nvmlDeviceGetHandleByIndex(d) for d in self.devices]
+                self._nvml, self.source = pynvml, "nvml"
+            except Exception:  # noqa: BLE001
+                self.source, self.period = "nvidia-smi", max(period, 0.25)
+
+    def _poll_nvml(self):
+        nv = self._nvml
+        for h in self._handles:
+            sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                else nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            flag = lambda name: "Active" if (r & getattr(nv, name, 0)) else "Not Active"
+            self.samples.append([str(sm), str(mx), flag("nvmlClocksThrottleReasonHwSlowdown"),
+                                 flag("nvmlClocksThrottleReasonHwThermalSlowdown"),
+                                 flag("nvmlClocksThrottleReasonSwThermalSlowdown"),
+                                 flag("nvmlClocksThrottleReasonSwPowerCap")])
+
+    def _poll_smi(self):
+        out = subprocess.run(["nvidia-smi", "-i", ",".join(str(d) for d in self.devices), "--query-gpu=" + self.Q,
+                              "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+        for row in out.strip().splitlines():
+            f = [x.strip() for x in row.split(",")]
+            if len(f) >= 6:
+                self.samples.append(f)
 
     def _run(self):
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                f = [x.strip() for x in out.strip().split(",")]
-                if len(f) >= 6:
-                    self.samples.append(f)
+                self._poll_nvml() if self._nvml is not None else self._poll_smi()
             except Exception:  # noqa: BLE001
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(self.period)
 
     def __enter__(self):
-        self._t = threading.Thread(target=self._run, daemon=True)
-        self._t.start()
+        if self.enabled:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
         return self
 
     def __exit__(self, *a):
         self._stop.set()
-        self._t.join(timeout=10)
+        if self._t is not None:
+            self._t.join(timeout=10)
 
     def summary(self):
         if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": self.source}
         sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
         mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.samples)}
+                "reasons": reasons, "samples": len(self.samples), "source": self.source}
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
@@ -323,7 +355,7 @@ def run_ours(args):
     alg_bytes = [8.0 * active_words(pos, neg, N_GENOMES) * k_local for _, pos, neg in timed]
     h2d = sum(active_words(pos, neg, N_GENOMES) * 20 for _, pos, neg in timed)
     tie_counts = []
-    with ClockSampler(local_rank) as clocks:
+    with ClockSampler(range(world), enabled=(rank == 0)) as clocks:
         sync_all()
         info_a = shard.info()
         shard.timer_start()
@@ -337,12 +369,11 @@ def run_ours(args):
         info_b = shard.info()
         launches = info_b.total_launches - info_a.total_launches
         kernel_ms_total = info_b.scan_ms_total - info_a.scan_ms_total
-        # keep the sampler alive for at least a few samples on very short runs
-        t_end = time.perf_counter() + max(0.0, 0.6 - wall_s)
-        i = 0
-        while time.perf_counter() < t_end:
+        # keep the sampler alive for at least a few samples on very short runs: the SAME number of extra
+        # (untimed) steps on every rank, since a step is collective
+        w = float(comm.allreduce_max(np.array([wall_s]))[0]) if comm is not None else wall_s
+        for i in range(max(0, int((0.6 - w) / max(w / args.steps, 1e-5)))):
             one_step(i)
-            i += 1
     d2h = sum(32 + 16 * max(256, c) for c in tie_counts)
     kernel_ms = [kernel_ms_total / args.steps] * args.steps
     if comm is not None:

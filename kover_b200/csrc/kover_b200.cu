@@ -2091,16 +2091,31 @@ extern "C" int kv_scm_scan_packet(kv_shard *s, const uint64_t *pos_mask, const u
 
 // Host-only: merge of the gathered packets (max of the block maxima, scm.py:270-286 replay, exact
 // isclose filter of the candidates with u recomputed as scm.py:263-264 does).
+static int merge_packets_strided(const void *rows, size_t stride, int64_t n_packets, int64_t n_blocks,
+                                 int64_t packet_capacity, double p, int64_t util_block_size, double *best_utility,
+                                 int64_t capacity, int64_t *rule_idx, int64_t *pos_err, int64_t *neg_cover,
+                                 int64_t *n_found, double *merged_block_max, uint8_t *selected, int *overflowed);
+
 extern "C" int kv_scm_merge_packets(const void *rows, int64_t n_packets, int64_t n_blocks, int64_t packet_capacity,
                                     double p, int64_t util_block_size, double *best_utility, int64_t capacity,
                                     int64_t *rule_idx, int64_t *pos_err, int64_t *neg_cover, int64_t *n_found,
                                     double *merged_block_max, uint8_t *selected, int *overflowed) {
+    return merge_packets_strided(rows, (size_t)kv_scm_packet_bytes(n_blocks, packet_capacity), n_packets, n_blocks,
+                                 packet_capacity, p, util_block_size, best_utility, capacity, rule_idx, pos_err,
+                                 neg_cover, n_found, merged_block_max, selected, overflowed);
+}
+
+static int merge_packets_strided(const void *rows, size_t stride, int64_t n_packets, int64_t n_blocks,
+                                 int64_t packet_capacity, double p, int64_t util_block_size, double *best_utility,
+                                 int64_t capacity, int64_t *rule_idx, int64_t *pos_err, int64_t *neg_cover,
+                                 int64_t *n_found, double *merged_block_max, uint8_t *selected, int *overflowed) {
     if (!rows || !best_utility || !n_found || !merged_block_max || !selected || !overflowed ||
         (capacity > 0 && (!rule_idx || !pos_err || !neg_cover)))
         return fail(KV_E_INVALID, "kv_scm_merge_packets: null pointer");
     if (n_packets <= 0 || n_blocks <= 0 || packet_capacity < 0 || util_block_size <= 0 || capacity < 0)
         return fail(KV_E_INVALID, "kv_scm_merge_packets: bad sizes");
-    const size_t stride = (size_t)kv_scm_packet_bytes(n_blocks, packet_capacity);
+    if (stride < (size_t)kv_scm_packet_bytes(n_blocks, packet_capacity))
+        return fail(KV_E_INVALID, "kv_scm_merge_packets: stride smaller than a packet");
     const char *base = (const char *)rows;
     const double ninf = -std::numeric_limits<double>::infinity();
     for (int64_t b = 0; b < n_blocks; ++b) merged_block_max[b] = ninf;
@@ -2310,18 +2325,18 @@ extern "C" int kv_scm_best_rules_p2p(kv_shard *s, const uint64_t *pos_mask, cons
     k_p2p_publish_wait<<<1, 256, 0, s->stream>>>(P);
     count_launch(s);
     const int parity = (int)(P.seq & 1ull);
-    // gathered rows of this parity, at the packet stride the merge expects, + the error word
-    CU(cudaMemcpy2DAsync(m->h_rows, bytes, m->box + (size_t)parity * m->world * m->slot_bytes, m->slot_bytes, bytes,
-                         (size_t)m->world, cudaMemcpyDeviceToHost, s->stream));
+    // gathered slots of this parity in ONE linear copy (slot stride) + the error word
+    CU(cudaMemcpyAsync(m->h_rows, m->box + (size_t)parity * m->world * m->slot_bytes, (size_t)m->world * m->slot_bytes,
+                       cudaMemcpyDeviceToHost, s->stream));
     KV_TRY(ensure_pinned(s, 64));
     CU(cudaMemcpyAsync(s->h_pin, m->d_error, 4, cudaMemcpyDeviceToHost, s->stream));
     CU(stream_sync_spin(s->stream));
     CU(cudaGetLastError());
     KV_TRY(finish_scan_timing(s));
     if (*(int *)s->h_pin != 0) return fail(KV_E_CUDA, "kv_scm_best_rules_p2p: timed out waiting for a peer rank's packet");
-    return kv_scm_merge_packets(m->h_rows, m->world, n_blocks, packet_capacity, p, util_block_size, best_utility,
-                                capacity, rule_idx, pos_err, neg_cover, n_found, merged_block_max, selected,
-                                overflowed);
+    return merge_packets_strided(m->h_rows, m->slot_bytes, m->world, n_blocks, packet_capacity, p, util_block_size,
+                                 best_utility, capacity, rule_idx, pos_err, neg_cover, n_found, merged_block_max,
+                                 selected, overflowed);
 }
 
 // ------------------------------------------------------------------------------------------------
