@@ -174,6 +174,7 @@ struct Scan2Params {
     const uint64_t *rec_m0, *rec_m1;
     int n_act;
     int inline_rec;                   // 1: the records travel in the kernel parameters (n_act <= SCAN_INLINE_ROWS)
+    int l2_hints;                     // bit 0: evict-first matrix loads, bit 1: evict-last count stores
     uint64_t inl_m0[SCAN_INLINE_ROWS], inl_m1[SCAN_INLINE_ROWS];
     uint32_t inl_row[SCAN_INLINE_ROWS];
     uint32_t *cnt0, *cnt1;            // [ld] each; cnt1 may be null (single-mask scan)
@@ -236,6 +237,29 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_
                      smem_u32(dst)),
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
+}
+// Same with an L2 eviction policy: the matrix is streamed once per scan (evict-first), which leaves the
+// L2 to the count / segment arrays the next kernels re-read.
+__device__ __forceinline__ void tma_bulk_g2s_hint(void *dst, const void *src, uint32_t bytes, uint64_t *bar,
+                                                  uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void st_u32x2_hint(uint32_t *ptr, uint32_t a, uint32_t b, uint64_t policy) {
+    asm volatile("st.global.L2::cache_hint.v2.u32 [%0], {%1, %2}, %3;" ::"l"(ptr), "r"(a), "r"(b), "l"(policy) : "memory");
 }
 __device__ __forceinline__ void consumer_bar(int n_threads) {
     asm volatile("bar.sync 1, %0;" ::"r"(n_threads) : "memory");
@@ -340,6 +364,8 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) k_scan_tma(const Scan2Par
         if (lane == 0) {
             int s = 0;
             uint32_t ph = 0;
+            const bool hint = P.l2_hints & 1;
+            const uint64_t pol = l2_policy_evict_first();
             for (long long tile = t0; tile < t1; ++tile) {
                 const uint64_t *src = P.mat + tile * TC;
                 for (int b = 0; b < nb; ++b) {
@@ -347,7 +373,11 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) k_scan_tma(const Scan2Par
                     mbar_wait(empty + s, ph ^ 1);
                     mbar_expect_tx(full + s, (uint32_t)rows_here * ROW_BYTES);
                     unsigned char *dst = ring + (size_t)s * R * ROW_BYTES;
-                    if (rows_here == R) {
+                    if (hint) {
+                        for (int r = 0; r < rows_here; ++r)
+                            tma_bulk_g2s_hint(dst + r * ROW_BYTES, src + (long long)s_row[b * R + r] * P.ld, ROW_BYTES,
+                                              full + s, pol);
+                    } else if (rows_here == R) {
 #pragma unroll
                         for (int r = 0; r < R; ++r)
                             tma_bulk_g2s(dst + r * ROW_BYTES, src + (long long)s_row[b * R + r] * P.ld, ROW_BYTES, full + s);
@@ -368,6 +398,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) k_scan_tma(const Scan2Par
     run[0].mx = run[1].mx = -INFINITY;
     const double neg_inf = -INFINITY;
     double gini_min = INFINITY;
+    const uint64_t pol_last = l2_policy_evict_last();
     int s = 0;
     uint32_t ph = 0;
     for (long long tile = t0; tile < t1; ++tile) {
@@ -389,8 +420,13 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) k_scan_tma(const Scan2Par
             if (++s == S) { s = 0; ph ^= 1; }
         }
         const long long col = tile * TC + 2 * (long long)threadIdx.x;
-        *reinterpret_cast<uint2 *>(P.cnt0 + col) = make_uint2(c0x, c0y);
-        if (P.cnt1) *reinterpret_cast<uint2 *>(P.cnt1 + col) = make_uint2(c1x, c1y);
+        if (P.l2_hints & 2) {
+            st_u32x2_hint(P.cnt0 + col, c0x, c0y, pol_last);
+            if (P.cnt1) st_u32x2_hint(P.cnt1 + col, c1x, c1y, pol_last);
+        } else {
+            *reinterpret_cast<uint2 *>(P.cnt0 + col) = make_uint2(c0x, c0y);
+            if (P.cnt1) *reinterpret_cast<uint2 *>(P.cnt1 + col) = make_uint2(c1x, c1y);
+        }
 
         if (EPI == EPI_GINI2) {
             const bool vx = col < P.n_cols, vy = col + 1 < P.n_cols;
@@ -1047,6 +1083,7 @@ struct kv_shard {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
     int scan_ctas_per_sm = 4;
+    int l2_hints = 0;                         // KOVER_B200_L2HINT (bit 0 loads evict-first, bit 1 count stores evict-last)
     int scan_variant = -1;                    // -1: choose per call; >= 0: forced (KOVER_B200_SCAN_VARIANT)
 
     std::vector<uint32_t *> d_cnt;            // count arrays, [ld] each
@@ -1154,6 +1191,7 @@ extern "C" int kv_create(int device, int64_t n_examples, int64_t n_kmers_total, 
     s->ld = (n_cols + LD_ALIGN - 1) / LD_ALIGN * LD_ALIGN;
     s->n_tiles = s->ld / TILE_COLS;
     if (const char *v = getenv("KOVER_B200_SCAN_VARIANT")) s->scan_variant = atoi(v);
+    if (const char *v = getenv("KOVER_B200_L2HINT")) s->l2_hints = atoi(v);
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
     s->sm_count = prop.multiProcessorCount;
@@ -1453,6 +1491,7 @@ static void fill_scan2(kv_shard *s, Scan2Params &P, int n_act) {
     P.col0 = s->col0;
     P.k_total = s->k_total;
     P.n_act = n_act;
+    P.l2_hints = s->l2_hints;
     if (n_act <= SCAN_INLINE_ROWS) {
         const uint64_t *pm0 = (const uint64_t *)s->h_pin, *pm1 = pm0 + n_act;
         const uint32_t *prow = (const uint32_t *)(pm1 + n_act);
