@@ -113,6 +113,18 @@ int kv_sum_rows_full(kv_shard *s, const uint64_t *mask, int64_t n_rows, void *ou
  * masks: [n_masks, W]; out: [n_masks, n_cols] uint32. */
 int kv_sum_rows_multi(kv_shard *s, int n_masks, const uint64_t *masks, uint32_t *out);
 
+/* ---- dataset split: per-k-mer individual risks (dataset/split.py:171-188, 213-228) ---------
+ * A k-mer's risk round(((n_pos - pos_present) + neg_present) / n_total, 5) depends only on its integer
+ * error count e in [0, n_total].  kv_risk_errors runs ONE two-mask scan, leaves e per k-mer on the device
+ * and ORs into present[n_total + 1] which values of e occur.  The caller evaluates the reference's float
+ * formula on those values, np.unique's them, and hands back two tables e -> index into unique_risks
+ * (presence rule, absence rule); kv_risk_map applies them: out_kmer / out_anti [n_cols] of out_itemsize bytes
+ * (split.py:186-187 stores them with _minimum_uint_size(len(unique_risks))). */
+int kv_risk_errors(kv_shard *s, const uint64_t *pos_mask, const uint64_t *neg_mask, int64_t n_pos, int64_t n_total,
+                   uint8_t *present);
+int kv_risk_map(kv_shard *s, const uint32_t *lut_kmer, const uint32_t *lut_anti, int64_t n_lut, int out_itemsize,
+                void *out_kmer, void *out_anti);
+
 /* ---- a4: KmerRuleClassifications.get_columns (rules.py:135-171) ---------------------------
  * cols: n LOCAL presence-column indices.  out: [n, W] packed words (column j's W words are
  * contiguous).  Unpacking / inversion for absence rules is host work on W words. */

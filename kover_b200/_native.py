@@ -44,6 +44,8 @@ SYMBOLS = {
     "kv_sum_rows": (ctypes.c_int, [_c_p, _c_p, _c_p, ctypes.c_int]),
     "kv_sum_rows_full": (ctypes.c_int, [_c_p, _c_p, _c_i64, _c_p, _c_p, ctypes.c_int]),
     "kv_sum_rows_multi": (ctypes.c_int, [_c_p, ctypes.c_int, _c_p, _c_p]),
+    "kv_risk_errors": (ctypes.c_int, [_c_p, _c_p, _c_p, _c_i64, _c_i64, _c_p]),
+    "kv_risk_map": (ctypes.c_int, [_c_p, _c_p, _c_p, _c_i64, ctypes.c_int, _c_p, _c_p]),
     "kv_get_columns": (ctypes.c_int, [_c_p, _c_p, _c_i64, _c_p]),
     "kv_set_blacklist": (ctypes.c_int, [_c_p, _c_p, _c_i64]),
     "kv_scm_n_blocks": (_c_i64, [_c_i64, _c_i64]),
@@ -221,6 +223,20 @@ class Shard(object):
         out = np.empty((masks.shape[0], self.n_cols), dtype=np.uint32)
         check(self._lib.kv_sum_rows_multi(self._h, masks.shape[0], ptr(masks), ptr(out)))
         return out
+
+    # -- dataset split risk tables
+    def risk_errors(self, pos_mask, neg_mask, n_pos, n_total, present):
+        pos_mask = np.ascontiguousarray(pos_mask, dtype=np.uint64)
+        neg_mask = np.ascontiguousarray(neg_mask, dtype=np.uint64)
+        assert present.dtype == np.uint8 and present.shape == (n_total + 1,)
+        check(self._lib.kv_risk_errors(self._h, ptr(pos_mask), ptr(neg_mask), int(n_pos), int(n_total), ptr(present)))
+
+    def risk_map(self, lut_kmer, lut_anti, out_kmer, out_anti):
+        lk = np.ascontiguousarray(lut_kmer, dtype=np.uint32)
+        la = np.ascontiguousarray(lut_anti, dtype=np.uint32)
+        assert out_kmer.shape == out_anti.shape == (self.n_cols,) and out_kmer.dtype == out_anti.dtype
+        check(self._lib.kv_risk_map(self._h, ptr(lk), ptr(la), lk.shape[0], out_kmer.itemsize, ptr(out_kmer),
+                                    ptr(out_anti)))
 
     # -- a4
     def get_columns(self, local_cols):

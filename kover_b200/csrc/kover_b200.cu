@@ -1023,6 +1023,29 @@ __global__ void k_narrow2(const uint32_t *src, T *pres, T *absn, long long n, un
     }
 }
 
+// dataset/split.py:178-188: a k-mer's individual risk depends only on its integer error count
+// e = (n_pos - pos_present) + neg_present, so the device produces e per k-mer plus the set of values that
+// occur; the host evaluates the reference's float formula on those <= n+1 values and sends back a table.
+__global__ void k_risk_errors(uint32_t *cnt_pos_inout, const uint32_t *cnt_neg, long long n, uint32_t n_pos,
+                              uint8_t *present) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint32_t e = (n_pos - cnt_pos_inout[i]) + cnt_neg[i];
+        cnt_pos_inout[i] = e;
+        present[e] = 1;                  // benign race: every writer stores 1
+    }
+}
+template <typename T>
+__global__ void k_risk_map(const uint32_t *e, const uint32_t *lut_kmer, const uint32_t *lut_anti, T *out_kmer,
+                           T *out_anti, long long n) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint32_t v = e[i];
+        out_kmer[i] = (T)lut_kmer[v];
+        out_anti[i] = (T)lut_anti[v];
+    }
+}
+
 template <typename T>
 __global__ void k_narrow(const uint32_t *src, T *dst, long long n) {
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -1103,7 +1126,8 @@ struct kv_shard {
     bool scm_valid = false, scm_swapped = false, reuse_armed = false, reuse_swap = false;
     long long scm_n_pos = 0, scm_n_neg = 0, scm_ubs = 0;
     double scm_p = 0.0;
-    bool gini_valid = false;
+    bool gini_valid = false, risk_valid = false;
+    long long risk_n = 0;
     GiniParams gini;
 
     double last_kernel_ms = 0.0, scan_ms_total = 0.0;
@@ -1638,6 +1662,70 @@ extern "C" int kv_sum_rows_full(kv_shard *s, const uint64_t *mask, int64_t n_row
     CU(cudaStreamSynchronize(s->stream));
     CU(cudaGetLastError());
     return finish_scan_timing(s);
+}
+
+// ------------------------------------------------------------------------------------------------
+// dataset split: per-k-mer individual risks (dataset/split.py:171-188, 213-228)
+// ------------------------------------------------------------------------------------------------
+extern "C" int kv_risk_errors(kv_shard *s, const uint64_t *pos_mask, const uint64_t *neg_mask, int64_t n_pos,
+                              int64_t n_total, uint8_t *present) {
+    if (!s || !pos_mask || !neg_mask || !present) return fail(KV_E_INVALID, "kv_risk_errors: null pointer");
+    if (n_pos < 0 || n_total < n_pos || n_total > s->n_examples) return fail(KV_E_INVALID, "kv_risk_errors: bad counts");
+    DeviceGuard g(s->device);
+    s->last_launches = 0;
+    s->scm_valid = s->gini_valid = s->risk_valid = false;
+    KV_TRY(ensure_counts(s, 2));
+    int n_act, n_both;
+    KV_TRY(push_records2(s, pos_mask, neg_mask, n_act, n_both));
+    Scan2Params P;
+    fill_scan2(s, P, n_act);
+    P.cnt0 = s->d_cnt[0];
+    P.cnt1 = s->d_cnt[1];
+    KV_TRY(launch_scan<EPI_COUNTS>(s, P, n_both));
+    const size_t nb = (size_t)n_total + 1;
+    KV_TRY(ensure(s->d_stage, nb + 64));
+    CU(cudaMemsetAsync(s->d_stage.p, 0, nb, s->stream));
+    const unsigned grid = (unsigned)std::min<long long>((s->n_cols + 255) / 256, (long long)s->sm_count * 8);
+    k_risk_errors<<<grid, 256, 0, s->stream>>>(s->d_cnt[0], s->d_cnt[1], s->n_cols, (uint32_t)n_pos, (uint8_t *)s->d_stage.p);
+    count_launch(s);
+    KV_TRY(ensure_pinned(s, nb));
+    CU(cudaMemcpyAsync(s->h_pin, s->d_stage.p, nb, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    CU(cudaGetLastError());
+    const uint8_t *h = (const uint8_t *)s->h_pin;
+    for (size_t i = 0; i < nb; ++i) present[i] |= h[i];
+    s->risk_valid = true;
+    s->risk_n = n_total;
+    return finish_scan_timing(s);
+}
+
+extern "C" int kv_risk_map(kv_shard *s, const uint32_t *lut_kmer, const uint32_t *lut_anti, int64_t n_lut,
+                           int out_itemsize, void *out_kmer, void *out_anti) {
+    if (!s || !lut_kmer || !lut_anti || !out_kmer || !out_anti) return fail(KV_E_INVALID, "kv_risk_map: null pointer");
+    if (!s->risk_valid) return fail(KV_E_INVALID, "kv_risk_map: no kv_risk_errors result on the device");
+    if (n_lut != s->risk_n + 1) return fail(KV_E_INVALID, "kv_risk_map: table must have n_total + 1 entries");
+    if (out_itemsize != 1 && out_itemsize != 2 && out_itemsize != 4 && out_itemsize != 8)
+        return fail(KV_E_INVALID, "kv_risk_map: out_itemsize must be 1, 2, 4 or 8");
+    DeviceGuard g(s->device);
+    s->last_launches = 0;
+    const size_t lut_bytes = (size_t)n_lut * 4, half = ((size_t)s->n_cols * out_itemsize + 15) / 16 * 16;
+    const size_t lut_pad = (lut_bytes + 15) / 16 * 16;
+    KV_TRY(ensure(s->d_stage, 2 * lut_pad + 2 * half + 64));
+    char *d_lk = (char *)s->d_stage.p, *d_la = d_lk + lut_pad, *d_ok = d_la + lut_pad, *d_oa = d_ok + half;
+    CU(cudaMemcpyAsync(d_lk, lut_kmer, lut_bytes, cudaMemcpyHostToDevice, s->stream));
+    CU(cudaMemcpyAsync(d_la, lut_anti, lut_bytes, cudaMemcpyHostToDevice, s->stream));
+    const unsigned grid = (unsigned)std::min<long long>((s->n_cols + 255) / 256, (long long)s->sm_count * 8);
+    const uint32_t *e = s->d_cnt[0], *lk = (const uint32_t *)d_lk, *la = (const uint32_t *)d_la;
+    if (out_itemsize == 1) k_risk_map<uint8_t><<<grid, 256, 0, s->stream>>>(e, lk, la, (uint8_t *)d_ok, (uint8_t *)d_oa, s->n_cols);
+    else if (out_itemsize == 2) k_risk_map<uint16_t><<<grid, 256, 0, s->stream>>>(e, lk, la, (uint16_t *)d_ok, (uint16_t *)d_oa, s->n_cols);
+    else if (out_itemsize == 4) k_risk_map<uint32_t><<<grid, 256, 0, s->stream>>>(e, lk, la, (uint32_t *)d_ok, (uint32_t *)d_oa, s->n_cols);
+    else k_risk_map<uint64_t><<<grid, 256, 0, s->stream>>>(e, lk, la, (uint64_t *)d_ok, (uint64_t *)d_oa, s->n_cols);
+    count_launch(s);
+    CU(cudaMemcpyAsync(out_kmer, d_ok, (size_t)s->n_cols * out_itemsize, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaMemcpyAsync(out_anti, d_oa, (size_t)s->n_cols * out_itemsize, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    CU(cudaGetLastError());
+    return KV_OK;
 }
 
 // counts of n_masks masks into d_cnt[first .. first+n_masks) (device resident)

@@ -295,6 +295,14 @@ class KmerRuleClassifications(BaseRuleClassifications):
         n_node = np.array([len(example_idx[c]) for c in classes], dtype=np.int64)
         return self._group.gini_best_split(masks, prior, total, n_node)
 
+    def kmer_risk_tables(self, train_pos_idx, train_neg_idx):
+        """The individual k-mer risk tables `kover dataset split` stores per split / fold (split.py:171-188):
+        -> (unique_risks, unique_risk_by_kmer, unique_risk_by_anti_kmer).  One pass over the matrix instead of
+        two sum_rows passes + six numpy passes over 2K floats + an np.unique over 2K values."""
+        train_pos_idx, train_neg_idx = np.asarray(train_pos_idx), np.asarray(train_neg_idx)
+        return self._group.kmer_risk_tables(self.row_mask(train_pos_idx), self.row_mask(train_neg_idx),
+                                            train_pos_idx.shape[0], train_pos_idx.shape[0] + train_neg_idx.shape[0])
+
     def gini_scores(self):
         """rules_criterion of the last gini_best_split call (cart.py:228-231), float64 [n_kmers]."""
         return self._group.gini_scores()

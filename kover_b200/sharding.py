@@ -179,6 +179,35 @@ class ShardGroup(object):
             out[k:] = n_rows - out[:k]
         return out
 
+    # ------------------------------------------------------------------ dataset split risk tables
+    def kmer_risk_tables(self, pos_mask, neg_mask, n_pos, n_total):
+        """dataset/split.py:178-188 -> (unique_risks float64, unique_risk_by_kmer, unique_risk_by_anti_kmer),
+        the two index arrays in _minimum_uint_size(len(unique_risks)) like split.py:186-187."""
+        from .utils import _minimum_uint_size
+        if self.comm is not None:
+            raise NotImplementedError("kmer_risk_tables runs in the single process that writes the split")
+        present = np.zeros(n_total + 1, dtype=np.uint8)
+        for s in self.shards:
+            s.risk_errors(pos_mask, neg_mask, n_pos, n_total, present)
+        e = np.flatnonzero(present)
+        # the reference's float arithmetic, on the distinct error counts only (it is elementwise)
+        kmer_risks = e.astype(float)
+        kmer_risks /= n_total
+        np.round(kmer_risks, 5, out=kmer_risks)
+        anti_kmer_risks = 1.0 - kmer_risks
+        np.round(anti_kmer_risks, 5, out=anti_kmer_risks)
+        unique_risks, inverse = np.unique(np.hstack((kmer_risks, anti_kmer_risks)), return_inverse=True)
+        lut_kmer = np.zeros(n_total + 1, dtype=np.uint32)
+        lut_anti = np.zeros(n_total + 1, dtype=np.uint32)
+        lut_kmer[e] = inverse[:e.shape[0]]
+        lut_anti[e] = inverse[e.shape[0]:]
+        dtype = _minimum_uint_size(len(unique_risks))
+        by_kmer = np.empty(self.n_kmers, dtype=dtype)
+        by_anti = np.empty(self.n_kmers, dtype=dtype)
+        for s in self.shards:
+            s.risk_map(lut_kmer, lut_anti, by_kmer[s.col0:s.col0 + s.n_cols], by_anti[s.col0:s.col0 + s.n_cols])
+        return unique_risks, by_kmer, by_anti
+
     # ------------------------------------------------------------------ a4
     def get_packed_columns(self, cols):
         """cols: presence-column indices (global).  -> uint64 [len(cols), W]."""

@@ -483,3 +483,21 @@ def cart_fit(rule_classifications, example_idx, criterion="gini", max_depth=10, 
         queue.append(node.left_child)
         queue.append(node.right_child)
     return root
+
+
+# --------------------------------------------------------------------------------------
+# dataset split: individual k-mer risk tables -- dataset/split.py:171-188 (== 213-228 per fold)
+# --------------------------------------------------------------------------------------
+def kmer_risk_tables(rule_classifications, train_pos_idx, train_neg_idx):
+    """-> (unique_risks, unique_risk_by_kmer, unique_risk_by_anti_kmer) exactly as split.py stores them."""
+    n_kmers = rule_classifications.shape[1] // 2
+    n_train = len(train_pos_idx) + len(train_neg_idx)
+    kmer_risks = (len(train_pos_idx) - rule_classifications.sum_rows(train_pos_idx)[:n_kmers]).astype(float)   # :178
+    kmer_risks += rule_classifications.sum_rows(train_neg_idx)[:n_kmers]                                       # :179
+    kmer_risks /= n_train                                                                                      # :180
+    np.round(kmer_risks, 5, out=kmer_risks)
+    anti_kmer_risks = 1.0 - kmer_risks
+    np.round(anti_kmer_risks, 5, out=anti_kmer_risks)
+    unique_risks, inverse = np.unique(np.hstack((kmer_risks, anti_kmer_risks)), return_inverse=True)           # :184
+    t = minimum_uint_size(len(unique_risks))
+    return unique_risks, inverse[:n_kmers].astype(t), inverse[n_kmers:].astype(t)

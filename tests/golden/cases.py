@@ -204,6 +204,15 @@ CART_CASES = [
 ]
 
 
+RISK_CASES = [
+    # name, matrix, labels, train subset seed
+    ("risk_M1", "M1", "M1_noisy", 41),
+    ("risk_M2_all", "M2", "M2_planted", None),
+    ("risk_MD", "MD", "MD_planted", 43),
+    ("risk_MS", "MS", "MS_random", None),
+]
+
+
 def utility_inputs(case):
     name, mname, lname, p, blacklist, ubs = case
     X, P, n, chunks = matrix(mname)

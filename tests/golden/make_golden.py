@@ -179,10 +179,37 @@ def gen_cart():
     # scores through `candidates == where(score == min)` at every node, which tree_json already holds)
 
 
+# ------------------------------------------------------------------ dataset split risk tables (f-4)
+def gen_risk():
+    """dataset/split.py:171-188 cannot be called as a function (it is inlined in _split, which needs an HDF5
+    file and h5py); the lines are replayed here verbatim on the REAL reference's sum_rows."""
+    for name, mname, lname, seed in cases.RISK_CASES:
+        X, P, n, chunks = cases.matrix(mname)
+        labels = cases.labels(lname)
+        train_idx = cases.train_subset(n, seed)
+        k = P.shape[1]
+        kmer_matrix = ref_rc(P, n, chunks)
+        train_pos_idx = train_idx[labels[train_idx] == 1]
+        train_neg_idx = train_idx[labels[train_idx] == 0]
+        kmer_risks = (len(train_pos_idx) - kmer_matrix.sum_rows(train_pos_idx)[: k]).astype(float)
+        kmer_risks += kmer_matrix.sum_rows(train_neg_idx)[: k]
+        kmer_risks /= len(train_idx)
+        np.round(kmer_risks, 5, out=kmer_risks)
+        anti_kmer_risks = 1.0 - kmer_risks
+        np.round(anti_kmer_risks, 5, out=anti_kmer_risks)
+        unique_risks, inv = np.unique(np.hstack((kmer_risks, anti_kmer_risks)), return_inverse=True)
+        t = ref.utils._minimum_uint_size(len(unique_risks))
+        save(name, unique_risks=unique_risks, by_kmer=inv[:k].astype(t), by_anti_kmer=inv[k:].astype(t))
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "risk":
+        gen_risk()
+        sys.exit(0)
     gen_popcount()
     gen_pack()
     gen_rules()
     gen_utility()
     gen_scm()
     gen_cart()
+    gen_risk()

@@ -371,6 +371,34 @@ def test_cross_entropy_fit_matches_checker_counts():
     assert sorted(r.kmer_index for r in t.decision_tree.rules) == [3, 9, 20]
 
 
+# ---------------------------------------------------------------------------------- dataset split risk tables
+@pytest.mark.parametrize("case", cases.RISK_CASES, ids=[c[0] for c in cases.RISK_CASES])
+@pytest.mark.parametrize("devices", [[0], [0, 0]], ids=["1shard", "2shards"])
+def test_kmer_risk_tables_golden(golden_dir, case, devices):
+    name, mname, lname, seed = case
+    g = load(golden_dir, name)
+    X, P, n, chunks = cases.matrix(mname)
+    y = cases.labels(lname)
+    train = cases.train_subset(n, seed)
+    rc = KmerRuleClassifications(as_dataset(P, chunks), n, devices=devices)
+    ur, bk, ba = rc.kmer_risk_tables(train[y[train] == 1], train[y[train] == 0])
+    assert np.array_equal(ur, g["unique_risks"])
+    assert bk.dtype == g["by_kmer"].dtype and np.array_equal(bk, g["by_kmer"])
+    assert ba.dtype == g["by_anti_kmer"].dtype and np.array_equal(ba, g["by_anti_kmer"])
+
+
+def test_kmer_risk_tables_vs_checker_large():
+    seed, n, k = 21, 3000, 150000
+    P = synthetic_block(seed, n, 0, k)
+    y = synthetic_labels(seed, n, sorted_by_label=False)
+    train = train_split(seed, n)
+    pos, neg = train[y[train] == 1], train[y[train] == 0]
+    want = ko.kmer_risk_tables(ko.OracleKmerRuleClassifications(P, n, fast=True), pos, neg)
+    got = KmerRuleClassifications(P, n, devices=[0]).kmer_risk_tables(pos, neg)
+    for w, g_ in zip(want, got):
+        assert w.dtype == g_.dtype and np.array_equal(w, g_)
+
+
 # ---------------------------------------------------------------------------------- full-size properties (config 2)
 @pytest.fixture(scope="module")
 def config2():

@@ -169,3 +169,17 @@ def test_cart_fit(golden_dir, case):
         tiebreaker = lambda idx: ko.cart_tiebreaker(idx, occ)
     root = ko.cart_fit(rc, example_idx, "gini", max_depth, mss, class_importance, [], tiebreaker)
     tree_equal(root.to_dict(), want)
+
+
+@pytest.mark.parametrize("case", cases.RISK_CASES, ids=[c[0] for c in cases.RISK_CASES])
+def test_kmer_risk_tables(golden_dir, case):
+    name, mname, lname, seed = case
+    g = load(golden_dir, name)
+    X, P, n, chunks = cases.matrix(mname)
+    y = cases.labels(lname)
+    train = cases.train_subset(n, seed)
+    rc = ko.OracleKmerRuleClassifications(as_dataset(P, chunks), n, fast=True)
+    ur, bk, ba = ko.kmer_risk_tables(rc, train[y[train] == 1], train[y[train] == 0])
+    assert np.array_equal(ur, g["unique_risks"])
+    assert bk.dtype == g["by_kmer"].dtype and np.array_equal(bk, g["by_kmer"])
+    assert ba.dtype == g["by_anti_kmer"].dtype and np.array_equal(ba, g["by_anti_kmer"])
