@@ -274,6 +274,23 @@ def extra_measurements(rc, shard, steps, k_local, reps=12):
     out["hp_grid_iteration_12_jobs"] = {"ms_per_grid": ms, "job_rules_per_s": len(jobs) * 2.0 * k_local / (ms * 1e-3),
                                         "matrix_scans_per_grid": (ib.scan_calls - ia.scan_calls) / 7.0,
                                         "rescores_per_grid": (ib.rescore_calls - ia.rescore_calls) / 7.0}
+    # whole greedy fits through the reference-shaped learners (host control flow + get_columns + bookkeeping)
+    from kover_b200.learning.common.rules import LazyKmerRuleList
+    from kover_b200.learning.learners.cart import DecisionTreeClassifier
+    from kover_b200.learning.learners.scm import SetCoveringMachine
+    rules = LazyKmerRuleList(np.arange(k_local), np.arange(k_local))
+    its = []
+    m = SetCoveringMachine(model_type="conjunction", p=1.0, max_rules=10)
+    t0 = time.perf_counter()
+    m.fit(rules, rc, pos, neg, tiebreaker=lambda idx: idx, iteration_callback=lambda i: its.append(1))
+    dt = time.perf_counter() - t0
+    out["scm_fit_max_rules_10"] = {"seconds": dt, "iterations": len(its), "ms_per_iteration": 1e3 * dt / max(1, len(its))}
+    t = DecisionTreeClassifier("gini", 5, 2, {0: 1.0, 1: 1.0})
+    t0 = time.perf_counter()
+    t.fit(rules, rc, ex)
+    dt = time.perf_counter() - t0
+    n_split = len(t.decision_tree.rules)
+    out["cart_fit_max_depth_5"] = {"seconds": dt, "split_nodes": n_split, "ms_per_split_node": 1e3 * dt / max(1, n_split)}
     # the reference's own operator API: sum_rows returns a 2K-long host array (D2H of 2K x uint16 per call)
     out["sum_rows_dropin_ms"] = timed(lambda: rc.sum_rows(steps[0][1]), 4)
     # upload path: host numpy block -> pinned ring -> HBM (kv_upload_block), on 1/8 of the matrix

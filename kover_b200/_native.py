@@ -148,7 +148,7 @@ class Shard(object):
         self.col0 = int(col0)
         self.n_cols = int(n_cols)
         # reusable output buffers of the per-step calls (their contents are copied out before returning)
-        self._tie_cap = 4096
+        self._tie_cap = 1 << 16
         self._tie_buf = [np.empty(self._tie_cap, dtype=np.int64) for _ in range(3)]
 
     def close(self):
@@ -363,21 +363,24 @@ class Shard(object):
                                      ctypes.byref(out)))
         return out.value
 
-    def gini_best_split(self, class_masks, altered_prior, n_total, n_node, capacity=4096):
+    def gini_best_split(self, class_masks, altered_prior, n_total, n_node, capacity=None):
         """Single-shard fused call -> (min score, rule indices achieving it, ascending)."""
         masks = np.ascontiguousarray(class_masks, dtype=np.uint64)
         assert masks.ndim == 2 and masks.shape[1] == self.n_words
         pri = np.ascontiguousarray(altered_prior, dtype=np.float64)
         tot = np.ascontiguousarray(n_total, dtype=np.float64)
         nn = np.ascontiguousarray(n_node, dtype=np.int64)
-        idx = np.empty(capacity, dtype=np.int64)
+        if capacity is None:
+            capacity, idx = self._tie_cap, self._tie_buf[0]
+        else:
+            idx = np.empty(capacity, dtype=np.int64)
         m, n = ctypes.c_double(0.0), _c_i64(0)
         rc = self._lib.kv_gini_best_split(self._h, masks.shape[0], ptr(masks), ptr(pri), ptr(tot), ptr(nn),
                                           ctypes.byref(m), capacity, ptr(idx), ctypes.byref(n))
         if rc == KV_E_OVERFLOW:      # the counts and the minimum are still on the device
             return m.value, self.gini_ties(m.value, int(n.value))
         check(rc)
-        return m.value, idx[:n.value]
+        return m.value, idx[:n.value].copy()
 
     def gini_ties(self, min_score, capacity=4096):
         while True:

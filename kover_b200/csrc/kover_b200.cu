@@ -19,6 +19,7 @@
 #include "kover_b200.h"
 
 #include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>   // only to order LARGE tie lists (not on the scan path)
 
 #include <algorithm>
 #include <cmath>
@@ -636,7 +637,13 @@ __device__ __forceinline__ void tie_emit(const TieParams &P, long long rule, dou
         const long long b = fast_div(rule, P.ubs, P.inv_ubs);
         if (!P.sel[b] || !tie_close(u, P.bm[b], P.tol[b])) return;
     }
-    const unsigned long long slot = atomicAdd(P.count, 1ull);
+    // one atomic per group of converged lanes that emit together
+    const unsigned peers = __activemask();
+    const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(P.count, (unsigned long long)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    const unsigned long long slot = base + __popc(peers & ((1u << lane) - 1u));
     if ((long long)slot < P.cap) {
         TieRec r;
         r.idx = rule; r.pe = pe; r.nc = nc;
@@ -966,8 +973,15 @@ __global__ void __launch_bounds__(256) k_gini2_ties_seg(const GiniParams P) {
             for (int j = 0; j < 2; ++j) {
                 const long long col = ((sb + src) << 6) + lane + 32 * j;
                 if (col >= P.n_cols) continue;
-                if (gini_score<2>(col, P) == target) {
-                    const unsigned long long slot = atomicAdd(P.counter, 1ull);
+                const bool hit = gini_score<2>(col, P) == target;
+                // one atomic per warp: a node with few examples can tie on most of the k-mers
+                const unsigned hits = __ballot_sync(__activemask(), hit);
+                if (hit) {
+                    const int leader = __ffs(hits) - 1;
+                    unsigned long long base = 0;
+                    if (lane == leader) base = atomicAdd(P.counter, (unsigned long long)__popc(hits));
+                    base = __shfl_sync(hits, base, leader);
+                    const unsigned long long slot = base + __popc(hits & ((1u << lane) - 1u));
                     if ((long long)slot < P.cap) P.out_idx[slot] = P.col0 + col;
                 }
             }
@@ -978,10 +992,14 @@ __global__ void __launch_bounds__(256) k_gini2_ties_seg(const GiniParams P) {
 // ------------------------------------------------------------------------------------------------
 // small kernels
 // ------------------------------------------------------------------------------------------------
+struct InlineCols {
+    long long c[8];
+};
 __global__ void k_gather_cols(const uint64_t *mat, long long ld, long long n_words, const long long *cols,
-                              long long n, uint64_t *out) {
+                              const InlineCols inl, long long n, uint64_t *out) {
     const long long j = blockIdx.x;
-    for (long long w = threadIdx.x; w < n_words; w += blockDim.x) out[j * n_words + w] = mat[w * ld + cols[j]];
+    const long long col = cols ? cols[j] : inl.c[j];          // up to 8 columns ride in the parameters
+    for (long long w = threadIdx.x; w < n_words; w += blockDim.x) out[j * n_words + w] = mat[w * ld + col];
 }
 
 // 32-bit packed rows -> halves of the 64-bit image (rules.py:123-125): row 2w is the high half
@@ -1110,7 +1128,7 @@ struct kv_shard {
     int scan_variant = -1;                    // -1: choose per call; >= 0: forced (KOVER_B200_SCAN_VARIANT)
 
     std::vector<uint32_t *> d_cnt;            // count arrays, [ld] each
-    DevBuf d_rec, d_misc, d_ties, d_stage;
+    DevBuf d_rec, d_misc, d_ties, d_stage, d_sort_tmp, d_sort_io;
     void *h_pin = nullptr;                    // pinned staging (records, block tables, small results)
     size_t h_pin_bytes = 0;
     void *h_up[2] = {nullptr, nullptr};       // pinned upload ring
@@ -1244,7 +1262,7 @@ extern "C" int kv_destroy(kv_shard *s) {
     p2p_destroy(s->p2p);
     cudaFree(s->d_mat);
     for (auto p : s->d_cnt) cudaFree(p);
-    for (DevBuf *b : {&s->d_rec, &s->d_misc, &s->d_ties, &s->d_stage})
+    for (DevBuf *b : {&s->d_rec, &s->d_misc, &s->d_ties, &s->d_stage, &s->d_sort_tmp, &s->d_sort_io})
         if (b->p) cudaFree(b->p);
     if (s->d_black_pres) cudaFree(s->d_black_pres);
     if (s->d_black_abs) cudaFree(s->d_black_abs);
@@ -1665,6 +1683,34 @@ extern "C" int kv_sum_rows_full(kv_shard *s, const uint64_t *mask, int64_t n_row
 }
 
 // ------------------------------------------------------------------------------------------------
+// Large tie lists (tens of thousands of equivalent rules are normal on real k-mer data): the tie
+// kernels append in arbitrary order, the reference's order is ascending rule index.  Small lists are
+// sorted on the host; large ones by a device radix sort so that the host only copies.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_split_tierecs(const TieRec *recs, long long n, long long *keys, unsigned long long *vals) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const TieRec r = recs[i];
+        keys[i] = r.idx;
+        vals[i] = ((unsigned long long)r.pe << 32) | r.nc;
+    }
+}
+
+// sorts keys (and vals if given) ascending; results land in keys_out / vals_out (device)
+static int device_sort(kv_shard *s, const long long *keys_in, long long *keys_out, const unsigned long long *vals_in,
+                       unsigned long long *vals_out, long long n) {
+    size_t tmp = 0;
+    if (vals_in) CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp, keys_in, keys_out, vals_in, vals_out, (int)n, 0, 64, s->stream));
+    else CU(cub::DeviceRadixSort::SortKeys(nullptr, tmp, keys_in, keys_out, (int)n, 0, 64, s->stream));
+    KV_TRY(ensure(s->d_sort_tmp, tmp + 64));
+    if (vals_in)
+        CU(cub::DeviceRadixSort::SortPairs(s->d_sort_tmp.p, tmp, keys_in, keys_out, vals_in, vals_out, (int)n, 0, 64, s->stream));
+    else CU(cub::DeviceRadixSort::SortKeys(s->d_sort_tmp.p, tmp, keys_in, keys_out, (int)n, 0, 64, s->stream));
+    count_launch(s, 4);
+    return KV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // dataset split: per-k-mer individual risks (dataset/split.py:171-188, 213-228)
 // ------------------------------------------------------------------------------------------------
 extern "C" int kv_risk_errors(kv_shard *s, const uint64_t *pos_mask, const uint64_t *neg_mask, int64_t n_pos,
@@ -1819,13 +1865,27 @@ extern "C" int kv_get_columns(kv_shard *s, const int64_t *cols, int64_t n, uint6
     s->last_launches = 0;
     const size_t out_bytes = (size_t)n * s->W * 8, idx_bytes = (size_t)n * 8;
     KV_TRY(ensure(s->d_stage, out_bytes + idx_bytes));
-    long long *d_cols = (long long *)((char *)s->d_stage.p + out_bytes);
-    CU(cudaMemcpyAsync(d_cols, cols, idx_bytes, cudaMemcpyHostToDevice, s->stream));
+    long long *d_cols = nullptr;
+    InlineCols inl;
+    memset(&inl, 0, sizeof inl);
+    if (n <= 8) {
+        for (int64_t i = 0; i < n; ++i) inl.c[i] = cols[i];
+    } else {
+        d_cols = (long long *)((char *)s->d_stage.p + out_bytes);
+        CU(cudaMemcpyAsync(d_cols, cols, idx_bytes, cudaMemcpyHostToDevice, s->stream));
+    }
     const int threads = (int)std::min<long long>(256, std::max<long long>(32, s->W));
-    k_gather_cols<<<(unsigned)n, threads, 0, s->stream>>>(s->d_mat, s->ld, s->W, d_cols, n, (uint64_t *)s->d_stage.p);
+    k_gather_cols<<<(unsigned)n, threads, 0, s->stream>>>(s->d_mat, s->ld, s->W, d_cols, inl, n, (uint64_t *)s->d_stage.p);
     count_launch(s);
-    CU(cudaMemcpyAsync(out, s->d_stage.p, out_bytes, cudaMemcpyDeviceToHost, s->stream));
-    CU(cudaStreamSynchronize(s->stream));
+    if (out_bytes <= ((size_t)1 << 16)) {          // small result: through pinned memory, polled
+        KV_TRY(ensure_pinned(s, out_bytes));
+        CU(cudaMemcpyAsync(s->h_pin, s->d_stage.p, out_bytes, cudaMemcpyDeviceToHost, s->stream));
+        CU(stream_sync_spin(s->stream));
+        memcpy(out, s->h_pin, out_bytes);
+    } else {
+        CU(cudaMemcpyAsync(out, s->d_stage.p, out_bytes, cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+    }
     CU(cudaGetLastError());
     return KV_OK;
 }
@@ -2073,10 +2133,24 @@ static int scm_collect_ties(kv_shard *s, int64_t n_blocks, int64_t capacity, dou
     if (found > capacity) return fail(KV_E_OVERFLOW, "tie buffer too small");
     if (found == 0) return KV_OK;
     if (found > kTieFirstBatch) {
-        KV_TRY(ensure_pinned(s, sizeof(TieHeader) + (size_t)found * sizeof(TieRec)));
-        CU(cudaMemcpyAsync(s->h_pin, d_hdr, sizeof(TieHeader) + (size_t)found * sizeof(TieRec), cudaMemcpyDeviceToHost,
-                           s->stream));
-        CU(stream_sync_spin(s->stream));
+        // split {rule, (pos_err, neg_cover)} -> radix sort by rule -> copy out in order
+        KV_TRY(ensure(s->d_sort_io, (size_t)found * 32));
+        long long *k_in = (long long *)s->d_sort_io.p, *k_out = k_in + found;
+        unsigned long long *v_in = (unsigned long long *)(k_out + found), *v_out = v_in + found;
+        const unsigned g2 = (unsigned)std::min<long long>((found + 255) / 256, (long long)s->sm_count * 8);
+        k_split_tierecs<<<g2, 256, 0, s->stream>>>(d_rec, found, k_in, v_in);
+        count_launch(s);
+        KV_TRY(device_sort(s, k_in, k_out, v_in, v_out, found));
+        KV_TRY(ensure_pinned(s, (size_t)found * 8));
+        CU(cudaMemcpyAsync(rule_idx, k_out, (size_t)found * 8, cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaMemcpyAsync(s->h_pin, v_out, (size_t)found * 8, cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+        const unsigned long long *v = (const unsigned long long *)s->h_pin;
+        for (long long i = 0; i < found; ++i) {
+            pos_err[i] = (int64_t)(v[i] >> 32);
+            neg_cover[i] = (int64_t)(v[i] & 0xFFFFFFFFull);
+        }
+        return KV_OK;
     }
     TieRec *recs = (TieRec *)((TieHeader *)s->h_pin + 1);
     std::sort(recs, recs + found, [](const TieRec &a, const TieRec &b) { return a.idx < b.idx; });
@@ -2597,11 +2671,13 @@ static int gini_ties_impl(kv_shard *s, bool from_device, double min_score, int64
     if (found > capacity) return fail(KV_E_OVERFLOW, "kv_gini_ties: tie buffer too small");
     if (found == 0) return KV_OK;
     if (found > kGiniFirstBatch) {
-        CU(cudaMemcpyAsync(rule_idx, G.out_idx, (size_t)found * 8, cudaMemcpyDeviceToHost, s->stream));
-        CU(stream_sync_spin(s->stream));
-    } else {
-        memcpy(rule_idx, h + 2, (size_t)found * 8);
+        KV_TRY(ensure(s->d_sort_io, (size_t)found * 8));
+        KV_TRY(device_sort(s, G.out_idx, (long long *)s->d_sort_io.p, nullptr, nullptr, found));
+        CU(cudaMemcpyAsync(rule_idx, s->d_sort_io.p, (size_t)found * 8, cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+        return KV_OK;
     }
+    memcpy(rule_idx, h + 2, (size_t)found * 8);
     std::sort(rule_idx, rule_idx + found);
     return KV_OK;
 }

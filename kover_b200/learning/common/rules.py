@@ -179,6 +179,12 @@ class KmerRuleClassifications(BaseRuleClassifications):
         if hasattr(columns, "__index__"):  # All int types implement the __index__ method (PEP 357)
             columns = [columns.__index__()]
             columns_is_int = True
+            c = columns[0]
+            if 0 <= c < 2 * self._n_kmers and not self.dataset_removed_rows:
+                # the learners' per-iteration call (scm.py:133, cart.py:245): one rule, nothing removed
+                packed = self._group.get_packed_columns(np.array([c % self._n_kmers], dtype=np.int64))[0]
+                bits = np.unpackbits(packed.astype(">u8").view(np.uint8))[:self.dataset_initial_n_rows]
+                return (1 - bits) if c >= self._n_kmers else bits
         elif isinstance(columns, np.ndarray):
             columns = columns.tolist()
         elif isinstance(columns, list):

@@ -184,6 +184,84 @@ def test_best_utility_rules_vs_checker(seed, n, k, p, ubs, sorted_labels):
         rc.close()
 
 
+def test_large_equivalent_rule_sets():
+    """Tens of thousands of equivalent rules (duplicated k-mers, as on real genomes): the device-sorted path of
+    both tie collectors, single- and multi-shard, against the checker."""
+    rs = np.random.RandomState(77)
+    n, k = 150, 90000
+    base = (rs.rand(n, 12) < 0.5).astype(np.uint8)
+    X = base[:, rs.randint(0, 12, size=k)]
+    P = cases.pack64(X)
+    y = (base[:, 3] & (1 - base[:, 7])).astype(np.uint8)
+    pos, neg = np.where(y == 1)[0], np.where(y == 0)[0]
+    orc = ko.OracleKmerRuleClassifications(P, n, fast=True)
+    wu, wi, wp, wn = ko.merge_utility_blocks(len(neg) - orc.sum_rows(neg), len(pos) - orc.sum_rows(pos), 1.0,
+                                             np.zeros(2 * k, dtype=bool), block_size=25000)
+    ex = {0: neg, 1: pos}
+    n_total, altered = ko.cart_altered_priors(ex, {0: 1.0, 1: 1.0})
+    score = ko.gini_rule_score(orc, ex, altered, n_total)
+    assert len(wi) > 5000 and (score == score.min()).sum() > 5000
+    for devices in ([0], [0, 0, 0]):
+        rc = KmerRuleClassifications(P, n, devices=devices)
+        bu, bi, bp, bn = rc.best_utility_rules(1.0, pos, neg, util_block_size=25000)
+        assert bu == wu and np.array_equal(bi, np.asarray(wi, dtype=np.int64))
+        assert np.array_equal(bp, wp) and np.array_equal(bn, wn)
+        m, cand = rc.gini_best_split(ex, altered, n_total)
+        assert m == score.min() and np.array_equal(cand, np.where(score == m)[0])
+        rc.close()
+
+
+@pytest.mark.parametrize("seed", range(48))
+def test_randomized_small_shapes(seed):
+    """Ragged / tiny / boundary shapes: 1..260 genomes, 1..5000 k-mers, random utility-block sizes, random
+    blacklists (sometimes whole blocks), random p, 1-3 shards -- SCM scan, sum_rows, get_columns and the Gini
+    scan against the CPU checker, bit for bit."""
+    rs = np.random.RandomState(1000 + seed)
+    n = int(rs.choice([1, 2, 63, 64, 65, 127, 128, 129, 200, 260]))
+    k = int(rs.choice([1, 2, 31, 63, 64, 65, 511, 512, 513, 1023, 1024, 1025, 2047, 3000, 5000]))
+    dens = rs.choice([0.0, 0.02, 0.3, 0.5, 0.9, 1.0], size=k)
+    X = (rs.rand(n, k) < dens[None, :]).astype(np.uint8)
+    P = cases.pack64(X)
+    y = (rs.rand(n) < rs.choice([0.2, 0.5, 0.8])).astype(np.uint8)
+    if rs.rand() < 0.5:
+        y = np.sort(y)
+    keep = rs.rand(n) < 0.8
+    pos, neg = np.where((y == 1) & keep)[0], np.where((y == 0) & keep)[0]
+    ubs = int(rs.choice([1, 7, 64, 100, 1000, 1000000]))
+    p = float(rs.choice([0.0, 0.1, 0.316, 1.0, 1.778, 10.0, 999999.0]))
+    blacklist = np.unique(rs.randint(0, 2 * k, size=rs.randint(0, max(1, k // 3))))
+    if rs.rand() < 0.3 and 2 * k > ubs:
+        blacklist = np.unique(np.concatenate([blacklist, np.arange(0, min(ubs, 2 * k - 1))]))   # a fully blacklisted head block
+    if len(blacklist) == 2 * k:
+        blacklist = blacklist[:-1]
+    devices = [0] * int(rs.choice([1, 2, 3]))
+    orc = ko.OracleKmerRuleClassifications(P, n, fast=True)
+    rc = KmerRuleClassifications(P, n, devices=devices)
+    assert np.array_equal(rc.sum_rows(pos), orc.sum_rows(pos))
+    bl = np.zeros(2 * k, dtype=bool)
+    bl[blacklist] = True
+    pe = len(pos) - orc.sum_rows(pos) if len(pos) else np.zeros(2 * k, dtype=np.uint8)
+    wu, wi, wp, wn = ko.merge_utility_blocks(len(neg) - orc.sum_rows(neg), pe, p, bl, block_size=ubs)
+    bu, bi, bp, bn = rc.best_utility_rules(p, pos, neg, rule_blacklist=blacklist, util_block_size=ubs)
+    assert bu == wu and np.array_equal(bi, np.asarray(wi, dtype=np.int64))
+    assert np.array_equal(bp, wp) and np.array_equal(bn, wn)
+    cols = sorted(set(int(c) for c in rs.randint(0, 2 * k, size=3)))
+    assert np.array_equal(rc.get_columns(cols), orc.get_columns(cols))
+    if len(pos) and len(neg):
+        ex = {0: neg, 1: pos}
+        n_total, altered = ko.cart_altered_priors({0: np.where(y == 0)[0], 1: np.where(y == 1)[0]}, {0: 1.0, 1: 1.7})
+        want = ko.gini_rule_score(orc, ex, altered, n_total)
+        kb = blacklist[blacklist < k]
+        want[kb] = np.inf
+        m, cand = rc.gini_best_split(ex, altered, n_total, rule_blacklist=kb)
+        assert m == want.min()
+        if m != np.inf:
+            assert np.array_equal(cand, np.where(want == m)[0])
+        else:
+            assert len(cand) == 0
+    rc.close()
+
+
 # ---------------------------------------------------------------------------------- a7 / a8
 @pytest.mark.parametrize("case", cases.SCM_CASES, ids=[c[0] for c in cases.SCM_CASES])
 def test_scm_fit_golden(golden_dir, case, monkeypatch):
