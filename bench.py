@@ -420,6 +420,12 @@ def run_ours(args):
     else:
         peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
     achieved = float(np.sum(alg_bytes) / (np.sum(kernel_ms) * 1e-3) / 1e9)
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.isfile(tpath):          # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture
+        t = json.load(open(tpath))
+        traffic = t["dram_bytes_read_per_launch"] + t["dram_bytes_write_per_launch"]
+        traffic_src = t["source"]
     line = {
         "metric": "kmer_rules_scored_per_sec_per_scm_iteration", "value": value, "unit": "rules/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
@@ -427,7 +433,8 @@ def run_ours(args):
         "dtype": "u64 popcount + f64 utility", "data": "synthetic (hash-generated on device, seed %d)" % SEED,
         "config": workload_config(world),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "k_scan_tma<EPI_SCM>", "peak_source": peak_src,
+                     "traffic": traffic, "traffic_source": traffic_src, "kernel": "k_scan_tma<EPI_SCM>",
+                     "peak_source": peak_src,
                      "bytes_per_launch": float(np.mean(alg_bytes)), "kernel_ms": float(np.mean(kernel_ms)),
                      "kernel_share_of_step": float(np.sum(kernel_ms) / dev_ms)},
         "e2e": {"value": rules_per_step * args.steps / e2e_s, "unit": "rules/s",

@@ -706,9 +706,21 @@ struct RescoreParams {
     unsigned long long *blockmax, *segmax;
 };
 
+// max over a 16-lane half warp of an enc_f64 image (the two halves reduce independently)
+__device__ __forceinline__ unsigned long long half_warp_max_enc(unsigned long long e, unsigned half_mask) {
+    const uint32_t hi = (uint32_t)(e >> 32), lo = (uint32_t)e;
+    const uint32_t mh = __reduce_max_sync(half_mask, hi);
+    const uint32_t ml = __reduce_max_sync(half_mask, hi == mh ? lo : 0u);
+    return ((unsigned long long)mh << 32) | ml;
+}
+
 __global__ void __launch_bounds__(256) k_scm_rescore(const RescoreParams P) {
+    // 2 048 columns per CTA; a warp takes 128 columns per step: each 16-lane half owns one 64-column
+    // segment, each lane four adjacent columns (one 128-bit load per count array).
     __shared__ unsigned long long s_red[2][8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int half = lane >> 4, sub = lane & 15;
+    const unsigned half_mask = half ? 0xFFFF0000u : 0x0000FFFFu;
     const long long chunk_c0 = (long long)blockIdx.x * 2048;
     const long long chunk_n = min(2048ll, P.n_cols - chunk_c0);
     unsigned long long run[2] = {0ull, 0ull};          // enc_f64 images; 0 = nothing seen
@@ -720,50 +732,50 @@ __global__ void __launch_bounds__(256) k_scm_rescore(const RescoreParams P) {
         bid[h] = r0 / P.ubs;
         uniform[h] = chunk_n > 0 && (r0 + chunk_n - 1) / P.ubs == bid[h];
     }
-    for (int sg = warp; sg < 32; sg += 8) {
-        const long long seg_c0 = chunk_c0 + sg * 64;
-        double um[2] = {-INFINITY, -INFINITY};
-        double u[2][2];
-        bool valid[2];
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const long long col = seg_c0 + lane + 32 * j;
-            valid[j] = col < P.n_cols;
-            u[0][j] = u[1][j] = -INFINITY;
-            if (valid[j]) {
-                const uint32_t cp = P.cnt_pos[col], cn = P.cnt_neg[col];
-                bool bp = false, ba = false;
-                if (P.black_pres) {
-                    bp = (P.black_pres[col >> 5] >> (col & 31)) & 1u;
-                    ba = (P.black_abs[col >> 5] >> (col & 31)) & 1u;
-                }
-                if (!bp) u[0][j] = scm_utility(P.n_neg - cn, P.n_pos - cp, P.p);
-                if (!ba) u[1][j] = scm_utility(cn, cp, P.p);
-            }
+    for (int it = 0; it < 2; ++it) {
+        const long long seg_c0 = chunk_c0 + (long long)(it * 16 + warp * 2 + half) * 64;
+        if (seg_c0 >= P.ld) continue;                   // half-warp uniform
+        const long long col = seg_c0 + sub * 4;         // ld is a multiple of 1024: the vector loads stay in bounds
+        const uint4 cp = *reinterpret_cast<const uint4 *>(P.cnt_pos + col);
+        const uint4 cn = *reinterpret_cast<const uint4 *>(P.cnt_neg + col);
+        const uint32_t cpv[4] = {cp.x, cp.y, cp.z, cp.w}, cnv[4] = {cn.x, cn.y, cn.z, cn.w};
+        uint32_t bp = 0, ba = 0;
+        if (P.black_pres) {
+            bp = P.black_pres[col >> 5] >> (col & 31);
+            ba = P.black_abs[col >> 5] >> (col & 31);
+        }
+        double u[2][4];
+        double um[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const bool valid = col + j < P.n_cols;
+            u[0][j] = (!valid || ((bp >> j) & 1u)) ? -INFINITY : scm_utility(P.n_neg - cnv[j], P.n_pos - cpv[j], P.p);
+            u[1][j] = (!valid || ((ba >> j) & 1u)) ? -INFINITY : scm_utility(cnv[j], cpv[j], P.p);
             um[0] = fmax(um[0], u[0][j]);
             um[1] = fmax(um[1], u[1][j]);
         }
-        if (seg_c0 < P.ld) {
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const unsigned long long seg = warp_max_enc(enc_f64(um[h]));
-                if (lane == 0) P.segmax[(size_t)h * (P.ld >> 6) + (seg_c0 >> 6)] = seg;
-                if (uniform[h]) {
-                    run[h] = seg > run[h] ? seg : run[h];
-                } else {
+        for (int h = 0; h < 2; ++h) {
+            const unsigned long long seg = half_warp_max_enc(enc_f64(um[h]), half_mask);
+            if (sub == 0) P.segmax[(size_t)h * (P.ld >> 6) + (seg_c0 >> 6)] = seg;
+            if (uniform[h]) {
+                run[h] = seg > run[h] ? seg : run[h];
+            } else {
 #pragma unroll
-                    for (int j = 0; j < 2; ++j)
-                        if (valid[j]) {
-                            const long long r = (long long)h * P.k_total + P.col0 + seg_c0 + lane + 32 * j;
-                            atomicMax(P.blockmax + r / P.ubs, enc_f64(u[h][j]));
-                        }
-                }
+                for (int j = 0; j < 4; ++j)
+                    if (col + j < P.n_cols) {
+                        const long long r = (long long)h * P.k_total + P.col0 + col + j;
+                        atomicMax(P.blockmax + r / P.ubs, enc_f64(u[h][j]));
+                    }
             }
         }
     }
+    // lanes 0 and 16 hold their half's running maxima
+    const unsigned long long o0 = __shfl_xor_sync(0xffffffffu, run[0], 16), o1 = __shfl_xor_sync(0xffffffffu, run[1], 16);
     if (lane == 0) {
-        s_red[0][warp] = run[0];
-        s_red[1][warp] = run[1];
+        s_red[0][warp] = run[0] > o0 ? run[0] : o0;
+        s_red[1][warp] = run[1] > o1 ? run[1] : o1;
     }
     __syncthreads();
     if (threadIdx.x < 2 && uniform[threadIdx.x]) {

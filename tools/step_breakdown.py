@@ -33,3 +33,17 @@ ex={0:neg,1:pos}
 from oracle import kover_oracle as ko
 n_total, altered = ko.cart_altered_priors(ex,{0:1.0,1:1.0})
 print("rc.gini_best_split    %7.1f us  (count kernel %.1f us)" % (t(lambda: rc.gini_best_split(ex,altered,n_total), 50), sh.info().last_kernel_ms*1e3))
+rs = np.random.RandomState(0)
+for nm in (1, 3, 4, 8):
+    y3 = rs.randint(0, nm, size=n)
+    sets = [np.where(y3 == c)[0] for c in range(nm)]
+    masks = np.stack([rc.row_mask(r) for r in sets])
+    sh.sum_rows_multi(masks[:, :])  # warm
+    t0 = time.perf_counter(); sh._lib.kv_sum_rows_multi  # noqa
+    out_ = sh.sum_rows_multi(masks)
+    dt = time.perf_counter() - t0
+    print("k_count_multi<%d>  kernel %.1f us = %.0f GB/s   (call incl. D2H of %d x K u32: %.1f ms)" % (nm, sh.info().last_kernel_ms * 1e3, 2.56 / sh.info().last_kernel_ms * 1e3, nm, dt * 1e3))
+ex3 = {c: np.where(rs.randint(0, 3, size=n) == c)[0] for c in range(3)}
+nt3 = {c: float(len(v)) for c, v in ex3.items()}
+pr3 = {c: nt3[c] / n for c in ex3}
+print("rc.gini_best_split 3 classes %7.1f us" % t(lambda: rc.gini_best_split(ex3, pr3, nt3), 20))
