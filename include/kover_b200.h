@@ -160,6 +160,20 @@ int kv_scm_select_blocks(const double *block_max, int64_t n_blocks, double *best
 int kv_scm_ties(kv_shard *s, const double *block_max, const uint8_t *selected, int64_t n_blocks,
                 int64_t capacity, int64_t *rule_idx, int64_t *pos_err, int64_t *neg_cover,
                 int64_t *n_found);
+/* Job queue (single shard): kv_scm_queue_push enqueues scan (reuse = 0) or re-score (reuse = 1: same masks as
+ * the previous push, 2: roles swapped; masks may then be NULL) + block merge + tie collection for job `slot` of
+ * `n_slots` WITHOUT synchronising; kv_scm_queue_collect waits once and returns, per job, best_utility[j],
+ * n_found[j] and its first min(n_found[j], 256) ties at rule_idx / pos_err / neg_cover [j * 256 ...]
+ * (ascending).  n_found[j] > 256 = truncated: run that job alone with kv_scm_best_rules.  This is how the
+ * lock-step fits of a hyper-parameter grid keep the GPU busy between jobs (north-star item 4). */
+int kv_scm_queue_push(kv_shard *s, int64_t slot, int64_t n_slots, const uint64_t *pos_mask, const uint64_t *neg_mask,
+                      int64_t n_pos, int64_t n_neg, double p, int64_t util_block_size, int reuse);
+int kv_scm_queue_collect(kv_shard *s, int64_t n_slots, double *best_utility, int64_t *n_found, int64_t *rule_idx,
+                         int64_t *pos_err, int64_t *neg_cover);
+/* Both in one call: masks [n_jobs][2][W] (positive mask, negative mask per job), per-job n_pos / n_neg / p / reuse. */
+int kv_scm_queue_run(kv_shard *s, int64_t n_jobs, const uint64_t *masks, const int64_t *n_pos, const int64_t *n_neg,
+                     const double *p, const int32_t *reuse, int64_t util_block_size, double *best_utility,
+                     int64_t *n_found, int64_t *rule_idx, int64_t *pos_err, int64_t *neg_cover);
 /* Multi-rank, one exchange per scan: phase 1 plus a LOCAL superset of the ties, written as one packet
  *   double block_max[n_blocks] | uint64 count | double threshold | {int64 rule, uint32 pos_err,
  *   uint32 neg_cover} records[capacity]

@@ -53,6 +53,10 @@ SYMBOLS = {
     "kv_scm_scan": (ctypes.c_int, [_c_p, _c_p, _c_p, _c_i64, _c_i64, ctypes.c_double, _c_i64, _c_p, _c_i64]),
     "kv_scm_select_blocks": (ctypes.c_int, [_c_p, _c_i64, ctypes.POINTER(ctypes.c_double), _c_p]),
     "kv_scm_ties": (ctypes.c_int, [_c_p, _c_p, _c_p, _c_i64, _c_i64, _c_p, _c_p, _c_p, ctypes.POINTER(_c_i64)]),
+    "kv_scm_queue_push": (ctypes.c_int, [_c_p, _c_i64, _c_i64, _c_p, _c_p, _c_i64, _c_i64, ctypes.c_double, _c_i64,
+                                         ctypes.c_int]),
+    "kv_scm_queue_collect": (ctypes.c_int, [_c_p, _c_i64, _c_p, _c_p, _c_p, _c_p, _c_p]),
+    "kv_scm_queue_run": (ctypes.c_int, [_c_p, _c_i64, _c_p, _c_p, _c_p, _c_p, _c_p, _c_i64, _c_p, _c_p, _c_p, _c_p, _c_p]),
     "kv_scm_packet_bytes": (_c_i64, [_c_i64, _c_i64]),
     "kv_scm_scan_packet": (ctypes.c_int, [_c_p, _c_p, _c_p, _c_i64, _c_i64, ctypes.c_double, _c_i64, _c_i64, _c_i64,
                                           _c_p, ctypes.c_int]),
@@ -326,6 +330,35 @@ class Shard(object):
         if over.value:
             return None, bm, best.value, sel
         return (best.value, idx[:n.value], pe[:n.value], nc[:n.value]), bm, best.value, sel
+
+    QUEUE_SLOT_RECS = 256
+
+    def scm_queue(self, jobs, util_block_size):
+        """jobs: [(p, pos_mask, neg_mask, n_pos, n_neg, reuse)] with reuse 0 = scan, 1 = re-score the previous
+        scan's counts, 2 = same with positives and negatives exchanged.  Everything is enqueued back to back and
+        collected with one synchronisation; jobs whose tie set did not fit their slot are redone alone.
+        -> [(best, idx, pos_err, neg_cover)] in job order."""
+        n = len(jobs)
+        r = self.QUEUE_SLOT_RECS
+        masks = np.empty((n, 2, self.n_words), dtype=np.uint64)
+        for j, job in enumerate(jobs):
+            masks[j, 0], masks[j, 1] = job[1], job[2]
+        n_pos = np.array([job[3] for job in jobs], dtype=np.int64)
+        n_neg = np.array([job[4] for job in jobs], dtype=np.int64)
+        ps = np.array([job[0] for job in jobs], dtype=np.float64)
+        reuse = np.array([job[5] for job in jobs], dtype=np.int32)
+        best, found = np.empty(n, dtype=np.float64), np.empty(n, dtype=np.int64)
+        idx, pe, nc = (np.empty((n, r), dtype=np.int64) for _ in range(3))
+        check(self._lib.kv_scm_queue_run(self._h, n, ptr(masks), ptr(n_pos), ptr(n_neg), ptr(ps), ptr(reuse),
+                                         int(util_block_size), ptr(best), ptr(found), ptr(idx), ptr(pe), ptr(nc)))
+        out = []
+        for j, (p, pm, nm, n_pos, n_neg, reuse) in enumerate(jobs):
+            m = int(found[j])
+            if m > r:
+                out.append(self.scm_best_rules(pm, nm, n_pos, n_neg, p, util_block_size, capacity=m))
+            else:
+                out.append((float(best[j]), idx[j, :m].copy(), pe[j, :m].copy(), nc[j, :m].copy()))
+        return out
 
     def scm_best_rules(self, pos_mask, neg_mask, n_pos, n_neg, p, util_block_size, capacity=None):
         if pos_mask.dtype != np.uint64 or neg_mask.dtype != np.uint64:

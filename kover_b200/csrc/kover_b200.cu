@@ -1140,7 +1140,7 @@ struct kv_shard {
     int scan_variant = -1;                    // -1: choose per call; >= 0: forced (KOVER_B200_SCAN_VARIANT)
 
     std::vector<uint32_t *> d_cnt;            // count arrays, [ld] each
-    DevBuf d_rec, d_misc, d_ties, d_stage, d_sort_tmp, d_sort_io;
+    DevBuf d_rec, d_misc, d_ties, d_stage, d_sort_tmp, d_sort_io, d_queue;
     void *h_pin = nullptr;                    // pinned staging (records, block tables, small results)
     size_t h_pin_bytes = 0;
     void *h_up[2] = {nullptr, nullptr};       // pinned upload ring
@@ -1274,7 +1274,7 @@ extern "C" int kv_destroy(kv_shard *s) {
     p2p_destroy(s->p2p);
     cudaFree(s->d_mat);
     for (auto p : s->d_cnt) cudaFree(p);
-    for (DevBuf *b : {&s->d_rec, &s->d_misc, &s->d_ties, &s->d_stage, &s->d_sort_tmp, &s->d_sort_io})
+    for (DevBuf *b : {&s->d_rec, &s->d_misc, &s->d_ties, &s->d_stage, &s->d_sort_tmp, &s->d_sort_io, &s->d_queue})
         if (b->p) cudaFree(b->p);
     if (s->d_black_pres) cudaFree(s->d_black_pres);
     if (s->d_black_abs) cudaFree(s->d_black_abs);
@@ -2101,11 +2101,21 @@ extern "C" int kv_scm_select_blocks(const double *block_max, int64_t n_blocks, d
 // Launch k_scm_ties on the block tables already in d_misc, then bring header + records back with as
 // few round trips as possible and sort by rule index (the kernel appends in arbitrary order; the
 // reference's order is ascending rule index, scm.py:273-280).
+static void launch_exact_ties(kv_shard *s, int64_t n_blocks, TieHeader *d_hdr, TieRec *d_rec, long long cap);
+static int scm_read_ties(kv_shard *s, TieHeader *d_hdr, TieRec *d_rec, int64_t capacity, double *best_utility,
+                         int64_t *rule_idx, int64_t *pos_err, int64_t *neg_cover, int64_t *n_found);
+
 static int scm_collect_ties(kv_shard *s, int64_t n_blocks, int64_t capacity, double *best_utility, int64_t *rule_idx,
                             int64_t *pos_err, int64_t *neg_cover, int64_t *n_found) {
-    MiscLayout L = misc_layout(s->d_misc.p, n_blocks);
     TieHeader *d_hdr = (TieHeader *)s->d_ties.p;
     TieRec *d_rec = (TieRec *)(d_hdr + 1);
+    launch_exact_ties(s, n_blocks, d_hdr, d_rec, std::max<long long>(capacity, kTieFirstBatch));
+    return scm_read_ties(s, d_hdr, d_rec, capacity, best_utility, rule_idx, pos_err, neg_cover, n_found);
+}
+
+// k_scm_ties in exact mode on the block tables in d_misc, appending into (d_hdr, d_rec[cap])
+static void launch_exact_ties(kv_shard *s, int64_t n_blocks, TieHeader *d_hdr, TieRec *d_rec, long long cap) {
+    MiscLayout L = misc_layout(s->d_misc.p, n_blocks);
     TieParams T;
     memset(&T, 0, sizeof T);
     T.cnt0 = s->d_cnt[s->scm_swapped ? 1 : 0];
@@ -2128,11 +2138,16 @@ static int scm_collect_ties(kv_shard *s, int64_t n_blocks, int64_t capacity, dou
     T.count = &d_hdr->count;
     T.threshold = nullptr;
     T.out = d_rec;
-    T.cap = std::max<long long>(capacity, kTieFirstBatch);     // device buffer holds at least the first batch
+    T.cap = cap;
     const long long n_seg = (s->n_cols + 63) / 64;
     const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((n_seg + 255) / 256, (long long)s->sm_count * 4));
     k_scm_ties<<<grid, 256, 0, s->stream>>>(T);
     count_launch(s);
+}
+
+// header + records back to the host with as few round trips as possible, ascending rule index
+static int scm_read_ties(kv_shard *s, TieHeader *d_hdr, TieRec *d_rec, int64_t capacity, double *best_utility,
+                         int64_t *rule_idx, int64_t *pos_err, int64_t *neg_cover, int64_t *n_found) {
     const size_t first_bytes = sizeof(TieHeader) + (size_t)kTieFirstBatch * sizeof(TieRec);
     KV_TRY(ensure_pinned(s, first_bytes));
     CU(cudaMemcpyAsync(s->h_pin, d_hdr, first_bytes, cudaMemcpyDeviceToHost, s->stream));
@@ -2231,6 +2246,83 @@ extern "C" int kv_scm_best_rules(kv_shard *s, const uint64_t *pos_mask, const ui
         s->scan_ms_total += ms;
     }
     return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Job queue: several single-shard SCM scans enqueued back to back on the shard's stream and collected
+// with ONE synchronisation -- the lock-step fits of a hyper-parameter grid / cross-validation.  Each
+// job's result (header + up to kQueueSlotRecs ties) lands in its own device slot.
+// ------------------------------------------------------------------------------------------------
+static constexpr long long kQueueSlotRecs = 256;
+static constexpr size_t kQueueSlotBytes = sizeof(TieHeader) + kQueueSlotRecs * sizeof(TieRec);
+
+extern "C" int kv_scm_queue_push(kv_shard *s, int64_t slot, int64_t n_slots, const uint64_t *pos_mask,
+                                 const uint64_t *neg_mask, int64_t n_pos, int64_t n_neg, double p,
+                                 int64_t util_block_size, int reuse) {
+    if (!s) return fail(KV_E_INVALID, "kv_scm_queue_push: null shard");
+    if (s->col0 != 0 || s->n_cols != s->k_total) return fail(KV_E_INVALID, "kv_scm_queue_push: single-shard only");
+    if (slot < 0 || n_slots <= 0 || slot >= n_slots) return fail(KV_E_INVALID, "kv_scm_queue_push: bad slot");
+    if (reuse < 0 || reuse > 2) return fail(KV_E_INVALID, "kv_scm_queue_push: reuse must be 0, 1 or 2");
+    const int64_t n_blocks = kv_scm_n_blocks(s->k_total, util_block_size);
+    if (n_blocks <= 0) return fail(KV_E_INVALID, "kv_scm_queue_push: util_block_size must be positive");
+    DeviceGuard g(s->device);
+    if (slot == 0) s->last_launches = 0;
+    KV_TRY(ensure(s->d_queue, (size_t)n_slots * kQueueSlotBytes));
+    if (reuse) {
+        KV_TRY(kv_scm_reuse_counts(s, reuse == 2));
+    } else if (s->W > SCAN_INLINE_ROWS) {
+        // the row records of a large scan are staged through one pinned buffer: let the previous job's copy finish
+        CU(cudaStreamSynchronize(s->stream));
+    }
+    KV_TRY(scm_scan_async(s, pos_mask, neg_mask, n_pos, n_neg, p, util_block_size, n_blocks));
+    MiscLayout L = misc_layout(s->d_misc.p, n_blocks);
+    TieHeader *d_hdr = (TieHeader *)((char *)s->d_queue.p + (size_t)slot * kQueueSlotBytes);
+    k_scm_select<<<1, 32, 0, s->stream>>>(L.blockmax, n_blocks, L.bm, L.tol, L.sel, d_hdr);
+    count_launch(s);
+    launch_exact_ties(s, n_blocks, d_hdr, (TieRec *)(d_hdr + 1), kQueueSlotRecs);
+    CU(cudaGetLastError());
+    return KV_OK;
+}
+
+extern "C" int kv_scm_queue_collect(kv_shard *s, int64_t n_slots, double *best_utility, int64_t *n_found,
+                                    int64_t *rule_idx, int64_t *pos_err, int64_t *neg_cover) {
+    if (!s || !best_utility || !n_found || !rule_idx || !pos_err || !neg_cover)
+        return fail(KV_E_INVALID, "kv_scm_queue_collect: null pointer");
+    if (n_slots <= 0 || (size_t)n_slots * kQueueSlotBytes > s->d_queue.bytes)
+        return fail(KV_E_INVALID, "kv_scm_queue_collect: more slots than were pushed");
+    DeviceGuard g(s->device);
+    const size_t bytes = (size_t)n_slots * kQueueSlotBytes;
+    KV_TRY(ensure_pinned(s, bytes));
+    CU(cudaMemcpyAsync(s->h_pin, s->d_queue.p, bytes, cudaMemcpyDeviceToHost, s->stream));
+    CU(stream_sync_spin(s->stream));
+    CU(cudaGetLastError());
+    for (int64_t j = 0; j < n_slots; ++j) {
+        const TieHeader *h = (const TieHeader *)((const char *)s->h_pin + (size_t)j * kQueueSlotBytes);
+        TieRec *recs = (TieRec *)(h + 1);
+        best_utility[j] = h->best_utility;
+        n_found[j] = (int64_t)h->count;            // > kQueueSlotRecs: truncated, the caller redoes the job alone
+        const long long m = std::min<long long>((long long)h->count, kQueueSlotRecs);
+        std::sort(recs, recs + m, [](const TieRec &a, const TieRec &b) { return a.idx < b.idx; });
+        for (long long i = 0; i < m; ++i) {
+            rule_idx[j * kQueueSlotRecs + i] = recs[i].idx;
+            pos_err[j * kQueueSlotRecs + i] = recs[i].pe;
+            neg_cover[j * kQueueSlotRecs + i] = recs[i].nc;
+        }
+    }
+    return KV_OK;
+}
+
+extern "C" int kv_scm_queue_run(kv_shard *s, int64_t n_jobs, const uint64_t *masks, const int64_t *n_pos,
+                                const int64_t *n_neg, const double *p, const int32_t *reuse, int64_t util_block_size,
+                                double *best_utility, int64_t *n_found, int64_t *rule_idx, int64_t *pos_err,
+                                int64_t *neg_cover) {
+    if (!s || !masks || !n_pos || !n_neg || !p || !reuse) return fail(KV_E_INVALID, "kv_scm_queue_run: null pointer");
+    if (n_jobs <= 0) return fail(KV_E_INVALID, "kv_scm_queue_run: no jobs");
+    for (int64_t j = 0; j < n_jobs; ++j) {
+        const uint64_t *pm = masks + (size_t)j * 2 * s->W, *nm = pm + s->W;
+        KV_TRY(kv_scm_queue_push(s, j, n_jobs, pm, nm, n_pos[j], n_neg[j], p[j], util_block_size, reuse[j]));
+    }
+    return kv_scm_queue_collect(s, n_jobs, best_utility, n_found, rule_idx, pos_err, neg_cover);
 }
 
 extern "C" int64_t kv_scm_packet_bytes(int64_t n_blocks, int64_t capacity) {

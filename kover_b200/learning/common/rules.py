@@ -284,10 +284,16 @@ class KmerRuleClassifications(BaseRuleClassifications):
         whose example sets coincide (every p of a grid; conjunction and disjunction, whose labels are swapped)
         share ONE pass over the matrix.  Returns the results in job order."""
         self.set_rule_blacklist(rule_blacklist)
-        packed = []
+        packed, masks = [], {}
+
+        def mask_of(idx):                 # jobs of a grid share their index arrays: pack each array once
+            key = id(idx)
+            if key not in masks:
+                masks[key] = (idx, self.row_mask(idx))
+            return masks[key][1]
         for p, pos, neg in jobs:
             pos, neg = np.asarray(pos), np.asarray(neg)
-            packed.append((float(p), self.row_mask(pos), self.row_mask(neg), pos.shape[0], neg.shape[0]))
+            packed.append((float(p), mask_of(pos), mask_of(neg), pos.shape[0], neg.shape[0]))
         return self._group.scm_best_rules_grid(packed, int(util_block_size))
 
     def gini_best_split(self, example_idx, altered_priors, n_total_class_examples, rule_blacklist=()):

@@ -293,6 +293,17 @@ class ShardGroup(object):
             else:
                 groups[key] = [(i, False)]
         results = [None] * len(jobs)
+        if self._single and hasattr(self.shards[0], "scm_queue"):
+            # one device: enqueue every job back to back, synchronise once
+            order, queued = [], []
+            for members in groups.values():
+                for rank_in_group, (i, swap) in enumerate(members):
+                    p, pm, nm, n_pos, n_neg = jobs[i]
+                    order.append(i)
+                    queued.append((p, pm, nm, n_pos, n_neg, 0 if rank_in_group == 0 else (2 if swap else 1)))
+            for i, res in zip(order, self.shards[0].scm_queue(queued, util_block_size)):
+                results[i] = res
+            return results
         for members in groups.values():
             for rank_in_group, (i, swap) in enumerate(members):
                 p, pm, nm, n_pos, n_neg = jobs[i]

@@ -47,6 +47,18 @@ def main():
                 bu, bi, bp, bn = rc.best_utility_rules(p, pos, neg, rule_blacklist=blacklist, util_block_size=ubs)
                 assert bu == wu and np.array_equal(bi, np.asarray(wi, dtype=np.int64)), (p2p, p, ubs)
                 assert np.array_equal(bp, wp) and np.array_equal(bn, wn)
+        # a hyper-parameter grid over the same examples: one matrix pass per rank, the rest re-scored
+        jobs = [(pp, a, b) for pp in (0.5, 1.0, 10.0) for a, b in ((pos, neg), (neg, pos))]
+        shard = rc._group.shards[0]
+        before = shard.info()
+        got = rc.best_utility_rules_grid(jobs, rule_blacklist=blacklist, util_block_size=99991)
+        after = shard.info()
+        assert after.scan_calls - before.scan_calls == 1 and after.rescore_calls - before.rescore_calls == 5
+        for (pp, a, b), g_ in zip(jobs, got):
+            wu, wi, wp, wn = ko.merge_utility_blocks(len(b) - orc.sum_rows(b), len(a) - orc.sum_rows(a), pp, bl,
+                                                     block_size=99991)
+            assert g_[0] == wu and np.array_equal(g_[1], np.asarray(wi, dtype=np.int64)), (p2p, pp)
+            assert np.array_equal(g_[2], wp) and np.array_equal(g_[3], wn)
         # a full fit and a tree
         rules = LazyKmerRuleList(["K%d" % i for i in range(k)], np.arange(k))
         m = kscm.SetCoveringMachine(model_type="conjunction", p=1.0, max_rules=4)
