@@ -65,7 +65,9 @@ _SUBS = [
 def _patched_source(path):
     with open(path, "r") as f:
         src = f.read()
+    # Python 2 reads a tab as "up to the next multiple of 8"; models.py mixes tabs consistently with 4
     src = src.expandtabs(4) if path.endswith("models.py") else src
+    src = src.expandtabs(8) if path.endswith("metrics.py") else src
     for pat, rep in _SUBS:
         src = re.sub(pat, rep, src, flags=re.M)
     return src
@@ -148,6 +150,17 @@ def load_reference():
     ns.tree = _exec_module(_PKG + ".learning.common.tree", os.path.join(_CORE, "learning/common/tree.py"))
     ns.scm = _exec_module(_PKG + ".learning.learners.scm", os.path.join(_CORE, "learning/learners/scm.py"))
     ns.cart = _exec_module(_PKG + ".learning.learners.cart", os.path.join(_CORE, "learning/learners/cart.py"))
+    # experiment drivers: only their pure functions (_bound, _predictions, metrics) are usable without HDF5
+    _mk_pkg(_PKG + ".dataset")
+    _mk_pkg(_PKG + ".learning.experiments")
+    if _PKG + ".dataset.ds" not in sys.modules:
+        ds = types.ModuleType(_PKG + ".dataset.ds")
+        ds.KoverDataset = type("KoverDataset", (), {})        # stub: needs h5py, never instantiated here
+        sys.modules[_PKG + ".dataset.ds"] = ds
+    ns.metrics = _exec_module(_PKG + ".learning.experiments.metrics",
+                              os.path.join(_CORE, "learning/experiments/metrics.py"))
+    ns.experiment_scm = _exec_module(_PKG + ".learning.experiments.experiment_scm",
+                                     os.path.join(_CORE, "learning/experiments/experiment_scm.py"))
     return ns
 
 

@@ -204,6 +204,21 @@ CART_CASES = [
 ]
 
 
+EXPERIMENT_CASES = [
+    # name, matrix, labels, train subset seed, p values, max_rules, max_equiv_rules, n_folds
+    ("exp_M1", "M1", "M1_noisy", 41, [0.1, 1.0, 10.0], 4, 3, 3),
+    ("exp_MD", "MD", "MD_planted", 43, [0.5, 2.0], 3, 10000, 4),
+]
+
+
+def experiment_folds(train, n_folds, seed=51):
+    """(fold_train_idx, fold_test_idx) like dataset/split.py:196-207."""
+    rs = np.random.RandomState(seed)
+    fold_of = np.arange(len(train)) % n_folds
+    rs.shuffle(fold_of)
+    return [(train[fold_of != f], train[fold_of == f]) for f in range(n_folds)]
+
+
 RISK_CASES = [
     # name, matrix, labels, train subset seed
     ("risk_M1", "M1", "M1_noisy", 41),

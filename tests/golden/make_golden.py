@@ -179,6 +179,106 @@ def gen_cart():
     # scores through `candidates == where(score == min)` at every node, which tree_json already holds)
 
 
+# ------------------------------------------------------------------ bound / CV model selection (north-star item 4)
+def gen_experiments():
+    """experiment_scm.py's per-HP scoring (_bound_score_hp :401-566, _cv_score_hp :102-193) needs a KoverDataset
+    (HDF5); its bodies are replayed here on the REAL reference's fit / _bound / _predictions / metrics, with the
+    best-HP rules of _bound_selection (:612-627) and _cross_validation (:233-246)."""
+    from copy import deepcopy
+    from itertools import product
+    E = ref.experiment_scm
+    for name, mname, lname, seed, p_values, max_rules, max_equiv, n_folds in cases.EXPERIMENT_CASES:
+        X, P, n, chunks = cases.matrix(mname)
+        labels = cases.labels(lname)
+        k = P.shape[1]
+        train = cases.train_subset(n, seed)
+        rules = ref.rules.LazyKmerRuleList(["K%d" % i for i in range(k)], np.arange(k))
+        risks = cases.rule_risks(2 * k)
+        out = {}
+
+        def tiebreaker(idx, model_type):
+            tie = risks[idx]
+            return idx[np.isclose(tie, tie.min())] if model_type == "conjunction" else idx[np.isclose(tie, tie.max())]
+
+        # ---- bound selection
+        best_score, best_hp, best_model = 1.0, {"model_type": None, "p": None, "max_rules": None}, None
+        for model_type, p in product(["conjunction", "disjunction"], p_values):
+            rc = ref_rc(P, n, chunks)
+            rng = np.random.RandomState(7)                # every pool task unpickles its own copy
+            tmp_model = ref.models.ConjunctionModel() if model_type == "conjunction" else ref.models.DisjunctionModel()
+            score_by_length, model_by_length, equivalent_rules = np.ones(max_rules), [], []
+            train_answers = labels[train]
+
+            def cb(info):
+                tmp_model.add(info["selected_rule"])
+                model_by_length.append(deepcopy(tmp_model))
+                eq = info["equivalent_rules_idx"]
+                if len(eq) > max_equiv:
+                    ridx = rng.choice(len(eq), max_equiv, replace=False)
+                    ridx.sort()
+                    eq = eq[ridx]
+                if model_type == "disjunction":
+                    eq = (eq + k) % (2 * k)
+                equivalent_rules.append(eq)
+                _, tp = E._predictions(tmp_model, P, [], train)
+                score_by_length[info["iteration_number"] - 1] = E._bound(
+                    train_predictions=tp, train_answers=train_answers, train_example_idx=train, model=tmp_model,
+                    delta=0.05, max_genome_size=10000, rule_classifications=rc)
+
+            m = ref.scm.SetCoveringMachine(model_type=model_type, p=p, max_rules=max_rules)
+            m.fit(rules, rc, train[labels[train] == 1], train[labels[train] == 0], rule_blacklist=[],
+                  tiebreaker=lambda idx: tiebreaker(idx, model_type), iteration_callback=cb,
+                  iteration_rule_importances=True)
+            key = "%s_%g" % (model_type, p)
+            out["bound_" + key] = score_by_length.copy()
+            for t, eq in enumerate(equivalent_rules):
+                out["equiv_%s_%d" % (key, t)] = np.asarray(eq, dtype=np.int64)
+            bi = int(np.argmin(score_by_length))
+            score, hp = score_by_length[bi], (model_type, p, bi + 1)
+            if (score < best_score) or (score == best_score and hp[2] < best_hp["max_rules"]) or \
+                    (score == best_score and hp[2] == best_hp["max_rules"] and abs(1.0 - hp[1]) < abs(1.0 - best_hp["p"])):
+                best_hp = {"model_type": hp[0], "p": hp[1], "max_rules": hp[2]}
+                best_score, best_model = score, model_by_length[bi]
+        out["bound_best_score"] = np.float64(best_score)
+        out["bound_best_hp"] = np.array(json.dumps(best_hp))
+        out["bound_best_model"] = np.array(str(best_model))
+        _, test_pred = E._predictions(best_model, P, [], np.setdiff1d(np.arange(n), train))
+        out["bound_best_model_test_predictions"] = test_pred
+
+        # ---- cross-validation
+        folds = cases.experiment_folds(train, n_folds)
+        best_score, best_hp = 1.0, {"model_type": None, "p": None, "max_rules": None}
+        for model_type, p in product(["conjunction", "disjunction"], p_values):
+            fold_scores = np.ones((n_folds, max_rules + 1)) * np.inf
+            for i, (ftrain, ftest) in enumerate(folds):
+                rc = ref_rc(P, n, chunks)
+                tmp_model = ref.models.ConjunctionModel() if model_type == "conjunction" else ref.models.DisjunctionModel()
+                preds = [E._predictions(tmp_model, P, [], ftest)[1]]
+
+                def cb(info):
+                    tmp_model.add(info["selected_rule"])
+                    preds.append(E._predictions(tmp_model, P, [], ftest)[1])
+
+                m = ref.scm.SetCoveringMachine(model_type=model_type, p=p, max_rules=max_rules)
+                m.fit(rules, rc, ftrain[labels[ftrain] == 1], ftrain[labels[ftrain] == 0], rule_blacklist=[],
+                      tiebreaker=lambda idx: tiebreaker(idx, model_type), iteration_callback=cb)
+                by_length = np.array(E._duplicate_last_element(preds, max_rules + 1))
+                fold_scores[i] = E._get_binary_metrics(predictions=by_length, answers=labels[ftest])["risk"]
+            mean = np.mean(fold_scores, axis=0)
+            out["cv_%s_%g" % (model_type, p)] = mean
+            bi = int(np.argmin(mean))
+            score, hp = mean[bi], (model_type, p, bi)
+            if (not np.allclose(score, best_score) and score < best_score) or \
+                    (np.allclose(score, best_score) and hp[2] < best_hp["max_rules"]) or \
+                    (np.allclose(score, best_score) and hp[2] == best_hp["max_rules"]
+                     and not np.allclose(hp[1], best_hp["p"]) and abs(1.0 - hp[1]) < abs(1.0 - best_hp["p"])):
+                best_hp = {"model_type": hp[0], "p": hp[1], "max_rules": hp[2]}
+                best_score = score
+        out["cv_best_score"] = np.float64(best_score)
+        out["cv_best_hp"] = np.array(json.dumps(best_hp))
+        save(name, **out)
+
+
 # ------------------------------------------------------------------ dataset split risk tables (f-4)
 def gen_risk():
     """dataset/split.py:171-188 cannot be called as a function (it is inlined in _split, which needs an HDF5
@@ -206,6 +306,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "risk":
         gen_risk()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "experiments":
+        gen_experiments()
+        sys.exit(0)
     gen_popcount()
     gen_pack()
     gen_rules()
@@ -213,3 +316,4 @@ if __name__ == "__main__":
     gen_scm()
     gen_cart()
     gen_risk()
+    gen_experiments()

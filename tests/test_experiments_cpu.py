@@ -1,0 +1,22 @@
+"""CPU: the model-selection host logic (bound values, predictions, CV risks, best-HP rules, lock-step fit_many)
+of kover_b200.learning.experiments over checker-backed shards, against golden vectors replayed from the real
+reference's _bound / _predictions / metrics / fit."""
+import numpy as np
+import pytest
+
+import cases
+from experiment_checks import check_experiment_case
+from kover_b200.learning.common.rules import KmerRuleClassifications
+from kover_b200.sharding import ShardGroup, partition_columns
+from oracle_shard import OracleShard
+
+
+def make_rc(P, n, chunks):
+    k = P.shape[1]
+    shards = [OracleShard(P, n, c0, nc) for c0, nc in partition_columns(k, 2) if nc > 0]
+    return KmerRuleClassifications(P, n, shard_group=ShardGroup(shards, n, k))
+
+
+@pytest.mark.parametrize("case", cases.EXPERIMENT_CASES, ids=[c[0] for c in cases.EXPERIMENT_CASES])
+def test_bound_and_cv_selection(golden_dir, case):
+    check_experiment_case(golden_dir, case, make_rc)

@@ -449,6 +449,17 @@ def test_cross_entropy_fit_matches_checker_counts():
     assert sorted(r.kmer_index for r in t.decision_tree.rules) == [3, 9, 20]
 
 
+# ---------------------------------------------------------------------------------- bound / CV model selection
+@pytest.mark.parametrize("case", cases.EXPERIMENT_CASES, ids=[c[0] for c in cases.EXPERIMENT_CASES])
+@pytest.mark.parametrize("devices", [[0], [0, 0]], ids=["1shard", "2shards"])
+def test_bound_and_cv_selection_golden(golden_dir, case, devices):
+    """Bound values, predictions, CV risks and the selected hyper-parameters over the device matrix, all fits
+    in lock-step (single shard: through the job queue), against the reference's own functions."""
+    from experiment_checks import check_experiment_case
+    check_experiment_case(golden_dir, case, lambda P, n, chunks: KmerRuleClassifications(as_dataset(P, chunks), n,
+                                                                                        devices=devices))
+
+
 # ---------------------------------------------------------------------------------- dataset split risk tables
 @pytest.mark.parametrize("case", cases.RISK_CASES, ids=[c[0] for c in cases.RISK_CASES])
 @pytest.mark.parametrize("devices", [[0], [0, 0]], ids=["1shard", "2shards"])
