@@ -6,11 +6,12 @@ on the host (cart.py:260-339); per node, the n_classes ``sum_rows`` passes and t
 of ``_gini_rule_score`` + the Python-level ``min`` over all k-mers (cart.py:112-161, 238) become
 one call to ``rule_classifications.gini_best_split`` (k_scan2 / k_count_multi + k_gini).
 
-Cost-complexity pruning (cart.py:362-470) is host code outside the hot path and is not part of this
-package.
+``_prune_tree`` (minimal cost-complexity pruning, cart.py:362-470) is host code on a handful of nodes; it is
+restated at the end of this module because the bound-based model selection needs it.
 """
 import logging
 from collections import deque
+from copy import deepcopy
 
 import numpy as np
 
@@ -186,3 +187,63 @@ class DecisionTreeClassifier(object):
 
     def _is_fitted(self):
         return self.decision_tree is not None
+
+
+def _make_leaf(node):
+    node.rule = None
+    node.left_child = None
+    node.right_child = None
+
+
+def _prune_tree(tree):
+    """Minimal cost-complexity pruning (Breiman et al. 1984, ch. 3), cart.py:362-470.
+    -> (alphas, trees): the nested sequence T1 > T2 > ... > {root} with the alpha at which each appears."""
+    def leaf_parents(node):
+        if node.is_leaf:
+            return []
+        if node.left_child.is_leaf and node.right_child.is_leaf:
+            return [node]
+        return leaf_parents(node.left_child) + leaf_parents(node.right_child)
+
+    def initial_pruning(root):                    # Tmax -> T1: collapse splits that do not reduce R (cart.py:384-404)
+        parents = leaf_parents(root)
+        while len(parents) > 0:
+            node = parents.pop()
+            if np.allclose(node.breiman_info.R_t, node.left_child.breiman_info.R_t + node.right_child.breiman_info.R_t):
+                _make_leaf(node)
+                if not node.is_root and node.parent.left_child.is_leaf and node.parent.right_child.is_leaf:
+                    parents.append(node.parent)
+
+    def find_weakest_links(node):                 # cart.py:406-432
+        if node.is_leaf:
+            return np.inf, [node]
+        RTt = sum(l.breiman_info.R_t for l in node.leaves)
+        current_gt = float(node.breiman_info.R_t - RTt) / (len(node.leaves) - 1)
+        left_min_gt, left_links = find_weakest_links(node.left_child)
+        right_min_gt, right_links = find_weakest_links(node.right_child)
+        if np.allclose(current_gt, min(left_min_gt, right_min_gt)):
+            if np.allclose(left_min_gt, right_min_gt):
+                return current_gt, [node] + left_links + right_links
+            return current_gt, [node] + (left_links if left_min_gt < right_min_gt else right_links)
+        elif current_gt < min(left_min_gt, right_min_gt):
+            return current_gt, [node]
+        elif np.allclose(left_min_gt, right_min_gt):
+            return left_min_gt, left_links + right_links
+        elif left_min_gt > right_min_gt:
+            return right_min_gt, right_links
+        elif left_min_gt < right_min_gt:
+            return left_min_gt, left_links
+        raise Exception("Unhandled case detected!")
+
+    T1 = deepcopy(deepcopy(tree))
+    initial_pruning(T1)
+    sequence = [(0, T1)]
+    current = T1
+    while not current.is_leaf:                    # cart.py:441-463
+        current = deepcopy(current)
+        min_gt, weakest_links = find_weakest_links(current)
+        for n in weakest_links:
+            _make_leaf(n)
+        sequence.append((min_gt, current))
+    alphas, trees = zip(*sequence)
+    return alphas, trees

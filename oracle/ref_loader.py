@@ -19,7 +19,8 @@ Mechanical patch list (each is a syntax/stdlib rename, never a semantic change):
   np.bool/np.float/np.infty -> bool/float/np.inf; integer ``/`` used as floor
   division in build_row_mask (rules.py:218,222) and a debug format (scm.py:84)
   -> ``//``; ``d.keys()[0]`` -> ``list(d.keys())[0]`` (cart.py:141, tree.py:108);
-  ``scipy.misc.comb`` -> ``scipy.special.comb``; tabs expanded in models.py;
+  ``scipy.misc.comb`` -> ``scipy.special.comb``; ``np.vstack(<generator>)`` -> ``np.vstack([...])``
+  (experiment_cart.py:139); tabs expanded in models.py / metrics.py;
   ``import h5py`` satisfied by a stub (h5py is not installed in this image).
 """
 import importlib.machinery
@@ -58,6 +59,9 @@ _SUBS = [
     (r"self\.breiman_info\.p_j_given_t\.keys\(\)\[np\.argmax\(self\.breiman_info\.p_j_given_t\.values\(\)\)\]",
      "list(self.breiman_info.p_j_given_t.keys())[np.argmax(list(self.breiman_info.p_j_given_t.values()))]"),
     (r"from scipy\.misc import comb", "from scipy.special import comb"),
+    # numpy >= 1.16 refuses a generator as the argument of vstack (experiment_cart.py:139)
+    (r"np\.vstack\(\((_unpack_binary_bytes_from_ints\(kmer_matrix\[:, idx\]\) for idx in kmer_idx_by_rule)\)\)",
+     r"np.vstack([\1])"),
     (r"^import h5py as h$", "import types as _t; h = _t.SimpleNamespace(h5f=_t.SimpleNamespace(ACC_RDONLY=0, ACC_RDWR=1))  # h5py stub"),
 ]
 
@@ -161,6 +165,8 @@ def load_reference():
                               os.path.join(_CORE, "learning/experiments/metrics.py"))
     ns.experiment_scm = _exec_module(_PKG + ".learning.experiments.experiment_scm",
                                      os.path.join(_CORE, "learning/experiments/experiment_scm.py"))
+    ns.experiment_cart = _exec_module(_PKG + ".learning.experiments.experiment_cart",
+                                      os.path.join(_CORE, "learning/experiments/experiment_cart.py"))
     return ns
 
 

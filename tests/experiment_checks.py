@@ -40,3 +40,23 @@ def check_experiment_case(golden_dir, case, make_rc):
         assert np.array_equal(mean, g["cv_%s_%g" % (mt, p)]), (mt, p)
     assert score == float(g["cv_best_score"])
     assert hp == json.loads(str(g["cv_best_hp"]))
+
+
+def check_cart_experiment_case(golden_dir, case, make_rc):
+    from kover_b200.learning.experiments import experiment_cart as C
+    name, mname, lname, seed, max_depth, mss, imp = case
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    X, P, n, chunks = cases.matrix(mname)
+    labels = cases.labels(lname)
+    k = P.shape[1]
+    train = cases.train_subset(n, seed)
+    test = np.setdiff1d(np.arange(n), train)
+    rules = LazyKmerRuleList(["K%d" % i for i in range(k)], np.arange(k))
+    rc = make_rc(P, n, chunks)
+    hps = {"criterion": "gini", "max_depth": max_depth, "min_samples_split": mss, "class_importance": imp}
+    hps, min_score, tree, sequence = C.learn_pruned_tree_bound(rc, rules, labels, train, 2, hps, 0.05, 10000, [])
+    assert np.array_equal(np.array([a for a, _ in sequence], dtype=np.float64), g["alphas"])      # pruning alphas, ==
+    assert np.array_equal(np.array([b for _, b in sequence]), g["bounds"])                         # bound values, ==
+    assert min_score == float(g["min_score"]) and hps["pruning_alpha"] == float(g["best_alpha"])
+    assert sorted(int(r.kmer_index) for r in tree.rules) == g["best_rules"].tolist()
+    assert np.array_equal(np.asarray(C._predictions(tree, rc, [], test)[1]), g["best_test_predictions"])

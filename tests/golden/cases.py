@@ -219,6 +219,14 @@ def experiment_folds(train, n_folds, seed=51):
     return [(train[fold_of != f], train[fold_of == f]) for f in range(n_folds)]
 
 
+CART_EXPERIMENT_CASES = [
+    # name, matrix, labels, train subset seed, max_depth, min_samples_split, class_importance
+    ("cartexp_M2", "M2", "M2_planted", 41, 10, 2, {0: 1.0, 1: 1.0}),
+    ("cartexp_M1_noisy", "M1", "M1_noisy", 42, 6, 2, {0: 1.0, 1: 2.0}),
+    ("cartexp_MD", "MD", "MD_planted", 43, 5, 4, {0: 1.0, 1: 1.0}),
+]
+
+
 RISK_CASES = [
     # name, matrix, labels, train subset seed
     ("risk_M1", "M1", "M1_noisy", 41),

@@ -279,6 +279,39 @@ def gen_experiments():
         save(name, **out)
 
 
+def gen_cart_experiments():
+    """_learn_pruned_tree_bound (experiment_cart.py:208-294) replayed on the REAL reference's fit / _prune_tree /
+    _predictions / _bound (it needs a KoverDataset, i.e. HDF5, as a whole)."""
+    from functools import partial
+    E = ref.experiment_cart
+    for name, mname, lname, seed, max_depth, mss, imp in cases.CART_EXPERIMENT_CASES:
+        X, P, n, chunks = cases.matrix(mname)
+        labels = cases.labels(lname)
+        k = P.shape[1]
+        train = cases.train_subset(n, seed)
+        test = np.setdiff1d(np.arange(n), train)
+        rules = ref.rules.LazyKmerRuleList(["K%d" % i for i in range(k)], np.arange(k))
+        rc = ref_rc(P, n, chunks)
+        t = ref.cart.DecisionTreeClassifier("gini", max_depth, mss, imp)
+        t.fit(rules=rules, rule_classifications=rc, example_idx={c: train[labels[train] == c] for c in range(2)},
+              rule_blacklist=[], tiebreaker=partial(E._tiebreaker, rule_kmer_occurrences=rc.sum_rows(train)),
+              level_callback=None, split_callback=E._split_callback)
+        alphas, trees = E._prune_tree(t.decision_tree)
+        bounds, min_score, best, best_alpha = [], np.inf, None, None
+        for alpha, tree in zip(alphas, trees):
+            tp = E._predictions(tree, P, train, [])[0]
+            b = E._bound(train_predictions=tp, train_answers=labels[train], train_example_idx=train, model=tree,
+                         delta=0.05, max_genome_size=10000, rule_classifications=ref_rc(P, n, chunks), n_classes=2)
+            bounds.append(b)
+            if b <= min_score:
+                min_score, best, best_alpha = b, tree, alpha
+        save(name, alphas=np.array(alphas, dtype=np.float64), tree_sizes=np.array([len(x) for x in trees]),
+             bounds=np.array(bounds), best_alpha=np.float64(best_alpha), min_score=np.float64(min_score),
+             best_rules=np.array(sorted(int(r.kmer_index) for r in best.rules), dtype=np.int64),
+             best_test_predictions=np.asarray(E._predictions(best, P, [], test)[1]),
+             master_size=np.array(len(t.decision_tree)))
+
+
 # ------------------------------------------------------------------ dataset split risk tables (f-4)
 def gen_risk():
     """dataset/split.py:171-188 cannot be called as a function (it is inlined in _split, which needs an HDF5
@@ -309,6 +342,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "experiments":
         gen_experiments()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "cart_experiments":
+        gen_cart_experiments()
+        sys.exit(0)
     gen_popcount()
     gen_pack()
     gen_rules()
@@ -317,3 +353,4 @@ if __name__ == "__main__":
     gen_cart()
     gen_risk()
     gen_experiments()
+    gen_cart_experiments()

@@ -460,6 +460,15 @@ def test_bound_and_cv_selection_golden(golden_dir, case, devices):
                                                                                         devices=devices))
 
 
+@pytest.mark.parametrize("case", cases.CART_EXPERIMENT_CASES, ids=[c[0] for c in cases.CART_EXPERIMENT_CASES])
+def test_pruned_tree_bound_selection_golden(golden_dir, case):
+    """Master tree grown on the device, cost-complexity pruning sequence, bound of every pruned tree, selected
+    tree and its predictions, against the reference's own _prune_tree / _bound / _predictions."""
+    from experiment_checks import check_cart_experiment_case
+    check_cart_experiment_case(golden_dir, case, lambda P, n, chunks: KmerRuleClassifications(as_dataset(P, chunks), n,
+                                                                                             devices=[0, 0]))
+
+
 # ---------------------------------------------------------------------------------- dataset split risk tables
 @pytest.mark.parametrize("case", cases.RISK_CASES, ids=[c[0] for c in cases.RISK_CASES])
 @pytest.mark.parametrize("devices", [[0], [0, 0]], ids=["1shard", "2shards"])
