@@ -20,52 +20,47 @@ from ...utils import _minimum_uint_size, _unpack_binary_bytes_from_ints, build_r
 
 
 class KmerRule(object):
+    """Presence ("presence") or absence ("absence") of one k-mer, as a boolean rule on unpacked genomes
+    (interface of rules.py:27-54)."""
+
     def __init__(self, kmer_index, kmer_sequence, type):
-        """A k-mer presence ("presence") or absence ("absence") rule (rules.py:27-54)."""
-        self.kmer_index = kmer_index
-        self.kmer_sequence = kmer_sequence
-        self.type = type
+        self.kmer_index, self.kmer_sequence, self.type = kmer_index, kmer_sequence, type
 
     def classify(self, X):
-        if self.type == "absence":
-            return (X[:, self.kmer_index] == 0).astype(np.uint8)
-        else:
-            return (X[:, self.kmer_index] == 1).astype(np.uint8)
+        wanted = 0 if self.type == "absence" else 1
+        return (X[:, self.kmer_index] == wanted).astype(np.uint8)
 
     def inverse(self):
-        return KmerRule(kmer_index=self.kmer_index, kmer_sequence=self.kmer_sequence,
-                        type="absence" if self.type == "presence" else "presence")
+        flipped = "presence" if self.type == "absence" else "absence"
+        return KmerRule(kmer_index=self.kmer_index, kmer_sequence=self.kmer_sequence, type=flipped)
 
     def __str__(self):
-        return ("Absence(" if self.type == "absence" else "Presence(") + str(self.kmer_sequence) + ")"
+        return "%s(%s)" % ("Absence" if self.type == "absence" else "Presence", self.kmer_sequence)
 
 
 class LazyKmerRuleList(object):
-    """First half: presence rules; second half: absence rules in the same order (rules.py:57-79)."""
+    """The 2K rules of a dataset, materialised on demand: rule i < K is the presence of the k-mer of matrix
+    column i, rule K + i its absence (interface and index convention of rules.py:57-79)."""
 
     def __init__(self, kmer_sequences, kmer_by_rule):
-        self.n_rules = kmer_by_rule.shape[0] * 2
         self.kmer_sequences = kmer_sequences
         self.kmer_by_rule = kmer_by_rule
-
-    def __getitem__(self, idx):
-        if idx >= self.n_rules:
-            raise ValueError("Index %d is out of range for list of size %d" % (idx, self.n_rules))
-        if idx >= len(self.kmer_sequences):
-            type = "absence"
-            kmer_idx = self.kmer_by_rule[idx % len(self.kmer_sequences)]
-        else:
-            type = "presence"
-            kmer_idx = self.kmer_by_rule[idx]
-        return KmerRule(idx % len(self.kmer_sequences), self.kmer_sequences[kmer_idx], type)
+        self.n_rules = 2 * kmer_by_rule.shape[0]
 
     def __len__(self):
         return self.n_rules
 
+    def __getitem__(self, idx):
+        if idx >= self.n_rules:
+            raise ValueError("Index %d is out of range for list of size %d" % (idx, self.n_rules))
+        n_kmers = len(self.kmer_sequences)
+        column = idx % n_kmers
+        kind = "absence" if idx >= n_kmers else "presence"
+        return KmerRule(column, self.kmer_sequences[self.kmer_by_rule[column]], kind)
+
 
 class BaseRuleClassifications(object):
-    def __init__(self):
-        pass
+    """The operator interface the learners consume (rules.py:81-96)."""
 
     def get_columns(self, columns):
         raise NotImplementedError()
@@ -103,40 +98,32 @@ class KmerRuleClassifications(BaseRuleClassifications):
 
     def __init__(self, dataset, n_rows, block_size=None, devices=None, comm=None, shard_group=None):
         self.dataset = dataset
-        self.dataset_initial_n_rows = n_rows
-        self.dataset_n_rows = n_rows
+        self.dataset_initial_n_rows = self.dataset_n_rows = n_rows
         self.dataset_removed_rows = []
-        self.dataset_removed_rows_mask = np.zeros(self.dataset_initial_n_rows, dtype=bool)
-        self.block_size = (None, None)
+        self.dataset_removed_rows_mask = np.zeros(n_rows, dtype=bool)
 
-        if block_size is None:
-            chunks = getattr(self.dataset, "chunks", None)
-            if chunks is None:
-                self.block_size = (1, self.dataset.shape[1])
-            else:
-                self.block_size = chunks
-        else:
-            if len(block_size) != 2 or not isinstance(block_size[0], int) or not isinstance(block_size[1], int):
+        # block_size: accepted and validated like the reference (rules.py:112-120); it only sizes upload slabs here
+        if block_size is not None:
+            if len(block_size) != 2 or not all(isinstance(b, int) for b in block_size):
                 raise ValueError("The block size must be a tuple of 2 integers.")
             self.block_size = block_size
-
-        # Get the size of the ints used to store the data
-        if self.dataset.dtype == np.uint32:
-            self.dataset_pack_size = 32
-        elif self.dataset.dtype == np.uint64:
-            self.dataset_pack_size = 64
         else:
+            chunks = getattr(dataset, "chunks", None)
+            self.block_size = chunks if chunks is not None else (1, dataset.shape[1])
+
+        pack_size = {np.dtype(np.uint32): 32, np.dtype(np.uint64): 64}.get(np.dtype(dataset.dtype))
+        if pack_size is None:
             raise ValueError("Unsupported data type for packed attribute classifications array. The supported data" +
                              " types are np.uint32 and np.uint64.")
+        self.dataset_pack_size = pack_size
 
-        self._n_kmers = int(self.dataset.shape[1])
+        self._n_kmers = int(dataset.shape[1])
         self._blacklist_key = None
         if shard_group is not None:
             self._group = shard_group
         else:
             self._group = self._build_group(devices, comm)
             self._upload()
-        super(BaseRuleClassifications, self).__init__()
 
     # ------------------------------------------------------------------ device image
     def _build_group(self, devices, comm):
@@ -172,51 +159,37 @@ class KmerRuleClassifications(BaseRuleClassifications):
 
     # ------------------------------------------------------------------ reference interface
     def get_columns(self, columns):
-        """
-        Columns can be an integer (or any object that implements __index__) or a sorted list/ndarray.
-        """
-        columns_is_int = False
-        if hasattr(columns, "__index__"):  # All int types implement the __index__ method (PEP 357)
-            columns = [columns.__index__()]
-            columns_is_int = True
-            c = columns[0]
-            if 0 <= c < 2 * self._n_kmers and not self.dataset_removed_rows:
-                # the learners' per-iteration call (scm.py:133, cart.py:245): one rule, nothing removed
-                packed = self._group.get_packed_columns(np.array([c % self._n_kmers], dtype=np.int64))[0]
-                bits = np.unpackbits(packed.astype(">u8").view(np.uint8))[:self.dataset_initial_n_rows]
-                return (1 - bits) if c >= self._n_kmers else bits
-        elif isinstance(columns, np.ndarray):
-            columns = columns.tolist()
-        elif isinstance(columns, list):
-            pass
-        else:
-            columns = list(columns)
-
+        """0/1 classifications of the given rules on every (non-removed) genome: uint8 [n_genomes] for an integer
+        (anything with ``__index__``), [n_genomes, len(columns)] for a list / tuple / array; rule indices >= K are
+        absence rules, i.e. the inverted column (rules.py:135-171)."""
         n_kmers = self._n_kmers
-        # Detect where an inversion is needed (columns corresponding to absence rules)
-        invert_result = np.array([c >= n_kmers for c in columns], dtype=bool)
-        columns = [(c if c < n_kmers else c % n_kmers) for c in columns]
-
-        # Don't return rows that have been deleted
-        row_mask = np.ones(self.dataset.shape[0] * self.dataset_pack_size, dtype=bool)
-        row_mask[self.dataset_initial_n_rows:] = False
-        row_mask[self.dataset_removed_rows] = False
-
-        unique, inverse = np.unique(columns, return_inverse=True)
-        if unique.size and (unique[0] < -n_kmers or unique[-1] >= n_kmers):
-            raise IndexError("column index out of range")
-        unique = np.where(unique < 0, unique + n_kmers, unique)
-        packed = self._group.get_packed_columns(unique)                       # [n_unique, W64]
-        result = _unpack_binary_bytes_from_ints(np.ascontiguousarray(packed.T))   # [W64 * 64, n_unique]
-        n_unpacked = min(row_mask.shape[0], result.shape[0])   # rows past n_rows are masked out anyway
-        result = result[:n_unpacked][row_mask[:n_unpacked]]
-        result = result[:, inverse]
-        result[:, invert_result] = 1 - result[:, invert_result]
-
-        if columns_is_int:
-            return result.reshape(-1)
+        if hasattr(columns, "__index__"):
+            c = columns.__index__()
+            if 0 <= c < 2 * n_kmers and not self.dataset_removed_rows:
+                # the learners' per-iteration call (scm.py:133, cart.py:245): one rule, nothing removed
+                packed = self._group.get_packed_columns(np.array([c % n_kmers], dtype=np.int64))[0]
+                bits = np.unpackbits(packed.astype(">u8").view(np.uint8))[:self.dataset_initial_n_rows]
+                return (1 - bits) if c >= n_kmers else bits
+            single, wanted = True, [c]
         else:
-            return result
+            single = False
+            wanted = columns.tolist() if isinstance(columns, np.ndarray) else list(columns)
+
+        is_absence = np.array([c >= n_kmers for c in wanted], dtype=bool)
+        kmer_cols = np.array([c if c < n_kmers else c % n_kmers for c in wanted], dtype=np.int64).reshape(-1)
+        if kmer_cols.size and (kmer_cols.min() < -n_kmers or kmer_cols.max() >= n_kmers):
+            raise IndexError("column index out of range")
+        kmer_cols = np.where(kmer_cols < 0, kmer_cols + n_kmers, kmer_cols)
+        distinct, position = np.unique(kmer_cols, return_inverse=True)
+
+        packed = self._group.get_packed_columns(distinct)                            # [n_distinct, W64]
+        unpacked = _unpack_binary_bytes_from_ints(np.ascontiguousarray(packed.T))    # [W64 * 64, n_distinct]
+        alive = np.zeros(unpacked.shape[0], dtype=bool)
+        alive[:self.dataset_initial_n_rows] = True                                   # drop the padding rows ...
+        alive[self.dataset_removed_rows] = False                                     # ... and the removed genomes
+        result = unpacked[alive][:, position]
+        result[:, is_absence] = 1 - result[:, is_absence]
+        return result.reshape(-1) if single else result
 
     def _dataset_relative_rows(self, rows):
         """The (r+1)-th row that has not been removed, for each r (rules.py:177-184, 227-236)."""
@@ -229,11 +202,13 @@ class KmerRuleClassifications(BaseRuleClassifications):
         return alive[rows]
 
     def remove_rows(self, rows):
-        dataset_removed_rows = self._dataset_relative_rows(rows).tolist()
-        if len(dataset_removed_rows) > 0:
-            self.dataset_removed_rows = sorted(set(self.dataset_removed_rows + dataset_removed_rows))
-            self.dataset_removed_rows_mask = np.zeros(self.dataset_initial_n_rows, dtype=bool)
-            self.dataset_removed_rows_mask[self.dataset_removed_rows] = True
+        """Hide genomes from every later call; ``rows`` index the genomes still visible (rules.py:173-194)."""
+        newly_removed = self._dataset_relative_rows(rows).tolist()
+        if newly_removed:
+            self.dataset_removed_rows = sorted(set(self.dataset_removed_rows).union(newly_removed))
+            hidden = np.zeros(self.dataset_initial_n_rows, dtype=bool)
+            hidden[self.dataset_removed_rows] = True
+            self.dataset_removed_rows_mask = hidden
             self.dataset_n_rows = self.dataset_initial_n_rows - len(self.dataset_removed_rows)
 
     @property

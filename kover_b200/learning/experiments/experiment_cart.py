@@ -16,47 +16,54 @@ from ..learners.cart import DecisionTreeClassifier, _prune_tree
 
 
 def _tiebreaker(best_score_idx, rule_kmer_occurrences):
-    """Prefer the k-mers with the most occurrences in the training set (:82-94)."""
-    tie_rule_kmer_occurrences = rule_kmer_occurrences[best_score_idx]
-    return best_score_idx[np.isclose(tie_rule_kmer_occurrences, tie_rule_kmer_occurrences.max())]
+    """Among equally good splits keep the k-mers that occur in the most training genomes (:82-94): they are less
+    likely to isolate a phylogenetic clade and give smaller compression sets."""
+    occurrences = rule_kmer_occurrences[best_score_idx]
+    return best_score_idx[np.isclose(occurrences, occurrences.max())]
 
 
 def _split_callback(node, equivalent_rules_idx):
+    """Remember the equivalent rules of a split on its rule object (:97-106)."""
     node.rule.equivalent_rules_idx = equivalent_rules_idx
 
 
 def _readdress_tree(tree, rule_new_idx_by_kmer_seq):
-    def _readdress(node, kmer_idx):
-        if node.rule is not None:
-            node.rule.kmer_index = kmer_idx[node.rule.kmer_sequence]
-            _readdress(node.left_child, kmer_idx)
-            _readdress(node.right_child, kmer_idx)
-    new_tree = deepcopy(tree)
-    _readdress(new_tree, rule_new_idx_by_kmer_seq)
-    return new_tree
+    """Copy of the tree whose rules point at columns of a compact matrix (k-mer sequence -> new column)."""
+    clone = deepcopy(tree)
+    for rule in clone.rules:
+        rule.kmer_index = rule_new_idx_by_kmer_seq[rule.kmer_sequence]
+    return clone
 
 
 def _predictions(decision_tree, rule_classifications, train_example_idx, test_example_idx, progress_callback=None):
-    """experiment_cart.py:120-152; the model's k-mer columns come from the HBM-resident matrix."""
-    if progress_callback is None:
-        progress_callback = lambda t, p: None
-    progress_callback("Testing", 0.0)
-    if len(decision_tree.rules) > 0:
-        model_rules = decision_tree.rules
-        kmer_idx_by_rule = np.array([r.kmer_index for r in model_rules])
-        kmer_sequence_by_rule = np.array([r.kmer_sequence for r in model_rules])
-        sort_by_idx = np.argsort(kmer_idx_by_rule)
-        kmer_idx_by_rule = kmer_idx_by_rule[sort_by_idx]
-        kmer_sequence_by_rule = kmer_sequence_by_rule[sort_by_idx]
-        readdressed = _readdress_tree(decision_tree, dict((s, i) for i, s in enumerate(kmer_sequence_by_rule)))
-        X = rule_classifications.get_columns([int(c) for c in kmer_idx_by_rule])
-        train_predictions = readdressed.predict(X[train_example_idx])
-        test_predictions = readdressed.predict(X[test_example_idx])
-    else:                                      # the model is just a leaf
+    """Class predictions of a tree for two sets of genomes (:120-152).  Only the k-mers the tree uses are fetched
+    -- from the HBM-resident matrix here, from the HDF5 file in the reference -- and the tree is re-addressed to
+    that compact matrix."""
+    report = progress_callback or (lambda task, fraction: None)
+    report("Testing", 0.0)
+    used = decision_tree.rules
+    if len(used) == 0:                         # a single leaf: the input only fixes the number of predictions
         train_predictions = decision_tree.predict(np.empty((len(train_example_idx), 1)))
         test_predictions = decision_tree.predict(np.empty((len(test_example_idx), 1)))
-    progress_callback("Testing", 1.0)
+    else:
+        order = np.argsort(np.array([r.kmer_index for r in used]))
+        columns = [int(used[i].kmer_index) for i in order]
+        compact_tree = _readdress_tree(decision_tree, dict((used[i].kmer_sequence, j) for j, i in enumerate(order)))
+        X = rule_classifications.get_columns(columns)
+        train_predictions = compact_tree.predict(X[train_example_idx])
+        test_predictions = compact_tree.predict(X[test_example_idx])
+    report("Testing", 1.0)
     return train_predictions, test_predictions
+
+
+def _greedy_compression_set(presence_by_example):
+    """Chvatal's greedy set cover: genomes (rows) chosen until every k-mer (column) is present in one of them."""
+    chosen = []
+    while presence_by_example.shape[1] != 0:
+        best = np.argmax(presence_by_example.sum(axis=1))
+        chosen.append(best)
+        presence_by_example = presence_by_example[:, presence_by_example[best] == 0]
+    return chosen
 
 
 def _bound(train_predictions, train_answers, train_example_idx, model, delta, max_genome_size, rule_classifications,
@@ -64,25 +71,22 @@ def _bound(train_predictions, train_answers, train_example_idx, model, delta, ma
     """Sample-compression bound of a decision tree (Drouin et al. 2017), experiment_cart.py:155-205."""
     compression_set = []
     if len(model.rules) > 0:
-        presence_by_example = rule_classifications.get_columns([r.kmer_index for r in model.rules])[train_example_idx]
-        while presence_by_example.shape[1] != 0:
-            score = presence_by_example.sum(axis=1)
-            best_example_relative_idx = np.argmax(score)
-            compression_set.append(best_example_relative_idx)
-            presence_by_example = presence_by_example[:, presence_by_example[best_example_relative_idx] == 0]
+        kmers = [r.kmer_index for r in model.rules]
+        compression_set = _greedy_compression_set(rule_classifications.get_columns(kmers)[train_example_idx])
     m = float(len(train_answers))
     Z_card = float(len(compression_set))
-    N_Z = Z_card * max_genome_size
-    r = float((train_predictions != train_answers).sum()
-              - (train_predictions[compression_set] != train_answers[compression_set]).sum())
+    N_Z = Z_card * max_genome_size                     # nucleotides in the compression set
+    wrong = train_predictions != train_answers
+    r = float(wrong.sum() - wrong[compression_set].sum())       # errors outside the compression set
     n = float(len(model.rules))
-    return 1.0 - exp((-1.0 / (m - Z_card - r)) * (ln(comb(m, Z_card, exact=True)) +
-                                                  ln(comb(m - Z_card, r, exact=True)) +
-                                                  (n * ln(N_Z) if n > 0 else 0.) +
-                                                  (n + 1) * ln(n_classes) +
-                                                  ln(comb(2 * n + 1, n, exact=True)) +
-                                                  ln(pi ** 6 * (n + 1) ** 2 * (r + 1) ** 2 * (Z_card + 1) ** 2 /
-                                                     (216 * delta))))
+    # the terms are added in the reference's order (floating point)
+    exponent = (ln(comb(m, Z_card, exact=True)) +
+                ln(comb(m - Z_card, r, exact=True)) +
+                (n * ln(N_Z) if n > 0 else 0.) +
+                (n + 1) * ln(n_classes) +
+                ln(comb(2 * n + 1, n, exact=True)) +
+                ln(pi ** 6 * (n + 1) ** 2 * (r + 1) ** 2 * (Z_card + 1) ** 2 / (216 * delta)))
+    return 1.0 - exp((-1.0 / (m - Z_card - r)) * exponent)
 
 
 def learn_pruned_tree_bound(rule_classifications, rules, example_labels, train_genome_idx, n_classes, hps, delta,

@@ -25,56 +25,64 @@ from .metrics import _get_binary_metrics
 
 
 def _duplicate_last_element(l, length):
-    """utils.py:49-54"""
-    l += [l[-1]] * (length - len(l))
+    """Pad a list in place with copies of its last element (utils.py:49-54)."""
+    l.extend([l[-1]] * (length - len(l)))
     return l
 
 
 def _predictions(model, rule_classifications, train_example_idx, test_example_idx, progress_callback=None):
-    """experiment_scm.py:43-100.  The reference gathers the model's k-mer columns from the HDF5 matrix and unpacks
-    them; here the same columns come from the HBM-resident matrix (``get_columns`` on presence-rule indices)."""
-    if progress_callback is None:
-        progress_callback = lambda t, p: None
-    progress_callback("Testing", 0.0)
-    if len(model) == 0:
+    """Predictions of an SCM model for two sets of genomes (experiment_scm.py:43-100).  Only the k-mers the model
+    uses are fetched -- from the HBM-resident matrix here (``get_columns`` on presence-rule indices), from the
+    HDF5 file in the reference -- and a copy of the model is re-addressed to that compact matrix."""
+    report = progress_callback or (lambda task, fraction: None)
+    report("Testing", 0.0)
+    if len(model) == 0:                        # empty model: the input only fixes the number of predictions
         train_predictions = model.predict(np.zeros(len(train_example_idx)))
         test_predictions = model.predict(np.zeros(len(test_example_idx)))
     else:
-        columns_to_load = []
-        readdressed_model = deepcopy(model)
-        for i, rule_idx in enumerate(np.argsort([r.kmer_index for r in model.rules])):
-            rule = readdressed_model.rules[rule_idx]
-            columns_to_load.append(int(rule.kmer_index))
-            rule.kmer_index = i
-        X = rule_classifications.get_columns(columns_to_load)
-        train_predictions = readdressed_model.predict(X[train_example_idx])
-        progress_callback("Testing", 1.0 * len(train_example_idx) / (len(train_example_idx) + len(test_example_idx)))
-        test_predictions = readdressed_model.predict(X[test_example_idx])
-    progress_callback("Testing", 1.0)
+        compact_model = deepcopy(model)
+        order = np.argsort([r.kmer_index for r in model.rules])
+        columns = []
+        for new_column, rule_pos in enumerate(order):
+            columns.append(int(compact_model.rules[rule_pos].kmer_index))
+            compact_model.rules[rule_pos].kmer_index = new_column
+        X = rule_classifications.get_columns(columns)
+        train_predictions = compact_model.predict(X[train_example_idx])
+        test_predictions = compact_model.predict(X[test_example_idx])
+    report("Testing", 1.0)
     return train_predictions, test_predictions
 
 
+def _greedy_compression_set(presence_by_example):
+    """Chvatal's greedy set cover: genomes (rows) chosen until every k-mer (column) is present in one of them."""
+    chosen = []
+    while presence_by_example.shape[1] != 0:
+        best = np.argmax(presence_by_example.sum(axis=1))
+        chosen.append(best)
+        presence_by_example = presence_by_example[:, presence_by_example[best] == 0]
+    return chosen
+
+
 def _bound(train_predictions, train_answers, train_example_idx, model, delta, max_genome_size, rule_classifications):
-    """experiment_scm.py:349-398 -- sample-compression bound of a model (Marchand & Sokolova 2005)."""
-    # Construct the smallest possible compression set (Chvatal greedy approx for minimum set cover)
+    """Sample-compression bound of an SCM model (Marchand & Sokolova 2005), experiment_scm.py:349-398."""
     compression_set = []
     if len(model) > 0:
-        presence_by_example = rule_classifications.get_columns([r.kmer_index for r in model])[train_example_idx]
-        while presence_by_example.shape[1] != 0:
-            score = presence_by_example.sum(axis=1)
-            best_example_relative_idx = np.argmax(score)
-            compression_set.append(best_example_relative_idx)
-            presence_by_example = presence_by_example[:, presence_by_example[best_example_relative_idx] == 0]
+        kmers = [r.kmer_index for r in model]
+        compression_set = _greedy_compression_set(rule_classifications.get_columns(kmers)[train_example_idx])
     h_card = float(len(model))
     Z_card = float(len(compression_set) * max_genome_size)
     m = float(len(train_answers))
     mz = float(len(compression_set))
-    r = float((train_predictions != train_answers).sum()
-              - (train_predictions[compression_set] != train_answers[compression_set]).sum())
-    # NB: the conditional expression binds looser than "+": for a non-empty model only the else-branch is used
-    return 1.0 - exp((-1.0 / (m - mz - r)) * (
-        ln(comb(m, mz, exact=True)) + ln(comb(m - mz, r, exact=True)) + 0 if h_card == 0
-        else (h_card * ln(2 * Z_card)) + ln(pi ** 6 * (h_card + 1) ** 2 * (r + 1) ** 2 * (mz + 1) ** 2 / (216 * delta))))
+    wrong = train_predictions != train_answers
+    r = float(wrong.sum() - wrong[compression_set].sum())       # errors outside the compression set
+    # The reference writes  A + B + 0 if h_card == 0 else C + D : the conditional expression binds looser than
+    # "+", so a non-empty model's bound holds ONLY the else branch (no ln C(m, mz), no ln C(m - mz, r)).
+    if h_card == 0:
+        exponent = ln(comb(m, mz, exact=True)) + ln(comb(m - mz, r, exact=True)) + 0
+    else:
+        exponent = (h_card * ln(2 * Z_card)) + ln(pi ** 6 * (h_card + 1) ** 2 * (r + 1) ** 2 * (mz + 1) ** 2 /
+                                                  (216 * delta))
+    return 1.0 - exp((-1.0 / (m - mz - r)) * exponent)
 
 
 def _tiebreaker(best_utility_idx, rule_risks, model_type):

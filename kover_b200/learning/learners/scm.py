@@ -1,12 +1,16 @@
 """Set Covering Machine learner driven by the fused device scan.
 
-Mirrors reference kover/learning/learners/scm.py:29-288: ``UTIL_BLOCK_SIZE``,
-``_compute_rule_importances``, ``BaseSetCoveringMachine`` and ``SetCoveringMachine`` with the same
-constructor / ``fit`` signature, iteration_info keys, stopping rules and exceptions.  The greedy
-control flow stays on the host exactly as in the reference (scm.py:88-150); the two full-matrix
-``sum_rows`` passes plus the ~5 numpy passes over 2K utilities of ``_get_best_utility_rules``
-(scm.py:238-288) are replaced by one call to ``rule_classifications.best_utility_rules``, i.e. one
-pass of k_scan2 + k_scm_ties over the HBM-resident matrix.
+Interface parity with reference kover/learning/learners/scm.py:29-288: ``UTIL_BLOCK_SIZE``,
+``SetCoveringMachine(model_type, p, max_rules)``, ``fit(rules, rule_classifications, positive_example_idx,
+negative_example_idx, rule_blacklist, tiebreaker, iteration_callback, iteration_rule_importances)``, the keys of
+the ``iteration_info`` dictionaries handed to the callback, ``rule_importances``, the stopping rules and the
+exceptions.  The greedy set-cover control flow stays on the host (it is a dozen iterations); what the reference
+spends its time on -- two full-matrix ``sum_rows`` passes and several numpy passes over all 2K utilities per
+iteration (scm.py:238-288) -- is ONE call to ``rule_classifications.best_utility_rules``, i.e. one pass of
+k_scan_tma + k_scm_select + k_scm_ties over the HBM-resident matrix.
+
+The loop is written once, as a generator that asks for one scan per iteration; ``fit`` answers the requests one
+by one, ``fit_many`` answers the requests of many learners together (lock-step hyper-parameter grids).
 """
 import logging
 
@@ -14,159 +18,122 @@ import numpy as np
 
 from ..common.models import ConjunctionModel, DisjunctionModel, conjunction, disjunction
 
-UTIL_BLOCK_SIZE = 1000000
+UTIL_BLOCK_SIZE = 1000000          # rules per utility block of the reference's merge (scm.py:29)
+
+_MODEL_CLASSES = {conjunction: ConjunctionModel, disjunction: DisjunctionModel}
 
 
 def _compute_rule_importances(rule_classifications, model_rules_idx, training_example_idx):
-    """scm.py:32-36"""
-    model_rule_classifications = rule_classifications.get_columns(model_rules_idx)[training_example_idx]
-    model_neg_prediction_idx = np.where(np.prod(model_rule_classifications, axis=1) == 0)[0]
-    return (float(len(model_neg_prediction_idx)) -
-            model_rule_classifications[model_neg_prediction_idx].sum(axis=0)) / len(model_neg_prediction_idx)
+    """Importance of each rule of the model = share of the examples the model rejects that THIS rule rejects
+    (scm.py:32-36)."""
+    outputs = rule_classifications.get_columns(model_rules_idx)[training_example_idx]
+    rejected = np.flatnonzero(outputs.prod(axis=1) == 0)
+    return (float(rejected.shape[0]) - outputs[rejected].sum(axis=0)) / rejected.shape[0]
 
 
 class BaseSetCoveringMachine(object):
     def __init__(self, model_type, max_rules):
-        if model_type == conjunction:
-            self._add_rule_to_model = self._append_conjunction_model
-            self.model_type = conjunction
-        elif model_type == disjunction:
-            self._add_rule_to_model = self._append_disjunction_model
-            self.model_type = disjunction
-        else:
+        if model_type not in _MODEL_CLASSES:
             raise ValueError("Unsupported model type.")
+        self.model_type = model_type
         self.max_rules = max_rules
         self._flags = {}
-        super(BaseSetCoveringMachine, self).__init__()
+        self.rule_importances = []
 
-    def fit(self, rules, rule_classifications, positive_example_idx, negative_example_idx, rule_blacklist=[],
-            tiebreaker=None, iteration_callback=None, iteration_rule_importances=False, **kwargs):
-        """scm.py:54-159.  The greedy loop is written once, as a generator that asks for one utility scan per
-        iteration (``_fit_steps``); ``fit`` answers each request with its own scan, ``fit_many`` answers the
-        requests of many learners together so that scans over the same examples share a matrix pass."""
-        steps = self._fit_steps(rules, rule_classifications, positive_example_idx, negative_example_idx,
-                                rule_blacklist, tiebreaker, iteration_callback, iteration_rule_importances, **kwargs)
-        try:
-            request = next(steps)
-            while True:
-                pos_idx, neg_idx, blacklist, extra = request
-                request = steps.send(self._get_best_utility_rules(rule_classifications=rule_classifications,
-                                                                  positive_example_idx=pos_idx,
-                                                                  negative_example_idx=neg_idx,
-                                                                  rule_blacklist=blacklist, **extra))
-        except StopIteration:
-            pass
-
-    def _fit_steps(self, rules, rule_classifications, positive_example_idx, negative_example_idx, rule_blacklist=[],
-                   tiebreaker=None, iteration_callback=None, iteration_rule_importances=False, **kwargs):
-        utility_function_additional_args = {}
-        if kwargs is not None:
-            for key, value in kwargs.items():
-                if key[:9] == "utility__":
-                    utility_function_additional_args[key[9:]] = value
-
-        # Validate that there are some positive and negative examples
-        if len(positive_example_idx) == 0 or len(negative_example_idx) == 0:
-            raise ValueError("There must be positive and negative examples to train the SCM.")
-
-        positive_example_idx = np.asarray(positive_example_idx)
-        negative_example_idx = np.asarray(negative_example_idx)
-        if self.model_type == disjunction:
-            # Switch the example labels (scm.py:69-73)
-            positive_example_idx, negative_example_idx = negative_example_idx, positive_example_idx
-
-        logging.debug("Got " + str(len(rules)) + " binary rules.")
-        if rule_classifications.shape[1] != len(rules):
-            raise ValueError("The number of rules must match between rule_classifications and rules.")
-
-        # Validate the rule blacklist
-        if len(rule_blacklist) > 0:
-            rule_blacklist = np.unique(rule_blacklist)
-            if len(rule_blacklist) == rule_classifications.shape[1]:
-                raise ValueError("The blacklist cannot include all the rules.")
-            logging.debug("Blacklisting: {0:d} kmers ({1:d} rules)".format(len(rule_blacklist) // 2,
-                                                                           len(rule_blacklist)))
-
-        training_example_idx = np.hstack((positive_example_idx, negative_example_idx))  # needed for rule importances
-        model_rules_idx = []
-        model_rule_importances = []
-        while len(negative_example_idx) > 0 and len(self.model) < self.max_rules:
-            iteration_info = {"iteration_number": len(self.model) + 1}
-
-            best_utility, best_utility_idx, best_utility_pos_error_counts, best_utility_neg_cover_counts = \
-                yield (positive_example_idx, negative_example_idx, rule_blacklist, utility_function_additional_args)
-
-            iteration_info["utility_max"] = best_utility
-            iteration_info["utility_argmax"] = best_utility_idx
-            logging.debug("Greatest utility is %.5f" % iteration_info["utility_max"])
-            logging.debug("There are %d rules with the same utility." % len(iteration_info["utility_argmax"]))
-
-            # Do not select rules that cover no negative examples and make errors on no positive examples
-            best_utility_idx = iteration_info["utility_argmax"][
-                np.logical_or(best_utility_neg_cover_counts != 0, best_utility_pos_error_counts != 0)]
-            if len(best_utility_idx) == 0:
-                logging.debug("The rule of maximal utility does not cover negative examples or make errors" +
-                              " on positive examples. It will not be added to the model. Stopping here.")
-                break
-
-            # Apply a user-specified tiebreaker if necessary
-            if len(best_utility_idx) == 1:
-                best_rule_idx = best_utility_idx[0]
-                iteration_info["equivalent_rules_idx"] = np.array([best_rule_idx])
-            elif len(best_utility_idx) > 1:
-                best_rule_idx = tiebreaker(best_utility_idx)
-                logging.debug("The tiebreaker returned %d equivalent rules." % len(best_rule_idx))
-                iteration_info["equivalent_rules_idx"] = best_rule_idx
-                best_rule_idx = best_rule_idx[0]  # If many are equivalent, just take the first one.
-
-            # Add the best rule to the model
-            iteration_info["selected_rule"] = self._add_rule_to_model(rules[best_rule_idx])
-            model_rules_idx.append(best_rule_idx)
-
-            # Get the best rule's classification for each example
-            best_rule_classifications = rule_classifications.get_columns(best_rule_idx)
-
-            # Discard examples predicted as negative
-            negative_example_idx = negative_example_idx[best_rule_classifications[negative_example_idx] != 0]
-            positive_example_idx = positive_example_idx[best_rule_classifications[positive_example_idx] != 0]
-            logging.debug("Remaining negative examples:" + str(len(negative_example_idx)))
-            logging.debug("Remaining positive examples:" + str(len(positive_example_idx)))
-
-            # If required, compute the current model's rule importances
-            if iteration_rule_importances:
-                model_rule_importances = _compute_rule_importances(rule_classifications, model_rules_idx,
-                                                                   training_example_idx)
-                iteration_info["rule_importances"] = model_rule_importances
-
-            if iteration_callback is not None:
-                iteration_callback(iteration_info)
-
-        # Get the complete model's rule importances
-        if len(model_rules_idx) > 0:
-            if iteration_rule_importances:
-                self.rule_importances = model_rule_importances
-            else:
-                self.rule_importances = _compute_rule_importances(rule_classifications, model_rules_idx,
-                                                                  training_example_idx)
-        else:
-            self.rule_importances = []
-
-    def predict(self, X):
-        return self._predict(X)
-
-    def _append_conjunction_model(self, new_rule):
-        self.model.add(new_rule)
-        logging.debug("Rule added to the model: " + str(new_rule))
-        return new_rule
-
-    def _append_disjunction_model(self, new_rule):
-        new_rule = new_rule.inverse()
-        self.model.add(new_rule)
-        logging.debug("Rule added to the model: " + str(new_rule))
-        return new_rule
+    # ------------------------------------------------------------------ model bookkeeping
+    def _add_rule_to_model(self, rule):
+        """A disjunction is learnt as a conjunction on swapped labels, so the rule that enters the model is the
+        inverse of the selected one (scm.py:180-184).  Returns the rule as stored."""
+        stored = rule.inverse() if self.model_type == disjunction else rule
+        self.model.add(stored)
+        logging.debug("Rule added to the model: %s", stored)
+        return stored
 
     def _is_fitted(self):
         return len(self.model) > 0
+
+    # ------------------------------------------------------------------ fitting
+    def fit(self, rules, rule_classifications, positive_example_idx, negative_example_idx, rule_blacklist=[],
+            tiebreaker=None, iteration_callback=None, iteration_rule_importances=False, **kwargs):
+        steps = self._fit_steps(rules, rule_classifications, positive_example_idx, negative_example_idx,
+                                rule_blacklist, tiebreaker, iteration_callback, iteration_rule_importances, **kwargs)
+        answer = None
+        while True:
+            try:
+                pos_idx, neg_idx, blacklist, extra = steps.send(answer)
+            except StopIteration:
+                return
+            answer = self._get_best_utility_rules(rule_classifications=rule_classifications,
+                                                  positive_example_idx=pos_idx, negative_example_idx=neg_idx,
+                                                  rule_blacklist=blacklist, **extra)
+
+    def _fit_steps(self, rules, rule_classifications, positive_example_idx, negative_example_idx, rule_blacklist=[],
+                   tiebreaker=None, iteration_callback=None, iteration_rule_importances=False, **kwargs):
+        """Generator: yields (positive_idx, negative_idx, blacklist, utility kwargs) whenever the greedy loop
+        needs the best-utility rules, and is sent the 4-tuple ``_get_best_utility_rules`` returns."""
+        scan_kwargs = dict((name[len("utility__"):], value) for name, value in (kwargs or {}).items()
+                           if name.startswith("utility__"))
+        if len(positive_example_idx) == 0 or len(negative_example_idx) == 0:
+            raise ValueError("There must be positive and negative examples to train the SCM.")
+        to_keep = np.asarray(positive_example_idx)       # examples the model must keep accepting
+        to_cover = np.asarray(negative_example_idx)      # examples the model must come to reject
+        if self.model_type == disjunction:               # learn the complement concept (scm.py:69-73)
+            to_keep, to_cover = to_cover, to_keep
+        n_rules = rule_classifications.shape[1]
+        if n_rules != len(rules):
+            raise ValueError("The number of rules must match between rule_classifications and rules.")
+        if len(rule_blacklist) > 0:
+            rule_blacklist = np.unique(rule_blacklist)
+            if len(rule_blacklist) == n_rules:
+                raise ValueError("The blacklist cannot include all the rules.")
+            logging.debug("Blacklisting %d rules.", len(rule_blacklist))
+
+        all_training_idx = np.hstack((to_keep, to_cover))
+        chosen, importances = [], []
+        while len(to_cover) > 0 and len(self.model) < self.max_rules:
+            info = {"iteration_number": len(self.model) + 1}
+            best_utility, tied, tied_pos_errors, tied_neg_cover = \
+                yield (to_keep, to_cover, rule_blacklist, scan_kwargs)
+            info["utility_max"], info["utility_argmax"] = best_utility, tied
+            logging.debug("Greatest utility is %.5f (%d rules)", best_utility, len(tied))
+
+            # a rule that rejects nothing at all cannot make progress (scm.py:109)
+            useful = tied[(tied_neg_cover != 0) | (tied_pos_errors != 0)]
+            if len(useful) == 0:
+                logging.debug("The best rule covers no example: stopping.")
+                break
+            if len(useful) == 1:
+                equivalent = np.array([useful[0]])
+            else:
+                equivalent = tiebreaker(useful)
+            info["equivalent_rules_idx"] = equivalent
+            selected = equivalent[0]                     # equivalent rules: the first one is kept (scm.py:124)
+
+            info["selected_rule"] = self._add_rule_to_model(rules[selected])
+            chosen.append(selected)
+
+            # examples the new rule rejects leave both sets (scm.py:133-139); the column spans ALL genomes
+            accepted = rule_classifications.get_columns(selected)
+            to_cover = to_cover[accepted[to_cover] != 0]
+            to_keep = to_keep[accepted[to_keep] != 0]
+            logging.debug("Remaining examples to cover: %d, to keep: %d", len(to_cover), len(to_keep))
+
+            if iteration_rule_importances:
+                importances = _compute_rule_importances(rule_classifications, chosen, all_training_idx)
+                info["rule_importances"] = importances
+            if iteration_callback is not None:
+                iteration_callback(info)
+
+        if len(chosen) == 0:
+            self.rule_importances = []
+        elif iteration_rule_importances:
+            self.rule_importances = importances
+        else:
+            self.rule_importances = _compute_rule_importances(rule_classifications, chosen, all_training_idx)
+
+    # ------------------------------------------------------------------ predictions
+    def predict(self, X):
+        return self._predict(X)
 
     def _predict(self, X):
         if not self._is_fitted():
@@ -181,69 +148,65 @@ class BaseSetCoveringMachine(object):
         return self.model.predict_proba(X)
 
 
+class SetCoveringMachine(BaseSetCoveringMachine):
+    """The Set Covering Machine (Marchand & Shawe-Taylor, JMLR 2003).
+
+    model_type: "conjunction" or "disjunction"; p: trade-off between covering negatives and erring on positives in
+    the utility ``N_neg_covered - p * N_pos_errors``; max_rules: early stopping (scm.py:210-236)."""
+
+    def __init__(self, model_type=conjunction, p=1.0, max_rules=10):
+        super(SetCoveringMachine, self).__init__(model_type=model_type, max_rules=max_rules)
+        self.model = _MODEL_CLASSES[model_type]()
+        self.p = p
+
+    def _get_best_utility_rules(self, rule_classifications, positive_example_idx, negative_example_idx,
+                                rule_blacklist=[]):
+        """-> (best_utility, best_utility_idx, pos_error_counts, neg_cover_counts), scm.py:238-288."""
+        assert isinstance(rule_blacklist, (list, np.ndarray))
+        scan = getattr(rule_classifications, "best_utility_rules", None)
+        if scan is None:
+            raise TypeError("kover_b200's SetCoveringMachine scans a device-resident matrix: pass a "
+                            "kover_b200.learning.common.rules.KmerRuleClassifications (there is no CPU path).")
+        return scan(self.p, positive_example_idx, negative_example_idx, rule_blacklist=rule_blacklist,
+                    util_block_size=UTIL_BLOCK_SIZE)
+
+
 def fit_many(learners, fit_args, rule_classifications):
     """Fit several SetCoveringMachine learners over the SAME rule_classifications in lock-step (the reference
     runs them one after the other, or in forked workers: experiment_scm.py:196-248, 568-629).
 
-    learners: list of SetCoveringMachine; fit_args: one dict of ``fit`` keyword arguments per learner
-    (rules, positive_example_idx, negative_example_idx, rule_blacklist, tiebreaker, iteration_callback,
+    learners: list of SetCoveringMachine; fit_args: one dict of ``fit`` keyword arguments per learner (rules,
+    positive_example_idx, negative_example_idx, rule_blacklist, tiebreaker, iteration_callback,
     iteration_rule_importances).  At every greedy iteration the pending utility scans of all learners are
-    answered together by ``rule_classifications.best_utility_rules_grid``: learners whose remaining example
-    sets coincide -- every p of the grid and both model types at iteration 1, and whenever they picked the
-    same rules -- share one pass over the matrix.  Each learner ends in exactly the state its own ``fit``
-    would have produced (same scans, same order of operations per learner)."""
-    gens, pending = [], {}
+    answered together by ``rule_classifications.best_utility_rules_grid``: learners whose remaining example sets
+    coincide -- every p of the grid and both model types at iteration 1, and whenever they picked the same
+    rules -- share one pass over the matrix.  Each learner ends in exactly the state its own ``fit`` would have
+    produced (same scans, same order of operations per learner)."""
+    running = {}
     for i, (learner, kw) in enumerate(zip(learners, fit_args)):
-        kw = dict(kw)
-        kw["rule_classifications"] = rule_classifications
-        g = learner._fit_steps(**kw)
-        gens.append(g)
+        gen = learner._fit_steps(rule_classifications=rule_classifications, **kw)
         try:
-            pending[i] = next(g)
+            running[i] = (gen, next(gen))
         except StopIteration:
             pass
-    while pending:
+    while running:
         # one grid call per distinct blacklist (the experiments use a single blacklist for all fits)
         by_blacklist = {}
-        for i, (pos_idx, neg_idx, blacklist, extra) in pending.items():
+        for i, (_, (pos_idx, neg_idx, blacklist, extra)) in running.items():
             if extra:
                 raise ValueError("fit_many does not support utility__ keyword arguments")
             by_blacklist.setdefault(np.asarray(blacklist, dtype=np.int64).tobytes(), []).append(i)
         answers = {}
         for members in by_blacklist.values():
-            jobs = [(learners[i].p, pending[i][0], pending[i][1]) for i in members]
-            res = rule_classifications.best_utility_rules_grid(jobs, rule_blacklist=pending[members[0]][2],
-                                                               util_block_size=UTIL_BLOCK_SIZE)
-            answers.update(zip(members, res))
-        nxt = {}
-        for i, ans in answers.items():
+            jobs = [(learners[i].p, running[i][1][0], running[i][1][1]) for i in members]
+            results = rule_classifications.best_utility_rules_grid(jobs, rule_blacklist=running[members[0]][1][2],
+                                                                   util_block_size=UTIL_BLOCK_SIZE)
+            answers.update(zip(members, results))
+        still_running = {}
+        for i, answer in answers.items():
+            gen = running[i][0]
             try:
-                nxt[i] = gens[i].send(ans)
+                still_running[i] = (gen, gen.send(answer))
             except StopIteration:
                 pass
-        pending = nxt
-
-
-class SetCoveringMachine(BaseSetCoveringMachine):
-    """The Set Covering Machine (Marchand & Shawe-Taylor, JMLR 2003); parameters as scm.py:210-236."""
-
-    def __init__(self, model_type=conjunction, p=1.0, max_rules=10):
-        super(SetCoveringMachine, self).__init__(model_type=model_type, max_rules=max_rules)
-        if model_type == conjunction:
-            self.model = ConjunctionModel()
-        elif model_type == disjunction:
-            self.model = DisjunctionModel()
-        else:
-            raise ValueError("Unsupported model type.")
-        self.p = p
-
-    def _get_best_utility_rules(self, rule_classifications, positive_example_idx, negative_example_idx,
-                                rule_blacklist=[]):
-        """scm.py:238-288 -> (best_utility, best_utility_idx, pos_error_counts, neg_cover_counts)."""
-        assert isinstance(rule_blacklist, list) or isinstance(rule_blacklist, np.ndarray)
-        if not hasattr(rule_classifications, "best_utility_rules"):
-            raise TypeError("kover_b200's SetCoveringMachine scans a device-resident matrix: pass a "
-                            "kover_b200.learning.common.rules.KmerRuleClassifications (there is no CPU path).")
-        return rule_classifications.best_utility_rules(self.p, positive_example_idx, negative_example_idx,
-                                                       rule_blacklist=rule_blacklist,
-                                                       util_block_size=UTIL_BLOCK_SIZE)
+        running = still_running
