@@ -7,7 +7,7 @@
 //                  per-utility-block maximum of scm.py:262-270; TMA bulk copies + mbarrier ring
 //   k_scm_select   scm.py:270-286 (sequential merge of the block maxima), on the device
 //   k_scm_ties     scm.py:273 (isclose tie set against the block maximum)
-//   k_count_multi  rules.py:201-267 for up to 8 masks per pass (CART classes, batched sum_rows)
+//   k_count_tma    rules.py:201-267 for up to 16 masks per pass (CV folds / CART levels / batched sum_rows)
 //   k_gini         cart.py:85-161 (_gini_impurity / _gini_rule_score), min + exact ties cart.py:238
 //   k_gather_cols  rules.py:164 (dataset[:, cols])
 //   k_popc_inplace popcount.pyx:31-50, 76-95
@@ -86,7 +86,6 @@ extern "C" int kv_device_count(int *n) {
 static constexpr int TILE_COLS = 512;    // columns per tile of the direct-load kernels: 256 threads x one 128-bit load
 static constexpr int LD_ALIGN = 1024;    // row pitch granularity: a multiple of every tile width (512 / 1024 columns)
 static constexpr int SCAN_THREADS = 256;
-static constexpr int MAX_MULTI = 8;      // masks per pass of k_count_multi
 static constexpr int MAX_CLASSES = 64;
 
 // ------------------------------------------------------------------------------------------------
@@ -786,64 +785,108 @@ __global__ void __launch_bounds__(256) k_scm_rescore(const RescoreParams P) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_count_multi: NM masks per pass (CART classes / batched sum_rows)
+// k_count_tma: presence counts under NM row masks in ONE pass over the shard (rules.py:201-267 for many
+// row sets at once): the mask pairs of different cross-validation folds / greedy states of a
+// hyper-parameter grid, the class masks of all the nodes of a CART level, batched sum_rows.
+// Same producer / ring / consumer structure as k_scan_tma; the masks of a packed row sit in shared memory
+// as [row][NM] and a zero mask word is skipped (warp-uniform), like the reference skips packed rows whose
+// mask is empty (rules.py:244).  With many masks the pass is bound by the POPC pipe (16 lanes/clk/SM), not
+// by HBM: DESIGN.md section 4.5.
 // ------------------------------------------------------------------------------------------------
-struct MultiParams {
+static constexpr int MAX_MULTI = 16;     // masks per pass of k_count_tma
+
+struct CountParams {
     const uint64_t *mat;
-    long long ld, n_tiles;
+    long long ld;
     const uint32_t *rec_row;      // active rows (any mask non-zero)
     const uint64_t *rec_m;        // [n_act][NM]
     int n_act;
-    uint32_t *cnt[MAX_MULTI];     // [ld] each
+    uint32_t *cnt[MAX_MULTI];     // [ld] each; null = discard (padding mask)
 };
 
-template <int NM>
-__global__ void __launch_bounds__(SCAN_THREADS, 4) k_count_multi(const MultiParams P) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint64_t *s_m = reinterpret_cast<uint64_t *>(smem_raw);
-    uint32_t *s_row = reinterpret_cast<uint32_t *>(s_m + (size_t)P.n_act * NM);
-    for (int i = threadIdx.x; i < P.n_act * NM; i += SCAN_THREADS) s_m[i] = P.rec_m[i];
-    for (int i = threadIdx.x; i < P.n_act; i += SCAN_THREADS) s_row[i] = P.rec_row[i];
+template <int NM, int CW, int R, int S>
+__global__ void __launch_bounds__((CW + 1) * 32, 1) k_count_tma(const CountParams P) {
+    static_assert(NM % 2 == 0, "masks are fetched two at a time");
+    extern __shared__ __align__(128) unsigned char smem_tma[];
+    constexpr int ROW_BYTES = CW * 32 * 16;
+    constexpr int TC = CW * 64;
+    const int n_act = P.n_act;
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_tma);
+    uint64_t *empty = full + S;
+    uint64_t *s_m = empty + S;                               // 16-byte aligned: 2*S*8 is a multiple of 16
+    uint32_t *s_row = reinterpret_cast<uint32_t *>(s_m + (size_t)n_act * NM);
+    unsigned char *ring = smem_tma + ((size_t)(2 * S) * 8 + (size_t)n_act * (NM * 8 + 4) + 127) / 128 * 128;
+    for (int i = threadIdx.x; i < n_act * NM; i += blockDim.x) s_m[i] = P.rec_m[i];
+    for (int i = threadIdx.x; i < n_act; i += blockDim.x) s_row[i] = P.rec_row[i];
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(full + s, 1);
+            mbar_init(empty + s, CW);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
-    const long long t0 = (P.n_tiles * (long long)blockIdx.x) / gridDim.x;
-    const long long t1 = (P.n_tiles * (long long)(blockIdx.x + 1)) / gridDim.x;
-    constexpr int UN = 4;
-    for (long long tile = t0; tile < t1; ++tile) {
-        const long long col = tile * TILE_COLS + 2 * (long long)threadIdx.x;
-        const uint64_t *base = P.mat + col;
-        uint32_t cx[NM], cy[NM];
-#pragma unroll
-        for (int m = 0; m < NM; ++m) cx[m] = cy[m] = 0;
-        int i = 0;
-#pragma unroll 1
-        for (; i + UN <= P.n_act; i += UN) {
-            ulonglong2 v[UN];
-#pragma unroll
-            for (int j = 0; j < UN; ++j) v[j] = ldg_stream(base + (long long)s_row[i + j] * P.ld);
-#pragma unroll
-            for (int j = 0; j < UN; ++j) {
-#pragma unroll
-                for (int m = 0; m < NM; ++m) {
-                    const uint64_t mk = s_m[(i + j) * NM + m];
-                    if (mk) {                                   // warp-uniform
-                        cx[m] += __popcll(v[j].x & mk);
-                        cy[m] += __popcll(v[j].y & mk);
-                    }
+    const long long n_tiles = P.ld / TC;
+    const long long t0 = (n_tiles * (long long)blockIdx.x) / gridDim.x;
+    const long long t1 = (n_tiles * (long long)(blockIdx.x + 1)) / gridDim.x;
+    const int nb = (n_act + R - 1) / R;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == CW) {
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            for (long long tile = t0; tile < t1; ++tile) {
+                const uint64_t *src = P.mat + tile * TC;
+                for (int b = 0; b < nb; ++b) {
+                    const int rows_here = min(R, n_act - b * R);
+                    mbar_wait(empty + s, ph ^ 1);
+                    mbar_expect_tx(full + s, (uint32_t)rows_here * ROW_BYTES);
+                    unsigned char *dst = ring + (size_t)s * R * ROW_BYTES;
+                    for (int r = 0; r < rows_here; ++r)
+                        tma_bulk_g2s(dst + r * ROW_BYTES, src + (long long)s_row[b * R + r] * P.ld, ROW_BYTES, full + s);
+                    if (++s == S) { s = 0; ph ^= 1; }
                 }
             }
         }
-#pragma unroll 1
-        for (; i < P.n_act; ++i) {
-            const ulonglong2 v = ldg_stream(base + (long long)s_row[i] * P.ld);
+        return;
+    }
+
+    int s = 0;
+    uint32_t ph = 0;
+    for (long long tile = t0; tile < t1; ++tile) {
+        uint32_t cx[NM], cy[NM];
 #pragma unroll
-            for (int m = 0; m < NM; ++m) {
-                const uint64_t mk = s_m[i * NM + m];
-                cx[m] += __popcll(v.x & mk);
-                cy[m] += __popcll(v.y & mk);
+        for (int m = 0; m < NM; ++m) cx[m] = cy[m] = 0;
+        for (int b = 0; b < nb; ++b) {
+            const int rows_here = min(R, n_act - b * R);
+            mbar_wait(full + s, ph);
+            const unsigned char *st = ring + (size_t)s * R * ROW_BYTES + threadIdx.x * 16;
+#pragma unroll 2
+            for (int r = 0; r < rows_here; ++r) {
+                const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(st + r * ROW_BYTES);
+                const ulonglong2 *mk = reinterpret_cast<const ulonglong2 *>(s_m + (size_t)(b * R + r) * NM);
+#pragma unroll
+                for (int m = 0; m < NM; m += 2) {
+                    const ulonglong2 mm = mk[m >> 1];          // broadcast read
+                    if (mm.x) {                                // warp-uniform
+                        cx[m] += __popcll(v.x & mm.x);
+                        cy[m] += __popcll(v.y & mm.x);
+                    }
+                    if (mm.y) {
+                        cx[m + 1] += __popcll(v.x & mm.y);
+                        cy[m + 1] += __popcll(v.y & mm.y);
+                    }
+                }
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty + s);
+            if (++s == S) { s = 0; ph ^= 1; }
         }
+        const long long col = tile * TC + 2 * (long long)threadIdx.x;
 #pragma unroll
-        for (int m = 0; m < NM; ++m) *reinterpret_cast<uint2 *>(P.cnt[m] + col) = make_uint2(cx[m], cy[m]);
+        for (int m = 0; m < NM; ++m)
+            if (P.cnt[m]) *reinterpret_cast<uint2 *>(P.cnt[m] + col) = make_uint2(cx[m], cy[m]);
     }
 }
 
@@ -1154,6 +1197,7 @@ struct kv_shard {
 
     // state left by the last scan for phase 2
     bool scm_valid = false, scm_swapped = false, reuse_armed = false, reuse_swap = false;
+    const uint32_t *scm_cnt_a = nullptr, *scm_cnt_b = nullptr;   // presence counts under the scanned pair's first / second mask
     long long scm_n_pos = 0, scm_n_neg = 0, scm_ubs = 0;
     double scm_p = 0.0;
     bool gini_valid = false, risk_valid = false;
@@ -1786,67 +1830,141 @@ extern "C" int kv_risk_map(kv_shard *s, const uint32_t *lut_kmer, const uint32_t
     return KV_OK;
 }
 
-// counts of n_masks masks into d_cnt[first .. first+n_masks) (device resident)
-static int count_masks(kv_shard *s, int n_masks, const uint64_t *masks, int first) {
+// ---- k_count_tma launch ------------------------------------------------------------------------
+template <int NM, int R, int S>
+static int launch_count_variant(kv_shard *s, const CountParams &P, size_t smem) {
+    constexpr int CW = 16;
+    static thread_local int attr_device = -1;
+    static thread_local size_t attr_bytes = 0;
+    if (attr_device != s->device || attr_bytes < smem) {
+        CU(cudaFuncSetAttribute(k_count_tma<NM, CW, R, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_device = s->device;
+        attr_bytes = smem;
+    }
+    const long long n_tiles = s->ld / (CW * 64);
+    const int grid = (int)std::max(1ll, std::min<long long>((long long)s->sm_count, n_tiles));
+    k_count_tma<NM, CW, R, S><<<grid, (CW + 1) * 32, smem, s->stream>>>(P);
+    return KV_OK;
+}
+
+static size_t count_smem_bytes(int n_act, int nm, int R, int S) {
+    return ((size_t)(2 * S) * 8 + (size_t)n_act * (nm * 8 + 4) + 127) / 128 * 128 + (size_t)S * R * 16 * 512;
+}
+
+template <int NM>
+static int launch_count_nm(kv_shard *s, const CountParams &P) {
+    // ring depth by what the mask staging leaves: 192 KB, 128 KB or 64 KB of reads in flight per SM
+    const size_t limit = 227 * 1024 - 2048;
+    size_t smem = count_smem_bytes(P.n_act, NM, 8, 3);
+    if (smem <= limit) return launch_count_variant<NM, 8, 3>(s, P, smem);
+    smem = count_smem_bytes(P.n_act, NM, 4, 4);
+    if (smem <= limit) return launch_count_variant<NM, 4, 4>(s, P, smem);
+    smem = count_smem_bytes(P.n_act, NM, 4, 2);
+    if (smem <= limit) return launch_count_variant<NM, 4, 2>(s, P, smem);
+    return fail(KV_E_INVALID, "too many active packed rows x masks for one pass (shared-memory staging limit)");
+}
+
+static int padded_nm(int nm) {
+    static const int sizes[] = {2, 4, 6, 8, 12, 16};
+    for (int v : sizes)
+        if (nm <= v) return v;
+    return -1;
+}
+
+// masks per pass so that the [row][mask] staging of W packed rows fits beside the smallest ring
+static int max_masks_per_pass(long long W) {
+    const long long budget = 227 * 1024 - 2048 - 64 * 1024 - 256;
+    long long nm = (budget / std::max<long long>(W, 1) - 4) / 8;
+    nm = std::min<long long>(nm, MAX_MULTI);
+    static const int sizes[] = {16, 12, 8, 6, 4, 2};
+    for (int v : sizes)
+        if (nm >= v) return v;
+    return 0;
+}
+
+// staging bytes of one pass (row records [n_act][NM] u64 + rows u32), rounded so that consecutive passes stay aligned
+static size_t count_batch_stride(long long W) {
+    return ((size_t)W * (8 * (size_t)MAX_MULTI + 4) + 127) / 128 * 128;
+}
+static size_t count_pin_bytes(long long W, int n_masks) {
+    const int per = std::max(2, max_masks_per_pass(W));
+    const int n_batches = (n_masks + per - 1) / per;
+    return (size_t)n_batches * count_batch_stride(W);
+}
+
+// Presence counts of n_masks row masks (host pointers, W words each) into the device arrays dst[m]
+// ([ld] uint32 each), ceil(n_masks / masks-per-pass) passes of k_count_tma enqueued on the shard's stream.
+// Nothing is synchronised: `pin` (pinned, count_pin_bytes(W, n_masks) bytes) stages the row records and
+// must stay untouched until the stream has drained.  ev0 / ev1 bracket the passes.
+static int count_masks_async(kv_shard *s, int n_masks, const uint64_t *const *masks, uint32_t *const *dst, char *pin) {
     const long long W = s->W;
-    KV_TRY(ensure_counts(s, first + n_masks));
-    float total_ms = 0;
-    for (int m0 = 0; m0 < n_masks; m0 += MAX_MULTI) {
-        const int nm = std::min(MAX_MULTI, n_masks - m0);
-        KV_TRY(ensure_pinned(s, (size_t)W * (8 * nm + 4) + 64));
-        // an in-flight H2D may still read h_pin from the previous group
-        CU(cudaStreamSynchronize(s->stream));
+    const int per = max_masks_per_pass(W);
+    if (per < 2) return fail(KV_E_INVALID, "too many packed rows for a multi-mask pass (shared-memory staging limit)");
+    KV_TRY(ensure(s->d_rec, count_pin_bytes(W, n_masks)));
+    CU(cudaEventRecord(s->ev0, s->stream));
+    size_t off = 0;
+    for (int m0 = 0; m0 < n_masks; m0 += per) {
+        const int nm = std::min(per, n_masks - m0);
+        const int nmp = padded_nm(nm);
         int n_act = 0;
         for (long long w = 0; w < W; ++w) {
             bool any = false;
-            for (int m = 0; m < nm; ++m) any |= masks[(size_t)(m0 + m) * W + w] != 0;
+            for (int m = 0; m < nm; ++m) any |= masks[m0 + m][w] != 0;
             n_act += any;
         }
-        uint64_t *pm = (uint64_t *)s->h_pin;
-        uint32_t *prow = (uint32_t *)(pm + (size_t)n_act * nm);
+        uint64_t *pm = (uint64_t *)(pin + off);
+        uint32_t *prow = (uint32_t *)(pm + (size_t)n_act * nmp);
         int i = 0;
         for (long long w = 0; w < W; ++w) {
             bool any = false;
-            for (int m = 0; m < nm; ++m) any |= masks[(size_t)(m0 + m) * W + w] != 0;
+            for (int m = 0; m < nm; ++m) any |= masks[m0 + m][w] != 0;
             if (!any) continue;
-            for (int m = 0; m < nm; ++m) pm[(size_t)i * nm + m] = masks[(size_t)(m0 + m) * W + w];
+            for (int m = 0; m < nm; ++m) pm[(size_t)i * nmp + m] = masks[m0 + m][w];
+            for (int m = nm; m < nmp; ++m) pm[(size_t)i * nmp + m] = 0;
             prow[i++] = (uint32_t)w;
         }
-        const size_t rec_bytes = (size_t)n_act * (8 * nm + 4);
-        KV_TRY(ensure(s->d_rec, rec_bytes + 64));
-        if (n_act) CU(cudaMemcpyAsync(s->d_rec.p, s->h_pin, rec_bytes, cudaMemcpyHostToDevice, s->stream));
-        MultiParams P;
+        const size_t rec_bytes = (size_t)n_act * (8 * nmp + 4);
+        char *d_rec = (char *)s->d_rec.p + off;
+        if (n_act) CU(cudaMemcpyAsync(d_rec, pin + off, rec_bytes, cudaMemcpyHostToDevice, s->stream));
+        CountParams P;
         memset(&P, 0, sizeof P);
         P.mat = s->d_mat;
         P.ld = s->ld;
-        P.n_tiles = s->n_tiles;
-        P.rec_m = (const uint64_t *)s->d_rec.p;
-        P.rec_row = (const uint32_t *)(P.rec_m + (size_t)n_act * nm);
+        P.rec_m = (const uint64_t *)d_rec;
+        P.rec_row = (const uint32_t *)(P.rec_m + (size_t)n_act * nmp);
         P.n_act = n_act;
-        for (int m = 0; m < nm; ++m) P.cnt[m] = s->d_cnt[first + m0 + m];
-        const size_t smem = rec_bytes + 16;
-        KV_TRY(check_smem(smem));
-        const int grid = scan_grid(s);
-        CU(cudaEventRecord(s->ev0, s->stream));
-#define LAUNCH_MULTI(NM)                                                                                      \
-    case NM:                                                                                                  \
-        CU(cudaFuncSetAttribute(k_count_multi<NM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
-        k_count_multi<NM><<<grid, SCAN_THREADS, smem, s->stream>>>(P);                                        \
-        break;
-        switch (nm) {
-            LAUNCH_MULTI(1) LAUNCH_MULTI(2) LAUNCH_MULTI(3) LAUNCH_MULTI(4)
-            LAUNCH_MULTI(5) LAUNCH_MULTI(6) LAUNCH_MULTI(7) LAUNCH_MULTI(8)
+        for (int m = 0; m < nm; ++m) P.cnt[m] = dst[m0 + m];
+        int rc = KV_OK;
+        switch (nmp) {
+            case 2: rc = launch_count_nm<2>(s, P); break;
+            case 4: rc = launch_count_nm<4>(s, P); break;
+            case 6: rc = launch_count_nm<6>(s, P); break;
+            case 8: rc = launch_count_nm<8>(s, P); break;
+            case 12: rc = launch_count_nm<12>(s, P); break;
+            case 16: rc = launch_count_nm<16>(s, P); break;
+            default: return fail(KV_E_INVALID, "count_masks: bad mask count");
         }
-#undef LAUNCH_MULTI
+        KV_TRY(rc);
         count_launch(s);
-        CU(cudaEventRecord(s->ev1, s->stream));
-        CU(cudaStreamSynchronize(s->stream));
-        CU(cudaGetLastError());
-        float ms = 0;
-        CU(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
-        total_ms += ms;
+        off += count_batch_stride(W);
     }
-    s->last_kernel_ms = total_ms;
+    CU(cudaEventRecord(s->ev1, s->stream));
+    return KV_OK;
+}
+
+// counts of n_masks masks ([n_masks][W] contiguous) into d_cnt[first .. first+n_masks), synchronised
+static int count_masks(kv_shard *s, int n_masks, const uint64_t *masks, int first) {
+    KV_TRY(ensure_counts(s, first + n_masks));
+    KV_TRY(ensure_pinned(s, count_pin_bytes(s->W, n_masks)));
+    CU(cudaStreamSynchronize(s->stream));          // an in-flight copy may still read h_pin
+    std::vector<const uint64_t *> ptrs(n_masks);
+    for (int m = 0; m < n_masks; ++m) ptrs[m] = masks + (size_t)m * s->W;
+    KV_TRY(count_masks_async(s, n_masks, ptrs.data(), s->d_cnt.data() + first, (char *)s->h_pin));
+    CU(cudaStreamSynchronize(s->stream));
+    CU(cudaGetLastError());
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+    s->last_kernel_ms = ms;
     return KV_OK;
 }
 
@@ -1985,8 +2103,8 @@ static int scm_scan_async(kv_shard *s, const uint64_t *pos_mask, const uint64_t 
         const bool swapped = s->reuse_swap;      // relative to the masks of the scan that produced the counts
         RescoreParams R;
         memset(&R, 0, sizeof R);
-        R.cnt_pos = s->d_cnt[swapped ? 1 : 0];
-        R.cnt_neg = s->d_cnt[swapped ? 0 : 1];
+        R.cnt_pos = swapped ? s->scm_cnt_b : s->scm_cnt_a;
+        R.cnt_neg = swapped ? s->scm_cnt_a : s->scm_cnt_b;
         R.n_cols = s->n_cols;
         R.ld = s->ld;
         R.col0 = s->col0;
@@ -2022,6 +2140,8 @@ static int scm_scan_async(kv_shard *s, const uint64_t *pos_mask, const uint64_t 
         P.blockmax = L.blockmax;
         P.segmax = s->d_segmax;
         KV_TRY(launch_scan<EPI_SCM>(s, P, n_both));
+        s->scm_cnt_a = s->d_cnt[0];
+        s->scm_cnt_b = s->d_cnt[1];
         s->scm_swapped = false;
         s->scan_calls += 1;
     }
@@ -2118,8 +2238,8 @@ static void launch_exact_ties(kv_shard *s, int64_t n_blocks, TieHeader *d_hdr, T
     MiscLayout L = misc_layout(s->d_misc.p, n_blocks);
     TieParams T;
     memset(&T, 0, sizeof T);
-    T.cnt0 = s->d_cnt[s->scm_swapped ? 1 : 0];
-    T.cnt1 = s->d_cnt[s->scm_swapped ? 0 : 1];
+    T.cnt0 = s->scm_swapped ? s->scm_cnt_b : s->scm_cnt_a;
+    T.cnt1 = s->scm_swapped ? s->scm_cnt_a : s->scm_cnt_b;
     T.segmax = s->d_segmax;
     T.n_cols = s->n_cols;
     T.ld = s->ld;
@@ -2312,12 +2432,78 @@ extern "C" int kv_scm_queue_collect(kv_shard *s, int64_t n_slots, double *best_u
     return KV_OK;
 }
 
+// Jobs whose reuse flag is 0 open a group (a new mask pair); the jobs that follow with reuse 1 / 2 re-score
+// that group's counts.  With two or more groups the pairs are counted SEVERAL PER MATRIX PASS by k_count_tma
+// (up to MAX_MULTI / 2 pairs: the folds of a cross-validation, the diverged greedy states of a grid) and
+// every job -- the group leaders included -- is then scored from the resident counts by k_scm_rescore.
+static int scm_queue_run_batched(kv_shard *s, int64_t n_jobs, const uint64_t *masks, const int64_t *n_pos,
+                                 const int64_t *n_neg, const double *p, const int32_t *reuse, int64_t util_block_size,
+                                 int pairs_per_pass) {
+    const int64_t n_blocks = kv_scm_n_blocks(s->k_total, util_block_size);
+    if (n_blocks <= 0) return fail(KV_E_INVALID, "kv_scm_queue_run: util_block_size must be positive");
+    std::vector<int64_t> leaders;
+    for (int64_t j = 0; j < n_jobs; ++j) {
+        if (reuse[j] < 0 || reuse[j] > 2) return fail(KV_E_INVALID, "kv_scm_queue_run: reuse must be 0, 1 or 2");
+        if (reuse[j] == 0) leaders.push_back(j);
+    }
+    const size_t n_passes = (leaders.size() + pairs_per_pass - 1) / pairs_per_pass;
+    s->last_launches = 0;
+    KV_TRY(ensure(s->d_queue, (size_t)n_jobs * kQueueSlotBytes));
+    KV_TRY(ensure_counts(s, 2 + 2 * pairs_per_pass));
+    KV_TRY(ensure_pinned(s, std::max(n_passes * count_batch_stride(s->W), (size_t)n_jobs * kQueueSlotBytes)));
+    KV_TRY(ensure(s->d_rec, count_batch_stride(s->W)));
+    if (!s->d_segmax) CU(cudaMalloc(&s->d_segmax, (size_t)(s->ld / 64) * 2 * 8));
+    CU(cudaStreamSynchronize(s->stream));                 // an earlier call's copies may still read the pinned buffer
+    for (size_t pass = 0; pass < n_passes; ++pass) {
+        const size_t l0 = pass * pairs_per_pass, l1 = std::min(leaders.size(), l0 + pairs_per_pass);
+        std::vector<const uint64_t *> ptrs;
+        std::vector<uint32_t *> dst;
+        for (size_t l = l0; l < l1; ++l) {
+            const uint64_t *pm = masks + (size_t)leaders[l] * 2 * s->W;
+            ptrs.push_back(pm);
+            ptrs.push_back(pm + s->W);
+            dst.push_back(s->d_cnt[2 + 2 * (l - l0)]);
+            dst.push_back(s->d_cnt[3 + 2 * (l - l0)]);
+        }
+        KV_TRY(count_masks_async(s, (int)ptrs.size(), ptrs.data(), dst.data(),
+                                 (char *)s->h_pin + pass * count_batch_stride(s->W)));
+        s->scan_calls += 1;
+        const int64_t j_end = l1 < leaders.size() ? leaders[l1] : n_jobs;
+        int64_t group = -1;
+        for (int64_t j = leaders[l0]; j < j_end; ++j) {
+            if (reuse[j] == 0) ++group;
+            s->scm_cnt_a = dst[2 * group];
+            s->scm_cnt_b = dst[2 * group + 1];
+            s->scm_valid = true;
+            s->reuse_armed = true;
+            s->reuse_swap = reuse[j] == 2;
+            KV_TRY(scm_scan_async(s, nullptr, nullptr, n_pos[j], n_neg[j], p[j], util_block_size, n_blocks));
+            MiscLayout L = misc_layout(s->d_misc.p, n_blocks);
+            TieHeader *d_hdr = (TieHeader *)((char *)s->d_queue.p + (size_t)j * kQueueSlotBytes);
+            k_scm_select<<<1, 32, 0, s->stream>>>(L.blockmax, n_blocks, L.bm, L.tol, L.sel, d_hdr);
+            count_launch(s);
+            launch_exact_ties(s, n_blocks, d_hdr, (TieRec *)(d_hdr + 1), kQueueSlotRecs);
+        }
+    }
+    CU(cudaGetLastError());
+    return KV_OK;
+}
+
 extern "C" int kv_scm_queue_run(kv_shard *s, int64_t n_jobs, const uint64_t *masks, const int64_t *n_pos,
                                 const int64_t *n_neg, const double *p, const int32_t *reuse, int64_t util_block_size,
                                 double *best_utility, int64_t *n_found, int64_t *rule_idx, int64_t *pos_err,
                                 int64_t *neg_cover) {
     if (!s || !masks || !n_pos || !n_neg || !p || !reuse) return fail(KV_E_INVALID, "kv_scm_queue_run: null pointer");
     if (n_jobs <= 0) return fail(KV_E_INVALID, "kv_scm_queue_run: no jobs");
+    int64_t n_groups = 0;
+    for (int64_t j = 0; j < n_jobs; ++j) n_groups += reuse[j] == 0;
+    const int per = max_masks_per_pass(s->W);
+    static const bool no_multi = getenv("KOVER_B200_NO_MULTI") != nullptr;
+    if (n_groups >= 2 && reuse[0] == 0 && per >= 4 && !no_multi && s->col0 == 0 && s->n_cols == s->k_total) {
+        DeviceGuard g(s->device);
+        KV_TRY(scm_queue_run_batched(s, n_jobs, masks, n_pos, n_neg, p, reuse, util_block_size, per / 2));
+        return kv_scm_queue_collect(s, n_jobs, best_utility, n_found, rule_idx, pos_err, neg_cover);
+    }
     for (int64_t j = 0; j < n_jobs; ++j) {
         const uint64_t *pm = masks + (size_t)j * 2 * s->W, *nm = pm + s->W;
         KV_TRY(kv_scm_queue_push(s, j, n_jobs, pm, nm, n_pos[j], n_neg[j], p[j], util_block_size, reuse[j]));
@@ -2341,8 +2527,8 @@ static int scm_packet_async(kv_shard *s, const uint64_t *pos_mask, const uint64_
     count_launch(s);
     TieParams T;
     memset(&T, 0, sizeof T);
-    T.cnt0 = s->d_cnt[s->scm_swapped ? 1 : 0];
-    T.cnt1 = s->d_cnt[s->scm_swapped ? 0 : 1];
+    T.cnt0 = s->scm_swapped ? s->scm_cnt_b : s->scm_cnt_a;
+    T.cnt1 = s->scm_swapped ? s->scm_cnt_a : s->scm_cnt_b;
     T.segmax = s->d_segmax;
     T.n_cols = s->n_cols;
     T.ld = s->ld;

@@ -369,6 +369,42 @@ def test_grid_shares_matrix_passes():
         assert np.array_equal(g_[2], wp) and np.array_equal(g_[3], wn)
 
 
+@pytest.mark.parametrize("sorted_labels", [True, False], ids=["sorted", "interleaved"])
+@pytest.mark.parametrize("n_folds", [2, 5, 11])
+def test_grid_batches_distinct_mask_pairs(sorted_labels, n_folds):
+    """The fits of a cross-validation in lock-step: every fold is a DIFFERENT mask pair.  They are counted several
+    pairs per matrix pass (k_count_tma) and scored from the resident counts; results identical to independent
+    scans, ceil(pairs / 8) matrix passes instead of one per pair."""
+    seed, n, k = 11, 1300, 70000
+    P = synthetic_block(seed, n, 0, k)
+    y = synthetic_labels(seed, n, sorted_by_label=sorted_labels)
+    train = train_split(seed, n)
+    rs = np.random.RandomState(seed)
+    fold_of = rs.randint(0, n_folds, size=len(train))
+    rc = KmerRuleClassifications(P, n, devices=[0])
+    shard = rc._group.shards[0]
+    jobs = []
+    for f in range(n_folds + 1):
+        tr = train if f == n_folds else train[fold_of != f]
+        if f == 1:
+            tr = tr[tr >= 64 * 3]          # a fold whose masks leave whole packed rows empty
+        pos, neg = tr[y[tr] == 1], tr[y[tr] == 0]
+        for p_ in (0.5, 2.0):
+            jobs.append((p_, pos, neg))
+            jobs.append((p_, neg, pos))
+    bl = rs.choice(2 * k, size=500, replace=False)
+    want = [rc.best_utility_rules(p_, a, b, rule_blacklist=bl, util_block_size=30000) for p_, a, b in jobs]
+    before = shard.info()
+    got = rc.best_utility_rules_grid(jobs, rule_blacklist=bl, util_block_size=30000)
+    after = shard.info()
+    n_pairs = n_folds + 1
+    assert after.scan_calls - before.scan_calls == -(-n_pairs // 8)
+    assert after.rescore_calls - before.rescore_calls == len(jobs)
+    for w, g_ in zip(want, got):
+        assert w[0] == g_[0] and all(np.array_equal(a, b) for a, b in zip(w[1:], g_[1:]))
+    rc.close()
+
+
 # ---------------------------------------------------------------------------------- a9 / a11
 def tree_to_dict(node):
     d = {"depth": node.depth, "criterion_value": float(node.criterion_value),
