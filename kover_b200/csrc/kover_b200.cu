@@ -804,20 +804,50 @@ struct CountParams {
     uint32_t *cnt[MAX_MULTI];     // [ld] each; null = discard (padding mask)
 };
 
-template <int NM, int CW, int R, int S>
+// 3:2 carry-save compressor on 32 bit lanes: a + b + d = s + 2 c, two LOP3
+__device__ __forceinline__ void csa32(uint32_t &s, uint32_t &c, uint32_t a, uint32_t b, uint32_t d) {
+    s = a ^ b ^ d;
+    c = (a & b) | (d & (a ^ b));
+}
+// popcount(a) + popcount(b) + popcount(c) + popcount(d) of four (already masked) 64-bit words with 4 POPC instead
+// of 8: the eight 32-bit halves go through four carry-save compressors (8 LOP3 on the ALU pipe, which idles
+// while the 16-lane POPC pipe is the bottleneck), leaving two words of weight 1, one of weight 2, one of weight 4.
+__device__ __forceinline__ uint32_t popc4x64_csa(uint64_t a, uint64_t b, uint64_t c, uint64_t d) {
+    uint32_t s1, c1, s2, c2, s3, c3, s4, c4;
+    csa32(s1, c1, (uint32_t)a, (uint32_t)(a >> 32), (uint32_t)b);
+    csa32(s2, c2, (uint32_t)(b >> 32), (uint32_t)c, (uint32_t)(c >> 32));
+    csa32(s3, c3, s1, s2, (uint32_t)d);
+    csa32(s4, c4, c1, c2, c3);
+    return (__popc(s3) + __popc((uint32_t)(d >> 32))) + 2 * (__popc(s4) + 2 * __popc(c4));
+}
+
+// Mask staging: [group of 4 consecutive active rows][NM][4] so that a (group, mask) needs two 128-bit broadcast
+// reads; s_nz[group] has bit m set when mask m is non-zero on any of the group's rows.
+template <int NM, int CW, int R, int S, bool CSA>
 __global__ void __launch_bounds__((CW + 1) * 32, 1) k_count_tma(const CountParams P) {
-    static_assert(NM % 2 == 0, "masks are fetched two at a time");
+    static_assert(R % 4 == 0, "row groups must not straddle ring stages");
     extern __shared__ __align__(128) unsigned char smem_tma[];
     constexpr int ROW_BYTES = CW * 32 * 16;
     constexpr int TC = CW * 64;
     const int n_act = P.n_act;
+    const int n_grp = (n_act + 3) >> 2;
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_tma);
     uint64_t *empty = full + S;
     uint64_t *s_m = empty + S;                               // 16-byte aligned: 2*S*8 is a multiple of 16
-    uint32_t *s_row = reinterpret_cast<uint32_t *>(s_m + (size_t)n_act * NM);
-    unsigned char *ring = smem_tma + ((size_t)(2 * S) * 8 + (size_t)n_act * (NM * 8 + 4) + 127) / 128 * 128;
-    for (int i = threadIdx.x; i < n_act * NM; i += blockDim.x) s_m[i] = P.rec_m[i];
-    for (int i = threadIdx.x; i < n_act; i += blockDim.x) s_row[i] = P.rec_row[i];
+    uint32_t *s_row = reinterpret_cast<uint32_t *>(s_m + (size_t)n_grp * NM * 4);
+    uint32_t *s_nz = s_row + n_grp * 4;
+    unsigned char *ring = smem_tma + ((size_t)(2 * S) * 8 + (size_t)n_grp * (NM * 32 + 20) + 127) / 128 * 128;
+    for (int i = threadIdx.x; i < n_grp * NM * 4; i += blockDim.x) s_m[i] = P.rec_m[i];
+    for (int i = threadIdx.x; i < n_grp * 4; i += blockDim.x) s_row[i] = P.rec_row[i];
+    __syncthreads();
+    for (int g = threadIdx.x; g < n_grp; g += blockDim.x) {
+        uint32_t nz = 0;
+        for (int m = 0; m < NM; ++m) {
+            const uint64_t *q = s_m + ((size_t)g * NM + m) * 4;
+            if (q[0] | q[1] | q[2] | q[3]) nz |= 1u << m;
+        }
+        s_nz[g] = nz;
+    }
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) {
             mbar_init(full + s, 1);
@@ -862,20 +892,38 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_count_tma(const CountParam
             const int rows_here = min(R, n_act - b * R);
             mbar_wait(full + s, ph);
             const unsigned char *st = ring + (size_t)s * R * ROW_BYTES + threadIdx.x * 16;
-#pragma unroll 2
-            for (int r = 0; r < rows_here; ++r) {
-                const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(st + r * ROW_BYTES);
-                const ulonglong2 *mk = reinterpret_cast<const ulonglong2 *>(s_m + (size_t)(b * R + r) * NM);
+#pragma unroll 1
+            for (int g = 0; g * 4 < rows_here; ++g) {
+                const int grp = ((b * R) >> 2) + g;
+                const uint32_t nz = s_nz[grp];
+                const ulonglong2 *mk = reinterpret_cast<const ulonglong2 *>(s_m + (size_t)grp * NM * 4);
+                const unsigned char *sg = st + g * 4 * ROW_BYTES;
+                if (CSA && g * 4 + 4 <= rows_here) {
+                    const ulonglong2 v0 = *reinterpret_cast<const ulonglong2 *>(sg);
+                    const ulonglong2 v1 = *reinterpret_cast<const ulonglong2 *>(sg + ROW_BYTES);
+                    const ulonglong2 v2 = *reinterpret_cast<const ulonglong2 *>(sg + 2 * ROW_BYTES);
+                    const ulonglong2 v3 = *reinterpret_cast<const ulonglong2 *>(sg + 3 * ROW_BYTES);
 #pragma unroll
-                for (int m = 0; m < NM; m += 2) {
-                    const ulonglong2 mm = mk[m >> 1];          // broadcast read
-                    if (mm.x) {                                // warp-uniform
-                        cx[m] += __popcll(v.x & mm.x);
-                        cy[m] += __popcll(v.y & mm.x);
+                    for (int m = 0; m < NM; ++m) {
+                        if (nz & (1u << m)) {                      // warp-uniform
+                            const ulonglong2 ma = mk[2 * m], mb = mk[2 * m + 1];
+                            cx[m] += popc4x64_csa(v0.x & ma.x, v1.x & ma.y, v2.x & mb.x, v3.x & mb.y);
+                            cy[m] += popc4x64_csa(v0.y & ma.x, v1.y & ma.y, v2.y & mb.x, v3.y & mb.y);
+                        }
                     }
-                    if (mm.y) {
-                        cx[m + 1] += __popcll(v.x & mm.y);
-                        cy[m + 1] += __popcll(v.y & mm.y);
+                } else {
+                    const int rows_g = min(4, rows_here - g * 4);
+                    const uint64_t *mk1 = reinterpret_cast<const uint64_t *>(mk);
+                    for (int r = 0; r < rows_g; ++r) {
+                        const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(sg + r * ROW_BYTES);
+#pragma unroll
+                        for (int m = 0; m < NM; ++m) {
+                            const uint64_t mm = mk1[m * 4 + r];
+                            if (mm) {                              // warp-uniform
+                                cx[m] += __popcll(v.x & mm);
+                                cy[m] += __popcll(v.y & mm);
+                            }
+                        }
                     }
                 }
             }
@@ -1831,24 +1879,30 @@ extern "C" int kv_risk_map(kv_shard *s, const uint32_t *lut_kmer, const uint32_t
 }
 
 // ---- k_count_tma launch ------------------------------------------------------------------------
-template <int NM, int R, int S>
-static int launch_count_variant(kv_shard *s, const CountParams &P, size_t smem) {
+template <int NM, int R, int S, bool CSA>
+static int launch_count_variant2(kv_shard *s, const CountParams &P, size_t smem) {
     constexpr int CW = 16;
     static thread_local int attr_device = -1;
     static thread_local size_t attr_bytes = 0;
     if (attr_device != s->device || attr_bytes < smem) {
-        CU(cudaFuncSetAttribute(k_count_tma<NM, CW, R, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(cudaFuncSetAttribute(k_count_tma<NM, CW, R, S, CSA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_device = s->device;
         attr_bytes = smem;
     }
     const long long n_tiles = s->ld / (CW * 64);
     const int grid = (int)std::max(1ll, std::min<long long>((long long)s->sm_count, n_tiles));
-    k_count_tma<NM, CW, R, S><<<grid, (CW + 1) * 32, smem, s->stream>>>(P);
+    k_count_tma<NM, CW, R, S, CSA><<<grid, (CW + 1) * 32, smem, s->stream>>>(P);
     return KV_OK;
+}
+template <int NM, int R, int S>
+static int launch_count_variant(kv_shard *s, const CountParams &P, size_t smem) {
+    static const bool plain = getenv("KOVER_B200_COUNT_PLAIN") != nullptr;    // measurement knob (profiles/README.md)
+    return plain ? launch_count_variant2<NM, R, S, false>(s, P, smem) : launch_count_variant2<NM, R, S, true>(s, P, smem);
 }
 
 static size_t count_smem_bytes(int n_act, int nm, int R, int S) {
-    return ((size_t)(2 * S) * 8 + (size_t)n_act * (nm * 8 + 4) + 127) / 128 * 128 + (size_t)S * R * 16 * 512;
+    const size_t n_grp = ((size_t)n_act + 3) / 4;
+    return ((size_t)(2 * S) * 8 + n_grp * ((size_t)nm * 32 + 20) + 127) / 128 * 128 + (size_t)S * R * 16 * 512;
 }
 
 template <int NM>
@@ -1874,7 +1928,8 @@ static int padded_nm(int nm) {
 // masks per pass so that the [row][mask] staging of W packed rows fits beside the smallest ring
 static int max_masks_per_pass(long long W) {
     const long long budget = 227 * 1024 - 2048 - 64 * 1024 - 256;
-    long long nm = (budget / std::max<long long>(W, 1) - 4) / 8;
+    const long long n_grp = (std::max<long long>(W, 1) + 3) / 4;
+    long long nm = (budget / n_grp - 20) / 32;
     nm = std::min<long long>(nm, MAX_MULTI);
     static const int sizes[] = {16, 12, 8, 6, 4, 2};
     for (int v : sizes)
@@ -1884,7 +1939,7 @@ static int max_masks_per_pass(long long W) {
 
 // staging bytes of one pass (row records [n_act][NM] u64 + rows u32), rounded so that consecutive passes stay aligned
 static size_t count_batch_stride(long long W) {
-    return ((size_t)W * (8 * (size_t)MAX_MULTI + 4) + 127) / 128 * 128;
+    return (((size_t)W + 3) / 4 * (32 * (size_t)MAX_MULTI + 16) + 127) / 128 * 128;
 }
 static size_t count_pin_bytes(long long W, int n_masks) {
     const int per = std::max(2, max_masks_per_pass(W));
@@ -1906,24 +1961,27 @@ static int count_masks_async(kv_shard *s, int n_masks, const uint64_t *const *ma
     for (int m0 = 0; m0 < n_masks; m0 += per) {
         const int nm = std::min(per, n_masks - m0);
         const int nmp = padded_nm(nm);
-        int n_act = 0;
+        // active rows (any mask non-zero), ordered by which masks touch them so that the groups of four rows
+        // the kernel skips masks on are as homogeneous as possible (stable: ties keep the matrix order)
+        std::vector<std::pair<uint32_t, uint32_t>> act;      // (pattern, row)
         for (long long w = 0; w < W; ++w) {
-            bool any = false;
-            for (int m = 0; m < nm; ++m) any |= masks[m0 + m][w] != 0;
-            n_act += any;
+            uint32_t pat = 0;
+            for (int m = 0; m < nm; ++m) pat |= (uint32_t)(masks[m0 + m][w] != 0) << m;
+            if (pat) act.emplace_back(pat, (uint32_t)w);
         }
+        std::stable_sort(act.begin(), act.end(),
+                         [](const std::pair<uint32_t, uint32_t> &a, const std::pair<uint32_t, uint32_t> &b) { return a.first < b.first; });
+        const int n_act = (int)act.size();
+        const int n_grp = (n_act + 3) / 4;
         uint64_t *pm = (uint64_t *)(pin + off);
-        uint32_t *prow = (uint32_t *)(pm + (size_t)n_act * nmp);
-        int i = 0;
-        for (long long w = 0; w < W; ++w) {
-            bool any = false;
-            for (int m = 0; m < nm; ++m) any |= masks[m0 + m][w] != 0;
-            if (!any) continue;
-            for (int m = 0; m < nm; ++m) pm[(size_t)i * nmp + m] = masks[m0 + m][w];
-            for (int m = nm; m < nmp; ++m) pm[(size_t)i * nmp + m] = 0;
-            prow[i++] = (uint32_t)w;
+        uint32_t *prow = (uint32_t *)(pm + (size_t)n_grp * nmp * 4);
+        memset(pm, 0, (size_t)n_grp * nmp * 32 + (size_t)n_grp * 16);
+        for (int i = 0; i < n_act; ++i) {
+            const uint32_t w = act[i].second;
+            for (int m = 0; m < nm; ++m) pm[((size_t)(i >> 2) * nmp + m) * 4 + (i & 3)] = masks[m0 + m][w];
+            prow[i] = w;
         }
-        const size_t rec_bytes = (size_t)n_act * (8 * nmp + 4);
+        const size_t rec_bytes = (size_t)n_grp * ((size_t)nmp * 32 + 16);
         char *d_rec = (char *)s->d_rec.p + off;
         if (n_act) CU(cudaMemcpyAsync(d_rec, pin + off, rec_bytes, cudaMemcpyHostToDevice, s->stream));
         CountParams P;
@@ -1931,7 +1989,7 @@ static int count_masks_async(kv_shard *s, int n_masks, const uint64_t *const *ma
         P.mat = s->d_mat;
         P.ld = s->ld;
         P.rec_m = (const uint64_t *)d_rec;
-        P.rec_row = (const uint32_t *)(P.rec_m + (size_t)n_act * nmp);
+        P.rec_row = (const uint32_t *)(P.rec_m + (size_t)n_grp * nmp * 4);
         P.n_act = n_act;
         for (int m = 0; m < nm; ++m) P.cnt[m] = dst[m0 + m];
         int rc = KV_OK;
