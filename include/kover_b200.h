@@ -227,6 +227,20 @@ int kv_gini_ties(kv_shard *s, double min_score, int64_t capacity, int64_t *rule_
 int kv_gini_best_split(kv_shard *s, int n_classes, const uint64_t *class_masks, const double *altered_prior,
                        const double *n_total, const int64_t *n_node, double *min_score, int64_t capacity,
                        int64_t *rule_idx, int64_t *n_found);
+/* A whole tree level at once (cart.py:260-339 visits the nodes of a level one after the other; their example
+ * sets are disjoint and their scans independent): the split search of n_nodes two-class nodes, class masks
+ * [n_nodes][2][W], n_node [n_nodes][2], the class masks of up to 8 nodes counted per matrix pass.  Returns per
+ * node the minimum score over the shard's presence rules and the number of rules achieving it exactly;
+ * kv_gini_level_fetch then copies node i's rule indices (GLOBAL, ascending) into a caller buffer of at least
+ * n_found[i] entries.  The results stay valid until the next kv_gini_level call on the shard. */
+int kv_gini_level(kv_shard *s, int64_t n_nodes, const uint64_t *class_masks, const double *altered_prior,
+                  const double *n_total, const int64_t *n_node, double *min_score, int64_t *n_found);
+int kv_gini_level_fetch(kv_shard *s, int64_t node, int64_t *rule_idx, int64_t capacity);
+/* Zero-copy variant: *rule_idx points at node i's n_found indices inside the shard's pinned result arena (tie sets
+ * of small nodes run to millions of rules; a second copy into fresh pageable memory costs more than the scan).
+ * READ-ONLY, valid until the next kv_gini_level / kv_destroy on the shard -- the one library-owned pointer this
+ * ABI hands out. */
+int kv_gini_level_result(kv_shard *s, int64_t node, const int64_t **rule_idx, int64_t *n_found);
 /* The split scores themselves (testing / callers that want rules_criterion): out[n_cols]. */
 int kv_gini_scores(kv_shard *s, double *out);
 

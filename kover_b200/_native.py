@@ -76,6 +76,10 @@ SYMBOLS = {
                                           _c_i64, _c_p, ctypes.POINTER(_c_i64)]),
     "kv_gini_ties": (ctypes.c_int, [_c_p, ctypes.c_double, _c_i64, _c_p, ctypes.POINTER(_c_i64)]),
     "kv_gini_scores": (ctypes.c_int, [_c_p, _c_p]),
+    "kv_gini_level": (ctypes.c_int, [_c_p, _c_i64, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p]),
+    "kv_gini_level_fetch": (ctypes.c_int, [_c_p, _c_i64, _c_p, _c_i64]),
+    "kv_gini_level_result": (ctypes.c_int, [_c_p, _c_i64, ctypes.POINTER(ctypes.POINTER(ctypes.c_int64)),
+                                            ctypes.POINTER(_c_i64)]),
 }
 
 _lib = None
@@ -425,6 +429,32 @@ class Shard(object):
                 continue
             check(rc)
             return idx[:n.value]
+
+    def gini_level(self, node_masks, altered_prior, n_total, n_node):
+        """Split search of several two-class nodes, up to 8 nodes per matrix pass.  node_masks [n_nodes, 2, W],
+        n_node [n_nodes, 2] -> [(min score over this shard, rule indices achieving it, ascending)] per node."""
+        masks = np.ascontiguousarray(node_masks, dtype=np.uint64)
+        assert masks.ndim == 3 and masks.shape[1] == 2 and masks.shape[2] == self.n_words
+        pri = np.ascontiguousarray(altered_prior, dtype=np.float64)
+        tot = np.ascontiguousarray(n_total, dtype=np.float64)
+        nn = np.ascontiguousarray(n_node, dtype=np.int64)
+        assert pri.shape == (2,) and tot.shape == (2,) and nn.shape == (masks.shape[0], 2)
+        mins = np.empty(masks.shape[0], dtype=np.float64)
+        found = np.empty(masks.shape[0], dtype=np.int64)
+        check(self._lib.kv_gini_level(self._h, masks.shape[0], ptr(masks), ptr(pri), ptr(tot), ptr(nn), ptr(mins),
+                                      ptr(found)))
+        # read-only views into the shard's pinned result arena, valid until the next gini_level on this shard
+        out = []
+        for i in range(masks.shape[0]):
+            if found[i] == 0:
+                out.append((float(mins[i]), np.zeros(0, dtype=np.int64)))
+                continue
+            p_idx, n = ctypes.POINTER(ctypes.c_int64)(), _c_i64(0)
+            check(self._lib.kv_gini_level_result(self._h, i, ctypes.byref(p_idx), ctypes.byref(n)))
+            idx = np.ctypeslib.as_array(p_idx, shape=(int(n.value),))
+            idx.flags.writeable = False
+            out.append((float(mins[i]), idx))
+        return out
 
     def gini_scores(self):
         out = np.empty(self.n_cols, dtype=np.float64)

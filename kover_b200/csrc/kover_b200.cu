@@ -85,7 +85,6 @@ extern "C" int kv_device_count(int *n) {
 // ------------------------------------------------------------------------------------------------
 static constexpr int TILE_COLS = 512;    // columns per tile of the direct-load kernels: 256 threads x one 128-bit load
 static constexpr int LD_ALIGN = 1024;    // row pitch granularity: a multiple of every tile width (512 / 1024 columns)
-static constexpr int SCAN_THREADS = 256;
 static constexpr int MAX_CLASSES = 64;
 
 // ------------------------------------------------------------------------------------------------
@@ -955,6 +954,9 @@ struct GiniParams {
     unsigned long long *counter;
     long long cap;
     double *scores;                 // MODE_SCORES
+    // two classes, small node: score of every (count 0, count 1) pair, [n_node0 + 1][table_stride], or null
+    const double *table;
+    int table_stride;
 };
 enum { GINI_MIN = 0, GINI_TIES = 1, GINI_SCORES = 2 };
 
@@ -1048,9 +1050,41 @@ __global__ void __launch_bounds__(256) k_gini(const GiniParams P) {
     }
 }
 
+// A node with few examples has few distinct (count 0, count 1) pairs: the split score -- 8 IEEE double divisions
+// per column -- is then tabulated once per node (k_gini2_table) and looked up.  Same values bit for bit: the table
+// entries are computed by the same gini_score arithmetic.
+static constexpr int GINI2_TABLE_MAX = 4096;
+
+__global__ void __launch_bounds__(256) k_gini2_table(const GiniParams P, double *table) {
+    const int n0 = (int)P.n_node[0] + 1, stride = P.table_stride;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n0 * stride; e += gridDim.x * blockDim.x) {
+        const double l[2] = {(double)(e / stride), (double)(e % stride)};
+        const double r[2] = {P.n_node[0] - l[0], P.n_node[1] - l[1]};
+        double v = INFINITY;                                           // cart.py:158-159
+        if (l[0] + l[1] != 0.0 && r[0] + r[1] != 0.0) v = __dadd_rn(gini_child<2>(l, P, 2), gini_child<2>(r, P, 2));
+        table[e] = v;
+    }
+}
+
+__device__ __forceinline__ void gini2_table_load(const GiniParams &P, double *s_tab) {
+    if (P.table) {
+        const int n = ((int)P.n_node[0] + 1) * P.table_stride;
+        for (int e = threadIdx.x; e < n; e += blockDim.x) s_tab[e] = P.table[e];
+        __syncthreads();
+    }
+}
+
+__device__ __forceinline__ double gini2_score_any(long long col, const GiniParams &P, const double *s_tab) {
+    if (!P.table) return gini_score<2>(col, P);
+    if (P.black_pres && ((P.black_pres[col >> 5] >> (col & 31)) & 1u)) return INFINITY;   // cart.py:231
+    return s_tab[P.cnt[0][col] * (uint32_t)P.table_stride + P.cnt[1][col]];
+}
+
 // Tie collection when the scan left exact per-segment minima: one lane screens one 64-column segment
 // (156 k segments for 10 M k-mers), the warp then rescans only the segments whose minimum IS the target.
 __global__ void __launch_bounds__(256) k_gini2_ties_seg(const GiniParams P) {
+    __shared__ double s_tab[GINI2_TABLE_MAX];
+    gini2_table_load(P, s_tab);
     double target = P.min_score;
     if (P.min_ptr) {
         const unsigned long long v = *reinterpret_cast<const unsigned long long *>(P.min_ptr);
@@ -1076,7 +1110,7 @@ __global__ void __launch_bounds__(256) k_gini2_ties_seg(const GiniParams P) {
             for (int j = 0; j < 2; ++j) {
                 const long long col = ((sb + src) << 6) + lane + 32 * j;
                 if (col >= P.n_cols) continue;
-                const bool hit = gini_score<2>(col, P) == target;
+                const bool hit = gini2_score_any(col, P, s_tab) == target;
                 // one atomic per warp: a node with few examples can tie on most of the k-mers
                 const unsigned hits = __ballot_sync(__activemask(), hit);
                 if (hit) {
@@ -1089,6 +1123,39 @@ __global__ void __launch_bounds__(256) k_gini2_ties_seg(const GiniParams P) {
                 }
             }
         }
+    }
+}
+
+// Two-class Gini scores from RESIDENT counts (the nodes of a CART level are counted several per matrix pass by
+// k_count_tma): the minimum split score of the node and the exact minima of the 64-column segments, i.e. what
+// k_scan_tma<EPI_GINI2> leaves behind, at 8 bytes per column.  One warp per segment: lane l scores columns l, l+32.
+__global__ void __launch_bounds__(256) k_gini2_counts(const GiniParams P, unsigned long long *segmin_out) {
+    __shared__ unsigned long long s_red[8];
+    __shared__ double s_tab[GINI2_TABLE_MAX];
+    gini2_table_load(P, s_tab);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long n_seg = (P.n_cols + 63) >> 6;
+    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    double mn = INFINITY;
+    for (long long g = warp0; g < n_seg; g += n_warps) {
+        double sm = INFINITY;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const long long col = (g << 6) + lane + 32 * j;
+            if (col < P.n_cols) sm = fmin(sm, gini2_score_any(col, P, s_tab));
+        }
+        const unsigned long long seg = warp_min_enc(enc_f64(sm));
+        if (lane == 0) segmin_out[g] = seg;
+        mn = fmin(mn, sm);
+    }
+    const unsigned long long v = warp_min_enc(enc_f64(mn));
+    if (lane == 0) s_red[warp] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long m = s_red[0];
+        for (int w = 1; w < 8; ++w) m = s_red[w] < m ? s_red[w] : m;
+        atomicMin(P.min_enc, m);
     }
 }
 
@@ -1252,6 +1319,11 @@ struct kv_shard {
     long long risk_n = 0;
     GiniParams gini;
 
+    DevBuf d_level;                           // kv_gini_level: per-node minima, counters, tie slots, segment minima
+    int64_t *h_level = nullptr;               // pinned arena: the tie lists of the last kv_gini_level, node after node
+    size_t h_level_cap = 0, h_level_used = 0; // in entries
+    std::vector<std::pair<size_t, size_t>> level_span;   // (offset, count) of every node in the arena
+
     double last_kernel_ms = 0.0, scan_ms_total = 0.0;
     long long last_launches = 0, total_launches = 0, scan_calls = 0, rescore_calls = 0;
 };
@@ -1304,11 +1376,6 @@ static int ensure_counts(kv_shard *s, int n) {
 static inline void count_launch(kv_shard *s, int n = 1) {
     s->last_launches += n;
     s->total_launches += n;
-}
-
-static int scan_grid(kv_shard *s) {
-    long long g = (long long)s->sm_count * s->scan_ctas_per_sm;
-    return (int)std::max(1ll, std::min(g, s->n_tiles));
 }
 
 extern "C" int kv_create(int device, int64_t n_examples, int64_t n_kmers_total, int64_t col0, int64_t n_cols,
@@ -1366,12 +1433,13 @@ extern "C" int kv_destroy(kv_shard *s) {
     p2p_destroy(s->p2p);
     cudaFree(s->d_mat);
     for (auto p : s->d_cnt) cudaFree(p);
-    for (DevBuf *b : {&s->d_rec, &s->d_misc, &s->d_ties, &s->d_stage, &s->d_sort_tmp, &s->d_sort_io, &s->d_queue})
+    for (DevBuf *b : {&s->d_rec, &s->d_misc, &s->d_ties, &s->d_stage, &s->d_sort_tmp, &s->d_sort_io, &s->d_queue, &s->d_level})
         if (b->p) cudaFree(b->p);
     if (s->d_black_pres) cudaFree(s->d_black_pres);
     if (s->d_black_abs) cudaFree(s->d_black_abs);
     if (s->d_segmax) cudaFree(s->d_segmax);
     if (s->h_pin) cudaFreeHost(s->h_pin);
+    if (s->h_level) cudaFreeHost(s->h_level);
     for (int i = 0; i < 2; ++i) {
         if (s->h_up[i]) cudaFreeHost(s->h_up[i]);
         if (s->ev_up[i]) cudaEventDestroy(s->ev_up[i]);
@@ -1653,12 +1721,6 @@ static void fill_scan2(kv_shard *s, Scan2Params &P, int n_act) {
     P.ubs = 1;
 }
 
-static int check_smem(size_t bytes) {
-    if (bytes > 200 * 1024)
-        return fail(KV_E_INVALID, "too many active packed rows for one scan (shared-memory staging limit)");
-    return KV_OK;
-}
-
 // Scan-kernel variants <consumer warps, rows per stage, stages, CTAs per SM>, measured on B200 by
 // tools/scan_sweep.cu (profiles/README.md): variant 0 is best when each packed row carries one
 // non-zero mask word (label-sorted datasets: 2 popc per streamed word), variant 1 when most rows
@@ -1801,15 +1863,18 @@ __global__ void k_split_tierecs(const TieRec *recs, long long n, long long *keys
 }
 
 // sorts keys (and vals if given) ascending; results land in keys_out / vals_out (device)
+// keys are rule indices < 2 * k_total: the radix sort only visits the bits they can use
 static int device_sort(kv_shard *s, const long long *keys_in, long long *keys_out, const unsigned long long *vals_in,
                        unsigned long long *vals_out, long long n) {
+    int end_bit = 1;
+    while (end_bit < 63 && (1ll << end_bit) <= 2 * s->k_total) ++end_bit;
     size_t tmp = 0;
-    if (vals_in) CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp, keys_in, keys_out, vals_in, vals_out, (int)n, 0, 64, s->stream));
-    else CU(cub::DeviceRadixSort::SortKeys(nullptr, tmp, keys_in, keys_out, (int)n, 0, 64, s->stream));
+    if (vals_in) CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp, keys_in, keys_out, vals_in, vals_out, (int)n, 0, end_bit, s->stream));
+    else CU(cub::DeviceRadixSort::SortKeys(nullptr, tmp, keys_in, keys_out, (int)n, 0, end_bit, s->stream));
     KV_TRY(ensure(s->d_sort_tmp, tmp + 64));
     if (vals_in)
-        CU(cub::DeviceRadixSort::SortPairs(s->d_sort_tmp.p, tmp, keys_in, keys_out, vals_in, vals_out, (int)n, 0, 64, s->stream));
-    else CU(cub::DeviceRadixSort::SortKeys(s->d_sort_tmp.p, tmp, keys_in, keys_out, (int)n, 0, 64, s->stream));
+        CU(cub::DeviceRadixSort::SortPairs(s->d_sort_tmp.p, tmp, keys_in, keys_out, vals_in, vals_out, (int)n, 0, end_bit, s->stream));
+    else CU(cub::DeviceRadixSort::SortKeys(s->d_sort_tmp.p, tmp, keys_in, keys_out, (int)n, 0, end_bit, s->stream));
     count_launch(s, 4);
     return KV_OK;
 }
@@ -3052,6 +3117,172 @@ extern "C" int kv_gini_best_split(kv_shard *s, int n_classes, const uint64_t *cl
     const int rc = gini_ties_impl(s, true, 0.0, capacity, rule_idx, n_found, min_score);
     if (n_classes == 2 && (rc == KV_OK || rc == KV_E_OVERFLOW)) finish_scan_timing(s);
     return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// CART level: the split search of SEVERAL nodes (two classes) with their class masks counted 8 nodes per
+// matrix pass.  Nodes of a tree level hold disjoint example sets, so most (packed row, node) mask words are
+// empty deep in the tree and are skipped; a level costs about one pass per 8 nodes instead of one per node.
+// Per node: k_gini2_counts (minimum + segment minima from the resident counts) and k_gini2_ties_seg.
+// ------------------------------------------------------------------------------------------------
+static constexpr int kLevelNodesPerPass = MAX_MULTI / 2;
+static constexpr long long kLevelSlotIdx = 1024;            // tie indices per node kept in the first-read slot
+
+// room for `need` entries in the pinned result arena, keeping what it holds; the shard's stream must be idle
+static int level_arena_reserve(kv_shard *s, size_t need) {
+    if (need <= s->h_level_cap) return KV_OK;
+    const size_t want = std::max({need, s->h_level_cap * 2, (size_t)1 << 20});
+    int64_t *p = nullptr;
+    CU(cudaMallocHost(&p, want * 8));
+    if (s->h_level_used) memcpy(p, s->h_level, s->h_level_used * 8);
+    if (s->h_level) cudaFreeHost(s->h_level);
+    s->h_level = p;
+    s->h_level_cap = want;
+    return KV_OK;
+}
+
+extern "C" int kv_gini_level(kv_shard *s, int64_t n_nodes, const uint64_t *class_masks, const double *altered_prior,
+                             const double *n_total, const int64_t *n_node, double *min_score, int64_t *n_found) {
+    if (!s || !class_masks || !altered_prior || !n_total || !n_node || !min_score || !n_found)
+        return fail(KV_E_INVALID, "kv_gini_level: null pointer");
+    if (n_nodes <= 0) return fail(KV_E_INVALID, "kv_gini_level: no nodes");
+    DeviceGuard g(s->device);
+    s->last_launches = 0;
+    s->scm_valid = s->gini_valid = false;
+    s->level_span.clear();
+    s->h_level_used = 0;
+    const int per = std::min(kLevelNodesPerPass, max_masks_per_pass(s->W) / 2);
+    if (per < 1) return fail(KV_E_INVALID, "kv_gini_level: too many packed rows for a multi-mask pass");
+    const long long W = s->W, n_seg_ld = s->ld / 64;
+    KV_TRY(ensure_counts(s, 2 + 2 * per));
+    // d_level: min enc [per] | counter [per] | ties [per][kLevelSlotIdx] | segmin [per][ld/64] | score tables [per][4096]
+    const size_t level_bytes = (size_t)per * 16 + (size_t)per * kLevelSlotIdx * 8 + (size_t)per * n_seg_ld * 8 +
+                               (size_t)per * GINI2_TABLE_MAX * 8;
+    KV_TRY(ensure(s->d_level, level_bytes));
+    unsigned long long *d_min = (unsigned long long *)s->d_level.p, *d_cntr = d_min + per;
+    long long *d_ties = (long long *)(d_cntr + per);
+    unsigned long long *d_segmin = (unsigned long long *)(d_ties + (size_t)per * kLevelSlotIdx);
+    double *d_tables = (double *)(d_segmin + (size_t)per * n_seg_ld);
+    const size_t hdr_bytes = (size_t)per * 16 + (size_t)per * kLevelSlotIdx * 8;
+    KV_TRY(ensure_pinned(s, count_batch_stride(W) + hdr_bytes));
+    CU(cudaStreamSynchronize(s->stream));
+    char *pin_rec = (char *)s->h_pin;
+    const unsigned long long *h_hdr = (const unsigned long long *)((char *)s->h_pin + count_batch_stride(W));
+    const long long n_seg = (s->n_cols + 63) / 64;
+    const unsigned grid_score = (unsigned)std::max<long long>(1, std::min<long long>((n_seg + 7) / 8, (long long)s->sm_count * 8));
+    const unsigned grid_ties = (unsigned)std::max<long long>(1, std::min<long long>((n_seg + 255) / 256, (long long)s->sm_count * 4));
+    float scan_ms = 0;
+    for (int64_t b0 = 0; b0 < n_nodes; b0 += per) {
+        const int nb = (int)std::min<int64_t>(per, n_nodes - b0);
+        std::vector<const uint64_t *> ptrs;
+        std::vector<uint32_t *> dst;
+        for (int i = 0; i < nb; ++i) {
+            const uint64_t *m = class_masks + (size_t)(b0 + i) * 2 * W;
+            ptrs.push_back(m);
+            ptrs.push_back(m + W);
+            dst.push_back(s->d_cnt[2 + 2 * i]);
+            dst.push_back(s->d_cnt[3 + 2 * i]);
+        }
+        KV_TRY(count_masks_async(s, 2 * nb, ptrs.data(), dst.data(), pin_rec));
+        s->scan_calls += 1;
+        CU(cudaMemsetAsync(d_min, 0xFF, (size_t)per * 8, s->stream));
+        CU(cudaMemsetAsync(d_cntr, 0, (size_t)per * 8, s->stream));
+        std::vector<GiniParams> params((size_t)nb);
+        for (int i = 0; i < nb; ++i) {
+            GiniParams &G = params[i];
+            memset(&G, 0, sizeof G);
+            G.n_classes = 2;
+            for (int c = 0; c < 2; ++c) {
+                G.cnt[c] = dst[2 * i + c];
+                G.prior[c] = altered_prior[c];
+                G.n_total[c] = n_total[c];
+                G.n_node[c] = (double)n_node[(b0 + i) * 2 + c];
+            }
+            G.n_cols = s->n_cols;
+            G.col0 = s->col0;
+            G.black_pres = s->have_black ? s->d_black_pres : nullptr;
+            G.min_enc = d_min + i;
+            G.min_ptr = (const double *)(d_min + i);
+            G.counter = d_cntr + i;
+            G.segmin = d_segmin + (size_t)i * n_seg_ld;
+            G.out_idx = d_ties + (size_t)i * kLevelSlotIdx;
+            G.cap = kLevelSlotIdx;
+            const long long pairs = (n_node[(b0 + i) * 2] + 1) * (n_node[(b0 + i) * 2 + 1] + 1);
+            if (pairs <= GINI2_TABLE_MAX) {
+                G.table_stride = (int)n_node[(b0 + i) * 2 + 1] + 1;
+                k_gini2_table<<<(unsigned)((pairs + 255) / 256), 256, 0, s->stream>>>(G, d_tables + (size_t)i * GINI2_TABLE_MAX);
+                count_launch(s);
+                G.table = d_tables + (size_t)i * GINI2_TABLE_MAX;
+            }
+            k_gini2_counts<<<grid_score, 256, 0, s->stream>>>(G, d_segmin + (size_t)i * n_seg_ld);
+            k_gini2_ties_seg<<<grid_ties, 256, 0, s->stream>>>(G);
+            count_launch(s, 2);
+        }
+        CU(cudaMemcpyAsync((void *)h_hdr, d_min, hdr_bytes, cudaMemcpyDeviceToHost, s->stream));
+        CU(stream_sync_spin(s->stream));
+        CU(cudaGetLastError());
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, s->ev0, s->ev1) == cudaSuccess) scan_ms += ms;
+        const long long *h_ties = (const long long *)(h_hdr + 2 * per);
+        size_t batch_total = 0, biggest = 0;
+        for (int i = 0; i < nb; ++i) {
+            batch_total += (size_t)h_hdr[per + i];
+            if ((long long)h_hdr[per + i] > kLevelSlotIdx) biggest = std::max(biggest, (size_t)h_hdr[per + i]);
+        }
+        KV_TRY(level_arena_reserve(s, s->h_level_used + batch_total));
+        if (biggest * 16 > s->d_sort_io.bytes) KV_TRY(ensure(s->d_sort_io, std::max(biggest * 16, s->d_sort_io.bytes * 2)));
+        bool pending = false;
+        for (int i = 0; i < nb; ++i) {
+            const long long found = (long long)h_hdr[per + i];
+            min_score[b0 + i] = dec_f64_min(h_hdr[i]);
+            n_found[b0 + i] = found;
+            int64_t *out = s->h_level + s->h_level_used;
+            s->level_span.emplace_back(s->h_level_used, (size_t)found);
+            s->h_level_used += (size_t)found;
+            if (found == 0) continue;
+            if (found <= kLevelSlotIdx) {
+                memcpy(out, h_ties + (size_t)i * kLevelSlotIdx, (size_t)found * 8);
+                std::sort(out, out + found);
+                continue;
+            }
+            // a node with few examples ties on a large share of the k-mers: its counts are still resident, collect
+            // again into a buffer of the now known size, sort on the device, copy into the pinned arena
+            GiniParams G = params[i];
+            long long *raw = (long long *)s->d_sort_io.p, *sorted = raw + found;
+            G.out_idx = raw;
+            G.cap = found;
+            CU(cudaMemsetAsync(d_cntr + i, 0, 8, s->stream));
+            k_gini2_ties_seg<<<grid_ties, 256, 0, s->stream>>>(G);
+            count_launch(s);
+            KV_TRY(device_sort(s, raw, sorted, nullptr, nullptr, found));
+            CU(cudaMemcpyAsync(out, sorted, (size_t)found * 8, cudaMemcpyDeviceToHost, s->stream));
+            pending = true;
+        }
+        if (pending) {
+            CU(stream_sync_spin(s->stream));
+            CU(cudaGetLastError());
+        }
+    }
+    s->last_kernel_ms = scan_ms;
+    s->scan_ms_total += scan_ms;
+    return KV_OK;
+}
+
+extern "C" int kv_gini_level_result(kv_shard *s, int64_t node, const int64_t **rule_idx, int64_t *n_found) {
+    if (!s || !rule_idx || !n_found) return fail(KV_E_INVALID, "kv_gini_level_result: null pointer");
+    if (node < 0 || (size_t)node >= s->level_span.size()) return fail(KV_E_INVALID, "kv_gini_level_result: no such node");
+    *rule_idx = s->h_level + s->level_span[(size_t)node].first;
+    *n_found = (int64_t)s->level_span[(size_t)node].second;
+    return KV_OK;
+}
+
+extern "C" int kv_gini_level_fetch(kv_shard *s, int64_t node, int64_t *rule_idx, int64_t capacity) {
+    if (!s || (capacity > 0 && !rule_idx)) return fail(KV_E_INVALID, "kv_gini_level_fetch: null pointer");
+    if (node < 0 || (size_t)node >= s->level_span.size()) return fail(KV_E_INVALID, "kv_gini_level_fetch: no such node");
+    const std::pair<size_t, size_t> &sp = s->level_span[(size_t)node];
+    if ((int64_t)sp.second > capacity) return fail(KV_E_OVERFLOW, "kv_gini_level_fetch: buffer too small");
+    if (sp.second) memcpy(rule_idx, s->h_level + sp.first, sp.second * 8);
+    return KV_OK;
 }
 
 extern "C" int kv_gini_scores(kv_shard *s, double *out) {

@@ -282,6 +282,21 @@ class KmerRuleClassifications(BaseRuleClassifications):
         n_node = np.array([len(example_idx[c]) for c in classes], dtype=np.int64)
         return self._group.gini_best_split(masks, prior, total, n_node)
 
+    def gini_best_splits(self, example_idx_by_node, altered_priors, n_total_class_examples, rule_blacklist=()):
+        """``gini_best_split`` for the nodes of a tree level at once (cart.py:260-339 scans them one after the
+        other): with two classes, the class masks of up to 8 nodes are counted per pass over the matrix.
+        -> [(min score, presence-rule indices achieving it, ascending)] in node order."""
+        nodes = list(example_idx_by_node)
+        if len(nodes) == 1 or any(len(ex) != 2 or list(ex.keys()) != list(nodes[0].keys()) for ex in nodes):
+            return [self.gini_best_split(ex, altered_priors, n_total_class_examples, rule_blacklist) for ex in nodes]
+        self.set_rule_blacklist(rule_blacklist)
+        classes = list(nodes[0].keys())
+        masks = np.stack([np.stack([self.row_mask(ex[c]) for c in classes]) for ex in nodes])
+        prior = np.array([altered_priors[c] for c in classes], dtype=np.float64)
+        total = np.array([n_total_class_examples[c] for c in classes], dtype=np.float64)
+        n_node = np.array([[len(ex[c]) for c in classes] for ex in nodes], dtype=np.int64)
+        return self._group.gini_best_splits(masks, prior, total, n_node)
+
     def kmer_risk_tables(self, train_pos_idx, train_neg_idx):
         """The individual k-mer risk tables `kover dataset split` stores per split / fold (split.py:171-188):
         -> (unique_risks, unique_risk_by_kmer, unique_risk_by_anti_kmer).  One pass over the matrix instead of

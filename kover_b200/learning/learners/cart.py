@@ -10,7 +10,6 @@ Python-level ``min`` over 2K floats (cart.py:112-161, 219-250) is ONE call to
 over the HBM-resident matrix) and k_gini2_ties_seg (the exact-tie set).
 """
 import logging
-from collections import deque
 from copy import deepcopy
 
 import numpy as np
@@ -108,45 +107,56 @@ class DecisionTreeClassifier(object):
                                          criterion_value=node_criterion(counts), class_priors=impurity.priors,
                                          total_n_examples_by_class=impurity.n_total)
 
+        many = getattr(rule_classifications, "gini_best_splits", None)
+        if self.criterion == "gini" and many is not None:
+            search_level = lambda idx_list: many(idx_list, impurity.priors, impurity.n_total, rule_blacklist)
+        else:
+            search_level = lambda idx_list: [search(idx) for idx in idx_list]
+
         root = new_node(example_idx, 0, counts=impurity.n_total)
-        frontier = deque([root])                       # breadth first: a level is complete before the next starts
-        infos, level = {}, -1
+        # Breadth first, one level at a time (the reference pops a FIFO queue, cart.py:260-339: same visiting
+        # order).  The nodes of a level are independent, so their split searches are issued together and share
+        # matrix passes; everything else -- callbacks, tiebreaker calls, child creation -- runs in node order.
+        level_nodes, depth = [root], 0
+        infos = {}
         min_split = max(self.min_samples_split, 2)
-        while frontier:
-            node = frontier.popleft()
-            if node.depth != level:
-                level = node.depth
-                infos["depth"] = level
-                if level > 0:
-                    level_callback(infos)              # all the nodes of the previous level exist now
-                if level == self.max_depth:
-                    break                              # the deepest level stays leaves
-            if 1.0 in node.class_proportions.values() or node.n_examples < min_split:
-                continue                               # pure, or too small to split
+        while level_nodes:
+            infos["depth"] = depth
+            if depth > 0:
+                level_callback(infos)                  # all the nodes of the previous level exist now
+            if depth == self.max_depth:
+                break                                  # the deepest level stays leaves
+            # pure nodes and nodes too small to split stay leaves
+            splittable = [node for node in level_nodes
+                          if not (1.0 in node.class_proportions.values() or node.n_examples < min_split)]
+            found = search_level([node.class_examples_idx for node in splittable]) if splittable else []
+            next_level = []
+            for node, (best_score, candidates) in zip(splittable, found):
+                if best_score == np.inf:
+                    continue                           # no rule separates the node into two non-empty children
+                members = node.class_examples_idx
+                equivalent = tiebreaker(candidates)
+                if np.may_share_memory(equivalent, candidates):
+                    equivalent = np.array(equivalent)  # candidates may be a view of a buffer the next level reuses
+                chosen = equivalent[0]
+                has_kmer = rule_classifications.get_columns(chosen)
+                left = dict((c, members[c][has_kmer[members[c]] == 1]) for c in members.keys())     # rule true
+                right = dict((c, members[c][has_kmer[members[c]] == 0]) for c in members.keys())    # rule false
 
-            members = node.class_examples_idx
-            best_score, candidates = search(members)
-            if best_score == np.inf:
-                continue                               # no rule separates the node into two non-empty children
-            equivalent = tiebreaker(candidates)
-            chosen = equivalent[0]
-            has_kmer = rule_classifications.get_columns(chosen)
-            left = dict((c, members[c][has_kmer[members[c]] == 1]) for c in members.keys())     # rule true
-            right = dict((c, members[c][has_kmer[members[c]] == 0]) for c in members.keys())    # rule false
-
-            node.rule = rules[chosen]
-            node.rule_idx = chosen
-            node.equivalent_rules_idx = equivalent
-            node.left_child = new_node(left, node.depth + 1, parent=node)
-            node.right_child = new_node(right, node.depth + 1, parent=node)
-            # unnormalised importance: decrease of p(t) * impurity (cart.py:321-325)
-            node.rule.importance = \
-                node.breiman_info.p_t * node.criterion_value - \
-                node.left_child.breiman_info.p_t * node.left_child.criterion_value - \
-                node.right_child.breiman_info.p_t * node.right_child.criterion_value
-            split_callback(node, equivalent)
-            frontier.extend((node.left_child, node.right_child))
-            infos["model"] = root
+                node.rule = rules[chosen]
+                node.rule_idx = chosen
+                node.equivalent_rules_idx = equivalent
+                node.left_child = new_node(left, node.depth + 1, parent=node)
+                node.right_child = new_node(right, node.depth + 1, parent=node)
+                # unnormalised importance: decrease of p(t) * impurity (cart.py:321-325)
+                node.rule.importance = \
+                    node.breiman_info.p_t * node.criterion_value - \
+                    node.left_child.breiman_info.p_t * node.left_child.criterion_value - \
+                    node.right_child.breiman_info.p_t * node.right_child.criterion_value
+                split_callback(node, equivalent)
+                next_level.extend((node.left_child, node.right_child))
+                infos["model"] = root
+            level_nodes, depth = next_level, depth + 1
         self.decision_tree = root
 
     # ------------------------------------------------------------------ predictions

@@ -330,6 +330,30 @@ class ShardGroup(object):
             idx = self.comm.allgather_concat(idx)
         return m, np.sort(idx)
 
+    def gini_best_splits(self, node_masks, altered_prior, n_total, n_node):
+        """gini_best_split for several two-class nodes (a tree level): node_masks [n_nodes, 2, W], n_node
+        [n_nodes, 2].  Every shard counts the class masks of up to 8 nodes per matrix pass (kv_gini_level); the
+        minima are merged over shards / ranks and the tie lists of the shards that hold a node's minimum are
+        concatenated in column order."""
+        if not hasattr(self.shards[0], "gini_level"):
+            return [self.gini_best_split(m, altered_prior, n_total, nn) for m, nn in zip(node_masks, n_node)]
+        per_shard = [s.gini_level(node_masks, altered_prior, n_total, n_node) for s in self.shards]
+        if self._single:
+            return per_shard[0]         # (the tie lists are read-only views, valid until the next level search)
+        n_nodes = len(per_shard[0])
+        mins = np.array([[res[i][0] for i in range(n_nodes)] for res in per_shard], dtype=np.float64).min(axis=0)
+        if self.comm is not None:
+            mins = self.comm.allreduce_min(mins)
+        out = []
+        for i in range(n_nodes):
+            m = float(mins[i])
+            parts = [res[i][1] for res in per_shard if res[i][0] == m and m != np.inf]
+            idx = np.concatenate(parts) if parts else np.zeros(0, dtype=np.int64)
+            if self.comm is not None:
+                idx = self.comm.allgather_concat(idx)
+            out.append((m, np.sort(idx)))
+        return out
+
     def gini_scores(self):
         if self.comm is not None:
             raise NotImplementedError("gini_scores is a single-process debugging aid")

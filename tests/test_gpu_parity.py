@@ -452,6 +452,40 @@ def test_cart_fit_golden(golden_dir, case, devices):
     tree_equal(tree_to_dict(t.decision_tree), want)
 
 
+@pytest.mark.parametrize("devices", [[0], [0, 0, 0]], ids=["1shard", "3shards"])
+@pytest.mark.parametrize("sorted_labels", [True, False], ids=["sorted", "interleaved"])
+def test_level_search_matches_per_node_search(devices, sorted_labels):
+    """The nodes of a tree level searched together (class masks of 8 nodes per matrix pass, kv_gini_level) give
+    exactly what one gini_best_split per node gives: same minimum, same tie set -- including tiny nodes that tie
+    on a large share of the k-mers (more ties than the per-node slot) and a node with no admissible split."""
+    seed, n, k = 21, 900, 60000
+    P = synthetic_block(seed, n, 0, k)
+    y = synthetic_labels(seed, n, sorted_by_label=sorted_labels)
+    rs = np.random.RandomState(seed)
+    perm = rs.permutation(n)
+    sizes = [300, 200, 150, 100, 60, 30, 20, 12, 8, 5, 4, 3, 2, 2, 2]          # 15 disjoint nodes: two passes
+    nodes, at = [], 0
+    for sz in sizes:
+        members = np.sort(perm[at:at + sz])
+        at += sz
+        nodes.append({0: members[y[members] == 0], 1: members[y[members] == 1]})
+    nodes = [ex for ex in nodes if len(ex[0]) and len(ex[1])]
+    assert len(nodes) > 8
+    rc = KmerRuleClassifications(P, n, devices=devices)
+    n_total = {0: float((y == 0).sum()), 1: float((y == 1).sum())}
+    priors = {0: 0.4, 1: 0.6}
+    bl = rs.choice(k, size=300, replace=False)
+    want = [rc.gini_best_split(ex, priors, n_total, rule_blacklist=bl) for ex in nodes]
+    before = [s_.info().scan_calls for s_ in rc._group.shards]
+    got = rc.gini_best_splits(nodes, priors, n_total, rule_blacklist=bl)
+    after = [s_.info().scan_calls for s_ in rc._group.shards]
+    assert all(a - b == -(-len(nodes) // 8) for a, b in zip(after, before))
+    assert max(len(w[1]) for w in want) > 1024
+    for w, g_ in zip(want, got):
+        assert w[0] == g_[0] and np.array_equal(w[1], g_[1])
+    rc.close()
+
+
 @pytest.mark.parametrize("n_classes", [2, 3, 5])
 def test_gini_scores_vs_checker(n_classes):
     seed, n, k = 11, 700, 40000
