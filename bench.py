@@ -274,6 +274,24 @@ def extra_measurements(rc, shard, steps, k_local, reps=12):
     out["hp_grid_iteration_12_jobs"] = {"ms_per_grid": ms, "job_rules_per_s": len(jobs) * 2.0 * k_local / (ms * 1e-3),
                                         "matrix_scans_per_grid": (ib.scan_calls - ia.scan_calls) / 7.0,
                                         "rescores_per_grid": (ib.rescore_calls - ia.rescore_calls) / 7.0}
+    # configs[1] in full at iteration 1: {train, 5 CV folds} x 6 p x {conjunction, disjunction} = 72 jobs over SIX
+    # distinct mask pairs: k_count_tma counts the 12 masks in ONE matrix pass, every job is scored from the counts
+    rs = np.random.RandomState(SEED)
+    train_all = np.sort(np.concatenate((pos, neg)))
+    fold_of = rs.randint(0, 5, size=len(train_all))
+    is_pos = np.isin(train_all, pos)
+    cv_jobs = []
+    for f in range(6):
+        keep = np.ones(len(train_all), dtype=bool) if f == 5 else fold_of != f
+        fp, fn = train_all[keep & is_pos], train_all[keep & ~is_pos]
+        cv_jobs += [(pp, a, b) for pp in P_GRID for a, b in ((fp, fn), (fn, fp))]
+    ia = shard.info()
+    ms = timed(lambda: rc.best_utility_rules_grid(cv_jobs, util_block_size=UTIL_BLOCK_SIZE), 6)
+    ib = shard.info()
+    out["cv_grid_iteration_72_jobs"] = {"ms_per_grid": ms, "job_rules_per_s": len(cv_jobs) * 2.0 * k_local / (ms * 1e-3),
+                                        "distinct_mask_pairs": 6,
+                                        "matrix_passes_per_grid": (ib.scan_calls - ia.scan_calls) / 7.0,
+                                        "rescores_per_grid": (ib.rescore_calls - ia.rescore_calls) / 7.0}
     # whole greedy fits through the reference-shaped learners (host control flow + get_columns + bookkeeping)
     from kover_b200.learning.common.rules import LazyKmerRuleList
     from kover_b200.learning.learners.cart import DecisionTreeClassifier
@@ -291,6 +309,16 @@ def extra_measurements(rc, shard, steps, k_local, reps=12):
     dt = time.perf_counter() - t0
     n_split = len(t.decision_tree.rules)
     out["cart_fit_max_depth_5"] = {"seconds": dt, "split_nodes": n_split, "ms_per_split_node": 1e3 * dt / max(1, n_split)}
+    # configs[2]'s depth: the nodes of a level are searched together, class masks of 8 nodes per matrix pass
+    t = DecisionTreeClassifier("gini", 10, 2, {0: 1.0, 1: 1.0})
+    ia = shard.info()
+    t0 = time.perf_counter()
+    t.fit(rules, rc, ex)
+    dt = time.perf_counter() - t0
+    ib = shard.info()
+    n_split = len(t.decision_tree.rules)
+    out["cart_fit_max_depth_10"] = {"seconds": dt, "split_nodes": n_split, "ms_per_split_node": 1e3 * dt / max(1, n_split),
+                                    "matrix_passes": ib.scan_calls - ia.scan_calls}
     # the reference's own operator API: sum_rows returns a 2K-long host array (D2H of 2K x uint16 per call)
     out["sum_rows_dropin_ms"] = timed(lambda: rc.sum_rows(steps[0][1]), 4)
     # upload path: host numpy block -> pinned ring -> HBM (kv_upload_block), on 1/8 of the matrix

@@ -547,9 +547,8 @@ __device__ __forceinline__ const double *select_prologue(unsigned long long *blo
     return in_smem ? s_bm : bm;
 }
 
-__global__ void __launch_bounds__(32) k_scm_select(unsigned long long *blockmax, long long n_blocks, double *bm,
-                                                   double *tol, uint8_t *sel, TieHeader *hdr) {
-    __shared__ double s_bm[SELECT_SMEM_BLOCKS];
+__device__ __forceinline__ void scm_select_body(unsigned long long *blockmax, long long n_blocks, double *bm, double *tol,
+                                                uint8_t *sel, TieHeader *hdr, double *s_bm) {
     const double *v = select_prologue(blockmax, n_blocks, bm, s_bm);
     if (threadIdx.x != 0) return;
     double best = -INFINITY;
@@ -572,6 +571,12 @@ __global__ void __launch_bounds__(32) k_scm_select(unsigned long long *blockmax,
     }
     hdr->best_utility = best;
     hdr->count = 0;
+}
+
+__global__ void __launch_bounds__(32) k_scm_select(unsigned long long *blockmax, long long n_blocks, double *bm,
+                                                   double *tol, uint8_t *sel, TieHeader *hdr) {
+    __shared__ double s_bm[SELECT_SMEM_BLOCKS];
+    scm_select_body(blockmax, n_blocks, bm, tol, sel, hdr, s_bm);
 }
 
 // Multi-rank variant: this rank only knows ITS block maxima.  Every rule that can survive the global
@@ -649,7 +654,7 @@ __device__ __forceinline__ void tie_emit(const TieParams &P, long long rule, dou
     }
 }
 
-__global__ void __launch_bounds__(256) k_scm_ties(const TieParams P) {
+__device__ __forceinline__ void scm_ties_body(const TieParams &P) {
     const int lane = threadIdx.x & 31;
     const long long n_seg = (P.n_cols + 63) >> 6;
     const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -687,6 +692,17 @@ __global__ void __launch_bounds__(256) k_scm_ties(const TieParams P) {
             }
         }
     }
+}
+
+__global__ void __launch_bounds__(256) k_scm_ties(const TieParams P) { scm_ties_body(P); }
+
+// the tie collection of up to QUEUE_BATCH jobs in one launch: blockIdx.y selects the job
+static constexpr int QUEUE_BATCH = 12;
+struct TieParamsMulti {
+    TieParams j[QUEUE_BATCH];
+};
+__global__ void __launch_bounds__(256) k_scm_ties_multi(const __grid_constant__ TieParamsMulti M) {
+    scm_ties_body(M.j[blockIdx.y]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -781,6 +797,129 @@ __global__ void __launch_bounds__(256) k_scm_rescore(const RescoreParams P) {
         for (int w = 0; w < 8; ++w) m = s_red[threadIdx.x][w] > m ? s_red[threadIdx.x][w] : m;
         if (m) atomicMax(P.blockmax + bid[threadIdx.x], m);
     }
+}
+
+// k_scm_rescore for up to QUEUE_BATCH jobs that share a mask pair (the p values of a grid, both model types): the
+// counts are read ONCE, every job gets its own segment maxima and block maxima.  Same arithmetic per job.
+struct RescoreMultiParams {
+    const uint32_t *cnt_a, *cnt_b;         // presence counts under the pair's first / second mask
+    long long n_cols, ld, col0, k_total, ubs;
+    const uint32_t *black_pres, *black_abs;
+    int n_jobs, n_plain;                   // jobs [0, n_plain): positives = the pair's FIRST mask; [n_plain, n_jobs): swapped
+    double p[QUEUE_BATCH];
+    double n_pos[QUEUE_BATCH], n_neg[QUEUE_BATCH];
+    unsigned long long *blockmax[QUEUE_BATCH], *segmax[QUEUE_BATCH];
+};
+
+// a chunk that straddles a utility-block boundary (rare): per-rule atomics, kept out of line
+__device__ __noinline__ void rescore_straddle(unsigned long long *blockmax, long long rule0, long long ubs, double u0,
+                                              double u1, bool v0, bool v1) {
+    if (v0) atomicMax(blockmax + rule0 / ubs, enc_f64(u0));
+    if (v1) atomicMax(blockmax + (rule0 + 1) / ubs, enc_f64(u1));
+}
+
+// 512 columns per CTA: every warp owns one 64-column segment, every lane two adjacent columns, so that the segment
+// maxima are full-warp redux.sync.  The counts are converted to double ONCE (int -> double conversions run on the
+// 16-lane XU pipe and would otherwise dominate); n_neg - cnt is then formed in double, which is exact for integers
+// and therefore the same value the reference converts (scm.py:245-264).  The kernel is issue-bound (about 150
+// instructions per warp and job before this shape, profiles/README.md), hence: jobs ordered plain-then-swapped so
+// that the roles of the two count arrays are fixed per loop, per-job scalars pre-converted on the host, maxima
+// taken on the order-preserving integer images.
+struct RescoreLane {
+    double cp0, cp1, cn0, cn1;      // presence counts of the lane's two columns under the positive / negative mask
+    uint32_t dead_p, dead_a;
+    bool any_dead, uniform[2];
+    long long col, rule0[2];
+    size_t seg_idx, seg_half;
+    int lane, warp;
+};
+
+__device__ __forceinline__ void rescore_job(const RescoreMultiParams &P, int j, const RescoreLane &L,
+                                            unsigned long long (*s_red)[2][8]) {
+    const double p = P.p[j], dn_pos = P.n_pos[j], dn_neg = P.n_neg[j];
+    // presence rule: covers the negatives WITHOUT the k-mer, errs on the positives without it; absence: complements
+    double u[2][2];
+    u[0][0] = __dsub_rn(__dsub_rn(dn_neg, L.cn0), __dmul_rn(p, __dsub_rn(dn_pos, L.cp0)));
+    u[0][1] = __dsub_rn(__dsub_rn(dn_neg, L.cn1), __dmul_rn(p, __dsub_rn(dn_pos, L.cp1)));
+    u[1][0] = __dsub_rn(L.cn0, __dmul_rn(p, L.cp0));
+    u[1][1] = __dsub_rn(L.cn1, __dmul_rn(p, L.cp1));
+    if (L.any_dead) {
+        if (L.dead_p & 1u) u[0][0] = -INFINITY;
+        if (L.dead_p & 2u) u[0][1] = -INFINITY;
+        if (L.dead_a & 1u) u[1][0] = -INFINITY;
+        if (L.dead_a & 2u) u[1][1] = -INFINITY;
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const unsigned long long e0 = enc_f64(u[h][0]), e1 = enc_f64(u[h][1]);
+        const unsigned long long seg = warp_max_enc(e0 > e1 ? e0 : e1);
+        if (L.lane == 0) {
+            P.segmax[j][h * L.seg_half + L.seg_idx] = seg;
+            s_red[j][h][L.warp] = seg;
+        }
+        if (!L.uniform[h])                                     // CTA-uniform
+            rescore_straddle(P.blockmax[j], L.rule0[h], P.ubs, u[h][0], u[h][1], L.col < P.n_cols, L.col + 1 < P.n_cols);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_scm_rescore_multi(const __grid_constant__ RescoreMultiParams P) {
+    __shared__ unsigned long long s_red[QUEUE_BATCH][2][8];
+    RescoreLane L;
+    L.lane = threadIdx.x & 31;
+    L.warp = threadIdx.x >> 5;
+    const long long chunk_c0 = (long long)blockIdx.x * 512;
+    const long long chunk_n = min(512ll, P.n_cols - chunk_c0);
+    long long bid[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const long long r0 = (long long)h * P.k_total + P.col0 + chunk_c0;
+        bid[h] = r0 / P.ubs;
+        L.uniform[h] = chunk_n > 0 && (r0 + chunk_n - 1) / P.ubs == bid[h];
+    }
+    const long long seg_c0 = chunk_c0 + (long long)L.warp * 64;                // < ld: ld is a multiple of 1024
+    L.col = seg_c0 + L.lane * 2;
+    L.rule0[0] = P.col0 + L.col;
+    L.rule0[1] = P.k_total + P.col0 + L.col;
+    const uint2 va = *reinterpret_cast<const uint2 *>(P.cnt_a + L.col);
+    const uint2 vb = *reinterpret_cast<const uint2 *>(P.cnt_b + L.col);
+    const double da0 = (double)va.x, da1 = (double)va.y, db0 = (double)vb.x, db1 = (double)vb.y;
+    // rules this lane may NOT score: padding columns and blacklisted rules (scm.py:267) -> -inf
+    L.dead_p = (L.col < P.n_cols ? 0u : 1u) | (L.col + 1 < P.n_cols ? 0u : 2u);
+    L.dead_a = L.dead_p;
+    if (P.black_pres) {
+        L.dead_p |= (P.black_pres[L.col >> 5] >> (L.col & 31)) & 3u;
+        L.dead_a |= (P.black_abs[L.col >> 5] >> (L.col & 31)) & 3u;
+    }
+    L.any_dead = (L.dead_p | L.dead_a) != 0;
+    L.seg_idx = (size_t)(seg_c0 >> 6);
+    L.seg_half = (size_t)(P.ld >> 6);
+    L.cp0 = da0; L.cp1 = da1; L.cn0 = db0; L.cn1 = db1;
+    for (int j = 0; j < P.n_plain; ++j) rescore_job(P, j, L, s_red);
+    L.cp0 = db0; L.cp1 = db1; L.cn0 = da0; L.cn1 = da1;
+    for (int j = P.n_plain; j < P.n_jobs; ++j) rescore_job(P, j, L, s_red);
+    __syncthreads();
+    if (threadIdx.x < 2 * P.n_jobs) {
+        const int j = threadIdx.x >> 1, h = threadIdx.x & 1;
+        if (L.uniform[h]) {
+            unsigned long long m = 0ull;
+            for (int w = 0; w < 8; ++w) m = s_red[j][h][w] > m ? s_red[j][h][w] : m;
+            if (m) atomicMax(P.blockmax[j] + bid[h], m);
+        }
+    }
+}
+
+// k_scm_select for up to QUEUE_BATCH jobs: one warp (block) per job
+struct SelectMultiParams {
+    unsigned long long *blockmax[QUEUE_BATCH];
+    double *bm[QUEUE_BATCH], *tol[QUEUE_BATCH];
+    uint8_t *sel[QUEUE_BATCH];
+    TieHeader *hdr[QUEUE_BATCH];
+    long long n_blocks;
+};
+__global__ void __launch_bounds__(32) k_scm_select_multi(const __grid_constant__ SelectMultiParams P) {
+    __shared__ double s_bm[SELECT_SMEM_BLOCKS];
+    const int j = blockIdx.x;
+    scm_select_body(P.blockmax[j], P.n_blocks, P.bm[j], P.tol[j], P.sel[j], P.hdr[j], s_bm);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1319,6 +1458,7 @@ struct kv_shard {
     long long risk_n = 0;
     GiniParams gini;
 
+    DevBuf d_qmisc, d_qseg;                   // block tables / segment maxima of the jobs of one queue batch
     DevBuf d_level;                           // kv_gini_level: per-node minima, counters, tie slots, segment minima
     int64_t *h_level = nullptr;               // pinned arena: the tie lists of the last kv_gini_level, node after node
     size_t h_level_cap = 0, h_level_used = 0; // in entries
@@ -1433,7 +1573,7 @@ extern "C" int kv_destroy(kv_shard *s) {
     p2p_destroy(s->p2p);
     cudaFree(s->d_mat);
     for (auto p : s->d_cnt) cudaFree(p);
-    for (DevBuf *b : {&s->d_rec, &s->d_misc, &s->d_ties, &s->d_stage, &s->d_sort_tmp, &s->d_sort_io, &s->d_queue, &s->d_level})
+    for (DevBuf *b : {&s->d_rec, &s->d_misc, &s->d_ties, &s->d_stage, &s->d_sort_tmp, &s->d_sort_io, &s->d_queue, &s->d_level, &s->d_qmisc, &s->d_qseg})
         if (b->p) cudaFree(b->p);
     if (s->d_black_pres) cudaFree(s->d_black_pres);
     if (s->d_black_abs) cudaFree(s->d_black_abs);
@@ -2555,13 +2695,101 @@ extern "C" int kv_scm_queue_collect(kv_shard *s, int64_t n_slots, double *best_u
     return KV_OK;
 }
 
-// Jobs whose reuse flag is 0 open a group (a new mask pair); the jobs that follow with reuse 1 / 2 re-score
-// that group's counts.  With two or more groups the pairs are counted SEVERAL PER MATRIX PASS by k_count_tma
-// (up to MAX_MULTI / 2 pairs: the folds of a cross-validation, the diverged greedy states of a grid) and
-// every job -- the group leaders included -- is then scored from the resident counts by k_scm_rescore.
-static int scm_queue_run_batched(kv_shard *s, int64_t n_jobs, const uint64_t *masks, const int64_t *n_pos,
+// Score jobs job_ids[0..n) -- all over the SAME mask pair, whose presence counts sit in cnt_a / cnt_b -- from the
+// resident counts: per batch of QUEUE_BATCH jobs one k_scm_rescore_multi (the counts are read once for the whole
+// batch), one k_scm_select_multi, one k_scm_ties_multi, each job's result landing in its queue slot.
+static int queue_score_group(kv_shard *s, const uint32_t *cnt_a, const uint32_t *cnt_b, const int64_t *job_ids, int n,
+                             const int64_t *n_pos, const int64_t *n_neg, const double *p, const int32_t *reuse,
+                             int64_t ubs, int64_t n_blocks) {
+    const MiscLayout L0 = misc_layout(nullptr, n_blocks);
+    const size_t misc_stride = (L0.bytes + 255) / 256 * 256, seg_stride = (size_t)(s->ld / 64) * 2 * 8;
+    KV_TRY(ensure(s->d_qmisc, misc_stride * QUEUE_BATCH));
+    KV_TRY(ensure(s->d_qseg, seg_stride * QUEUE_BATCH));
+    const long long n_seg = (s->n_cols + 63) / 64;
+    const unsigned grid_ties = (unsigned)std::max<long long>(1, std::min<long long>((n_seg + 255) / 256, (long long)s->sm_count * 4));
+    for (int b0 = 0; b0 < n; b0 += QUEUE_BATCH) {
+        const int nb = std::min(QUEUE_BATCH, n - b0);
+        RescoreMultiParams R;
+        SelectMultiParams S;
+        TieParamsMulti T;
+        memset(&R, 0, sizeof R);
+        memset(&S, 0, sizeof S);
+        memset(&T, 0, sizeof T);
+        R.cnt_a = cnt_a;
+        R.cnt_b = cnt_b;
+        R.n_cols = s->n_cols;
+        R.ld = s->ld;
+        R.col0 = s->col0;
+        R.k_total = s->k_total;
+        R.ubs = ubs;
+        R.black_pres = s->have_black ? s->d_black_pres : nullptr;
+        R.black_abs = s->have_black ? s->d_black_abs : nullptr;
+        R.n_jobs = nb;
+        S.n_blocks = n_blocks;
+        // plain jobs first, then the jobs whose positives are the pair's second mask (fixed roles per kernel loop)
+        std::vector<int64_t> order;
+        for (int pass = 0; pass < 2; ++pass)
+            for (int i = 0; i < nb; ++i)
+                if ((reuse[job_ids[b0 + i]] == 2) == (pass == 1)) order.push_back(job_ids[b0 + i]);
+        for (int i = 0; i < nb; ++i) R.n_plain += reuse[order[i]] != 2;
+        for (int i = 0; i < nb; ++i) {
+            const int64_t j = order[i];
+            if (n_pos[j] < 0 || n_neg[j] < 0 || n_pos[j] > s->n_examples || n_neg[j] > s->n_examples)
+                return fail(KV_E_INVALID, "kv_scm_queue_run: n_pos / n_neg out of range");
+            const bool swap = reuse[j] == 2;
+            const MiscLayout L = misc_layout((char *)s->d_qmisc.p + (size_t)i * misc_stride, n_blocks);
+            unsigned long long *seg = (unsigned long long *)((char *)s->d_qseg.p + (size_t)i * seg_stride);
+            TieHeader *d_hdr = (TieHeader *)((char *)s->d_queue.p + (size_t)j * kQueueSlotBytes);
+            R.p[i] = p[j];
+            R.n_pos[i] = (double)n_pos[j];
+            R.n_neg[i] = (double)n_neg[j];
+            R.blockmax[i] = L.blockmax;
+            R.segmax[i] = seg;
+            S.blockmax[i] = L.blockmax;
+            S.bm[i] = L.bm;
+            S.tol[i] = L.tol;
+            S.sel[i] = L.sel;
+            S.hdr[i] = d_hdr;
+            TieParams &t = T.j[i];
+            t.cnt0 = swap ? cnt_b : cnt_a;
+            t.cnt1 = swap ? cnt_a : cnt_b;
+            t.segmax = seg;
+            t.n_cols = s->n_cols;
+            t.ld = s->ld;
+            t.col0 = s->col0;
+            t.k_total = s->k_total;
+            t.ubs = ubs;
+            t.inv_ubs = 1.0 / (double)ubs;
+            t.p = p[j];
+            t.n_pos = (uint32_t)n_pos[j];
+            t.n_neg = (uint32_t)n_neg[j];
+            t.black_pres = R.black_pres;
+            t.black_abs = R.black_abs;
+            t.bm = L.bm;
+            t.tol = L.tol;
+            t.sel = L.sel;
+            t.count = &d_hdr->count;
+            t.threshold = nullptr;
+            t.out = (TieRec *)(d_hdr + 1);
+            t.cap = kQueueSlotRecs;
+        }
+        k_scm_rescore_multi<<<(unsigned)(s->ld / 512), 256, 0, s->stream>>>(R);
+        k_scm_select_multi<<<nb, 32, 0, s->stream>>>(S);
+        k_scm_ties_multi<<<dim3(grid_ties, nb), 256, 0, s->stream>>>(T);
+        count_launch(s, 3);
+        s->rescore_calls += nb;
+    }
+    return KV_OK;
+}
+
+// Jobs whose reuse flag is 0 open a group (a new mask pair); the jobs that follow with reuse 1 / 2 re-score that
+// group's counts.  One group: the leader is the fused scan (k_scan_tma<EPI_SCM>), its followers are scored from
+// the counts it leaves.  Two or more groups: the pairs are counted SEVERAL PER MATRIX PASS by k_count_tma (up to
+// MAX_MULTI / 2 pairs: the folds of a cross-validation, the diverged greedy states of a grid) and every job -- the
+// group leaders included -- is scored from the resident counts.
+static int scm_queue_run_grouped(kv_shard *s, int64_t n_jobs, const uint64_t *masks, const int64_t *n_pos,
                                  const int64_t *n_neg, const double *p, const int32_t *reuse, int64_t util_block_size,
-                                 int pairs_per_pass) {
+                                 int pairs_per_pass, bool batch_pairs) {
     const int64_t n_blocks = kv_scm_n_blocks(s->k_total, util_block_size);
     if (n_blocks <= 0) return fail(KV_E_INVALID, "kv_scm_queue_run: util_block_size must be positive");
     std::vector<int64_t> leaders;
@@ -2569,13 +2797,35 @@ static int scm_queue_run_batched(kv_shard *s, int64_t n_jobs, const uint64_t *ma
         if (reuse[j] < 0 || reuse[j] > 2) return fail(KV_E_INVALID, "kv_scm_queue_run: reuse must be 0, 1 or 2");
         if (reuse[j] == 0) leaders.push_back(j);
     }
-    const size_t n_passes = (leaders.size() + pairs_per_pass - 1) / pairs_per_pass;
     s->last_launches = 0;
     KV_TRY(ensure(s->d_queue, (size_t)n_jobs * kQueueSlotBytes));
+    std::vector<int64_t> ids;
+    if (!batch_pairs) {
+        // one matrix pass per group, fused with the leader's utility epilogue
+        KV_TRY(ensure_pinned(s, (size_t)n_jobs * kQueueSlotBytes));
+        for (size_t l = 0; l < leaders.size(); ++l) {
+            const int64_t j0 = leaders[l], j1 = l + 1 < leaders.size() ? leaders[l + 1] : n_jobs;
+            if (l > 0 && s->W > SCAN_INLINE_ROWS) CU(cudaStreamSynchronize(s->stream));   // pinned row records are reused
+            const uint64_t *pm = masks + (size_t)j0 * 2 * s->W;
+            KV_TRY(scm_scan_async(s, pm, pm + s->W, n_pos[j0], n_neg[j0], p[j0], util_block_size, n_blocks));
+            MiscLayout L = misc_layout(s->d_misc.p, n_blocks);
+            TieHeader *d_hdr = (TieHeader *)((char *)s->d_queue.p + (size_t)j0 * kQueueSlotBytes);
+            k_scm_select<<<1, 32, 0, s->stream>>>(L.blockmax, n_blocks, L.bm, L.tol, L.sel, d_hdr);
+            count_launch(s);
+            launch_exact_ties(s, n_blocks, d_hdr, (TieRec *)(d_hdr + 1), kQueueSlotRecs);
+            ids.clear();
+            for (int64_t j = j0 + 1; j < j1; ++j) ids.push_back(j);
+            if (!ids.empty())
+                KV_TRY(queue_score_group(s, s->d_cnt[0], s->d_cnt[1], ids.data(), (int)ids.size(), n_pos, n_neg, p, reuse,
+                                         util_block_size, n_blocks));
+        }
+        CU(cudaGetLastError());
+        return KV_OK;
+    }
+    const size_t n_passes = (leaders.size() + pairs_per_pass - 1) / pairs_per_pass;
     KV_TRY(ensure_counts(s, 2 + 2 * pairs_per_pass));
     KV_TRY(ensure_pinned(s, std::max(n_passes * count_batch_stride(s->W), (size_t)n_jobs * kQueueSlotBytes)));
     KV_TRY(ensure(s->d_rec, count_batch_stride(s->W)));
-    if (!s->d_segmax) CU(cudaMalloc(&s->d_segmax, (size_t)(s->ld / 64) * 2 * 8));
     CU(cudaStreamSynchronize(s->stream));                 // an earlier call's copies may still read the pinned buffer
     for (size_t pass = 0; pass < n_passes; ++pass) {
         const size_t l0 = pass * pairs_per_pass, l1 = std::min(leaders.size(), l0 + pairs_per_pass);
@@ -2591,23 +2841,15 @@ static int scm_queue_run_batched(kv_shard *s, int64_t n_jobs, const uint64_t *ma
         KV_TRY(count_masks_async(s, (int)ptrs.size(), ptrs.data(), dst.data(),
                                  (char *)s->h_pin + pass * count_batch_stride(s->W)));
         s->scan_calls += 1;
-        const int64_t j_end = l1 < leaders.size() ? leaders[l1] : n_jobs;
-        int64_t group = -1;
-        for (int64_t j = leaders[l0]; j < j_end; ++j) {
-            if (reuse[j] == 0) ++group;
-            s->scm_cnt_a = dst[2 * group];
-            s->scm_cnt_b = dst[2 * group + 1];
-            s->scm_valid = true;
-            s->reuse_armed = true;
-            s->reuse_swap = reuse[j] == 2;
-            KV_TRY(scm_scan_async(s, nullptr, nullptr, n_pos[j], n_neg[j], p[j], util_block_size, n_blocks));
-            MiscLayout L = misc_layout(s->d_misc.p, n_blocks);
-            TieHeader *d_hdr = (TieHeader *)((char *)s->d_queue.p + (size_t)j * kQueueSlotBytes);
-            k_scm_select<<<1, 32, 0, s->stream>>>(L.blockmax, n_blocks, L.bm, L.tol, L.sel, d_hdr);
-            count_launch(s);
-            launch_exact_ties(s, n_blocks, d_hdr, (TieRec *)(d_hdr + 1), kQueueSlotRecs);
+        for (size_t l = l0; l < l1; ++l) {
+            const int64_t j1 = l + 1 < leaders.size() ? leaders[l + 1] : n_jobs;
+            ids.clear();
+            for (int64_t j = leaders[l]; j < j1; ++j) ids.push_back(j);
+            KV_TRY(queue_score_group(s, dst[2 * (l - l0)], dst[2 * (l - l0) + 1], ids.data(), (int)ids.size(), n_pos, n_neg, p,
+                                     reuse, util_block_size, n_blocks));
         }
     }
+    s->scm_valid = false;
     CU(cudaGetLastError());
     return KV_OK;
 }
@@ -2618,15 +2860,18 @@ extern "C" int kv_scm_queue_run(kv_shard *s, int64_t n_jobs, const uint64_t *mas
                                 int64_t *neg_cover) {
     if (!s || !masks || !n_pos || !n_neg || !p || !reuse) return fail(KV_E_INVALID, "kv_scm_queue_run: null pointer");
     if (n_jobs <= 0) return fail(KV_E_INVALID, "kv_scm_queue_run: no jobs");
-    int64_t n_groups = 0;
-    for (int64_t j = 0; j < n_jobs; ++j) n_groups += reuse[j] == 0;
-    const int per = max_masks_per_pass(s->W);
-    static const bool no_multi = getenv("KOVER_B200_NO_MULTI") != nullptr;
-    if (n_groups >= 2 && reuse[0] == 0 && per >= 4 && !no_multi && s->col0 == 0 && s->n_cols == s->k_total) {
+    if (s->col0 != 0 || s->n_cols != s->k_total) return fail(KV_E_INVALID, "kv_scm_queue_run: single-shard only");
+    if (reuse[0] == 0) {
+        int64_t n_groups = 0;
+        for (int64_t j = 0; j < n_jobs; ++j) n_groups += reuse[j] == 0;
+        const int per = max_masks_per_pass(s->W);
+        static const bool no_multi = getenv("KOVER_B200_NO_MULTI") != nullptr;    // measurement knob
         DeviceGuard g(s->device);
-        KV_TRY(scm_queue_run_batched(s, n_jobs, masks, n_pos, n_neg, p, reuse, util_block_size, per / 2));
+        KV_TRY(scm_queue_run_grouped(s, n_jobs, masks, n_pos, n_neg, p, reuse, util_block_size, std::max(1, per / 2),
+                                     n_groups >= 2 && per >= 4 && !no_multi));
         return kv_scm_queue_collect(s, n_jobs, best_utility, n_found, rule_idx, pos_err, neg_cover);
     }
+    // the first job re-scores counts an earlier call left on the device: one job after the other
     for (int64_t j = 0; j < n_jobs; ++j) {
         const uint64_t *pm = masks + (size_t)j * 2 * s->W, *nm = pm + s->W;
         KV_TRY(kv_scm_queue_push(s, j, n_jobs, pm, nm, n_pos[j], n_neg[j], p[j], util_block_size, reuse[j]));
@@ -3013,6 +3258,7 @@ static int gini_scan_async(kv_shard *s, int n_classes, const uint64_t *class_mas
             P.g_nnode[c] = G.n_node[c];
         }
         KV_TRY(launch_scan<EPI_GINI2>(s, P, n_both));
+        s->scan_calls += 1;
         G.segmin = s->d_segmax;
     } else {
         KV_TRY(count_masks(s, n_classes, class_masks, 0));
