@@ -56,7 +56,10 @@ class LazyKmerRuleList(object):
         n_kmers = len(self.kmer_sequences)
         column = idx % n_kmers
         kind = "absence" if idx >= n_kmers else "presence"
-        return KmerRule(column, self.kmer_sequences[self.kmer_by_rule[column]], kind)
+        sequence = self.kmer_sequences[self.kmer_by_rule[column]]
+        if isinstance(sequence, bytes):          # fixed-length HDF5 strings come back as bytes
+            sequence = sequence.decode("ascii")
+        return KmerRule(column, sequence, kind)
 
 
 class BaseRuleClassifications(object):

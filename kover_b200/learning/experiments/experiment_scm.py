@@ -225,3 +225,194 @@ def cross_validation(rule_classifications, rules, labels, folds, model_types, p_
             best_hp["model_type"], best_hp["p"], best_hp["max_rules"] = hp
             best_hp_score = score
     return best_hp_score, best_hp, per_hp
+
+
+# ------------------------------------------------------------------------------------------------ dataset-bound driver
+def _fasta_to_sequences(path):
+    """All the sequences of a FASTA file, in order (utils.py:57-74)."""
+    sequences, current = [], []
+    with open(path, "r") as fh:
+        for line in fh:
+            line = line.strip()
+            if line.startswith(">"):
+                if current:
+                    sequences.append("".join(current))
+                current = []
+            elif line:
+                current.append(line)
+    if current:
+        sequences.append("".join(current))
+    return sequences
+
+
+def _parse_kmer_blacklist(blacklist_path, expected_kmer_len):
+    """k-mers to blacklist: a FASTA file or one k-mer per line (utils.py:189-213)."""
+    if any(blacklist_path.endswith(ext) for ext in (".fasta", ".fa", ".fas", ".fna")):
+        kmers = _fasta_to_sequences(blacklist_path)
+    else:
+        with open(blacklist_path, "r") as fh:
+            kmers = [line.rstrip("\n") for line in fh]
+        kmers = [k for k in kmers if k]
+    for kmer in kmers:
+        if set(kmer).difference("ACGTacgt"):
+            raise ValueError("{} is not a valid DNA sequence".format(kmer))
+    if not all(len(kmer) == expected_kmer_len for kmer in kmers):
+        raise ValueError("Extracted k-mers to blacklist do not have all the same length as the dataset k-mers")
+    return kmers
+
+
+def _as_text(x):
+    return x.decode("ascii") if isinstance(x, bytes) else str(x)
+
+
+def _find_rule_blacklist(dataset, kmer_blacklist_file, warning_callback):
+    """Indices of the presence AND absence rules of the k-mers listed in ``kmer_blacklist_file``
+    (experiment_scm.py:632-672; a dictionary lookup replaces the reference's two ``list.index`` scans per k-mer)."""
+    if kmer_blacklist_file is None:
+        return []
+    to_blacklist = _parse_kmer_blacklist(kmer_blacklist_file, dataset.kmer_length)
+    if not to_blacklist:
+        return []
+    sequences = [_as_text(s) for s in dataset.kmer_sequences[...].tolist()]   # (assumed upper-cased in the dataset)
+    column_of_sequence_idx = dict((int(seq_idx), col) for col, seq_idx in
+                                  reversed(list(enumerate(dataset.kmer_by_matrix_column[...].tolist()))))
+    first_idx = {}
+    for i, s in enumerate(sequences):
+        first_idx.setdefault(s, i)
+    n_kmers = len(sequences)
+    rule_blacklist, not_found = [], []
+    for kmer in to_blacklist:
+        kmer = kmer.upper()
+        column = column_of_sequence_idx.get(first_idx.get(kmer, -1))
+        if column is None:
+            not_found.append(kmer)
+        else:
+            rule_blacklist += [column, column + n_kmers]
+    if not_found:
+        warning_callback("The following kmers could not be found in the dataset: " + ", ".join(not_found))
+    return rule_blacklist
+
+
+def _full_train(rule_classifications, rules, labels, split_train_idx, rule_risks, model_type, p, max_rules,
+                max_equiv_rules, rule_blacklist, random_generator, progress_callback):
+    """One SCM on the whole training set with the selected hyper-parameters (experiment_scm.py:250-347)."""
+    predictor = SetCoveringMachine(model_type=model_type, p=p, max_rules=max_rules)
+    if max_rules == 0:                 # cross-validation may prefer the empty model: nothing to train
+        return predictor.model, np.array([]), np.array([])
+    n_kmers = rule_classifications.shape[1] // 2
+    equivalent_rules, done = [], {"n_rules": 0.0}
+
+    def _iteration_callback(iteration_infos):
+        done["n_rules"] += 1
+        progress_callback("Training", done["n_rules"] / max_rules)
+        equiv = iteration_infos["equivalent_rules_idx"]
+        if len(equiv) > max_equiv_rules:
+            random_idx = random_generator.choice(len(equiv), max_equiv_rules, replace=False)
+            random_idx.sort()
+            equiv = equiv[random_idx]
+        if model_type == "disjunction":
+            equiv = (equiv + n_kmers) % (2 * n_kmers)
+        iteration_infos["equivalent_rules_idx"] = equiv
+        equivalent_rules.append(equiv)
+
+    positive_example_idx, negative_example_idx = _split_labels(labels, split_train_idx)
+    progress_callback("Training", 0)
+    predictor.fit(rules=rules, rule_classifications=rule_classifications, positive_example_idx=positive_example_idx,
+                  negative_example_idx=negative_example_idx, rule_blacklist=rule_blacklist,
+                  tiebreaker=partial(_tiebreaker, rule_risks=rule_risks, model_type=model_type),
+                  iteration_callback=_iteration_callback)
+    return predictor.model, predictor.rule_importances, equivalent_rules
+
+
+def learn_SCM(dataset_file, split_name, model_type, p, kmer_blacklist_file, max_rules, max_equiv_rules,
+              parameter_selection, n_cpu, random_seed, authorized_rules=None, bound_delta=None,
+              bound_max_genome_size=None, progress_callback=None, warning_callback=None, error_callback=None,
+              devices=None, comm=None):
+    """``kover learn scm`` on a Kover dataset file: same arguments and return value as the reference's
+    ``learn_SCM`` (experiment_scm.py:675-888).  parameter_selection: "bound", "cv" or "none" (first value of each
+    hyper-parameter).  What differs is the execution: the packed ``kmer_matrix`` is streamed into HBM ONCE and every
+    fit of the selection (all hyper-parameter combinations, all folds) runs in lock-step over that resident image,
+    instead of one forked worker per combination, each re-reading the HDF5 chunks on every scan; ``n_cpu`` is
+    accepted and ignored.  -> (best_hp, best_hp_score, train_metrics, test_metrics, model, rule_importances,
+    model_equivalent_rules, classifications)."""
+    from collections import defaultdict
+
+    from ...dataset.ds import KoverDataset
+    from ..common.rules import KmerRuleClassifications, LazyKmerRuleList
+    warning_callback = warning_callback or (lambda w: logging.warning(w))
+    progress_callback = progress_callback or (lambda task, fraction: None)
+    if error_callback is None:
+        def error_callback(exception):
+            raise exception
+    random_generator = np.random.RandomState(random_seed)
+    model_type, p = np.unique(model_type), np.unique(p)
+
+    dataset = KoverDataset(dataset_file)
+    rule_blacklist = _find_rule_blacklist(dataset, kmer_blacklist_file, warning_callback)
+    split = dataset.get_split(split_name)
+    labels = np.asarray(dataset.phenotype.metadata[...])
+    train_example_idx = np.asarray(split.train_genome_idx[...])
+    test_example_idx = np.asarray(split.test_genome_idx[...])
+    rules = LazyKmerRuleList(dataset.kmer_sequences[...], dataset.kmer_by_matrix_column[...])
+    rule_classifications = KmerRuleClassifications(dataset.kmer_matrix, dataset.genome_count, devices=devices, comm=comm)
+    split_risks = np.hstack((split.unique_risk_by_kmer[...], split.unique_risk_by_anti_kmer[...]))
+    model_types, p_values = [str(m) for m in model_type], [float(x) for x in p]
+
+    best_model = best_importances = best_equiv = None
+    if parameter_selection == "bound":
+        if bound_delta is None or bound_max_genome_size is None:
+            error_callback(Exception("Bound selection cannot be performed without delta and the maximum genome length."))
+        best_hp_score, best_hp, best_model, best_importances, best_equiv, _ = bound_selection(
+            rule_classifications, rules, labels, train_example_idx, split_risks, model_types, p_values, max_rules,
+            max_equiv_rules, rule_blacklist, bound_delta, bound_max_genome_size, random_generator)
+    elif parameter_selection == "cv":
+        if len(split.folds) < 1:
+            error_callback(Exception("Cross-validation cannot be performed on a split with no folds."))
+        folds = [(np.asarray(f.train_genome_idx[...]), np.asarray(f.test_genome_idx[...]),
+                  np.hstack((f.unique_risk_by_kmer[...], f.unique_risk_by_anti_kmer[...]))) for f in split.folds]
+        best_hp_score, best_hp, _ = cross_validation(rule_classifications, rules, labels, folds, model_types, p_values,
+                                                     max_rules, rule_blacklist)
+    else:
+        best_hp = {"model_type": model_types[0], "p": p_values[0], "max_rules": max_rules}
+        best_hp_score = None
+
+    if parameter_selection == "bound":
+        model, rule_importances, equivalent_rules = best_model, best_importances, best_equiv
+    else:
+        model, rule_importances, equivalent_rules = _full_train(
+            rule_classifications, rules, labels, train_example_idx, split_risks, best_hp["model_type"], best_hp["p"],
+            best_hp["max_rules"], max_equiv_rules, rule_blacklist, random_generator, progress_callback)
+
+    train_predictions, test_predictions = _predictions(model, rule_classifications, train_example_idx,
+                                                       test_example_idx, progress_callback)
+    train_answers = labels[train_example_idx]
+    train_metrics = _get_binary_metrics(train_predictions, train_answers)
+    if parameter_selection == "bound":
+        train_metrics["bound"] = best_hp_score
+    else:
+        train_metrics["bound"] = _bound(train_predictions=train_predictions, train_answers=train_answers,
+                                        train_example_idx=train_example_idx, model=model, delta=bound_delta,
+                                        max_genome_size=bound_max_genome_size,
+                                        rule_classifications=rule_classifications)
+    test_metrics = None
+    if len(test_example_idx) > 0:
+        test_answers = labels[test_example_idx]
+        test_metrics = _get_binary_metrics(test_predictions, test_answers)
+
+    genome_ids = np.array([_as_text(g) for g in dataset.genome_identifiers[...].tolist()], dtype=object)
+    classifications = defaultdict(list)
+    classifications["train_correct"] = genome_ids[train_example_idx[train_predictions == train_answers]].tolist() \
+        if train_metrics["risk"][0] < 1.0 else []
+    classifications["train_errors"] = genome_ids[train_example_idx[train_predictions != train_answers]].tolist() \
+        if train_metrics["risk"][0] > 0 else []
+    if len(test_example_idx) > 0:
+        classifications["test_correct"] = genome_ids[test_example_idx[test_predictions == test_answers]].tolist() \
+            if test_metrics["risk"][0] < 1.0 else []
+        classifications["test_errors"] = genome_ids[test_example_idx[test_predictions != test_answers]].tolist() \
+            if test_metrics["risk"][0] > 0 else []
+
+    model_equivalent_rules = [[rules[i] for i in equiv_idx] for equiv_idx in equivalent_rules]
+    rule_classifications.close()
+    dataset.close()
+    return (best_hp, best_hp_score, train_metrics, test_metrics, model, rule_importances, model_equivalent_rules,
+            classifications)
