@@ -229,7 +229,9 @@ int kv_gini_best_split(kv_shard *s, int n_classes, const uint64_t *class_masks, 
                        int64_t *rule_idx, int64_t *n_found);
 /* A whole tree level at once (cart.py:260-339 visits the nodes of a level one after the other; their example
  * sets are disjoint and their scans independent): the split search of n_nodes two-class nodes, class masks
- * [n_nodes][2][W], n_node [n_nodes][2], the class masks of up to 8 nodes counted per matrix pass.  Returns per
+ * [n_nodes][2][W], altered_prior / n_total / n_node [n_nodes][2] (per node, so that the nodes of SEVERAL trees --
+ * the fold trees and the master tree of a cross-validation -- can share passes), the class masks of up to 8
+ * nodes counted per matrix pass.  Returns per
  * node the minimum score over the shard's presence rules and the number of rules achieving it exactly;
  * kv_gini_level_fetch then copies node i's rule indices (GLOBAL, ascending) into a caller buffer of at least
  * n_found[i] entries.  The results stay valid until the next kv_gini_level call on the shard. */

@@ -435,10 +435,11 @@ class Shard(object):
         n_node [n_nodes, 2] -> [(min score over this shard, rule indices achieving it, ascending)] per node."""
         masks = np.ascontiguousarray(node_masks, dtype=np.uint64)
         assert masks.ndim == 3 and masks.shape[1] == 2 and masks.shape[2] == self.n_words
-        pri = np.ascontiguousarray(altered_prior, dtype=np.float64)
-        tot = np.ascontiguousarray(n_total, dtype=np.float64)
         nn = np.ascontiguousarray(n_node, dtype=np.int64)
-        assert pri.shape == (2,) and tot.shape == (2,) and nn.shape == (masks.shape[0], 2)
+        # priors / class totals: one pair for all the nodes (one tree) or one pair per node (several trees)
+        pri = np.ascontiguousarray(np.broadcast_to(np.asarray(altered_prior, dtype=np.float64), nn.shape))
+        tot = np.ascontiguousarray(np.broadcast_to(np.asarray(n_total, dtype=np.float64), nn.shape))
+        assert nn.shape == (masks.shape[0], 2)
         mins = np.empty(masks.shape[0], dtype=np.float64)
         found = np.empty(masks.shape[0], dtype=np.int64)
         check(self._lib.kv_gini_level(self._h, masks.shape[0], ptr(masks), ptr(pri), ptr(tot), ptr(nn), ptr(mins),

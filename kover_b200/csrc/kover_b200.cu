@@ -3440,8 +3440,8 @@ extern "C" int kv_gini_level(kv_shard *s, int64_t n_nodes, const uint64_t *class
             G.n_classes = 2;
             for (int c = 0; c < 2; ++c) {
                 G.cnt[c] = dst[2 * i + c];
-                G.prior[c] = altered_prior[c];
-                G.n_total[c] = n_total[c];
+                G.prior[c] = altered_prior[(b0 + i) * 2 + c];
+                G.n_total[c] = n_total[(b0 + i) * 2 + c];
                 G.n_node[c] = (double)n_node[(b0 + i) * 2 + c];
             }
             G.n_cols = s->n_cols;

@@ -286,17 +286,22 @@ class KmerRuleClassifications(BaseRuleClassifications):
         return self._group.gini_best_split(masks, prior, total, n_node)
 
     def gini_best_splits(self, example_idx_by_node, altered_priors, n_total_class_examples, rule_blacklist=()):
-        """``gini_best_split`` for the nodes of a tree level at once (cart.py:260-339 scans them one after the
-        other): with two classes, the class masks of up to 8 nodes are counted per pass over the matrix.
+        """``gini_best_split`` for several nodes at once -- the nodes of a tree level (cart.py:260-339 scans them one
+        after the other), or of the same level of SEVERAL trees (the fold trees and the master tree of a
+        cross-validation): with two classes, the class masks of up to 8 nodes are counted per pass over the matrix.
+        altered_priors / n_total_class_examples: one dict for all the nodes, or one dict per node.
         -> [(min score, presence-rule indices achieving it, ascending)] in node order."""
         nodes = list(example_idx_by_node)
+        per_node = isinstance(altered_priors, (list, tuple))
+        priors = list(altered_priors) if per_node else [altered_priors] * len(nodes)
+        totals = list(n_total_class_examples) if per_node else [n_total_class_examples] * len(nodes)
         if len(nodes) == 1 or any(len(ex) != 2 or list(ex.keys()) != list(nodes[0].keys()) for ex in nodes):
-            return [self.gini_best_split(ex, altered_priors, n_total_class_examples, rule_blacklist) for ex in nodes]
+            return [self.gini_best_split(ex, pr, tt, rule_blacklist) for ex, pr, tt in zip(nodes, priors, totals)]
         self.set_rule_blacklist(rule_blacklist)
         classes = list(nodes[0].keys())
         masks = np.stack([np.stack([self.row_mask(ex[c]) for c in classes]) for ex in nodes])
-        prior = np.array([altered_priors[c] for c in classes], dtype=np.float64)
-        total = np.array([n_total_class_examples[c] for c in classes], dtype=np.float64)
+        prior = np.array([[pr[c] for c in classes] for pr in priors], dtype=np.float64)
+        total = np.array([[tt[c] for c in classes] for tt in totals], dtype=np.float64)
         n_node = np.array([[len(ex[c]) for c in classes] for ex in nodes], dtype=np.int64)
         return self._group.gini_best_splits(masks, prior, total, n_node)
 
@@ -315,4 +320,8 @@ class KmerRuleClassifications(BaseRuleClassifications):
     def sum_rows_multi(self, row_sets):
         """Presence counts for several row sets in one pass (the reference's TODO at rules.py:200).
         -> uint32 [len(row_sets), n_kmers]."""
-        return self._group.sum_rows_multi(np.stack([self.row_mask(r) for r in row_sets]))
+        group = self._group
+        if group.comm is not None or not all(hasattr(s, "sum_rows_multi") for s in group.shards):
+            # multi-rank groups (sum_rows all-gathers its result) and checker-backed shards: one pass per set
+            return np.stack([self.sum_rows(r)[:self._n_kmers].astype(np.uint32) for r in row_sets])
+        return group.sum_rows_multi(np.stack([self.row_mask(r) for r in row_sets]))

@@ -121,3 +121,215 @@ def learn_pruned_tree_bound(rule_classifications, rules, example_labels, train_g
             min_score, min_score_tree = bound_value, tree
             hps["pruning_alpha"] = alpha
     return hps, min_score, min_score_tree, sequence
+
+
+class _AlphaIntervals(object):
+    """Risk of a fold's pruned trees as a function of the pruning parameter: tree j is the fold's choice for every
+    alpha in [alpha_j, alpha_j+1), the last one up to infinity.  Lookup semantics of the reference's ``BetweenDict``
+    (experiment_cart.py:43-80): the FIRST interval, in insertion order, that contains the key; an interval whose
+    bounds are not strictly increasing is an error."""
+
+    def __init__(self):
+        self._intervals = []
+
+    def add(self, low, high, value):
+        if not low < high:
+            raise RuntimeError("First element of a BetweenDict key must be strictly less than the second element. "
+                               "Got [%.6f, %.6f]" % (low, high))
+        for i, (lo, hi, _) in enumerate(self._intervals):
+            if lo == low and hi == high:                      # same key: the value is replaced, the position kept
+                self._intervals[i] = (low, high, value)
+                return
+        self._intervals.append((low, high, value))
+
+    def __getitem__(self, key):
+        for low, high, value in self._intervals:
+            if low <= key < high or (low <= key and high == np.inf) or (low == -np.inf and key < high):
+                return value
+        raise KeyError("Key '%s' is not between any values in the BetweenDict" % key)
+
+
+def learn_pruned_tree_cv(rule_classifications, rules, example_labels, train_genome_idx, folds, n_classes, hps,
+                         rule_blacklist):
+    """``_learn_pruned_tree_cv`` (:297-436): cost-complexity pruning with the pruning parameter chosen by k-fold
+    cross-validation (Breiman et al. 1984, section 3.4).  folds: [(train_genome_idx, test_genome_idx)] in the
+    reference's fold order.  The fold trees and the master tree are grown in LOCK-STEP over the resident matrix
+    (learners.cart.fit_many: at every depth the nodes of all the trees share matrix passes) and their k-mer
+    occurrence tables (the tiebreaker's input) come from one multi-mask pass.
+    -> (hps with "pruning_alpha", cross-validation score, pruned master tree)."""
+    from math import sqrt
+
+    from ..learners.cart import fit_many
+    from .metrics import _get_binary_metrics
+    example_labels = np.asarray(example_labels)
+    train_genome_idx = np.asarray(train_genome_idx)
+    folds = [(np.asarray(tr), np.asarray(te)) for tr, te in folds]
+    hps = dict(hps)
+
+    def new_tree():
+        return DecisionTreeClassifier(criterion=hps["criterion"], max_depth=hps["max_depth"],
+                                      min_samples_split=hps["min_samples_split"],
+                                      class_importance=hps["class_importance"])
+
+    training_sets = [tr for tr, _ in folds] + [train_genome_idx]
+    n_kmers = rule_classifications.shape[1] // 2
+    presence = rule_classifications.sum_rows_multi(training_sets)             # one pass instead of one per tree
+    learners, fit_args = [], []
+    for i, tr in enumerate(training_sets):
+        # the reference's table is sum_rows(train): presence counts then absence counts, in the smallest uint type
+        occurrences = np.concatenate((presence[i], len(tr) - presence[i])).astype(_occurrence_dtype(len(tr)))
+        assert occurrences.shape[0] == 2 * n_kmers
+        learners.append(new_tree())
+        fit_args.append(dict(rules=rules, example_idx={c: tr[example_labels[tr] == c] for c in range(n_classes)},
+                             rule_blacklist=rule_blacklist,
+                             tiebreaker=partial(_tiebreaker, rule_kmer_occurrences=occurrences),
+                             level_callback=None,
+                             split_callback=_split_callback if i == len(folds) else None))
+    fit_many(learners, fit_args, rule_classifications)
+    fold_predictors, master_predictor = learners[:-1], learners[-1]
+
+    master_alphas, master_pruned_trees = _prune_tree(master_predictor.decision_tree)
+    fold_scores_by_alpha = []
+    for (_, fold_test_idx), predictor in zip(folds, fold_predictors):
+        alphas, trees = _prune_tree(predictor.decision_tree)
+        answers = example_labels[fold_test_idx]
+        by_alpha = _AlphaIntervals()
+        for j, tree in enumerate(trees):
+            risk = _get_binary_metrics(predictions=_predictions(tree, rule_classifications, [], fold_test_idx)[1],
+                                       answers=answers)["risk"][0]
+            by_alpha.add(alphas[j], alphas[j + 1] if j < len(alphas) - 1 else np.inf, risk)
+        fold_scores_by_alpha.append(by_alpha)
+
+    min_score, min_score_tree = np.inf, None
+    for i, tree in enumerate(master_pruned_trees):
+        geo_mean_alpha = sqrt(master_alphas[i] * master_alphas[i + 1]) if i < len(master_alphas) - 1 else np.inf
+        cv_score = np.mean([scores[geo_mean_alpha] for scores in fold_scores_by_alpha])
+        if cv_score <= min_score:          # alphas increase: ties prefer the more pruned tree
+            min_score, min_score_tree = cv_score, tree
+            hps["pruning_alpha"] = geo_mean_alpha
+    return hps, min_score, min_score_tree
+
+
+def _occurrence_dtype(n_rows):
+    from ...utils import _minimum_uint_size
+    return _minimum_uint_size(n_rows)
+
+
+def train_tree(hp_search, criterion, class_importance, max_depth, min_samples_split, progress_callback,
+               hp_search_type):
+    """Best hyper-parameter combination according to ``hp_search(hps) -> (hps, score, pruned master tree)``, visited
+    in the reference's ``--n-cpu 1`` order ``product(criterion, class_importance, max_depth, min_samples_split)``
+    (:437-487).  Ties (``isclose``) go to the smaller tree, then to the less spread class importances -- and, like
+    the reference (:480-483), a tie replaces the hyper-parameters and the score but KEEPS the earlier tree."""
+    from itertools import product
+    combinations = list(product(criterion, class_importance, max_depth, min_samples_split))
+    best_hps, best_score, best_master_tree = None, np.inf, None
+    progress_callback(hp_search_type.title(), 0.0)
+    for done, (crit, importance, depth, mss) in enumerate(combinations):
+        hps, score, master_tree = hp_search({"criterion": crit, "class_importance": importance, "max_depth": depth,
+                                             "min_samples_split": mss})
+        progress_callback(hp_search_type.title(), (done + 1.0) / len(combinations))
+        if score < best_score:
+            best_hps, best_score, best_master_tree = hps, score, master_tree
+        elif np.isclose(score, best_score):
+            n_new, n_best = len(master_tree), len(best_master_tree)
+            if n_new < n_best or (n_new == n_best and np.var(list(hps["class_importance"].values())) <
+                                  np.var(list(best_hps["class_importance"].values()))):
+                best_hps, best_score = hps, score
+    return best_score, best_hps, best_master_tree
+
+
+def _find_rule_blacklist(dataset, kmer_blacklist_file, warning_callback):
+    """Presence-rule indices of the k-mers to blacklist (:490-518: a tree only uses presence rules)."""
+    from .experiment_scm import _find_rule_blacklist as _scm_blacklist
+    n_kmers = dataset.kmer_count
+    return [r for r in _scm_blacklist(dataset, kmer_blacklist_file, warning_callback) if r < n_kmers]
+
+
+def learn_CART(dataset_file, split_name, criterion, max_depth, min_samples_split, class_importance, bound_delta,
+               bound_max_genome_size, kmer_blacklist_file, parameter_selection, n_cpu, authorized_rules=None,
+               progress_callback=None, warning_callback=None, error_callback=None, devices=None, comm=None):
+    """``kover learn tree`` on a Kover dataset file: same arguments and return value as the reference's
+    ``learn_CART`` (:521-649).  The packed matrix is streamed into HBM once; every hyper-parameter combination is
+    evaluated over that resident image (``n_cpu`` is accepted and ignored).  -> (best_hps, best_hp_score,
+    train_metrics, test_metrics, model, rule_importances, model_equivalent_rules, classifications)."""
+    from collections import defaultdict
+
+    from ...dataset.ds import KoverDataset
+    from ..common.models import CARTModel
+    from ..common.rules import KmerRuleClassifications, LazyKmerRuleList
+    from .experiment_scm import _as_text
+    from .metrics import _get_binary_metrics, _get_multiclass_metrics
+    warning_callback = warning_callback or (lambda w: logging.warning(w))
+    progress_callback = progress_callback or (lambda task, fraction: None)
+    if error_callback is None:
+        def error_callback(exception):
+            raise exception
+
+    dataset = KoverDataset(dataset_file)
+    rule_blacklist = _find_rule_blacklist(dataset, kmer_blacklist_file, warning_callback)
+    criterion, max_depth = np.unique(criterion), np.unique(max_depth)
+    min_samples_split = np.unique(min_samples_split)
+    # (np.unique cannot order dictionaries on Python 3; the distinct class-importance dicts keep their given order)
+    importances = []
+    for ci in class_importance:
+        if ci not in importances:
+            importances.append(ci)
+
+    split = dataset.get_split(split_name)
+    train_idx, test_idx = np.asarray(split.train_genome_idx[...]), np.asarray(split.test_genome_idx[...])
+    example_labels = np.asarray(dataset.phenotype.metadata[...])
+    phenotype_tags = dataset.phenotype.tags[...]
+    n_classes = len(phenotype_tags)
+    rules = LazyKmerRuleList(dataset.kmer_sequences, dataset.kmer_by_matrix_column)
+    rule_classifications = KmerRuleClassifications(dataset.kmer_matrix, dataset.genome_count, devices=devices, comm=comm)
+
+    if parameter_selection == "bound":
+        def hp_search(hps):
+            return learn_pruned_tree_bound(rule_classifications, rules, example_labels, train_idx, n_classes, hps,
+                                           bound_delta, bound_max_genome_size, rule_blacklist)[:3]
+        search_type = "bound selection"
+    elif parameter_selection == "cv":
+        if len(split.folds) < 1:
+            error_callback(Exception("Cross-validation cannot be performed on a split with no folds."))
+        folds = [(np.asarray(f.train_genome_idx[...]), np.asarray(f.test_genome_idx[...])) for f in split.folds]
+
+        def hp_search(hps):
+            return learn_pruned_tree_cv(rule_classifications, rules, example_labels, train_idx, folds, n_classes, hps,
+                                        rule_blacklist)
+        search_type = "cross-validation"
+    else:
+        error_callback(ValueError("Unknown hyperparameter selection strategy specified."))
+    best_hp_score, best_hps, best_master_tree = train_tree(
+        hp_search, [str(c) for c in criterion], importances, [int(d) for d in max_depth],
+        [int(m) for m in min_samples_split], progress_callback, search_type)
+
+    train_predictions, test_predictions = _predictions(best_master_tree, rule_classifications, train_idx, test_idx,
+                                                       progress_callback)
+    train_answers, test_answers = example_labels[train_idx], example_labels[test_idx]
+    binary = _as_text(dataset.classification_type) == "binary"
+    metrics_of = _get_binary_metrics if binary else (lambda p_, a_: _get_multiclass_metrics(p_, a_, n_classes))
+    train_metrics = metrics_of(train_predictions, train_answers)
+    test_metrics = metrics_of(test_predictions, test_answers) if len(test_idx) > 0 else None
+
+    genome_ids = np.array([_as_text(g) for g in dataset.genome_identifiers[...].tolist()], dtype=object)
+    classifications = defaultdict(list)
+    classifications["train_correct"] = genome_ids[train_idx[train_predictions == train_answers]].tolist() \
+        if train_metrics["risk"][0] < 1.0 else []
+    classifications["train_errors"] = genome_ids[train_idx[train_predictions != train_answers]].tolist() \
+        if train_metrics["risk"][0] > 0 else []
+    if len(test_idx) > 0:
+        classifications["test_correct"] = genome_ids[test_idx[test_predictions == test_answers]].tolist() \
+            if test_metrics["risk"][0] < 1.0 else []
+        classifications["test_errors"] = genome_ids[test_idx[test_predictions != test_answers]].tolist() \
+            if test_metrics["risk"][0] > 0 else []
+
+    best_model = CARTModel(class_tags=phenotype_tags)
+    best_model.decision_tree = best_master_tree
+    model_equivalent_rules = dict((r, [rules[i] for i in r.equivalent_rules_idx]) for r in best_master_tree.rules)
+    importance_sum = float(sum(r.importance for r in best_master_tree.rules))
+    rule_importances = dict((r, r.importance / importance_sum) for r in best_master_tree.rules)
+    rule_classifications.close()
+    dataset.close()
+    return (best_hps, best_hp_score, train_metrics, test_metrics, best_model, rule_importances, model_equivalent_rules,
+            classifications)

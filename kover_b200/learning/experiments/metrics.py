@@ -30,3 +30,14 @@ def _get_binary_metrics(predictions, answers):
         for key, value in values.items():
             metrics[key].append(value)
     return metrics
+
+
+def _get_multiclass_metrics(predictions, answers, nb_class):
+    """``risk`` and the [actual][predicted] ``confusion_matrix`` per row of ``predictions`` (metrics.py:65-92)."""
+    predictions = np.atleast_2d(predictions)
+    metrics = defaultdict(list)
+    for row in predictions:
+        metrics["risk"].append(1.0 * int(np.count_nonzero(row != answers)) / len(answers))
+        metrics["confusion_matrix"].append([[int(np.count_nonzero(row[answers == actual] == predicted))
+                                             for predicted in range(nb_class)] for actual in range(nb_class)])
+    return metrics

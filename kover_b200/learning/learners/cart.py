@@ -83,6 +83,30 @@ class DecisionTreeClassifier(object):
 
     def fit(self, rules, rule_classifications, example_idx, rule_blacklist=None, tiebreaker=None,
             level_callback=None, split_callback=None):
+        levels = self._fit_levels(rules, rule_classifications, example_idx, rule_blacklist, tiebreaker,
+                                  level_callback, split_callback)
+        answer = None
+        while True:
+            try:
+                nodes, impurity, blacklist = levels.send(answer)
+            except StopIteration:
+                return
+            answer = self._search_level(rule_classifications, nodes, impurity, blacklist)
+
+    def _search_level(self, rule_classifications, nodes, impurity, rule_blacklist):
+        """Best split of every node of ``nodes`` (class -> example indices dicts) -> [(score, candidate rules)]."""
+        if self.criterion == "gini":
+            many = getattr(rule_classifications, "gini_best_splits", None)
+            if many is not None:
+                return many(nodes, impurity.priors, impurity.n_total, rule_blacklist)
+            return [rule_classifications.gini_best_split(idx, impurity.priors, impurity.n_total, rule_blacklist)
+                    for idx in nodes]
+        return [self._cross_entropy_split(rule_classifications, impurity, idx, rule_blacklist) for idx in nodes]
+
+    def _fit_levels(self, rules, rule_classifications, example_idx, rule_blacklist=None, tiebreaker=None,
+                    level_callback=None, split_callback=None):
+        """Generator: yields (node example dicts, impurity, blacklist) once per tree level and is sent the list of
+        (best score, candidate rules) of those nodes."""
         if not hasattr(rule_classifications, "gini_best_split"):
             raise TypeError("kover_b200's DecisionTreeClassifier scans a device-resident matrix: pass a "
                             "kover_b200.learning.common.rules.KmerRuleClassifications (there is no CPU path).")
@@ -93,25 +117,13 @@ class DecisionTreeClassifier(object):
 
         example_idx = dict((c, np.asarray(idx)) for c, idx in example_idx.items())
         impurity = _NodeImpurity(example_idx, self.class_importance)
-        if self.criterion == "gini":
-            node_criterion = impurity.gini
-            search = lambda idx: rule_classifications.gini_best_split(idx, impurity.priors, impurity.n_total,
-                                                                      rule_blacklist)
-        else:
-            node_criterion = impurity.cross_entropy
-            search = lambda idx: self._cross_entropy_split(rule_classifications, impurity, idx, rule_blacklist)
+        node_criterion = impurity.gini if self.criterion == "gini" else impurity.cross_entropy
 
         def new_node(idx_by_class, depth, parent=None, counts=None):
             counts = counts if counts is not None else dict((c, len(i)) for c, i in idx_by_class.items())
             return ProbabilisticTreeNode(class_examples_idx=idx_by_class, depth=depth, parent=parent,
                                          criterion_value=node_criterion(counts), class_priors=impurity.priors,
                                          total_n_examples_by_class=impurity.n_total)
-
-        many = getattr(rule_classifications, "gini_best_splits", None)
-        if self.criterion == "gini" and many is not None:
-            search_level = lambda idx_list: many(idx_list, impurity.priors, impurity.n_total, rule_blacklist)
-        else:
-            search_level = lambda idx_list: [search(idx) for idx in idx_list]
 
         root = new_node(example_idx, 0, counts=impurity.n_total)
         # Breadth first, one level at a time (the reference pops a FIFO queue, cart.py:260-339: same visiting
@@ -129,7 +141,9 @@ class DecisionTreeClassifier(object):
             # pure nodes and nodes too small to split stay leaves
             splittable = [node for node in level_nodes
                           if not (1.0 in node.class_proportions.values() or node.n_examples < min_split)]
-            found = search_level([node.class_examples_idx for node in splittable]) if splittable else []
+            found = []
+            if splittable:
+                found = yield ([node.class_examples_idx for node in splittable], impurity, rule_blacklist)
             next_level = []
             for node, (best_score, candidates) in zip(splittable, found):
                 if best_score == np.inf:
@@ -173,6 +187,58 @@ class DecisionTreeClassifier(object):
 
     def predict_proba(self, X):
         return self._fitted_tree().predict_proba(X)
+
+
+def fit_many(learners, fit_args, rule_classifications):
+    """Grow several Gini trees over the SAME rule_classifications in lock-step -- the fold trees and the master tree
+    of a cross-validation (experiment_cart.py:345-378 grows them one after the other): at every depth the
+    splittable nodes of ALL the trees are searched together, their class masks counted 8 nodes per matrix pass.
+    fit_args: one dict of ``fit`` keyword arguments per learner.  Each learner ends in exactly the state its own
+    ``fit`` would have produced; tie lists handed to a tiebreaker are consumed before the next search starts."""
+    running = {}
+    for i, (learner, kw) in enumerate(zip(learners, fit_args)):
+        gen = learner._fit_levels(rule_classifications=rule_classifications, **kw)
+        try:
+            running[i] = (gen, next(gen))
+        except StopIteration:
+            pass
+    many = getattr(rule_classifications, "gini_best_splits", None)
+    while running:
+        batchable = [i for i in running if learners[i].criterion == "gini" and many is not None]
+        answers = {}
+        # one call per distinct blacklist (the experiments use a single blacklist for all the trees)
+        by_blacklist = {}
+        for i in batchable:
+            by_blacklist.setdefault(np.asarray(running[i][1][2], dtype=np.int64).tobytes(), []).append(i)
+        for members in by_blacklist.values():
+            nodes, priors, totals = [], [], []
+            for i in members:
+                level_nodes, impurity, _ = running[i][1]
+                nodes += level_nodes
+                priors += [impurity.priors] * len(level_nodes)
+                totals += [impurity.n_total] * len(level_nodes)
+            found = many(nodes, priors, totals, running[members[0]][1][2])
+            # the tie lists may be views of one result buffer: every learner of the batch consumes its share before
+            # the next search is issued (below), so they are handed over as they are
+            at = 0
+            for i in members:
+                n = len(running[i][1][0])
+                answers[i] = found[at:at + n]
+                at += n
+        for i in running:
+            if i not in answers:
+                level_nodes, impurity, blacklist = running[i][1]
+                answers[i] = learners[i]._search_level(rule_classifications, level_nodes, impurity, blacklist)
+                # (a per-learner search invalidates earlier views: materialise what the batch produced)
+                answers = dict((j, [(sc, np.array(c)) for sc, c in a]) if j != i else (j, a) for j, a in answers.items())
+        still_running = {}
+        for i, answer in answers.items():
+            gen = running[i][0]
+            try:
+                still_running[i] = (gen, gen.send(answer))
+            except StopIteration:
+                pass
+        running = still_running
 
 
 def _to_leaf(node):

@@ -335,8 +335,11 @@ class ShardGroup(object):
         [n_nodes, 2].  Every shard counts the class masks of up to 8 nodes per matrix pass (kv_gini_level); the
         minima are merged over shards / ranks and the tie lists of the shards that hold a node's minimum are
         concatenated in column order."""
+        n_node = np.asarray(n_node, dtype=np.int64)
+        altered_prior = np.broadcast_to(np.asarray(altered_prior, dtype=np.float64), n_node.shape)
+        n_total = np.broadcast_to(np.asarray(n_total, dtype=np.float64), n_node.shape)
         if not hasattr(self.shards[0], "gini_level"):
-            return [self.gini_best_split(m, altered_prior, n_total, nn) for m, nn in zip(node_masks, n_node)]
+            return [self.gini_best_split(m, pr, tt, nn) for m, pr, tt, nn in zip(node_masks, altered_prior, n_total, n_node)]
         per_shard = [s.gini_level(node_masks, altered_prior, n_total, n_node) for s in self.shards]
         if self._single:
             return per_shard[0]         # (the tie lists are read-only views, valid until the next level search)

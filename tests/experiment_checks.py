@@ -60,3 +60,24 @@ def check_cart_experiment_case(golden_dir, case, make_rc):
     assert min_score == float(g["min_score"]) and hps["pruning_alpha"] == float(g["best_alpha"])
     assert sorted(int(r.kmer_index) for r in tree.rules) == g["best_rules"].tolist()
     assert np.array_equal(np.asarray(C._predictions(tree, rc, [], test)[1]), g["best_test_predictions"])
+
+
+def check_cart_cv_case(golden_dir, case, make_rc):
+    """learn_pruned_tree_cv (fold trees + master tree grown in lock-step) against the REAL reference's
+    _learn_pruned_tree_cv run unmodified (tests/golden/make_golden.py::gen_cart_cv)."""
+    from kover_b200.learning.experiments import experiment_cart as C
+    name, mname, lname, seed, n_folds, max_depth, mss, imp = case
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    X, P, n, chunks = cases.matrix(mname)
+    labels = cases.labels(lname)
+    k = P.shape[1]
+    train = cases.train_subset(n, seed)
+    test = np.setdiff1d(np.arange(n), train)
+    folds = cases.cv_folds(train, n_folds, seed)
+    rules = LazyKmerRuleList(["K%d" % i for i in range(k)], np.arange(k))
+    rc = make_rc(P, n, chunks)
+    hps = {"criterion": "gini", "max_depth": max_depth, "min_samples_split": mss, "class_importance": imp}
+    hps, score, tree = C.learn_pruned_tree_cv(rc, rules, labels, train, folds, 2, hps, [])
+    assert score == float(g["cv_score"]) and hps["pruning_alpha"] == float(g["pruning_alpha"])
+    assert sorted(int(r.kmer_index) for r in tree.rules) == g["best_rules"].tolist() and len(tree) == int(g["tree_size"])
+    assert np.array_equal(np.asarray(C._predictions(tree, rc, [], test)[1]), g["best_test_predictions"])

@@ -227,6 +227,20 @@ CART_EXPERIMENT_CASES = [
 ]
 
 
+CART_CV_CASES = [
+    # name, matrix, labels, train subset seed, n folds, max_depth, min_samples_split, class_importance
+    ("cartcv_M2", "M2", "M2_planted", 51, 3, 10, 2, {0: 1.0, 1: 1.0}),
+    ("cartcv_M1_noisy", "M1", "M1_noisy", 52, 4, 6, 2, {0: 1.0, 1: 2.0}),
+    ("cartcv_MD", "MD", "MD_planted", 53, 3, 5, 4, {0: 1.0, 1: 1.0}),
+]
+
+
+def cv_folds(train, n_folds, seed):
+    """(train idx, test idx) per fold, drawn like `kover dataset split` (split.py:198-199)."""
+    fold_of = np.random.RandomState(seed).randint(0, n_folds, size=len(train))
+    return [(train[fold_of != f], train[fold_of == f]) for f in range(n_folds)]
+
+
 RISK_CASES = [
     # name, matrix, labels, train subset seed
     ("risk_M1", "M1", "M1_noisy", 41),

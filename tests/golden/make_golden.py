@@ -312,6 +312,37 @@ def gen_cart_experiments():
              master_size=np.array(len(t.decision_tree)))
 
 
+def gen_cart_cv():
+    """The REAL reference's _learn_pruned_tree_cv (experiment_cart.py:297-436), run UNMODIFIED: only the HDF5-backed
+    KoverDataset it opens is replaced by an in-memory stand-in with the same attributes."""
+    import types
+    E = ref.experiment_cart
+    for name, mname, lname, seed, n_folds, max_depth, mss, imp in cases.CART_CV_CASES:
+        X, P, n, chunks = cases.matrix(mname)
+        labels = cases.labels(lname)
+        k = P.shape[1]
+        train = cases.train_subset(n, seed)
+        folds = cases.cv_folds(train, n_folds, seed)
+
+        def stub_dataset(dataset_file):
+            split = types.SimpleNamespace(train_genome_idx=train, folds=[
+                types.SimpleNamespace(train_genome_idx=tr, test_genome_idx=te) for tr, te in folds])
+            return types.SimpleNamespace(
+                get_split=lambda split_name: split,
+                phenotype=types.SimpleNamespace(metadata=labels, tags=np.array(["0", "1"])),
+                kmer_sequences=["K%d" % i for i in range(k)], kmer_by_matrix_column=np.arange(k),
+                kmer_matrix=ChunkedArray(P, chunks), genome_count=n)
+
+        E.KoverDataset = stub_dataset
+        hps = {"criterion": "gini", "max_depth": max_depth, "min_samples_split": mss, "class_importance": imp}
+        hps, score, tree = E._learn_pruned_tree_cv(hps, "unused.kover", "unused", [])
+        test = np.setdiff1d(np.arange(n), train)
+        save(name, cv_score=np.float64(score), pruning_alpha=np.float64(hps["pruning_alpha"]),
+             best_rules=np.array(sorted(int(r.kmer_index) for r in tree.rules), dtype=np.int64),
+             tree_size=np.array(len(tree)),
+             best_test_predictions=np.asarray(E._predictions(tree, P, [], test)[1]))
+
+
 # ------------------------------------------------------------------ dataset split risk tables (f-4)
 def gen_risk():
     """dataset/split.py:171-188 cannot be called as a function (it is inlined in _split, which needs an HDF5
@@ -345,6 +376,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "cart_experiments":
         gen_cart_experiments()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "cart_cv":
+        gen_cart_cv()
+        sys.exit(0)
     gen_popcount()
     gen_pack()
     gen_rules()
@@ -354,3 +388,4 @@ if __name__ == "__main__":
     gen_risk()
     gen_experiments()
     gen_cart_experiments()
+    gen_cart_cv()

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 import cases
-from experiment_checks import check_cart_experiment_case, check_experiment_case
+from experiment_checks import check_cart_cv_case, check_cart_experiment_case, check_experiment_case
 from kover_b200.learning.common.rules import KmerRuleClassifications
 from kover_b200.sharding import ShardGroup, partition_columns
 from oracle_shard import OracleShard
@@ -25,3 +25,8 @@ def test_bound_and_cv_selection(golden_dir, case):
 @pytest.mark.parametrize("case", cases.CART_EXPERIMENT_CASES, ids=[c[0] for c in cases.CART_EXPERIMENT_CASES])
 def test_pruned_tree_bound_selection(golden_dir, case):
     check_cart_experiment_case(golden_dir, case, make_rc)
+
+
+@pytest.mark.parametrize("case", cases.CART_CV_CASES, ids=[c[0] for c in cases.CART_CV_CASES])
+def test_pruned_tree_cv_selection(golden_dir, case):
+    check_cart_cv_case(golden_dir, case, make_rc)

@@ -539,6 +539,16 @@ def test_pruned_tree_bound_selection_golden(golden_dir, case):
                                                                                              devices=[0, 0]))
 
 
+@pytest.mark.parametrize("case", cases.CART_CV_CASES, ids=[c[0] for c in cases.CART_CV_CASES])
+@pytest.mark.parametrize("devices", [[0], [0, 0]], ids=["1shard", "2shards"])
+def test_pruned_tree_cv_selection_golden(golden_dir, case, devices):
+    """Fold trees and master tree grown in LOCK-STEP on the device (the nodes of one depth of all the trees share
+    matrix passes), CV choice of the pruning parameter, against the reference's _learn_pruned_tree_cv."""
+    from experiment_checks import check_cart_cv_case
+    check_cart_cv_case(golden_dir, case, lambda P, n, chunks: KmerRuleClassifications(as_dataset(P, chunks), n,
+                                                                                     devices=devices))
+
+
 # ---------------------------------------------------------------------------------- dataset split risk tables
 @pytest.mark.parametrize("case", cases.RISK_CASES, ids=[c[0] for c in cases.RISK_CASES])
 @pytest.mark.parametrize("devices", [[0], [0, 0]], ids=["1shard", "2shards"])

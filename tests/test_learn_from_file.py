@@ -85,3 +85,36 @@ def test_learn_scm_from_file(kover_file, selection, tmp_path):
     n_train = len(f["train"])
     assert len(classifications["train_correct"]) + len(classifications["train_errors"]) == n_train
     assert all(g.startswith("genome_") for g in classifications["test_correct"])
+
+
+@pytest.mark.parametrize("selection", ["bound", "cv"])
+def test_learn_cart_from_file(kover_file, selection):
+    from kover_b200.learning.experiments import experiment_cart as cexp
+    f = kover_file
+    importances = [{0: 1.0, 1: 1.0}, {0: 1.0, 1: 2.0}]
+    out = cexp.learn_CART(f["path"], "split1", ["gini"], [3, 6], [2], importances, 0.05, 12, None, selection, 1)
+    best_hps, best_score, train_metrics, test_metrics, model, rule_imp, equiv, classifications = out
+
+    # the same search on the in-memory matrix through the functions the golden vectors pin
+    rc = KmerRuleClassifications(f["packed"], f["n"], devices=[0])
+    rules = LazyKmerRuleList(["s%d" % i for i in range(f["k"])], np.arange(f["k"]))
+    results = []
+    for imp in importances:
+        for depth in (3, 6):
+            hps = {"criterion": "gini", "class_importance": imp, "max_depth": depth, "min_samples_split": 2}
+            if selection == "bound":
+                results.append(cexp.learn_pruned_tree_bound(rc, rules, f["y"], f["train"], 2, hps, 0.05, 12, [])[:3])
+            else:
+                results.append(cexp.learn_pruned_tree_cv(rc, rules, f["y"], f["train"], [(np.sort(a), np.sort(b)) for a, b in f["folds"]],
+                                                         2, hps, []))
+    rc.close()
+    assert best_score == min(r[1] for r in results)
+    assert best_hps["criterion"] == "gini" and best_hps["max_depth"] in (3, 6) and "pruning_alpha" in best_hps
+    tree = model.decision_tree
+    used = sorted(int(r.kmer_index) for r in tree.rules)
+    assert (70 in used or 4000 in used) and 1100 in used, used
+    assert train_metrics["risk"][0] < 0.06 and test_metrics["risk"][0] < 0.1
+    assert abs(sum(rule_imp.values()) - 1.0) < 1e-12 and set(equiv.keys()) == set(tree.rules)
+    root_equiv = sorted(str(r) for r in equiv[tree.rule])
+    assert len(classifications["train_correct"]) + len(classifications["train_errors"]) == len(f["train"])
+    assert any(f["seqs"][70] in t for t in root_equiv) or any(f["seqs"][1100] in t for t in root_equiv)
