@@ -174,6 +174,15 @@ int kv_scm_queue_collect(kv_shard *s, int64_t n_slots, double *best_utility, int
 int kv_scm_queue_run(kv_shard *s, int64_t n_jobs, const uint64_t *masks, const int64_t *n_pos, const int64_t *n_neg,
                      const double *p, const int32_t *reuse, int64_t util_block_size, double *best_utility,
                      int64_t *n_found, int64_t *rule_idx, int64_t *pos_err, int64_t *neg_cover);
+/* The same lock-step grid on a PARTIAL shard (several shards per process, or one process per GPU): distinct mask
+ * pairs counted several per matrix pass, every job scored from the resident counts, each job ending as a packet
+ * (format below) at packets + job * kv_scm_packet_bytes(n_blocks, capacity) -- host memory, or device memory of
+ * the shard's GPU when packets_on_device.  The caller gathers the packets of all shards / ranks with ONE exchange
+ * for the whole grid and merges them job by job with kv_scm_merge_packets; a job whose count exceeds `capacity`
+ * on some shard is redone alone.  The first job must have reuse = 0. */
+int kv_scm_queue_packets(kv_shard *s, int64_t n_jobs, const uint64_t *masks, const int64_t *n_pos, const int64_t *n_neg,
+                         const double *p, const int32_t *reuse, int64_t util_block_size, int64_t capacity, void *packets,
+                         int packets_on_device);
 /* Multi-rank, one exchange per scan: phase 1 plus a LOCAL superset of the ties, written as one packet
  *   double block_max[n_blocks] | uint64 count | double threshold | {int64 rule, uint32 pos_err,
  *   uint32 neg_cover} records[capacity]

@@ -57,6 +57,7 @@ SYMBOLS = {
                                          ctypes.c_int]),
     "kv_scm_queue_collect": (ctypes.c_int, [_c_p, _c_i64, _c_p, _c_p, _c_p, _c_p, _c_p]),
     "kv_scm_queue_run": (ctypes.c_int, [_c_p, _c_i64, _c_p, _c_p, _c_p, _c_p, _c_p, _c_i64, _c_p, _c_p, _c_p, _c_p, _c_p]),
+    "kv_scm_queue_packets": (ctypes.c_int, [_c_p, _c_i64, _c_p, _c_p, _c_p, _c_p, _c_p, _c_i64, _c_i64, _c_p, ctypes.c_int]),
     "kv_scm_packet_bytes": (_c_i64, [_c_i64, _c_i64]),
     "kv_scm_scan_packet": (ctypes.c_int, [_c_p, _c_p, _c_p, _c_i64, _c_i64, ctypes.c_double, _c_i64, _c_i64, _c_i64,
                                           _c_p, ctypes.c_int]),
@@ -363,6 +364,28 @@ class Shard(object):
             else:
                 out.append((float(best[j]), idx[j, :m].copy(), pe[j, :m].copy(), nc[j, :m].copy()))
         return out
+
+    def scm_queue_packets(self, jobs, util_block_size, capacity, packets):
+        """The lock-step grid on a partial shard (kv_scm_queue_packets).  jobs as in scm_queue; ``packets``: a host
+        numpy uint8 array or a torch uint8 tensor on this shard's GPU of n_jobs * packet_bytes bytes, filled with one
+        packet per job."""
+        n = len(jobs)
+        masks = np.empty((n, 2, self.n_words), dtype=np.uint64)
+        for j, job in enumerate(jobs):
+            masks[j, 0], masks[j, 1] = job[1], job[2]
+        n_pos = np.array([job[3] for job in jobs], dtype=np.int64)
+        n_neg = np.array([job[4] for job in jobs], dtype=np.int64)
+        ps = np.array([job[0] for job in jobs], dtype=np.float64)
+        reuse = np.array([job[5] for job in jobs], dtype=np.int32)
+        need = n * packet_bytes(n_utility_blocks(self.n_kmers_total, util_block_size), capacity)
+        if isinstance(packets, np.ndarray):
+            assert packets.dtype == np.uint8 and packets.size >= need and packets.flags.c_contiguous
+            addr, on_device = packets.ctypes.data, 0
+        else:
+            assert packets.numel() * packets.element_size() >= need and packets.is_contiguous()
+            addr, on_device = packets.data_ptr(), int(packets.is_cuda)
+        check(self._lib.kv_scm_queue_packets(self._h, n, ptr(masks), ptr(n_pos), ptr(n_neg), ptr(ps), ptr(reuse),
+                                             int(util_block_size), int(capacity), ctypes.c_void_p(addr), on_device))
 
     def scm_best_rules(self, pos_mask, neg_mask, n_pos, n_neg, p, util_block_size, capacity=None):
         if pos_mask.dtype != np.uint64 or neg_mask.dtype != np.uint64:

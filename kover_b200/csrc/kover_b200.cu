@@ -598,6 +598,24 @@ __global__ void __launch_bounds__(32) k_scm_select_local(unsigned long long *blo
     hdr->threshold = isfinite(lmax) ? lmax - 5.0 * np_tol_dev(lmax) : -INFINITY;
 }
 
+// k_scm_select_local for up to 12 jobs (QUEUE_BATCH): one warp (block) per job
+struct SelectLocalMultiParams {
+    unsigned long long *blockmax[12];
+    double *packet_bm[12];
+    PacketHeader *hdr[12];
+    long long n_blocks;
+};
+__global__ void __launch_bounds__(32) k_scm_select_local_multi(const __grid_constant__ SelectLocalMultiParams P) {
+    __shared__ double s_bm[SELECT_SMEM_BLOCKS];
+    const int j = blockIdx.x;
+    const double *v = select_prologue(P.blockmax[j], P.n_blocks, P.packet_bm[j], s_bm);
+    if (threadIdx.x != 0) return;
+    double lmax = -INFINITY;
+    for (long long b = 0; b < P.n_blocks; ++b) lmax = fmax(lmax, v[b]);
+    P.hdr[j]->count = 0;
+    P.hdr[j]->threshold = isfinite(lmax) ? lmax - 5.0 * np_tol_dev(lmax) : -INFINITY;
+}
+
 // ------------------------------------------------------------------------------------------------
 // k_scm_ties: rules of the selected utility blocks whose utility is isclose to the block maximum
 // ------------------------------------------------------------------------------------------------
@@ -2700,7 +2718,12 @@ extern "C" int kv_scm_queue_collect(kv_shard *s, int64_t n_slots, double *best_u
 // batch), one k_scm_select_multi, one k_scm_ties_multi, each job's result landing in its queue slot.
 static int queue_score_group(kv_shard *s, const uint32_t *cnt_a, const uint32_t *cnt_b, const int64_t *job_ids, int n,
                              const int64_t *n_pos, const int64_t *n_neg, const double *p, const int32_t *reuse,
-                             int64_t ubs, int64_t n_blocks) {
+                             int64_t ubs, int64_t n_blocks, char *d_packets = nullptr, int64_t packet_capacity = 0) {
+    // d_packets != null (partial shards): instead of the exact block merge + ties into the job's queue slot, every job
+    // gets a PACKET {block maxima, count, threshold, local superset of the ties} at d_packets + job * packet_bytes
+    // (kv_scm_scan_packet's format), to be merged with the other shards' packets on the host.
+    static_assert(QUEUE_BATCH == 12, "SelectLocalMultiParams is sized for 12 jobs");
+    const int64_t packet_bytes = kv_scm_packet_bytes(n_blocks, packet_capacity);
     const MiscLayout L0 = misc_layout(nullptr, n_blocks);
     const size_t misc_stride = (L0.bytes + 255) / 256 * 256, seg_stride = (size_t)(s->ld / 64) * 2 * 8;
     KV_TRY(ensure(s->d_qmisc, misc_stride * QUEUE_BATCH));
@@ -2711,10 +2734,13 @@ static int queue_score_group(kv_shard *s, const uint32_t *cnt_a, const uint32_t 
         const int nb = std::min(QUEUE_BATCH, n - b0);
         RescoreMultiParams R;
         SelectMultiParams S;
+        SelectLocalMultiParams SL;
         TieParamsMulti T;
         memset(&R, 0, sizeof R);
         memset(&S, 0, sizeof S);
+        memset(&SL, 0, sizeof SL);
         memset(&T, 0, sizeof T);
+        SL.n_blocks = n_blocks;
         R.cnt_a = cnt_a;
         R.cnt_b = cnt_b;
         R.n_cols = s->n_cols;
@@ -2772,9 +2798,23 @@ static int queue_score_group(kv_shard *s, const uint32_t *cnt_a, const uint32_t 
             t.threshold = nullptr;
             t.out = (TieRec *)(d_hdr + 1);
             t.cap = kQueueSlotRecs;
+            if (d_packets) {
+                char *pk = d_packets + (size_t)j * packet_bytes;
+                PacketHeader *ph = (PacketHeader *)(pk + (size_t)n_blocks * 8);
+                SL.blockmax[i] = L.blockmax;
+                SL.packet_bm[i] = (double *)pk;
+                SL.hdr[i] = ph;
+                t.bm = t.tol = nullptr;
+                t.sel = nullptr;
+                t.count = &ph->count;
+                t.threshold = &ph->threshold;
+                t.out = (TieRec *)(ph + 1);
+                t.cap = packet_capacity;
+            }
         }
         k_scm_rescore_multi<<<(unsigned)(s->ld / 512), 256, 0, s->stream>>>(R);
-        k_scm_select_multi<<<nb, 32, 0, s->stream>>>(S);
+        if (d_packets) k_scm_select_local_multi<<<nb, 32, 0, s->stream>>>(SL);
+        else k_scm_select_multi<<<nb, 32, 0, s->stream>>>(S);
         k_scm_ties_multi<<<dim3(grid_ties, nb), 256, 0, s->stream>>>(T);
         count_launch(s, 3);
         s->rescore_calls += nb;
@@ -2789,7 +2829,8 @@ static int queue_score_group(kv_shard *s, const uint32_t *cnt_a, const uint32_t 
 // group leaders included -- is scored from the resident counts.
 static int scm_queue_run_grouped(kv_shard *s, int64_t n_jobs, const uint64_t *masks, const int64_t *n_pos,
                                  const int64_t *n_neg, const double *p, const int32_t *reuse, int64_t util_block_size,
-                                 int pairs_per_pass, bool batch_pairs) {
+                                 int pairs_per_pass, bool batch_pairs, char *d_packets = nullptr,
+                                 int64_t packet_capacity = 0) {
     const int64_t n_blocks = kv_scm_n_blocks(s->k_total, util_block_size);
     if (n_blocks <= 0) return fail(KV_E_INVALID, "kv_scm_queue_run: util_block_size must be positive");
     std::vector<int64_t> leaders;
@@ -2799,6 +2840,7 @@ static int scm_queue_run_grouped(kv_shard *s, int64_t n_jobs, const uint64_t *ma
     }
     s->last_launches = 0;
     KV_TRY(ensure(s->d_queue, (size_t)n_jobs * kQueueSlotBytes));
+    if (!s->d_segmax) CU(cudaMalloc(&s->d_segmax, (size_t)(s->ld / 64) * 2 * 8));
     std::vector<int64_t> ids;
     if (!batch_pairs) {
         // one matrix pass per group, fused with the leader's utility epilogue
@@ -2846,7 +2888,7 @@ static int scm_queue_run_grouped(kv_shard *s, int64_t n_jobs, const uint64_t *ma
             ids.clear();
             for (int64_t j = leaders[l]; j < j1; ++j) ids.push_back(j);
             KV_TRY(queue_score_group(s, dst[2 * (l - l0)], dst[2 * (l - l0) + 1], ids.data(), (int)ids.size(), n_pos, n_neg, p,
-                                     reuse, util_block_size, n_blocks));
+                                     reuse, util_block_size, n_blocks, d_packets, packet_capacity));
         }
     }
     s->scm_valid = false;
@@ -2877,6 +2919,37 @@ extern "C" int kv_scm_queue_run(kv_shard *s, int64_t n_jobs, const uint64_t *mas
         KV_TRY(kv_scm_queue_push(s, j, n_jobs, pm, nm, n_pos[j], n_neg[j], p[j], util_block_size, reuse[j]));
     }
     return kv_scm_queue_collect(s, n_jobs, best_utility, n_found, rule_idx, pos_err, neg_cover);
+}
+
+// The lock-step grid on a PARTIAL shard (several shards per process, or one process per GPU): same grouping as
+// kv_scm_queue_run -- distinct mask pairs counted several per matrix pass, every job scored from the counts --
+// but each job ends as a packet (kv_scm_scan_packet's format) at packets + job * kv_scm_packet_bytes(...), in host
+// memory or (packets_on_device) on the shard's GPU.  The caller gathers the packets of all shards / ranks with ONE
+// exchange for the whole grid and merges them job by job with kv_scm_merge_packets.
+extern "C" int kv_scm_queue_packets(kv_shard *s, int64_t n_jobs, const uint64_t *masks, const int64_t *n_pos,
+                                    const int64_t *n_neg, const double *p, const int32_t *reuse,
+                                    int64_t util_block_size, int64_t capacity, void *packets, int packets_on_device) {
+    if (!s || !masks || !n_pos || !n_neg || !p || !reuse || !packets)
+        return fail(KV_E_INVALID, "kv_scm_queue_packets: null pointer");
+    if (n_jobs <= 0 || capacity < 0) return fail(KV_E_INVALID, "kv_scm_queue_packets: bad job count / capacity");
+    if (reuse[0] != 0) return fail(KV_E_INVALID, "kv_scm_queue_packets: the first job must open a group (reuse = 0)");
+    const int per = max_masks_per_pass(s->W);
+    if (per < 2) return fail(KV_E_INVALID, "kv_scm_queue_packets: too many packed rows for a multi-mask pass");
+    const int64_t n_blocks = kv_scm_n_blocks(s->k_total, util_block_size);
+    if (n_blocks <= 0) return fail(KV_E_INVALID, "kv_scm_queue_packets: util_block_size must be positive");
+    const size_t bytes = (size_t)n_jobs * (size_t)kv_scm_packet_bytes(n_blocks, capacity);
+    DeviceGuard g(s->device);
+    char *d_packets = (char *)packets;
+    if (!packets_on_device) {
+        KV_TRY(ensure(s->d_stage, bytes));
+        d_packets = (char *)s->d_stage.p;
+    }
+    KV_TRY(scm_queue_run_grouped(s, n_jobs, masks, n_pos, n_neg, p, reuse, util_block_size, per / 2, true, d_packets,
+                                 capacity));
+    if (!packets_on_device) CU(cudaMemcpyAsync(packets, d_packets, bytes, cudaMemcpyDeviceToHost, s->stream));
+    CU(stream_sync_spin(s->stream));
+    CU(cudaGetLastError());
+    return KV_OK;
 }
 
 extern "C" int64_t kv_scm_packet_bytes(int64_t n_blocks, int64_t capacity) {

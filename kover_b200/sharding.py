@@ -304,6 +304,8 @@ class ShardGroup(object):
             for i, res in zip(order, self.shards[0].scm_queue(queued, util_block_size)):
                 results[i] = res
             return results
+        if all(hasattr(s, "scm_queue_packets") for s in self.shards) and (self.comm is None or len(self.shards) == 1):
+            return self._scm_grid_packets(jobs, groups, util_block_size)
         for members in groups.values():
             for rank_in_group, (i, swap) in enumerate(members):
                 p, pm, nm, n_pos, n_neg = jobs[i]
@@ -311,6 +313,42 @@ class ShardGroup(object):
                     for s in self.shards:
                         s.scm_reuse_counts(swap)
                 results[i] = self.scm_best_rules(pm, nm, n_pos, n_neg, p, util_block_size)
+        return results
+
+    def _scm_grid_packets(self, jobs, groups, util_block_size):
+        """The lock-step grid over partial shards (several per process, or one process per GPU): every shard runs
+        the whole grid locally (kv_scm_queue_packets: distinct mask pairs counted several per matrix pass, every job
+        scored from the resident counts) and emits one packet per job; ONE exchange gathers the packets of all the
+        jobs; every host then merges them job by job (max-merge of the block maxima, the reference's sequential block
+        merge, exact isclose filter).  A job whose candidates overflowed a packet is redone alone."""
+        cap = self.PACKET_CAPACITY
+        nb = _native.n_utility_blocks(self.n_kmers, util_block_size)
+        pb = _native.packet_bytes(nb, cap)
+        order, queued = [], []
+        for members in groups.values():
+            for rank_in_group, (i, swap) in enumerate(members):
+                p, pm, nm, n_pos, n_neg = jobs[i]
+                order.append(i)
+                queued.append((p, pm, nm, n_pos, n_neg, 0 if rank_in_group == 0 else (2 if swap else 1)))
+        n = len(queued)
+        if self.comm is not None:
+            local, gathered = self.comm.byte_buffers(n * pb)
+            self.shards[0].scm_queue_packets(queued, util_block_size, cap, local)
+            rows = self.comm.allgather_bytes(local, gathered).reshape(self.comm.world_size, n, pb)
+        else:
+            rows = np.empty((len(self.shards), n, pb), dtype=np.uint8)
+            for k, s in enumerate(self.shards):
+                s.scm_queue_packets(queued, util_block_size, cap, rows[k])
+        self.exchange_stats["grid_exchanges"] = self.exchange_stats.get("grid_exchanges", 0) + 1
+        results = [None] * len(jobs)
+        for slot, i in enumerate(order):
+            out, _bm, _best, _sel = merge_packets(np.ascontiguousarray(rows[:, slot]), nb, cap, queued[slot][0],
+                                                  util_block_size)
+            if out is None:                  # a huge equivalent-rule set on some shard: this job alone, two-phase
+                p, pm, nm, n_pos, n_neg = jobs[i]
+                self.exchange_stats["two_phase_fallback"] += 1
+                out = self.scm_best_rules(pm, nm, n_pos, n_neg, p, util_block_size)
+            results[i] = out
         return results
 
     # ------------------------------------------------------------------ a9 / a11

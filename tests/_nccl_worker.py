@@ -53,8 +53,26 @@ def main():
         before = shard.info()
         got = rc.best_utility_rules_grid(jobs, rule_blacklist=blacklist, util_block_size=99991)
         after = shard.info()
-        assert after.scan_calls - before.scan_calls == 1 and after.rescore_calls - before.rescore_calls == 5
+        # (one packet gather for the whole grid; every job, the group leader included, is scored from the counts)
+        assert after.scan_calls - before.scan_calls == 1 and after.rescore_calls - before.rescore_calls == 6
         for (pp, a, b), g_ in zip(jobs, got):
+            wu, wi, wp, wn = ko.merge_utility_blocks(len(b) - orc.sum_rows(b), len(a) - orc.sum_rows(a), pp, bl,
+                                                     block_size=99991)
+            assert g_[0] == wu and np.array_equal(g_[1], np.asarray(wi, dtype=np.int64)), (p2p, pp)
+            assert np.array_equal(g_[2], wp) and np.array_equal(g_[3], wn)
+        # the fits of a cross-validation in lock-step: 4 DIFFERENT mask pairs x 2 p x both roles, one pass per rank
+        fold_of = np.random.RandomState(seed).randint(0, 3, size=len(train))
+        cv_jobs = []
+        for f in range(4):
+            tr = train if f == 3 else train[fold_of != f]
+            fp, fn = tr[y[tr] == 1], tr[y[tr] == 0]
+            cv_jobs += [(pp, a, b) for pp in (0.5, 2.0) for a, b in ((fp, fn), (fn, fp))]
+        before, ex_before = shard.info(), rc._group.exchange_stats.get("grid_exchanges", 0)
+        got = rc.best_utility_rules_grid(cv_jobs, rule_blacklist=blacklist, util_block_size=99991)
+        after = shard.info()
+        assert after.scan_calls - before.scan_calls == 1 and after.rescore_calls - before.rescore_calls == len(cv_jobs)
+        assert rc._group.exchange_stats.get("grid_exchanges", 0) - ex_before == 1
+        for (pp, a, b), g_ in zip(cv_jobs, got):
             wu, wi, wp, wn = ko.merge_utility_blocks(len(b) - orc.sum_rows(b), len(a) - orc.sum_rows(a), pp, bl,
                                                      block_size=99991)
             assert g_[0] == wu and np.array_equal(g_[1], np.asarray(wi, dtype=np.int64)), (p2p, pp)

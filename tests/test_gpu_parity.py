@@ -369,9 +369,10 @@ def test_grid_shares_matrix_passes():
         assert np.array_equal(g_[2], wp) and np.array_equal(g_[3], wn)
 
 
+@pytest.mark.parametrize("devices", [[0], [0, 0, 0]], ids=["1shard", "3shards"])
 @pytest.mark.parametrize("sorted_labels", [True, False], ids=["sorted", "interleaved"])
 @pytest.mark.parametrize("n_folds", [2, 5, 11])
-def test_grid_batches_distinct_mask_pairs(sorted_labels, n_folds):
+def test_grid_batches_distinct_mask_pairs(sorted_labels, n_folds, devices):
     """The fits of a cross-validation in lock-step: every fold is a DIFFERENT mask pair.  They are counted several
     pairs per matrix pass (k_count_tma) and scored from the resident counts; results identical to independent
     scans, ceil(pairs / 8) matrix passes instead of one per pair."""
@@ -381,8 +382,7 @@ def test_grid_batches_distinct_mask_pairs(sorted_labels, n_folds):
     train = train_split(seed, n)
     rs = np.random.RandomState(seed)
     fold_of = rs.randint(0, n_folds, size=len(train))
-    rc = KmerRuleClassifications(P, n, devices=[0])
-    shard = rc._group.shards[0]
+    rc = KmerRuleClassifications(P, n, devices=devices)
     jobs = []
     for f in range(n_folds + 1):
         tr = train if f == n_folds else train[fold_of != f]
@@ -394,12 +394,15 @@ def test_grid_batches_distinct_mask_pairs(sorted_labels, n_folds):
             jobs.append((p_, neg, pos))
     bl = rs.choice(2 * k, size=500, replace=False)
     want = [rc.best_utility_rules(p_, a, b, rule_blacklist=bl, util_block_size=30000) for p_, a, b in jobs]
-    before = shard.info()
+    before = [s_.info() for s_ in rc._group.shards]
     got = rc.best_utility_rules_grid(jobs, rule_blacklist=bl, util_block_size=30000)
-    after = shard.info()
+    after = [s_.info() for s_ in rc._group.shards]
     n_pairs = n_folds + 1
-    assert after.scan_calls - before.scan_calls == -(-n_pairs // 8)
-    assert after.rescore_calls - before.rescore_calls == len(jobs)
+    for b_, a_ in zip(before, after):          # every shard: ceil(pairs / 8) passes, every job scored from the counts
+        assert a_.scan_calls - b_.scan_calls == -(-n_pairs // 8)
+        assert a_.rescore_calls - b_.rescore_calls == len(jobs)
+    if len(devices) > 1:                       # several shards: ONE packet gather for the whole grid
+        assert rc._group.exchange_stats.get("grid_exchanges", 0) == 1
     for w, g_ in zip(want, got):
         assert w[0] == g_[0] and all(np.array_equal(a, b) for a, b in zip(w[1:], g_[1:]))
     rc.close()
