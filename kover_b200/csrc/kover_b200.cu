@@ -2949,6 +2949,8 @@ extern "C" int kv_scm_queue_packets(kv_shard *s, int64_t n_jobs, const uint64_t 
     if (!packets_on_device) CU(cudaMemcpyAsync(packets, d_packets, bytes, cudaMemcpyDeviceToHost, s->stream));
     CU(stream_sync_spin(s->stream));
     CU(cudaGetLastError());
+    float ms = 0;                                   // ev0 / ev1 bracket the (last) multi-mask pass
+    if (cudaEventElapsedTime(&ms, s->ev0, s->ev1) == cudaSuccess) s->last_kernel_ms = ms;
     return KV_OK;
 }
 
