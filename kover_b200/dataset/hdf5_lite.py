@@ -23,6 +23,15 @@ import numpy as np
 
 _SIGNATURE = b"\x89HDF\r\n\x1a\n"
 _UNDEF = 0xFFFFFFFFFFFFFFFF
+_POOL = None
+
+
+def _pool():
+    """One inflate pool per process (zlib releases the GIL): chunk reads of a slab run on all the host cores."""
+    global _POOL
+    if _POOL is None:
+        _POOL = ThreadPoolExecutor(max_workers=max(2, min(32, os.cpu_count() or 8)))
+    return _POOL
 
 
 class _VlenStr(object):
@@ -517,9 +526,9 @@ class Dataset(_Object):
             return np.frombuffer(self._f._read(self._addr, self.size * sd.itemsize), dtype=sd).reshape(self.shape)
         return self._read_box_raw(tuple((0, n) for n in self.shape))
 
-    def _read_box_raw(self, box, threads=8):
+    def _read_box_raw(self, box, threads=None):
         """The hyper-rectangle ``box`` = ((lo, hi), ...) of a chunked dataset, chunks inflated by a thread pool
-        (zlib releases the GIL)."""
+        (zlib releases the GIL).  threads: None = the process-wide pool, 1 = inline, n = a private pool."""
         out = np.zeros(tuple(hi - lo for lo, hi in box), dtype=self._storage_dtype())
         ranges = [range((lo // c) * c, hi, c) for (lo, hi), c in zip(box, self.chunks)]
         todo = [()]
@@ -535,7 +544,9 @@ class Dataset(_Object):
                 dst.append(slice(a - lo, b - lo))
             out[tuple(dst)] = chunk[tuple(src)]
 
-        if len(todo) > 4 and threads > 1:
+        if len(todo) > 4 and threads is None:
+            list(_pool().map(place, todo))
+        elif len(todo) > 4 and threads > 1:
             with ThreadPoolExecutor(max_workers=threads) as pool:
                 list(pool.map(place, todo))
         else:
@@ -596,8 +607,12 @@ class Dataset(_Object):
             raw = self._read_box_raw(tuple(box))
         else:
             raw = self._read_all_raw()[tuple(slice(lo, hi) for lo, hi in box)]
-        out = self._finish(np.asarray(raw))[tuple(post)]
+        whole = all(isinstance(q, slice) for q in post)
+        out = self._finish(np.asarray(raw))
+        out = out if whole else out[tuple(post)]
         if isinstance(out, np.ndarray):
+            if self._kind == "chunked" and whole and out.flags.owndata:
+                return out                                     # assembled from inflated chunks: already a private copy
             return np.array(out)                               # own the memory (the file may be closed later)
         if isinstance(out, np.bytes_):
             return bytes(out)

@@ -144,17 +144,30 @@ class KmerRuleClassifications(BaseRuleClassifications):
         return ShardGroup([_native.Shard(d, n, k, c0, nc) for d, (c0, nc) in zip(devices, slices)], n, k)
 
     def _upload(self, slab_bytes=128 << 20):
-        """Stream the packed matrix into HBM: row slabs x the column span of the local shards."""
+        """Stream the packed matrix into HBM: row slabs x the column span of the local shards.  The next slab is
+        read (HDF5: chunk reads + inflate on the host cores) while the current one is staged and copied."""
+        from concurrent.futures import ThreadPoolExecutor
         ds = self.dataset
         itemsize = np.dtype(ds.dtype).itemsize
         n_packed_rows = int(ds.shape[0])
         needed_rows = -(-int(self.dataset_initial_n_rows) // self.dataset_pack_size)
+        chunk_rows = (getattr(ds, "chunks", None) or (1,))[0] or 1
+        slabs = []
         for s in self._group.shards:
             c0, c1 = s.col0, s.col0 + s.n_cols
             rows_per_slab = max(1, min(needed_rows, slab_bytes // max(1, s.n_cols * itemsize)))
+            rows_per_slab = max(chunk_rows, rows_per_slab // chunk_rows * chunk_rows)     # whole chunk rows per read
             for r0 in range(0, min(needed_rows, n_packed_rows), rows_per_slab):
-                r1 = min(r0 + rows_per_slab, needed_rows, n_packed_rows)
-                block = np.asarray(ds[r0:r1, c0:c1])
+                slabs.append((s, r0, min(r0 + rows_per_slab, needed_rows, n_packed_rows), c0, c1))
+        if not slabs:
+            return
+        read = lambda slab: np.asarray(ds[slab[1]:slab[2], slab[3]:slab[4]])
+        with ThreadPoolExecutor(max_workers=1) as prefetch:
+            pending = prefetch.submit(read, slabs[0])
+            for i, (s, r0, r1, c0, c1) in enumerate(slabs):
+                block = pending.result()
+                if i + 1 < len(slabs):
+                    pending = prefetch.submit(read, slabs[i + 1])
                 s.upload_block(block, r0, c0)
 
     def close(self):
