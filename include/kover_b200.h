@@ -60,6 +60,10 @@ typedef struct kv_shard_info {
 
 const char *kv_last_error(void);
 int kv_abi_version(void);
+/* Page-locked host memory for caller-owned result arrays (optional: every entry point accepts pageable pointers;
+ * copies into pinned memory run at the PCIe rate instead of the 4-6 GB/s of staged pageable copies). */
+int kv_host_alloc(int64_t bytes, void **out);
+int kv_host_free(void *p);
 int kv_device_count(int *n_devices);
 
 /* ---- lifecycle ---------------------------------------------------------------------------

@@ -77,6 +77,8 @@ SYMBOLS = {
                                           _c_i64, _c_p, ctypes.POINTER(_c_i64)]),
     "kv_gini_ties": (ctypes.c_int, [_c_p, ctypes.c_double, _c_i64, _c_p, ctypes.POINTER(_c_i64)]),
     "kv_gini_scores": (ctypes.c_int, [_c_p, _c_p]),
+    "kv_host_alloc": (ctypes.c_int, [_c_i64, ctypes.POINTER(ctypes.c_void_p)]),
+    "kv_host_free": (ctypes.c_int, [_c_p]),
     "kv_gini_level": (ctypes.c_int, [_c_p, _c_i64, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p]),
     "kv_gini_level_fetch": (ctypes.c_int, [_c_p, _c_i64, _c_p, _c_i64]),
     "kv_gini_level_result": (ctypes.c_int, [_c_p, _c_i64, ctypes.POINTER(ctypes.POINTER(ctypes.c_int64)),
@@ -132,6 +134,50 @@ def ptr(a):
         return None
     assert a.flags.c_contiguous
     return a.ctypes.data_as(ctypes.c_void_p)
+
+
+# ---- pinned result arrays ------------------------------------------------------------------------
+_PINNED_FREE = {}            # rounded size -> [addresses] of page-locked blocks nobody references any more
+_PINNED_MIN = 1 << 20        # smaller results stay in ordinary numpy memory
+_PINNED_CACHE_LIMIT = 4 << 30
+_pinned_cached_bytes = 0
+
+
+def _pinned_release(addr, size):
+    global _pinned_cached_bytes
+    if _pinned_cached_bytes + size > _PINNED_CACHE_LIMIT:
+        try:
+            load().kv_host_free(ctypes.c_void_p(addr))
+        except Exception:  # noqa: BLE001 (interpreter shutdown)
+            pass
+        return
+    _PINNED_FREE.setdefault(size, []).append(addr)
+    _pinned_cached_bytes += size
+
+
+def result_empty(shape, dtype):
+    """np.empty for RESULT arrays that a device-to-host copy fills: page-locked memory from a recycling pool when
+    the array is large (a block returns to the pool when the last view of the array dies), plain numpy otherwise
+    or when pinning fails.  The caller owns the array like any numpy array."""
+    global _pinned_cached_bytes
+    import weakref
+    dtype = np.dtype(dtype)
+    nbytes = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
+    if nbytes < _PINNED_MIN:
+        return np.empty(shape, dtype=dtype)
+    size = 1 << (nbytes - 1).bit_length() if nbytes < (64 << 20) else -(-nbytes // (16 << 20)) * (16 << 20)
+    free = _PINNED_FREE.get(size)
+    if free:
+        addr = free.pop()
+        _pinned_cached_bytes -= size
+    else:
+        p = ctypes.c_void_p()
+        if load().kv_host_alloc(size, ctypes.byref(p)) != 0:
+            return np.empty(shape, dtype=dtype)
+        addr = p.value
+    block = (ctypes.c_char * size).from_address(addr)
+    weakref.finalize(block, _pinned_release, addr, size)       # every numpy view keeps `block` alive through .base
+    return np.frombuffer(block, dtype=dtype, count=nbytes // dtype.itemsize).reshape(shape)
 
 
 def device_count():
@@ -229,7 +275,7 @@ class Shard(object):
     def sum_rows_multi(self, masks):
         masks = np.ascontiguousarray(masks, dtype=np.uint64)
         assert masks.ndim == 2 and masks.shape[1] == self.n_words
-        out = np.empty((masks.shape[0], self.n_cols), dtype=np.uint32)
+        out = result_empty((masks.shape[0], self.n_cols), np.uint32)
         check(self._lib.kv_sum_rows_multi(self._h, masks.shape[0], ptr(masks), ptr(out)))
         return out
 

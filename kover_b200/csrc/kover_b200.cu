@@ -74,6 +74,23 @@ static inline cudaError_t stream_sync_spin(cudaStream_t st) {
 extern "C" const char *kv_last_error(void) { return g_err.c_str(); }
 extern "C" int kv_abi_version(void) { return 1; }
 
+// Page-locked host memory for the CALLER's result arrays: a D2H copy into pageable memory runs at 4-6 GB/s (driver
+// staging + first-touch page faults), into pinned memory at the PCIe rate.  The Python layer keeps a pool of these
+// and wraps them as numpy arrays (sum_rows returns 2K counts: 40 MB per call at config 2).
+extern "C" int kv_host_alloc(int64_t bytes, void **out) {
+    if (!out || bytes <= 0) return fail(KV_E_INVALID, "kv_host_alloc: bad arguments");
+    *out = nullptr;
+    if (cudaHostAlloc(out, (size_t)bytes, cudaHostAllocPortable) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(KV_E_NOMEM, "kv_host_alloc: cannot pin host memory");
+    }
+    return KV_OK;
+}
+extern "C" int kv_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+    return KV_OK;
+}
+
 extern "C" int kv_device_count(int *n) {
     if (!n) return fail(KV_E_INVALID, "kv_device_count: null pointer");
     CU(cudaGetDeviceCount(n));

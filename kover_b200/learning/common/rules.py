@@ -243,7 +243,7 @@ class KmerRuleClassifications(BaseRuleClassifications):
         rows = np.asarray(rows)
         result_dtype = _minimum_uint_size(rows.shape[0])
         n_kmers = self._n_kmers
-        result = np.empty(n_kmers * 2, dtype=result_dtype)
+        result = _native.result_empty(n_kmers * 2, result_dtype)      # (page-locked when large: D2H at the PCIe rate)
         mask = self.row_mask(rows)
         # presence counts and, for the absence rules, len(rows) - presence (rules.py:265): both halves are
         # produced on the device in the result dtype

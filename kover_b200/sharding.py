@@ -202,8 +202,8 @@ class ShardGroup(object):
         lut_kmer[e] = inverse[:e.shape[0]]
         lut_anti[e] = inverse[e.shape[0]:]
         dtype = _minimum_uint_size(len(unique_risks))
-        by_kmer = np.empty(self.n_kmers, dtype=dtype)
-        by_anti = np.empty(self.n_kmers, dtype=dtype)
+        by_kmer = _native.result_empty(self.n_kmers, dtype)
+        by_anti = _native.result_empty(self.n_kmers, dtype)
         for s in self.shards:
             s.risk_map(lut_kmer, lut_anti, by_kmer[s.col0:s.col0 + s.n_cols], by_anti[s.col0:s.col0 + s.n_cols])
         return unique_risks, by_kmer, by_anti
@@ -408,6 +408,8 @@ class ShardGroup(object):
         if self.comm is not None:
             raise NotImplementedError("sum_rows_multi is per-process")
         masks = np.ascontiguousarray(masks, dtype=np.uint64)
+        if len(self.shards) == 1:
+            return self.shards[0].sum_rows_multi(masks)
         out = np.empty((masks.shape[0], self.n_kmers), dtype=np.uint32)
         for s in self.shards:
             out[:, s.col0:s.col0 + s.n_cols] = s.sum_rows_multi(masks)
