@@ -17,9 +17,10 @@ vectors) and by ``tests/test_oracle_vs_reference.py`` (skipped when absent).
 Mechanical patch list (each is a syntax/stdlib rename, never a semantic change):
   xrange -> range; dict.iter{items,keys,values} -> {items,keys,values};
   np.bool/np.float/np.infty -> bool/float/np.inf; integer ``/`` used as floor
-  division in build_row_mask (rules.py:218,222) and a debug format (scm.py:84)
-  -> ``//``; ``d.keys()[0]`` -> ``list(d.keys())[0]`` (cart.py:141, tree.py:108);
-  ``scipy.misc.comb`` -> ``scipy.special.comb``; ``np.vstack(<generator>)`` -> ``np.vstack([...])``
+  division in build_row_mask (rules.py:218,222), a debug format (scm.py:84) and ``n_kmers =
+  shape[1] / 2`` (experiment_scm.py:286,455) -> ``//``; ``d.keys()[0]`` -> ``list(d.keys())[0]`` (cart.py:141, tree.py:108);
+  ``scipy.misc.comb`` -> ``scipy.special.comb``; ``np.var(d.values())`` -> ``np.var(list(d.values()))``
+  (experiment_cart.py:477); ``np.vstack(<generator>)`` -> ``np.vstack([...])``
   (experiment_cart.py:139); tabs expanded in models.py / metrics.py;
   ``import h5py`` satisfied by a stub (h5py is not installed in this image).
 """
@@ -55,6 +56,9 @@ _SUBS = [
     (r"idx / mask_n_bits", "idx // mask_n_bits"),
     (r"mask_n_bits / 8", "mask_n_bits // 8"),
     (r"len\(rule_blacklist\) / 2", "len(rule_blacklist) // 2"),
+    (r"rule_classifications\.shape\[1\] / 2", "rule_classifications.shape[1] // 2"),      # experiment_scm.py:286, 455
+    # dict.values() is a view on Python 3 (experiment_cart.py:477)
+    (r'np\.var\((\w+)\["class_importance"\]\.values\(\)\)', r'np.var(list(\1["class_importance"].values()))'),
     (r"left_n_examples_by_class\.keys\(\)\[0\]", "list(left_n_examples_by_class.keys())[0]"),
     (r"self\.breiman_info\.p_j_given_t\.keys\(\)\[np\.argmax\(self\.breiman_info\.p_j_given_t\.values\(\)\)\]",
      "list(self.breiman_info.p_j_given_t.keys())[np.argmax(list(self.breiman_info.p_j_given_t.values()))]"),

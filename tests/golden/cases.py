@@ -241,6 +241,43 @@ def cv_folds(train, n_folds, seed):
     return [(train[fold_of != f], train[fold_of == f]) for f in range(n_folds)]
 
 
+# ----------------------------------------------------------------------------- dataset-file drivers
+DRIVER_CASES = [
+    # name, matrix, labels, seed, n folds, learner, parameter_selection, max_equiv_rules
+    ("drv_scm_bound_M1", "M1", "M1_planted", 61, 3, "scm", "bound", 10000),
+    ("drv_scm_cv_M1", "M1", "M1_noisy", 62, 4, "scm", "cv", 2),
+    ("drv_scm_none_MD", "MD", "MD_planted", 63, 3, "scm", "none", 10000),
+    ("drv_cart_bound_M2", "M2", "M2_planted", 64, 3, "cart", "bound", None),
+    ("drv_cart_cv_M1", "M1", "M1_noisy", 65, 3, "cart", "cv", None),
+]
+DRIVER_SCM_ARGS = dict(model_type=["conjunction", "disjunction"], p=[0.5, 1.0, 2.0], max_rules=4, random_seed=42,
+                       bound_delta=0.05, bound_max_genome_size=1000)
+# (one class-importance dictionary: the reference's np.unique over dictionaries, experiment_cart.py:545, only runs on
+# Python 2, where dictionaries are ordered)
+DRIVER_CART_ARGS = dict(criterion=["gini"], max_depth=[6, 2, 4], min_samples_split=[2, 6],
+                        class_importance=[{0: 1.0, 1: 2.0}], bound_delta=0.05, bound_max_genome_size=1000)
+
+
+def driver_dataset(case):
+    """Everything a Kover dataset file of a DRIVER case holds (numpy, no HDF5): the golden generator serves it to the
+    reference through a stand-in KoverDataset, the tests write it to an HDF5 file."""
+    name, mname, lname, seed, n_folds = case[:5]
+    X, P, n, chunks = matrix(mname)
+    y = labels(lname)
+    k = P.shape[1]
+    train = train_subset(n, seed)
+    test = np.setdiff1d(np.arange(n), train)
+    folds = cv_folds(train, n_folds, seed)
+    seqs = ["".join("ACGT"[(i >> (2 * j)) & 3] for j in range(12)) for i in range(k)]     # sequence of matrix column i
+    perm = np.random.RandomState(seed).permutation(k)      # kmer_by_matrix_column: column -> index in kmer_sequences
+    ordered = [None] * k
+    for col, seq_idx in enumerate(perm):
+        ordered[seq_idx] = seqs[col]
+    ids = ["genome_%d" % i for i in range(n)]
+    return dict(P=P, n=n, k=k, chunks=chunks, y=y, train=train, test=test, folds=folds, kmer_sequences=ordered,
+                kmer_by_matrix_column=perm, genome_identifiers=ids, column_sequences=seqs)
+
+
 RISK_CASES = [
     # name, matrix, labels, train subset seed
     ("risk_M1", "M1", "M1_noisy", 41),

@@ -343,6 +343,81 @@ def gen_cart_cv():
              best_test_predictions=np.asarray(E._predictions(tree, P, [], test)[1]))
 
 
+class _SerialPool(object):
+    """multiprocessing.Pool stand-in: tasks run in order in this process, each with ITS OWN copy of the callable,
+    like a task unpickled in a pool worker (experiment_scm.py:594-603 hands the random generator over that way)."""
+
+    def __init__(self, processes=None):
+        pass
+
+    def imap_unordered(self, func, iterable):
+        from copy import deepcopy
+        for item in iterable:
+            yield deepcopy(func)(item)
+
+
+def _stub_dataset(d):
+    """In-memory KoverDataset with the attributes the reference's drivers read (dataset/ds.py:27-196)."""
+    import types
+    from oracle import kover_oracle as ko
+    orc = ko.OracleKmerRuleClassifications(d["P"], d["n"], fast=True)
+    y = d["y"]
+
+    def tables(tr):
+        ur, bk, ba = ko.kmer_risk_tables(orc, tr[y[tr] == 1], tr[y[tr] == 0])
+        return dict(unique_risks=ur, unique_risk_by_kmer=bk, unique_risk_by_anti_kmer=ba)
+
+    folds = [types.SimpleNamespace(name="fold_%d" % (i + 1), train_genome_idx=np.sort(tr), test_genome_idx=np.sort(te),
+                                   **tables(tr)) for i, (tr, te) in enumerate(d["folds"])]
+    split = types.SimpleNamespace(name="split1", train_genome_idx=d["train"], test_genome_idx=d["test"], folds=folds,
+                                  **tables(d["train"]))
+    ds = types.SimpleNamespace(
+        get_split=lambda split_name: split, genome_count=d["n"], kmer_count=d["k"], kmer_length=12,
+        classification_type="binary",
+        phenotype=types.SimpleNamespace(metadata=y, tags=np.array(["0", "1"])),
+        kmer_sequences=np.array(d["kmer_sequences"]), kmer_by_matrix_column=d["kmer_by_matrix_column"],
+        kmer_matrix=ChunkedArray(d["P"], d["chunks"]), genome_identifiers=np.array(d["genome_identifiers"]))
+    return lambda dataset_file: ds
+
+
+def gen_drivers():
+    """The REAL reference's learn_SCM (experiment_scm.py:675-888) and learn_CART (experiment_cart.py:521-649), run
+    UNMODIFIED end to end: only the HDF5-backed KoverDataset and the fork pool are replaced by in-process
+    stand-ins."""
+    S, C = ref.experiment_scm, ref.experiment_cart
+    for case in cases.DRIVER_CASES:
+        name, _, _, _, _, learner, selection, max_equiv = case
+        d = cases.driver_dataset(case)
+        if learner == "scm":
+            S.KoverDataset, S.Pool = _stub_dataset(d), _SerialPool
+            a = cases.DRIVER_SCM_ARGS
+            out = S.learn_SCM("unused.kover", "split1", a["model_type"], a["p"], None, a["max_rules"], max_equiv, selection,
+                              1, a["random_seed"], None, bound_delta=a["bound_delta"],
+                              bound_max_genome_size=a["bound_max_genome_size"])
+            best_hp, score, trm, tem, model, imp, equiv, cls = out
+            save(name, best_hp=json.dumps({k_: (v.item() if hasattr(v, "item") else v) for k_, v in best_hp.items()}),
+                 score=np.float64(np.nan if score is None else score),
+                 train_risk=np.float64(trm["risk"][0]), test_risk=np.float64(tem["risk"][0]),
+                 train_bound=np.float64(trm["bound"]), train_f1=np.float64(trm["f1_score"][0]),
+                 model=json.dumps([str(r) for r in model]), importances=np.asarray(imp, dtype=np.float64),
+                 equiv=json.dumps([sorted(str(r) for r in e) for e in equiv]),
+                 classifications=json.dumps({k_: list(v) for k_, v in cls.items()}))
+        else:
+            C.KoverDataset, C.Pool = _stub_dataset(d), _SerialPool
+            a = cases.DRIVER_CART_ARGS
+            out = C.learn_CART("unused.kover", "split1", a["criterion"], a["max_depth"], a["min_samples_split"],
+                               a["class_importance"], a["bound_delta"], a["bound_max_genome_size"], None, selection, 1, None)
+            best_hps, score, trm, tem, model, imp, equiv, cls = out
+            tree = model.decision_tree
+            save(name, best_hps=json.dumps({k_: ({str(c): w for c, w in v.items()} if isinstance(v, dict) else
+                                                  (v.item() if hasattr(v, "item") else v)) for k_, v in best_hps.items()}),
+                 score=np.float64(score), train_risk=np.float64(trm["risk"][0]), test_risk=np.float64(tem["risk"][0]),
+                 rules=json.dumps(sorted(str(r) for r in tree.rules)), tree_size=np.array(len(tree)),
+                 importances=json.dumps(sorted((str(r), float(v)) for r, v in imp.items())),
+                 equiv=json.dumps(sorted((str(r), sorted(str(e) for e in v)) for r, v in equiv.items())),
+                 classifications=json.dumps({k_: list(v) for k_, v in cls.items()}))
+
+
 # ------------------------------------------------------------------ dataset split risk tables (f-4)
 def gen_risk():
     """dataset/split.py:171-188 cannot be called as a function (it is inlined in _split, which needs an HDF5
@@ -379,6 +454,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "cart_cv":
         gen_cart_cv()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "drivers":
+        gen_drivers()
+        sys.exit(0)
     gen_popcount()
     gen_pack()
     gen_rules()
@@ -389,3 +467,4 @@ if __name__ == "__main__":
     gen_experiments()
     gen_cart_experiments()
     gen_cart_cv()
+    gen_drivers()

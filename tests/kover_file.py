@@ -8,8 +8,9 @@ from oracle import kover_oracle as ko
 
 
 def write_kover_file(path, packed, n_genomes, labels, train_idx, test_idx, folds, seed=42, chunks=(1, 1000), gzip=4,
-                     fixed_strings=False):
-    """packed: uint64/uint32 [W, K]; folds: list of (train_idx, test_idx)."""
+                     fixed_strings=False, names=None):
+    """packed: uint64/uint32 [W, K]; folds: list of (train_idx, test_idx); names: optional (kmer_sequences in file
+    order, kmer_by_matrix_column, genome_identifiers) -- generated from `seed` when omitted."""
     k = packed.shape[1]
     rc = ko.OracleKmerRuleClassifications(packed, n_genomes, fast=True)
     w = Writer(path)
@@ -22,12 +23,17 @@ def write_kover_file(path, packed, n_genomes, labels, train_idx, test_idx, folds
     ordered = [None] * k
     for col, seq_idx in enumerate(perm):
         ordered[seq_idx] = seqs[col]
+    ids = ["genome_%d" % i for i in range(n_genomes)]
+    if names is not None:
+        ordered, perm, ids = names
+        perm = np.asarray(perm)
+        seqs = [ordered[perm[col]] for col in range(k)]
     if fixed_strings:
         w.create_dataset("kmer_sequences", np.array(ordered, dtype="S12"), chunks=(max(1, min(k, 4096)),), compression=gzip)
-        w.create_dataset("genome_identifiers", np.array(["genome_%d" % i for i in range(n_genomes)], dtype="S16"))
+        w.create_dataset("genome_identifiers", np.array(ids, dtype="S16"))
     else:
         w.create_dataset("kmer_sequences", np.array(ordered, dtype=object), chunks=(max(1, min(k, 4096)),), compression=gzip)
-        w.create_dataset("genome_identifiers", np.array(["genome_%d" % i for i in range(n_genomes)], dtype=object))
+        w.create_dataset("genome_identifiers", np.array(ids, dtype=object))
     w.create_dataset("kmer_by_matrix_column", perm.astype(_minimum_uint_size(k)), chunks=(max(1, min(k, 4096)),),
                      compression=gzip)
     w.create_dataset("phenotype", np.asarray(labels, dtype=np.uint8), attrs={"description": "synthetic phenotype"})
