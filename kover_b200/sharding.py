@@ -385,14 +385,22 @@ class ShardGroup(object):
         mins = np.array([[res[i][0] for i in range(n_nodes)] for res in per_shard], dtype=np.float64).min(axis=0)
         if self.comm is not None:
             mins = self.comm.allreduce_min(mins)
-        out = []
+        local = []
         for i in range(n_nodes):
             m = float(mins[i])
             parts = [res[i][1] for res in per_shard if res[i][0] == m and m != np.inf]
-            idx = np.concatenate(parts) if parts else np.zeros(0, dtype=np.int64)
-            if self.comm is not None:
-                idx = self.comm.allgather_concat(idx)
-            out.append((m, np.sort(idx)))
+            local.append(np.concatenate(parts) if parts else np.zeros(0, dtype=np.int64))
+        if self.comm is None:
+            return [(float(mins[i]), np.sort(local[i])) for i in range(n_nodes)]
+        # one exchange for the whole level: every rank's per-node tie counts, then all the tie indices at once
+        sizes = np.array([len(a) for a in local], dtype=np.int64)
+        all_sizes = self.comm.allgather_concat(sizes).reshape(self.comm.world_size, n_nodes)
+        flat = self.comm.allgather_concat(np.concatenate(local) if n_nodes else np.zeros(0, dtype=np.int64))
+        starts = np.concatenate(([0], np.cumsum(all_sizes.reshape(-1))))
+        out = []
+        for i in range(n_nodes):
+            parts = [flat[starts[r * n_nodes + i]:starts[r * n_nodes + i + 1]] for r in range(self.comm.world_size)]
+            out.append((float(mins[i]), np.sort(np.concatenate(parts))))
         return out
 
     def gini_scores(self):
