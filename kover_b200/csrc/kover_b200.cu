@@ -846,55 +846,71 @@ struct RescoreMultiParams {
     unsigned long long *blockmax[QUEUE_BATCH], *segmax[QUEUE_BATCH];
 };
 
-// a chunk that straddles a utility-block boundary (rare): per-rule atomics, kept out of line
-__device__ __noinline__ void rescore_straddle(unsigned long long *blockmax, long long rule0, long long ubs, double u0,
-                                              double u1, bool v0, bool v1) {
-    if (v0) atomicMax(blockmax + rule0 / ubs, enc_f64(u0));
-    if (v1) atomicMax(blockmax + (rule0 + 1) / ubs, enc_f64(u1));
+// 2 048 columns per CTA: every warp owns 256 consecutive columns, every lane eight of them (two 128-bit loads per
+// count array).  The kernel is issue-bound, not memory-bound (the first versions spent ~150, then ~100 instructions
+// per warp, job and 64 columns -- profiles/README.md), so the per-job overhead (parameter loads, order-preserving
+// image, the two redux.sync of a 64-bit maximum, the store) is paid once per 256 columns: the maximum of the 256
+// columns is written to all four of their 64-column segment slots, an UPPER bound of each, which is all the tie
+// kernel's screening needs (it only skips segments whose bound cannot reach the block maximum).  The counts are
+// converted to double ONCE (int -> double conversions run on the 16-lane XU pipe and would otherwise dominate);
+// n_neg - cnt is then formed in double, which is exact for integers and therefore the same value the reference
+// converts (scm.py:245-264).  Jobs are ordered plain-then-swapped by the host so that the roles of the two count
+// arrays are fixed per loop.
+// exact uint32 -> double without the XU pipe's I2F: 2^52 + x has x in its low mantissa bits; subtracting 2^52 is exact
+__device__ __forceinline__ double u32_to_f64(uint32_t x) {
+    return __dsub_rn(__hiloint2double(0x43300000, (int)x), 4503599627370496.0);
 }
 
-// 512 columns per CTA: every warp owns one 64-column segment, every lane two adjacent columns, so that the segment
-// maxima are full-warp redux.sync.  The counts are converted to double ONCE (int -> double conversions run on the
-// 16-lane XU pipe and would otherwise dominate); n_neg - cnt is then formed in double, which is exact for integers
-// and therefore the same value the reference converts (scm.py:245-264).  The kernel is issue-bound (about 150
-// instructions per warp and job before this shape, profiles/README.md), hence: jobs ordered plain-then-swapped so
-// that the roles of the two count arrays are fixed per loop, per-job scalars pre-converted on the host, maxima
-// taken on the order-preserving integer images.
 struct RescoreLane {
-    double cp0, cp1, cn0, cn1;      // presence counts of the lane's two columns under the positive / negative mask
-    uint32_t dead_p, dead_a;
-    bool any_dead, uniform[2];
-    long long col, rule0[2];
+    double cp[8], cn[8];            // presence counts of the lane's columns under the positive / negative mask
+    uint32_t dead_p, dead_a;        // bit q: rule of column q must score -inf (padding column / blacklisted)
+    bool uniform[2];
+    long long col[2], rule0[2];     // first column of the lane's two quads; first rule of the warp's span per half
     size_t seg_idx, seg_half;
-    int lane, warp;
+    int lane, warp, n_seg;
 };
+
+__device__ __noinline__ void rescore_straddle(unsigned long long *blockmax, long long rule0, long long ubs, int n_valid,
+                                              double u0, double u1, double u2, double u3) {
+    const double u[4] = {u0, u1, u2, u3};
+    for (int q = 0; q < n_valid; ++q) atomicMax(blockmax + (rule0 + q) / ubs, enc_f64(u[q]));
+}
+
+template <int H>
+__device__ __forceinline__ void rescore_half(const RescoreMultiParams &P, int j, const RescoreLane &L, const double (&u)[8],
+                                             unsigned long long (*s_red)[2][8]) {
+    const double m = fmax(fmax(fmax(u[0], u[1]), fmax(u[2], u[3])), fmax(fmax(u[4], u[5]), fmax(u[6], u[7])));
+    const unsigned long long seg = warp_max_enc(enc_f64(m));
+    if (L.lane < L.n_seg) P.segmax[j][H * L.seg_half + L.seg_idx + L.lane] = seg;
+    if (L.lane == 0) s_red[j][H][L.warp] = seg;
+    if (!L.uniform[H]) {                                       // CTA-uniform, rare: the CTA's span straddles two blocks
+        const long long base = (long long)H * P.k_total + P.col0;
+        rescore_straddle(P.blockmax[j], base + L.col[0], P.ubs, (int)max(0ll, min(4ll, P.n_cols - L.col[0])), u[0], u[1],
+                         u[2], u[3]);
+        rescore_straddle(P.blockmax[j], base + L.col[1], P.ubs, (int)max(0ll, min(4ll, P.n_cols - L.col[1])), u[4], u[5],
+                         u[6], u[7]);
+    }
+}
 
 __device__ __forceinline__ void rescore_job(const RescoreMultiParams &P, int j, const RescoreLane &L,
                                             unsigned long long (*s_red)[2][8]) {
     const double p = P.p[j], dn_pos = P.n_pos[j], dn_neg = P.n_neg[j];
     // presence rule: covers the negatives WITHOUT the k-mer, errs on the positives without it; absence: complements
-    double u[2][2];
-    u[0][0] = __dsub_rn(__dsub_rn(dn_neg, L.cn0), __dmul_rn(p, __dsub_rn(dn_pos, L.cp0)));
-    u[0][1] = __dsub_rn(__dsub_rn(dn_neg, L.cn1), __dmul_rn(p, __dsub_rn(dn_pos, L.cp1)));
-    u[1][0] = __dsub_rn(L.cn0, __dmul_rn(p, L.cp0));
-    u[1][1] = __dsub_rn(L.cn1, __dmul_rn(p, L.cp1));
-    if (L.any_dead) {
-        if (L.dead_p & 1u) u[0][0] = -INFINITY;
-        if (L.dead_p & 2u) u[0][1] = -INFINITY;
-        if (L.dead_a & 1u) u[1][0] = -INFINITY;
-        if (L.dead_a & 2u) u[1][1] = -INFINITY;
-    }
+    double up[8], ua[8];
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        const unsigned long long e0 = enc_f64(u[h][0]), e1 = enc_f64(u[h][1]);
-        const unsigned long long seg = warp_max_enc(e0 > e1 ? e0 : e1);
-        if (L.lane == 0) {
-            P.segmax[j][h * L.seg_half + L.seg_idx] = seg;
-            s_red[j][h][L.warp] = seg;
-        }
-        if (!L.uniform[h])                                     // CTA-uniform
-            rescore_straddle(P.blockmax[j], L.rule0[h], P.ubs, u[h][0], u[h][1], L.col < P.n_cols, L.col + 1 < P.n_cols);
+    for (int q = 0; q < 8; ++q) {
+        up[q] = __dsub_rn(__dsub_rn(dn_neg, L.cn[q]), __dmul_rn(p, __dsub_rn(dn_pos, L.cp[q])));
+        ua[q] = __dsub_rn(L.cn[q], __dmul_rn(p, L.cp[q]));
     }
+    if (L.dead_p | L.dead_a) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            if ((L.dead_p >> q) & 1u) up[q] = -INFINITY;
+            if ((L.dead_a >> q) & 1u) ua[q] = -INFINITY;
+        }
+    }
+    rescore_half<0>(P, j, L, up, s_red);
+    rescore_half<1>(P, j, L, ua, s_red);
 }
 
 __global__ void __launch_bounds__(256) k_scm_rescore_multi(const __grid_constant__ RescoreMultiParams P) {
@@ -902,8 +918,8 @@ __global__ void __launch_bounds__(256) k_scm_rescore_multi(const __grid_constant
     RescoreLane L;
     L.lane = threadIdx.x & 31;
     L.warp = threadIdx.x >> 5;
-    const long long chunk_c0 = (long long)blockIdx.x * 512;
-    const long long chunk_n = min(512ll, P.n_cols - chunk_c0);
+    const long long chunk_c0 = (long long)blockIdx.x * 2048;
+    const long long chunk_n = min(2048ll, P.n_cols - chunk_c0);
     long long bid[2];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -911,26 +927,40 @@ __global__ void __launch_bounds__(256) k_scm_rescore_multi(const __grid_constant
         bid[h] = r0 / P.ubs;
         L.uniform[h] = chunk_n > 0 && (r0 + chunk_n - 1) / P.ubs == bid[h];
     }
-    const long long seg_c0 = chunk_c0 + (long long)L.warp * 64;                // < ld: ld is a multiple of 1024
-    L.col = seg_c0 + L.lane * 2;
-    L.rule0[0] = P.col0 + L.col;
-    L.rule0[1] = P.k_total + P.col0 + L.col;
-    const uint2 va = *reinterpret_cast<const uint2 *>(P.cnt_a + L.col);
-    const uint2 vb = *reinterpret_cast<const uint2 *>(P.cnt_b + L.col);
-    const double da0 = (double)va.x, da1 = (double)va.y, db0 = (double)vb.x, db1 = (double)vb.y;
-    // rules this lane may NOT score: padding columns and blacklisted rules (scm.py:267) -> -inf
-    L.dead_p = (L.col < P.n_cols ? 0u : 1u) | (L.col + 1 < P.n_cols ? 0u : 2u);
-    L.dead_a = L.dead_p;
-    if (P.black_pres) {
-        L.dead_p |= (P.black_pres[L.col >> 5] >> (L.col & 31)) & 3u;
-        L.dead_a |= (P.black_abs[L.col >> 5] >> (L.col & 31)) & 3u;
-    }
-    L.any_dead = (L.dead_p | L.dead_a) != 0;
-    L.seg_idx = (size_t)(seg_c0 >> 6);
+    const long long span_c0 = chunk_c0 + (long long)L.warp * 256;       // the warp's 256 columns (ld is a multiple of 1024)
+    const bool in_ld = span_c0 < P.ld;
+    L.seg_idx = (size_t)(span_c0 >> 6);
     L.seg_half = (size_t)(P.ld >> 6);
-    L.cp0 = da0; L.cp1 = da1; L.cn0 = db0; L.cn1 = db1;
+    L.n_seg = in_ld ? 4 : 0;
+    L.dead_p = L.dead_a = 0;
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+        L.col[g] = span_c0 + g * 128 + L.lane * 4;
+        uint4 va = make_uint4(0, 0, 0, 0), vb = va;
+        uint32_t bp = 0, ba = 0;
+        if (in_ld) {
+            va = *reinterpret_cast<const uint4 *>(P.cnt_a + L.col[g]);
+            vb = *reinterpret_cast<const uint4 *>(P.cnt_b + L.col[g]);
+            if (P.black_pres) {
+                bp = (P.black_pres[L.col[g] >> 5] >> (L.col[g] & 31)) & 15u;
+                ba = (P.black_abs[L.col[g] >> 5] >> (L.col[g] & 31)) & 15u;
+            }
+        }
+        L.cp[g * 4 + 0] = u32_to_f64(va.x); L.cp[g * 4 + 1] = u32_to_f64(va.y); L.cp[g * 4 + 2] = u32_to_f64(va.z); L.cp[g * 4 + 3] = u32_to_f64(va.w);
+        L.cn[g * 4 + 0] = u32_to_f64(vb.x); L.cn[g * 4 + 1] = u32_to_f64(vb.y); L.cn[g * 4 + 2] = u32_to_f64(vb.z); L.cn[g * 4 + 3] = u32_to_f64(vb.w);
+        // rules this lane may NOT score: padding columns and blacklisted rules (scm.py:267) -> -inf
+        const int n_valid = (int)max(0ll, min(4ll, P.n_cols - L.col[g]));
+        const uint32_t pad = 15u & ~((1u << n_valid) - 1u);
+        L.dead_p |= (bp | pad) << (4 * g);
+        L.dead_a |= (ba | pad) << (4 * g);
+    }
     for (int j = 0; j < P.n_plain; ++j) rescore_job(P, j, L, s_red);
-    L.cp0 = db0; L.cp1 = db1; L.cn0 = da0; L.cn1 = da1;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {                               // swapped jobs: the two count arrays exchange roles
+        const double t = L.cp[q];
+        L.cp[q] = L.cn[q];
+        L.cn[q] = t;
+    }
     for (int j = P.n_plain; j < P.n_jobs; ++j) rescore_job(P, j, L, s_red);
     __syncthreads();
     if (threadIdx.x < 2 * P.n_jobs) {
@@ -2829,7 +2859,7 @@ static int queue_score_group(kv_shard *s, const uint32_t *cnt_a, const uint32_t 
                 t.cap = packet_capacity;
             }
         }
-        k_scm_rescore_multi<<<(unsigned)(s->ld / 512), 256, 0, s->stream>>>(R);
+        k_scm_rescore_multi<<<(unsigned)((s->ld + 2047) / 2048), 256, 0, s->stream>>>(R);
         if (d_packets) k_scm_select_local_multi<<<nb, 32, 0, s->stream>>>(SL);
         else k_scm_select_multi<<<nb, 32, 0, s->stream>>>(S);
         k_scm_ties_multi<<<dim3(grid_ties, nb), 256, 0, s->stream>>>(T);
