@@ -657,14 +657,15 @@ __device__ __forceinline__ bool tie_close(double u, double m, double tol) {
     return (u == m) || (isfinite(m) && fabs(__dsub_rn(u, m)) <= tol);
 }
 
-// can the 64-column segment hold a tie?  If all its rules sit in one block: only if the block is
-// selected and the segment maximum itself is close to the block maximum (u <= segmax <= m and rounding
-// is monotonic, so no smaller u can be close when segmax is not).  Straddling segments are scanned.
+// can the 64-column segment hold a tie?  `smax` is the segment's maximum or an UPPER bound of it (k_scm_rescore_multi
+// stores the maximum of the surrounding 256 columns, which may reach into the next utility block).  If all the
+// segment's rules sit in one block: only if the block is selected and the bound reaches the block's tie window --
+// every u of the segment is <= smax, so when smax < m - tol no u can be close to m.  Straddling segments are scanned.
 __device__ __forceinline__ bool seg_candidate(const TieParams &P, long long r0, long long r1, double smax) {
     if (P.threshold) return smax >= *P.threshold;
     const long long b0 = fast_div(r0, P.ubs, P.inv_ubs), b1 = fast_div(r1, P.ubs, P.inv_ubs);
     if (b0 != b1) return true;
-    return P.sel[b0] && tie_close(smax, P.bm[b0], P.tol[b0]);
+    return P.sel[b0] && (smax >= P.bm[b0] || tie_close(smax, P.bm[b0], P.tol[b0]));
 }
 
 __device__ __forceinline__ void tie_emit(const TieParams &P, long long rule, double u, uint32_t pe, uint32_t nc) {

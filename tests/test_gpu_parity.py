@@ -408,6 +408,36 @@ def test_grid_batches_distinct_mask_pairs(sorted_labels, n_folds, devices):
     rc.close()
 
 
+def test_grid_ties_next_to_a_larger_but_close_block():
+    """scm.py:271-286 appends a block whose maximum is larger than, but isclose to, the running best without raising
+    it: selected blocks can then differ by more than the tie tolerance.  The scoring kernel of the grid stores, per
+    64-column segment, the maximum of the surrounding 256 columns -- which may come from the NEXT block -- so the
+    tie kernel must treat it as an upper bound.  Block maxima -999899 / -999908 / -999890 (tolerance 10): the tie of
+    block 1 sits 110 columns before block 2's larger maximum."""
+    n_pos, n_neg, k, ubs, p_ = 5, 120, 3000, 1000, 999999.0
+    n = n_pos + n_neg
+    X = np.zeros((n, k), dtype=np.uint8)
+    X[:2, :] = 1                                   # ordinary k-mers: in 2 of the 5 positives, in every negative
+    X[n_pos:, :] = 1
+    for col, nc in ((10, 100), (1900, 91), (2010, 109)):
+        X[:n_pos, col] = [1, 1, 1, 1, 0]           # presence rule: one positive error ...
+        X[n_pos:n_pos + nc, col] = 0               # ... and nc negatives covered
+    from kover_b200.utils import _pack_binary_bytes_to_ints
+    P = _pack_binary_bytes_to_ints(X, 64)
+    pos, neg = np.arange(n_pos), np.arange(n_pos, n)
+    orc = ko.OracleKmerRuleClassifications(P, n, fast=True)
+    want = ko.merge_utility_blocks(len(neg) - orc.sum_rows(neg), len(pos) - orc.sum_rows(pos), p_,
+                                   np.zeros(2 * k, dtype=bool), block_size=ubs)
+    assert list(want[1]) == [10, 1900, 2010] and want[0] == 100 - 999999.0      # all three blocks keep their tie
+    rc = KmerRuleClassifications(P, n, devices=[0])
+    one = rc.best_utility_rules(p_, pos, neg, util_block_size=ubs)
+    grid = rc.best_utility_rules_grid([(p_, pos, neg), (p_, pos, neg), (1.0, pos[:4], neg)], util_block_size=ubs)
+    for got in (one, grid[0], grid[1]):
+        assert got[0] == want[0] and np.array_equal(got[1], np.asarray(want[1], dtype=np.int64))
+        assert np.array_equal(got[2], want[2]) and np.array_equal(got[3], want[3])
+    rc.close()
+
+
 # ---------------------------------------------------------------------------------- a9 / a11
 def tree_to_dict(node):
     d = {"depth": node.depth, "criterion_value": float(node.criterion_value),
