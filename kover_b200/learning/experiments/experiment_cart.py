@@ -248,11 +248,14 @@ def _find_rule_blacklist(dataset, kmer_blacklist_file, warning_callback):
 
 def learn_CART(dataset_file, split_name, criterion, max_depth, min_samples_split, class_importance, bound_delta,
                bound_max_genome_size, kmer_blacklist_file, parameter_selection, n_cpu, authorized_rules=None,
-               progress_callback=None, warning_callback=None, error_callback=None, devices=None, comm=None):
+               progress_callback=None, warning_callback=None, error_callback=None, devices=None, comm=None,
+               rule_classifications=None):
     """``kover learn tree`` on a Kover dataset file: same arguments and return value as the reference's
     ``learn_CART`` (:521-649).  The packed matrix is streamed into HBM once; every hyper-parameter combination is
-    evaluated over that resident image (``n_cpu`` is accepted and ignored).  -> (best_hps, best_hp_score,
-    train_metrics, test_metrics, model, rule_importances, model_equivalent_rules, classifications)."""
+    evaluated over that resident image (``n_cpu`` is accepted and ignored).  ``rule_classifications``: an already
+    resident KmerRuleClassifications of this dataset to adopt instead of uploading again; it is then left open.
+    -> (best_hps, best_hp_score, train_metrics, test_metrics, model, rule_importances, model_equivalent_rules,
+    classifications)."""
     from collections import defaultdict
 
     from ...dataset.ds import KoverDataset
@@ -282,7 +285,10 @@ def learn_CART(dataset_file, split_name, criterion, max_depth, min_samples_split
     phenotype_tags = dataset.phenotype.tags[...]
     n_classes = len(phenotype_tags)
     rules = LazyKmerRuleList(dataset.kmer_sequences, dataset.kmer_by_matrix_column)
-    rule_classifications = KmerRuleClassifications(dataset.kmer_matrix, dataset.genome_count, devices=devices, comm=comm)
+    owns_matrix = rule_classifications is None
+    if owns_matrix:
+        rule_classifications = KmerRuleClassifications(dataset.kmer_matrix, dataset.genome_count, devices=devices,
+                                                       comm=comm)
 
     if parameter_selection == "bound":
         def hp_search(hps):
@@ -329,7 +335,8 @@ def learn_CART(dataset_file, split_name, criterion, max_depth, min_samples_split
     model_equivalent_rules = dict((r, [rules[i] for i in r.equivalent_rules_idx]) for r in best_master_tree.rules)
     importance_sum = float(sum(r.importance for r in best_master_tree.rules))
     rule_importances = dict((r, r.importance / importance_sum) for r in best_master_tree.rules)
-    rule_classifications.close()
+    if owns_matrix:
+        rule_classifications.close()
     dataset.close()
     return (best_hps, best_hp_score, train_metrics, test_metrics, best_model, rule_importances, model_equivalent_rules,
             classifications)

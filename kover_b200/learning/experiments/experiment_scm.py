@@ -327,14 +327,16 @@ def _full_train(rule_classifications, rules, labels, split_train_idx, rule_risks
 def learn_SCM(dataset_file, split_name, model_type, p, kmer_blacklist_file, max_rules, max_equiv_rules,
               parameter_selection, n_cpu, random_seed, authorized_rules=None, bound_delta=None,
               bound_max_genome_size=None, progress_callback=None, warning_callback=None, error_callback=None,
-              devices=None, comm=None):
+              devices=None, comm=None, rule_classifications=None):
     """``kover learn scm`` on a Kover dataset file: same arguments and return value as the reference's
     ``learn_SCM`` (experiment_scm.py:675-888).  parameter_selection: "bound", "cv" or "none" (first value of each
     hyper-parameter).  What differs is the execution: the packed ``kmer_matrix`` is streamed into HBM ONCE and every
     fit of the selection (all hyper-parameter combinations, all folds) runs in lock-step over that resident image,
     instead of one forked worker per combination, each re-reading the HDF5 chunks on every scan; ``n_cpu`` is
-    accepted and ignored.  -> (best_hp, best_hp_score, train_metrics, test_metrics, model, rule_importances,
-    model_equivalent_rules, classifications)."""
+    accepted and ignored.  ``rule_classifications``: an already resident KmerRuleClassifications of this dataset to
+    adopt instead of uploading again (several experiments on one dataset); it is then left open.
+    -> (best_hp, best_hp_score, train_metrics, test_metrics, model, rule_importances, model_equivalent_rules,
+    classifications)."""
     from collections import defaultdict
 
     from ...dataset.ds import KoverDataset
@@ -354,7 +356,10 @@ def learn_SCM(dataset_file, split_name, model_type, p, kmer_blacklist_file, max_
     train_example_idx = np.asarray(split.train_genome_idx[...])
     test_example_idx = np.asarray(split.test_genome_idx[...])
     rules = LazyKmerRuleList(dataset.kmer_sequences[...], dataset.kmer_by_matrix_column[...])
-    rule_classifications = KmerRuleClassifications(dataset.kmer_matrix, dataset.genome_count, devices=devices, comm=comm)
+    owns_matrix = rule_classifications is None
+    if owns_matrix:
+        rule_classifications = KmerRuleClassifications(dataset.kmer_matrix, dataset.genome_count, devices=devices,
+                                                       comm=comm)
     split_risks = np.hstack((split.unique_risk_by_kmer[...], split.unique_risk_by_anti_kmer[...]))
     model_types, p_values = [str(m) for m in model_type], [float(x) for x in p]
 
@@ -412,7 +417,8 @@ def learn_SCM(dataset_file, split_name, model_type, p, kmer_blacklist_file, max_
             if test_metrics["risk"][0] > 0 else []
 
     model_equivalent_rules = [[rules[i] for i in equiv_idx] for equiv_idx in equivalent_rules]
-    rule_classifications.close()
+    if owns_matrix:
+        rule_classifications.close()
     dataset.close()
     return (best_hp, best_hp_score, train_metrics, test_metrics, model, rule_importances, model_equivalent_rules,
             classifications)

@@ -126,47 +126,5 @@ def test_drivers_against_the_reference(case, tmp_path, golden_dir):
     """learn_SCM / learn_CART on a Kover dataset FILE (HDF5 -> dataset adapter -> HBM -> lock-step selection) against
     the REAL reference's learn_SCM / learn_CART run unmodified on the same content (make_golden.py::gen_drivers):
     selected hyper-parameters, score, metrics, model, importances, equivalent rules and the classified genomes."""
-    import json
-    import os
-
-    import cases
-    from kover_b200.learning.experiments import experiment_cart as cexp
-    name, _, _, seed, _, learner, selection, max_equiv = case
-    g = np.load(os.path.join(golden_dir, name + ".npz"))
-    d = cases.driver_dataset(case)
-    path = str(tmp_path / (name + ".kover"))
-    write_kover_file(path, d["P"], d["n"], d["y"], d["train"], d["test"], d["folds"], chunks=d["chunks"] or (1, d["k"]),
-                     fixed_strings=(seed % 2 == 0),
-                     names=(d["kmer_sequences"], d["kmer_by_matrix_column"], d["genome_identifiers"]))
-    want_cls = json.loads(str(g["classifications"]))
-    if learner == "scm":
-        a = cases.DRIVER_SCM_ARGS
-        best_hp, score, trm, tem, model, imp, equiv, cls = kexp.learn_SCM(
-            path, "split1", a["model_type"], a["p"], None, a["max_rules"], max_equiv, selection, 1, a["random_seed"], None,
-            bound_delta=a["bound_delta"], bound_max_genome_size=a["bound_max_genome_size"])
-        want_hp = json.loads(str(g["best_hp"]))
-        assert best_hp["model_type"] == want_hp["model_type"] and best_hp["p"] == want_hp["p"]
-        assert int(best_hp["max_rules"]) == want_hp["max_rules"]
-        assert (score is None and np.isnan(g["score"])) or score == float(g["score"])
-        assert trm["bound"] == float(g["train_bound"]) and trm["f1_score"][0] == float(g["train_f1"])
-        assert [str(r) for r in model] == json.loads(str(g["model"]))
-        assert np.array_equal(np.asarray(imp, dtype=np.float64), g["importances"])
-        assert [sorted(str(r) for r in e) for e in equiv] == json.loads(str(g["equiv"]))
-    else:
-        a = cases.DRIVER_CART_ARGS
-        best_hps, score, trm, tem, model, imp, equiv, cls = cexp.learn_CART(
-            path, "split1", a["criterion"], a["max_depth"], a["min_samples_split"], a["class_importance"], a["bound_delta"],
-            a["bound_max_genome_size"], None, selection, 1, None)
-        want_hps = json.loads(str(g["best_hps"]))
-        assert best_hps["criterion"] == want_hps["criterion"] and int(best_hps["max_depth"]) == want_hps["max_depth"]
-        assert int(best_hps["min_samples_split"]) == want_hps["min_samples_split"]
-        assert float(best_hps["pruning_alpha"]) == want_hps["pruning_alpha"]
-        assert {str(c): w for c, w in best_hps["class_importance"].items()} == want_hps["class_importance"]
-        assert score == float(g["score"])
-        tree = model.decision_tree
-        assert sorted(str(r) for r in tree.rules) == json.loads(str(g["rules"])) and len(tree) == int(g["tree_size"])
-        assert sorted((str(r), float(v)) for r, v in imp.items()) == [tuple(x) for x in json.loads(str(g["importances"]))]
-        assert sorted((str(r), sorted(str(e) for e in v)) for r, v in equiv.items()) == \
-            [(x[0], x[1]) for x in json.loads(str(g["equiv"]))]
-    assert trm["risk"][0] == float(g["train_risk"]) and tem["risk"][0] == float(g["test_risk"])
-    assert {k_: list(v) for k_, v in cls.items()} == want_cls
+    from experiment_checks import check_driver_case
+    check_driver_case(golden_dir, case, str(tmp_path), None)
