@@ -96,6 +96,37 @@ def test_sum_rows_multi_matches_single():
         assert np.array_equal(multi[i], rc.sum_rows(rows)[:P.shape[1]].astype(np.uint32)), i
 
 
+@pytest.mark.parametrize("n,n_masks", [(260, 5), (16000, 16), (51200, 16), (51200, 7)],
+                         ids=["W5", "W250_ring128K", "W800_ring64K", "W800_7masks"])
+def test_multi_mask_pass_shapes(n, n_masks):
+    """k_count_tma over the shapes that select its three ring depths (the mask staging grows with packed rows x
+    masks), with empty masks, masks that touch a single packed row, row groups that are not a multiple of four and
+    masks that leave most rows untouched -- against one single-mask pass per mask."""
+    seed, k = 31, 2100
+    P = cases.random_words(seed, n, k)
+    rs = np.random.RandomState(seed)
+    sets = []
+    for m in range(n_masks):
+        kind = m % 5
+        if kind == 0:
+            sets.append(np.sort(rs.choice(n, size=n // 3, replace=False)))
+        elif kind == 1:
+            sets.append(np.arange(64 * (m % ((n + 63) // 64)), min(n, 64 * (m % ((n + 63) // 64)) + 5)))    # one packed row
+        elif kind == 2:
+            sets.append(np.zeros(0, dtype=np.int64))                                                    # empty
+        elif kind == 3:
+            lo = (n // 7) * (m % 7)
+            sets.append(np.arange(lo, min(n, lo + 64 * 3 + 1)))                                           # 3-4 rows
+        else:
+            sets.append(np.arange(n))                                                                     # everything
+    rc = KmerRuleClassifications(P, n, devices=[0])
+    got = rc.sum_rows_multi(sets)
+    for i, rows in enumerate(sets):
+        want = rc.sum_rows(rows)[:k].astype(np.uint32) if len(rows) else np.zeros(k, dtype=np.uint32)
+        assert np.array_equal(got[i], want), i
+    rc.close()
+
+
 # ---------------------------------------------------------------------------------- a6
 @pytest.mark.parametrize("case", cases.UTILITY_CASES, ids=[c[0] for c in cases.UTILITY_CASES])
 @pytest.mark.parametrize("devices", [[0], [0, 0]], ids=["1shard", "2shards"])
