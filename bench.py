@@ -309,11 +309,15 @@ def extra_measurements(rc, shard, steps, k_local, reps=12):
     dt = time.perf_counter() - t0
     n_split = len(t.decision_tree.rules)
     out["cart_fit_max_depth_5"] = {"seconds": dt, "split_nodes": n_split, "ms_per_split_node": 1e3 * dt / max(1, n_split)}
-    # configs[2]'s depth: the nodes of a level are searched together, class masks of 8 nodes per matrix pass
+    # configs[2]'s depth with the experiments' tiebreaker (experiment_cart.py:82-94, 264): the nodes of a level are
+    # searched together, class masks of 8 nodes per matrix pass, the occurrence tiebreaker applied on the device
+    from kover_b200.learning.experiments.experiment_cart import OccurrenceTiebreaker
     t = DecisionTreeClassifier("gini", 10, 2, {0: 1.0, 1: 1.0})
     ia = shard.info()
     t0 = time.perf_counter()
-    t.fit(rules, rc, ex)
+    tb = OccurrenceTiebreaker(rc, train)
+    t.fit(rules, rc, ex, tiebreaker=tb)
+    tb.release()
     dt = time.perf_counter() - t0
     ib = shard.info()
     n_split = len(t.decision_tree.rules)

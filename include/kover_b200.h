@@ -249,7 +249,18 @@ int kv_gini_best_split(kv_shard *s, int n_classes, const uint64_t *class_masks, 
  * kv_gini_level_fetch then copies node i's rule indices (GLOBAL, ascending) into a caller buffer of at least
  * n_found[i] entries.  The results stay valid until the next kv_gini_level call on the shard. */
 int kv_gini_level(kv_shard *s, int64_t n_nodes, const uint64_t *class_masks, const double *altered_prior,
-                  const double *n_total, const int64_t *n_node, double *min_score, int64_t *n_found);
+                  const double *n_total, const int64_t *n_node, const int32_t *occ_table, double *min_score,
+                  int64_t *n_found, uint32_t *occ_max);
+/* The reference's CART tiebreaker on the device (experiment_cart.py:82-94, 264: among the best splits keep the
+ * k-mers whose occurrence count in the tree's training set is numpy.isclose to the largest one).
+ * kv_occ_table_set(table 0..63, mask) computes the presence counts of the shard's k-mers under `mask` into a
+ * device-resident table (mask = NULL frees it).  A node of kv_gini_level with occ_table[i] >= 0 (occ_table may be
+ * NULL) then reports only the ties that survive the tiebreaker WITHIN THIS SHARD, and their largest occurrence in
+ * occ_max[i] (occ_max may be NULL) so that several shards can be merged: a shard's survivors stand when its
+ * maximum is the global one; kv_occ_table_gather returns the occurrences of given rules for the rare re-filter
+ * (maxima of 100 000 and more, where the tolerance exceeds 1). */
+int kv_occ_table_set(kv_shard *s, int table, const uint64_t *mask);
+int kv_occ_table_gather(kv_shard *s, int table, const int64_t *rule_idx, int64_t n, uint32_t *out);
 int kv_gini_level_fetch(kv_shard *s, int64_t node, int64_t *rule_idx, int64_t capacity);
 /* Zero-copy variant: *rule_idx points at node i's n_found indices inside the shard's pinned result arena (tie sets
  * of small nodes run to millions of rules; a second copy into fresh pageable memory costs more than the scan).

@@ -79,7 +79,9 @@ SYMBOLS = {
     "kv_gini_scores": (ctypes.c_int, [_c_p, _c_p]),
     "kv_host_alloc": (ctypes.c_int, [_c_i64, ctypes.POINTER(ctypes.c_void_p)]),
     "kv_host_free": (ctypes.c_int, [_c_p]),
-    "kv_gini_level": (ctypes.c_int, [_c_p, _c_i64, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p]),
+    "kv_gini_level": (ctypes.c_int, [_c_p, _c_i64, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p]),
+    "kv_occ_table_set": (ctypes.c_int, [_c_p, ctypes.c_int, _c_p]),
+    "kv_occ_table_gather": (ctypes.c_int, [_c_p, ctypes.c_int, _c_p, _c_i64, _c_p]),
     "kv_gini_level_fetch": (ctypes.c_int, [_c_p, _c_i64, _c_p, _c_i64]),
     "kv_gini_level_result": (ctypes.c_int, [_c_p, _c_i64, ctypes.POINTER(ctypes.POINTER(ctypes.c_int64)),
                                             ctypes.POINTER(_c_i64)]),
@@ -499,9 +501,26 @@ class Shard(object):
             check(rc)
             return idx[:n.value]
 
-    def gini_level(self, node_masks, altered_prior, n_total, n_node):
+    def occ_table_set(self, table, mask):
+        """Device-resident occurrence table ``table`` = presence counts under ``mask`` (None frees it)."""
+        if mask is None:
+            check(self._lib.kv_occ_table_set(self._h, int(table), None))
+            return
+        mask = np.ascontiguousarray(mask, dtype=np.uint64)
+        assert mask.shape == (self.n_words,)
+        check(self._lib.kv_occ_table_set(self._h, int(table), ptr(mask)))
+
+    def occ_table_gather(self, table, rule_idx):
+        idx = np.ascontiguousarray(rule_idx, dtype=np.int64)
+        out = np.empty(idx.shape[0], dtype=np.uint32)
+        check(self._lib.kv_occ_table_gather(self._h, int(table), ptr(idx), idx.shape[0], ptr(out)))
+        return out
+
+    def gini_level(self, node_masks, altered_prior, n_total, n_node, occ_tables=None):
         """Split search of several two-class nodes, up to 8 nodes per matrix pass.  node_masks [n_nodes, 2, W],
-        n_node [n_nodes, 2] -> [(min score over this shard, rule indices achieving it, ascending)] per node."""
+        n_node [n_nodes, 2] -> [(min score over this shard, rule indices achieving it, ascending)] per node.
+        occ_tables [n_nodes] (table id per node, -1 = none): the occurrence tiebreaker is applied on the device; the
+        result entries then carry a third element, the largest occurrence among the node's ties on this shard."""
         masks = np.ascontiguousarray(node_masks, dtype=np.uint64)
         assert masks.ndim == 3 and masks.shape[1] == 2 and masks.shape[2] == self.n_words
         nn = np.ascontiguousarray(n_node, dtype=np.int64)
@@ -511,19 +530,25 @@ class Shard(object):
         assert nn.shape == (masks.shape[0], 2)
         mins = np.empty(masks.shape[0], dtype=np.float64)
         found = np.empty(masks.shape[0], dtype=np.int64)
-        check(self._lib.kv_gini_level(self._h, masks.shape[0], ptr(masks), ptr(pri), ptr(tot), ptr(nn), ptr(mins),
-                                      ptr(found)))
+        occ, occ_max = None, None
+        if occ_tables is not None:
+            occ = np.ascontiguousarray(occ_tables, dtype=np.int32)
+            assert occ.shape == (masks.shape[0],)
+            occ_max = np.zeros(masks.shape[0], dtype=np.uint32)
+        check(self._lib.kv_gini_level(self._h, masks.shape[0], ptr(masks), ptr(pri), ptr(tot), ptr(nn),
+                                      ptr(occ) if occ is not None else None, ptr(mins), ptr(found),
+                                      ptr(occ_max) if occ_max is not None else None))
         # read-only views into the shard's pinned result arena, valid until the next gini_level on this shard
         out = []
         for i in range(masks.shape[0]):
             if found[i] == 0:
-                out.append((float(mins[i]), np.zeros(0, dtype=np.int64)))
-                continue
-            p_idx, n = ctypes.POINTER(ctypes.c_int64)(), _c_i64(0)
-            check(self._lib.kv_gini_level_result(self._h, i, ctypes.byref(p_idx), ctypes.byref(n)))
-            idx = np.ctypeslib.as_array(p_idx, shape=(int(n.value),))
-            idx.flags.writeable = False
-            out.append((float(mins[i]), idx))
+                idx = np.zeros(0, dtype=np.int64)
+            else:
+                p_idx, n = ctypes.POINTER(ctypes.c_int64)(), _c_i64(0)
+                check(self._lib.kv_gini_level_result(self._h, i, ctypes.byref(p_idx), ctypes.byref(n)))
+                idx = np.ctypeslib.as_array(p_idx, shape=(int(n.value),))
+                idx.flags.writeable = False
+            out.append((float(mins[i]), idx) if occ is None else (float(mins[i]), idx, int(occ_max[i])))
         return out
 
     def gini_scores(self):

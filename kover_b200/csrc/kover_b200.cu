@@ -1162,6 +1162,10 @@ struct GiniParams {
     // two classes, small node: score of every (count 0, count 1) pair, [n_node0 + 1][table_stride], or null
     const double *table;
     int table_stride;
+    // occurrence tiebreak on the device (experiment_cart.py:82-94): k-mer occurrence counts of the tree's training
+    // set, and the maximum occurrence among the node's ties
+    const uint32_t *occ;
+    unsigned int *occ_max;
 };
 enum { GINI_MIN = 0, GINI_TIES = 1, GINI_SCORES = 2 };
 
@@ -1287,8 +1291,13 @@ __device__ __forceinline__ double gini2_score_any(long long col, const GiniParam
 
 // Tie collection when the scan left exact per-segment minima: one lane screens one 64-column segment
 // (156 k segments for 10 M k-mers), the warp then rescans only the segments whose minimum IS the target.
-__global__ void __launch_bounds__(256) k_gini2_ties_seg(const GiniParams P) {
-    __shared__ double s_tab[GINI2_TABLE_MAX];
+// OCC = 0: every tie.  OCC = 1 / 2, the reference's CART tiebreaker on the device: among the ties keep the k-mers whose
+// occurrence count in the tree's training set is isclose to the largest one (experiment_cart.py:82-94,
+// numpy.isclose(o, o.max()): |o - max| <= 1e-8 + 1e-5 * |max|) -- pass 1 finds the maximum, pass 2 emits the survivors.
+// A node with few examples ties on millions of k-mers, of which the tiebreaker keeps a handful: filtering here
+// removes their sort and their trip to the host.
+template <int OCC>
+__device__ __forceinline__ void gini2_ties_body(const GiniParams &P, double *s_tab) {
     gini2_table_load(P, s_tab);
     double target = P.min_score;
     if (P.min_ptr) {
@@ -1296,6 +1305,12 @@ __global__ void __launch_bounds__(256) k_gini2_ties_seg(const GiniParams P) {
         target = (v == ~0ull) ? INFINITY : dec_f64_max_dev(v);
     }
     if (target == INFINITY) return;
+    double occ_best = 0.0, occ_tol = 0.0;
+    if (OCC == 2) {
+        occ_best = (double)*P.occ_max;
+        occ_tol = __dadd_rn(1e-8, __dmul_rn(1e-5, fabs(occ_best)));
+    }
+    unsigned int occ_run = 0;
     const int lane = threadIdx.x & 31;
     const long long n_seg = (P.n_cols + 63) >> 6;
     const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -1315,7 +1330,12 @@ __global__ void __launch_bounds__(256) k_gini2_ties_seg(const GiniParams P) {
             for (int j = 0; j < 2; ++j) {
                 const long long col = ((sb + src) << 6) + lane + 32 * j;
                 if (col >= P.n_cols) continue;
-                const bool hit = gini2_score_any(col, P, s_tab) == target;
+                bool hit = gini2_score_any(col, P, s_tab) == target;
+                if (OCC == 1) {
+                    if (hit) occ_run = max(occ_run, P.occ[col]);
+                    continue;
+                }
+                if (OCC == 2 && hit) hit = fabs(__dsub_rn((double)P.occ[col], occ_best)) <= occ_tol;
                 // one atomic per warp: a node with few examples can tie on most of the k-mers
                 const unsigned hits = __ballot_sync(__activemask(), hit);
                 if (hit) {
@@ -1329,6 +1349,23 @@ __global__ void __launch_bounds__(256) k_gini2_ties_seg(const GiniParams P) {
             }
         }
     }
+    if (OCC == 1) {
+        occ_run = __reduce_max_sync(0xffffffffu, occ_run);
+        if (lane == 0 && occ_run) atomicMax(P.occ_max, occ_run);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_gini2_ties_seg(const GiniParams P) {
+    __shared__ double s_tab[GINI2_TABLE_MAX];
+    gini2_ties_body<0>(P, s_tab);
+}
+__global__ void __launch_bounds__(256) k_gini2_ties_occmax(const GiniParams P) {
+    __shared__ double s_tab[GINI2_TABLE_MAX];
+    gini2_ties_body<1>(P, s_tab);
+}
+__global__ void __launch_bounds__(256) k_gini2_ties_occ(const GiniParams P) {
+    __shared__ double s_tab[GINI2_TABLE_MAX];
+    gini2_ties_body<2>(P, s_tab);
 }
 
 // Two-class Gini scores from RESIDENT counts (the nodes of a CART level are counted several per matrix pass by
@@ -1526,6 +1563,7 @@ struct kv_shard {
 
     DevBuf d_qmisc, d_qseg;                   // block tables / segment maxima of the jobs of one queue batch
     DevBuf d_level;                           // kv_gini_level: per-node minima, counters, tie slots, segment minima
+    std::vector<uint32_t *> occ_tables;       // kv_occ_table_set: k-mer occurrence counts of a training set, [ld] each
     int64_t *h_level = nullptr;               // pinned arena: the tie lists of the last kv_gini_level, node after node
     size_t h_level_cap = 0, h_level_used = 0; // in entries
     std::vector<std::pair<size_t, size_t>> level_span;   // (offset, count) of every node in the arena
@@ -1639,6 +1677,8 @@ extern "C" int kv_destroy(kv_shard *s) {
     p2p_destroy(s->p2p);
     cudaFree(s->d_mat);
     for (auto p : s->d_cnt) cudaFree(p);
+    for (auto p : s->occ_tables)
+        if (p) cudaFree(p);
     for (DevBuf *b : {&s->d_rec, &s->d_misc, &s->d_ties, &s->d_stage, &s->d_sort_tmp, &s->d_sort_io, &s->d_queue, &s->d_level, &s->d_qmisc, &s->d_qseg})
         if (b->p) cudaFree(b->p);
     if (s->d_black_pres) cudaFree(s->d_black_pres);
@@ -3510,11 +3550,64 @@ static int level_arena_reserve(kv_shard *s, size_t need) {
     return KV_OK;
 }
 
+static constexpr int kMaxOccTables = 64;
+
+// Device-resident k-mer occurrence table `table` (0..63) = presence counts of the shard's k-mers under `mask` (the
+// training set of a tree): the input of the reference's CART tiebreaker (experiment_cart.py:82-94, 264), kept on
+// the device so that kv_gini_level can apply the tiebreaker there.  mask = NULL frees the table.
+extern "C" int kv_occ_table_set(kv_shard *s, int table, const uint64_t *mask) {
+    if (!s) return fail(KV_E_INVALID, "kv_occ_table_set: null shard");
+    if (table < 0 || table >= kMaxOccTables) return fail(KV_E_INVALID, "kv_occ_table_set: table must be 0..63");
+    DeviceGuard g(s->device);
+    if ((int)s->occ_tables.size() <= table) s->occ_tables.resize((size_t)table + 1, nullptr);
+    if (!mask) {
+        if (s->occ_tables[table]) {
+            CU(cudaStreamSynchronize(s->stream));
+            cudaFree(s->occ_tables[table]);
+            s->occ_tables[table] = nullptr;
+        }
+        return KV_OK;
+    }
+    if (!s->occ_tables[table]) CU(cudaMalloc(&s->occ_tables[table], (size_t)s->ld * sizeof(uint32_t)));
+    s->last_launches = 0;
+    int n_act, n_both;
+    KV_TRY(push_records2(s, mask, nullptr, n_act, n_both));
+    Scan2Params P;
+    fill_scan2(s, P, n_act);
+    P.cnt0 = s->occ_tables[table];
+    P.cnt1 = nullptr;
+    KV_TRY(launch_scan<EPI_COUNTS>(s, P, n_both));
+    s->scan_calls += 1;
+    CU(cudaStreamSynchronize(s->stream));
+    CU(cudaGetLastError());
+    return KV_OK;
+}
+
+// occurrence counts of the given GLOBAL rule indices (presence rules of this shard) from table `table`
+extern "C" int kv_occ_table_gather(kv_shard *s, int table, const int64_t *rule_idx, int64_t n, uint32_t *out) {
+    if (!s || (n > 0 && (!rule_idx || !out))) return fail(KV_E_INVALID, "kv_occ_table_gather: null pointer");
+    if (table < 0 || table >= (int)s->occ_tables.size() || !s->occ_tables[table])
+        return fail(KV_E_INVALID, "kv_occ_table_gather: no such table");
+    DeviceGuard g(s->device);
+    CU(cudaStreamSynchronize(s->stream));
+    for (int64_t i = 0; i < n; ++i) {
+        const int64_t c = rule_idx[i] - s->col0;
+        if (c < 0 || c >= s->n_cols) return fail(KV_E_INVALID, "kv_occ_table_gather: rule outside the shard");
+        CU(cudaMemcpy(out + i, s->occ_tables[table] + c, 4, cudaMemcpyDeviceToHost));
+    }
+    return KV_OK;
+}
+
 extern "C" int kv_gini_level(kv_shard *s, int64_t n_nodes, const uint64_t *class_masks, const double *altered_prior,
-                             const double *n_total, const int64_t *n_node, double *min_score, int64_t *n_found) {
+                             const double *n_total, const int64_t *n_node, const int32_t *occ_table, double *min_score,
+                             int64_t *n_found, uint32_t *occ_max) {
     if (!s || !class_masks || !altered_prior || !n_total || !n_node || !min_score || !n_found)
         return fail(KV_E_INVALID, "kv_gini_level: null pointer");
     if (n_nodes <= 0) return fail(KV_E_INVALID, "kv_gini_level: no nodes");
+    if (occ_table)
+        for (int64_t i = 0; i < n_nodes; ++i)
+            if (occ_table[i] >= 0 && (occ_table[i] >= (int)s->occ_tables.size() || !s->occ_tables[occ_table[i]]))
+                return fail(KV_E_INVALID, "kv_gini_level: unknown occurrence table");
     DeviceGuard g(s->device);
     s->last_launches = 0;
     s->scm_valid = s->gini_valid = false;
@@ -3525,15 +3618,17 @@ extern "C" int kv_gini_level(kv_shard *s, int64_t n_nodes, const uint64_t *class
     const long long W = s->W, n_seg_ld = s->ld / 64;
     KV_TRY(ensure_counts(s, 2 + 2 * per));
     // d_level: min enc [per] | counter [per] | ties [per][kLevelSlotIdx] | segmin [per][ld/64] | score tables [per][4096]
+    //          | occurrence maxima u32 [2 * per]
     const size_t level_bytes = (size_t)per * 16 + (size_t)per * kLevelSlotIdx * 8 + (size_t)per * n_seg_ld * 8 +
-                               (size_t)per * GINI2_TABLE_MAX * 8;
+                               (size_t)per * GINI2_TABLE_MAX * 8 + (size_t)per * 8;
     KV_TRY(ensure(s->d_level, level_bytes));
     unsigned long long *d_min = (unsigned long long *)s->d_level.p, *d_cntr = d_min + per;
     long long *d_ties = (long long *)(d_cntr + per);
     unsigned long long *d_segmin = (unsigned long long *)(d_ties + (size_t)per * kLevelSlotIdx);
     double *d_tables = (double *)(d_segmin + (size_t)per * n_seg_ld);
+    unsigned int *d_occmax = (unsigned int *)(d_tables + (size_t)per * GINI2_TABLE_MAX);
     const size_t hdr_bytes = (size_t)per * 16 + (size_t)per * kLevelSlotIdx * 8;
-    KV_TRY(ensure_pinned(s, count_batch_stride(W) + hdr_bytes));
+    KV_TRY(ensure_pinned(s, count_batch_stride(W) + hdr_bytes + (size_t)per * 8));
     CU(cudaStreamSynchronize(s->stream));
     char *pin_rec = (char *)s->h_pin;
     const unsigned long long *h_hdr = (const unsigned long long *)((char *)s->h_pin + count_batch_stride(W));
@@ -3556,6 +3651,7 @@ extern "C" int kv_gini_level(kv_shard *s, int64_t n_nodes, const uint64_t *class
         s->scan_calls += 1;
         CU(cudaMemsetAsync(d_min, 0xFF, (size_t)per * 8, s->stream));
         CU(cudaMemsetAsync(d_cntr, 0, (size_t)per * 8, s->stream));
+        CU(cudaMemsetAsync(d_occmax, 0, (size_t)per * 8, s->stream));
         std::vector<GiniParams> params((size_t)nb);
         for (int i = 0; i < nb; ++i) {
             GiniParams &G = params[i];
@@ -3584,10 +3680,22 @@ extern "C" int kv_gini_level(kv_shard *s, int64_t n_nodes, const uint64_t *class
                 G.table = d_tables + (size_t)i * GINI2_TABLE_MAX;
             }
             k_gini2_counts<<<grid_score, 256, 0, s->stream>>>(G, d_segmin + (size_t)i * n_seg_ld);
-            k_gini2_ties_seg<<<grid_ties, 256, 0, s->stream>>>(G);
-            count_launch(s, 2);
+            if (occ_table && occ_table[b0 + i] >= 0) {
+                // the reference's tiebreaker on the device: largest occurrence among the ties, then the survivors
+                G.occ = s->occ_tables[occ_table[b0 + i]];
+                G.occ_max = d_occmax + i;
+                k_gini2_ties_occmax<<<grid_ties, 256, 0, s->stream>>>(G);
+                k_gini2_ties_occ<<<grid_ties, 256, 0, s->stream>>>(G);
+                count_launch(s, 3);
+            } else {
+                k_gini2_ties_seg<<<grid_ties, 256, 0, s->stream>>>(G);
+                count_launch(s, 2);
+            }
         }
         CU(cudaMemcpyAsync((void *)h_hdr, d_min, hdr_bytes, cudaMemcpyDeviceToHost, s->stream));
+        KV_TRY(ensure_pinned(s, count_batch_stride(W) + hdr_bytes + (size_t)per * 8));
+        unsigned int *h_occmax = (unsigned int *)((char *)s->h_pin + count_batch_stride(W) + hdr_bytes);
+        CU(cudaMemcpyAsync(h_occmax, d_occmax, (size_t)per * 4, cudaMemcpyDeviceToHost, s->stream));
         CU(stream_sync_spin(s->stream));
         CU(cudaGetLastError());
         float ms = 0;
@@ -3605,6 +3713,7 @@ extern "C" int kv_gini_level(kv_shard *s, int64_t n_nodes, const uint64_t *class
             const long long found = (long long)h_hdr[per + i];
             min_score[b0 + i] = dec_f64_min(h_hdr[i]);
             n_found[b0 + i] = found;
+            if (occ_max) occ_max[b0 + i] = h_occmax[i];
             int64_t *out = s->h_level + s->h_level_used;
             s->level_span.emplace_back(s->h_level_used, (size_t)found);
             s->h_level_used += (size_t)found;
@@ -3621,7 +3730,8 @@ extern "C" int kv_gini_level(kv_shard *s, int64_t n_nodes, const uint64_t *class
             G.out_idx = raw;
             G.cap = found;
             CU(cudaMemsetAsync(d_cntr + i, 0, 8, s->stream));
-            k_gini2_ties_seg<<<grid_ties, 256, 0, s->stream>>>(G);
+            if (G.occ) k_gini2_ties_occ<<<grid_ties, 256, 0, s->stream>>>(G);      // (its maximum is still in d_occmax)
+            else k_gini2_ties_seg<<<grid_ties, 256, 0, s->stream>>>(G);
             count_launch(s);
             KV_TRY(device_sort(s, raw, sorted, nullptr, nullptr, found));
             CU(cudaMemcpyAsync(out, sorted, (size_t)found * 8, cudaMemcpyDeviceToHost, s->stream));

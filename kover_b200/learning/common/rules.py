@@ -79,6 +79,32 @@ class BaseRuleClassifications(object):
         raise NotImplementedError()
 
 
+class DeviceOccurrences(object):
+    """k-mer occurrence counts of a set of genomes (the input of the reference's CART tiebreaker,
+    experiment_cart.py:82-94, 264), resident on the device when the shards support it."""
+
+    def __init__(self, rule_classifications, rows):
+        self._rc = rule_classifications
+        self.rows = np.asarray(rows)
+        self._host = None
+        self.table = None
+        group = rule_classifications._group
+        if group.occurrence_table_supported() and rule_classifications._free_tables:
+            self.table = rule_classifications._free_tables.pop()
+            group.occurrence_table_set(self.table, rule_classifications.row_mask(self.rows))
+
+    def host(self):
+        if self._host is None:
+            self._host = self._rc.sum_rows(self.rows)
+        return self._host
+
+    def release(self):
+        if self.table is not None and self._rc._group.shards:
+            self._rc._group.occurrence_table_set(self.table, None)
+            self._rc._free_tables.append(self.table)
+        self.table = None
+
+
 def _default_devices():
     env = os.environ.get("KOVER_B200_DEVICES")
     if env:
@@ -122,6 +148,7 @@ class KmerRuleClassifications(BaseRuleClassifications):
 
         self._n_kmers = int(dataset.shape[1])
         self._blacklist_key = None
+        self._free_tables = list(range(63, -1, -1))         # device occurrence tables (DeviceOccurrences)
         if shard_group is not None:
             self._group = shard_group
         else:
@@ -298,25 +325,48 @@ class KmerRuleClassifications(BaseRuleClassifications):
         n_node = np.array([len(example_idx[c]) for c in classes], dtype=np.int64)
         return self._group.gini_best_split(masks, prior, total, n_node)
 
-    def gini_best_splits(self, example_idx_by_node, altered_priors, n_total_class_examples, rule_blacklist=()):
+    def gini_best_splits(self, example_idx_by_node, altered_priors, n_total_class_examples, rule_blacklist=(),
+                         tie_tables=None):
         """``gini_best_split`` for several nodes at once -- the nodes of a tree level (cart.py:260-339 scans them one
         after the other), or of the same level of SEVERAL trees (the fold trees and the master tree of a
         cross-validation): with two classes, the class masks of up to 8 nodes are counted per pass over the matrix.
         altered_priors / n_total_class_examples: one dict for all the nodes, or one dict per node.
+        tie_tables: one DeviceOccurrences (``occurrence_table``) or None per node -- the candidates of such a node are
+        then already reduced by the reference's occurrence tiebreaker (experiment_cart.py:82-94), on the device
+        whenever the level search runs there.
         -> [(min score, presence-rule indices achieving it, ascending)] in node order."""
         nodes = list(example_idx_by_node)
         per_node = isinstance(altered_priors, (list, tuple))
         priors = list(altered_priors) if per_node else [altered_priors] * len(nodes)
         totals = list(n_total_class_examples) if per_node else [n_total_class_examples] * len(nodes)
-        if len(nodes) == 1 or any(len(ex) != 2 or list(ex.keys()) != list(nodes[0].keys()) for ex in nodes):
-            return [self.gini_best_split(ex, pr, tt, rule_blacklist) for ex, pr, tt in zip(nodes, priors, totals)]
+        tables = list(tie_tables) if tie_tables is not None else [None] * len(nodes)
+        any_table = any(t is not None for t in tables)
+        two_class = all(len(ex) == 2 and list(ex.keys()) == list(nodes[0].keys()) for ex in nodes)
+        on_device = two_class and (len(nodes) > 1 or any_table) and \
+            (not any_table or self._group.occurrence_table_supported())
+        if not on_device:
+            found = [self.gini_best_split(ex, pr, tt, rule_blacklist) for ex, pr, tt in zip(nodes, priors, totals)]
+            out = []
+            for (score, idx), table in zip(found, tables):
+                if table is not None and len(idx) > 0:
+                    occ = table.host()[idx]
+                    idx = idx[np.isclose(occ, occ.max())]
+                out.append((score, idx))
+            return out
         self.set_rule_blacklist(rule_blacklist)
         classes = list(nodes[0].keys())
         masks = np.stack([np.stack([self.row_mask(ex[c]) for c in classes]) for ex in nodes])
         prior = np.array([[pr[c] for c in classes] for pr in priors], dtype=np.float64)
         total = np.array([[tt[c] for c in classes] for tt in totals], dtype=np.float64)
         n_node = np.array([[len(ex[c]) for c in classes] for ex in nodes], dtype=np.int64)
-        return self._group.gini_best_splits(masks, prior, total, n_node)
+        occ_ids = np.array([-1 if t is None else t.table for t in tables], dtype=np.int32) if any_table else None
+        return self._group.gini_best_splits(masks, prior, total, n_node, occ_ids)
+
+    def occurrence_table(self, rows):
+        """Occurrence counts of every k-mer in the genomes ``rows`` (= ``sum_rows(rows)[:K]``), kept on the device
+        for the tiebreaker of the tree learner; ``.host()`` fetches them.  Up to 64 tables at a time; ``release()``
+        returns a table."""
+        return DeviceOccurrences(self, rows)
 
     def kmer_risk_tables(self, train_pos_idx, train_neg_idx):
         """The individual k-mer risk tables `kover dataset split` stores per split / fold (split.py:171-188):

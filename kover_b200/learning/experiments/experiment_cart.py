@@ -22,6 +22,34 @@ def _tiebreaker(best_score_idx, rule_kmer_occurrences):
     return best_score_idx[np.isclose(occurrences, occurrences.max())]
 
 
+class OccurrenceTiebreaker(object):
+    """``_tiebreaker`` (:82-94) bound to the k-mer occurrences of a training set (:264 computes them with
+    ``sum_rows(train)``).  When the rule_classifications can keep that table on the device, the tree learner has
+    the split search apply the tiebreaker there (``device_occurrences``): the millions of ties of a small node
+    never reach the host.  Calling the object applies it on the host (same result)."""
+
+    def __init__(self, rule_classifications, train_genome_idx):
+        self._rc, self._rows = rule_classifications, np.asarray(train_genome_idx)
+        make = getattr(rule_classifications, "occurrence_table", None)
+        table = make(self._rows) if make is not None else None
+        self.device_occurrences = table if table is not None and table.table is not None else None
+        self._host = None
+
+    def _occurrences(self):
+        if self._host is None:
+            self._host = self.device_occurrences.host() if self.device_occurrences is not None \
+                else self._rc.sum_rows(self._rows)
+        return self._host
+
+    def __call__(self, best_score_idx):
+        return _tiebreaker(best_score_idx, self._occurrences())
+
+    def release(self):
+        if self.device_occurrences is not None:
+            self.device_occurrences.release()
+            self.device_occurrences = None
+
+
 def _split_callback(node, equivalent_rules_idx):
     """Remember the equivalent rules of a split on its rule object (:97-106)."""
     node.rule.equivalent_rules_idx = equivalent_rules_idx
@@ -100,13 +128,13 @@ def learn_pruned_tree_bound(rule_classifications, rules, example_labels, train_g
     master_predictor = DecisionTreeClassifier(criterion=hps["criterion"], max_depth=hps["max_depth"],
                                               min_samples_split=hps["min_samples_split"],
                                               class_importance=hps["class_importance"])
+    tiebreaker = OccurrenceTiebreaker(rule_classifications, train_genome_idx)
     master_predictor.fit(rules=rules, rule_classifications=rule_classifications,
                          example_idx={c: train_genome_idx[example_labels[train_genome_idx] == c]
                                       for c in range(n_classes)},
-                         rule_blacklist=rule_blacklist,
-                         tiebreaker=partial(_tiebreaker,
-                                            rule_kmer_occurrences=rule_classifications.sum_rows(train_genome_idx)),
+                         rule_blacklist=rule_blacklist, tiebreaker=tiebreaker,
                          level_callback=None, split_callback=_split_callback)
+    tiebreaker.release()
     min_score, min_score_tree = np.inf, None
     train_answers = example_labels[train_genome_idx]
     sequence = []
@@ -154,8 +182,8 @@ def learn_pruned_tree_cv(rule_classifications, rules, example_labels, train_geno
     """``_learn_pruned_tree_cv`` (:297-436): cost-complexity pruning with the pruning parameter chosen by k-fold
     cross-validation (Breiman et al. 1984, section 3.4).  folds: [(train_genome_idx, test_genome_idx)] in the
     reference's fold order.  The fold trees and the master tree are grown in LOCK-STEP over the resident matrix
-    (learners.cart.fit_many: at every depth the nodes of all the trees share matrix passes) and their k-mer
-    occurrence tables (the tiebreaker's input) come from one multi-mask pass.
+    (learners.cart.fit_many: at every depth the nodes of all the trees share matrix passes); their k-mer
+    occurrence tables (the tiebreaker's input) stay on the device, where the tiebreaker is applied.
     -> (hps with "pruning_alpha", cross-validation score, pruned master tree)."""
     from math import sqrt
 
@@ -172,20 +200,17 @@ def learn_pruned_tree_cv(rule_classifications, rules, example_labels, train_geno
                                       class_importance=hps["class_importance"])
 
     training_sets = [tr for tr, _ in folds] + [train_genome_idx]
-    n_kmers = rule_classifications.shape[1] // 2
-    presence = rule_classifications.sum_rows_multi(training_sets)             # one pass instead of one per tree
-    learners, fit_args = [], []
+    learners, fit_args, tiebreakers = [], [], []
     for i, tr in enumerate(training_sets):
-        # the reference's table is sum_rows(train): presence counts then absence counts, in the smallest uint type
-        occurrences = np.concatenate((presence[i], len(tr) - presence[i])).astype(_occurrence_dtype(len(tr)))
-        assert occurrences.shape[0] == 2 * n_kmers
+        # the tiebreaker's table is sum_rows(train) (:345, :364): kept on the device when the matrix lives there
+        tiebreakers.append(OccurrenceTiebreaker(rule_classifications, tr))
         learners.append(new_tree())
         fit_args.append(dict(rules=rules, example_idx={c: tr[example_labels[tr] == c] for c in range(n_classes)},
-                             rule_blacklist=rule_blacklist,
-                             tiebreaker=partial(_tiebreaker, rule_kmer_occurrences=occurrences),
-                             level_callback=None,
+                             rule_blacklist=rule_blacklist, tiebreaker=tiebreakers[-1], level_callback=None,
                              split_callback=_split_callback if i == len(folds) else None))
     fit_many(learners, fit_args, rule_classifications)
+    for tb in tiebreakers:
+        tb.release()
     fold_predictors, master_predictor = learners[:-1], learners[-1]
 
     master_alphas, master_pruned_trees = _prune_tree(master_predictor.decision_tree)
@@ -208,11 +233,6 @@ def learn_pruned_tree_cv(rule_classifications, rules, example_labels, train_geno
             min_score, min_score_tree = cv_score, tree
             hps["pruning_alpha"] = geo_mean_alpha
     return hps, min_score, min_score_tree
-
-
-def _occurrence_dtype(n_rows):
-    from ...utils import _minimum_uint_size
-    return _minimum_uint_size(n_rows)
 
 
 def train_tree(hp_search, criterion, class_importance, max_depth, min_samples_split, progress_callback,

@@ -88,16 +88,20 @@ class DecisionTreeClassifier(object):
         answer = None
         while True:
             try:
-                nodes, impurity, blacklist = levels.send(answer)
+                nodes, impurity, blacklist, tie_table = levels.send(answer)
             except StopIteration:
                 return
-            answer = self._search_level(rule_classifications, nodes, impurity, blacklist)
+            answer = self._search_level(rule_classifications, nodes, impurity, blacklist, tie_table)
 
-    def _search_level(self, rule_classifications, nodes, impurity, rule_blacklist):
-        """Best split of every node of ``nodes`` (class -> example indices dicts) -> [(score, candidate rules)]."""
+    def _search_level(self, rule_classifications, nodes, impurity, rule_blacklist, tie_table=None):
+        """Best split of every node of ``nodes`` (class -> example indices dicts) -> [(score, candidate rules)];
+        with a tie_table (see _fit_levels) the candidates are already reduced by the occurrence tiebreaker."""
         if self.criterion == "gini":
             many = getattr(rule_classifications, "gini_best_splits", None)
             if many is not None:
+                if tie_table is not None:
+                    return many(nodes, impurity.priors, impurity.n_total, rule_blacklist,
+                                tie_tables=[tie_table] * len(nodes))
                 return many(nodes, impurity.priors, impurity.n_total, rule_blacklist)
             return [rule_classifications.gini_best_split(idx, impurity.priors, impurity.n_total, rule_blacklist)
                     for idx in nodes]
@@ -105,8 +109,10 @@ class DecisionTreeClassifier(object):
 
     def _fit_levels(self, rules, rule_classifications, example_idx, rule_blacklist=None, tiebreaker=None,
                     level_callback=None, split_callback=None):
-        """Generator: yields (node example dicts, impurity, blacklist) once per tree level and is sent the list of
-        (best score, candidate rules) of those nodes."""
+        """Generator: yields (node example dicts, impurity, blacklist, tie table) once per tree level and is sent the
+        list of (best score, candidate rules) of those nodes.  A tiebreaker that carries ``device_occurrences`` (a
+        rules.DeviceOccurrences: the reference's occurrence tiebreaker, experiment_cart.py:82-94) is applied by the
+        split search itself -- on the device -- and not called again on the host."""
         if not hasattr(rule_classifications, "gini_best_split"):
             raise TypeError("kover_b200's DecisionTreeClassifier scans a device-resident matrix: pass a "
                             "kover_b200.learning.common.rules.KmerRuleClassifications (there is no CPU path).")
@@ -114,6 +120,9 @@ class DecisionTreeClassifier(object):
         split_callback = split_callback or (lambda node, equivalent_rules_idx: None)
         tiebreaker = tiebreaker or (lambda candidates: candidates)
         rule_blacklist = [] if rule_blacklist is None else rule_blacklist
+        tie_table = getattr(tiebreaker, "device_occurrences", None)
+        if self.criterion != "gini" or not hasattr(rule_classifications, "gini_best_splits"):
+            tie_table = None
 
         example_idx = dict((c, np.asarray(idx)) for c, idx in example_idx.items())
         impurity = _NodeImpurity(example_idx, self.class_importance)
@@ -143,13 +152,13 @@ class DecisionTreeClassifier(object):
                           if not (1.0 in node.class_proportions.values() or node.n_examples < min_split)]
             found = []
             if splittable:
-                found = yield ([node.class_examples_idx for node in splittable], impurity, rule_blacklist)
+                found = yield ([node.class_examples_idx for node in splittable], impurity, rule_blacklist, tie_table)
             next_level = []
             for node, (best_score, candidates) in zip(splittable, found):
                 if best_score == np.inf:
                     continue                           # no rule separates the node into two non-empty children
                 members = node.class_examples_idx
-                equivalent = tiebreaker(candidates)
+                equivalent = candidates if tie_table is not None else tiebreaker(candidates)
                 if np.may_share_memory(equivalent, candidates):
                     equivalent = np.array(equivalent)  # candidates may be a view of a buffer the next level reuses
                 chosen = equivalent[0]
@@ -211,13 +220,15 @@ def fit_many(learners, fit_args, rule_classifications):
         for i in batchable:
             by_blacklist.setdefault(np.asarray(running[i][1][2], dtype=np.int64).tobytes(), []).append(i)
         for members in by_blacklist.values():
-            nodes, priors, totals = [], [], []
+            nodes, priors, totals, tables = [], [], [], []
             for i in members:
-                level_nodes, impurity, _ = running[i][1]
+                level_nodes, impurity, _, tie_table = running[i][1]
                 nodes += level_nodes
                 priors += [impurity.priors] * len(level_nodes)
                 totals += [impurity.n_total] * len(level_nodes)
-            found = many(nodes, priors, totals, running[members[0]][1][2])
+                tables += [tie_table] * len(level_nodes)
+            found = many(nodes, priors, totals, running[members[0]][1][2],
+                         tie_tables=tables if any(t is not None for t in tables) else None)
             # the tie lists may be views of one result buffer: every learner of the batch consumes its share before
             # the next search is issued (below), so they are handed over as they are
             at = 0
@@ -227,8 +238,8 @@ def fit_many(learners, fit_args, rule_classifications):
                 at += n
         for i in running:
             if i not in answers:
-                level_nodes, impurity, blacklist = running[i][1]
-                answers[i] = learners[i]._search_level(rule_classifications, level_nodes, impurity, blacklist)
+                level_nodes, impurity, blacklist, tie_table = running[i][1]
+                answers[i] = learners[i]._search_level(rule_classifications, level_nodes, impurity, blacklist, tie_table)
                 # (a per-learner search invalidates earlier views: materialise what the batch produced)
                 answers = dict((j, [(sc, np.array(c)) for sc, c in a]) if j != i else (j, a) for j, a in answers.items())
         still_running = {}

@@ -368,16 +368,51 @@ class ShardGroup(object):
             idx = self.comm.allgather_concat(idx)
         return m, np.sort(idx)
 
-    def gini_best_splits(self, node_masks, altered_prior, n_total, n_node):
+    # ------------------------------------------------------------------ occurrence tables (CART tiebreaker on the device)
+    def occurrence_table_supported(self):
+        return self.comm is None and all(hasattr(s, "occ_table_set") for s in self.shards)
+
+    def occurrence_table_set(self, table, mask):
+        for s in self.shards:
+            s.occ_table_set(table, mask)
+
+    def gini_best_splits(self, node_masks, altered_prior, n_total, n_node, occ_tables=None):
         """gini_best_split for several two-class nodes (a tree level): node_masks [n_nodes, 2, W], n_node
         [n_nodes, 2].  Every shard counts the class masks of up to 8 nodes per matrix pass (kv_gini_level); the
         minima are merged over shards / ranks and the tie lists of the shards that hold a node's minimum are
-        concatenated in column order."""
+        concatenated in column order.  occ_tables [n_nodes] (local shards only): the reference's occurrence
+        tiebreaker (experiment_cart.py:82-94) is applied on the device, the lists hold its survivors."""
         n_node = np.asarray(n_node, dtype=np.int64)
         altered_prior = np.broadcast_to(np.asarray(altered_prior, dtype=np.float64), n_node.shape)
         n_total = np.broadcast_to(np.asarray(n_total, dtype=np.float64), n_node.shape)
         if not hasattr(self.shards[0], "gini_level"):
+            assert occ_tables is None
             return [self.gini_best_split(m, pr, tt, nn) for m, pr, tt, nn in zip(node_masks, altered_prior, n_total, n_node)]
+        if occ_tables is not None:
+            assert self.comm is None
+            per_shard = [s.gini_level(node_masks, altered_prior, n_total, n_node, occ_tables) for s in self.shards]
+            if self._single:
+                return [(m, idx) for m, idx, _ in per_shard[0]]
+            out = []
+            for i in range(len(per_shard[0])):
+                m = min(res[i][0] for res in per_shard)
+                holders = [(s, res[i]) for s, res in zip(self.shards, per_shard) if res[i][0] == m and m != np.inf]
+                if not holders:
+                    out.append((float(m), np.zeros(0, dtype=np.int64)))
+                    continue
+                # a shard's survivors are relative to ITS largest occurrence: they stand when that is the global one;
+                # a smaller maximum within the tolerance (only possible from 100 000 occurrences up) is re-filtered
+                g = max(r[2] for _, r in holders)
+                tol = 1e-8 + 1e-5 * abs(float(g))
+                parts = []
+                for s, (_, idx, local_max) in holders:
+                    if local_max == g or occ_tables[i] < 0:
+                        parts.append(np.array(idx))
+                    elif abs(float(local_max) - float(g)) <= tol:
+                        o = s.occ_table_gather(int(occ_tables[i]), idx).astype(np.float64)
+                        parts.append(np.array(idx)[np.abs(o - float(g)) <= tol])
+                out.append((float(m), np.sort(np.concatenate(parts))))
+            return out
         per_shard = [s.gini_level(node_masks, altered_prior, n_total, n_node) for s in self.shards]
         if self._single:
             return per_shard[0]         # (the tie lists are read-only views, valid until the next level search)

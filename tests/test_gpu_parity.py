@@ -550,6 +550,53 @@ def test_level_search_matches_per_node_search(devices, sorted_labels):
     rc.close()
 
 
+@pytest.mark.parametrize("devices", [[0], [0, 0, 0]], ids=["1shard", "3shards"])
+def test_device_occurrence_tiebreaker(devices):
+    """The reference's CART tiebreaker (experiment_cart.py:82-94: among the best splits keep the k-mers that occur in
+    the most training genomes, numpy.isclose to the maximum) applied by the level search on the device == the host
+    tiebreaker applied to the plain tie lists; per-node tables (two trees in one search), tiny nodes with huge tie
+    sets, and the single-node call."""
+    from kover_b200.learning.experiments import experiment_cart as cexp
+    seed, n, k = 23, 700, 50000
+    P = synthetic_block(seed, n, 0, k)
+    y = synthetic_labels(seed, n, sorted_by_label=False)
+    rs = np.random.RandomState(seed)
+    perm = rs.permutation(n)
+    train_a, train_b = np.sort(perm[:450]), np.sort(perm[200:650])
+    nodes, tables_of = [], []
+    rc = KmerRuleClassifications(P, n, devices=devices)
+    tb_a, tb_b = cexp.OccurrenceTiebreaker(rc, train_a), cexp.OccurrenceTiebreaker(rc, train_b)
+    assert tb_a.device_occurrences is not None and tb_a.device_occurrences.table != tb_b.device_occurrences.table
+    at = 0
+    for sz, tb in ((200, tb_a), (120, tb_b), (60, tb_a), (9, tb_b), (4, tb_a), (3, tb_b), (2, tb_a), (40, None), (2, tb_b), (30, tb_a)):
+        pool = train_a if tb is tb_a or tb is None else train_b
+        members = np.sort(pool[at % 300:at % 300 + sz])
+        at += sz
+        ex = {0: members[y[members] == 0], 1: members[y[members] == 1]}
+        if len(ex[0]) and len(ex[1]):
+            nodes.append(ex)
+            tables_of.append(tb)
+    n_total = {0: float((y == 0).sum()), 1: float((y == 1).sum())}
+    priors = {0: 0.5, 1: 0.5}
+    plain = rc.gini_best_splits(nodes, priors, n_total)
+    plain = [(s_, np.array(c)) for s_, c in plain]
+    got = rc.gini_best_splits(nodes, priors, n_total,
+                              tie_tables=[None if t is None else t.device_occurrences for t in tables_of])
+    assert max(len(c) for _, c in plain) > 1024
+    for (ws, wc), (gs, gc), tb in zip(plain, got, tables_of):
+        want = wc if tb is None else tb(wc)                      # the host tiebreaker on the full tie list
+        assert gs == ws and np.array_equal(np.sort(want), np.asarray(gc)), (len(wc), len(want), len(gc))
+    # occurrences on the device == sum_rows on the host
+    assert np.array_equal(tb_a.device_occurrences.host()[:k], rc.sum_rows(train_a)[:k])
+    # a single node goes through the same path
+    one = rc.gini_best_splits(nodes[:1], priors, n_total, tie_tables=[tables_of[0].device_occurrences])
+    assert one[0][0] == plain[0][0] and np.array_equal(np.asarray(one[0][1]), np.sort(tables_of[0](plain[0][1])))
+    tb_a.release()
+    tb_b.release()
+    assert len(rc._free_tables) == 64
+    rc.close()
+
+
 @pytest.mark.parametrize("n_classes", [2, 3, 5])
 def test_gini_scores_vs_checker(n_classes):
     seed, n, k = 11, 700, 40000

@@ -37,6 +37,10 @@ def tiebreaker(idx):                      # experiment_cart.py:82-94: keep the m
     return idx[np.isclose(o, o.max())]
 
 
+from kover_b200.learning.experiments.experiment_cart import OccurrenceTiebreaker
+device_tiebreaker = OccurrenceTiebreaker(rc, train)      # the same tiebreaker, applied by the level search on the device
+
+
 def tree_sig(node):
     if node.rule is None:
         return ("leaf", node.n_examples)
@@ -47,7 +51,7 @@ import cProfile
 import pstats
 res = {}
 DecisionTreeClassifier("gini", 4, 2, {0: 1.0, 1: 1.0}).fit(rules, rc, ex, tiebreaker=tiebreaker)     # warm-up: allocations
-for mode in (("level",) if "--level-only" in sys.argv else ("level", "per-node")):
+for mode in (("level",) if "--level-only" in sys.argv else ("level+device tiebreak", "level", "per-node")):
     if mode == "per-node":
         rc.gini_best_splits = lambda nodes, pri, tot, bl=(): [rc.gini_best_split(e, pri, tot, bl) for e in nodes]
     t = DecisionTreeClassifier("gini", depth, 2, {0: 1.0, 1: 1.0})
@@ -57,16 +61,17 @@ for mode in (("level",) if "--level-only" in sys.argv else ("level", "per-node")
     t0 = time.perf_counter()
     if prof:
         prof.enable()
-    t.fit(rules, rc, ex, tiebreaker=tiebreaker, level_callback=lambda infos: levels.append(time.perf_counter()))
+    t.fit(rules, rc, ex, tiebreaker=device_tiebreaker if "device" in mode else tiebreaker,
+          level_callback=lambda infos: levels.append(time.perf_counter()))
     if prof:
         prof.disable()
         pstats.Stats(prof).sort_stats("tottime").print_stats(12)
     dt = time.perf_counter() - t0
     i1 = sh.info()
     n_split = len(t.decision_tree.rules)
-    print("%-8s: fit %.3f s, %d split nodes, depth %d, %d matrix passes, %.1f ms in count/scan kernels"
+    print("%-22s: fit %.3f s, %d split nodes, depth %d, %d matrix passes, %.1f ms in count/scan kernels"
           % (mode, dt, n_split, len(levels), i1.scan_calls - i0.scan_calls, i1.scan_ms_total - i0.scan_ms_total))
     res[mode] = tree_sig(t.decision_tree)
 if "per-node" in res:
-    assert res["level"] == res["per-node"]
+    assert res["level"] == res["per-node"] == res["level+device tiebreak"]
     print("identical trees")
