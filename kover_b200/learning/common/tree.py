@@ -5,6 +5,8 @@ Interface parity with reference kover/learning/common/tree.py:28-264 (``BreimanI
 The node statistics follow Breiman et al. (1984): eq. 2.2-2.4 and def. 2.10; their floating-point operation order
 is kept (prior * n / N, sum in class order) since rule importances and pruning thresholds are compared exactly.
 """
+from copy import deepcopy
+
 import numpy as np
 
 from .models import BaseModel
@@ -38,6 +40,22 @@ class TreeNode(BaseModel):
         self.criterion_value = criterion_value
         counts = dict((c, len(idx)) for c, idx in class_examples_idx.items())
         self.breiman_info = BreimanInfo(counts, class_priors, total_n_examples_by_class)
+
+    def __deepcopy__(self, memo):
+        """Independent copy of the (sub)tree: nodes and rule objects are copied (pruning turns nodes into leaves,
+        predictions re-address rule indices), the per-class example index arrays and the node statistics are shared --
+        nothing modifies them in place.  The pruning sequence copies the tree once per pruned tree (cart.py:434-470),
+        which made the array copies the dominant cost of the experiment drivers."""
+        clone = object.__new__(type(self))
+        memo[id(self)] = clone
+        for name, value in self.__dict__.items():
+            if name == "class_examples_idx":
+                clone.__dict__[name] = dict(value)
+            elif name == "breiman_info":
+                clone.__dict__[name] = value
+            else:
+                clone.__dict__[name] = deepcopy(value, memo)
+        return clone
 
     # -- structure
     @property
@@ -113,14 +131,24 @@ class ProbabilisticTreeNode(TreeNode):
         return node
 
     def predict_proba(self, X):
-        """[n_classes, n_examples]: class posterior of the leaf every example reaches."""
+        """[n_classes, n_examples]: class posterior of the leaf every example reaches.  The examples are routed down
+        the tree node by node (one vectorised rule evaluation per internal node) instead of one by one."""
         X = np.ascontiguousarray(X)
         classes = list(self.class_examples_idx.keys())
         out = np.zeros((len(classes), X.shape[0]))
-        for i in range(X.shape[0]):
-            posterior = self._leaf_of(X[i].reshape(1, -1)).breiman_info.p_j_given_t
-            for c in classes:
-                out[c][i] = posterior[c]
+        pending = [(self, np.arange(X.shape[0]))]
+        while pending:
+            node, rows = pending.pop()
+            if rows.size == 0:
+                continue
+            if node.is_leaf:
+                posterior = node.breiman_info.p_j_given_t
+                for c in classes:
+                    out[c][rows] = posterior[c]
+                continue
+            goes_left = node.rule.classify(X[rows]) != 0          # rule true -> left child
+            pending.append((node.left_child, rows[goes_left]))
+            pending.append((node.right_child, rows[~goes_left]))
         return out
 
     def predict(self, X):
