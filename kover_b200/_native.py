@@ -370,7 +370,8 @@ class Shard(object):
         neg_mask = np.ascontiguousarray(neg_mask, dtype=np.uint64)
         nb = n_utility_blocks(self.n_kmers_total, util_block_size)
         bm, sel = np.empty(nb, dtype=np.float64), np.empty(nb, dtype=np.uint8)
-        idx, pe, nc = (np.empty(capacity, dtype=np.int64) for _ in range(3))
+        reuse = capacity <= self._tie_cap              # the step's scratch arrays are allocated once per shard
+        idx, pe, nc = self._tie_buf if reuse else (np.empty(capacity, dtype=np.int64) for _ in range(3))
         best, n, over = ctypes.c_double(0.0), _c_i64(0), ctypes.c_int(0)
         rc = self._lib.kv_scm_best_rules_p2p(self._h, ptr(pos_mask), ptr(neg_mask), int(n_pos), int(n_neg), float(p),
                                              int(util_block_size), int(packet_capacity), ctypes.byref(best), capacity,
@@ -382,7 +383,10 @@ class Shard(object):
             check(rc)
         if over.value:
             return None, bm, best.value, sel
-        return (best.value, idx[:n.value], pe[:n.value], nc[:n.value]), bm, best.value, sel
+        m = n.value
+        if reuse:
+            return (best.value, idx[:m].copy(), pe[:m].copy(), nc[:m].copy()), bm, best.value, sel
+        return (best.value, idx[:m], pe[:m], nc[:m]), bm, best.value, sel
 
     QUEUE_SLOT_RECS = 256
 
