@@ -120,3 +120,28 @@ def test_kover_dataset_adapter(tmp_path, fixed_strings):
     assert s.unique_risk_by_kmer.shape == (k,) and s.unique_risk_by_anti_kmer.shape == (k,)
     assert np.array_equal(s.folds[1].train_genome_idx[...], np.sort(folds[1][0]))
     d.close()
+
+
+def test_randomized_round_trips(tmp_path):
+    """Random shapes / chunk shapes / element types / compression levels / slices: what the writer lays out, the
+    reader returns (chunk grid edges, partial edge chunks, multi-level chunk B-trees, 1-D and 2-D)."""
+    rs = np.random.RandomState(99)
+    dtypes = [np.uint8, np.uint16, np.uint32, np.uint64, np.int64, np.float64, np.float32]
+    for trial in range(25):
+        ndim = 1 + trial % 2
+        shape = tuple(int(rs.randint(1, 40 if ndim == 2 else 5000)) if d == 0 else int(rs.randint(1, 700)) for d in range(ndim))
+        dt = dtypes[trial % len(dtypes)]
+        data = (rs.rand(*shape) * 1000).astype(dt)
+        chunks = tuple(int(rs.randint(1, max(2, s // 2 + 2))) for s in shape) if trial % 5 else None
+        gz = [None, 1, 4, 9][trial % 4] if chunks is not None else None
+        path = str(tmp_path / ("r%d.h5" % trial))
+        with Writer(path) as w:
+            w.create_dataset("g/sub/data", data, chunks=chunks, compression=gz, attrs={"trial": np.int64(trial)})
+        d = hdf5_lite.File(path)["g/sub/data"]
+        assert d.shape == shape and d.dtype == np.dtype(dt) and d.attrs["trial"] == trial
+        assert np.array_equal(d[...], data)
+        for _ in range(6):
+            key = tuple(slice(*sorted(rs.randint(0, s + 1, size=2))) for s in shape)
+            assert np.array_equal(d[key], data[key]), (trial, key)
+        i = tuple(int(rs.randint(0, s)) for s in shape)
+        assert d[i] == data[i]
