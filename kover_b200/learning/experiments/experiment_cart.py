@@ -12,7 +12,7 @@ from math import exp, log as ln, pi
 import numpy as np
 from scipy.special import comb
 
-from ..learners.cart import DecisionTreeClassifier, _prune_tree
+from ..learners.cart import DecisionTreeClassifier, _prune_tree, _to_leaf
 
 
 def _tiebreaker(best_score_idx, rule_kmer_occurrences):
@@ -117,28 +117,66 @@ def _bound(train_predictions, train_answers, train_example_idx, model, delta, ma
     return 1.0 - exp((-1.0 / (m - Z_card - r)) * exponent)
 
 
+def _truncate_tree(tree, max_depth, min_samples_split):
+    """The tree ``DecisionTreeClassifier(max_depth, min_samples_split)`` grows, derived from one grown deeper and / or
+    with a smaller ``min_samples_split`` on the same examples: the breadth-first growth (cart.py:260-339) splits a
+    node from its own examples only, so the shallower tree IS the deeper one cut at ``max_depth`` and below the nodes
+    that are too small to split.  A hyper-parameter grid over (max_depth, min_samples_split) therefore needs ONE
+    growth per (criterion, class importances, training set) instead of one per combination."""
+    clone = deepcopy(tree)
+    min_split = max(int(min_samples_split), 2)
+    pending = [clone]
+    while pending:
+        node = pending.pop()
+        if node.is_leaf:
+            continue
+        if node.depth >= max_depth or node.n_examples < min_split:
+            _to_leaf(node)
+        else:
+            pending.extend((node.left_child, node.right_child))
+    return clone
+
+
+def _grown_trees(grown, kind, hps, grow):
+    """Trees of ``grow(max_depth, min_samples_split)`` for ``hps``.  ``grown`` (or None): {"max_depth": the largest
+    depth of the grid, "min_samples_split": its smallest value, "trees": {}} -- the trees are then grown once at
+    those values per (kind, criterion, class importances) and cut down to ``hps`` (_truncate_tree)."""
+    if grown is None:
+        return grow(hps["max_depth"], hps["min_samples_split"])
+    key = (kind, hps["criterion"], tuple(sorted(hps["class_importance"].items())))
+    if key not in grown["trees"]:
+        grown["trees"][key] = grow(grown["max_depth"], grown["min_samples_split"])
+    return [_truncate_tree(t, hps["max_depth"], hps["min_samples_split"]) for t in grown["trees"][key]]
+
+
 def learn_pruned_tree_bound(rule_classifications, rules, example_labels, train_genome_idx, n_classes, hps, delta,
-                            max_genome_size, rule_blacklist):
+                            max_genome_size, rule_blacklist, grown=None):
     """``_learn_pruned_tree_bound`` (:208-294): grow the master tree on the training set (split scans on the device),
     prune it by minimal cost-complexity and keep the most pruned tree with the smallest bound.
+    grown: see _grown_trees (one growth for all the (max_depth, min_samples_split) of a grid).
     -> (hps with "pruning_alpha", min bound, tree, [(alpha, bound)] for the whole pruning sequence)."""
     example_labels = np.asarray(example_labels)
     train_genome_idx = np.asarray(train_genome_idx)
     hps = dict(hps)
-    master_predictor = DecisionTreeClassifier(criterion=hps["criterion"], max_depth=hps["max_depth"],
-                                              min_samples_split=hps["min_samples_split"],
-                                              class_importance=hps["class_importance"])
-    tiebreaker = OccurrenceTiebreaker(rule_classifications, train_genome_idx)
-    master_predictor.fit(rules=rules, rule_classifications=rule_classifications,
-                         example_idx={c: train_genome_idx[example_labels[train_genome_idx] == c]
-                                      for c in range(n_classes)},
-                         rule_blacklist=rule_blacklist, tiebreaker=tiebreaker,
-                         level_callback=None, split_callback=_split_callback)
-    tiebreaker.release()
+
+    def grow(max_depth, min_samples_split):
+        master_predictor = DecisionTreeClassifier(criterion=hps["criterion"], max_depth=max_depth,
+                                                  min_samples_split=min_samples_split,
+                                                  class_importance=hps["class_importance"])
+        tiebreaker = OccurrenceTiebreaker(rule_classifications, train_genome_idx)
+        master_predictor.fit(rules=rules, rule_classifications=rule_classifications,
+                             example_idx={c: train_genome_idx[example_labels[train_genome_idx] == c]
+                                          for c in range(n_classes)},
+                             rule_blacklist=rule_blacklist, tiebreaker=tiebreaker,
+                             level_callback=None, split_callback=_split_callback)
+        tiebreaker.release()
+        return [master_predictor.decision_tree]
+
+    master_tree = _grown_trees(grown, "bound", hps, grow)[0]
     min_score, min_score_tree = np.inf, None
     train_answers = example_labels[train_genome_idx]
     sequence = []
-    for alpha, tree in zip(*_prune_tree(master_predictor.decision_tree)):
+    for alpha, tree in zip(*_prune_tree(master_tree)):
         train_predictions = _predictions(tree, rule_classifications, train_genome_idx, [])[0]
         bound_value = _bound(train_predictions=train_predictions, train_answers=train_answers,
                              train_example_idx=train_genome_idx, model=tree, delta=delta,
@@ -178,12 +216,13 @@ class _AlphaIntervals(object):
 
 
 def learn_pruned_tree_cv(rule_classifications, rules, example_labels, train_genome_idx, folds, n_classes, hps,
-                         rule_blacklist):
+                         rule_blacklist, grown=None):
     """``_learn_pruned_tree_cv`` (:297-436): cost-complexity pruning with the pruning parameter chosen by k-fold
     cross-validation (Breiman et al. 1984, section 3.4).  folds: [(train_genome_idx, test_genome_idx)] in the
     reference's fold order.  The fold trees and the master tree are grown in LOCK-STEP over the resident matrix
     (learners.cart.fit_many: at every depth the nodes of all the trees share matrix passes); their k-mer
     occurrence tables (the tiebreaker's input) stay on the device, where the tiebreaker is applied.
+    grown: see _grown_trees (one growth for all the (max_depth, min_samples_split) of a grid).
     -> (hps with "pruning_alpha", cross-validation score, pruned master tree)."""
     from math import sqrt
 
@@ -194,29 +233,31 @@ def learn_pruned_tree_cv(rule_classifications, rules, example_labels, train_geno
     folds = [(np.asarray(tr), np.asarray(te)) for tr, te in folds]
     hps = dict(hps)
 
-    def new_tree():
-        return DecisionTreeClassifier(criterion=hps["criterion"], max_depth=hps["max_depth"],
-                                      min_samples_split=hps["min_samples_split"],
-                                      class_importance=hps["class_importance"])
-
     training_sets = [tr for tr, _ in folds] + [train_genome_idx]
-    learners, fit_args, tiebreakers = [], [], []
-    for i, tr in enumerate(training_sets):
-        # the tiebreaker's table is sum_rows(train) (:345, :364): kept on the device when the matrix lives there
-        tiebreakers.append(OccurrenceTiebreaker(rule_classifications, tr))
-        learners.append(new_tree())
-        fit_args.append(dict(rules=rules, example_idx={c: tr[example_labels[tr] == c] for c in range(n_classes)},
-                             rule_blacklist=rule_blacklist, tiebreaker=tiebreakers[-1], level_callback=None,
-                             split_callback=_split_callback if i == len(folds) else None))
-    fit_many(learners, fit_args, rule_classifications)
-    for tb in tiebreakers:
-        tb.release()
-    fold_predictors, master_predictor = learners[:-1], learners[-1]
 
-    master_alphas, master_pruned_trees = _prune_tree(master_predictor.decision_tree)
+    def grow(max_depth, min_samples_split):
+        learners, fit_args, tiebreakers = [], [], []
+        for i, tr in enumerate(training_sets):
+            # the tiebreaker's table is sum_rows(train) (:345, :364): kept on the device when the matrix lives there
+            tiebreakers.append(OccurrenceTiebreaker(rule_classifications, tr))
+            learners.append(DecisionTreeClassifier(criterion=hps["criterion"], max_depth=max_depth,
+                                                   min_samples_split=min_samples_split,
+                                                   class_importance=hps["class_importance"]))
+            fit_args.append(dict(rules=rules, example_idx={c: tr[example_labels[tr] == c] for c in range(n_classes)},
+                                 rule_blacklist=rule_blacklist, tiebreaker=tiebreakers[-1], level_callback=None,
+                                 split_callback=_split_callback if i == len(folds) else None))
+        fit_many(learners, fit_args, rule_classifications)
+        for tb in tiebreakers:
+            tb.release()
+        return [learner.decision_tree for learner in learners]
+
+    trees_grown = _grown_trees(grown, "cv", hps, grow)
+    fold_trees, master_tree = trees_grown[:-1], trees_grown[-1]
+
+    master_alphas, master_pruned_trees = _prune_tree(master_tree)
     fold_scores_by_alpha = []
-    for (_, fold_test_idx), predictor in zip(folds, fold_predictors):
-        alphas, trees = _prune_tree(predictor.decision_tree)
+    for (_, fold_test_idx), fold_tree in zip(folds, fold_trees):
+        alphas, trees = _prune_tree(fold_tree)
         answers = example_labels[fold_test_idx]
         by_alpha = _AlphaIntervals()
         for j, tree in enumerate(trees):
@@ -310,10 +351,13 @@ def learn_CART(dataset_file, split_name, criterion, max_depth, min_samples_split
         rule_classifications = KmerRuleClassifications(dataset.kmer_matrix, dataset.genome_count, devices=devices,
                                                        comm=comm)
 
+    # the trees of a (max_depth, min_samples_split) grid are cuts of ONE tree grown at the largest depth and the
+    # smallest min_samples_split (the reference grows every combination separately, :437-464)
+    grown = {"max_depth": int(max(max_depth)), "min_samples_split": int(min(min_samples_split)), "trees": {}}
     if parameter_selection == "bound":
         def hp_search(hps):
             return learn_pruned_tree_bound(rule_classifications, rules, example_labels, train_idx, n_classes, hps,
-                                           bound_delta, bound_max_genome_size, rule_blacklist)[:3]
+                                           bound_delta, bound_max_genome_size, rule_blacklist, grown=grown)[:3]
         search_type = "bound selection"
     elif parameter_selection == "cv":
         if len(split.folds) < 1:
@@ -322,7 +366,7 @@ def learn_CART(dataset_file, split_name, criterion, max_depth, min_samples_split
 
         def hp_search(hps):
             return learn_pruned_tree_cv(rule_classifications, rules, example_labels, train_idx, folds, n_classes, hps,
-                                        rule_blacklist)
+                                        rule_blacklist, grown=grown)
         search_type = "cross-validation"
     else:
         error_callback(ValueError("Unknown hyperparameter selection strategy specified."))

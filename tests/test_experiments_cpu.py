@@ -37,3 +37,37 @@ def test_drivers_against_the_reference(golden_dir, case, tmp_path):
     """learn_SCM / learn_CART reading a Kover-layout HDF5 file (hdf5_lite + the dataset adapter), with the matrix
     served by checker-backed shards: the host side of the drivers against the real reference's drivers."""
     check_driver_case(golden_dir, case, str(tmp_path), make_rc)
+
+
+def _tree_signature(node):
+    if node.rule is None:
+        return ("leaf", node.depth, tuple(sorted((int(c), len(v)) for c, v in node.class_examples_idx.items())))
+    return (int(node.rule.kmer_index), float(node.criterion_value), float(node.rule.importance),
+            tuple(int(x) for x in node.equivalent_rules_idx), _tree_signature(node.left_child),
+            _tree_signature(node.right_child))
+
+
+@pytest.mark.parametrize("mname,lname", [("M1", "M1_noisy"), ("M2", "M2_planted")])
+def test_truncated_tree_equals_directly_grown_tree(mname, lname):
+    """A (max_depth, min_samples_split) grid needs one growth: the tree grown at the largest depth / smallest
+    min_samples_split, cut at max_depth and below the nodes too small to split, IS the tree grown with those values."""
+    from kover_b200.learning.common.rules import LazyKmerRuleList
+    from kover_b200.learning.experiments.experiment_cart import _truncate_tree
+    from kover_b200.learning.learners.cart import DecisionTreeClassifier
+    X, P, n, chunks = cases.matrix(mname)
+    y = cases.labels(lname)
+    rc = make_rc(P, n, chunks)
+    rules = LazyKmerRuleList(["K%d" % i for i in range(P.shape[1])], np.arange(P.shape[1]))
+    train = cases.train_subset(n, 7)
+    ex = {0: train[y[train] == 0], 1: train[y[train] == 1]}
+
+    def grow(depth, mss):
+        t = DecisionTreeClassifier("gini", depth, mss, {0: 1.0, 1: 1.5})
+        t.fit(rules, rc, ex)
+        return t.decision_tree
+
+    big = grow(8, 2)
+    before = _tree_signature(big)
+    for depth, mss in ((1, 2), (3, 2), (3, 9), (5, 4), (8, 30), (8, 2)):
+        assert _tree_signature(_truncate_tree(big, depth, mss)) == _tree_signature(grow(depth, mss)), (depth, mss)
+    assert _tree_signature(big) == before           # the grown tree itself is left untouched
