@@ -550,6 +550,67 @@ def test_level_search_matches_per_node_search(devices, sorted_labels):
     rc.close()
 
 
+@pytest.mark.parametrize("seed", range(12))
+def test_randomized_trees_vs_checker(seed):
+    """Whole trees on random small / ragged shapes: level-batched split search + occurrence tiebreaker on the device,
+    alone and grown in lock-step with a second tree on other examples (fit_many), 1-3 shards, random blacklists,
+    depths and min_samples_split -- against the CPU checker's tree (one node at a time, host tiebreaker)."""
+    from kover_b200.learning.experiments import experiment_cart as cexp
+    rs = np.random.RandomState(2000 + seed)
+    n = int(rs.choice([30, 64, 65, 127, 200, 300]))
+    k = int(rs.choice([40, 511, 513, 1500, 4000]))
+    dens = rs.choice([0.05, 0.3, 0.5, 0.7, 0.95], size=k)
+    X = (rs.rand(n, k) < dens[None, :]).astype(np.uint8)
+    P = cases.pack64(X)
+    y = ((X[:, rs.randint(k)] ^ (rs.rand(n) < 0.15)) & 1).astype(np.uint8)
+    if rs.rand() < 0.5:
+        order = np.argsort(y, kind="stable")
+        X, y = X[order], y[order]
+        P = cases.pack64(X)
+    depth, mss = int(rs.choice([2, 4, 7])), int(rs.choice([2, 2, 5]))
+    imp = {0: 1.0, 1: float(rs.choice([1.0, 2.5]))}
+    blacklist = np.unique(rs.randint(0, k, size=rs.randint(0, max(1, k // 10))))
+    devices = [0] * int(rs.choice([1, 2, 3]))
+    orc = ko.OracleKmerRuleClassifications(P, n, fast=True)
+    rc = KmerRuleClassifications(P, n, devices=devices)
+    rules = rule_list(k)
+    subsets = [np.sort(rs.choice(n, size=max(4, int(n * f)), replace=False)) for f in (0.8, 0.6)]
+    examples = [{0: s_[y[s_] == 0], 1: s_[y[s_] == 1]} for s_ in subsets]
+    if any(len(e[0]) == 0 or len(e[1]) == 0 for e in examples):
+        pytest.skip("degenerate labels")
+    want = []
+    for s_, ex in zip(subsets, examples):
+        occ = orc.sum_rows(s_)
+        want.append(ko.cart_fit(orc, ex, "gini", depth, mss, imp, rule_blacklist=list(blacklist),
+                                tiebreaker=lambda idx, occ=occ: ko.cart_tiebreaker(idx, occ)))
+
+    def same(a, b):
+        assert (a.rule is None) == b.is_leaf
+        assert {int(c): len(v) for c, v in a.class_examples_idx.items()} == {int(c): len(v) for c, v in b.class_examples_idx.items()}
+        if a.rule is not None:
+            assert int(a.rule_idx) == int(b.rule_idx) and float(a.criterion_value) == float(b.criterion_value)
+            assert np.array_equal(np.asarray(a.equivalent_rules_idx), np.asarray(b.equivalent_rules_idx))
+            same(a.left_child, b.left_child)
+            same(a.right_child, b.right_child)
+
+    # alone
+    tb = cexp.OccurrenceTiebreaker(rc, subsets[0])
+    t = kcart.DecisionTreeClassifier("gini", depth, mss, imp)
+    t.fit(rules, rc, examples[0], rule_blacklist=list(blacklist), tiebreaker=tb)
+    tb.release()
+    same(t.decision_tree, want[0])
+    # two trees in lock-step, each with its own occurrence table
+    tbs = [cexp.OccurrenceTiebreaker(rc, s_) for s_ in subsets]
+    learners = [kcart.DecisionTreeClassifier("gini", depth, mss, imp) for _ in subsets]
+    kcart.fit_many(learners, [dict(rules=rules, example_idx=ex, rule_blacklist=list(blacklist), tiebreaker=b_)
+                              for ex, b_ in zip(examples, tbs)], rc)
+    for b_ in tbs:
+        b_.release()
+    for learner, w in zip(learners, want):
+        same(learner.decision_tree, w)
+    rc.close()
+
+
 @pytest.mark.parametrize("devices", [[0], [0, 0, 0]], ids=["1shard", "3shards"])
 def test_device_occurrence_tiebreaker(devices):
     """The reference's CART tiebreaker (experiment_cart.py:82-94: among the best splits keep the k-mers that occur in
