@@ -1725,6 +1725,7 @@ extern "C" int kv_get_info(kv_shard *s, kv_shard_info *o) {
 static int ensure_upload_ring(kv_shard *s) {
     if (s->h_up[0]) return KV_OK;
     s->h_up_bytes = (size_t)32 << 20;
+    if (const char *v = getenv("KOVER_B200_UPLOAD_SLOT_MB")) s->h_up_bytes = (size_t)std::max(1, atoi(v)) << 20;
     for (int i = 0; i < 2; ++i) {
         CU(cudaMallocHost(&s->h_up[i], s->h_up_bytes));
         CU(cudaEventCreateWithFlags(&s->ev_up[i], cudaEventDisableTiming));
@@ -1745,7 +1746,8 @@ static void stage_rows(char *pin, const char *src, long long n_rows, size_t row_
         }
     };
     const unsigned hw = std::thread::hardware_concurrency();
-    const int n_threads = total < ((size_t)4 << 20) ? 1 : (int)std::max(1u, std::min(hw ? hw : 1u, 6u));
+    static const unsigned max_threads = getenv("KOVER_B200_UPLOAD_THREADS") ? (unsigned)atoi(getenv("KOVER_B200_UPLOAD_THREADS")) : 6u;
+    const int n_threads = total < ((size_t)4 << 20) ? 1 : (int)std::max(1u, std::min(hw ? hw : 1u, std::max(1u, max_threads)));
     if (n_threads == 1) {
         copy_range(0, total);
         return;
