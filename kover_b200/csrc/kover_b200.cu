@@ -3695,7 +3695,6 @@ extern "C" int kv_gini_level(kv_shard *s, int64_t n_nodes, const uint64_t *class
             }
         }
         CU(cudaMemcpyAsync((void *)h_hdr, d_min, hdr_bytes, cudaMemcpyDeviceToHost, s->stream));
-        KV_TRY(ensure_pinned(s, count_batch_stride(W) + hdr_bytes + (size_t)per * 8));
         unsigned int *h_occmax = (unsigned int *)((char *)s->h_pin + count_batch_stride(W) + hdr_bytes);
         CU(cudaMemcpyAsync(h_occmax, d_occmax, (size_t)per * 4, cudaMemcpyDeviceToHost, s->stream));
         CU(stream_sync_spin(s->stream));
