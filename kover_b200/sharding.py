@@ -370,7 +370,7 @@ class ShardGroup(object):
 
     # ------------------------------------------------------------------ occurrence tables (CART tiebreaker on the device)
     def occurrence_table_supported(self):
-        return self.comm is None and all(hasattr(s, "occ_table_set") for s in self.shards)
+        return all(hasattr(s, "occ_table_set") for s in self.shards) and (self.comm is None or len(self.shards) == 1)
 
     def occurrence_table_set(self, table, mask):
         for s in self.shards:
@@ -388,8 +388,9 @@ class ShardGroup(object):
         if not hasattr(self.shards[0], "gini_level"):
             assert occ_tables is None
             return [self.gini_best_split(m, pr, tt, nn) for m, pr, tt, nn in zip(node_masks, altered_prior, n_total, n_node)]
+        if occ_tables is not None and self.comm is not None:
+            return self._gini_best_splits_ranks_tiebroken(node_masks, altered_prior, n_total, n_node, occ_tables)
         if occ_tables is not None:
-            assert self.comm is None
             per_shard = [s.gini_level(node_masks, altered_prior, n_total, n_node, occ_tables) for s in self.shards]
             if self._single:
                 return [(m, idx) for m, idx, _ in per_shard[0]]
@@ -428,6 +429,44 @@ class ShardGroup(object):
         if self.comm is None:
             return [(float(mins[i]), np.sort(local[i])) for i in range(n_nodes)]
         # one exchange for the whole level: every rank's per-node tie counts, then all the tie indices at once
+        sizes = np.array([len(a) for a in local], dtype=np.int64)
+        all_sizes = self.comm.allgather_concat(sizes).reshape(self.comm.world_size, n_nodes)
+        flat = self.comm.allgather_concat(np.concatenate(local) if n_nodes else np.zeros(0, dtype=np.int64))
+        starts = np.concatenate(([0], np.cumsum(all_sizes.reshape(-1))))
+        out = []
+        for i in range(n_nodes):
+            parts = [flat[starts[r * n_nodes + i]:starts[r * n_nodes + i + 1]] for r in range(self.comm.world_size)]
+            out.append((float(mins[i]), np.sort(np.concatenate(parts))))
+        return out
+
+    def _gini_best_splits_ranks_tiebroken(self, node_masks, altered_prior, n_total, n_node, occ_tables):
+        """One process per GPU, occurrence tiebreaker on the device: every rank reports, per node, its minimum, the
+        largest occurrence among ITS ties and the ties that survive relative to that; two small reductions find the
+        global minimum and the global largest occurrence, the ranks whose survivors stand send them in one exchange
+        for the whole level -- the millions of ties of small nodes never cross NVLink."""
+        shard = self.shards[0]
+        res = shard.gini_level(node_masks, altered_prior, n_total, n_node, occ_tables)
+        n_nodes = len(res)
+        local_min = np.array([r[0] for r in res], dtype=np.float64)
+        mins = self.comm.allreduce_min(local_min)
+        holder = (local_min == mins) & (mins != np.inf)
+        local_max = np.array([float(r[2]) if h and occ_tables[i] >= 0 else 0.0
+                              for i, (r, h) in enumerate(zip(res, holder))], dtype=np.float64)
+        g = self.comm.allreduce_max(local_max)
+        local = []
+        for i in range(n_nodes):
+            if not holder[i]:
+                local.append(np.zeros(0, dtype=np.int64))
+                continue
+            idx = np.array(res[i][1])
+            if occ_tables[i] >= 0 and local_max[i] != g[i]:
+                tol = 1e-8 + 1e-5 * abs(g[i])
+                if abs(local_max[i] - g[i]) <= tol:      # only possible from 100 000 occurrences up
+                    o = shard.occ_table_gather(int(occ_tables[i]), idx).astype(np.float64)
+                    idx = idx[np.abs(o - g[i]) <= tol]
+                else:
+                    idx = np.zeros(0, dtype=np.int64)
+            local.append(idx)
         sizes = np.array([len(a) for a in local], dtype=np.int64)
         all_sizes = self.comm.allgather_concat(sizes).reshape(self.comm.world_size, n_nodes)
         flat = self.comm.allgather_concat(np.concatenate(local) if n_nodes else np.zeros(0, dtype=np.int64))

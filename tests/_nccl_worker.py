@@ -96,6 +96,24 @@ def main():
                 walk(a.left_child, b.left_child)
                 walk(a.right_child, b.right_child)
         walk(t.decision_tree, root)
+        # the experiments' occurrence tiebreaker applied on every rank's device (one exchange per level)
+        from kover_b200.learning.experiments.experiment_cart import OccurrenceTiebreaker
+        occ = orc.sum_rows(train)
+        tb = OccurrenceTiebreaker(rc, train)
+        assert tb.device_occurrences is not None
+        t = kcart.DecisionTreeClassifier("gini", 5, 2, {0: 1.0, 1: 1.0})
+        t.fit(rules, rc, ex, tiebreaker=tb)
+        tb.release()
+        root = ko.cart_fit(orc, ex, "gini", 5, 2, {0: 1.0, 1: 1.0}, tiebreaker=lambda idx: ko.cart_tiebreaker(idx, occ))
+
+        def walk_eq(a, b):
+            assert (a.rule is None) == b.is_leaf
+            if a.rule is not None:
+                assert int(a.rule_idx) == int(b.rule_idx)
+                assert np.array_equal(np.asarray(a.equivalent_rules_idx), np.asarray(b.equivalent_rules_idx))
+                walk_eq(a.left_child, b.left_child)
+                walk_eq(a.right_child, b.right_child)
+        walk_eq(t.decision_tree, root)
         stats = dict(rc._group.exchange_stats)
         rc.close()
     comm.barrier()
