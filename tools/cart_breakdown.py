@@ -14,11 +14,12 @@ rc = KmerRuleClassifications(Meta(), n, shard_group=ShardGroup([sh], n, k))
 y = synthetic_labels(72, n); train = train_split(72, n)
 ex = {0: train[y[train]==0], 1: train[y[train]==1]}
 rules = LazyKmerRuleList(np.arange(k), np.arange(k))
-orig = rc.gini_best_split
+orig = rc.gini_best_split            # (per-node timing: the level-batched search is switched off for this breakdown)
 log = []
 def timed(*a, **kw):
     t0=time.perf_counter(); r = orig(*a, **kw); log.append((time.perf_counter()-t0, len(r[1]), sum(len(v) for v in a[0].values()))); return r
 rc.gini_best_split = timed
+rc.gini_best_splits = lambda nodes, pri, tot, bl=(), tie_tables=None: [timed(e, pri, tot, bl) for e in nodes]
 t = DecisionTreeClassifier("gini", 5, 2, {0:1.0,1:1.0})
 t0=time.perf_counter(); t.fit(rules, rc, ex); dt=time.perf_counter()-t0
 print("fit %.1f ms, %d split nodes" % (dt*1e3, len(t.decision_tree.rules)))
