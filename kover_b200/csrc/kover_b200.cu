@@ -880,7 +880,11 @@ __device__ __noinline__ void rescore_straddle(unsigned long long *blockmax, long
 template <int H>
 __device__ __forceinline__ void rescore_half(const RescoreMultiParams &P, int j, const RescoreLane &L, const double (&u)[8],
                                              unsigned long long (*s_red)[2][8]) {
-    const double m = fmax(fmax(fmax(u[0], u[1]), fmax(u[2], u[3])), fmax(fmax(u[4], u[5]), fmax(u[6], u[7])));
+    // (utilities are never NaN: a plain compare-and-select maximum, without fmax's NaN handling)
+    const double m01 = u[0] > u[1] ? u[0] : u[1], m23 = u[2] > u[3] ? u[2] : u[3];
+    const double m45 = u[4] > u[5] ? u[4] : u[5], m67 = u[6] > u[7] ? u[6] : u[7];
+    const double m03 = m01 > m23 ? m01 : m23, m47 = m45 > m67 ? m45 : m67;
+    const double m = m03 > m47 ? m03 : m47;
     const unsigned long long seg = warp_max_enc(enc_f64(m));
     if (L.lane < L.n_seg) P.segmax[j][H * L.seg_half + L.seg_idx + L.lane] = seg;
     if (L.lane == 0) s_red[j][H][L.warp] = seg;
