@@ -333,7 +333,10 @@ __device__ __forceinline__ void accum_word(const unsigned char *p, uint64_t a, u
     }
 }
 
-template <int EPI, int CW, int R, int S, int MINB>
+// GREC = true: the row records stay in global memory (read through L1) instead of being staged in shared memory --
+// the fallback for masks with more active packed rows than fit beside the ring (~5 000 rows = 320 000 genomes); the
+// reference has no such limit (rules.py:243-262 walks any number of rows).
+template <int EPI, int CW, int R, int S, int MINB, bool GREC = false>
 __global__ void __launch_bounds__((CW + 1) * 32, MINB) k_scan_tma(const Scan2Params P) {
     extern __shared__ __align__(128) unsigned char smem_tma[];
     constexpr int ROW_BYTES = CW * 32 * 16;
@@ -342,21 +345,26 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) k_scan_tma(const Scan2Par
     const int n_act = P.n_act;
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_tma);
     uint64_t *empty = full + S;
-    uint64_t *s_m0 = empty + S;
-    uint64_t *s_m1 = s_m0 + n_act;
-    uint32_t *s_row = reinterpret_cast<uint32_t *>(s_m1 + n_act);
-    unsigned char *ring = smem_tma + ((size_t)(2 * S) * 8 + (size_t)n_act * 20 + 127) / 128 * 128;
-    if (P.inline_rec) {
+    uint64_t *sw_m0 = empty + S;
+    uint64_t *sw_m1 = sw_m0 + n_act;
+    uint32_t *sw_row = reinterpret_cast<uint32_t *>(sw_m1 + n_act);
+    const uint64_t *s_m0 = GREC ? P.rec_m0 : sw_m0;
+    const uint64_t *s_m1 = GREC ? P.rec_m1 : sw_m1;
+    const uint32_t *s_row = GREC ? P.rec_row : sw_row;
+    unsigned char *ring = smem_tma + ((size_t)(2 * S) * 8 + (GREC ? 0 : (size_t)n_act * 20) + 127) / 128 * 128;
+    if (GREC) {
+        // nothing to stage
+    } else if (P.inline_rec) {
         for (int i = threadIdx.x; i < n_act; i += blockDim.x) {
-            s_m0[i] = P.inl_m0[i];
-            s_m1[i] = P.inl_m1[i];
-            s_row[i] = P.inl_row[i];
+            sw_m0[i] = P.inl_m0[i];
+            sw_m1[i] = P.inl_m1[i];
+            sw_row[i] = P.inl_row[i];
         }
     } else {
         for (int i = threadIdx.x; i < n_act; i += blockDim.x) {
-            s_m0[i] = P.rec_m0[i];
-            s_m1[i] = P.rec_m1[i];
-            s_row[i] = P.rec_row[i];
+            sw_m0[i] = P.rec_m0[i];
+            sw_m1[i] = P.rec_m1[i];
+            sw_row[i] = P.rec_row[i];
         }
     }
     if (threadIdx.x == 0) {
@@ -1566,6 +1574,7 @@ struct kv_shard {
     GiniParams gini;
 
     DevBuf d_qmisc, d_qseg;                   // block tables / segment maxima of the jobs of one queue batch
+    long long misc_n_blocks = -1, qmisc_n_blocks = -1;   // block count d_misc / d_qmisc are currently laid out for
     DevBuf d_level;                           // kv_gini_level: per-node minima, counters, tie slots, segment minima
     std::vector<uint32_t *> occ_tables;       // kv_occ_table_set: k-mer occurrence counts of a training set, [ld] each
     int64_t *h_level = nullptr;               // pinned arena: the tie lists of the last kv_gini_level, node after node
@@ -1987,21 +1996,29 @@ static void fill_scan2(kv_shard *s, Scan2Params &P, int n_act) {
     X(5, 16, 4, 4, 1)
 static constexpr int kNumScanVariants = 6;
 
-template <int EPI, int CW, int R, int S, int MINB>
+static constexpr size_t kSmemLimit = 227 * 1024 - 2048;   // opt-in limit per CTA, minus static + driver-reserved shared memory
+
+template <int CW, int R, int S>
+static constexpr size_t scan_smem_bytes(size_t n_act_staged) {
+    return ((size_t)(2 * S) * 8 + n_act_staged * 20 + 127) / 128 * 128 + (size_t)S * R * CW * 512;
+}
+
+template <int EPI, int CW, int R, int S, int MINB, bool GREC = false>
 static int launch_scan_variant(kv_shard *s, const Scan2Params &P) {
-    const size_t smem = ((size_t)(2 * S) * 8 + (size_t)P.n_act * 20 + 127) / 128 * 128 + (size_t)S * R * CW * 512;
-    if (smem + 2048 > 227 * 1024)      // opt-in limit per CTA, minus static + driver-reserved shared memory
-        return fail(KV_E_INVALID, "too many active packed rows for one scan (shared-memory staging limit)");
+    const size_t smem = scan_smem_bytes<CW, R, S>(GREC ? 0 : (size_t)P.n_act);
+    if (smem > kSmemLimit)
+        return fail(KV_E_INVALID, "too many active packed rows for this scan variant (shared-memory staging limit)");
+    if (GREC && P.inline_rec) return fail(KV_E_INVALID, "global-record scan needs the records in device memory");
     static thread_local int attr_device = -1;
     static thread_local size_t attr_bytes = 0;
     if (attr_device != s->device || attr_bytes < smem) {   // per (instantiation, device)
-        CU(cudaFuncSetAttribute(k_scan_tma<EPI, CW, R, S, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(cudaFuncSetAttribute(k_scan_tma<EPI, CW, R, S, MINB, GREC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_device = s->device;
         attr_bytes = smem;
     }
     const long long n_tiles = s->ld / (CW * 64);
     const int grid = (int)std::max(1ll, std::min<long long>((long long)s->sm_count * MINB, n_tiles));
-    k_scan_tma<EPI, CW, R, S, MINB><<<grid, (CW + 1) * 32, smem, s->stream>>>(P);
+    k_scan_tma<EPI, CW, R, S, MINB, GREC><<<grid, (CW + 1) * 32, smem, s->stream>>>(P);
     return KV_OK;
 }
 
@@ -2011,9 +2028,13 @@ static int launch_scan(kv_shard *s, const Scan2Params &P, int n_both) {
     // within 1 % of the best variant for label-sorted masks and the best when both masks hit every
     // row (profiles/README.md).  With more than ~1500 active packed rows the mask staging no longer fits
     // beside that ring: variant 5 (128 KB ring).
+    // Beyond what variant 5 can stage (~4 900 active rows) the records stay in global memory: variant 6 = variant 1's
+    // ring with GREC (no row limit; KOVER_B200_SCAN_VARIANT=6 forces it for tests).
     (void)n_both;
     int v = s->scan_variant;
-    if (v < 0 || v >= kNumScanVariants) v = ((size_t)P.n_act * 20 > 30 * 1024) ? 5 : 1;
+    if (v == 6 && P.inline_rec) v = -1;               // forced GREC needs device-resident records (n_act > 64)
+    if (v < 0 || v > kNumScanVariants) v = ((size_t)P.n_act * 20 > 30 * 1024) ? 5 : 1;
+    if (v == 5 && scan_smem_bytes<16, 4, 4>((size_t)P.n_act) > kSmemLimit) v = 6;
     CU(cudaEventRecord(s->ev0, s->stream));
     int rc = KV_OK;
     switch (v) {
@@ -2021,6 +2042,7 @@ static int launch_scan(kv_shard *s, const Scan2Params &P, int n_both) {
     case ID: rc = launch_scan_variant<EPI, CW_, R_, S_, MINB_>(s, P); break;
         KV_SCAN_VARIANTS(KV_CASE)
 #undef KV_CASE
+        case 6: rc = launch_scan_variant<EPI, 16, 8, 3, 1, true>(s, P); break;
         default: return fail(KV_E_INVALID, "unknown scan variant");
     }
     KV_TRY(rc);
@@ -2271,7 +2293,25 @@ static size_t count_pin_bytes(long long W, int n_masks) {
 static int count_masks_async(kv_shard *s, int n_masks, const uint64_t *const *masks, uint32_t *const *dst, char *pin) {
     const long long W = s->W;
     const int per = max_masks_per_pass(W);
-    if (per < 2) return fail(KV_E_INVALID, "too many packed rows for a multi-mask pass (shared-memory staging limit)");
+    if (per < 2) {
+        // More packed rows than the [row][mask] staging of k_count_tma can hold (W > ~7 800 = 500 000 genomes): two
+        // masks per pass through the two-mask scan, whose records can stay in global memory (no row limit).  Rare
+        // and huge, so every pass is synchronised (the pinned record buffer is reused).
+        (void)pin;
+        for (int m0 = 0; m0 < n_masks; m0 += 2) {
+            CU(cudaStreamSynchronize(s->stream));
+            int n_act, n_both;
+            const bool two = m0 + 1 < n_masks;
+            KV_TRY(push_records2(s, masks[m0], two ? masks[m0 + 1] : nullptr, n_act, n_both));
+            Scan2Params P;
+            fill_scan2(s, P, n_act);
+            P.cnt0 = dst[m0];
+            P.cnt1 = two ? dst[m0 + 1] : nullptr;
+            KV_TRY(launch_scan<EPI_COUNTS>(s, P, n_both));
+        }
+        CU(cudaStreamSynchronize(s->stream));
+        return KV_OK;
+    }
     KV_TRY(ensure(s->d_rec, count_pin_bytes(W, n_masks)));
     CU(cudaEventRecord(s->ev0, s->stream));
     size_t off = 0;
@@ -2470,7 +2510,13 @@ static int scm_scan_async(kv_shard *s, const uint64_t *pos_mask, const uint64_t 
     MiscLayout L0 = misc_layout(nullptr, n_blocks);
     KV_TRY(ensure(s->d_misc, L0.bytes));
     MiscLayout L = misc_layout(s->d_misc.p, n_blocks);
-    // L.blockmax is all-zero here: zeroed at allocation and re-zeroed by whoever consumed it last
+    // L.blockmax is all-zero here: zeroed at allocation and re-zeroed by whoever consumed it last -- as long as the
+    // layout stays the same.  Another block count (another util_block_size) moves the accumulators over what used to
+    // be block maxima / tolerances: start from a clean buffer.
+    if (s->misc_n_blocks != n_blocks) {
+        CU(cudaMemsetAsync(s->d_misc.p, 0, s->d_misc.bytes, s->stream));
+        s->misc_n_blocks = n_blocks;
+    }
     if (s->reuse_armed) {
         // kv_scm_reuse_counts: same masks as the previous scan (possibly with swapped roles) -> rescore only
         s->reuse_armed = false;
@@ -2822,6 +2868,10 @@ static int queue_score_group(kv_shard *s, const uint32_t *cnt_a, const uint32_t 
     const size_t misc_stride = (L0.bytes + 255) / 256 * 256, seg_stride = (size_t)(s->ld / 64) * 2 * 8;
     KV_TRY(ensure(s->d_qmisc, misc_stride * QUEUE_BATCH));
     KV_TRY(ensure(s->d_qseg, seg_stride * QUEUE_BATCH));
+    if (s->qmisc_n_blocks != n_blocks) {              // (see scm_scan_async: the accumulators must start zeroed)
+        CU(cudaMemsetAsync(s->d_qmisc.p, 0, s->d_qmisc.bytes, s->stream));
+        s->qmisc_n_blocks = n_blocks;
+    }
     const long long n_seg = (s->n_cols + 63) / 64;
     const unsigned grid_ties = (unsigned)std::max<long long>(1, std::min<long long>((n_seg + 255) / 256, (long long)s->sm_count * 4));
     for (int b0 = 0; b0 < n; b0 += QUEUE_BATCH) {
@@ -3027,8 +3077,7 @@ extern "C" int kv_scm_queue_packets(kv_shard *s, int64_t n_jobs, const uint64_t 
         return fail(KV_E_INVALID, "kv_scm_queue_packets: null pointer");
     if (n_jobs <= 0 || capacity < 0) return fail(KV_E_INVALID, "kv_scm_queue_packets: bad job count / capacity");
     if (reuse[0] != 0) return fail(KV_E_INVALID, "kv_scm_queue_packets: the first job must open a group (reuse = 0)");
-    const int per = max_masks_per_pass(s->W);
-    if (per < 2) return fail(KV_E_INVALID, "kv_scm_queue_packets: too many packed rows for a multi-mask pass");
+    const int per = std::max(2, max_masks_per_pass(s->W));      // (beyond the staging limit: two-mask passes)
     const int64_t n_blocks = kv_scm_n_blocks(s->k_total, util_block_size);
     if (n_blocks <= 0) return fail(KV_E_INVALID, "kv_scm_queue_packets: util_block_size must be positive");
     const size_t bytes = (size_t)n_jobs * (size_t)kv_scm_packet_bytes(n_blocks, capacity);
@@ -3619,8 +3668,7 @@ extern "C" int kv_gini_level(kv_shard *s, int64_t n_nodes, const uint64_t *class
     s->scm_valid = s->gini_valid = false;
     s->level_span.clear();
     s->h_level_used = 0;
-    const int per = std::min(kLevelNodesPerPass, max_masks_per_pass(s->W) / 2);
-    if (per < 1) return fail(KV_E_INVALID, "kv_gini_level: too many packed rows for a multi-mask pass");
+    const int per = std::max(1, std::min(kLevelNodesPerPass, max_masks_per_pass(s->W) / 2));
     const long long W = s->W, n_seg_ld = s->ld / 64;
     KV_TRY(ensure_counts(s, 2 + 2 * per));
     // d_level: min enc [per] | counter [per] | ties [per][kLevelSlotIdx] | segmin [per][ld/64] | score tables [per][4096]

@@ -164,12 +164,14 @@ def learn_pruned_tree_bound(rule_classifications, rules, example_labels, train_g
                                                   min_samples_split=min_samples_split,
                                                   class_importance=hps["class_importance"])
         tiebreaker = OccurrenceTiebreaker(rule_classifications, train_genome_idx)
-        master_predictor.fit(rules=rules, rule_classifications=rule_classifications,
-                             example_idx={c: train_genome_idx[example_labels[train_genome_idx] == c]
-                                          for c in range(n_classes)},
-                             rule_blacklist=rule_blacklist, tiebreaker=tiebreaker,
-                             level_callback=None, split_callback=_split_callback)
-        tiebreaker.release()
+        try:                                 # the device occurrence table goes back even when the fit raises
+            master_predictor.fit(rules=rules, rule_classifications=rule_classifications,
+                                 example_idx={c: train_genome_idx[example_labels[train_genome_idx] == c]
+                                              for c in range(n_classes)},
+                                 rule_blacklist=rule_blacklist, tiebreaker=tiebreaker,
+                                 level_callback=None, split_callback=_split_callback)
+        finally:
+            tiebreaker.release()
         return [master_predictor.decision_tree]
 
     master_tree = _grown_trees(grown, "bound", hps, grow)[0]
@@ -237,18 +239,21 @@ def learn_pruned_tree_cv(rule_classifications, rules, example_labels, train_geno
 
     def grow(max_depth, min_samples_split):
         learners, fit_args, tiebreakers = [], [], []
-        for i, tr in enumerate(training_sets):
-            # the tiebreaker's table is sum_rows(train) (:345, :364): kept on the device when the matrix lives there
-            tiebreakers.append(OccurrenceTiebreaker(rule_classifications, tr))
-            learners.append(DecisionTreeClassifier(criterion=hps["criterion"], max_depth=max_depth,
-                                                   min_samples_split=min_samples_split,
-                                                   class_importance=hps["class_importance"]))
-            fit_args.append(dict(rules=rules, example_idx={c: tr[example_labels[tr] == c] for c in range(n_classes)},
-                                 rule_blacklist=rule_blacklist, tiebreaker=tiebreakers[-1], level_callback=None,
-                                 split_callback=_split_callback if i == len(folds) else None))
-        fit_many(learners, fit_args, rule_classifications)
-        for tb in tiebreakers:
-            tb.release()
+        try:                                 # the device occurrence tables go back even when a fit raises
+            for i, tr in enumerate(training_sets):
+                # the tiebreaker's table is sum_rows(train) (:345, :364): kept on the device when the matrix lives there
+                tiebreakers.append(OccurrenceTiebreaker(rule_classifications, tr))
+                learners.append(DecisionTreeClassifier(criterion=hps["criterion"], max_depth=max_depth,
+                                                       min_samples_split=min_samples_split,
+                                                       class_importance=hps["class_importance"]))
+                fit_args.append(dict(rules=rules,
+                                     example_idx={c: tr[example_labels[tr] == c] for c in range(n_classes)},
+                                     rule_blacklist=rule_blacklist, tiebreaker=tiebreakers[-1], level_callback=None,
+                                     split_callback=_split_callback if i == len(folds) else None))
+            fit_many(learners, fit_args, rule_classifications)
+        finally:
+            for tb in tiebreakers:
+                tb.release()
         return [learner.decision_tree for learner in learners]
 
     trees_grown = _grown_trees(grown, "cv", hps, grow)
@@ -334,11 +339,14 @@ def learn_CART(dataset_file, split_name, criterion, max_depth, min_samples_split
     rule_blacklist = _find_rule_blacklist(dataset, kmer_blacklist_file, warning_callback)
     criterion, max_depth = np.unique(criterion), np.unique(max_depth)
     min_samples_split = np.unique(min_samples_split)
-    # (np.unique cannot order dictionaries on Python 3; the distinct class-importance dicts keep their given order)
+    # np.unique(class_importance) (:545) sorts the distinct dictionaries with Python 2's dict ordering: by size, then
+    # by the value at the smallest key where they differ -- for dictionaries over the same classes that is the order
+    # of their sorted items.  The order decides which HP combination wins train_tree's first-wins ties.
     importances = []
     for ci in class_importance:
         if ci not in importances:
             importances.append(ci)
+    importances.sort(key=lambda ci: (len(ci), sorted(ci.items())))
 
     split = dataset.get_split(split_name)
     train_idx, test_idx = np.asarray(split.train_genome_idx[...]), np.asarray(split.test_genome_idx[...])

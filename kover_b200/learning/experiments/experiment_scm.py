@@ -170,8 +170,11 @@ def bound_selection(rule_classifications, rules, labels, train_example_idx, rule
             model = st["model_by_length"][best_score_idx]
             importances = st["rule_importances"][best_score_idx]
             equiv = st["equivalent_rules"][: best_score_idx + 1]
-        if (score < best_hp_score) or (score == best_hp_score and hp[2] < best_hp["max_rules"]) or \
-                (score == best_hp_score and hp[2] == best_hp["max_rules"]
+        # (the reference runs on Python 2, where `int < None` is False: while no HP has been selected yet a score
+        # equal to the initial 1.0 selects nothing -- reproduced by the `seen` guard instead of a TypeError)
+        seen = best_hp["max_rules"] is not None
+        if (score < best_hp_score) or (seen and score == best_hp_score and hp[2] < best_hp["max_rules"]) or \
+                (seen and score == best_hp_score and hp[2] == best_hp["max_rules"]
                  and abs(1.0 - hp[1]) < abs(1.0 - best_hp["p"])):              # :612-627
             best_hp["model_type"], best_hp["p"], best_hp["max_rules"] = hp
             best_hp_score, best_model, best_equiv_rules, best_rule_importances = score, model, equiv, importances
@@ -218,9 +221,10 @@ def cross_validation(rule_classifications, rules, labels, folds, model_types, p_
         per_hp[hp_mt_p] = score_by_model_length
         best_score_idx = np.argmin(score_by_model_length)
         score, hp = score_by_model_length[best_score_idx], (hp_mt_p[0], hp_mt_p[1], best_score_idx)
+        seen = best_hp["max_rules"] is not None           # Python 2's `int < None` is False (see bound_selection)
         if (not np.allclose(score, best_hp_score) and score < best_hp_score) or \
-                (np.allclose(score, best_hp_score) and hp[2] < best_hp["max_rules"]) or \
-                (np.allclose(score, best_hp_score) and hp[2] == best_hp["max_rules"]
+                (seen and np.allclose(score, best_hp_score) and hp[2] < best_hp["max_rules"]) or \
+                (seen and np.allclose(score, best_hp_score) and hp[2] == best_hp["max_rules"]
                  and not np.allclose(hp[1], best_hp["p"]) and abs(1.0 - hp[1]) < abs(1.0 - best_hp["p"])):   # :233-246
             best_hp["model_type"], best_hp["p"], best_hp["max_rules"] = hp
             best_hp_score = score

@@ -380,6 +380,29 @@ def gini_rule_score(rule_classifications, example_idx, altered_priors, n_total):
     return gini
 
 
+def cross_entropy(n_by_class, altered_priors, n_total, multiply_by_node_proba=False):
+    """cart.py:167-178"""
+    p_j_t = {c: 1.0 * altered_priors[c] * n_by_class[c] / n_total[c] for c in n_by_class.keys()}
+    p_t = sum(p_j_t.values())
+    with np.errstate(divide="ignore", invalid="ignore"):
+        p_j_given_t = {c: np.divide(p_j_t[c], p_t) for c in p_j_t.keys()}
+        div = -1.0 * sum([np.nan_to_num(p_j_given_t[c] * np.log(p_j_given_t[c])) for c in p_j_given_t.keys()])
+    return div * (p_t if multiply_by_node_proba else 1.0)
+
+
+def cross_entropy_rule_score(rule_classifications, example_idx, altered_priors, n_total):
+    """cart.py:180-207 (classes without examples in the node are left out, :197-198; no 100k blocking here)"""
+    n_kmers = rule_classifications.shape[1] // 2
+    left = {c: np.asarray(rule_classifications.sum_rows(example_idx[c])[:n_kmers], dtype=float)
+            for c in example_idx.keys() if example_idx[c].size}
+    right = {c: np.asarray(example_idx[c].shape[0] - left[c], dtype=float) for c in left.keys()}
+    score = cross_entropy(left, altered_priors, n_total, True)
+    score += cross_entropy(right, altered_priors, n_total, True)
+    score[sum(left.values()) == 0] = np.inf
+    score[sum(right.values()) == 0] = np.inf
+    return score
+
+
 def cart_tiebreaker(best_score_idx, rule_kmer_occurrences):
     """experiments/experiment_cart.py:82-94"""
     occ = rule_kmer_occurrences[best_score_idx]
@@ -425,10 +448,13 @@ class OracleTreeNode(object):
 
 def cart_fit(rule_classifications, example_idx, criterion="gini", max_depth=10, min_samples_split=2,
              class_importance=None, rule_blacklist=None, tiebreaker=None):
-    """cart.py:54-346 (Gini only: cross-entropy is unreachable from the CLI).
+    """cart.py:54-346, both criteria ("cross-entropy" is unreachable from the reference CLI, SURVEY section 5, and
+    its scores go through np.log, whose last bit depends on the libm / SIMD dispatch of the machine).
     Returns the root OracleTreeNode."""
-    if criterion != "gini":
-        raise ValueError("oracle implements the gini criterion only")
+    if criterion not in ("gini", "cross-entropy"):
+        raise ValueError("The supporting splitting criteria are: ['gini', 'cross-entropy'].")
+    rule_score = gini_rule_score if criterion == "gini" else cross_entropy_rule_score
+    node_impurity = gini_impurity if criterion == "gini" else cross_entropy
     if max_depth < 1:
         raise ValueError("The maximum tree depth must be greater than 1.")
     if min_samples_split < 2.0:
@@ -444,7 +470,7 @@ def cart_fit(rule_classifications, example_idx, criterion="gini", max_depth=10, 
 
     def find_best_split(node):                                        # cart.py:219-250
         ex = node.class_examples_idx
-        score = gini_rule_score(rule_classifications, ex, altered, n_total)
+        score = rule_score(rule_classifications, ex, altered, n_total)
         score[rule_blacklist] = np.inf                                # :231
         smin = min(score)                                             # builtin min, :234/:238
         if smin == np.inf:
@@ -457,7 +483,7 @@ def cart_fit(rule_classifications, example_idx, criterion="gini", max_depth=10, 
         right = {c: ex[c][preds[ex[c]] == 0] for c in ex.keys()}      # :248
         return sel, best, left, right
 
-    root = OracleTreeNode(0, example_idx, gini_impurity(n_total, altered, n_total))
+    root = OracleTreeNode(0, example_idx, node_impurity(n_total, altered, n_total))
     queue = deque([root])
     current_depth = -1
     while len(queue) > 0:                                             # cart.py:267-339
@@ -477,9 +503,9 @@ def cart_fit(rule_classifications, example_idx, criterion="gini", max_depth=10, 
         node.rule_idx = sel
         node.equivalent_rules_idx = equiv
         node.left_child = OracleTreeNode(node.depth + 1, left,
-                                         gini_impurity({c: len(v) for c, v in left.items()}, altered, n_total), node)
+                                         node_impurity({c: len(v) for c, v in left.items()}, altered, n_total), node)
         node.right_child = OracleTreeNode(node.depth + 1, right,
-                                          gini_impurity({c: len(v) for c, v in right.items()}, altered, n_total), node)
+                                          node_impurity({c: len(v) for c, v in right.items()}, altered, n_total), node)
         queue.append(node.left_child)
         queue.append(node.right_child)
     return root

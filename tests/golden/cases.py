@@ -204,6 +204,15 @@ CART_CASES = [
 ]
 
 
+CART_CE_CASES = [
+    # the cross-entropy criterion (cart.py:167-207); same fields as CART_CASES
+    ("cartce_appendix", "M2", "M2_planted", 4, 2, {0: 1.0, 1: 1.0}, "none", None),
+    ("cartce_noisy_occ", "M1", "M1_noisy", 3, 2, {0: 1.0, 1: 2.0}, "occurrence", 41),
+    ("cartce_3class", "M1", "M1_3class", 3, 5, {0: 1.0, 1: 2.0, 2: 0.5}, "occurrence", 42),
+    ("cartce_MD", "MD", "MD_planted", 4, 4, {0: 1.0, 1: 1.0}, "occurrence", 43),
+]
+
+
 EXPERIMENT_CASES = [
     # name, matrix, labels, train subset seed, p values, max_rules, max_equiv_rules, n_folds
     ("exp_M1", "M1", "M1_noisy", 41, [0.1, 1.0, 10.0], 4, 3, 3),

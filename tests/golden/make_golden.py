@@ -179,6 +179,45 @@ def gen_cart():
     # scores through `candidates == where(score == min)` at every node, which tree_json already holds)
 
 
+def gen_cart_ce():
+    """The cross-entropy criterion (cart.py:167-207): whole trees (criterion values, selected rules, the equivalent
+    rules = the tie set that survived the tiebreaker at every node) plus the raw score vector of every searched
+    node, captured where _find_best_split hands it to the builtin ``min`` (cart.py:234)."""
+    import builtins
+    for case in cases.CART_CE_CASES:
+        name, mname, lname, max_depth, mss, class_importance, tb, subset_seed = case
+        X, P, n, chunks = cases.matrix(mname)
+        y = cases.labels(lname)
+        k = P.shape[1]
+        rc = ref_rc(P, n, chunks)
+        rules = ref.rules.LazyKmerRuleList(["K%d" % i for i in range(k)], np.arange(k))
+        train = cases.train_subset(n, subset_seed)
+        example_idx = {c: train[y[train] == c] for c in sorted(class_importance.keys())}
+        tiebreaker = None
+        if tb == "occurrence":
+            occ = rc.sum_rows(train)
+            tiebreaker = lambda idx: idx[np.isclose(occ[idx], occ[idx].max())]
+        captured = []
+
+        def spy_min(*args, **kwargs):                 # module-level name: shadows the builtin inside cart.py only
+            if len(args) == 1 and isinstance(args[0], np.ndarray) and args[0].shape == (k,):
+                if not captured or captured[-1] is not args[0]:
+                    captured.append(args[0])
+            return builtins.min(*args, **kwargs)
+
+        def split_cb(node, equiv):
+            node.rule.equivalent_rules_idx = equiv
+
+        ref.cart.min = spy_min
+        try:
+            t = ref.cart.DecisionTreeClassifier("cross-entropy", max_depth, mss, class_importance)
+            t.fit(rules, rc, example_idx, rule_blacklist=[], tiebreaker=tiebreaker, split_callback=split_cb)
+        finally:
+            del ref.cart.min
+        save(name, tree_json=np.array(json.dumps(tree_to_dict(t.decision_tree))),
+             node_scores=np.array([np.array(c) for c in captured]))
+
+
 # ------------------------------------------------------------------ bound / CV model selection (north-star item 4)
 def gen_experiments():
     """experiment_scm.py's per-HP scoring (_bound_score_hp :401-566, _cv_score_hp :102-193) needs a KoverDataset
@@ -454,6 +493,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "cart_cv":
         gen_cart_cv()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "cart_ce":
+        gen_cart_ce()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "drivers":
         gen_drivers()
         sys.exit(0)
@@ -463,6 +505,7 @@ if __name__ == "__main__":
     gen_utility()
     gen_scm()
     gen_cart()
+    gen_cart_ce()
     gen_risk()
     gen_experiments()
     gen_cart_experiments()

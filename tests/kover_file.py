@@ -2,7 +2,7 @@
 package's minimal writer.  The risk tables come from the CPU checker (oracle/), so the helper needs no GPU."""
 import numpy as np
 
-from kover_b200.dataset.hdf5_lite_writer import Writer
+from hdf5_lite_writer import Writer
 from kover_b200.utils import _minimum_uint_size
 from oracle import kover_oracle as ko
 

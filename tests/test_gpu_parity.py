@@ -215,6 +215,31 @@ def test_best_utility_rules_vs_checker(seed, n, k, p, ubs, sorted_labels):
         rc.close()
 
 
+@pytest.mark.parametrize("devices", [[0], [0, 0]], ids=["1shard", "2shards"])
+def test_util_block_size_changes_between_calls(devices):
+    """Another util_block_size re-lays the block-maximum accumulators over what used to be block maxima / tolerances
+    of the previous call (round-2 regression: a stale raw double decoded as a small negative "maximum" and beat the
+    real, hugely negative maxima of a p = 999999 scan).  Grow, shrink and grow the block count on one shard."""
+    n, k, seed = 700, 20000, 9
+    P = synthetic_block(seed, n, 0, k)
+    y = synthetic_labels(seed, n, sorted_by_label=False)
+    pos, neg = np.where(y == 1)[0], np.where(y == 0)[0]
+    orc = ko.OracleKmerRuleClassifications(P, n, fast=True)
+    nc, pe = len(neg) - orc.sum_rows(neg), len(pos) - orc.sum_rows(pos)
+    rc = KmerRuleClassifications(P, n, devices=devices)
+    for p, ubs in ((1.0, 1000000), (999999.0, 3001), (0.5, 40000), (999999.0, 777), (999999.0, 1000000), (2.0, 100)):
+        wu, wi, wp, wn = ko.merge_utility_blocks(nc, pe, p, np.zeros(2 * k, dtype=bool), block_size=ubs)
+        bu, bi, bp, bn = rc.best_utility_rules(p, pos, neg, util_block_size=ubs)
+        assert bu == wu and np.array_equal(bi, np.asarray(wi, dtype=np.int64)), (p, ubs)
+        assert np.array_equal(bp, wp) and np.array_equal(bn, wn)
+        jobs = [(q, a, b) for a, b in ((pos, neg), (pos[::2], neg[1::2])) for q in (p, 0.25)]
+        for (q, a, b), got in zip(jobs, rc.best_utility_rules_grid(jobs, util_block_size=ubs)):
+            wu, wi, wp, wn = ko.merge_utility_blocks(len(b) - orc.sum_rows(b), len(a) - orc.sum_rows(a), q,
+                                                     np.zeros(2 * k, dtype=bool), block_size=ubs)
+            assert got[0] == wu and np.array_equal(got[1], np.asarray(wi, dtype=np.int64)), (q, ubs)
+    rc.close()
+
+
 def test_large_equivalent_rule_sets():
     """Tens of thousands of equivalent rules (duplicated k-mers, as on real genomes): the device-sorted path of
     both tie collectors, single- and multi-shard, against the checker."""

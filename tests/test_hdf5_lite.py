@@ -12,7 +12,7 @@ import pytest
 
 from kover_b200.dataset import hdf5_lite
 from kover_b200.dataset.ds import KoverDataset
-from kover_b200.dataset.hdf5_lite_writer import Writer
+from hdf5_lite_writer import Writer
 
 
 def test_reads_a_file_written_by_the_hdf5_library():
