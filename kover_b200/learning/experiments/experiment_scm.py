@@ -170,15 +170,30 @@ def bound_selection(rule_classifications, rules, labels, train_example_idx, rule
             model = st["model_by_length"][best_score_idx]
             importances = st["rule_importances"][best_score_idx]
             equiv = st["equivalent_rules"][: best_score_idx + 1]
-        # (the reference runs on Python 2, where `int < None` is False: while no HP has been selected yet a score
-        # equal to the initial 1.0 selects nothing -- reproduced by the `seen` guard instead of a TypeError)
-        seen = best_hp["max_rules"] is not None
-        if (score < best_hp_score) or (seen and score == best_hp_score and hp[2] < best_hp["max_rules"]) or \
-                (seen and score == best_hp_score and hp[2] == best_hp["max_rules"]
-                 and abs(1.0 - hp[1]) < abs(1.0 - best_hp["p"])):              # :612-627
+        if _bound_hp_is_better(score, hp, best_hp_score, best_hp):
             best_hp["model_type"], best_hp["p"], best_hp["max_rules"] = hp
             best_hp_score, best_model, best_equiv_rules, best_rule_importances = score, model, equiv, importances
     return best_hp_score, best_hp, best_model, best_rule_importances, best_equiv_rules, per_hp
+
+
+def _bound_hp_is_better(score, hp, best_hp_score, best_hp):
+    """The HP replacement rule of ``_bound_selection`` (:612-627): smaller bound, then fewer rules, then p closer to 1.
+    The reference runs on Python 2, where ``int < None`` is False and ``int == None`` is False: while no HP has been
+    selected yet (best_hp all None) a score EQUAL to the initial 1.0 selects nothing, and a later HP with a smaller
+    score is still picked up.  The ``seen`` guard reproduces that instead of Python 3's TypeError."""
+    seen = best_hp["max_rules"] is not None
+    return bool((score < best_hp_score) or (seen and score == best_hp_score and hp[2] < best_hp["max_rules"]) or
+                (seen and score == best_hp_score and hp[2] == best_hp["max_rules"]
+                 and abs(1.0 - hp[1]) < abs(1.0 - best_hp["p"])))
+
+
+def _cv_hp_is_better(score, hp, best_hp_score, best_hp):
+    """The HP replacement rule of ``_cross_validation`` (:233-246), with the same Python 2 ``None`` semantics."""
+    seen = best_hp["max_rules"] is not None
+    close = bool(np.allclose(score, best_hp_score))
+    return bool((not close and score < best_hp_score) or (seen and close and hp[2] < best_hp["max_rules"]) or
+                (seen and close and hp[2] == best_hp["max_rules"] and not np.allclose(hp[1], best_hp["p"])
+                 and abs(1.0 - hp[1]) < abs(1.0 - best_hp["p"])))
 
 
 def cross_validation(rule_classifications, rules, labels, folds, model_types, p_values, max_rules, rule_blacklist):
@@ -221,11 +236,7 @@ def cross_validation(rule_classifications, rules, labels, folds, model_types, p_
         per_hp[hp_mt_p] = score_by_model_length
         best_score_idx = np.argmin(score_by_model_length)
         score, hp = score_by_model_length[best_score_idx], (hp_mt_p[0], hp_mt_p[1], best_score_idx)
-        seen = best_hp["max_rules"] is not None           # Python 2's `int < None` is False (see bound_selection)
-        if (not np.allclose(score, best_hp_score) and score < best_hp_score) or \
-                (seen and np.allclose(score, best_hp_score) and hp[2] < best_hp["max_rules"]) or \
-                (seen and np.allclose(score, best_hp_score) and hp[2] == best_hp["max_rules"]
-                 and not np.allclose(hp[1], best_hp["p"]) and abs(1.0 - hp[1]) < abs(1.0 - best_hp["p"])):   # :233-246
+        if _cv_hp_is_better(score, hp, best_hp_score, best_hp):
             best_hp["model_type"], best_hp["p"], best_hp["max_rules"] = hp
             best_hp_score = score
     return best_hp_score, best_hp, per_hp

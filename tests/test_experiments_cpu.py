@@ -71,3 +71,19 @@ def test_truncated_tree_equals_directly_grown_tree(mname, lname):
     for depth, mss in ((1, 2), (3, 2), (3, 9), (5, 4), (8, 30), (8, 2)):
         assert _tree_signature(_truncate_tree(big, depth, mss)) == _tree_signature(grow(depth, mss)), (depth, mss)
     assert _tree_signature(big) == before           # the grown tree itself is left untouched
+
+
+def test_first_hp_scoring_exactly_one_selects_nothing_like_python2():
+    """the reference compares ``hp[2] < best_hp["max_rules"]`` while best_hp is still all None; Python 2
+    evaluates ``int < None`` as False and carries on (experiment_scm.py:233-246, 612-627), Python 3 raises.  A first
+    HP whose score equals the initial 1.0 must select nothing, and a later HP with a smaller score must win."""
+    from kover_b200.learning.experiments.experiment_scm import _bound_hp_is_better, _cv_hp_is_better
+    empty = {"model_type": None, "p": None, "max_rules": None}
+    for better in (_bound_hp_is_better, _cv_hp_is_better):
+        assert better(1.0, ("conjunction", 0.1, 3), 1.0, dict(empty)) is False
+        assert better(0.99, ("conjunction", 0.1, 3), 1.0, dict(empty)) is True
+        chosen = {"model_type": "conjunction", "p": 0.1, "max_rules": 3}
+        assert better(0.5, ("disjunction", 1.0, 2), 0.5, chosen) is True          # same score, fewer rules
+        assert better(0.5, ("disjunction", 1.0, 3), 0.5, chosen) is True          # same score and size, p closer to 1
+        assert better(0.5, ("disjunction", 10.0, 3), 0.5, chosen) is False
+        assert better(0.6, ("disjunction", 1.0, 1), 0.5, chosen) is False

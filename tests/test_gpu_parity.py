@@ -507,17 +507,21 @@ def tree_to_dict(node):
     return d
 
 
-def tree_equal(got, want, path="root"):
+def tree_equal(got, want, path="root", rtol=0.0):
+    """rtol = 0: bit-exact criterion values (Gini).  rtol > 0 only for the cross-entropy criterion (np.log)."""
     assert got["depth"] == want["depth"], path
     assert got["n_by_class"] == {int(c): v for c, v in want["n_by_class"].items()}, path
-    assert got["criterion_value"] == want["criterion_value"], path
+    if rtol:
+        assert abs(got["criterion_value"] - want["criterion_value"]) <= rtol * abs(want["criterion_value"]), path
+    else:
+        assert got["criterion_value"] == want["criterion_value"], path
     assert ("rule_idx" in got) == ("rule_idx" in want), path
     if "rule_idx" in want:
         assert got["rule_idx"] == want["rule_idx"], path
         assert got["equivalent_rules_idx"] == want["equivalent_rules_idx"], path
         assert got["importance"] == want["importance"], path
-        tree_equal(got["left"], want["left"], path + ".L")
-        tree_equal(got["right"], want["right"], path + ".R")
+        tree_equal(got["left"], want["left"], path + ".L", rtol)
+        tree_equal(got["right"], want["right"], path + ".R", rtol)
 
 
 @pytest.mark.parametrize("case", cases.CART_CASES, ids=[c[0] for c in cases.CART_CASES])
@@ -705,15 +709,61 @@ def test_gini_scores_vs_checker(n_classes):
     assert m == want.min() and np.array_equal(cand, np.where(want == want.min())[0])
 
 
-def test_cross_entropy_fit_matches_checker_counts():
-    # cross-entropy: device counts + the reference's numpy formula on the host (cart.py:167-207)
-    X, P, n, chunks = cases.matrix("M2")
-    y = cases.labels("M2_planted")
+@pytest.mark.parametrize("case", cases.CART_CE_CASES, ids=[c[0] for c in cases.CART_CE_CASES])
+@pytest.mark.parametrize("devices", [[0], [0, 0]], ids=["1shard", "2shards"])
+def test_cross_entropy_fit_golden(golden_dir, case, devices):
+    """a10 (cart.py:167-207): device counts (one multi-mask pass per node) + the reference's numpy formula on the
+    host.  Whole trees against the REAL reference's: selected rules, tie sets (equivalent rules), importances
+    identical; criterion values to 4 ulp (np.log's last bit depends on the host's libm / SIMD dispatch)."""
+    name, mname, lname, max_depth, mss, class_importance, tb, subset_seed = case
+    g = load(golden_dir, name)
+    want = json.loads(str(g["tree_json"]))
+    X, P, n, chunks = cases.matrix(mname)
+    y = cases.labels(lname)
     k = P.shape[1]
-    rc = KmerRuleClassifications(P, n, devices=[0])
-    t = kcart.DecisionTreeClassifier("cross-entropy", 3, 2, {0: 1.0, 1: 1.0})
-    t.fit(rule_list(k), rc, {0: np.where(y == 0)[0], 1: np.where(y == 1)[0]})
-    assert sorted(r.kmer_index for r in t.decision_tree.rules) == [3, 9, 20]
+    rc = KmerRuleClassifications(as_dataset(P, chunks), n, devices=devices)
+    train = cases.train_subset(n, subset_seed)
+    example_idx = {c: train[y[train] == c] for c in sorted(class_importance.keys())}
+    tiebreaker = None
+    if tb == "occurrence":
+        occ = rc.sum_rows(train)
+        tiebreaker = lambda idx: ko.cart_tiebreaker(idx, occ)
+    t = kcart.DecisionTreeClassifier("cross-entropy", max_depth, mss, class_importance)
+    t.fit(rule_list(k), rc, example_idx, rule_blacklist=[], tiebreaker=tiebreaker)
+    tree_equal(tree_to_dict(t.decision_tree), want, rtol=1e-15)
+    # the root's split search against the reference's raw score vector: same minimum, same tie set
+    from kover_b200.learning.learners.cart import _NodeImpurity
+    best, ties = t._cross_entropy_split(rc, _NodeImpurity(example_idx, class_importance), example_idx, [])
+    ref_score = g["node_scores"][0]
+    assert abs(best - ref_score.min()) <= 1e-15 * abs(ref_score.min())
+    assert np.array_equal(ties, np.where(ref_score == ref_score.min())[0])
+    rc.close()
+
+
+def test_cross_entropy_vs_checker_randomized():
+    """Cross-entropy split search on random nodes (2 and 3 classes, class importances, blacklist) against the
+    checker's score vector: same host, same np.log -> bit-exact minimum and tie set."""
+    from kover_b200.learning.learners.cart import _NodeImpurity
+    for seed in range(6):
+        rs = np.random.RandomState(500 + seed)
+        n, k, nc = int(rs.randint(100, 900)), int(rs.randint(2000, 9000)), 2 + seed % 2
+        P = synthetic_block(seed, n, 0, k)
+        y = rs.randint(0, nc, size=n)
+        imp = {c: float(rs.choice([0.5, 1.0, 2.0])) for c in range(nc)}
+        ex_all = {c: np.where(y == c)[0] for c in range(nc)}
+        node = {c: v[rs.rand(len(v)) < 0.4] for c, v in ex_all.items()}
+        if seed == 3:
+            node[0] = node[0][:0]                     # a class without examples in the node (cart.py:197-198)
+        blacklist = np.unique(rs.randint(0, k, size=40))
+        orc = ko.OracleKmerRuleClassifications(P, n, fast=True)
+        n_total, altered = ko.cart_altered_priors(ex_all, imp)
+        score = ko.cross_entropy_rule_score(orc, node, altered, n_total)
+        score[blacklist] = np.inf
+        rc = KmerRuleClassifications(P, n, devices=[0] if seed % 2 else [0, 0, 0])
+        t = kcart.DecisionTreeClassifier("cross-entropy", 3, 2, imp)
+        best, ties = t._cross_entropy_split(rc, _NodeImpurity(ex_all, imp), node, blacklist)
+        assert best == score.min() and np.array_equal(ties, np.where(score == score.min())[0])
+        rc.close()
 
 
 # ---------------------------------------------------------------------------------- bound / CV model selection

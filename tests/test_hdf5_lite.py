@@ -4,7 +4,8 @@ Pinned against a file written by the real HDF5 library: scipy ships ``testhdf5_7
 HDF5 behind a 512-byte user block: version-0 superblock with a base address, symbol-table root group, version-1
 object header, contiguous float64 dataset, fixed-string attribute).  The chunk B-tree, deflate, global-heap and
 multi-node group paths have no library-written file in this image: they are checked against this package's writer,
-which follows the same format specification (stated as such in DESIGN.md)."""
+which follows the same format specification (stated as such in DESIGN.md), and against a file assembled by hand from
+the specification in libhdf5 1.8's layout (tests/golden/make_hdf5_fixture.py), plus malformed variants of it."""
 import os
 
 import numpy as np
@@ -145,3 +146,94 @@ def test_randomized_round_trips(tmp_path):
             assert np.array_equal(d[key], data[key]), (trial, key)
         i = tuple(int(rs.randint(0, s)) for s in shape)
         assert d[i] == data[i]
+
+
+# ------------------------------------------------------------------------------------------------ hand-assembled fixture
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _fixture_bytes():
+    with open(os.path.join(GOLDEN, "hand_assembled_chunked.h5"), "rb") as fh:
+        return fh.read()
+
+
+def test_hand_assembled_chunked_deflate_file():
+    """A chunked + deflate dataset assembled byte by byte from the format specification by
+    tests/golden/make_hdf5_fixture.py -- independent of hdf5_lite_writer.py -- laid out the way libhdf5 1.8 / h5py 2.x
+    wrote Kover files: cached root symbol-table entry, NIL / modification-time / old fill-value messages, an
+    object-header continuation block, B-tree nodes at full capacity with garbage in unused slots, a TWO-level chunk
+    B-tree, a named version-1 deflate filter with its padding word, an edge chunk, maximum dimensions."""
+    import make_hdf5_fixture as mk
+    f = hdf5_lite.File(os.path.join(GOLDEN, "hand_assembled_chunked.h5"))
+    assert f.keys() == ["kmer_matrix", "phenotype"]
+    d = f["kmer_matrix"]
+    assert d.shape == (3, 250) and d.dtype == np.dtype("<u8") and d.chunks == (1, 100)
+    assert d.compression == "gzip" and d.compression_opts == 4
+    M = mk.matrix()
+    assert np.array_equal(d[...], M)
+    assert np.array_equal(d[1:3, 50:240], M[1:3, 50:240]) and np.array_equal(d[:, [3, 249, 100]], M[:, [3, 249, 100]])
+    assert np.array_equal(d[2, 200:], M[2, 200:])                   # the edge chunk
+    assert len(d._chunk_index()) == 9                               # both leaves of the two-level B-tree
+    assert np.array_equal(f["phenotype"][...], mk.phenotype())
+    f.close()
+
+
+def test_hand_assembled_fixture_is_reproducible():
+    import make_hdf5_fixture as mk
+    assert mk.build() == _fixture_bytes()
+
+
+def _patched(tmp_path, name, edit):
+    data = bytearray(_fixture_bytes())
+    data = edit(data)
+    path = str(tmp_path / name)
+    with open(path, "wb") as fh:
+        fh.write(bytes(data))
+    return path
+
+
+def test_truncated_chunk_is_an_error(tmp_path):
+    """A file cut in the middle of its chunk data: reading the dataset must fail loudly, not return zeros."""
+    f0 = hdf5_lite.File(os.path.join(GOLDEN, "hand_assembled_chunked.h5"))
+    last_chunk_end = max(a + n for a, n, _ in f0["kmer_matrix"]._chunk_index().values())
+    f0.close()
+    # keep the metadata (it lies after the chunks in this file) but blank out and shorten nothing else: emulate a
+    # truncated download by zeroing the tail of the last chunk's deflate stream
+    def corrupt(data):
+        data[last_chunk_end - 40:last_chunk_end] = b"\x00" * 40
+        return data
+    d = hdf5_lite.File(_patched(tmp_path, "corrupt.h5", corrupt))["kmer_matrix"]
+    with pytest.raises(Exception) as e:
+        d[...]
+    assert "zlib" in type(e.value).__module__ or "Error" in type(e.value).__name__
+    # and a file that simply ends early
+    with pytest.raises(ValueError, match="out of range|not an HDF5"):
+        f = hdf5_lite.File(_patched(tmp_path, "short.h5", lambda data: data[:len(data) // 2]))
+        f["kmer_matrix"][...]
+
+
+def test_unknown_filter_is_not_implemented(tmp_path):
+    def edit(data):
+        i = data.index(b"deflate\x00")
+        assert bytes(data[i - 8:i - 6]) == b"\x01\x00"            # filter id 1 = deflate
+        data[i - 8:i - 6] = (32001).to_bytes(2, "little")         # a registered third-party filter (Blosc)
+        return data
+    d = hdf5_lite.File(_patched(tmp_path, "filter.h5", edit))["kmer_matrix"]
+    assert d.compression is None
+    with pytest.raises(NotImplementedError, match="filter 32001"):
+        d[...]
+
+
+def test_version_2_object_header_is_not_implemented(tmp_path):
+    """libver='latest' files start object headers with "OHDR": documented as unsupported, raised as such."""
+    f0 = hdf5_lite.File(os.path.join(GOLDEN, "hand_assembled_chunked.h5"))
+    addr = f0._root._load_links()["kmer_matrix"]
+    f0.close()
+
+    def edit(data):
+        data[addr:addr + 4] = b"OHDR"
+        return data
+    f = hdf5_lite.File(_patched(tmp_path, "v2.h5", edit))
+    with pytest.raises(NotImplementedError, match="version-2 object headers"):
+        f["kmer_matrix"]
+    assert np.array_equal(f["phenotype"][...], np.array([0, 0, 1, 1, 0, 1], dtype=np.uint8))

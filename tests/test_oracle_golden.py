@@ -141,16 +141,20 @@ def test_scm_fit(golden_dir, case, monkeypatch):
     assert np.array_equal(np.asarray(imp, dtype=np.float64), g["rule_importances"])
 
 
-def tree_equal(got, want, path="root"):
+def tree_equal(got, want, path="root", rtol=0.0):
+    """rtol = 0: bit-exact criterion values (Gini).  rtol > 0 only for the cross-entropy criterion (np.log)."""
     assert got["depth"] == want["depth"], path
     assert got["n_by_class"] == {int(c): v for c, v in want["n_by_class"].items()}, path
-    assert got["criterion_value"] == want["criterion_value"], path
+    if rtol:
+        assert abs(got["criterion_value"] - want["criterion_value"]) <= rtol * abs(want["criterion_value"]), path
+    else:
+        assert got["criterion_value"] == want["criterion_value"], path
     assert ("rule_idx" in got) == ("rule_idx" in want), path
     if "rule_idx" in want:
         assert got["rule_idx"] == want["rule_idx"], path
         assert got["equivalent_rules_idx"] == want["equivalent_rules_idx"], path
-        tree_equal(got["left"], want["left"], path + ".L")
-        tree_equal(got["right"], want["right"], path + ".R")
+        tree_equal(got["left"], want["left"], path + ".L", rtol)
+        tree_equal(got["right"], want["right"], path + ".R", rtol)
 
 
 @pytest.mark.parametrize("case", cases.CART_CASES, ids=[c[0] for c in cases.CART_CASES])
@@ -169,6 +173,52 @@ def test_cart_fit(golden_dir, case):
         tiebreaker = lambda idx: ko.cart_tiebreaker(idx, occ)
     root = ko.cart_fit(rc, example_idx, "gini", max_depth, mss, class_importance, [], tiebreaker)
     tree_equal(root.to_dict(), want)
+
+
+def ce_case_inputs(case):
+    name, mname, lname, max_depth, mss, class_importance, tb, subset_seed = case
+    X, P, n, chunks = cases.matrix(mname)
+    y = cases.labels(lname)
+    train = cases.train_subset(n, subset_seed)
+    example_idx = {c: train[y[train] == c] for c in sorted(class_importance.keys())}
+    return P, n, chunks, train, example_idx
+
+
+def searched_nodes(tree):
+    """The nodes whose split search produced a score vector, in the learner's breadth-first order (cart.py:267-339):
+    every internal node, plus the leaves that were searched without finding a split -- none in these cases."""
+    out, queue = [], [tree]
+    while queue:
+        node = queue.pop(0)
+        if "rule_idx" in node:
+            out.append(node)
+            queue += [node["left"], node["right"]]
+    return out
+
+
+@pytest.mark.parametrize("case", cases.CART_CE_CASES, ids=[c[0] for c in cases.CART_CE_CASES])
+def test_cart_cross_entropy_fit(golden_dir, case):
+    """a10: the reference's cross-entropy criterion (cart.py:167-207).  Trees, tie sets (equivalent rules) and
+    selected rules must be identical; the raw score vectors go through np.log, whose last bit depends on the
+    machine's libm / SIMD dispatch, so they are compared to 4 ulp (rtol 1e-15) -- stated tolerance, floating point."""
+    name, mname, lname, max_depth, mss, class_importance, tb, subset_seed = case
+    g = load(golden_dir, name)
+    want = json.loads(str(g["tree_json"]))
+    P, n, chunks, train, example_idx = ce_case_inputs(case)
+    rc = ko.OracleKmerRuleClassifications(as_dataset(P, chunks), n, fast=True)
+    tiebreaker = None
+    if tb == "occurrence":
+        occ = rc.sum_rows(train)
+        tiebreaker = lambda idx: ko.cart_tiebreaker(idx, occ)
+    root = ko.cart_fit(rc, example_idx, "cross-entropy", max_depth, mss, class_importance, [], tiebreaker)
+    tree_equal(root.to_dict(), want, rtol=1e-15)
+    # the score vector of the root and of every other searched node against the reference's own
+    n_total, altered = ko.cart_altered_priors(example_idx, class_importance)
+    score = ko.cross_entropy_rule_score(rc, example_idx, altered, n_total)
+    ref_scores = g["node_scores"]
+    assert ref_scores.shape[0] >= len(searched_nodes(want))
+    np.testing.assert_allclose(score, ref_scores[0], rtol=1e-15, atol=0)
+    assert np.array_equal(np.where(score == score.min())[0], np.where(ref_scores[0] == ref_scores[0].min())[0])
 
 
 @pytest.mark.parametrize("case", cases.RISK_CASES, ids=[c[0] for c in cases.RISK_CASES])
