@@ -238,6 +238,7 @@ def extra_measurements(rc, shard, steps, k_local, reps=12):
     from kover_b200.synthetic import synthetic_labels, train_split
     from kover_b200.utils import build_row_mask
     out = {}
+    shard.set_profiling(True)          # the extras report scan-kernel times (CUDA events around every scan)
 
     def timed(fn, n=reps):
         fn()
@@ -423,7 +424,16 @@ def run_ours(args):
         wall_s = time.perf_counter() - wall0
         info_b = shard.info()
         launches = info_b.total_launches - info_a.total_launches
-        kernel_ms_total = info_b.scan_ms_total - info_a.scan_ms_total
+        # the scan kernel's own duration: the same K steps once more with CUDA events around every scan launch
+        # (kv_set_profiling; the events are off in the region above -- they cost host and stream time per step)
+        shard.set_profiling(True)
+        sync_all()
+        info_c = shard.info()
+        for p, pos, neg in timed:
+            rc.best_utility_rules(p, pos, neg, util_block_size=UTIL_BLOCK_SIZE)
+        sync_all()
+        kernel_ms_total = shard.info().scan_ms_total - info_c.scan_ms_total
+        shard.set_profiling(False)
         # keep the sampler alive for at least a few samples on very short runs: the SAME number of extra
         # (untimed) steps on every rank, since a step is collective
         w = float(comm.allreduce_max(np.array([wall_s]))[0]) if comm is not None else wall_s

@@ -37,6 +37,7 @@ extern "C" {
 #define KV_E_CUDA (-2)      /* CUDA runtime error / no device (RuntimeError)             */
 #define KV_E_NOMEM (-3)     /* device or pinned allocation failed (MemoryError)          */
 #define KV_E_OVERFLOW (-4)  /* caller's tie buffer too small; *n_found holds the need    */
+#define KV_E_INDEX (-5)     /* example index outside [0, n_examples) (IndexError)        */
 
 typedef struct kv_shard kv_shard;
 
@@ -221,11 +222,24 @@ int kv_scm_best_rules_p2p(kv_shard *s, const uint64_t *pos_mask, const uint64_t 
                           double *best_utility, int64_t capacity, int64_t *rule_idx, int64_t *pos_err,
                           int64_t *neg_cover, int64_t *n_found, double *merged_block_max, uint8_t *selected,
                           int *overflowed);
-/* Single-shard convenience: scan + select + ties in one call. */
+/* Single-shard step, the whole of _get_best_utility_rules (scm.py:238-288) in one call and ONE kernel launch: the
+ * scan kernel ends in a grid-wide barrier, replays the block merge, collects the ties of its own tiles into mapped
+ * page-locked memory and raises an epoch flag the host polls (no copy, no extra launch; KOVER_B200_FUSED=0 restores
+ * the scan + select + ties sequence).  More than 4 096 ties fall back to the tie kernel + device sort. */
 int kv_scm_best_rules(kv_shard *s, const uint64_t *pos_mask, const uint64_t *neg_mask, int64_t n_pos,
                       int64_t n_neg, double p, int64_t util_block_size, double *best_utility,
                       int64_t capacity, int64_t *rule_idx, int64_t *pos_err, int64_t *neg_cover,
                       int64_t *n_found);
+/* The same from the learner's example index arrays (scm.py:238-253 passes index lists to sum_rows; the masks of
+ * rules.py:210-222 are built inside the call).  KV_E_INDEX for an index outside [0, n_examples). */
+int kv_scm_best_rules_idx(kv_shard *s, const int64_t *pos_idx, int64_t n_pos, const int64_t *neg_idx,
+                          int64_t n_neg, double p, int64_t util_block_size, double *best_utility,
+                          int64_t capacity, int64_t *rule_idx, int64_t *pos_err, int64_t *neg_cover,
+                          int64_t *n_found);
+/* CUDA events around every scan kernel (kv_shard_info.last_kernel_ms / scan_ms_total are only maintained while
+ * this is on; off by default -- two event records per scan are a visible share of a 0.4 ms step).  Also
+ * KOVER_B200_PROFILE=1 at kv_create. */
+int kv_set_profiling(kv_shard *s, int on);
 
 /* ---- a9 / a11: DecisionTreeClassifier _gini_rule_score + _find_best_split (cart.py:112-161,
  * 219-250) --------------------------------------------------------------------------------

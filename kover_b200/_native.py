@@ -12,7 +12,7 @@ import numpy as np
 
 from . import build as _build
 
-KV_OK, KV_E_INVALID, KV_E_CUDA, KV_E_NOMEM, KV_E_OVERFLOW = 0, -1, -2, -3, -4
+KV_OK, KV_E_INVALID, KV_E_CUDA, KV_E_NOMEM, KV_E_OVERFLOW, KV_E_INDEX = 0, -1, -2, -3, -4, -5
 
 _c_i64 = ctypes.c_int64
 _c_p = ctypes.c_void_p
@@ -72,6 +72,10 @@ SYMBOLS = {
     "kv_scm_best_rules": (ctypes.c_int, [_c_p, _c_p, _c_p, _c_i64, _c_i64, ctypes.c_double, _c_i64,
                                          ctypes.POINTER(ctypes.c_double), _c_i64, _c_p, _c_p, _c_p,
                                          ctypes.POINTER(_c_i64)]),
+    "kv_scm_best_rules_idx": (ctypes.c_int, [_c_p, _c_p, _c_i64, _c_p, _c_i64, ctypes.c_double, _c_i64,
+                                             ctypes.POINTER(ctypes.c_double), _c_i64, _c_p, _c_p, _c_p,
+                                             ctypes.POINTER(_c_i64)]),
+    "kv_set_profiling": (ctypes.c_int, [_c_p, ctypes.c_int]),
     "kv_gini_scan": (ctypes.c_int, [_c_p, ctypes.c_int, _c_p, _c_p, _c_p, _c_p, ctypes.POINTER(ctypes.c_double)]),
     "kv_gini_best_split": (ctypes.c_int, [_c_p, ctypes.c_int, _c_p, _c_p, _c_p, _c_p, ctypes.POINTER(ctypes.c_double),
                                           _c_i64, _c_p, ctypes.POINTER(_c_i64)]),
@@ -127,6 +131,8 @@ def check(rc):
         raise ValueError(msg)
     if rc == KV_E_NOMEM:
         raise MemoryError(msg)
+    if rc == KV_E_INDEX:
+        raise IndexError(msg)
     raise RuntimeError(msg)
 
 
@@ -461,6 +467,24 @@ class Shard(object):
         check(rc)
         m = n.value
         return best.value, idx[:m].copy(), pe[:m].copy(), nc[:m].copy()
+
+    def scm_best_rules_idx(self, pos_idx, neg_idx, p, util_block_size):
+        """scm_best_rules from example index arrays (int64, contiguous): the row masks are built in the library."""
+        capacity, (idx, pe, nc) = self._tie_cap, self._tie_buf
+        best = ctypes.c_double(0.0)
+        n = _c_i64(0)
+        rc = self._lib.kv_scm_best_rules_idx(self._h, pos_idx.ctypes.data, pos_idx.shape[0], neg_idx.ctypes.data,
+                                             neg_idx.shape[0], float(p), int(util_block_size), ctypes.byref(best),
+                                             capacity, idx.ctypes.data, pe.ctypes.data, nc.ctypes.data, ctypes.byref(n))
+        if rc == KV_E_OVERFLOW:
+            return None
+        check(rc)
+        m = n.value
+        return best.value, idx[:m].copy(), pe[:m].copy(), nc[:m].copy()
+
+    def set_profiling(self, on=True):
+        """CUDA events around the scan kernels (info().last_kernel_ms / scan_ms_total); off by default."""
+        check(self._lib.kv_set_profiling(self._h, int(bool(on))))
 
     # -- a9 / a11
     def gini_scan(self, class_masks, altered_prior, n_total, n_node):

@@ -182,6 +182,25 @@ __device__ __forceinline__ double warp_min(double v) {
 // up to this many active packed rows (4 096 genomes) ride in the kernel parameter block: no H2D copy per scan
 static constexpr int SCAN_INLINE_ROWS = 64;
 
+// Fused tail of an SCM scan (single-shard step in ONE launch): after its last tile every CTA arrives at a grid-wide
+// barrier, replays the block merge on the complete block maxima, collects the ties of ITS OWN tiles straight into
+// mapped page-locked host memory, and the last CTA to finish publishes {best utility, tie count, epoch flag} there.
+struct TieRec;
+struct FusedTail {
+    int mode;                                   // 0 = off, 1 = exact ties
+    unsigned long long *barrier, *done;         // monotonic device counters (never reset)
+    unsigned long long barrier_target, done_target;
+    unsigned long long *zero_next;              // the block-maximum accumulators of the NEXT fused scan (other parity)
+    long long n_blocks;
+    double *bm, *tol;                           // block tables in d_misc: what k_scm_select leaves (overflow path)
+    uint8_t *sel;
+    unsigned long long *tie_count;              // device tie counter
+    TieRec *out;                                // tie records (mapped host memory)
+    long long cap;
+    volatile unsigned long long *host;          // mapped host header: [0] best utility bits, [1] tie count, [2] epoch
+    unsigned long long epoch;
+};
+
 struct Scan2Params {
     const uint64_t *mat;
     long long ld, n_cols, col0, k_total;
@@ -204,6 +223,7 @@ struct Scan2Params {
     // Gini epilogue (two classes = the two masks, in the caller's dict order): cart.py:71-77, 99-110
     double g_prior[2], g_ntot[2], g_nnode[2];
     unsigned long long *gmin;                 // enc_f64 of the minimum split score; segmax[0..ld/64) holds segment minima
+    FusedTail tail;
 };
 
 enum { EPI_COUNTS = 0, EPI_SCM = 1, EPI_GINI2 = 2 };
@@ -332,6 +352,9 @@ __device__ __forceinline__ void accum_word(const unsigned char *p, uint64_t a, u
         c1y += __popcll(v.y & m);
     }
 }
+
+template <int CW>
+__device__ void scm_fused_tail(const Scan2Params &P, long long t0, long long t1, unsigned char *ring);
 
 // GREC = true: the row records stay in global memory (read through L1) instead of being staged in shared memory --
 // the fallback for masks with more active packed rows than fit beside the ring (~5 000 rows = 320 000 genomes); the
@@ -514,6 +537,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) k_scan_tma(const Scan2Par
     if (EPI == EPI_SCM) {
         runmax_flush<CW>(run[0], P.blockmax, s_red);
         runmax_flush<CW>(run[1], P.blockmax, s_red);
+        if (P.tail.mode) scm_fused_tail<CW>(P, t0, t1, ring);      // (the ring is idle: every stage was consumed)
     }
     if (EPI == EPI_GINI2) {
         const unsigned long long v = warp_min_enc(enc_f64(gini_min));
@@ -698,12 +722,11 @@ __device__ __forceinline__ void tie_emit(const TieParams &P, long long rule, dou
     }
 }
 
-__device__ __forceinline__ void scm_ties_body(const TieParams &P) {
+// segments [seg0, n_seg) screened 32 at a time by warp `warp0` of `n_warps`
+__device__ __forceinline__ void scm_ties_range(const TieParams &P, long long seg0, long long n_seg, long long warp0,
+                                               long long n_warps) {
     const int lane = threadIdx.x & 31;
-    const long long n_seg = (P.n_cols + 63) >> 6;
-    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
-    for (long long sb = warp0 * 32; sb < n_seg; sb += n_warps * 32) {
+    for (long long sb = seg0 + warp0 * 32; sb < n_seg; sb += n_warps * 32) {
         // each lane screens one segment; the warp then scans the candidates together
         const long long g = sb + lane;
         unsigned cand = 0;
@@ -738,7 +761,114 @@ __device__ __forceinline__ void scm_ties_body(const TieParams &P) {
     }
 }
 
+__device__ __forceinline__ void scm_ties_body(const TieParams &P) {
+    scm_ties_range(P, 0, (P.n_cols + 63) >> 6, ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5,
+                   ((long long)gridDim.x * blockDim.x) >> 5);
+}
+
 __global__ void __launch_bounds__(256) k_scm_ties(const TieParams P) { scm_ties_body(P); }
+
+// ---- the fused tail of k_scan_tma<EPI_SCM> (see FusedTail) ----------------------------------------
+__device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+static constexpr long long FUSED_MAX_BLOCKS = 4096;      // block tables of the tail live in the idle TMA ring
+
+template <int CW>
+__device__ void scm_fused_tail(const Scan2Params &P, long long t0, long long t1, unsigned char *ring) {
+    const FusedTail &F = P.tail;
+    const int tid = threadIdx.x;
+    constexpr int NT = CW * 32;
+    __shared__ double s_best;
+    if (blockIdx.x == 0) {
+        for (long long b = tid; b < F.n_blocks; b += NT) F.zero_next[b] = 0ull;
+        if (tid == 0) *F.tie_count = 0ull;
+    }
+    consumer_bar(NT);                            // this CTA's block maxima (atomicMax) and segment maxima are issued
+    if (tid == 0) {
+        __threadfence();
+        atomicAdd(F.barrier, 1ull);
+        while (ld_acquire_gpu_u64(F.barrier) < F.barrier_target) {
+        }
+    }
+    consumer_bar(NT);
+    // every CTA replays the sequential block merge (scm.py:270-286) on the complete maxima: ~20 blocks at config 2
+    double *s_bm = reinterpret_cast<double *>(ring);
+    double *s_tol = s_bm + F.n_blocks;
+    uint8_t *s_sel = reinterpret_cast<uint8_t *>(s_tol + F.n_blocks);
+    for (long long b = tid; b < F.n_blocks; b += NT) s_bm[b] = dec_f64_max_dev(__ldcg(P.blockmax + b));
+    consumer_bar(NT);
+    if (tid == 0) {
+        double best = -INFINITY;
+        long long first = 0;
+        for (long long b = 0; b < F.n_blocks; ++b) {
+            const double m = s_bm[b];
+            s_tol[b] = np_tol_dev(m);
+            uint8_t keep = 0;
+            if (m > best || np_isclose_dev(best, m)) {
+                if (np_isclose_dev(m, best)) {
+                    keep = 1;
+                } else {
+                    best = m;
+                    for (long long q = first; q < b; ++q) s_sel[q] = 0;
+                    first = b;
+                    keep = 1;
+                }
+            }
+            s_sel[b] = keep;
+        }
+        s_best = best;
+    }
+    consumer_bar(NT);
+    if (blockIdx.x == 0) {                       // the tables later phases expect in d_misc (tie-buffer overflow path)
+        for (long long b = tid; b < F.n_blocks; b += NT) {
+            F.bm[b] = s_bm[b];
+            F.tol[b] = s_tol[b];
+            F.sel[b] = s_sel[b];
+        }
+    }
+    TieParams T;
+    T.cnt0 = P.cnt0;
+    T.cnt1 = P.cnt1;
+    T.segmax = P.segmax;
+    T.n_cols = P.n_cols;
+    T.ld = P.ld;
+    T.col0 = P.col0;
+    T.k_total = P.k_total;
+    T.ubs = P.ubs;
+    T.inv_ubs = 1.0 / (double)P.ubs;
+    T.p = P.p;
+    T.n_pos = P.n_pos;
+    T.n_neg = P.n_neg;
+    T.black_pres = P.black_pres;
+    T.black_abs = P.black_abs;
+    T.bm = s_bm;
+    T.tol = s_tol;
+    T.sel = s_sel;
+    T.count = F.tie_count;
+    T.threshold = nullptr;
+    T.out = F.out;
+    T.cap = F.cap;
+    const long long n_seg = (P.n_cols + 63) >> 6;
+    const long long seg0 = t0 * (CW * 64 / 64), seg1 = min(t1 * (long long)(CW * 64 / 64), n_seg);
+    scm_ties_range(T, seg0, seg1, tid >> 5, CW);
+    consumer_bar(NT);
+    if (tid == 0) {
+        __threadfence_system();                  // this CTA's tie records (host memory) before its ticket
+        const unsigned long long ticket = atomicAdd(F.done, 1ull);
+        if (ticket + 1 == F.done_target) {       // last CTA: publish the result
+            __threadfence();
+            const unsigned long long found = atomicAdd(F.tie_count, 0ull);
+            F.host[0] = (unsigned long long)__double_as_longlong(s_best);
+            F.host[1] = found;
+            __threadfence_system();
+            F.host[2] = F.epoch;
+        }
+    }
+}
 
 // the tie collection of up to QUEUE_BATCH jobs in one launch: blockIdx.y selects the job
 static constexpr int QUEUE_BATCH = 12;
@@ -1575,6 +1705,17 @@ struct kv_shard {
 
     DevBuf d_qmisc, d_qseg;                   // block tables / segment maxima of the jobs of one queue batch
     long long misc_n_blocks = -1, qmisc_n_blocks = -1;   // block count d_misc / d_qmisc are currently laid out for
+
+    // fused single-launch SCM step (FusedTail)
+    int fused = 1;                            // KOVER_B200_FUSED=0 switches back to scan + select + ties launches
+    int cooperative = 1;                      // KOVER_B200_COOP=0: plain launch (the grid never exceeds the resident CTAs)
+    void *h_fused = nullptr;                  // mapped page-locked: 64-byte header + kFusedCap tie records
+    unsigned long long *d_fused_ctr = nullptr;   // [0] grid barrier, [16] done tickets, [32] tie counter (128 B apart)
+    unsigned long long *d_fused_bm = nullptr;    // block-maximum accumulators, two parities of fused_n_blocks
+    long long fused_n_blocks = -1;
+    unsigned long long fused_epoch = 0, fused_barrier_total = 0, fused_done_total = 0;
+    std::vector<uint64_t> h_masks;            // masks built from index arrays (kv_scm_best_rules_idx)
+    bool profiling = false;                   // CUDA events around the scan kernels (kv_set_profiling / KOVER_B200_PROFILE)
     DevBuf d_level;                           // kv_gini_level: per-node minima, counters, tie slots, segment minima
     std::vector<uint32_t *> occ_tables;       // kv_occ_table_set: k-mer occurrence counts of a training set, [ld] each
     int64_t *h_level = nullptr;               // pinned arena: the tie lists of the last kv_gini_level, node after node
@@ -1662,6 +1803,9 @@ extern "C" int kv_create(int device, int64_t n_examples, int64_t n_kmers_total, 
     s->n_tiles = s->ld / TILE_COLS;
     if (const char *v = getenv("KOVER_B200_SCAN_VARIANT")) s->scan_variant = atoi(v);
     if (const char *v = getenv("KOVER_B200_L2HINT")) s->l2_hints = atoi(v);
+    if (const char *v = getenv("KOVER_B200_FUSED")) s->fused = atoi(v);
+    if (const char *v = getenv("KOVER_B200_COOP")) s->cooperative = atoi(v);
+    if (const char *v = getenv("KOVER_B200_PROFILE")) s->profiling = atoi(v) != 0;
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
     s->sm_count = prop.multiProcessorCount;
@@ -1699,6 +1843,9 @@ extern "C" int kv_destroy(kv_shard *s) {
     if (s->d_segmax) cudaFree(s->d_segmax);
     if (s->h_pin) cudaFreeHost(s->h_pin);
     if (s->h_level) cudaFreeHost(s->h_level);
+    if (s->h_fused) cudaFreeHost(s->h_fused);
+    if (s->d_fused_ctr) cudaFree(s->d_fused_ctr);
+    if (s->d_fused_bm) cudaFree(s->d_fused_bm);
     for (int i = 0; i < 2; ++i) {
         if (s->h_up[i]) cudaFreeHost(s->h_up[i]);
         if (s->ev_up[i]) cudaEventDestroy(s->ev_up[i]);
@@ -2018,6 +2165,25 @@ static int launch_scan_variant(kv_shard *s, const Scan2Params &P) {
     }
     const long long n_tiles = s->ld / (CW * 64);
     const int grid = (int)std::max(1ll, std::min<long long>((long long)s->sm_count * MINB, n_tiles));
+    if (EPI == EPI_SCM && P.tail.mode) {
+        // the tail's grid barrier needs every CTA resident: at most MINB CTAs per SM are launched (persistent grid)
+        // and a cooperative launch makes the driver verify it
+        if ((size_t)P.tail.n_blocks * 17 + 64 > (size_t)S * R * CW * 512)
+            return fail(KV_E_INVALID, "fused scan: block tables do not fit the ring");
+        Scan2Params Q = P;
+        Q.tail.barrier_target = s->fused_barrier_total + (unsigned long long)grid;
+        Q.tail.done_target = s->fused_done_total + (unsigned long long)grid;
+        if (s->cooperative) {
+            void *args[] = {(void *)&Q};
+            CU(cudaLaunchCooperativeKernel((const void *)k_scan_tma<EPI, CW, R, S, MINB, GREC>, dim3(grid),
+                                           dim3((CW + 1) * 32), args, smem, s->stream));
+        } else {
+            k_scan_tma<EPI, CW, R, S, MINB, GREC><<<grid, (CW + 1) * 32, smem, s->stream>>>(Q);
+        }
+        s->fused_barrier_total += (unsigned long long)grid;
+        s->fused_done_total += (unsigned long long)grid;
+        return KV_OK;
+    }
     k_scan_tma<EPI, CW, R, S, MINB, GREC><<<grid, (CW + 1) * 32, smem, s->stream>>>(P);
     return KV_OK;
 }
@@ -2035,7 +2201,7 @@ static int launch_scan(kv_shard *s, const Scan2Params &P, int n_both) {
     if (v == 6 && P.inline_rec) v = -1;               // forced GREC needs device-resident records (n_act > 64)
     if (v < 0 || v > kNumScanVariants) v = ((size_t)P.n_act * 20 > 30 * 1024) ? 5 : 1;
     if (v == 5 && scan_smem_bytes<16, 4, 4>((size_t)P.n_act) > kSmemLimit) v = 6;
-    CU(cudaEventRecord(s->ev0, s->stream));
+    if (s->profiling) CU(cudaEventRecord(s->ev0, s->stream));
     int rc = KV_OK;
     switch (v) {
 #define KV_CASE(ID, CW_, R_, S_, MINB_) \
@@ -2047,7 +2213,7 @@ static int launch_scan(kv_shard *s, const Scan2Params &P, int n_both) {
     }
     KV_TRY(rc);
     count_launch(s);
-    CU(cudaEventRecord(s->ev1, s->stream));
+    if (s->profiling) CU(cudaEventRecord(s->ev1, s->stream));
     return KV_OK;
 }
 
@@ -2082,9 +2248,11 @@ extern "C" int kv_sum_rows(kv_shard *s, const uint64_t *mask, void *out, int out
     }
     CU(cudaStreamSynchronize(s->stream));
     CU(cudaGetLastError());
-    float ms = 0;
-    CU(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
-    s->last_kernel_ms = ms;
+    if (s->profiling) {
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+        s->last_kernel_ms = ms;
+    }
     return KV_OK;
 }
 
@@ -2313,7 +2481,7 @@ static int count_masks_async(kv_shard *s, int n_masks, const uint64_t *const *ma
         return KV_OK;
     }
     KV_TRY(ensure(s->d_rec, count_pin_bytes(W, n_masks)));
-    CU(cudaEventRecord(s->ev0, s->stream));
+    if (s->profiling) CU(cudaEventRecord(s->ev0, s->stream));
     size_t off = 0;
     for (int m0 = 0; m0 < n_masks; m0 += per) {
         const int nm = std::min(per, n_masks - m0);
@@ -2363,7 +2531,7 @@ static int count_masks_async(kv_shard *s, int n_masks, const uint64_t *const *ma
         count_launch(s);
         off += count_batch_stride(W);
     }
-    CU(cudaEventRecord(s->ev1, s->stream));
+    if (s->profiling) CU(cudaEventRecord(s->ev1, s->stream));
     return KV_OK;
 }
 
@@ -2377,9 +2545,11 @@ static int count_masks(kv_shard *s, int n_masks, const uint64_t *masks, int firs
     KV_TRY(count_masks_async(s, n_masks, ptrs.data(), s->d_cnt.data() + first, (char *)s->h_pin));
     CU(cudaStreamSynchronize(s->stream));
     CU(cudaGetLastError());
-    float ms = 0;
-    CU(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
-    s->last_kernel_ms = ms;
+    if (s->profiling) {
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+        s->last_kernel_ms = ms;
+    }
     return KV_OK;
 }
 
@@ -2538,10 +2708,10 @@ static int scm_scan_async(kv_shard *s, const uint64_t *pos_mask, const uint64_t 
         R.black_abs = s->have_black ? s->d_black_abs : nullptr;
         R.blockmax = L.blockmax;
         R.segmax = s->d_segmax;
-        CU(cudaEventRecord(s->ev0, s->stream));
+        if (s->profiling) CU(cudaEventRecord(s->ev0, s->stream));
         k_scm_rescore<<<(unsigned)((s->ld + 2047) / 2048), 256, 0, s->stream>>>(R);
         count_launch(s);
-        CU(cudaEventRecord(s->ev1, s->stream));
+        if (s->profiling) CU(cudaEventRecord(s->ev1, s->stream));
         s->scm_swapped = swapped;
         s->rescore_calls += 1;
     } else {
@@ -2595,10 +2765,7 @@ extern "C" int kv_scm_scan(kv_shard *s, const uint64_t *pos_mask, const uint64_t
     CU(cudaMemsetAsync(L.blockmax, 0, (size_t)n_blocks * 8, s->stream));
     CU(stream_sync_spin(s->stream));
     CU(cudaGetLastError());
-    float ms = 0;
-    CU(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
-    s->last_kernel_ms = ms;
-    s->scan_ms_total += ms;
+    KV_TRY(finish_scan_timing(s));
     const unsigned long long *enc = (const unsigned long long *)s->h_pin;
     for (int64_t b = 0; b < n_blocks; ++b) block_max[b] = dec_f64_max(enc[b]);
     return KV_OK;
@@ -2761,6 +2928,140 @@ extern "C" int kv_scm_ties(kv_shard *s, const double *block_max, const uint8_t *
     return scm_collect_ties(s, n_blocks, capacity, nullptr, rule_idx, pos_err, neg_cover, n_found);
 }
 
+// ---- the single-shard step in ONE launch (FusedTail) -------------------------------------------------------------
+static constexpr long long kFusedCap = 4096;                 // tie records the mapped result buffer holds
+static constexpr size_t kFusedHdrBytes = 64;
+
+static int ensure_fused(kv_shard *s, int64_t n_blocks) {
+    if (!s->h_fused) {
+        CU(cudaHostAlloc(&s->h_fused, kFusedHdrBytes + (size_t)kFusedCap * sizeof(TieRec), cudaHostAllocMapped));
+        memset(s->h_fused, 0, kFusedHdrBytes);
+        CU(cudaMalloc(&s->d_fused_ctr, 3 * 128));
+        CU(cudaMemset(s->d_fused_ctr, 0, 3 * 128));
+        CU(cudaDeviceSynchronize());
+    }
+    if (s->fused_n_blocks != n_blocks) {                     // both parities zeroed: the kernels keep them that way
+        CU(cudaStreamSynchronize(s->stream));
+        if (s->d_fused_bm) cudaFree(s->d_fused_bm);
+        s->d_fused_bm = nullptr;
+        CU(cudaMalloc(&s->d_fused_bm, (size_t)n_blocks * 2 * 8));
+        CU(cudaMemset(s->d_fused_bm, 0, (size_t)n_blocks * 2 * 8));
+        CU(cudaDeviceSynchronize());
+        s->fused_n_blocks = n_blocks;
+    }
+    return KV_OK;
+}
+
+// scan + block merge + tie collection in one kernel, results through mapped host memory: one launch, no copy, the
+// host polls the epoch flag the last CTA writes.  Falls back to the tie kernel when more than kFusedCap rules tie.
+static int scm_best_rules_fused(kv_shard *s, const uint64_t *pos_mask, const uint64_t *neg_mask, int64_t n_pos,
+                                int64_t n_neg, double p, int64_t ubs, int64_t n_blocks, double *best_utility,
+                                int64_t capacity, int64_t *rule_idx, int64_t *pos_err, int64_t *neg_cover,
+                                int64_t *n_found) {
+    if (n_pos < 0 || n_neg < 0 || n_pos > s->n_examples || n_neg > s->n_examples)
+        return fail(KV_E_INVALID, "kv_scm_scan: n_pos / n_neg out of range");
+    KV_TRY(ensure_fused(s, n_blocks));
+    KV_TRY(ensure_counts(s, 2));
+    if (!s->d_segmax) CU(cudaMalloc(&s->d_segmax, (size_t)(s->ld / 64) * 2 * 8));
+    KV_TRY(ensure(s->d_misc, misc_layout(nullptr, n_blocks).bytes));
+    if (s->misc_n_blocks != n_blocks) {
+        CU(cudaMemsetAsync(s->d_misc.p, 0, s->d_misc.bytes, s->stream));
+        s->misc_n_blocks = n_blocks;
+    }
+    const MiscLayout L = misc_layout(s->d_misc.p, n_blocks);
+    int n_act, n_both;
+    KV_TRY(push_records2(s, pos_mask, neg_mask, n_act, n_both));
+    Scan2Params P;
+    fill_scan2(s, P, n_act);
+    P.cnt0 = s->d_cnt[0];
+    P.cnt1 = s->d_cnt[1];
+    P.p = p;
+    P.n_pos = (uint32_t)n_pos;
+    P.n_neg = (uint32_t)n_neg;
+    P.ubs = ubs;
+    P.black_pres = s->have_black ? s->d_black_pres : nullptr;
+    P.black_abs = s->have_black ? s->d_black_abs : nullptr;
+    P.segmax = s->d_segmax;
+    const unsigned long long epoch = ++s->fused_epoch;
+    const int parity = (int)(epoch & 1ull);
+    P.blockmax = s->d_fused_bm + (size_t)parity * n_blocks;
+    FusedTail &F = P.tail;
+    F.mode = 1;
+    F.barrier = s->d_fused_ctr;
+    F.done = s->d_fused_ctr + 16;
+    F.tie_count = s->d_fused_ctr + 32;
+    F.zero_next = s->d_fused_bm + (size_t)(parity ^ 1) * n_blocks;
+    F.n_blocks = n_blocks;
+    F.bm = L.bm;
+    F.tol = L.tol;
+    F.sel = L.sel;
+    F.out = (TieRec *)((char *)s->h_fused + kFusedHdrBytes);      // (mapped with UVA: the host pointer is the device pointer)
+    F.cap = kFusedCap;
+    F.host = (volatile unsigned long long *)s->h_fused;
+    F.epoch = epoch;
+    KV_TRY(launch_scan<EPI_SCM>(s, P, n_both));
+    s->scm_cnt_a = s->d_cnt[0];
+    s->scm_cnt_b = s->d_cnt[1];
+    s->scm_swapped = false;
+    s->scan_calls += 1;
+    s->scm_valid = true;
+    s->gini_valid = false;
+    s->scm_n_pos = n_pos;
+    s->scm_n_neg = n_neg;
+    s->scm_ubs = ubs;
+    s->scm_p = p;
+    // wait for the epoch flag (the kernel is then a few hundred nanoseconds from retiring)
+    volatile unsigned long long *h = (volatile unsigned long long *)s->h_fused;
+    unsigned spins = 0;
+    while (h[2] != epoch) {
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+        if ((++spins & 0x7FF) == 0) {
+            const cudaError_t e = cudaStreamQuery(s->stream);
+            if (e == cudaErrorNotReady) continue;
+            if (h[2] == epoch) break;
+            if (e == cudaSuccess) return fail(KV_E_CUDA, "fused scan retired without publishing its result");
+            CU(e);
+        }
+    }
+    __atomic_thread_fence(__ATOMIC_ACQUIRE);
+    const unsigned long long best_bits = h[0];
+    const long long found = (long long)h[1];
+    double best;
+    memcpy(&best, &best_bits, 8);
+    *best_utility = best;
+    *n_found = found;
+    if (s->profiling) {
+        CU(cudaStreamSynchronize(s->stream));
+        KV_TRY(finish_scan_timing(s));
+    }
+    if (found > kFusedCap) {
+        // a huge equivalent-rule set: the counts, segment maxima and block tables are resident -- tie kernel + device sort
+        if (found > capacity) return fail(KV_E_OVERFLOW, "tie buffer too small");
+        KV_TRY(ensure_ties(s, found));
+        TieHeader *d_hdr = (TieHeader *)s->d_ties.p;
+        CU(cudaMemsetAsync(d_hdr, 0, sizeof(TieHeader), s->stream));
+        launch_exact_ties(s, n_blocks, d_hdr, (TieRec *)(d_hdr + 1), std::max<long long>(found, kTieFirstBatch));
+        return scm_read_ties(s, d_hdr, (TieRec *)(d_hdr + 1), capacity, nullptr, rule_idx, pos_err, neg_cover, n_found);
+    }
+    if (found > capacity) return fail(KV_E_OVERFLOW, "tie buffer too small");
+    TieRec *recs = (TieRec *)((char *)s->h_fused + kFusedHdrBytes);
+    std::sort(recs, recs + found, [](const TieRec &a, const TieRec &b) { return a.idx < b.idx; });
+    for (long long i = 0; i < found; ++i) {
+        rule_idx[i] = recs[i].idx;
+        pos_err[i] = recs[i].pe;
+        neg_cover[i] = recs[i].nc;
+    }
+    return KV_OK;
+}
+
+extern "C" int kv_set_profiling(kv_shard *s, int on) {
+    if (!s) return fail(KV_E_INVALID, "kv_set_profiling: null shard");
+    s->profiling = on != 0;
+    return KV_OK;
+}
+
 extern "C" int kv_scm_best_rules(kv_shard *s, const uint64_t *pos_mask, const uint64_t *neg_mask, int64_t n_pos,
                                  int64_t n_neg, double p, int64_t util_block_size, double *best_utility,
                                  int64_t capacity, int64_t *rule_idx, int64_t *pos_err, int64_t *neg_cover,
@@ -2774,6 +3075,11 @@ extern "C" int kv_scm_best_rules(kv_shard *s, const uint64_t *pos_mask, const ui
     if (n_blocks <= 0) return fail(KV_E_INVALID, "kv_scm_best_rules: util_block_size must be positive");
     DeviceGuard g(s->device);
     s->last_launches = 0;
+    if (s->fused && !s->reuse_armed && n_blocks <= FUSED_MAX_BLOCKS) {
+        if (!pos_mask || !neg_mask) return fail(KV_E_INVALID, "kv_scm_scan: null mask");
+        return scm_best_rules_fused(s, pos_mask, neg_mask, n_pos, n_neg, p, util_block_size, n_blocks, best_utility,
+                                    capacity, rule_idx, pos_err, neg_cover, n_found);
+    }
     // scan -> device-side block merge -> tie collection, one host synchronisation for the whole call
     KV_TRY(ensure_ties(s, capacity));
     KV_TRY(scm_scan_async(s, pos_mask, neg_mask, n_pos, n_neg, p, util_block_size, n_blocks));
@@ -2781,12 +3087,36 @@ extern "C" int kv_scm_best_rules(kv_shard *s, const uint64_t *pos_mask, const ui
     k_scm_select<<<1, 32, 0, s->stream>>>(L.blockmax, n_blocks, L.bm, L.tol, L.sel, (TieHeader *)s->d_ties.p);
     count_launch(s);
     const int rc = scm_collect_ties(s, n_blocks, capacity, best_utility, rule_idx, pos_err, neg_cover, n_found);
-    float ms = 0;
-    if (cudaEventElapsedTime(&ms, s->ev0, s->ev1) == cudaSuccess) {
-        s->last_kernel_ms = ms;
-        s->scan_ms_total += ms;
-    }
+    if (rc == KV_OK || rc == KV_E_OVERFLOW) finish_scan_timing(s);
     return rc;
+}
+
+// Row mask over the packed rows from example indices (rules.py:210-222): example i = bit 63-(i%64) of word i/64;
+// duplicates count once.  -> KV_E_INDEX when an index is outside [0, n_examples).
+static int fill_row_mask(kv_shard *s, const int64_t *idx, int64_t n, uint64_t *mask) {
+    memset(mask, 0, (size_t)s->W * 8);
+    for (int64_t i = 0; i < n; ++i) {
+        const int64_t e = idx[i];
+        if (e < 0 || e >= s->n_examples) return fail(KV_E_INDEX, "index out of bounds");
+        mask[e >> 6] |= 1ull << (63 - (e & 63));
+    }
+    return KV_OK;
+}
+
+// kv_scm_best_rules straight from the learner's example index arrays (scm.py:238-253 hands sum_rows the index
+// lists): the two row masks are built here instead of in two numpy round trips.
+extern "C" int kv_scm_best_rules_idx(kv_shard *s, const int64_t *pos_idx, int64_t n_pos, const int64_t *neg_idx,
+                                     int64_t n_neg, double p, int64_t util_block_size, double *best_utility,
+                                     int64_t capacity, int64_t *rule_idx, int64_t *pos_err, int64_t *neg_cover,
+                                     int64_t *n_found) {
+    if (!s || (n_pos > 0 && !pos_idx) || (n_neg > 0 && !neg_idx))
+        return fail(KV_E_INVALID, "kv_scm_best_rules_idx: null pointer");
+    if (n_pos < 0 || n_neg < 0) return fail(KV_E_INVALID, "kv_scm_best_rules_idx: negative count");
+    s->h_masks.resize((size_t)s->W * 2);
+    KV_TRY(fill_row_mask(s, pos_idx, n_pos, s->h_masks.data()));
+    KV_TRY(fill_row_mask(s, neg_idx, n_neg, s->h_masks.data() + s->W));
+    return kv_scm_best_rules(s, s->h_masks.data(), s->h_masks.data() + s->W, n_pos, n_neg, p, util_block_size,
+                             best_utility, capacity, rule_idx, pos_err, neg_cover, n_found);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -3093,7 +3423,7 @@ extern "C" int kv_scm_queue_packets(kv_shard *s, int64_t n_jobs, const uint64_t 
     CU(stream_sync_spin(s->stream));
     CU(cudaGetLastError());
     float ms = 0;                                   // ev0 / ev1 bracket the (last) multi-mask pass
-    if (cudaEventElapsedTime(&ms, s->ev0, s->ev1) == cudaSuccess) s->last_kernel_ms = ms;
+    if (s->profiling && cudaEventElapsedTime(&ms, s->ev0, s->ev1) == cudaSuccess) s->last_kernel_ms = ms;
     return KV_OK;
 }
 
@@ -3138,7 +3468,9 @@ static int scm_packet_async(kv_shard *s, const uint64_t *pos_mask, const uint64_
     return KV_OK;
 }
 
+// CUDA-event time of the last scan kernel (ev0 / ev1), when profiling is on; the stream must have drained
 static int finish_scan_timing(kv_shard *s) {
+    if (!s->profiling) return KV_OK;
     float ms = 0;
     CU(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
     s->last_kernel_ms = ms;
@@ -3752,7 +4084,7 @@ extern "C" int kv_gini_level(kv_shard *s, int64_t n_nodes, const uint64_t *class
         CU(stream_sync_spin(s->stream));
         CU(cudaGetLastError());
         float ms = 0;
-        if (cudaEventElapsedTime(&ms, s->ev0, s->ev1) == cudaSuccess) scan_ms += ms;
+        if (s->profiling && cudaEventElapsedTime(&ms, s->ev0, s->ev1) == cudaSuccess) scan_ms += ms;
         const long long *h_ties = (const long long *)(h_hdr + 2 * per);
         size_t batch_total = 0, biggest = 0;
         for (int i = 0; i < nb; ++i) {

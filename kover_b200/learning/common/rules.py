@@ -292,6 +292,14 @@ class KmerRuleClassifications(BaseRuleClassifications):
         positive_example_idx = np.asarray(positive_example_idx)
         negative_example_idx = np.asarray(negative_example_idx)
         self.set_rule_blacklist(rule_blacklist)
+        group = self._group
+        if group._single and not self.dataset_removed_rows and hasattr(group.shards[0], "scm_best_rules_idx"):
+            # one shard: index arrays straight into the library (masks built there), one kernel launch per call
+            out = group.shards[0].scm_best_rules_idx(np.ascontiguousarray(positive_example_idx, dtype=np.int64).reshape(-1),
+                                                     np.ascontiguousarray(negative_example_idx, dtype=np.int64).reshape(-1),
+                                                     float(p), int(util_block_size))
+            if out is not None:
+                return out
         pos_mask = self.row_mask(positive_example_idx)
         neg_mask = self.row_mask(negative_example_idx)
         return self._group.scm_best_rules(pos_mask, neg_mask, positive_example_idx.shape[0],

@@ -240,6 +240,45 @@ def test_util_block_size_changes_between_calls(devices):
     rc.close()
 
 
+@pytest.mark.parametrize("fused,coop", [("1", "1"), ("1", "0"), ("0", "1")], ids=["fused-coop", "fused-plain", "unfused"])
+def test_single_launch_step_modes(monkeypatch, fused, coop):
+    """The single-shard step as ONE kernel (scan -> grid barrier -> block merge -> ties into mapped host memory,
+    cooperative or plain launch) and as the scan + select + ties sequence: both against the checker, over repeated
+    calls (the monotonic barrier / epoch counters and the parity-alternating accumulators), several block counts,
+    few and thousands of ties, blacklists, through the mask and the index-array entry points."""
+    monkeypatch.setenv("KOVER_B200_FUSED", fused)
+    monkeypatch.setenv("KOVER_B200_COOP", coop)
+    n, k, seed = 900, 200000, 12
+    P = synthetic_block(seed, n, 0, k)
+    P[:, 150000:150050] = P[:, 7:8]                    # 50 copies of one k-mer: equivalent rules
+    y = synthetic_labels(seed, n, sorted_by_label=False)
+    pos, neg = np.where(y == 1)[0], np.where(y == 0)[0]
+    orc = ko.OracleKmerRuleClassifications(P, n, fast=True)
+    rc = KmerRuleClassifications(P, n, devices=[0])
+    shard = rc._group.shards[0]
+    rs = np.random.RandomState(4)
+    for it in range(40):
+        a = pos[rs.rand(len(pos)) < rs.choice([1.0, 0.5, 0.05])]
+        b = neg[rs.rand(len(neg)) < rs.choice([1.0, 0.5, 0.05])]
+        p = float(rs.choice([0.1, 1.0, 2.0, 999999.0]))
+        ubs = int(rs.choice([1000000, 33333, 4099, 150]))
+        bl = np.unique(rs.randint(0, 2 * k, size=int(rs.choice([0, 60]))))
+        blm = np.zeros(2 * k, dtype=bool)
+        blm[bl] = True
+        want = ko.merge_utility_blocks(len(b) - orc.sum_rows(b), len(a) - orc.sum_rows(a), p, blm, block_size=ubs)
+        got = rc.best_utility_rules(p, a, b, rule_blacklist=bl, util_block_size=ubs)
+        assert got[0] == want[0] and np.array_equal(got[1], np.asarray(want[1], dtype=np.int64)), (it, p, ubs)
+        assert np.array_equal(got[2], want[2]) and np.array_equal(got[3], want[3])
+        if it % 5 == 0:                                # the mask entry point of the C ABI
+            got = shard.scm_best_rules(rc.row_mask(a), rc.row_mask(b), len(a), len(b), p, ubs)
+            assert got[0] == want[0] and np.array_equal(got[1], np.asarray(want[1], dtype=np.int64))
+    with pytest.raises(IndexError):
+        rc.best_utility_rules(1.0, np.array([0, n]), neg)
+    with pytest.raises(IndexError):
+        rc.best_utility_rules(1.0, pos, np.array([-1]))
+    rc.close()
+
+
 def test_large_equivalent_rule_sets():
     """Tens of thousands of equivalent rules (duplicated k-mers, as on real genomes): the device-sorted path of
     both tie collectors, single- and multi-shard, against the checker."""

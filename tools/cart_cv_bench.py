@@ -1,6 +1,8 @@
 """BASELINE configs[2] through the experiment layer: cost-complexity pruning with 5-fold cross-validation
 (experiment_cart.py:297-436) -- five fold trees + the master tree grown in lock-step over the resident matrix --
 and bound-based pruning (:208-294).  usage: python tools/cart_cv_bench.py [n k max_depth]"""
+import os as _os
+_os.environ.setdefault("KOVER_B200_PROFILE", "1")   # CUDA events around the scan kernels (info().scan_ms_total)
 import sys
 import time
 

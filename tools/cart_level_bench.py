@@ -1,5 +1,7 @@
 """CART fit (Gini, two classes) on a synthetic matrix resident in HBM: level-batched split search (class masks of
 8 nodes per matrix pass) against one scan per node.  usage: python tools/cart_level_bench.py [n k max_depth]"""
+import os as _os
+_os.environ.setdefault("KOVER_B200_PROFILE", "1")   # CUDA events around the scan kernels (info().scan_ms_total)
 import os
 import sys
 import time

@@ -2,6 +2,8 @@
 cross-validation + the bound selection on the full training set, over a synthetic 2 000 x 10 M matrix resident
 in HBM (experiment_scm.py:196-248, 568-629).  Prints where the wall time goes: matrix passes, re-scores, host.
 usage: python tools/cv_experiment.py [n_genomes n_kmers max_rules]"""
+import os as _os
+_os.environ.setdefault("KOVER_B200_PROFILE", "1")   # CUDA events around the scan kernels (info().scan_ms_total)
 import cProfile
 import pstats
 import sys

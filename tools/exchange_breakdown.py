@@ -1,4 +1,6 @@
 """torchrun --nproc-per-node N tools/exchange_breakdown.py : where the multi-rank SCM step spends its time."""
+import os as _os
+_os.environ.setdefault("KOVER_B200_PROFILE", "1")   # CUDA events around the scan kernels (info().scan_ms_total)
 import os, sys, time
 import numpy as np
 sys.path.insert(0, ".")

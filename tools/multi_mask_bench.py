@@ -1,6 +1,8 @@
 """k_count_tma: time one pass over a config-2 shard for the mask pairs of a cross-validation (full training set
 + n folds, positives / negatives as separate masks, genomes sorted by label) against one two-mask scan per
 pair, and check the counts against single-mask sum_rows passes.  usage: python tools/multi_mask_bench.py [n k]"""
+import os as _os
+_os.environ.setdefault("KOVER_B200_PROFILE", "1")   # CUDA events around the scan kernels (info().scan_ms_total)
 import sys
 import time
 

@@ -1,5 +1,7 @@
 """Fixed cost of one fused SCM step (kv_scm_best_rules: launch + block merge + tie collection + result copy + one
 synchronisation) measured on a shard so small that the kernels take microseconds."""
+import os as _os
+_os.environ.setdefault("KOVER_B200_PROFILE", "1")   # CUDA events around the scan kernels (info().scan_ms_total)
 import sys, time
 import numpy as np
 sys.path.insert(0, ".")

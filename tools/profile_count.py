@@ -1,5 +1,7 @@
 """Three passes of k_count_tma over a config-2 shard with the 12 masks of a 5-fold cross-validation + full training
 set (genomes sorted by label unless --interleaved): the command the ncu captures under profiles/ are taken on."""
+import os as _os
+_os.environ.setdefault("KOVER_B200_PROFILE", "1")   # CUDA events around the scan kernels (info().scan_ms_total)
 import sys
 
 import numpy as np

@@ -1,4 +1,6 @@
 """Where a single-GPU SCM step spends its time (host pieces timed with perf_counter, kernels with events)."""
+import os as _os
+_os.environ.setdefault("KOVER_B200_PROFILE", "1")   # CUDA events around the scan kernels (info().scan_ms_total)
 import sys, time
 import numpy as np
 sys.path.insert(0, ".")
