@@ -343,6 +343,200 @@ def extra_measurements(rc, shard, steps, k_local, reps=12):
     return out
 
 
+def _peak_gbs():
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(peaks_path):
+        return float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy)"
+    return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+
+def parity_check(rc, comm, rank, n_genomes, k_local, k_total, seed, pos, neg, p_values=(0.1, 10.0), slice_cols=50_000):
+    """Before any timing: (1) the presence / absence counts of two column slices of THIS rank's shard against the CPU
+    checker run on the CPU twin of the device generator; (2) the merged best utility / tie set of one multi-rank step
+    against the checker's block merge (oracle.merge_utility_blocks, scm.py:258-288) over the gathered count vectors
+    (rank 0 computes it).  The oracle is used as the checker only.  -> True on every rank, or raises."""
+    from kover_b200.synthetic import synthetic_block
+    from oracle import kover_oracle as ko
+    sp, sn = rc.sum_rows(pos), rc.sum_rows(neg)                      # collective: the reference's full 2K vectors
+    ok = True
+    col0 = rank * k_local
+    for c0 in (col0 + min(1_234_944, max(0, k_local - slice_cols)) // 512 * 512, col0 + max(0, k_local - slice_cols)):
+        n_c = min(slice_cols, k_local)
+        P = synthetic_block(seed, n_genomes, c0, n_c)
+        orc = ko.OracleKmerRuleClassifications(P, n_genomes, fast=True)
+        ok &= bool(np.array_equal(sp[c0:c0 + n_c], orc.sum_rows(pos)[:n_c]))
+        ok &= bool(np.array_equal(sn[k_total + c0:k_total + c0 + n_c], orc.sum_rows(neg)[n_c:]))
+    for p in p_values:
+        got = rc.best_utility_rules(p, pos, neg, util_block_size=UTIL_BLOCK_SIZE)      # collective
+        if rank == 0:
+            want = ko.merge_utility_blocks(len(neg) - sn, len(pos) - sp, p, np.zeros(2 * k_total, dtype=bool),
+                                           block_size=UTIL_BLOCK_SIZE)
+            ok &= bool(got[0] == want[0] and np.array_equal(got[1], np.asarray(want[1], dtype=np.int64))
+                       and np.array_equal(got[2], want[2]) and np.array_equal(got[3], want[3]))
+    if comm is not None:
+        ok = bool(comm.allreduce_min(np.array([int(ok)], dtype=np.int64))[0])
+    if not ok:
+        raise SystemExit("bench: parity check against the CPU checker FAILED (rank %d)" % rank)
+    return True
+
+
+def measure_shape(name, n_genomes, k_local, world, rank, local_rank, comm, seed, kind, steps=10):
+    """One BASELINE config (or its per-GPU shard) resident on this rank's GPU: parity on slices + one merged step
+    against the checker, then `steps` scans timed on the device.  kind: "scm" (utility scan) or "cart" (Gini scan)."""
+    import time as _t
+    from kover_b200 import _native
+    from kover_b200.learning.common.rules import KmerRuleClassifications
+    from kover_b200.sharding import ShardGroup
+    from kover_b200.synthetic import synthetic_labels, train_split
+    k_total = k_local * world
+    W = (n_genomes + 63) // 64
+    shard = _native.Shard(local_rank, n_genomes, k_total, rank * k_local, k_local)
+    t0 = _t.perf_counter()
+    shard.generate_synthetic(seed)
+    gen_s = _t.perf_counter() - t0
+    group = ShardGroup([shard], n_genomes, k_total, comm=comm, rank_slices=[(r * k_local, k_local) for r in range(world)])
+
+    class Meta(object):
+        shape = (W, k_total)
+        dtype = np.dtype(np.uint64)
+        chunks = (1, 100000)
+    rc = KmerRuleClassifications(Meta(), n_genomes, shard_group=group)
+    y = synthetic_labels(seed, n_genomes)
+    train = train_split(seed, n_genomes)
+    pos, neg = train[y[train] == 1], train[y[train] == 0]
+    out = {"n_genomes": n_genomes, "packed_rows": W, "n_kmers_per_gpu": k_local, "n_kmers_total": k_total, "n_gpus": world,
+           "matrix_GB_per_gpu": 8.0 * W * k_local / 1e9, "generate_s": gen_s}
+    out["parity_checked"] = parity_check(rc, comm, rank, n_genomes, k_local, k_total, seed, pos, neg, p_values=(1.0,),
+                                         slice_cols=20_000 if W > 100 else 50_000)
+    peak, _ = _peak_gbs()
+    w_act = active_words(pos, neg, n_genomes)
+    if kind == "scm":
+        call = lambda: rc.best_utility_rules(1.0, pos, neg, util_block_size=UTIL_BLOCK_SIZE)
+        units = 2.0 * k_total
+    else:
+        from oracle import kover_oracle as ko
+        ex = {0: neg, 1: pos}
+        n_total, altered = ko.cart_altered_priors(ex, {0: 1.0, 1: 1.0})
+        call = lambda: rc.gini_best_split(ex, altered, n_total)
+        units = 1.0 * k_total
+    for _ in range(3):
+        call()
+    if comm is not None:
+        comm.barrier()
+    shard.timer_start()
+    for _ in range(steps):
+        call()
+    dev_ms = shard.timer_stop()
+    shard.set_profiling(True)
+    a = shard.info().scan_ms_total
+    for _ in range(steps):
+        call()
+    kms = (shard.info().scan_ms_total - a) / steps
+    shard.set_profiling(False)
+    if comm is not None:
+        dev_ms = float(comm.allreduce_max(np.array([dev_ms]))[0])
+        kms = float(comm.allreduce_max(np.array([kms]))[0])
+    out.update({"ms_per_step": dev_ms / steps, "scan_kernel_ms": kms,
+                ("rules_per_s" if kind == "scm" else "splits_per_s"): units * steps / (dev_ms * 1e-3),
+                "scan_kernel_GBps_per_gpu": 8.0 * w_act * k_local / (kms * 1e-3) / 1e9,
+                "frac_of_hbm_peak": 8.0 * w_act * k_local / (kms * 1e-3) / 1e9 / peak,
+                "step_GBps_per_gpu": 8.0 * w_act * k_local * steps / (dev_ms * 1e-3) / 1e9,
+                "step_frac_of_hbm_peak": 8.0 * w_act * k_local * steps / (dev_ms * 1e-3) / 1e9 / peak})
+    if kind == "cart" and world == 1:
+        # configs[2] in full: depth-10 tree with the experiments' occurrence tiebreaker (experiment_cart.py:82-94, 264)
+        from kover_b200.learning.common.rules import LazyKmerRuleList
+        from kover_b200.learning.experiments.experiment_cart import OccurrenceTiebreaker
+        from kover_b200.learning.learners.cart import DecisionTreeClassifier
+        rules = LazyKmerRuleList(np.arange(k_local), np.arange(k_local))
+        warm = OccurrenceTiebreaker(rc, train)
+        DecisionTreeClassifier("gini", 3, 2, {0: 1.0, 1: 1.0}).fit(rules, rc, ex, tiebreaker=warm)
+        warm.release()
+        t = DecisionTreeClassifier("gini", 10, 2, {0: 1.0, 1: 1.0})
+        ia = shard.info()
+        t0 = _t.perf_counter()
+        tb = OccurrenceTiebreaker(rc, train)
+        t.fit(rules, rc, ex, tiebreaker=tb)
+        tb.release()
+        out["depth10_fit_s"] = _t.perf_counter() - t0
+        out["depth10_split_nodes"] = len(t.decision_tree.rules)
+        out["depth10_matrix_passes"] = shard.info().scan_calls - ia.scan_calls
+    rc.close()
+    return out
+
+
+def config_extras(world, rank, local_rank, comm):
+    """BASELINE.json's other configs, as far as this job's GPUs hold them -- untimed by the headline."""
+    out = {}
+    if world == 1:
+        c1 = measure_shape("C1", 500, 1_000_000, 1, 0, local_rank, None, 71, "scm", steps=200)
+        c1["note"] = "launch-bound: 64 MB of matrix is a 10 us scan; the step is the fixed cost of one launch + result poll"
+        out["C1_500x1M_scm"] = c1
+        out["C3_5kx20M_cart_root_node"] = measure_shape("C3", 5000, 20_000_000, 1, 0, local_rank, None, 73, "cart", steps=10)
+        out["C4_shard_20kx12.5M_scm_(per_GPU_share_at_N=4)"] = measure_shape("C4", 20000, 12_500_000, 1, 0, local_rank, None,
+                                                                             74, "scm", steps=10)
+        out["C5_shard_50kx12.5M_scm_(per_GPU_share_at_N=8)"] = measure_shape("C5", 50000, 12_500_000, 1, 0, local_rank, None,
+                                                                             75, "scm", steps=10)
+    elif world in (2, 4):
+        out["C4_20kx50M_scm_sharded"] = measure_shape("C4", 20000, 50_000_000 // world, world, rank, local_rank, comm, 74,
+                                                      "scm", steps=10)
+    elif world == 8:
+        out["C5_50kx100M_scm_sharded"] = measure_shape("C5", 50000, 100_000_000 // world, world, rank, local_rank, comm, 75,
+                                                       "scm", steps=10)
+    return out
+
+
+def hdf5_to_hbm(shard, n_genomes, k_cols):
+    """north-star item (1): a Kover-layout HDF5 file (kmer_matrix uint64, chunks (1, 100000), gzip 4: create.py:222-230)
+    of the first k_cols columns of the resident matrix, written with the test writer, then
+    KmerRuleClassifications(dataset.kmer_matrix, n) timed with the chunks inflated on the device and on the host."""
+    import tempfile
+    import time as _t
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from hdf5_lite_writer import Writer
+    from kover_b200.dataset import hdf5_lite
+    from kover_b200.learning.common.rules import KmerRuleClassifications
+    W = shard.n_words
+    P = shard.read_block(0, W, 0, k_cols)
+    d_tmp = tempfile.mkdtemp(dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    path = os.path.join(d_tmp, "bench.kover")
+    t0 = _t.perf_counter()
+    with Writer(path) as w:
+        w.create_dataset("kmer_matrix", P, chunks=(1, 100000), compression=4)
+    out = {"packed_GB": P.nbytes / 1e9, "file_GB": os.path.getsize(path) / 1e9, "write_s": _t.perf_counter() - t0,
+           "layout": "uint64 [%d, %d], chunks (1, 100000), gzip 4" % (W, k_cols)}
+    try:
+        small = os.path.join(d_tmp, "warm.kover")                        # first-use costs out of the timing
+        with Writer(small) as w:
+            w.create_dataset("kmer_matrix", P[:, :200_000], chunks=(1, 100000), compression=4)
+        for mode in ("1", "0"):
+            os.environ["KOVER_B200_DEVICE_INFLATE"] = mode
+            f = hdf5_lite.File(small)
+            KmerRuleClassifications(f["kmer_matrix"], n_genomes, devices=[shard.device]).close()
+            f.close()
+        ok = True
+        for mode, key in (("1", "device_inflate"), ("0", "host_inflate")):
+            os.environ["KOVER_B200_DEVICE_INFLATE"] = mode
+            f = hdf5_lite.File(path)
+            t0 = _t.perf_counter()
+            rc = KmerRuleClassifications(f["kmer_matrix"], n_genomes, devices=[shard.device])
+            dt = _t.perf_counter() - t0
+            sh = rc._group.shards[0]
+            for c0 in (0, k_cols // 2, k_cols - 100_000):
+                ok &= bool(np.array_equal(sh.read_block(0, W, c0, 100_000), P[:, c0:c0 + 100_000]))
+            rc.close()
+            f.close()
+            out[key + "_s"] = dt
+            out[key + "_GBps"] = P.nbytes / dt / 1e9
+        out["resident_image_identical"] = ok
+        out["hdf5_to_hbm_GBps"] = out["device_inflate_GBps"]
+    finally:
+        os.environ.pop("KOVER_B200_DEVICE_INFLATE", None)
+        for name in os.listdir(d_tmp):
+            os.remove(os.path.join(d_tmp, name))
+        os.rmdir(d_tmp)
+    return out
+
+
 def workload_config(n_gpus):
     return {"workload": "BASELINE configs[1]: SCM utility scan, 2000 genomes x 10M k-mers per GPU (W=32 packed rows, "
                         "2.56 GB per GPU), p grid {0.1,0.5,1,2,5,10} x {conjunction,disjunction} x {train, 5 CV folds}",
@@ -400,6 +594,10 @@ def run_ours(args):
             comm.barrier()
         torch.cuda.synchronize()
 
+    # parity before timing, on every rank count: slices of this rank's shard and the merged result of a step
+    _, pos0, neg0 = steps[0]
+    parity_ok = parity_check(rc, comm, rank, N_GENOMES, k_local, k_total, SEED, pos0, neg0)
+
     for i in range(args.warmup):
         one_step(i)
 
@@ -439,7 +637,9 @@ def run_ours(args):
         w = float(comm.allreduce_max(np.array([wall_s]))[0]) if comm is not None else wall_s
         for i in range(max(0, int((0.6 - w) / max(w / args.steps, 1e-5)))):
             one_step(i)
-    d2h = sum(32 + 16 * max(256, c) for c in tie_counts)
+    # results: the kernel writes a 64-byte header + 16 bytes per tie into mapped page-locked host memory (multi-rank:
+    # + the merged block maxima / selected flags, 9 bytes per utility block)
+    d2h = sum(64 + 16 * c + (9 * n_blocks if world > 1 else 0) for c in tie_counts)
     kernel_ms = [kernel_ms_total / args.steps] * args.steps
     if comm is not None:
         dev_ms = float(comm.allreduce_max(np.array([dev_ms]))[0])
@@ -462,11 +662,7 @@ def run_ours(args):
 
     rules_per_step = 2.0 * k_total
     value = rules_per_step * args.steps / (dev_ms * 1e-3)
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.isfile(peaks_path):
-        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy)"
-    else:
-        peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+    peak, peak_src = _peak_gbs()
     achieved = float(np.sum(alg_bytes) / (np.sum(kernel_ms) * 1e-3) / 1e9)
     traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
@@ -487,21 +683,40 @@ def run_ours(args):
                      "kernel_share_of_step": float(np.sum(kernel_ms) / dev_ms)},
         "e2e": {"value": rules_per_step * args.steps / e2e_s, "unit": "rules/s",
                 "h2d_bytes_per_step": int(h2d / args.steps), "d2h_bytes_per_step": int(d2h / args.steps),
-                "d2h_note": "header + block maxima + the first 256 tie records travel in one 4 KB copy",
+                "h2d_note": "the step's inputs are two index arrays (host) -> two row masks -> 20 B per active packed row, "
+                            "which ride in the kernel parameter block of the ONE launch per step",
+                "d2h_note": "the scan kernel itself writes header + tie records into mapped page-locked host memory; "
+                            "the host polls the epoch flag (no copy call)",
                 "ms_per_step": 1e3 * e2e_s / args.steps,
                 "api": "SetCoveringMachine._get_best_utility_rules(rule_classifications, pos_idx, neg_idx) with host "
                        "index arrays in, host tie arrays out; matrix resident (uploaded once per dataset)"},
         "gpu_launches": int(launches),
+        "parity_checked": bool(parity_ok),
         "clocks": clocks.summary(),
         "wall_ms_per_step": 1e3 * wall_s / args.steps,
         "generate_s": gen_s,
     }
+    line["roofline"]["step_GBps"] = float(np.sum(alg_bytes) / (dev_ms * 1e-3) / 1e9)
+    line["roofline"]["step_frac"] = line["roofline"]["step_GBps"] / peak
+    if world > 1:
+        info_x = shard.info()
+        m = max(1, info_x.exch_steps)
+        line["exchange"] = {"steps": int(info_x.exch_steps), "publish_us": info_x.exch_publish_us / m,
+                            "wait_for_peers_us": info_x.exch_wait_us / m, "merge_and_result_us": info_x.exch_merge_us / m,
+                            "note": "rank 0, device clock of its last CTA, per step: packet stores into the peers' mailboxes; "
+                                    "waiting for every peer's packet (NVLink latency + rank skew); merge + result to the host"}
     if rank == 0 and world == 1:
         line["extra"] = extra_measurements(rc, shard, steps, k_local)
+        if not args.no_extras:
+            line["extra"]["hdf5_to_hbm"] = hdf5_to_hbm(shard, N_GENOMES, 8_400_000)
         line["cpu_baseline"] = cpu_baseline(N_GENOMES, SEED, steps)
+    rc.close()
+    if not args.no_extras:
+        cfg = config_extras(world, rank, local_rank, comm)
+        if rank == 0:
+            line.setdefault("extra", {})["configs"] = cfg
     if rank == 0:
         print(json.dumps(line))
-    rc.close()
     if comm is not None:
         import torch.distributed as dist
         dist.destroy_process_group()
@@ -513,6 +728,7 @@ def main():
     ap.add_argument("--steps", type=int, default=72)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-extras", action="store_true", help="skip the untimed extras (other configs, HDF5 upload)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -57,6 +57,10 @@ typedef struct kv_shard_info {
     double scan_ms_total;    /* sum of the scan kernels' CUDA-event times since kv_create */
     int64_t scan_calls;      /* SCM matrix scans since kv_create                         */
     int64_t rescore_calls;   /* SCM scans served from resident counts (kv_scm_reuse_counts) */
+    int64_t exch_steps;      /* multi-rank fused steps (kv_scm_best_rules_p2p) since kv_create          */
+    double exch_publish_us;  /* summed over those steps, device clock of the rank's last CTA: packet stores, */
+    double exch_wait_us;     /* ... waiting for every peer's packet (rank skew + NVLink latency),          */
+    double exch_merge_us;    /* ... merging the packets and publishing the result to the host              */
 } kv_shard_info;
 
 const char *kv_last_error(void);
@@ -83,6 +87,17 @@ int kv_get_info(kv_shard *s, kv_shard_info *out);
  * rows 2w, 2w+1 become the high / low halves of 64-bit row w. */
 int kv_upload_block(kv_shard *s, int pack_bits, int64_t row0, int64_t n_rows, int64_t gcol0,
                     int64_t n_cols, const void *host, int64_t ld_elems);
+/* The same for gzip-filtered chunks WITHOUT inflating them on the host: the reference's `dataset[rows, c0:c1]`
+ * (rules.py:253) makes libhdf5 inflate every chunk (create.py:222-230: chunks (1, <=100000), gzip) on a host core
+ * on every call; here the raw zlib streams (RFC 1950) travel to the GPU and one warp inflates one chunk (stored,
+ * fixed and dynamic Huffman blocks; header and Adler-32 checked).  src[i] / src_bytes[i]: the i-th chunk's stream
+ * as stored in the file; (row0[i], gcol0[i]): dataset coordinates of its first element, rows in pack_bits units;
+ * every chunk inflates to chunk_rows x chunk_cols elements (HDF5 stores edge chunks at full size); parts outside the
+ * dataset or outside this shard's columns are dropped.  status[i] = 0, or a non-zero code when the stream is
+ * malformed: the caller then inflates that chunk on the host (its error-reporting path) and uses kv_upload_block. */
+int kv_upload_deflate(kv_shard *s, int pack_bits, int64_t n_chunks, const void *const *src,
+                      const int64_t *src_bytes, const int64_t *row0, const int64_t *gcol0,
+                      int64_t chunk_rows, int64_t chunk_cols, int32_t *status);
 /* Fill the shard with the deterministic synthetic matrix of kover_b200/synthetic.py (bench and
  * full-size parity tests; the CPU twin regenerates any column slice). */
 int kv_generate_synthetic(kv_shard *s, uint64_t seed);
@@ -222,6 +237,12 @@ int kv_scm_best_rules_p2p(kv_shard *s, const uint64_t *pos_mask, const uint64_t 
                           double *best_utility, int64_t capacity, int64_t *rule_idx, int64_t *pos_err,
                           int64_t *neg_cover, int64_t *n_found, double *merged_block_max, uint8_t *selected,
                           int *overflowed);
+/* kv_scm_best_rules_p2p from example index arrays (masks built inside the call, see kv_scm_best_rules_idx). */
+int kv_scm_best_rules_p2p_idx(kv_shard *s, const int64_t *pos_idx, int64_t n_pos, const int64_t *neg_idx,
+                              int64_t n_neg, double p, int64_t util_block_size, int64_t packet_capacity,
+                              double *best_utility, int64_t capacity, int64_t *rule_idx, int64_t *pos_err,
+                              int64_t *neg_cover, int64_t *n_found, double *merged_block_max,
+                              uint8_t *selected, int *overflowed);
 /* Single-shard step, the whole of _get_best_utility_rules (scm.py:238-288) in one call and ONE kernel launch: the
  * scan kernel ends in a grid-wide barrier, replays the block merge, collects the ties of its own tiles into mapped
  * page-locked memory and raises an epoch flag the host polls (no copy, no extra launch; KOVER_B200_FUSED=0 restores
@@ -236,6 +257,17 @@ int kv_scm_best_rules_idx(kv_shard *s, const int64_t *pos_idx, int64_t n_pos, co
                           int64_t n_neg, double p, int64_t util_block_size, double *best_utility,
                           int64_t capacity, int64_t *rule_idx, int64_t *pos_err, int64_t *neg_cover,
                           int64_t *n_found);
+/* ---- a7: the greedy loop's example bookkeeping on the device (scm.py:133-139) -------------------
+ * After a pick the reference fetches the rule's column (get_columns) and keeps the examples it accepts.  Here the
+ * shard keeps the remaining positive / negative masks resident: kv_scm_state_set uploads them once per fit,
+ * kv_mask_and_column ANDs both with the chosen column (invert = 1 for an absence rule: mask &= ~column) and returns
+ * what is left.  local_col >= 0: the column is read from this shard's matrix and its W raw words are returned in
+ * col_words_out (may be NULL) for the shards / ranks that do not hold it; local_col < 0: apply col_words_in.
+ * The scan entry points take pos_mask = neg_mask = NULL to scan the resident state (n_pos / n_neg are then ignored:
+ * the state's counts are used). */
+int kv_scm_state_set(kv_shard *s, const uint64_t *pos_mask, const uint64_t *neg_mask, int64_t *n_pos, int64_t *n_neg);
+int kv_mask_and_column(kv_shard *s, int64_t local_col, const uint64_t *col_words_in, int invert,
+                       uint64_t *col_words_out, int64_t *n_pos, int64_t *n_neg);
 /* CUDA events around every scan kernel (kv_shard_info.last_kernel_ms / scan_ms_total are only maintained while
  * this is on; off by default -- two event records per scan are a visible share of a 0.4 ms step).  Also
  * KOVER_B200_PROFILE=1 at kv_create. */

@@ -23,7 +23,9 @@ class ShardInfo(ctypes.Structure):
                 ("n_words", _c_i64), ("n_kmers_total", _c_i64), ("col0", _c_i64), ("n_cols", _c_i64),
                 ("ld", _c_i64), ("matrix_bytes", _c_i64), ("last_kernel_ms", ctypes.c_double),
                 ("last_launches", _c_i64), ("total_launches", _c_i64), ("scan_ms_total", ctypes.c_double),
-                ("scan_calls", _c_i64), ("rescore_calls", _c_i64)]
+                ("scan_calls", _c_i64), ("rescore_calls", _c_i64), ("exch_steps", _c_i64),
+                ("exch_publish_us", ctypes.c_double), ("exch_wait_us", ctypes.c_double),
+                ("exch_merge_us", ctypes.c_double)]
 
 
 # every exported symbol with (restype, argtypes); tests/test_abi.py checks this table against the header
@@ -35,6 +37,7 @@ SYMBOLS = {
     "kv_destroy": (ctypes.c_int, [_c_p]),
     "kv_get_info": (ctypes.c_int, [_c_p, ctypes.POINTER(ShardInfo)]),
     "kv_upload_block": (ctypes.c_int, [_c_p, ctypes.c_int, _c_i64, _c_i64, _c_i64, _c_i64, _c_p, _c_i64]),
+    "kv_upload_deflate": (ctypes.c_int, [_c_p, ctypes.c_int, _c_i64, _c_p, _c_p, _c_p, _c_p, _c_i64, _c_i64, _c_p]),
     "kv_generate_synthetic": (ctypes.c_int, [_c_p, ctypes.c_uint64]),
     "kv_read_block": (ctypes.c_int, [_c_p, _c_i64, _c_i64, _c_i64, _c_i64, _c_p, _c_i64]),
     "kv_timer_start": (ctypes.c_int, [_c_p]),
@@ -69,6 +72,9 @@ SYMBOLS = {
     "kv_scm_best_rules_p2p": (ctypes.c_int, [_c_p, _c_p, _c_p, _c_i64, _c_i64, ctypes.c_double, _c_i64, _c_i64,
                                              ctypes.POINTER(ctypes.c_double), _c_i64, _c_p, _c_p, _c_p,
                                              ctypes.POINTER(_c_i64), _c_p, _c_p, ctypes.POINTER(ctypes.c_int)]),
+    "kv_scm_best_rules_p2p_idx": (ctypes.c_int, [_c_p, _c_p, _c_i64, _c_p, _c_i64, ctypes.c_double, _c_i64, _c_i64,
+                                                 ctypes.POINTER(ctypes.c_double), _c_i64, _c_p, _c_p, _c_p,
+                                                 ctypes.POINTER(_c_i64), _c_p, _c_p, ctypes.POINTER(ctypes.c_int)]),
     "kv_scm_best_rules": (ctypes.c_int, [_c_p, _c_p, _c_p, _c_i64, _c_i64, ctypes.c_double, _c_i64,
                                          ctypes.POINTER(ctypes.c_double), _c_i64, _c_p, _c_p, _c_p,
                                          ctypes.POINTER(_c_i64)]),
@@ -76,6 +82,9 @@ SYMBOLS = {
                                              ctypes.POINTER(ctypes.c_double), _c_i64, _c_p, _c_p, _c_p,
                                              ctypes.POINTER(_c_i64)]),
     "kv_set_profiling": (ctypes.c_int, [_c_p, ctypes.c_int]),
+    "kv_scm_state_set": (ctypes.c_int, [_c_p, _c_p, _c_p, ctypes.POINTER(_c_i64), ctypes.POINTER(_c_i64)]),
+    "kv_mask_and_column": (ctypes.c_int, [_c_p, _c_i64, _c_p, ctypes.c_int, _c_p, ctypes.POINTER(_c_i64),
+                                          ctypes.POINTER(_c_i64)]),
     "kv_gini_scan": (ctypes.c_int, [_c_p, ctypes.c_int, _c_p, _c_p, _c_p, _c_p, ctypes.POINTER(ctypes.c_double)]),
     "kv_gini_best_split": (ctypes.c_int, [_c_p, ctypes.c_int, _c_p, _c_p, _c_p, _c_p, ctypes.POINTER(ctypes.c_double),
                                           _c_i64, _c_p, ctypes.POINTER(_c_i64)]),
@@ -248,6 +257,21 @@ class Shard(object):
         check(self._lib.kv_upload_block(self._h, bits, int(row0), block.shape[0], int(gcol0), block.shape[1],
                                         ctypes.c_void_p(block.ctypes.data), int(ld)))
 
+    def upload_deflate(self, pack_bits, addresses, nbytes, row0, gcol0, chunk_rows, chunk_cols):
+        """Raw zlib streams of HDF5 chunks -> the resident image, inflated on the device (kv_upload_deflate).
+        addresses: host addresses of the streams (uint64 array; the memory must stay mapped during the call).
+        -> int32 status per chunk (0 = placed; non-zero = malformed stream, redo that chunk on the host)."""
+        addresses = np.ascontiguousarray(addresses, dtype=np.uint64)
+        nbytes = np.ascontiguousarray(nbytes, dtype=np.int64)
+        row0 = np.ascontiguousarray(row0, dtype=np.int64)
+        gcol0 = np.ascontiguousarray(gcol0, dtype=np.int64)
+        n = addresses.shape[0]
+        assert nbytes.shape == row0.shape == gcol0.shape == (n,)
+        status = np.zeros(n, dtype=np.int32)
+        check(self._lib.kv_upload_deflate(self._h, int(pack_bits), n, ptr(addresses), ptr(nbytes), ptr(row0), ptr(gcol0),
+                                          int(chunk_rows), int(chunk_cols), ptr(status)))
+        return status
+
     def generate_synthetic(self, seed):
         check(self._lib.kv_generate_synthetic(self._h, ctypes.c_uint64(int(seed))))
 
@@ -394,6 +418,25 @@ class Shard(object):
             return (best.value, idx[:m].copy(), pe[:m].copy(), nc[:m].copy()), bm, best.value, sel
         return (best.value, idx[:m], pe[:m], nc[:m]), bm, best.value, sel
 
+    def scm_best_rules_p2p_idx(self, pos_idx, neg_idx, p, util_block_size, packet_capacity):
+        """The multi-rank step from example index arrays (int64, contiguous) -> the 4-tuple, or None when a packet or
+        the merged result overflowed (the caller redoes the step through the mask path and its two-phase fallback)."""
+        nb = n_utility_blocks(self.n_kmers_total, util_block_size)
+        if getattr(self, "_p2p_nb", None) != nb:
+            self._p2p_nb, self._p2p_bm, self._p2p_sel = nb, np.empty(nb, dtype=np.float64), np.empty(nb, dtype=np.uint8)
+        capacity, (idx, pe, nc) = self._tie_cap, self._tie_buf
+        best, n, over = ctypes.c_double(0.0), _c_i64(0), ctypes.c_int(0)
+        rc = self._lib.kv_scm_best_rules_p2p_idx(self._h, pos_idx.ctypes.data, pos_idx.shape[0], neg_idx.ctypes.data,
+                                                 neg_idx.shape[0], float(p), int(util_block_size), int(packet_capacity),
+                                                 ctypes.byref(best), capacity, idx.ctypes.data, pe.ctypes.data,
+                                                 nc.ctypes.data, ctypes.byref(n), self._p2p_bm.ctypes.data,
+                                                 self._p2p_sel.ctypes.data, ctypes.byref(over))
+        if rc == KV_E_OVERFLOW or (rc == KV_OK and over.value):
+            return None
+        check(rc)
+        m = n.value
+        return best.value, idx[:m].copy(), pe[:m].copy(), nc[:m].copy()
+
     QUEUE_SLOT_RECS = 256
 
     def scm_queue(self, jobs, util_block_size):
@@ -477,6 +520,56 @@ class Shard(object):
                                              neg_idx.shape[0], float(p), int(util_block_size), ctypes.byref(best),
                                              capacity, idx.ctypes.data, pe.ctypes.data, nc.ctypes.data, ctypes.byref(n))
         if rc == KV_E_OVERFLOW:
+            return None
+        check(rc)
+        m = n.value
+        return best.value, idx[:m].copy(), pe[:m].copy(), nc[:m].copy()
+
+    # -- device-resident greedy state (scm.py:133-139)
+    def scm_state_set(self, pos_mask, neg_mask):
+        pos_mask = np.ascontiguousarray(pos_mask, dtype=np.uint64)
+        neg_mask = np.ascontiguousarray(neg_mask, dtype=np.uint64)
+        assert pos_mask.shape == (self.n_words,) and neg_mask.shape == (self.n_words,)
+        n_pos, n_neg = _c_i64(0), _c_i64(0)
+        check(self._lib.kv_scm_state_set(self._h, ptr(pos_mask), ptr(neg_mask), ctypes.byref(n_pos), ctypes.byref(n_neg)))
+        return n_pos.value, n_neg.value
+
+    def mask_and_column(self, local_col=None, words=None, invert=False, want_words=False):
+        """AND the resident masks with a column of this shard (local_col) or with the given W words.
+        -> (n_pos, n_neg, column words or None)."""
+        n_pos, n_neg = _c_i64(0), _c_i64(0)
+        out = np.empty(self.n_words, dtype=np.uint64) if want_words else None
+        if local_col is None:
+            words = np.ascontiguousarray(words, dtype=np.uint64)
+            assert words.shape == (self.n_words,)
+        check(self._lib.kv_mask_and_column(self._h, -1 if local_col is None else int(local_col),
+                                           ptr(words) if local_col is None else None, int(bool(invert)),
+                                           ptr(out), ctypes.byref(n_pos), ctypes.byref(n_neg)))
+        return n_pos.value, n_neg.value, out
+
+    def scm_best_rules_state(self, p, util_block_size):
+        """scm_best_rules over the resident greedy state.  -> the 4-tuple, or None on tie-buffer overflow."""
+        capacity, (idx, pe, nc) = self._tie_cap, self._tie_buf
+        best, n = ctypes.c_double(0.0), _c_i64(0)
+        rc = self._lib.kv_scm_best_rules(self._h, None, None, 0, 0, float(p), int(util_block_size), ctypes.byref(best),
+                                         capacity, idx.ctypes.data, pe.ctypes.data, nc.ctypes.data, ctypes.byref(n))
+        if rc == KV_E_OVERFLOW:
+            return None
+        check(rc)
+        m = n.value
+        return best.value, idx[:m].copy(), pe[:m].copy(), nc[:m].copy()
+
+    def scm_best_rules_p2p_state(self, p, util_block_size, packet_capacity):
+        """The multi-rank step over the resident greedy state -> the 4-tuple, or None on overflow."""
+        nb = n_utility_blocks(self.n_kmers_total, util_block_size)
+        if getattr(self, "_p2p_nb", None) != nb:
+            self._p2p_nb, self._p2p_bm, self._p2p_sel = nb, np.empty(nb, dtype=np.float64), np.empty(nb, dtype=np.uint8)
+        capacity, (idx, pe, nc) = self._tie_cap, self._tie_buf
+        best, n, over = ctypes.c_double(0.0), _c_i64(0), ctypes.c_int(0)
+        rc = self._lib.kv_scm_best_rules_p2p(self._h, None, None, 0, 0, float(p), int(util_block_size),
+                                             int(packet_capacity), ctypes.byref(best), capacity, ptr(idx), ptr(pe), ptr(nc),
+                                             ctypes.byref(n), ptr(self._p2p_bm), ptr(self._p2p_sel), ctypes.byref(over))
+        if rc == KV_E_OVERFLOW or (rc == KV_OK and over.value):
             return None
         check(rc)
         m = n.value

@@ -7,6 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 SRC = os.path.join(HERE, "csrc", "kover_b200.cu")
 HDR = os.path.join(ROOT, "include", "kover_b200.h")
+INC = os.path.join(HERE, "csrc", "kv_inflate.cuh")
 LIB = os.path.join(HERE, "libkoverb200.so")
 
 NVCC_FLAGS = [
@@ -30,7 +31,7 @@ def is_stale():
     if not os.path.isfile(LIB):
         return True
     t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(p) > t for p in (SRC, HDR))
+    return any(os.path.getmtime(p) > t for p in (SRC, HDR, INC))
 
 
 def build_native(force=False, verbose=False):

@@ -22,6 +22,7 @@
 #include <cub/device/device_radix_sort.cuh>   // only to order LARGE tie lists (not on the scan path)
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -197,8 +198,23 @@ struct FusedTail {
     unsigned long long *tie_count;              // device tie counter
     TieRec *out;                                // tie records (mapped host memory)
     long long cap;
-    volatile unsigned long long *host;          // mapped host header: [0] best utility bits, [1] tie count, [2] epoch
-    unsigned long long epoch;
+    volatile unsigned long long *host;          // mapped host header: [0] best utility bits, [1] tie count, [2] epoch,
+    unsigned long long epoch;                   //                     [3] status (0 ok, 1 peer timeout, 2 overflow)
+    // mode 2 (one process per GPU): candidates -> packet, the last CTA publishes it into every peer's mailbox over
+    // NVLink, waits for theirs and merges all of them (block maxima, block merge, exact filter) on the device
+    const struct P2PDev *p2p;
+    unsigned long long p2p_seq, timeout_ns;
+    char *packet;                               // local packet: block maxima f64 | PacketHeader | TieRec[packet_cap]
+    long long packet_cap;
+    double *host_bm;                            // mapped host: merged block maxima / selected flags (fallback inputs)
+    uint8_t *host_sel;
+};
+static constexpr int P2P_MAX_WORLD = 64;
+struct P2PDev {                                 // device-resident, written once by kv_p2p_connect
+    char *peer_box[P2P_MAX_WORLD];              // mailbox base of every rank, mapped into this process
+    unsigned long long *peer_flags[P2P_MAX_WORLD];
+    int rank, world;
+    size_t slot_bytes;
 };
 
 struct Scan2Params {
@@ -777,12 +793,155 @@ __device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned 
 
 static constexpr long long FUSED_MAX_BLOCKS = 4096;      // block tables of the tail live in the idle TMA ring
 
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// the sequential block merge of scm.py:270-286 on n_blocks maxima (one thread); fills tol / sel, returns best
+__device__ __forceinline__ double block_merge_seq(const double *bm, double *tol, uint8_t *sel, long long n_blocks) {
+    double best = -INFINITY;
+    long long first = 0;
+    for (long long b = 0; b < n_blocks; ++b) {
+        const double m = bm[b];
+        tol[b] = np_tol_dev(m);
+        uint8_t keep = 0;
+        if (m > best || np_isclose_dev(best, m)) {
+            if (np_isclose_dev(m, best)) {
+                keep = 1;
+            } else {
+                best = m;
+                for (long long q = first; q < b; ++q) sel[q] = 0;
+                first = b;
+                keep = 1;
+            }
+        }
+        sel[b] = keep;
+    }
+    return best;
+}
+
+// Mode 2, last CTA of the rank: publish the local packet into every peer's mailbox (remote stores over NVLink),
+// exchange sequence flags, then merge the packets of all ranks exactly as kv_scm_merge_packets does on the host --
+// element-wise max of the block maxima, the sequential block merge, and the isclose filter of the candidates with
+// u recomputed from the integer counts by the same two rounded operations (scm.py:263-264).
+template <int NT>
+__device__ void p2p_exchange_merge(const Scan2Params &P, double *s_bm, double *s_tol, uint8_t *s_sel,
+                                   unsigned long long t_tail) {
+    const FusedTail &F = P.tail;
+    const P2PDev &X = *F.p2p;
+    const int tid = threadIdx.x;
+    const int world = X.world, parity = (int)(F.p2p_seq & 1ull);
+    __shared__ unsigned long long s_out;
+    __shared__ int s_status;
+    __shared__ double s_best2;
+    const size_t nb_bytes = (size_t)F.n_blocks * 8;
+    const PacketHeader *hdr = reinterpret_cast<const PacketHeader *>(F.packet + nb_bytes);
+    const long long n_rec = min((long long)__ldcg(&hdr->count), F.packet_cap);
+    const size_t n16 = (nb_bytes + sizeof(PacketHeader) + (size_t)n_rec * sizeof(TieRec) + 15) / 16;
+    const uint4 *src = reinterpret_cast<const uint4 *>(F.packet);
+    for (int r = 0; r < world; ++r) {
+        uint4 *dst = reinterpret_cast<uint4 *>(X.peer_box[r] + ((size_t)parity * world + X.rank) * X.slot_bytes);
+        for (size_t i = tid; i < n16; i += NT) dst[i] = __ldcg(src + i);
+    }
+    __shared__ unsigned long long s_stamp[2];    // (kept on chip: a store to host memory here would sit in front of
+    if (tid == 0) {                              //  the system-scope fence below and cost a PCIe round trip)
+        s_out = 0ull;
+        s_status = 0;
+        s_stamp[0] = globaltimer_ns();           // packet published (stores issued), about to exchange flags
+    }
+    __threadfence_system();
+    consumer_bar(NT);
+    if (tid < world) {
+        unsigned long long *f = X.peer_flags[tid] + X.rank;
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(F.p2p_seq) : "memory");
+        const unsigned long long *mine = X.peer_flags[X.rank] + tid;
+        const unsigned long long t0 = globaltimer_ns();
+        unsigned long long v = 0;
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
+            if (v >= F.p2p_seq) break;
+            if (globaltimer_ns() - t0 > F.timeout_ns) {
+                s_status = 1;
+                break;
+            }
+        }
+    }
+    __threadfence_system();
+    consumer_bar(NT);
+    if (tid == 0) s_stamp[1] = globaltimer_ns();    // every peer's packet has arrived
+    const char *box = X.peer_box[X.rank] + (size_t)parity * world * X.slot_bytes;
+    for (long long b = tid; b < F.n_blocks; b += NT) {
+        double m = -INFINITY;
+        for (int r = 0; r < world; ++r) {
+            const double v = __ldcv(reinterpret_cast<const double *>(box + (size_t)r * X.slot_bytes) + b);
+            m = v > m ? v : m;
+        }
+        s_bm[b] = m;
+    }
+    consumer_bar(NT);
+    if (tid == 0) {
+        s_best2 = block_merge_seq(s_bm, s_tol, s_sel, F.n_blocks);
+        for (int r = 0; r < world; ++r) {
+            const PacketHeader *h = reinterpret_cast<const PacketHeader *>(box + (size_t)r * X.slot_bytes + nb_bytes);
+            if ((long long)__ldcv(&h->count) > F.packet_cap && s_status == 0) s_status = 2;
+        }
+    }
+    consumer_bar(NT);
+    if (s_status == 0) {
+        const double inv_ubs = 1.0 / (double)P.ubs;
+        for (int r = 0; r < world; ++r) {
+            const PacketHeader *h = reinterpret_cast<const PacketHeader *>(box + (size_t)r * X.slot_bytes + nb_bytes);
+            const long long cnt = (long long)__ldcv(&h->count);
+            const TieRec *recs = reinterpret_cast<const TieRec *>(h + 1);
+            for (long long i = tid; i < cnt; i += NT) {
+                // (records are 8-byte aligned only: the packet head is n_blocks doubles + a 16-byte header)
+                const unsigned long long *rw = reinterpret_cast<const unsigned long long *>(recs + i);
+                long long idx = (long long)__ldcv(rw);
+                const unsigned long long cnts = __ldcv(rw + 1);
+                const uint32_t pe = (uint32_t)cnts, nc = (uint32_t)(cnts >> 32);
+                const bool ninf = (idx & TIE_FLAG_NEG_INF) != 0;
+                idx &= ~TIE_FLAG_NEG_INF;
+                const long long b = fast_div(idx, P.ubs, inv_ubs);
+                if (b < 0 || b >= F.n_blocks || !s_sel[b]) continue;
+                const double u = ninf ? -INFINITY : __dsub_rn((double)nc, __dmul_rn(P.p, (double)pe));
+                if (!np_isclose_dev(u, s_bm[b])) continue;
+                const unsigned long long slot = atomicAdd(&s_out, 1ull);
+                if ((long long)slot < F.cap) {
+                    TieRec o;
+                    o.idx = idx; o.pe = pe; o.nc = nc;
+                    F.out[slot] = o;
+                }
+            }
+        }
+    }
+    for (long long b = tid; b < F.n_blocks; b += NT) {
+        F.host_bm[b] = s_bm[b];
+        F.host_sel[b] = s_sel[b];
+    }
+    consumer_bar(NT);
+    if (tid == 0) {
+        if (s_status == 0 && (long long)s_out > F.cap) s_status = 2;
+        F.host[0] = (unsigned long long)__double_as_longlong(s_best2);
+        F.host[1] = s_out;
+        F.host[3] = (unsigned long long)s_status;
+        F.host[4] = t_tail;
+        F.host[5] = s_stamp[0];
+        F.host[6] = s_stamp[1];
+        F.host[7] = globaltimer_ns();
+        __threadfence_system();
+        F.host[2] = F.epoch;
+    }
+}
+
 template <int CW>
 __device__ void scm_fused_tail(const Scan2Params &P, long long t0, long long t1, unsigned char *ring) {
     const FusedTail &F = P.tail;
     const int tid = threadIdx.x;
     constexpr int NT = CW * 32;
-    __shared__ double s_best;
+    __shared__ double s_best;               // mode 1: best utility; mode 2: the rank's candidate threshold
+    __shared__ int s_last;
     if (blockIdx.x == 0) {
         for (long long b = tid; b < F.n_blocks; b += NT) F.zero_next[b] = 0ull;
         if (tid == 0) *F.tie_count = 0ull;
@@ -795,39 +954,34 @@ __device__ void scm_fused_tail(const Scan2Params &P, long long t0, long long t1,
         }
     }
     consumer_bar(NT);
-    // every CTA replays the sequential block merge (scm.py:270-286) on the complete maxima: ~20 blocks at config 2
+    // every CTA works on the complete block maxima of this shard: ~20 blocks at config 2
     double *s_bm = reinterpret_cast<double *>(ring);
     double *s_tol = s_bm + F.n_blocks;
     uint8_t *s_sel = reinterpret_cast<uint8_t *>(s_tol + F.n_blocks);
     for (long long b = tid; b < F.n_blocks; b += NT) s_bm[b] = dec_f64_max_dev(__ldcg(P.blockmax + b));
     consumer_bar(NT);
     if (tid == 0) {
-        double best = -INFINITY;
-        long long first = 0;
-        for (long long b = 0; b < F.n_blocks; ++b) {
-            const double m = s_bm[b];
-            s_tol[b] = np_tol_dev(m);
-            uint8_t keep = 0;
-            if (m > best || np_isclose_dev(best, m)) {
-                if (np_isclose_dev(m, best)) {
-                    keep = 1;
-                } else {
-                    best = m;
-                    for (long long q = first; q < b; ++q) s_sel[q] = 0;
-                    first = b;
-                    keep = 1;
-                }
-            }
-            s_sel[b] = keep;
+        if (F.mode == 1) {
+            s_best = block_merge_seq(s_bm, s_tol, s_sel, F.n_blocks);       // scm.py:270-286
+        } else {
+            // this rank only knows ITS maxima: superset threshold (see k_scm_select_local)
+            double lmax = -INFINITY;
+            for (long long b = 0; b < F.n_blocks; ++b) lmax = fmax(lmax, s_bm[b]);
+            s_best = isfinite(lmax) ? lmax - 5.0 * np_tol_dev(lmax) : -INFINITY;
         }
-        s_best = best;
     }
     consumer_bar(NT);
-    if (blockIdx.x == 0) {                       // the tables later phases expect in d_misc (tie-buffer overflow path)
-        for (long long b = tid; b < F.n_blocks; b += NT) {
-            F.bm[b] = s_bm[b];
-            F.tol[b] = s_tol[b];
-            F.sel[b] = s_sel[b];
+    if (blockIdx.x == 0) {
+        if (F.mode == 1) {                       // the tables later phases expect in d_misc (tie-buffer overflow path)
+            for (long long b = tid; b < F.n_blocks; b += NT) {
+                F.bm[b] = s_bm[b];
+                F.tol[b] = s_tol[b];
+                F.sel[b] = s_sel[b];
+            }
+        } else {                                 // the head of the packet: block maxima + threshold
+            double *pk = reinterpret_cast<double *>(F.packet);
+            for (long long b = tid; b < F.n_blocks; b += NT) pk[b] = s_bm[b];
+            if (tid == 0) reinterpret_cast<PacketHeader *>(F.packet + (size_t)F.n_blocks * 8)->threshold = s_best;
         }
     }
     TieParams T;
@@ -849,25 +1003,37 @@ __device__ void scm_fused_tail(const Scan2Params &P, long long t0, long long t1,
     T.tol = s_tol;
     T.sel = s_sel;
     T.count = F.tie_count;
-    T.threshold = nullptr;
-    T.out = F.out;
-    T.cap = F.cap;
+    T.threshold = F.mode == 1 ? nullptr : &s_best;
+    T.out = F.mode == 1 ? F.out : reinterpret_cast<TieRec *>(F.packet + (size_t)F.n_blocks * 8 + sizeof(PacketHeader));
+    T.cap = F.mode == 1 ? F.cap : F.packet_cap;
     const long long n_seg = (P.n_cols + 63) >> 6;
-    const long long seg0 = t0 * (CW * 64 / 64), seg1 = min(t1 * (long long)(CW * 64 / 64), n_seg);
+    const long long seg0 = t0 * (long long)CW, seg1 = min(t1 * (long long)CW, n_seg);
     scm_ties_range(T, seg0, seg1, tid >> 5, CW);
     consumer_bar(NT);
     if (tid == 0) {
-        __threadfence_system();                  // this CTA's tie records (host memory) before its ticket
+        __threadfence_system();                  // this CTA's tie records before its ticket
         const unsigned long long ticket = atomicAdd(F.done, 1ull);
-        if (ticket + 1 == F.done_target) {       // last CTA: publish the result
-            __threadfence();
+        s_last = ticket + 1 == F.done_target;
+        __threadfence();
+    }
+    consumer_bar(NT);
+    if (!s_last) return;
+    __shared__ unsigned long long s_t_last;
+    if (tid == 0) s_t_last = globaltimer_ns();      // the scan and this rank's tie / candidate collection are complete
+    if (F.mode == 1) {
+        if (tid == 0) {                          // last CTA: publish the result
             const unsigned long long found = atomicAdd(F.tie_count, 0ull);
             F.host[0] = (unsigned long long)__double_as_longlong(s_best);
             F.host[1] = found;
+            F.host[3] = 0ull;
+            F.host[4] = s_t_last;
+            F.host[5] = F.host[6] = F.host[7] = globaltimer_ns();
             __threadfence_system();
             F.host[2] = F.epoch;
         }
+        return;
     }
+    p2p_exchange_merge<NT>(P, s_bm, s_tol, s_sel, s_t_last);
 }
 
 // the tie collection of up to QUEUE_BATCH jobs in one launch: blockIdx.y selects the job
@@ -1658,6 +1824,108 @@ __global__ void k_generate(uint64_t *mat, long long ld, long long n_words, long 
 }
 
 // ------------------------------------------------------------------------------------------------
+// k_mask_and_column: the greedy step's example bookkeeping on the device (scm.py:133-139).  After a rule is picked
+// the reference fetches its column and keeps the examples the rule accepts; here the shard keeps the remaining
+// positive / negative example masks resident and ANDs them with the chosen column (presence rule: mask &= column,
+// absence rule: mask &= ~column), counts what is left, and rebuilds the compacted active-row records the scan
+// kernel consumes (rows with only mask 0, only mask 1, both -- ascending row order inside each group).  One CTA:
+// W is a few hundred to a few thousand words.  The counts (and the column words, for the other shards / ranks)
+// go to mapped host memory; the host polls the epoch word.
+// ------------------------------------------------------------------------------------------------
+struct MaskColParams {
+    const uint64_t *mat;             // column source: mat[w * ld + col] when col >= 0,
+    long long ld, col;
+    const uint64_t *words;           // else these W words (device), or null = all ones (state initialisation)
+    int invert;
+    long long W;
+    uint64_t *pos, *neg;             // resident masks [W], updated in place
+    uint64_t *rec_m0, *rec_m1;       // records out [W]
+    uint32_t *rec_row;
+    volatile unsigned long long *host;   // mapped: [0] n_pos [1] n_neg [2] n_act [3] n_both [4] epoch, [8 ..] column words
+    unsigned long long epoch;
+};
+
+__global__ void __launch_bounds__(1024) k_mask_and_column(const MaskColParams P) {
+    __shared__ unsigned int s_cnt[5][32];          // per warp: pos bits, neg bits, rows A, rows B, rows C
+    __shared__ unsigned int s_tot[5];
+    __shared__ unsigned int s_run[3];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned int c_pos = 0, c_neg = 0, nA = 0, nB = 0, nC = 0;
+    for (long long w = tid; w < P.W; w += 1024) {
+        uint64_t c = ~0ull;
+        if (P.col >= 0) c = P.mat[w * P.ld + P.col];
+        else if (P.words) c = P.words[w];
+        if (P.col >= 0 || P.words) P.host[8 + w] = c;                  // the raw column, for the other shards
+        if (P.invert) c = ~c;
+        const uint64_t a = P.pos[w] & c, b = P.neg[w] & c;
+        P.pos[w] = a;
+        P.neg[w] = b;
+        c_pos += __popcll(a);
+        c_neg += __popcll(b);
+        nA += (a != 0 && b == 0);
+        nB += (a == 0 && b != 0);
+        nC += (a != 0 && b != 0);
+    }
+    unsigned int v[5] = {c_pos, c_neg, nA, nB, nC};
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+        v[q] = __reduce_add_sync(0xffffffffu, v[q]);
+        if (lane == 0) s_cnt[q][warp] = v[q];
+    }
+    __syncthreads();
+    if (tid < 5) {
+        unsigned int t = 0;
+        for (int w = 0; w < 32; ++w) t += s_cnt[tid][w];
+        s_tot[tid] = t;
+    }
+    if (tid < 3) s_run[tid] = 0;
+    __syncthreads();
+    const unsigned int base[3] = {0u, s_tot[2], s_tot[2] + s_tot[3]};
+    // second pass: positions inside the three groups, 1024 rows at a time, ascending rows
+    for (long long w0 = 0; w0 < P.W; w0 += 1024) {
+        const long long w = w0 + tid;
+        uint64_t a = 0, b = 0;
+        if (w < P.W) {
+            a = P.pos[w];
+            b = P.neg[w];
+        }
+        const int cat = (a != 0 && b != 0) ? 2 : (a != 0 ? 0 : (b != 0 ? 1 : -1));
+        unsigned int before[3], wtot[3];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            const unsigned int m = __ballot_sync(0xffffffffu, cat == q);
+            before[q] = __popc(m & ((1u << lane) - 1u));
+            wtot[q] = __popc(m);
+            if (lane == 0) s_cnt[q][warp] = wtot[q];
+        }
+        __syncthreads();
+        if (cat >= 0) {
+            unsigned int off = s_run[cat];
+            for (int ww = 0; ww < warp; ++ww) off += s_cnt[cat][ww];
+            const unsigned int i = base[cat] + off + before[cat];
+            P.rec_m0[i] = a;
+            P.rec_m1[i] = b;
+            P.rec_row[i] = (uint32_t)w;
+        }
+        __syncthreads();
+        if (tid < 3) {
+            unsigned int t = 0;
+            for (int ww = 0; ww < 32; ++ww) t += s_cnt[tid][ww];
+            s_run[tid] += t;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        P.host[0] = s_tot[0];
+        P.host[1] = s_tot[1];
+        P.host[2] = s_tot[2] + s_tot[3] + s_tot[4];
+        P.host[3] = s_tot[4];
+        __threadfence_system();
+        P.host[4] = P.epoch;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // shard
 // ------------------------------------------------------------------------------------------------
 struct DevBuf {
@@ -1669,6 +1937,8 @@ struct kv_p2p;
 static void p2p_destroy(kv_p2p *m);
 struct kv_shard;
 static int finish_scan_timing(kv_shard *s);
+struct Scan2Params;
+static void fill_scan2_state(kv_shard *s, Scan2Params &P);
 
 struct kv_shard {
     kv_p2p *p2p = nullptr;                    // peer mailbox (multi-rank), optional
@@ -1715,6 +1985,13 @@ struct kv_shard {
     long long fused_n_blocks = -1;
     unsigned long long fused_epoch = 0, fused_barrier_total = 0, fused_done_total = 0;
     std::vector<uint64_t> h_masks;            // masks built from index arrays (kv_scm_best_rules_idx)
+    // device-resident greedy state (kv_scm_state_set / kv_mask_and_column)
+    uint64_t *d_state = nullptr;              // pos [W] | neg [W] | column words [W] | rec m0 [W] | rec m1 [W] | rec row u32 [W]
+    void *h_state = nullptr;                  // mapped page-locked: 64-byte header + column words [W]
+    unsigned long long state_epoch = 0;
+    bool state_valid = false;
+    long long state_n_pos = 0, state_n_neg = 0;
+    int state_n_act = 0, state_n_both = 0;
     bool profiling = false;                   // CUDA events around the scan kernels (kv_set_profiling / KOVER_B200_PROFILE)
     DevBuf d_level;                           // kv_gini_level: per-node minima, counters, tie slots, segment minima
     std::vector<uint32_t *> occ_tables;       // kv_occ_table_set: k-mer occurrence counts of a training set, [ld] each
@@ -1722,6 +1999,8 @@ struct kv_shard {
     size_t h_level_cap = 0, h_level_used = 0; // in entries
     std::vector<std::pair<size_t, size_t>> level_span;   // (offset, count) of every node in the arena
 
+    double exch_publish_us = 0.0, exch_wait_us = 0.0, exch_merge_us = 0.0;   // fused multi-rank tail, summed over steps
+    long long exch_steps = 0;
     double last_kernel_ms = 0.0, scan_ms_total = 0.0;
     long long last_launches = 0, total_launches = 0, scan_calls = 0, rescore_calls = 0;
 };
@@ -1844,6 +2123,8 @@ extern "C" int kv_destroy(kv_shard *s) {
     if (s->h_pin) cudaFreeHost(s->h_pin);
     if (s->h_level) cudaFreeHost(s->h_level);
     if (s->h_fused) cudaFreeHost(s->h_fused);
+    if (s->h_state) cudaFreeHost(s->h_state);
+    if (s->d_state) cudaFree(s->d_state);
     if (s->d_fused_ctr) cudaFree(s->d_fused_ctr);
     if (s->d_fused_bm) cudaFree(s->d_fused_bm);
     for (int i = 0; i < 2; ++i) {
@@ -1876,6 +2157,10 @@ extern "C" int kv_get_info(kv_shard *s, kv_shard_info *o) {
     o->scan_ms_total = s->scan_ms_total;
     o->scan_calls = s->scan_calls;
     o->rescore_calls = s->rescore_calls;
+    o->exch_steps = s->exch_steps;
+    o->exch_publish_us = s->exch_publish_us;
+    o->exch_wait_us = s->exch_wait_us;
+    o->exch_merge_us = s->exch_merge_us;
     return KV_OK;
 }
 
@@ -1971,6 +2256,225 @@ extern "C" int kv_upload_block(kv_shard *s, int pack_bits, int64_t row0, int64_t
     CU(cudaStreamSynchronize(s->stream));
     CU(cudaGetLastError());
     s->scm_valid = s->gini_valid = false;
+    return KV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// upload of gzip-filtered HDF5 chunks, inflated on the device (kv_inflate.cuh)
+// ------------------------------------------------------------------------------------------------
+#include "kv_inflate.cuh"
+
+namespace {
+struct DeflateUploader {
+    static constexpr int kSlots = 4;
+    cudaStream_t copy_stream = nullptr;
+    void *pin[kSlots] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t pin_free[kSlots] = {nullptr, nullptr, nullptr, nullptr};
+    size_t slot_bytes = 0;
+    unsigned char *d_comp[2] = {nullptr, nullptr}, *d_scratch[2] = {nullptr, nullptr};
+    InflateJob *d_jobs[2] = {nullptr, nullptr};
+    ScatterJob *d_sjobs[2] = {nullptr, nullptr};
+    int *d_status = nullptr;
+    unsigned int *d_next = nullptr;
+    cudaEvent_t copied[2] = {nullptr, nullptr}, done[2] = {nullptr, nullptr};
+    ~DeflateUploader() {
+        for (int i = 0; i < 2; ++i) {
+            if (d_comp[i]) cudaFree(d_comp[i]);
+            if (d_scratch[i]) cudaFree(d_scratch[i]);
+            if (d_jobs[i]) cudaFree(d_jobs[i]);
+            if (d_sjobs[i]) cudaFree(d_sjobs[i]);
+            if (copied[i]) cudaEventDestroy(copied[i]);
+            if (done[i]) cudaEventDestroy(done[i]);
+        }
+        if (d_status) cudaFree(d_status);
+        if (d_next) cudaFree(d_next);
+        for (int i = 0; i < kSlots; ++i) {
+            if (pin[i]) cudaFreeHost(pin[i]);
+            if (pin_free[i]) cudaEventDestroy(pin_free[i]);
+        }
+        if (copy_stream) cudaStreamDestroy(copy_stream);
+    }
+};
+
+// copy `n` byte ranges (src[i], bytes[i]) to dst + off[i] with a few threads (page cache -> pinned memory)
+void gather_streams(char *dst, const void *const *src, const int64_t *bytes, const size_t *off, int64_t i0, int64_t i1) {
+    const unsigned hw = std::thread::hardware_concurrency();
+    static const unsigned max_threads =
+        getenv("KOVER_B200_UPLOAD_THREADS") ? (unsigned)atoi(getenv("KOVER_B200_UPLOAD_THREADS")) : 8u;
+    size_t total = 0;
+    for (int64_t i = i0; i < i1; ++i) total += (size_t)bytes[i];
+    const int n_threads = total < ((size_t)2 << 20) ? 1 : (int)std::max(1u, std::min(hw ? hw : 1u, std::max(1u, max_threads)));
+    auto work = [&](int t) {
+        for (int64_t i = i0 + t; i < i1; i += n_threads) memcpy(dst + off[i], src[i], (size_t)bytes[i]);
+    };
+    if (n_threads == 1) {
+        work(0);
+        return;
+    }
+    std::vector<std::thread> pool;
+    for (int t = 0; t < n_threads; ++t) pool.emplace_back(work, t);
+    for (auto &th : pool) th.join();
+}
+}   // namespace
+
+extern "C" int kv_upload_deflate(kv_shard *s, int pack_bits, int64_t n_chunks, const void *const *src,
+                                 const int64_t *src_bytes, const int64_t *row0, const int64_t *gcol0,
+                                 int64_t chunk_rows, int64_t chunk_cols, int32_t *status) {
+    if (!s || (n_chunks > 0 && (!src || !src_bytes || !row0 || !gcol0 || !status)))
+        return fail(KV_E_INVALID, "kv_upload_deflate: null pointer");
+    if (pack_bits != 64 && pack_bits != 32)
+        return fail(KV_E_INVALID, "Unsupported data type for packed attribute classifications array. The supported "
+                                  "data types are np.uint32 and np.uint64.");
+    if (n_chunks < 0 || chunk_rows <= 0 || chunk_cols <= 0 || chunk_rows > 0x7FFFFFFF)
+        return fail(KV_E_INVALID, "kv_upload_deflate: bad chunk shape / count");
+    if (n_chunks == 0) return KV_OK;
+    const size_t esz = (size_t)pack_bits / 8;
+    const size_t chunk_bytes = (size_t)chunk_rows * (size_t)chunk_cols * esz;
+    if (chunk_bytes >= ((size_t)1 << 31)) return fail(KV_E_INVALID, "kv_upload_deflate: chunk larger than 2 GB");
+    const long long rows_total = pack_bits == 64 ? s->W : (s->n_examples + 31) / 32;
+    for (int64_t i = 0; i < n_chunks; ++i) {
+        if (!src[i] || src_bytes[i] < 6 || src_bytes[i] >= ((int64_t)1 << 31) || row0[i] < 0 || gcol0[i] < 0)
+            return fail(KV_E_INVALID, "kv_upload_deflate: bad chunk descriptor");
+    }
+    DeviceGuard g(s->device);
+    s->last_launches = 0;
+    s->scm_valid = s->gini_valid = false;
+    static const bool stats = getenv("KOVER_B200_INFLATE_STATS") != nullptr;      // phase times on stderr
+    const auto now = [] { return std::chrono::steady_clock::now(); };
+    const auto ms_since = [](std::chrono::steady_clock::time_point t0) {
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    };
+    const auto t_begin = now();
+    double t_gather = 0.0;
+    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;
+    if (stats) {
+        cudaEventCreate(&ev_k0);
+        cudaEventCreate(&ev_k1);
+    }
+    DeflateUploader U;
+    // decode slabs: enough chunks to occupy every SM, bounded by a quarter of the free HBM for the two scratch parities
+    const size_t chunk_stride = (chunk_bytes + 15) / 16 * 16;
+    size_t free_b = 0, total_b = 0;
+    CU(cudaMemGetInfo(&free_b, &total_b));
+    int64_t slab = std::min<int64_t>(n_chunks, 4096);
+    while (slab > 64 && (size_t)slab * chunk_stride * 4 > free_b / 4) slab /= 2;
+    size_t max_comp = 0;
+    for (int64_t a = 0; a < n_chunks; a += slab) {
+        size_t c = 0;
+        for (int64_t i = a; i < std::min(n_chunks, a + slab); ++i) c += ((size_t)src_bytes[i] + 4 + 15) / 16 * 16;
+        max_comp = std::max(max_comp, c);
+    }
+    U.slot_bytes = (size_t)16 << 20;
+    size_t biggest = 0;
+    for (int64_t i = 0; i < n_chunks; ++i) biggest = std::max(biggest, ((size_t)src_bytes[i] + 4 + 15) / 16 * 16);
+    U.slot_bytes = std::max(U.slot_bytes, biggest);
+    CU(cudaStreamCreateWithFlags(&U.copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < DeflateUploader::kSlots; ++i) {
+        CU(cudaMallocHost(&U.pin[i], U.slot_bytes));
+        CU(cudaEventCreateWithFlags(&U.pin_free[i], cudaEventDisableTiming));
+    }
+    const int n_par = n_chunks > slab ? 2 : 1;
+    for (int i = 0; i < n_par; ++i) {
+        CU(cudaMalloc(&U.d_comp[i], max_comp + 64));
+        CU(cudaMalloc(&U.d_scratch[i], (size_t)slab * chunk_stride));
+        CU(cudaMalloc(&U.d_jobs[i], (size_t)slab * sizeof(InflateJob)));
+        CU(cudaMalloc(&U.d_sjobs[i], (size_t)slab * sizeof(ScatterJob)));
+        CU(cudaEventCreateWithFlags(&U.copied[i], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&U.done[i], cudaEventDisableTiming));
+    }
+    CU(cudaMalloc(&U.d_status, (size_t)n_chunks * sizeof(int)));
+    CU(cudaMalloc(&U.d_next, ((size_t)(n_chunks + slab - 1) / slab) * sizeof(unsigned int)));
+    CU(cudaMemsetAsync(U.d_status, 0xFF, (size_t)n_chunks * sizeof(int), s->stream));
+    CU(cudaMemsetAsync(U.d_next, 0, ((size_t)(n_chunks + slab - 1) / slab) * sizeof(unsigned int), s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    const double t_setup = ms_since(t_begin);
+    float t_kernels = 0.f;
+    std::vector<InflateJob> jobs((size_t)slab);
+    std::vector<ScatterJob> sjobs((size_t)slab);
+    std::vector<size_t> off((size_t)n_chunks);
+    int slot = 0;
+    int64_t slab_no = 0;
+    for (int64_t a = 0; a < n_chunks; a += slab, ++slab_no) {
+        const int64_t b = std::min(n_chunks, a + slab);
+        const int par = (int)(slab_no & 1) % n_par;
+        if (slab_no >= 2) CU(cudaStreamWaitEvent(U.copy_stream, U.done[par], 0));     // the buffers of slab - 2 are free again
+        // layout of the slab's streams in the device buffer, and of its output in the scratch
+        size_t c = 0;
+        for (int64_t i = a; i < b; ++i) {
+            off[(size_t)i] = c;
+            InflateJob &J = jobs[(size_t)(i - a)];
+            J.src_off = c;
+            J.src_bytes = (unsigned int)src_bytes[i];
+            J.dst_bytes = (unsigned int)chunk_bytes;
+            J.dst_off = (size_t)(i - a) * chunk_stride;
+            ScatterJob &Q = sjobs[(size_t)(i - a)];
+            Q.src_off = J.dst_off;
+            Q.row0 = row0[i];
+            Q.gcol0 = gcol0[i];
+            Q.ok = 1;
+            c += ((size_t)src_bytes[i] + 4 + 15) / 16 * 16;
+        }
+        // stream the compressed bytes through the pinned slots: whole chunks per slot
+        int64_t i = a;
+        while (i < b) {
+            const size_t base = off[(size_t)i];
+            int64_t j = i;
+            while (j < b && off[(size_t)j] + ((size_t)src_bytes[j] + 4 + 15) / 16 * 16 - base <= U.slot_bytes) ++j;
+            CU(cudaEventSynchronize(U.pin_free[slot]));
+            std::vector<size_t> rel((size_t)(j - i));
+            for (int64_t q = i; q < j; ++q) rel[(size_t)(q - i)] = off[(size_t)q] - base;
+            const auto t_g = now();
+            gather_streams((char *)U.pin[slot], src + i, src_bytes + i, rel.data(), 0, j - i);
+            t_gather += ms_since(t_g);
+            const size_t span = (j < b ? off[(size_t)j] : c) - base;
+            CU(cudaMemcpyAsync(U.d_comp[par] + base, U.pin[slot], span, cudaMemcpyHostToDevice, U.copy_stream));
+            CU(cudaEventRecord(U.pin_free[slot], U.copy_stream));
+            slot = (slot + 1) % DeflateUploader::kSlots;
+            i = j;
+        }
+        CU(cudaMemcpyAsync(U.d_jobs[par], jobs.data(), (size_t)(b - a) * sizeof(InflateJob), cudaMemcpyHostToDevice, U.copy_stream));
+        CU(cudaMemcpyAsync(U.d_sjobs[par], sjobs.data(), (size_t)(b - a) * sizeof(ScatterJob), cudaMemcpyHostToDevice, U.copy_stream));
+        CU(cudaEventRecord(U.copied[par], U.copy_stream));
+        CU(cudaStreamSynchronize(U.copy_stream));            // `jobs` / `sjobs` are reused by the next slab
+        CU(cudaStreamWaitEvent(s->stream, U.copied[par], 0));
+        const int n_here = (int)(b - a);
+        const int grid = (int)std::min<long long>((n_here + INF_WARPS - 1) / INF_WARPS, (long long)s->sm_count * 6);
+        if (stats) cudaEventRecord(ev_k0, s->stream);
+        k_inflate<<<grid, INF_WARPS * 32, 0, s->stream>>>(U.d_comp[par], U.d_scratch[par], U.d_jobs[par], n_here,
+                                                          U.d_status + a, U.d_next + slab_no);
+        if (stats) {
+            cudaEventRecord(ev_k1, s->stream);
+            cudaEventSynchronize(ev_k1);
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ev_k0, ev_k1);
+            t_kernels += ms;
+        }
+        const long long per_chunk = (long long)chunk_rows * chunk_cols;
+        const dim3 sgrid((unsigned)std::min<long long>((per_chunk + 255) / 256, 64), (unsigned)n_here);
+        // (a failed chunk is scattered too and re-done by the caller: its rows are overwritten then)
+        if (pack_bits == 64)
+            k_scatter_chunks<uint64_t><<<sgrid, 256, 0, s->stream>>>(U.d_scratch[par], U.d_sjobs[par], s->d_mat, s->ld, s->col0,
+                                                                     s->n_cols, rows_total, s->k_total, (int)chunk_rows, chunk_cols);
+        else
+            k_scatter_chunks<uint32_t><<<sgrid, 256, 0, s->stream>>>(U.d_scratch[par], U.d_sjobs[par], s->d_mat, s->ld, s->col0,
+                                                                     s->n_cols, rows_total, s->k_total, (int)chunk_rows, chunk_cols);
+        count_launch(s, 2);
+        CU(cudaEventRecord(U.done[par], s->stream));
+    }
+    static_assert(sizeof(int) == sizeof(int32_t), "status array");
+    CU(cudaMemcpyAsync(status, U.d_status, (size_t)n_chunks * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    CU(cudaGetLastError());
+    if (stats) {
+        size_t comp = 0;
+        for (int64_t q = 0; q < n_chunks; ++q) comp += (size_t)src_bytes[q];
+        fprintf(stderr, "kv_upload_deflate: %lld chunks (%.1f MB deflated -> %.1f MB), slabs of %lld: setup %.1f ms, "
+                        "gather %.1f ms, inflate kernels %.1f ms (serialised for this report), total %.1f ms\n",
+                (long long)n_chunks, comp / 1e6, (double)n_chunks * chunk_bytes / 1e6, (long long)slab, t_setup, t_gather,
+                t_kernels, ms_since(t_begin));
+        cudaEventDestroy(ev_k0);
+        cudaEventDestroy(ev_k1);
+    }
     return KV_OK;
 }
 
@@ -2715,11 +3219,20 @@ static int scm_scan_async(kv_shard *s, const uint64_t *pos_mask, const uint64_t 
         s->scm_swapped = swapped;
         s->rescore_calls += 1;
     } else {
-        if (!pos_mask || !neg_mask) return fail(KV_E_INVALID, "kv_scm_scan: null mask");
+        if ((pos_mask == nullptr) != (neg_mask == nullptr)) return fail(KV_E_INVALID, "kv_scm_scan: null mask");
         int n_act, n_both;
-        KV_TRY(push_records2(s, pos_mask, neg_mask, n_act, n_both));
         Scan2Params P;
-        fill_scan2(s, P, n_act);
+        if (!pos_mask) {                                         // the device-resident greedy state
+            if (!s->state_valid) return fail(KV_E_INVALID, "kv_scm_scan: no greedy state on the device (kv_scm_state_set)");
+            n_act = s->state_n_act;
+            n_both = s->state_n_both;
+            n_pos = s->state_n_pos;
+            n_neg = s->state_n_neg;
+            fill_scan2_state(s, P);
+        } else {
+            KV_TRY(push_records2(s, pos_mask, neg_mask, n_act, n_both));
+            fill_scan2(s, P, n_act);
+        }
         P.cnt0 = s->d_cnt[0];
         P.cnt1 = s->d_cnt[1];
         P.p = p;
@@ -2928,13 +3441,130 @@ extern "C" int kv_scm_ties(kv_shard *s, const double *block_max, const uint8_t *
     return scm_collect_ties(s, n_blocks, capacity, nullptr, rule_idx, pos_err, neg_cover, n_found);
 }
 
+// ---- device-resident greedy state --------------------------------------------------------------------------------
+static int ensure_state(kv_shard *s) {
+    if (s->d_state) return KV_OK;
+    const size_t W = (size_t)s->W;
+    CU(cudaMalloc(&s->d_state, W * 8 * 5 + W * 4 + 64));
+    CU(cudaMemset(s->d_state, 0, W * 8 * 5 + W * 4 + 64));
+    CU(cudaHostAlloc(&s->h_state, 64 + W * 8, cudaHostAllocMapped));
+    memset(s->h_state, 0, 64 + W * 8);
+    CU(cudaDeviceSynchronize());
+    return KV_OK;
+}
+
+// launch k_mask_and_column and wait for its epoch word; fills the shard's state counters
+static int run_mask_kernel(kv_shard *s, long long col, const uint64_t *d_words, int invert) {
+    const long long W = s->W;
+    MaskColParams M;
+    memset(&M, 0, sizeof M);
+    M.mat = s->d_mat;
+    M.ld = s->ld;
+    M.col = col;
+    M.words = d_words;
+    M.invert = invert;
+    M.W = W;
+    M.pos = s->d_state;
+    M.neg = s->d_state + W;
+    M.rec_m0 = s->d_state + 3 * W;
+    M.rec_m1 = s->d_state + 4 * W;
+    M.rec_row = (uint32_t *)(s->d_state + 5 * W);
+    M.host = (volatile unsigned long long *)s->h_state;
+    M.epoch = ++s->state_epoch;
+    k_mask_and_column<<<1, 1024, 0, s->stream>>>(M);
+    count_launch(s);
+    volatile unsigned long long *h = (volatile unsigned long long *)s->h_state;
+    unsigned spins = 0;
+    while (h[4] != M.epoch) {
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+        if ((++spins & 0x7FF) == 0) {
+            const cudaError_t e = cudaStreamQuery(s->stream);
+            if (e == cudaErrorNotReady) continue;
+            if (h[4] == M.epoch) break;
+            if (e == cudaSuccess) return fail(KV_E_CUDA, "k_mask_and_column retired without publishing its result");
+            CU(e);
+        }
+    }
+    __atomic_thread_fence(__ATOMIC_ACQUIRE);
+    s->state_n_pos = (long long)h[0];
+    s->state_n_neg = (long long)h[1];
+    s->state_n_act = (int)h[2];
+    s->state_n_both = (int)h[3];
+    s->state_valid = true;
+    return KV_OK;
+}
+
+extern "C" int kv_scm_state_set(kv_shard *s, const uint64_t *pos_mask, const uint64_t *neg_mask, int64_t *n_pos,
+                                int64_t *n_neg) {
+    if (!s || !pos_mask || !neg_mask) return fail(KV_E_INVALID, "kv_scm_state_set: null pointer");
+    DeviceGuard g(s->device);
+    s->last_launches = 0;
+    KV_TRY(ensure_state(s));
+    const size_t W = (size_t)s->W;
+    KV_TRY(ensure_pinned(s, 2 * W * 8));
+    CU(cudaStreamSynchronize(s->stream));                       // an in-flight copy may still read h_pin
+    memcpy(s->h_pin, pos_mask, W * 8);
+    memcpy((char *)s->h_pin + W * 8, neg_mask, W * 8);
+    CU(cudaMemcpyAsync(s->d_state, s->h_pin, 2 * W * 8, cudaMemcpyHostToDevice, s->stream));
+    KV_TRY(run_mask_kernel(s, -1, nullptr, 0));
+    if (n_pos) *n_pos = s->state_n_pos;
+    if (n_neg) *n_neg = s->state_n_neg;
+    return KV_OK;
+}
+
+extern "C" int kv_mask_and_column(kv_shard *s, int64_t local_col, const uint64_t *col_words_in, int invert,
+                                  uint64_t *col_words_out, int64_t *n_pos, int64_t *n_neg) {
+    if (!s) return fail(KV_E_INVALID, "kv_mask_and_column: null shard");
+    if (!s->state_valid) return fail(KV_E_INVALID, "kv_mask_and_column: no greedy state on the device (kv_scm_state_set)");
+    if (local_col >= s->n_cols) return fail(KV_E_INVALID, "kv_mask_and_column: column outside the shard");
+    if (local_col < 0 && !col_words_in) return fail(KV_E_INVALID, "kv_mask_and_column: neither a column nor its words");
+    DeviceGuard g(s->device);
+    s->last_launches = 0;
+    const size_t W = (size_t)s->W;
+    uint64_t *d_words = nullptr;
+    if (local_col < 0) {
+        KV_TRY(ensure_pinned(s, W * 8));
+        CU(cudaStreamSynchronize(s->stream));
+        memcpy(s->h_pin, col_words_in, W * 8);
+        d_words = s->d_state + 2 * W;
+        CU(cudaMemcpyAsync(d_words, s->h_pin, W * 8, cudaMemcpyHostToDevice, s->stream));
+    }
+    KV_TRY(run_mask_kernel(s, local_col < 0 ? -1 : local_col, d_words, invert != 0));
+    if (col_words_out) memcpy(col_words_out, (const char *)s->h_state + 64, W * 8);
+    if (n_pos) *n_pos = s->state_n_pos;
+    if (n_neg) *n_neg = s->state_n_neg;
+    return KV_OK;
+}
+
+// scan parameters over the resident greedy state's records (device memory)
+static void fill_scan2_state(kv_shard *s, Scan2Params &P) {
+    const long long W = s->W;
+    memset(&P, 0, sizeof P);
+    P.mat = s->d_mat;
+    P.ld = s->ld;
+    P.n_cols = s->n_cols;
+    P.col0 = s->col0;
+    P.k_total = s->k_total;
+    P.n_act = s->state_n_act;
+    P.l2_hints = s->l2_hints;
+    P.inline_rec = 0;
+    P.rec_m0 = s->d_state + 3 * W;
+    P.rec_m1 = s->d_state + 4 * W;
+    P.rec_row = (const uint32_t *)(s->d_state + 5 * W);
+    P.ubs = 1;
+}
+
 // ---- the single-shard step in ONE launch (FusedTail) -------------------------------------------------------------
 static constexpr long long kFusedCap = 4096;                 // tie records the mapped result buffer holds
 static constexpr size_t kFusedHdrBytes = 64;
 
 static int ensure_fused(kv_shard *s, int64_t n_blocks) {
     if (!s->h_fused) {
-        CU(cudaHostAlloc(&s->h_fused, kFusedHdrBytes + (size_t)kFusedCap * sizeof(TieRec), cudaHostAllocMapped));
+        // header | tie records | merged block maxima | selected flags (the last two: multi-rank mode)
+        CU(cudaHostAlloc(&s->h_fused, kFusedHdrBytes + (size_t)kFusedCap * sizeof(TieRec) + (size_t)FUSED_MAX_BLOCKS * 9,
+                         cudaHostAllocMapped));
         memset(s->h_fused, 0, kFusedHdrBytes);
         CU(cudaMalloc(&s->d_fused_ctr, 3 * 128));
         CU(cudaMemset(s->d_fused_ctr, 0, 3 * 128));
@@ -2954,10 +3584,18 @@ static int ensure_fused(kv_shard *s, int64_t n_blocks) {
 
 // scan + block merge + tie collection in one kernel, results through mapped host memory: one launch, no copy, the
 // host polls the epoch flag the last CTA writes.  Falls back to the tie kernel when more than kFusedCap rules tie.
+struct P2PTail {                 // what the multi-rank variant of the fused step adds
+    const P2PDev *dev;
+    unsigned long long seq, timeout_ns;
+    char *packet;
+    long long packet_cap;
+    int status = 0;              // out: 0 ok, 1 peer timeout, 2 packet / result overflow
+};
+
 static int scm_best_rules_fused(kv_shard *s, const uint64_t *pos_mask, const uint64_t *neg_mask, int64_t n_pos,
                                 int64_t n_neg, double p, int64_t ubs, int64_t n_blocks, double *best_utility,
                                 int64_t capacity, int64_t *rule_idx, int64_t *pos_err, int64_t *neg_cover,
-                                int64_t *n_found) {
+                                int64_t *n_found, P2PTail *p2p_tail = nullptr) {
     if (n_pos < 0 || n_neg < 0 || n_pos > s->n_examples || n_neg > s->n_examples)
         return fail(KV_E_INVALID, "kv_scm_scan: n_pos / n_neg out of range");
     KV_TRY(ensure_fused(s, n_blocks));
@@ -2970,9 +3608,18 @@ static int scm_best_rules_fused(kv_shard *s, const uint64_t *pos_mask, const uin
     }
     const MiscLayout L = misc_layout(s->d_misc.p, n_blocks);
     int n_act, n_both;
-    KV_TRY(push_records2(s, pos_mask, neg_mask, n_act, n_both));
     Scan2Params P;
-    fill_scan2(s, P, n_act);
+    if (!pos_mask) {                                             // the device-resident greedy state
+        if (!s->state_valid) return fail(KV_E_INVALID, "kv_scm_best_rules: no greedy state on the device (kv_scm_state_set)");
+        n_act = s->state_n_act;
+        n_both = s->state_n_both;
+        n_pos = s->state_n_pos;
+        n_neg = s->state_n_neg;
+        fill_scan2_state(s, P);
+    } else {
+        KV_TRY(push_records2(s, pos_mask, neg_mask, n_act, n_both));
+        fill_scan2(s, P, n_act);
+    }
     P.cnt0 = s->d_cnt[0];
     P.cnt1 = s->d_cnt[1];
     P.p = p;
@@ -2999,6 +3646,17 @@ static int scm_best_rules_fused(kv_shard *s, const uint64_t *pos_mask, const uin
     F.cap = kFusedCap;
     F.host = (volatile unsigned long long *)s->h_fused;
     F.epoch = epoch;
+    if (p2p_tail) {                                               // one process per GPU: exchange + merge on the device
+        F.mode = 2;
+        F.p2p = p2p_tail->dev;
+        F.p2p_seq = p2p_tail->seq;
+        F.timeout_ns = p2p_tail->timeout_ns;
+        F.packet = p2p_tail->packet;
+        F.packet_cap = p2p_tail->packet_cap;
+        F.tie_count = &((PacketHeader *)(p2p_tail->packet + (size_t)n_blocks * 8))->count;
+        F.host_bm = (double *)((char *)s->h_fused + kFusedHdrBytes + (size_t)kFusedCap * sizeof(TieRec));
+        F.host_sel = (uint8_t *)(F.host_bm + FUSED_MAX_BLOCKS);
+    }
     KV_TRY(launch_scan<EPI_SCM>(s, P, n_both));
     s->scm_cnt_a = s->d_cnt[0];
     s->scm_cnt_b = s->d_cnt[1];
@@ -3035,6 +3693,14 @@ static int scm_best_rules_fused(kv_shard *s, const uint64_t *pos_mask, const uin
     if (s->profiling) {
         CU(cudaStreamSynchronize(s->stream));
         KV_TRY(finish_scan_timing(s));
+    }
+    if (p2p_tail) {
+        s->exch_publish_us += (double)(h[5] - h[4]) * 1e-3;      // device globaltimer stamps of the last CTA
+        s->exch_wait_us += (double)(h[6] - h[5]) * 1e-3;
+        s->exch_merge_us += (double)(h[7] - h[6]) * 1e-3;
+        s->exch_steps += 1;
+        p2p_tail->status = (int)h[3];
+        if (p2p_tail->status != 0) return KV_OK;                  // the caller reports the timeout / redoes in two phases
     }
     if (found > kFusedCap) {
         // a huge equivalent-rule set: the counts, segment maxima and block tables are resident -- tie kernel + device sort
@@ -3076,7 +3742,7 @@ extern "C" int kv_scm_best_rules(kv_shard *s, const uint64_t *pos_mask, const ui
     DeviceGuard g(s->device);
     s->last_launches = 0;
     if (s->fused && !s->reuse_armed && n_blocks <= FUSED_MAX_BLOCKS) {
-        if (!pos_mask || !neg_mask) return fail(KV_E_INVALID, "kv_scm_scan: null mask");
+        if ((pos_mask == nullptr) != (neg_mask == nullptr)) return fail(KV_E_INVALID, "kv_scm_scan: null mask");
         return scm_best_rules_fused(s, pos_mask, neg_mask, n_pos, n_neg, p, util_block_size, n_blocks, best_utility,
                                     capacity, rule_idx, pos_err, neg_cover, n_found);
     }
@@ -3575,7 +4241,6 @@ static int merge_packets_strided(const void *rows, size_t stride, int64_t n_pack
 // kernel does both, so the host synchronises once per step and no NCCL call sits on the step's path.
 // (Ranks run on different GPUs; never use this with several ranks time-slicing one GPU.)
 // ------------------------------------------------------------------------------------------------
-static constexpr int P2P_MAX_WORLD = 64;
 struct P2PParams {
     char *peer_box[P2P_MAX_WORLD];        // mailbox base of every rank, mapped into this process
     unsigned long long *peer_flags[P2P_MAX_WORLD];
@@ -3587,12 +4252,6 @@ struct P2PParams {
     int *error;                           // device int: 1 = timed out waiting for a peer
     unsigned long long timeout_ns;
 };
-
-__device__ __forceinline__ unsigned long long globaltimer_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
 
 __global__ void __launch_bounds__(256) k_p2p_publish_wait(const P2PParams P) {
     // bytes worth sending: block maxima + header + the records actually present
@@ -3640,6 +4299,7 @@ struct kv_p2p {
     int *d_error = nullptr;
     unsigned long long seq = 0;
     void *h_rows = nullptr;                // pinned: gathered rows of one parity
+    P2PDev *d_dev = nullptr;               // the peer table for the fused step (device copy)
 };
 
 extern "C" int kv_p2p_create(kv_shard *s, int rank, int world, int64_t slot_bytes, void *ipc_handle_out) {
@@ -3685,6 +4345,17 @@ extern "C" int kv_p2p_connect(kv_shard *s, const void *all_handles) {
         m->peer_box[r] = (char *)ptr;
         m->opened[r] = true;
     }
+    P2PDev dev;
+    memset(&dev, 0, sizeof dev);
+    for (int r = 0; r < m->world; ++r) {
+        dev.peer_box[r] = m->peer_box[r];
+        dev.peer_flags[r] = (unsigned long long *)(m->peer_box[r] + m->flags_off + 256);
+    }
+    dev.rank = m->rank;
+    dev.world = m->world;
+    dev.slot_bytes = m->slot_bytes;
+    if (!m->d_dev) CU(cudaMalloc(&m->d_dev, sizeof(P2PDev)));
+    CU(cudaMemcpy(m->d_dev, &dev, sizeof dev, cudaMemcpyHostToDevice));
     return KV_OK;
 }
 
@@ -3695,6 +4366,7 @@ static void p2p_destroy(kv_p2p *m) {
     cudaFree(m->box);
     cudaFree(m->d_packet);
     cudaFree(m->d_error);
+    if (m->d_dev) cudaFree(m->d_dev);
     if (m->h_rows) cudaFreeHost(m->h_rows);
     delete m;
 }
@@ -3714,6 +4386,34 @@ extern "C" int kv_scm_best_rules_p2p(kv_shard *s, const uint64_t *pos_mask, cons
     if (bytes > m->slot_bytes) return fail(KV_E_INVALID, "kv_scm_best_rules_p2p: packet larger than the mailbox slot");
     DeviceGuard g(s->device);
     s->last_launches = 0;
+    if (s->fused && !s->reuse_armed && n_blocks <= FUSED_MAX_BLOCKS && m->d_dev &&
+        (int64_t)m->world * packet_capacity <= kFusedCap) {
+        // ONE kernel per step and rank: scan, candidates, publish into every peer's mailbox, wait, merge on the device
+        if ((pos_mask == nullptr) != (neg_mask == nullptr) || !best_utility || !n_found || !merged_block_max || !selected ||
+            !overflowed)
+            return fail(KV_E_INVALID, "kv_scm_best_rules_p2p: null pointer");
+        P2PTail t;
+        t.dev = m->d_dev;
+        t.seq = ++m->seq;
+        t.timeout_ns = 20ull * 1000 * 1000 * 1000;
+        t.packet = m->d_packet;
+        t.packet_cap = packet_capacity;
+        *overflowed = 0;
+        const int rc = scm_best_rules_fused(s, pos_mask, neg_mask, n_pos, n_neg, p, util_block_size, n_blocks, best_utility,
+                                            capacity, rule_idx, pos_err, neg_cover, n_found, &t);
+        if (rc != KV_OK && rc != KV_E_OVERFLOW) return rc;
+        if (t.status == 1) return fail(KV_E_CUDA, "kv_scm_best_rules_p2p: timed out waiting for a peer rank's packet");
+        const double *hb = (const double *)((const char *)s->h_fused + kFusedHdrBytes + (size_t)kFusedCap * sizeof(TieRec));
+        const uint8_t *hs = (const uint8_t *)(hb + FUSED_MAX_BLOCKS);
+        memcpy(merged_block_max, hb, (size_t)n_blocks * 8);
+        memcpy(selected, hs, (size_t)n_blocks);
+        if (t.status == 2) {
+            *overflowed = 1;
+            *n_found = 0;
+            return KV_OK;
+        }
+        return rc;
+    }
     KV_TRY(scm_packet_async(s, pos_mask, neg_mask, n_pos, n_neg, p, util_block_size, n_blocks, packet_capacity,
                             m->d_packet));
     P2PParams P;
@@ -3746,6 +4446,23 @@ extern "C" int kv_scm_best_rules_p2p(kv_shard *s, const uint64_t *pos_mask, cons
     return merge_packets_strided(m->h_rows, m->slot_bytes, m->world, n_blocks, packet_capacity, p, util_block_size,
                                  best_utility, capacity, rule_idx, pos_err, neg_cover, n_found, merged_block_max,
                                  selected, overflowed);
+}
+
+// kv_scm_best_rules_p2p from the learner's example index arrays (see kv_scm_best_rules_idx)
+extern "C" int kv_scm_best_rules_p2p_idx(kv_shard *s, const int64_t *pos_idx, int64_t n_pos, const int64_t *neg_idx,
+                                         int64_t n_neg, double p, int64_t util_block_size, int64_t packet_capacity,
+                                         double *best_utility, int64_t capacity, int64_t *rule_idx, int64_t *pos_err,
+                                         int64_t *neg_cover, int64_t *n_found, double *merged_block_max,
+                                         uint8_t *selected, int *overflowed) {
+    if (!s || (n_pos > 0 && !pos_idx) || (n_neg > 0 && !neg_idx))
+        return fail(KV_E_INVALID, "kv_scm_best_rules_p2p_idx: null pointer");
+    if (n_pos < 0 || n_neg < 0) return fail(KV_E_INVALID, "kv_scm_best_rules_p2p_idx: negative count");
+    s->h_masks.resize((size_t)s->W * 2);
+    KV_TRY(fill_row_mask(s, pos_idx, n_pos, s->h_masks.data()));
+    KV_TRY(fill_row_mask(s, neg_idx, n_neg, s->h_masks.data() + s->W));
+    return kv_scm_best_rules_p2p(s, s->h_masks.data(), s->h_masks.data() + s->W, n_pos, n_neg, p, util_block_size,
+                                 packet_capacity, best_utility, capacity, rule_idx, pos_err, neg_cover, n_found,
+                                 merged_block_max, selected, overflowed);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -1,0 +1,503 @@
+// kv_inflate.cuh -- zlib / DEFLATE (RFC 1950 / 1951) decoding on the device, for the HDF5 -> HBM upload.
+//
+// A Kover dataset stores `kmer_matrix` as independent gzip-filtered chunks of (1, <=100 000) packed words
+// (reference dataset/create.py:222-230, tools/kmer_tools/src/kl_64.cpp:229-263); the reference inflates them on
+// the host inside every `dataset[rows, c0:c1]` read (learning/common/rules.py:253, h5py -> libhdf5 -> zlib).  Here
+// the RAW streams go to the GPU and ONE WARP decodes ONE chunk:
+//   * lane 0 walks the bit stream (64-bit bit buffer refilled with aligned 32-bit words) and decodes Huffman
+//     symbols through per-warp tables in shared memory -- 10-bit primary table for literal/length codes, 8-bit for
+//     distance codes, longer (rare) codes through the canonical bit-by-bit walk;
+//   * literals are staged (up to 128) and written by the whole warp; an LZ77 match ends the batch and is copied by
+//     the whole warp from the already written output (the 32 KB window is simply the output itself);
+//   * stored, fixed-Huffman and dynamic-Huffman blocks, zlib header and the Adler-32 trailer are all checked;
+//     any violation marks the chunk (status != 0) and the caller inflates that chunk on the host instead.
+// Output goes to a scratch slab (one chunk after the other); k_scatter_chunks then places the rows of every chunk
+// into the [W, ld] image (edge chunks, shard boundaries inside a chunk and 32-bit packing are handled there).
+#pragma once
+
+enum {
+    INF_OK = 0,
+    INF_BAD_HEADER = 1,
+    INF_BAD_BLOCK = 2,
+    INF_BAD_LENGTHS = 3,
+    INF_OUT_OVERFLOW = 4,
+    INF_IN_OVERRUN = 5,
+    INF_BAD_DISTANCE = 6,
+    INF_BAD_CHECKSUM = 7,
+    INF_OUT_SHORT = 8,
+    INF_BAD_CODE = 9,
+};
+
+struct InflateJob {
+    unsigned long long src_off;     // byte offset of the zlib stream in the compressed slab (16-byte aligned)
+    unsigned int src_bytes;
+    unsigned int dst_bytes;         // expected size after inflation
+    unsigned long long dst_off;     // byte offset in the scratch slab (16-byte aligned)
+};
+
+static constexpr int INF_WARPS = 8;            // chunks decoded concurrently per CTA
+static constexpr int INF_LIT_BITS = 10, INF_DIST_BITS = 8;
+static constexpr int INF_STAGE = 128;          // literals staged per batch
+
+struct InflateWarp {                            // per-warp shared memory (~3.8 KB)
+    unsigned short lit_tab[1 << INF_LIT_BITS];  // (symbol << 4) | code length; 0 = longer code / unused
+    unsigned short dist_tab[1 << INF_DIST_BITS];
+    unsigned short lit_sym[288], dist_sym[32];  // symbols in canonical order
+    unsigned short lit_cnt[16], dist_cnt[16];   // codes per length
+    unsigned char lens[320];                    // code lengths of the block being set up
+    unsigned char stage[INF_STAGE];
+};
+
+__constant__ unsigned short c_len_base[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31,
+                                              35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
+__constant__ unsigned char c_len_extra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+__constant__ unsigned short c_dist_base[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769,
+                                               1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
+__constant__ unsigned char c_dist_extra[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
+__constant__ unsigned char c_clen_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+
+struct BitReader {                  // lane 0 only; lives in registers (never pass it to a non-inlined function)
+    const unsigned int *words;      // stream start, 4-byte aligned
+    unsigned int n_words;           // words that may be read (stream bytes rounded up)
+    unsigned int next;              // index of the word AFTER `ahead`
+    unsigned int ahead;             // the next word, loaded one refill early (hides the load latency)
+    unsigned long long buf;
+    int cnt;                        // valid bits in buf
+};
+
+__device__ __forceinline__ unsigned int br_load(const BitReader &b, unsigned int i) {
+    return i < b.n_words ? __ldg(b.words + i) : 0u;
+}
+__device__ __forceinline__ void br_start(BitReader &b, unsigned int word) {      // position the reader at `word`
+    b.buf = 0;
+    b.cnt = 0;
+    b.ahead = br_load(b, word);
+    b.next = word + 1;
+}
+__device__ __forceinline__ void br_refill(BitReader &b) {                       // afterwards cnt >= 33
+    if (b.cnt <= 32) {
+        b.buf |= (unsigned long long)b.ahead << b.cnt;
+        b.cnt += 32;
+        b.ahead = br_load(b, b.next);
+        ++b.next;
+    }
+}
+// more words consumed than the stream holds (two words of slack: `ahead` and the final refill may run past the end)
+__device__ __forceinline__ bool br_overrun(const BitReader &b) { return b.next > b.n_words + 2; }
+__device__ __forceinline__ unsigned int br_bits(BitReader &b, int n) {      // n <= 32, after a refill
+    const unsigned int v = (unsigned int)(b.buf & ((1ull << n) - 1ull));
+    b.buf >>= n;
+    b.cnt -= n;
+    return v;
+}
+// stream position (bytes) of the next unread byte, when the reader is byte aligned
+__device__ __forceinline__ unsigned int br_byte_pos(const BitReader &b) { return (b.next - 1) * 4 - (unsigned int)(b.cnt >> 3); }
+
+// Canonical bit-by-bit decode of the code that starts at bit 0 of `bits` (codes longer than the primary table, or
+// tables with unused entries).  Pure function, deliberately NOT inlined: it is rare, and inlining it (unrolled) into
+// the symbol loop bloats the loop beyond the instruction cache.  -> symbol | length << 16, or -1.
+__device__ __noinline__ int slow_decode(unsigned int bits, const unsigned short *cnt, const unsigned short *sym) {
+    int code = 0, first = 0, index = 0;
+#pragma unroll 1
+    for (int len = 1; len <= 15; ++len) {
+        code |= (int)(bits & 1u);
+        bits >>= 1;
+        const int c = cnt[len];
+        if (code - c < first) return (int)sym[index + (code - first)] | (len << 16);
+        index += c;
+        first += c;
+        first <<= 1;
+        code <<= 1;
+    }
+    return -1;
+}
+__device__ __forceinline__ int br_slow_symbol(BitReader &b, const unsigned short *cnt, const unsigned short *sym) {
+    const int r = slow_decode((unsigned int)b.buf, cnt, sym);
+    if (r < 0) return -1;
+    b.buf >>= (r >> 16);
+    b.cnt -= (r >> 16);
+    return r & 0xFFFF;
+}
+
+// Canonical Huffman set-up from code lengths (whole warp).  lens[n] -> cnt[16], sym[] (canonical order), primary table
+// tab[1 << bits].  Returns false for an over-subscribed set of lengths.
+__device__ __forceinline__ bool build_tables(const unsigned char *lens, int n, unsigned short *cnt, unsigned short *sym,
+                             unsigned short *tab, int bits, int lane) {
+    __shared__ unsigned short s_first_code[INF_WARPS][16], s_first_idx[INF_WARPS][16];
+    const int w = threadIdx.x >> 5;
+    for (int i = lane; i < (1 << bits); i += 32) tab[i] = 0;
+    bool ok = true;
+    if (lane == 0) {
+#pragma unroll 1
+        for (int l = 0; l < 16; ++l) cnt[l] = 0;
+#pragma unroll 1
+        for (int s = 0; s < n; ++s) cnt[lens[s]]++;
+        cnt[0] = 0;
+        int left = 1;
+#pragma unroll 1
+        for (int l = 1; l <= 15; ++l) {
+            left <<= 1;
+            left -= cnt[l];
+            if (left < 0) ok = false;
+        }
+        unsigned short offs[16];
+        int code = 0, idx = 0;
+#pragma unroll 1
+        for (int l = 1; l <= 15; ++l) {
+            code = (code + cnt[l - 1]) << 1;
+            s_first_code[w][l] = (unsigned short)code;
+            s_first_idx[w][l] = (unsigned short)idx;
+            offs[l] = (unsigned short)idx;
+            idx += cnt[l];
+        }
+#pragma unroll 1
+        for (int s = 0; s < n; ++s)
+            if (lens[s]) sym[offs[lens[s]]++] = (unsigned short)s;
+    }
+    ok = __shfl_sync(0xffffffffu, (int)ok, 0) != 0;
+    __syncwarp();
+    if (!ok) return false;
+    int total = 0;
+#pragma unroll 1
+    for (int l = 1; l <= 15; ++l) total += cnt[l];
+    for (int i = lane; i < total; i += 32) {
+        const int s = sym[i];
+        const int l = lens[s];
+        if (l > bits) continue;
+        const unsigned int code = (unsigned int)s_first_code[w][l] + (unsigned int)(i - s_first_idx[w][l]);
+        const unsigned int rev = __brev(code) >> (32 - l);
+        const unsigned short e = (unsigned short)((s << 4) | l);
+        for (unsigned int j = rev; j < (1u << bits); j += (1u << l)) tab[j] = e;
+    }
+    __syncwarp();
+    return true;
+}
+
+// dynamic block header (RFC 1951 3.2.7), lane 0: fills lens[0 .. hlit + hdist)
+__device__ __forceinline__ int read_dynamic_lengths(BitReader &b, unsigned char *lens, int &hlit, int &hdist) {
+    br_refill(b);
+    hlit = (int)br_bits(b, 5) + 257;
+    hdist = (int)br_bits(b, 5) + 1;
+    const int hclen = (int)br_bits(b, 4) + 4;
+    if (hlit > 286 || hdist > 30) return INF_BAD_LENGTHS;
+    unsigned char cl[19];
+#pragma unroll 1
+    for (int i = 0; i < 19; ++i) cl[i] = 0;
+#pragma unroll 1
+    for (int i = 0; i < hclen; ++i) {
+        br_refill(b);
+        cl[c_clen_order[i]] = (unsigned char)br_bits(b, 3);
+    }
+    // the 19-symbol code is decoded canonically, bit by bit (at most 7 bits, a few hundred symbols per block)
+    unsigned short ccnt[16], csym[19];
+#pragma unroll 1
+    for (int l = 0; l < 16; ++l) ccnt[l] = 0;
+#pragma unroll 1
+    for (int s = 0; s < 19; ++s) ccnt[cl[s]]++;
+    ccnt[0] = 0;
+    {
+        int left = 1;
+#pragma unroll 1
+        for (int l = 1; l <= 7; ++l) {
+            left <<= 1;
+            left -= ccnt[l];
+            if (left < 0) return INF_BAD_LENGTHS;
+        }
+        unsigned short offs[16];
+        int idx = 0;
+#pragma unroll 1
+        for (int l = 1; l <= 15; ++l) {
+            offs[l] = (unsigned short)idx;
+            idx += ccnt[l];
+        }
+#pragma unroll 1
+        for (int s = 0; s < 19; ++s)
+            if (cl[s]) csym[offs[cl[s]]++] = (unsigned short)s;
+    }
+    int n = 0;
+    const int total = hlit + hdist;
+    while (n < total) {
+        br_refill(b);
+        const int s = br_slow_symbol(b, ccnt, csym);
+        if (s < 0) return INF_BAD_CODE;
+        if (s < 16) {
+            lens[n++] = (unsigned char)s;
+            continue;
+        }
+        int rep, val = 0;
+        if (s == 16) {
+            if (n == 0) return INF_BAD_LENGTHS;
+            val = lens[n - 1];
+            rep = 3 + (int)br_bits(b, 2);
+        } else if (s == 17) {
+            rep = 3 + (int)br_bits(b, 3);
+        } else {
+            rep = 11 + (int)br_bits(b, 7);
+        }
+        if (n + rep > total) return INF_BAD_LENGTHS;
+        for (int i = 0; i < rep; ++i) lens[n++] = (unsigned char)val;
+    }
+    if (lens[256] == 0) return INF_BAD_LENGTHS;          // no end-of-block code
+    return br_overrun(b) ? INF_IN_OVERRUN : INF_OK;
+}
+
+// Adler-32 of dst[0 .. n) by the whole warp (RFC 1950): s1 = 1 + sum b_i, s2 = n + sum (n - i) b_i, mod 65521
+__device__ __forceinline__ unsigned int warp_adler32(const unsigned char *dst, unsigned int n, int lane) {
+    unsigned long long s1 = 0, s2 = 0;
+    const unsigned int n16 = n / 16;
+    const uint4 *v = reinterpret_cast<const uint4 *>(dst);
+    for (unsigned int i = lane; i < n16; i += 32) {
+        const uint4 q = __ldcg(v + i);
+        const unsigned int w[4] = {q.x, q.y, q.z, q.w};
+        unsigned int a = 0, wsum = 0;                      // a = sum b_j, wsum = sum j * b_j over the 16 bytes
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const unsigned int byte = (w[k] >> (8 * j)) & 0xFFu;
+                a += byte;
+                wsum += (unsigned int)(k * 4 + j) * byte;
+            }
+        }
+        const unsigned long long base = (unsigned long long)n - (unsigned long long)i * 16ull;   // weight of byte 0
+        s1 += a;
+        s2 += base * a - wsum;
+    }
+    for (unsigned int i = n16 * 16 + lane; i < n; i += 32) {
+        const unsigned int byte = dst[i];
+        s1 += byte;
+        s2 += (unsigned long long)(n - i) * byte;
+    }
+    s1 %= 65521ull;
+    s2 %= 65521ull;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    s1 = (s1 + 1ull) % 65521ull;
+    s2 = (s2 + (unsigned long long)n) % 65521ull;
+    return (unsigned int)((s2 << 16) | s1);
+}
+
+__global__ void __launch_bounds__(INF_WARPS * 32) k_inflate(const unsigned char *src_base, unsigned char *dst_base,
+                                                             const InflateJob *jobs, int n_jobs, int *status,
+                                                             unsigned int *next_job) {
+    __shared__ InflateWarp s_w[INF_WARPS];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    InflateWarp &S = s_w[wid];
+    for (;;) {
+        // dynamic work distribution: chunks differ in cost (sparse rows inflate faster)
+        int job = 0;
+        if (lane == 0) job = (int)atomicAdd(next_job, 1u);
+        job = __shfl_sync(0xffffffffu, job, 0);
+        if (job >= n_jobs) return;
+        const InflateJob J = jobs[job];
+        unsigned char *dst = dst_base + J.dst_off;
+        BitReader b;
+        b.words = reinterpret_cast<const unsigned int *>(src_base + J.src_off);
+        b.n_words = (J.src_bytes + 3) / 4;
+        br_start(b, 0);
+        int st = INF_OK;
+        unsigned int out = 0;
+        if (lane == 0) {
+            br_refill(b);
+            const unsigned int cmf = br_bits(b, 8), flg = br_bits(b, 8);
+            if ((cmf & 15u) != 8u || (cmf >> 4) > 7u || ((cmf << 8) | flg) % 31u != 0u || (flg & 32u)) st = INF_BAD_HEADER;
+        }
+        st = __shfl_sync(0xffffffffu, st, 0);
+        bool last = false;
+        while (st == INF_OK && !last) {
+            int btype = 0, hlit = 0, hdist = 0;
+            if (lane == 0) {
+                br_refill(b);
+                last = br_bits(b, 1) != 0;
+                btype = (int)br_bits(b, 2);
+            }
+            last = __shfl_sync(0xffffffffu, (int)last, 0) != 0;
+            btype = __shfl_sync(0xffffffffu, btype, 0);
+            if (btype == 0) {
+                // stored block: skip to the byte boundary, LEN / NLEN, raw bytes
+                unsigned int len = 0, byte_pos = 0;
+                if (lane == 0) {
+                    br_bits(b, b.cnt & 7);
+                    br_refill(b);
+                    len = br_bits(b, 16);
+                    br_refill(b);
+                    const unsigned int nlen = br_bits(b, 16);
+                    if ((len ^ nlen) != 0xFFFFu) st = INF_BAD_BLOCK;
+                    byte_pos = br_byte_pos(b);
+                    if (byte_pos + len > J.src_bytes) st = INF_IN_OVERRUN;
+                    if (out + len > J.dst_bytes) st = INF_OUT_OVERFLOW;
+                }
+                st = __shfl_sync(0xffffffffu, st, 0);
+                len = __shfl_sync(0xffffffffu, len, 0);
+                byte_pos = __shfl_sync(0xffffffffu, byte_pos, 0);
+                if (st != INF_OK) break;
+                const unsigned char *sb = src_base + J.src_off + byte_pos;
+                for (unsigned int i = lane; i < len; i += 32) dst[out + i] = sb[i];
+                out += len;
+                if (lane == 0) {                                              // restart the bit reader after the raw bytes
+                    const unsigned int p = byte_pos + len;
+                    br_start(b, p / 4);
+                    br_refill(b);
+                    br_bits(b, (int)(p & 3u) * 8);
+                }
+                __syncwarp();
+                continue;
+            }
+            if (btype == 3) {
+                st = INF_BAD_BLOCK;
+                break;
+            }
+            if (btype == 1) {
+                for (int i = lane; i < 288; i += 32) S.lens[i] = i < 144 ? 8 : (i < 256 ? 9 : (i < 280 ? 7 : 8));
+                for (int i = lane; i < 32; i += 32) S.lens[288 + i] = i < 30 ? 5 : 0;
+                hlit = 288;
+                hdist = 30;
+            } else {
+                if (lane == 0) st = read_dynamic_lengths(b, S.lens, hlit, hdist);
+                st = __shfl_sync(0xffffffffu, st, 0);
+                hlit = __shfl_sync(0xffffffffu, hlit, 0);
+                hdist = __shfl_sync(0xffffffffu, hdist, 0);
+                if (st != INF_OK) break;
+            }
+            __syncwarp();
+            if (!build_tables(S.lens, hlit, S.lit_cnt, S.lit_sym, S.lit_tab, INF_LIT_BITS, lane) ||
+                !build_tables(S.lens + hlit, hdist, S.dist_cnt, S.dist_sym, S.dist_tab, INF_DIST_BITS, lane)) {
+                st = INF_BAD_LENGTHS;
+                break;
+            }
+            // ---- symbols of the block, in batches: up to INF_STAGE literals, then at most one match
+            bool end_of_block = false;
+            while (!end_of_block && st == INF_OK) {
+                int nlit = 0, mlen = 0, mdist = 0;
+                if (lane == 0) {
+#pragma unroll 1
+                    while (nlit < INF_STAGE) {
+                        br_refill(b);
+                        unsigned int e = S.lit_tab[(unsigned int)b.buf & ((1u << INF_LIT_BITS) - 1u)];
+                        int sym;
+                        if (e & 15u) {
+                            b.buf >>= (e & 15u);
+                            b.cnt -= (int)(e & 15u);
+                            sym = (int)(e >> 4);
+                        } else {
+                            sym = br_slow_symbol(b, S.lit_cnt, S.lit_sym);
+                            if (sym < 0) {
+                                st = INF_BAD_CODE;
+                                break;
+                            }
+                        }
+                        if (sym < 256) {
+                            S.stage[nlit++] = (unsigned char)sym;
+                            continue;
+                        }
+                        if (sym == 256) {
+                            end_of_block = true;
+                            break;
+                        }
+                        sym -= 257;
+                        if (sym >= 29) {
+                            st = INF_BAD_CODE;
+                            break;
+                        }
+                        mlen = c_len_base[sym] + (int)br_bits(b, c_len_extra[sym]);
+                        br_refill(b);
+                        e = S.dist_tab[(unsigned int)b.buf & ((1u << INF_DIST_BITS) - 1u)];
+                        int ds;
+                        if (e & 15u) {
+                            b.buf >>= (e & 15u);
+                            b.cnt -= (int)(e & 15u);
+                            ds = (int)(e >> 4);
+                        } else {
+                            ds = br_slow_symbol(b, S.dist_cnt, S.dist_sym);
+                        }
+                        if (ds < 0 || ds >= 30) {
+                            st = INF_BAD_CODE;
+                            break;
+                        }
+                        mdist = c_dist_base[ds] + (int)br_bits(b, c_dist_extra[ds]);
+                        break;
+                    }
+                    if (br_overrun(b) && st == INF_OK) st = INF_IN_OVERRUN;
+                    if (st == INF_OK && (unsigned long long)out + nlit + mlen > J.dst_bytes) st = INF_OUT_OVERFLOW;
+                    if (st == INF_OK && mlen && (unsigned int)mdist > out + nlit) st = INF_BAD_DISTANCE;
+                }
+                st = __shfl_sync(0xffffffffu, st, 0);
+                if (st != INF_OK) break;
+                nlit = __shfl_sync(0xffffffffu, nlit, 0);
+                mlen = __shfl_sync(0xffffffffu, mlen, 0);
+                mdist = __shfl_sync(0xffffffffu, mdist, 0);
+                end_of_block = __shfl_sync(0xffffffffu, (int)end_of_block, 0) != 0;
+                __syncwarp();                                   // lane 0's staged literals are visible
+                for (int i = lane; i < nlit; i += 32) dst[out + i] = S.stage[i];
+                out += (unsigned int)nlit;
+                if (mlen) {
+                    __syncwarp();                               // the literals just written may be the match source
+                    const unsigned char *from = dst + out - mdist;
+                    for (int i = lane; i < mlen; i += 32) dst[out + i] = from[i % mdist];
+                    out += (unsigned int)mlen;
+                }
+                __syncwarp();
+            }
+        }
+        // ---- trailer: Adler-32 of the output, stored big-endian after the last block (byte aligned)
+        unsigned int want = 0;
+        if (st == INF_OK) {
+            if (lane == 0) {
+                br_bits(b, b.cnt & 7);
+                br_refill(b);
+                const unsigned int a0 = br_bits(b, 16);
+                br_refill(b);
+                const unsigned int a1 = br_bits(b, 16);
+                const unsigned int le = a0 | (a1 << 16);
+                want = __byte_perm(le, 0, 0x0123);
+                if (br_overrun(b)) st = INF_IN_OVERRUN;
+                if (st == INF_OK && out != J.dst_bytes) st = INF_OUT_SHORT;
+            }
+            st = __shfl_sync(0xffffffffu, st, 0);
+            want = __shfl_sync(0xffffffffu, want, 0);
+        }
+        if (st == INF_OK) {
+            __syncwarp();
+            __threadfence_block();
+            if (warp_adler32(dst, J.dst_bytes, lane) != want) st = INF_BAD_CHECKSUM;
+        }
+        if (lane == 0) status[job] = st;
+        __syncwarp();
+    }
+}
+
+// Places the inflated chunks into the [W, ld] image.  A chunk holds chunk_rows x chunk_cols elements of the dataset
+// starting at (row0, gcol0); only the part inside the dataset and inside this shard's columns is kept (HDF5 stores
+// edge chunks at full size; shards are cut on 512-column tiles, so a chunk can belong to two shards).
+struct ScatterJob {
+    unsigned long long src_off;     // in the scratch slab
+    long long row0, gcol0;          // dataset coordinates of the chunk's first element (row in pack_bits units)
+    int ok;                         // 0: skip (the host re-does this chunk)
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_scatter_chunks(const unsigned char *scratch, const ScatterJob *jobs, uint64_t *mat,
+                                                         long long ld, long long shard_col0, long long shard_cols,
+                                                         long long n_rows_total, long long n_cols_total,
+                                                         int chunk_rows, long long chunk_cols) {
+    const ScatterJob J = jobs[blockIdx.y];
+    if (!J.ok) return;
+    const T *src = reinterpret_cast<const T *>(scratch + J.src_off);
+    const long long per_chunk = (long long)chunk_rows * chunk_cols;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < per_chunk; e += (long long)gridDim.x * blockDim.x) {
+        const long long r = J.row0 + e / chunk_cols, c = J.gcol0 + e % chunk_cols;
+        if (r >= n_rows_total || c >= n_cols_total) continue;
+        const long long lc = c - shard_col0;
+        if (lc < 0 || lc >= shard_cols) continue;
+        if (sizeof(T) == 8) {
+            mat[r * ld + lc] = (uint64_t)src[e];
+        } else {
+            // 32-bit packing (rules.py:123-128): packed row 2w is the HIGH half of word w -- written as a 32-bit store
+            uint32_t *m32 = reinterpret_cast<uint32_t *>(mat + (r >> 1) * ld + lc);
+            m32[(r & 1) ? 0 : 1] = (uint32_t)src[e];
+        }
+    }
+}

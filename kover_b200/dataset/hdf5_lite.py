@@ -502,6 +502,39 @@ class Dataset(_Object):
             else:
                 self._walk_chunk_btree(child, index)
 
+    def deflate_chunk_table(self, row0, row1, col0, col1):
+        """The raw gzip streams of the chunks that intersect rows [row0, row1) x columns [col0, col1) of a 2-D chunked
+        dataset whose ONLY filter is deflate (what `kover dataset create` writes: create.py:222-230, kl_64.cpp:229-263),
+        so that they can be inflated on the device instead of on the host.
+        -> None when the dataset is not of that kind, else a dict of arrays, one entry per allocated chunk:
+        ``address`` (host address of the stream inside the memory-mapped file), ``nbytes``, ``row0``, ``col0``, and
+        ``raw`` = True for chunks stored with the filter skipped (filter mask bit 0): those need the host path."""
+        if self._kind != "chunked" or len(self.shape) != 2 or [fid for fid, _ in self._filters] != [1]:
+            return None
+        if isinstance(self._dtype, _VlenStr) or self._dtype not in (np.dtype("<u8"), np.dtype("<u4")):
+            return None
+        index = self._chunk_index()
+        cr, cc = self.chunks
+        base = self._f._buf.ctypes.data + self._f._base
+        size = len(self._f._mv)
+        rows, cols, addr, nbytes, raw = [], [], [], [], []
+        for r in range((row0 // cr) * cr, min(row1, self.shape[0]), cr):
+            for c in range((col0 // cc) * cc, min(col1, self.shape[1]), cc):
+                entry = index.get((r, c))
+                if entry is None:                             # unallocated chunk: fill value (zero)
+                    continue
+                a, n, mask = entry
+                if self._f._base + a + n > size:
+                    raise ValueError("HDF5: address out of range (truncated or unsupported file)")
+                rows.append(r)
+                cols.append(c)
+                addr.append(base + a)
+                nbytes.append(n)
+                raw.append(bool(mask & 1))
+        return {"address": np.array(addr, dtype=np.uint64), "nbytes": np.array(nbytes, dtype=np.int64),
+                "row0": np.array(rows, dtype=np.int64), "col0": np.array(cols, dtype=np.int64),
+                "raw": np.array(raw, dtype=bool), "chunks": (cr, cc)}
+
     def _read_chunk(self, offs):
         entry = self._chunk_index().get(offs)
         n_items = int(np.prod(self.chunks, dtype=np.int64))

@@ -105,6 +105,45 @@ class DeviceOccurrences(object):
         self.table = None
 
 
+class ScmGreedyState(object):
+    """The remaining positive / negative examples of one SCM fit, kept as row masks ON THE DEVICE (scm.py:133-139
+    keeps two index lists on the host and filters them with a fetched column after every pick).  ``scan`` runs the
+    utility scan over the resident masks, ``apply`` ANDs them with the picked rule's column (kv_mask_and_column) and
+    returns how many examples are left.  The index lists are kept as well, lazily: they are only rebuilt (from one
+    get_columns call per applied rule) if a scan has to fall back to the index-array path."""
+
+    def __init__(self, rule_classifications, positive_example_idx, negative_example_idx):
+        self._rc = rule_classifications
+        self._pos = np.asarray(positive_example_idx)
+        self._neg = np.asarray(negative_example_idx)
+        self._pending = []                                  # rules applied on the device but not yet to the index lists
+        self.n_pos, self.n_neg = rule_classifications._group.scm_state_set(
+            rule_classifications.row_mask(self._pos), rule_classifications.row_mask(self._neg))
+
+    def index_lists(self):
+        for rule in self._pending:
+            accepted = self._rc.get_columns(rule)
+            self._pos = self._pos[accepted[self._pos] != 0]
+            self._neg = self._neg[accepted[self._neg] != 0]
+        self._pending = []
+        return self._pos, self._neg
+
+    def scan(self, p, rule_blacklist, util_block_size):
+        self._rc.set_rule_blacklist(rule_blacklist)
+        out = self._rc._group.scm_best_rules_state(float(p), int(util_block_size))
+        if out is None:                                     # huge equivalent-rule set: the general path sizes its buffers
+            pos, neg = self.index_lists()
+            out = self._rc.best_utility_rules(p, pos, neg, rule_blacklist=rule_blacklist, util_block_size=util_block_size)
+        return out
+
+    def apply(self, rule_idx):
+        n_kmers = self._rc._n_kmers
+        rule_idx = int(rule_idx)
+        self.n_pos, self.n_neg = self._rc._group.scm_state_apply(rule_idx % n_kmers, invert=rule_idx >= n_kmers)
+        self._pending.append(rule_idx)
+        return self.n_pos, self.n_neg
+
+
 def _default_devices():
     env = os.environ.get("KOVER_B200_DEVICES")
     if env:
@@ -170,10 +209,43 @@ class KmerRuleClassifications(BaseRuleClassifications):
         slices = [s for s in partition_columns(k, len(devices)) if s[1] > 0]
         return ShardGroup([_native.Shard(d, n, k, c0, nc) for d, (c0, nc) in zip(devices, slices)], n, k)
 
+    def _upload_device_inflate(self):
+        """HDF5 -> HBM without inflating on the host: the raw gzip streams of the chunks (rules.py:253 inflates them
+        through libhdf5 on every read) go to the GPU, one warp inflates one chunk (kv_upload_deflate).  Used when the
+        dataset can hand out its raw chunks (hdf5_lite: chunked, deflate only) and the shards live on a device;
+        KOVER_B200_DEVICE_INFLATE=0 switches it off.  A chunk the device rejects (malformed stream) or that was stored
+        unfiltered is read through the host path, which raises the proper error if it really is corrupt.
+        -> False when this path does not apply."""
+        ds = self.dataset
+        table_of = getattr(ds, "deflate_chunk_table", None)
+        if table_of is None or os.environ.get("KOVER_B200_DEVICE_INFLATE", "1") == "0":
+            return False
+        if not all(hasattr(s, "upload_deflate") for s in self._group.shards):
+            return False
+        needed_rows = min(-(-int(self.dataset_initial_n_rows) // self.dataset_pack_size), int(ds.shape[0]))
+        for s in self._group.shards:
+            tab = table_of(0, needed_rows, s.col0, s.col0 + s.n_cols)
+            if tab is None:
+                return False
+            cr, cc = tab["chunks"]
+            on_device = np.flatnonzero(~tab["raw"])
+            status = np.zeros(tab["raw"].shape[0], dtype=np.int32)
+            if on_device.size:
+                status[on_device] = s.upload_deflate(self.dataset_pack_size, tab["address"][on_device],
+                                                     tab["nbytes"][on_device], tab["row0"][on_device],
+                                                     tab["col0"][on_device], cr, cc)
+            for i in np.flatnonzero(tab["raw"] | (status != 0)):
+                r0, c0 = int(tab["row0"][i]), int(tab["col0"][i])
+                chunk = ds._read_chunk((r0, c0))                       # host inflate: raises on a corrupt stream
+                s.upload_block(np.ascontiguousarray(chunk[:needed_rows - r0, :int(ds.shape[1]) - c0]), r0, c0)
+        return True
+
     def _upload(self, slab_bytes=128 << 20):
         """Stream the packed matrix into HBM: row slabs x the column span of the local shards.  The next slab is
         read (HDF5: chunk reads + inflate on the host cores) while the current one is staged and copied."""
         from concurrent.futures import ThreadPoolExecutor
+        if self._upload_device_inflate():
+            return
         ds = self.dataset
         itemsize = np.dtype(ds.dtype).itemsize
         n_packed_rows = int(ds.shape[0])
@@ -292,18 +364,24 @@ class KmerRuleClassifications(BaseRuleClassifications):
         positive_example_idx = np.asarray(positive_example_idx)
         negative_example_idx = np.asarray(negative_example_idx)
         self.set_rule_blacklist(rule_blacklist)
-        group = self._group
-        if group._single and not self.dataset_removed_rows and hasattr(group.shards[0], "scm_best_rules_idx"):
-            # one shard: index arrays straight into the library (masks built there), one kernel launch per call
-            out = group.shards[0].scm_best_rules_idx(np.ascontiguousarray(positive_example_idx, dtype=np.int64).reshape(-1),
-                                                     np.ascontiguousarray(negative_example_idx, dtype=np.int64).reshape(-1),
-                                                     float(p), int(util_block_size))
+        if not self.dataset_removed_rows:
+            # index arrays straight into the library (masks built there): one kernel launch per call and rank
+            out = self._group.scm_best_rules_idx(np.ascontiguousarray(positive_example_idx, dtype=np.int64).reshape(-1),
+                                                 np.ascontiguousarray(negative_example_idx, dtype=np.int64).reshape(-1),
+                                                 float(p), int(util_block_size))
             if out is not None:
                 return out
         pos_mask = self.row_mask(positive_example_idx)
         neg_mask = self.row_mask(negative_example_idx)
         return self._group.scm_best_rules(pos_mask, neg_mask, positive_example_idx.shape[0],
                                           negative_example_idx.shape[0], float(p), int(util_block_size))
+
+    def scm_state(self, positive_example_idx, negative_example_idx):
+        """A device-resident greedy state for one SCM fit (ScmGreedyState), or None when the shards cannot keep one
+        (several shards in one process, checker-backed shards, removed rows)."""
+        if self.dataset_removed_rows or not self._group.scm_state_supported():
+            return None
+        return ScmGreedyState(self, positive_example_idx, negative_example_idx)
 
     def best_utility_rules_grid(self, jobs, rule_blacklist=(), util_block_size=1000000):
         """``best_utility_rules`` for several (p, positive_example_idx, negative_example_idx) jobs at once: jobs

@@ -56,21 +56,28 @@ class BaseSetCoveringMachine(object):
     def fit(self, rules, rule_classifications, positive_example_idx, negative_example_idx, rule_blacklist=[],
             tiebreaker=None, iteration_callback=None, iteration_rule_importances=False, **kwargs):
         steps = self._fit_steps(rules, rule_classifications, positive_example_idx, negative_example_idx,
-                                rule_blacklist, tiebreaker, iteration_callback, iteration_rule_importances, **kwargs)
+                                rule_blacklist, tiebreaker, iteration_callback, iteration_rule_importances,
+                                device_state=True, **kwargs)
         answer = None
         while True:
             try:
                 pos_idx, neg_idx, blacklist, extra = steps.send(answer)
             except StopIteration:
                 return
-            answer = self._get_best_utility_rules(rule_classifications=rule_classifications,
-                                                  positive_example_idx=pos_idx, negative_example_idx=neg_idx,
-                                                  rule_blacklist=blacklist, **extra)
+            if neg_idx is None:                          # pos_idx is the device-resident greedy state
+                answer = pos_idx.scan(self.p, blacklist, UTIL_BLOCK_SIZE)
+            else:
+                answer = self._get_best_utility_rules(rule_classifications=rule_classifications,
+                                                      positive_example_idx=pos_idx, negative_example_idx=neg_idx,
+                                                      rule_blacklist=blacklist, **extra)
 
     def _fit_steps(self, rules, rule_classifications, positive_example_idx, negative_example_idx, rule_blacklist=[],
-                   tiebreaker=None, iteration_callback=None, iteration_rule_importances=False, **kwargs):
+                   tiebreaker=None, iteration_callback=None, iteration_rule_importances=False, device_state=False,
+                   **kwargs):
         """Generator: yields (positive_idx, negative_idx, blacklist, utility kwargs) whenever the greedy loop
-        needs the best-utility rules, and is sent the 4-tuple ``_get_best_utility_rules`` returns."""
+        needs the best-utility rules, and is sent the 4-tuple ``_get_best_utility_rules`` returns.
+        device_state: keep the remaining examples as masks on the device (rule_classifications.scm_state) and yield
+        (state, None, blacklist, kwargs) instead -- the index lists are then never filtered on the host."""
         scan_kwargs = dict((name[len("utility__"):], value) for name, value in (kwargs or {}).items()
                            if name.startswith("utility__"))
         if len(positive_example_idx) == 0 or len(negative_example_idx) == 0:
@@ -90,10 +97,15 @@ class BaseSetCoveringMachine(object):
 
         all_training_idx = np.hstack((to_keep, to_cover))
         chosen, importances = [], []
-        while len(to_cover) > 0 and len(self.model) < self.max_rules:
+        state = None
+        if device_state and not scan_kwargs and hasattr(rule_classifications, "scm_state"):
+            state = rule_classifications.scm_state(to_keep, to_cover)
+        n_to_cover = len(to_cover)
+        while n_to_cover > 0 and len(self.model) < self.max_rules:
             info = {"iteration_number": len(self.model) + 1}
             best_utility, tied, tied_pos_errors, tied_neg_cover = \
-                yield (to_keep, to_cover, rule_blacklist, scan_kwargs)
+                yield ((state, None, rule_blacklist, scan_kwargs) if state is not None
+                       else (to_keep, to_cover, rule_blacklist, scan_kwargs))
             info["utility_max"], info["utility_argmax"] = best_utility, tied
             logging.debug("Greatest utility is %.5f (%d rules)", best_utility, len(tied))
 
@@ -113,10 +125,14 @@ class BaseSetCoveringMachine(object):
             chosen.append(selected)
 
             # examples the new rule rejects leave both sets (scm.py:133-139); the column spans ALL genomes
-            accepted = rule_classifications.get_columns(selected)
-            to_cover = to_cover[accepted[to_cover] != 0]
-            to_keep = to_keep[accepted[to_keep] != 0]
-            logging.debug("Remaining examples to cover: %d, to keep: %d", len(to_cover), len(to_keep))
+            if state is not None:
+                n_to_keep, n_to_cover = state.apply(selected)          # masks &= column, on the device
+            else:
+                accepted = rule_classifications.get_columns(selected)
+                to_cover = to_cover[accepted[to_cover] != 0]
+                to_keep = to_keep[accepted[to_keep] != 0]
+                n_to_keep, n_to_cover = len(to_keep), len(to_cover)
+            logging.debug("Remaining examples to cover: %d, to keep: %d", n_to_cover, n_to_keep)
 
             if iteration_rule_importances:
                 importances = _compute_rule_importances(rule_classifications, chosen, all_training_idx)

@@ -239,6 +239,62 @@ class ShardGroup(object):
         shard.scm_scan_packet(pos_mask, neg_mask, n_pos, n_neg, p, util_block_size, cap, local)
         return merge_packets(self.comm.allgather_bytes(local, gathered), nb, cap, p, util_block_size)
 
+    # ------------------------------------------------------------------ device-resident greedy state (scm.py:133-139)
+    def scm_state_supported(self):
+        return all(hasattr(s, "mask_and_column") for s in self.shards) and \
+            (self._single or (self.comm is not None and len(self.shards) == 1 and self.p2p_slot_bytes > 0))
+
+    def scm_state_set(self, pos_mask, neg_mask):
+        return self.shards[0].scm_state_set(pos_mask, neg_mask)
+
+    def scm_state_apply(self, kmer_col, invert):
+        """AND the resident masks of every shard / rank with matrix column ``kmer_col`` (global), inverted for an
+        absence rule.  The owner reads the column from its matrix; the other ranks receive its W words.
+        -> (n_pos, n_neg) left."""
+        shard = self.shards[0]
+        if self.comm is None:
+            n_pos, n_neg, _ = shard.mask_and_column(local_col=kmer_col - shard.col0, invert=invert)
+            return n_pos, n_neg
+        owner = next(r for r, (c0, nc) in enumerate(self.rank_slices) if c0 <= kmer_col < c0 + nc)
+        if owner == self.comm.rank:
+            n_pos, n_neg, words = shard.mask_and_column(local_col=kmer_col - shard.col0, invert=invert, want_words=True)
+            self.comm.broadcast(words.view(np.int64), owner)
+            return n_pos, n_neg
+        words = self.comm.broadcast(np.zeros(self.n_words, dtype=np.int64), owner).view(np.uint64)
+        n_pos, n_neg, _ = shard.mask_and_column(words=words, invert=invert)
+        return n_pos, n_neg
+
+    def scm_best_rules_state(self, p, util_block_size):
+        """The scan over the resident state -> the 4-tuple, or None (overflow: the caller falls back to index arrays)."""
+        shard = self.shards[0]
+        if self._single:
+            return shard.scm_best_rules_state(p, util_block_size)
+        nb = _native.n_utility_blocks(self.n_kmers, util_block_size)
+        if self.p2p_slot_bytes >= _native.packet_bytes(nb, self.PACKET_CAPACITY):
+            out = shard.scm_best_rules_p2p_state(p, util_block_size, self.PACKET_CAPACITY)
+            if out is not None:
+                self.exchange_stats["one_exchange"] += 1
+            return out
+        return None
+
+    def scm_best_rules_idx(self, pos_idx, neg_idx, p, util_block_size):
+        """scm_best_rules from contiguous int64 example index arrays, when the shards can take them directly (one
+        device shard, or one process per GPU with the peer mailbox up): the masks are built inside the library and
+        the whole step is one kernel launch.  -> the 4-tuple, or None: use scm_best_rules with masks."""
+        shard = self.shards[0]
+        if self._single:
+            if hasattr(shard, "scm_best_rules_idx"):
+                return shard.scm_best_rules_idx(pos_idx, neg_idx, p, util_block_size)
+            return None
+        if self.comm is not None and len(self.shards) == 1 and hasattr(shard, "scm_best_rules_p2p_idx"):
+            nb = _native.n_utility_blocks(self.n_kmers, util_block_size)
+            if self.p2p_slot_bytes >= _native.packet_bytes(nb, self.PACKET_CAPACITY):
+                out = shard.scm_best_rules_p2p_idx(pos_idx, neg_idx, p, util_block_size, self.PACKET_CAPACITY)
+                if out is not None:
+                    self.exchange_stats["one_exchange"] += 1
+                return out
+        return None
+
     def scm_best_rules(self, pos_mask, neg_mask, n_pos, n_neg, p, util_block_size):
         """-> (best_utility, rule_idx ascending int64, pos_err int64, neg_cover int64); scm.py:238-288."""
         if self._single:

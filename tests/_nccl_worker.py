@@ -19,6 +19,33 @@ from kover_b200.synthetic import synthetic_block, synthetic_labels, train_split 
 from oracle import kover_oracle as ko  # noqa: E402
 
 
+def many_equivalent_rules(lr, comm, p2p, fused):
+    """Thousands of equivalent rules: every rank's candidate packet overflows, the step falls back to the exact
+    two-phase collection; and a shape with a few hundred ties spread over the ranks (merged on the device)."""
+    import cases
+    rs = np.random.RandomState(77)
+    n, k = 150, 60000
+    base = (rs.rand(n, 12) < 0.5).astype(np.uint8)
+    y = (base[:, 3] & (1 - base[:, 7])).astype(np.uint8)
+    pos, neg = np.where(y == 1)[0], np.where(y == 0)[0]
+    for n_copies in (k, 300):
+        X = (rs.rand(n, k) < 0.5).astype(np.uint8)
+        cols = rs.choice(k, size=n_copies, replace=False)
+        X[:, cols] = base[:, rs.randint(0, 12, size=n_copies)]
+        P = cases.pack64(X)
+        orc = ko.OracleKmerRuleClassifications(P, n, fast=True)
+        rc = KmerRuleClassifications(P, n, devices=[lr], comm=comm)
+        for p in (1.0, 999999.0):
+            wu, wi, wp, wn = ko.merge_utility_blocks(len(neg) - orc.sum_rows(neg), len(pos) - orc.sum_rows(pos), p,
+                                                     np.zeros(2 * k, dtype=bool), block_size=25000)
+            bu, bi, bp, bn = rc.best_utility_rules(p, pos, neg, util_block_size=25000)
+            assert bu == wu and np.array_equal(bi, np.asarray(wi, dtype=np.int64)), (p2p, fused, n_copies, p)
+            assert np.array_equal(bp, wp) and np.array_equal(bn, wn)
+        if n_copies == k and p2p == "1":
+            assert rc._group.exchange_stats["two_phase_fallback"] >= 1
+        rc.close()
+
+
 def main():
     lr = int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(lr)
@@ -34,10 +61,14 @@ def main():
     bl = np.zeros(2 * k, dtype=bool)
     bl[blacklist] = True
     used = {}
-    for p2p in ("1", "0"):
+    # the multi-rank step as ONE kernel per rank (scan, candidates, mailbox exchange and merge on the device), as
+    # scan + select + ties + exchange kernels with the merge on the host, and through NCCL
+    for p2p, fused in (("1", "1"), ("1", "0"), ("0", "1")):
         os.environ["KOVER_B200_P2P"] = p2p
+        os.environ["KOVER_B200_FUSED"] = fused
         rc = KmerRuleClassifications(P, n, devices=[lr], comm=comm)
         used[p2p] = rc._group.p2p_slot_bytes > 0
+        many_equivalent_rules(lr, comm, p2p, fused)
         got = rc.sum_rows(pos)
         assert np.array_equal(got, orc.sum_rows(pos))
         for p, ubs in ((1.0, 1000000), (0.316, 99991), (999999.0, 1000000), (2.0, 4096)):

@@ -161,7 +161,14 @@ class Writer(object):
     # ---- datasets
     def _write_dataset(self, node):
         d = node.dataset
-        dt, shape, raw = self._encode(d["data"])
+        big = None
+        if isinstance(d["data"], np.ndarray) and d["data"].dtype.kind in "ui" and d["chunks"] is not None \
+                and d["data"].dtype.byteorder != ">":
+            # a large numeric matrix written in chunks: no intermediate copies of the whole array
+            big = np.ascontiguousarray(d["data"])
+            dt, shape, raw = self._datatype(big.dtype), big.shape, b""
+        else:
+            dt, shape, raw = self._encode(d["data"])
         raw = bytearray(raw)
         if dt[0] & 0x0F == 9:
             self._flush_gheap([raw])
@@ -178,21 +185,33 @@ class Writer(object):
             level = d["compression"]
             if level is not None:
                 msgs.append(_msg(0x0B, struct.pack("<BB6x", 1, 1) +
-                                 struct.pack("<HHHH", 1, 8, 1, 1) + _pad8(b"deflate\x00") + struct.pack("<I4x", int(level))))
-            arr = np.frombuffer(bytes(raw), dtype=np.dtype("V%d" % item)).reshape(shape)
+                                 struct.pack("<HHHH", 1, 8, 1, 1) + _pad8(b"deflate\x00") + struct.pack("<I4x", 4 if callable(level) else int(level))))
+            arr = big if big is not None else np.frombuffer(bytes(raw), dtype=np.dtype("V%d" % item)).reshape(shape)
             entries = []
             grid = [range(0, max(n, 1), c) for n, c in zip(shape, chunks)]
             offsets = [()]
             for r in grid:
                 offsets = [t + (o,) for t in offsets for o in r]
-            for offs in offsets:
+            def stored(offs):
                 block = np.zeros(chunks, dtype=arr.dtype)
                 src = tuple(slice(o, min(o + c, n)) for o, c, n in zip(offs, chunks, shape))
                 part = arr[src]
                 block[tuple(slice(0, s) for s in part.shape)] = part
                 data = block.tobytes()
-                if level is not None:
+                if callable(level):                     # a caller-made zlib stream (stored / fixed-Huffman blocks, ...)
+                    data = level(data)
+                elif level is not None:
                     data = zlib.compress(data, int(level))
+                return data
+
+            if len(offsets) > 16:                        # zlib releases the GIL: deflate the chunks on all the cores
+                import os
+                from concurrent.futures import ThreadPoolExecutor
+                with ThreadPoolExecutor(max_workers=max(2, min(32, os.cpu_count() or 4))) as pool:
+                    blobs = list(pool.map(stored, offsets))
+            else:
+                blobs = [stored(offs) for offs in offsets]
+            for offs, data in zip(offsets, blobs):
                 entries.append((offs, self._alloc(data), len(data)))
             btree = self._chunk_btree(entries, shape, chunks, item)
             msgs.append(_msg(0x08, struct.pack("<BBB", 3, 2, len(shape) + 1) + struct.pack("<Q", btree) +

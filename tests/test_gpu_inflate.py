@@ -1,0 +1,150 @@
+"""GPU: HDF5 -> HBM with the gzip chunks inflated ON THE DEVICE (kv_upload_deflate, csrc/kv_inflate.cuh) against the
+host path (hdf5_lite + zlib + kv_upload_block) and against the matrix that was written: the resident image read back
+with kv_read_block must be bit-identical.  Streams of every DEFLATE block type (stored, fixed Huffman, dynamic
+Huffman at levels 1 / 4 / 9), 64- and 32-bit packing, chunk shapes incl. Kover's (1, 100000), edge chunks, shard
+boundaries inside a chunk, highly compressible rows (long overlapping matches) and incompressible rows; corrupt
+streams must surface as errors through the host path.  Reference: rules.py:247-262 reads + inflates the same chunks
+through h5py on every sum_rows call; create.py:222-230 / kl_64.cpp:229-263 define the chunking."""
+import os
+import zlib
+
+import numpy as np
+import pytest
+
+from hdf5_lite_writer import Writer
+from kover_b200.dataset import hdf5_lite
+from kover_b200.learning.common.rules import KmerRuleClassifications
+
+pytestmark = pytest.mark.gpu
+
+
+def matrix(seed, n_rows, n_cols, dtype, kind):
+    rs = np.random.RandomState(seed)
+    bits = np.dtype(dtype).itemsize * 8
+    if kind == "random":
+        hi = rs.randint(0, 2 ** 32, size=(n_rows, n_cols), dtype=np.uint64)
+        m = (hi << np.uint64(32) | rs.randint(0, 2 ** 32, size=(n_rows, n_cols), dtype=np.uint64)) if bits == 64 else hi
+    elif kind == "sparse":                       # k-mer-like: most words zero, runs of identical words
+        m = np.zeros((n_rows, n_cols), dtype=np.uint64)
+        idx = rs.rand(n_rows, n_cols) < 0.03
+        m[idx] = rs.randint(0, 2 ** 16, size=int(idx.sum())).astype(np.uint64) << np.uint64(rs.randint(0, bits - 16))
+        m[:, n_cols // 3:n_cols // 3 + 900] = np.uint64(0x0102030405060708 & (2 ** bits - 1))
+    else:                                        # "mixed": rows of different character
+        m = np.zeros((n_rows, n_cols), dtype=np.uint64)
+        for r in range(n_rows):
+            sub = matrix(seed * 100 + r, 1, n_cols, np.uint64 if bits == 64 else np.uint32, "random" if r % 3 == 0 else "sparse")
+            m[r] = sub[0]
+        m[n_rows // 2] = 0                        # an all-zero chunk row
+    return (m & np.uint64(2 ** bits - 1)).astype(dtype)
+
+
+def raw_deflate(strategy=zlib.Z_DEFAULT_STRATEGY, level=6):
+    def make(data):
+        c = zlib.compressobj(level, zlib.DEFLATED, 15, 8, strategy)
+        return c.compress(data) + c.flush()
+    return make
+
+
+def resident(rc, n_words):
+    return np.hstack([s.read_block(0, n_words, 0, s.n_cols) for s in rc._group.shards])
+
+
+def expect64(M, pack_bits):
+    if pack_bits == 64:
+        return M
+    rows = M.shape[0] + (M.shape[0] & 1)
+    P = np.zeros((rows, M.shape[1]), dtype=np.uint64)
+    P[:M.shape[0]] = M
+    return (P[0::2] << np.uint64(32)) | P[1::2]
+
+
+CASES = [
+    # id, dtype, rows, cols, chunks, compression, data kind
+    ("kover_1x100000_gz4", np.uint64, 5, 250_123, (1, 100_000), 4, "mixed"),
+    ("gz1_sparse", np.uint64, 7, 40_000, (1, 10_000), 1, "sparse"),
+    ("gz9_mixed", np.uint64, 6, 30_011, (1, 4_096), 9, "mixed"),
+    ("stored_blocks", np.uint64, 4, 20_000, (1, 7_000), 0, "random"),
+    ("fixed_huffman", np.uint64, 4, 20_000, (1, 7_000), raw_deflate(zlib.Z_FIXED), "mixed"),
+    ("huffman_only", np.uint64, 4, 20_000, (1, 7_000), raw_deflate(zlib.Z_HUFFMAN_ONLY), "mixed"),
+    ("rle", np.uint64, 4, 20_000, (1, 7_000), raw_deflate(zlib.Z_RLE), "sparse"),
+    ("multi_row_chunks", np.uint64, 9, 12_345, (2, 700), 4, "mixed"),
+    ("pack32_gz4", np.uint32, 11, 33_333, (1, 5_000), 4, "mixed"),
+    ("pack32_multi_row", np.uint32, 8, 9_999, (3, 1_000), 6, "sparse"),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+@pytest.mark.parametrize("devices", [[0], [0, 0, 0]], ids=["1shard", "3shards"])
+def test_device_inflate_matches_host_path(tmp_path, monkeypatch, case, devices):
+    name, dtype, n_rows, n_cols, chunks, compression, kind = case
+    pack_bits = np.dtype(dtype).itemsize * 8
+    M = matrix(len(name), n_rows, n_cols, dtype, kind)
+    path = str(tmp_path / "m.h5")
+    with Writer(path) as w:
+        w.create_dataset("kmer_matrix", M, chunks=chunks, compression=compression)
+    n_genomes = n_rows * pack_bits - 3                        # ragged last packed row
+    want = expect64(M, pack_bits)
+    images = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("KOVER_B200_DEVICE_INFLATE", mode)
+        f = hdf5_lite.File(path)
+        d = f["kmer_matrix"]
+        assert d.deflate_chunk_table(0, n_rows, 0, n_cols) is not None
+        rc = KmerRuleClassifications(d, n_genomes, devices=devices)
+        launches = sum(s.info().total_launches for s in rc._group.shards)
+        images[mode] = resident(rc, want.shape[0])
+        rc.close()
+        f.close()
+        if mode == "1":
+            assert launches >= 2 * len(devices)               # the inflate + scatter kernels ran
+    assert np.array_equal(images["1"], want)
+    assert np.array_equal(images["0"], want)
+
+
+def test_corrupt_stream_is_reported_through_the_host_path(tmp_path):
+    """A flipped byte inside one chunk: the device marks the chunk (bad code / distance / checksum), the host path
+    re-inflates it and raises zlib's own error; the other chunks are unaffected."""
+    M = matrix(5, 4, 30_000, np.uint64, "mixed")
+    path = str(tmp_path / "c.h5")
+    with Writer(path) as w:
+        w.create_dataset("kmer_matrix", M, chunks=(1, 10_000), compression=4)
+    f = hdf5_lite.File(path)
+    tab = f["kmer_matrix"].deflate_chunk_table(0, 4, 0, 30_000)
+    victim = 5
+    offset = int(tab["address"][victim] - f._buf.ctypes.data) + int(tab["nbytes"][victim]) // 2
+    f.close()
+    data = bytearray(open(path, "rb").read())
+    data[offset] ^= 0x5A
+    open(path, "wb").write(bytes(data))
+    f = hdf5_lite.File(path)
+    with pytest.raises(zlib.error):
+        KmerRuleClassifications(f["kmer_matrix"], 4 * 64, devices=[0])
+    f.close()
+
+
+def test_status_codes_of_malformed_streams():
+    """kv_upload_deflate's per-chunk status on hand-made streams (C ABI level): good, truncated, wrong checksum,
+    wrong size, bad header."""
+    from kover_b200 import _native
+    n_cols = 4096
+    shard = _native.Shard(0, 64 * 8, n_cols)
+    rs = np.random.RandomState(1)
+    rows = rs.randint(0, 2 ** 62, size=(8, n_cols), dtype=np.int64).astype(np.uint64)
+    rows[1] = 7
+    good = [zlib.compress(rows[r].tobytes(), 4) for r in range(8)]
+    streams = list(good)
+    streams[2] = good[2][:len(good[2]) // 2]                                      # truncated
+    streams[3] = good[3][:-1] + bytes([good[3][-1] ^ 1])                          # Adler-32 mismatch
+    streams[4] = zlib.compress(rows[4, :100].tobytes(), 4)                        # inflates to fewer bytes
+    streams[5] = b"\x79" + good[5][1:]                                            # bad CMF / FLG check
+    streams[6] = zlib.compress(np.concatenate((rows[6], rows[6])).tobytes(), 4)   # inflates to more bytes
+    bufs = [np.frombuffer(s + b"\x00" * 8, dtype=np.uint8).copy() for s in streams]
+    addr = np.array([b.ctypes.data for b in bufs], dtype=np.uint64)
+    nbytes = np.array([len(s) for s in streams], dtype=np.int64)
+    status = shard.upload_deflate(64, addr, nbytes, np.arange(8), np.zeros(8, dtype=np.int64), 1, n_cols)
+    assert status[0] == 0 and status[1] == 0 and status[7] == 0
+    assert all(status[i] != 0 for i in (2, 3, 4, 5, 6)), status
+    img = shard.read_block(0, 8, 0, n_cols)
+    for r in (0, 1, 7):
+        assert np.array_equal(img[r], rows[r])
+    shard.close()

@@ -279,6 +279,40 @@ def test_single_launch_step_modes(monkeypatch, fused, coop):
     rc.close()
 
 
+@pytest.mark.parametrize("n,k", [(700, 30000), (5000, 12000), (20000, 6000)], ids=["W11", "W79", "W313"])
+def test_device_resident_greedy_state(n, k):
+    """g1 / north-star (3): the remaining-example masks live on the device; kv_mask_and_column ANDs them with the picked
+    rule's column (presence: keep the genomes WITH the k-mer; absence: without) and rebuilds the scan's row records.
+    Against the reference's host bookkeeping (scm.py:133-139: get_columns + index filtering) and the checker's scan
+    after every pick, on a random walk of presence and absence rules."""
+    seed = n % 97
+    P = synthetic_block(seed, n, 0, k)
+    y = synthetic_labels(seed, n, sorted_by_label=False)
+    pos, neg = np.where(y == 1)[0], np.where(y == 0)[0]
+    orc = ko.OracleKmerRuleClassifications(P, n, fast=True)
+    rc = KmerRuleClassifications(P, n, devices=[0])
+    state = rc.scm_state(pos, neg)
+    assert state is not None and (state.n_pos, state.n_neg) == (len(pos), len(neg))
+    rs = np.random.RandomState(seed)
+    for it in range(8):
+        p = float(rs.choice([0.1, 1.0, 999999.0]))
+        want = ko.merge_utility_blocks(len(neg) - orc.sum_rows(neg), len(pos) - orc.sum_rows(pos), p,
+                                       np.zeros(2 * k, dtype=bool), block_size=7777)
+        got = state.scan(p, [], 7777)
+        assert got[0] == want[0] and np.array_equal(got[1], np.asarray(want[1], dtype=np.int64)), it
+        assert np.array_equal(got[2], want[2]) and np.array_equal(got[3], want[3])
+        # pick a rule of middling density so that examples remain: presence and absence alternate
+        rule = int(rs.randint(0, k)) + (k if it % 2 else 0)
+        accepted = orc.get_columns(rule)
+        pos, neg = pos[accepted[pos] != 0], neg[accepted[neg] != 0]
+        assert state.apply(rule) == (len(pos), len(neg)), (it, rule)
+        if len(pos) == 0 or len(neg) == 0:
+            break
+    lp, ln = state.index_lists()
+    assert np.array_equal(lp, pos) and np.array_equal(ln, neg)
+    rc.close()
+
+
 def test_large_equivalent_rule_sets():
     """Tens of thousands of equivalent rules (duplicated k-mers, as on real genomes): the device-sorted path of
     both tie collectors, single- and multi-shard, against the checker."""

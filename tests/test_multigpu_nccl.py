@@ -36,7 +36,7 @@ def test_sharded_learners_over_nccl():
     outs = []
     for p in procs:
         try:
-            o, _ = p.communicate(timeout=240)
+            o, _ = p.communicate(timeout=600)
         except subprocess.TimeoutExpired:
             for q in procs:
                 q.kill()
