@@ -451,13 +451,14 @@ def measure_shape(name, n_genomes, k_local, world, rank, local_rank, comm, seed,
         warm = OccurrenceTiebreaker(rc, train)
         DecisionTreeClassifier("gini", 3, 2, {0: 1.0, 1: 1.0}).fit(rules, rc, ex, tiebreaker=warm)
         warm.release()
-        t = DecisionTreeClassifier("gini", 10, 2, {0: 1.0, 1: 1.0})
-        ia = shard.info()
-        t0 = _t.perf_counter()
-        tb = OccurrenceTiebreaker(rc, train)
-        t.fit(rules, rc, ex, tiebreaker=tb)
-        tb.release()
-        out["depth10_fit_s"] = _t.perf_counter() - t0
+        for attempt in ("first", "steady"):      # the first deep fit grows the pinned tie arena / sort buffers once
+            t = DecisionTreeClassifier("gini", 10, 2, {0: 1.0, 1: 1.0})
+            ia = shard.info()
+            t0 = _t.perf_counter()
+            tb = OccurrenceTiebreaker(rc, train)
+            t.fit(rules, rc, ex, tiebreaker=tb)
+            tb.release()
+            out["depth10_fit_s" if attempt == "steady" else "depth10_first_fit_s"] = _t.perf_counter() - t0
         out["depth10_split_nodes"] = len(t.decision_tree.rules)
         out["depth10_matrix_passes"] = shard.info().scan_calls - ia.scan_calls
     rc.close()

@@ -851,7 +851,8 @@ __device__ void p2p_exchange_merge(const Scan2Params &P, double *s_bm, double *s
         s_status = 0;
         s_stamp[0] = globaltimer_ns();           // packet published (stores issued), about to exchange flags
     }
-    __threadfence_system();
+    // (no separate system fence here: the packet stores of all threads happen-before the barrier, and the flag store
+    //  below is a release at system scope, which is cumulative over them)
     consumer_bar(NT);
     if (tid < world) {
         unsigned long long *f = X.peer_flags[tid] + X.rank;
@@ -868,8 +869,7 @@ __device__ void p2p_exchange_merge(const Scan2Params &P, double *s_bm, double *s
             }
         }
     }
-    __threadfence_system();
-    consumer_bar(NT);
+    consumer_bar(NT);                            // (the acquire loads above order the packet reads below, through the barrier)
     if (tid == 0) s_stamp[1] = globaltimer_ns();    // every peer's packet has arrived
     const char *box = X.peer_box[X.rank] + (size_t)parity * world * X.slot_bytes;
     for (long long b = tid; b < F.n_blocks; b += NT) {
@@ -1993,6 +1993,11 @@ struct kv_shard {
     long long state_n_pos = 0, state_n_neg = 0;
     int state_n_act = 0, state_n_both = 0;
     bool profiling = false;                   // CUDA events around the scan kernels (kv_set_profiling / KOVER_B200_PROFILE)
+    // deflate upload: page-locked staging slots + copy stream (kv_upload_deflate)
+    cudaStream_t inf_copy_stream = nullptr;
+    void *inf_pin[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t inf_pin_free[4] = {nullptr, nullptr, nullptr, nullptr};
+    size_t inf_slot_bytes = 0;
     DevBuf d_level;                           // kv_gini_level: per-node minima, counters, tie slots, segment minima
     std::vector<uint32_t *> occ_tables;       // kv_occ_table_set: k-mer occurrence counts of a training set, [ld] each
     int64_t *h_level = nullptr;               // pinned arena: the tie lists of the last kv_gini_level, node after node
@@ -2124,6 +2129,11 @@ extern "C" int kv_destroy(kv_shard *s) {
     if (s->h_level) cudaFreeHost(s->h_level);
     if (s->h_fused) cudaFreeHost(s->h_fused);
     if (s->h_state) cudaFreeHost(s->h_state);
+    for (int i = 0; i < 4; ++i) {
+        if (s->inf_pin[i]) cudaFreeHost(s->inf_pin[i]);
+        if (s->inf_pin_free[i]) cudaEventDestroy(s->inf_pin_free[i]);
+    }
+    if (s->inf_copy_stream) cudaStreamDestroy(s->inf_copy_stream);
     if (s->d_state) cudaFree(s->d_state);
     if (s->d_fused_ctr) cudaFree(s->d_fused_ctr);
     if (s->d_fused_bm) cudaFree(s->d_fused_bm);
@@ -2265,47 +2275,16 @@ extern "C" int kv_upload_block(kv_shard *s, int pack_bits, int64_t row0, int64_t
 #include "kv_inflate.cuh"
 
 namespace {
-struct DeflateUploader {
-    static constexpr int kSlots = 4;
-    cudaStream_t copy_stream = nullptr;
-    void *pin[kSlots] = {nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t pin_free[kSlots] = {nullptr, nullptr, nullptr, nullptr};
-    size_t slot_bytes = 0;
-    unsigned char *d_comp[2] = {nullptr, nullptr}, *d_scratch[2] = {nullptr, nullptr};
-    InflateJob *d_jobs[2] = {nullptr, nullptr};
-    ScatterJob *d_sjobs[2] = {nullptr, nullptr};
-    int *d_status = nullptr;
-    unsigned int *d_next = nullptr;
-    cudaEvent_t copied[2] = {nullptr, nullptr}, done[2] = {nullptr, nullptr};
-    ~DeflateUploader() {
-        for (int i = 0; i < 2; ++i) {
-            if (d_comp[i]) cudaFree(d_comp[i]);
-            if (d_scratch[i]) cudaFree(d_scratch[i]);
-            if (d_jobs[i]) cudaFree(d_jobs[i]);
-            if (d_sjobs[i]) cudaFree(d_sjobs[i]);
-            if (copied[i]) cudaEventDestroy(copied[i]);
-            if (done[i]) cudaEventDestroy(done[i]);
-        }
-        if (d_status) cudaFree(d_status);
-        if (d_next) cudaFree(d_next);
-        for (int i = 0; i < kSlots; ++i) {
-            if (pin[i]) cudaFreeHost(pin[i]);
-            if (pin_free[i]) cudaEventDestroy(pin_free[i]);
-        }
-        if (copy_stream) cudaStreamDestroy(copy_stream);
-    }
-};
-
 // copy `n` byte ranges (src[i], bytes[i]) to dst + off[i] with a few threads (page cache -> pinned memory)
-void gather_streams(char *dst, const void *const *src, const int64_t *bytes, const size_t *off, int64_t i0, int64_t i1) {
+void gather_streams(char *dst, const void *const *src, const int64_t *bytes, const size_t *off, int64_t n) {
     const unsigned hw = std::thread::hardware_concurrency();
     static const unsigned max_threads =
-        getenv("KOVER_B200_UPLOAD_THREADS") ? (unsigned)atoi(getenv("KOVER_B200_UPLOAD_THREADS")) : 8u;
+        getenv("KOVER_B200_UPLOAD_THREADS") ? (unsigned)atoi(getenv("KOVER_B200_UPLOAD_THREADS")) : 16u;
     size_t total = 0;
-    for (int64_t i = i0; i < i1; ++i) total += (size_t)bytes[i];
+    for (int64_t i = 0; i < n; ++i) total += (size_t)bytes[i];
     const int n_threads = total < ((size_t)2 << 20) ? 1 : (int)std::max(1u, std::min(hw ? hw : 1u, std::max(1u, max_threads)));
     auto work = [&](int t) {
-        for (int64_t i = i0 + t; i < i1; i += n_threads) memcpy(dst + off[i], src[i], (size_t)bytes[i]);
+        for (int64_t i = t; i < n; i += n_threads) memcpy(dst + off[i], src[i], (size_t)bytes[i]);
     };
     if (n_threads == 1) {
         work(0);
@@ -2315,7 +2294,34 @@ void gather_streams(char *dst, const void *const *src, const int64_t *bytes, con
     for (int t = 0; t < n_threads; ++t) pool.emplace_back(work, t);
     for (auto &th : pool) th.join();
 }
+
+struct DevFree {                      // frees device buffers / events of one kv_upload_deflate call on every exit path
+    std::vector<void *> bufs;
+    std::vector<cudaEvent_t> events;
+    ~DevFree() {
+        for (void *p : bufs)
+            if (p) cudaFree(p);
+        for (cudaEvent_t e : events)
+            if (e) cudaEventDestroy(e);
+    }
+};
 }   // namespace
+
+static constexpr int kInflateSlots = 4;
+
+// page-locked staging slots + the copy stream of the deflate upload: allocated once per shard (pinning memory is slow)
+static int ensure_inflate_staging(kv_shard *s, size_t slot_bytes) {
+    if (!s->inf_copy_stream) CU(cudaStreamCreateWithFlags(&s->inf_copy_stream, cudaStreamNonBlocking));
+    if (s->inf_slot_bytes >= slot_bytes) return KV_OK;
+    for (int i = 0; i < kInflateSlots; ++i) {
+        if (s->inf_pin[i]) cudaFreeHost(s->inf_pin[i]);
+        s->inf_pin[i] = nullptr;
+        CU(cudaMallocHost(&s->inf_pin[i], slot_bytes));
+        if (!s->inf_pin_free[i]) CU(cudaEventCreateWithFlags(&s->inf_pin_free[i], cudaEventDisableTiming));
+    }
+    s->inf_slot_bytes = slot_bytes;
+    return KV_OK;
+}
 
 extern "C" int kv_upload_deflate(kv_shard *s, int pack_bits, int64_t n_chunks, const void *const *src,
                                  const int64_t *src_bytes, const int64_t *row0, const int64_t *gcol0,
@@ -2346,134 +2352,178 @@ extern "C" int kv_upload_deflate(kv_shard *s, int pack_bits, int64_t n_chunks, c
     };
     const auto t_begin = now();
     double t_gather = 0.0;
+    float t_kernels = 0.f;
+    DevFree F;
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;
     if (stats) {
         cudaEventCreate(&ev_k0);
         cudaEventCreate(&ev_k1);
+        F.events.push_back(ev_k0);
+        F.events.push_back(ev_k1);
     }
-    DeflateUploader U;
-    // decode slabs: enough chunks to occupy every SM, bounded by a quarter of the free HBM for the two scratch parities
+    // A chunk that lies wholly inside this shard's part of the dataset (one 64-bit packed row, 16-byte aligned
+    // destination) inflates straight into its row of the resident image; edge chunks, chunks cut by a shard boundary,
+    // multi-row chunks and 32-bit packing inflate into a scratch slot and are placed by k_scatter_chunks.
+    auto direct = [&](int64_t i) {
+        return pack_bits == 64 && chunk_rows == 1 && row0[i] < rows_total && gcol0[i] >= s->col0 &&
+               gcol0[i] + chunk_cols <= s->col0 + s->n_cols && ((gcol0[i] - s->col0) & 1) == 0;
+    };
     const size_t chunk_stride = (chunk_bytes + 15) / 16 * 16;
+    auto comp_bytes = [&](int64_t i) { return ((size_t)src_bytes[i] + 4 + 15) / 16 * 16; };
+    // decode slabs: enough chunks to occupy every SM several times over, bounded by a quarter of the free HBM
     size_t free_b = 0, total_b = 0;
     CU(cudaMemGetInfo(&free_b, &total_b));
-    int64_t slab = std::min<int64_t>(n_chunks, 4096);
+    // One warp needs ~0.1 s per 800 KB chunk whatever the load (a single lane walks the Huffman stream), so the call
+    // lasts (time to stage the last slab) + (one slab's kernel): small uploads are cut into up to four slabs whose
+    // kernels run concurrently on their own streams and start as soon as their streams have arrived.
+    int64_t slab = std::min<int64_t>(n_chunks, 8192);
+    if (n_chunks <= 8192) slab = std::max<int64_t>(256, (n_chunks + 3) / 4);
     while (slab > 64 && (size_t)slab * chunk_stride * 4 > free_b / 4) slab /= 2;
-    size_t max_comp = 0;
+    size_t max_comp = 0, max_scratch = 0, biggest = 0;
     for (int64_t a = 0; a < n_chunks; a += slab) {
-        size_t c = 0;
-        for (int64_t i = a; i < std::min(n_chunks, a + slab); ++i) c += ((size_t)src_bytes[i] + 4 + 15) / 16 * 16;
+        size_t c = 0, q = 0;
+        for (int64_t i = a; i < std::min(n_chunks, a + slab); ++i) {
+            c += comp_bytes(i);
+            q += direct(i) ? 0 : 1;
+            biggest = std::max(biggest, comp_bytes(i));
+        }
         max_comp = std::max(max_comp, c);
+        max_scratch = std::max(max_scratch, q);
     }
-    U.slot_bytes = (size_t)16 << 20;
-    size_t biggest = 0;
-    for (int64_t i = 0; i < n_chunks; ++i) biggest = std::max(biggest, ((size_t)src_bytes[i] + 4 + 15) / 16 * 16);
-    U.slot_bytes = std::max(U.slot_bytes, biggest);
-    CU(cudaStreamCreateWithFlags(&U.copy_stream, cudaStreamNonBlocking));
-    for (int i = 0; i < DeflateUploader::kSlots; ++i) {
-        CU(cudaMallocHost(&U.pin[i], U.slot_bytes));
-        CU(cudaEventCreateWithFlags(&U.pin_free[i], cudaEventDisableTiming));
-    }
-    const int n_par = n_chunks > slab ? 2 : 1;
+    KV_TRY(ensure_inflate_staging(s, std::max((size_t)16 << 20, biggest)));
+    constexpr int kMaxPar = 4;
+    const size_t n_slabs = (size_t)((n_chunks + slab - 1) / slab);
+    const int n_par = (int)std::min<size_t>(kMaxPar, n_slabs);
+    unsigned char *d_comp[kMaxPar] = {nullptr}, *d_scratch[kMaxPar] = {nullptr};
+    InflateJob *d_jobs[kMaxPar] = {nullptr};
+    ScatterJob *d_sjobs[kMaxPar] = {nullptr};
+    cudaEvent_t copied[kMaxPar] = {nullptr}, done[kMaxPar] = {nullptr};
+    cudaStream_t k_stream[kMaxPar] = {s->stream, nullptr, nullptr, nullptr};
+    struct StreamFree {
+        cudaStream_t *st;
+        ~StreamFree() {
+            for (int i = 1; i < kMaxPar; ++i)
+                if (st[i]) cudaStreamDestroy(st[i]);
+        }
+    } stream_free{k_stream};
+    for (int i = 1; i < n_par; ++i) CU(cudaStreamCreateWithFlags(&k_stream[i], cudaStreamNonBlocking));
     for (int i = 0; i < n_par; ++i) {
-        CU(cudaMalloc(&U.d_comp[i], max_comp + 64));
-        CU(cudaMalloc(&U.d_scratch[i], (size_t)slab * chunk_stride));
-        CU(cudaMalloc(&U.d_jobs[i], (size_t)slab * sizeof(InflateJob)));
-        CU(cudaMalloc(&U.d_sjobs[i], (size_t)slab * sizeof(ScatterJob)));
-        CU(cudaEventCreateWithFlags(&U.copied[i], cudaEventDisableTiming));
-        CU(cudaEventCreateWithFlags(&U.done[i], cudaEventDisableTiming));
+        CU(cudaMalloc(&d_comp[i], max_comp + 64));
+        F.bufs.push_back(d_comp[i]);
+        if (max_scratch) {
+            CU(cudaMalloc(&d_scratch[i], max_scratch * chunk_stride));
+            F.bufs.push_back(d_scratch[i]);
+            CU(cudaMalloc(&d_sjobs[i], max_scratch * sizeof(ScatterJob)));
+            F.bufs.push_back(d_sjobs[i]);
+        }
+        CU(cudaMalloc(&d_jobs[i], (size_t)slab * sizeof(InflateJob)));
+        F.bufs.push_back(d_jobs[i]);
+        CU(cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming));
+        F.events.push_back(copied[i]);
+        CU(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
+        F.events.push_back(done[i]);
     }
-    CU(cudaMalloc(&U.d_status, (size_t)n_chunks * sizeof(int)));
-    CU(cudaMalloc(&U.d_next, ((size_t)(n_chunks + slab - 1) / slab) * sizeof(unsigned int)));
-    CU(cudaMemsetAsync(U.d_status, 0xFF, (size_t)n_chunks * sizeof(int), s->stream));
-    CU(cudaMemsetAsync(U.d_next, 0, ((size_t)(n_chunks + slab - 1) / slab) * sizeof(unsigned int), s->stream));
+    int *d_status = nullptr;
+    unsigned int *d_next = nullptr;
+    CU(cudaMalloc(&d_status, (size_t)n_chunks * sizeof(int)));
+    F.bufs.push_back(d_status);
+    CU(cudaMalloc(&d_next, n_slabs * sizeof(unsigned int)));
+    F.bufs.push_back(d_next);
+    CU(cudaMemsetAsync(d_status, 0xFF, (size_t)n_chunks * sizeof(int), s->stream));
+    CU(cudaMemsetAsync(d_next, 0, n_slabs * sizeof(unsigned int), s->stream));
     CU(cudaStreamSynchronize(s->stream));
     const double t_setup = ms_since(t_begin);
-    float t_kernels = 0.f;
     std::vector<InflateJob> jobs((size_t)slab);
-    std::vector<ScatterJob> sjobs((size_t)slab);
-    std::vector<size_t> off((size_t)n_chunks);
+    std::vector<ScatterJob> sjobs(max_scratch);
+    std::vector<size_t> off((size_t)slab);
     int slot = 0;
     int64_t slab_no = 0;
     for (int64_t a = 0; a < n_chunks; a += slab, ++slab_no) {
         const int64_t b = std::min(n_chunks, a + slab);
-        const int par = (int)(slab_no & 1) % n_par;
-        if (slab_no >= 2) CU(cudaStreamWaitEvent(U.copy_stream, U.done[par], 0));     // the buffers of slab - 2 are free again
-        // layout of the slab's streams in the device buffer, and of its output in the scratch
-        size_t c = 0;
+        const int par = (int)(slab_no % n_par);
+        cudaStream_t ks = k_stream[par];
+        if (slab_no >= n_par) CU(cudaStreamWaitEvent(s->inf_copy_stream, done[par], 0));   // this parity's buffers are free again
+        // layout of the slab's streams in the device buffer; destination of every chunk
+        size_t c = 0, n_scr = 0;
         for (int64_t i = a; i < b; ++i) {
-            off[(size_t)i] = c;
+            off[(size_t)(i - a)] = c;
             InflateJob &J = jobs[(size_t)(i - a)];
             J.src_off = c;
             J.src_bytes = (unsigned int)src_bytes[i];
             J.dst_bytes = (unsigned int)chunk_bytes;
-            J.dst_off = (size_t)(i - a) * chunk_stride;
-            ScatterJob &Q = sjobs[(size_t)(i - a)];
-            Q.src_off = J.dst_off;
-            Q.row0 = row0[i];
-            Q.gcol0 = gcol0[i];
-            Q.ok = 1;
-            c += ((size_t)src_bytes[i] + 4 + 15) / 16 * 16;
+            if (direct(i)) {
+                J.dst = (unsigned char *)(s->d_mat + row0[i] * s->ld + (gcol0[i] - s->col0));
+            } else {
+                J.dst = d_scratch[par] + n_scr * chunk_stride;
+                ScatterJob &Q = sjobs[n_scr++];
+                Q.src = J.dst;
+                Q.row0 = row0[i];
+                Q.gcol0 = gcol0[i];
+            }
+            c += comp_bytes(i);
         }
         // stream the compressed bytes through the pinned slots: whole chunks per slot
         int64_t i = a;
         while (i < b) {
-            const size_t base = off[(size_t)i];
+            const size_t base = off[(size_t)(i - a)];
             int64_t j = i;
-            while (j < b && off[(size_t)j] + ((size_t)src_bytes[j] + 4 + 15) / 16 * 16 - base <= U.slot_bytes) ++j;
-            CU(cudaEventSynchronize(U.pin_free[slot]));
+            while (j < b && off[(size_t)(j - a)] + comp_bytes(j) - base <= s->inf_slot_bytes) ++j;
+            CU(cudaEventSynchronize(s->inf_pin_free[slot]));
             std::vector<size_t> rel((size_t)(j - i));
-            for (int64_t q = i; q < j; ++q) rel[(size_t)(q - i)] = off[(size_t)q] - base;
+            for (int64_t q = i; q < j; ++q) rel[(size_t)(q - i)] = off[(size_t)(q - a)] - base;
             const auto t_g = now();
-            gather_streams((char *)U.pin[slot], src + i, src_bytes + i, rel.data(), 0, j - i);
+            gather_streams((char *)s->inf_pin[slot], src + i, src_bytes + i, rel.data(), j - i);
             t_gather += ms_since(t_g);
-            const size_t span = (j < b ? off[(size_t)j] : c) - base;
-            CU(cudaMemcpyAsync(U.d_comp[par] + base, U.pin[slot], span, cudaMemcpyHostToDevice, U.copy_stream));
-            CU(cudaEventRecord(U.pin_free[slot], U.copy_stream));
-            slot = (slot + 1) % DeflateUploader::kSlots;
+            const size_t span = (j < b ? off[(size_t)(j - a)] : c) - base;
+            CU(cudaMemcpyAsync(d_comp[par] + base, s->inf_pin[slot], span, cudaMemcpyHostToDevice, s->inf_copy_stream));
+            CU(cudaEventRecord(s->inf_pin_free[slot], s->inf_copy_stream));
+            slot = (slot + 1) % kInflateSlots;
             i = j;
         }
-        CU(cudaMemcpyAsync(U.d_jobs[par], jobs.data(), (size_t)(b - a) * sizeof(InflateJob), cudaMemcpyHostToDevice, U.copy_stream));
-        CU(cudaMemcpyAsync(U.d_sjobs[par], sjobs.data(), (size_t)(b - a) * sizeof(ScatterJob), cudaMemcpyHostToDevice, U.copy_stream));
-        CU(cudaEventRecord(U.copied[par], U.copy_stream));
-        CU(cudaStreamSynchronize(U.copy_stream));            // `jobs` / `sjobs` are reused by the next slab
-        CU(cudaStreamWaitEvent(s->stream, U.copied[par], 0));
         const int n_here = (int)(b - a);
+        CU(cudaMemcpyAsync(d_jobs[par], jobs.data(), (size_t)n_here * sizeof(InflateJob), cudaMemcpyHostToDevice, s->inf_copy_stream));
+        if (n_scr)
+            CU(cudaMemcpyAsync(d_sjobs[par], sjobs.data(), n_scr * sizeof(ScatterJob), cudaMemcpyHostToDevice, s->inf_copy_stream));
+        CU(cudaEventRecord(copied[par], s->inf_copy_stream));
+        CU(cudaStreamSynchronize(s->inf_copy_stream));           // `jobs` / `sjobs` are reused by the next slab
+        CU(cudaStreamWaitEvent(ks, copied[par], 0));
         const int grid = (int)std::min<long long>((n_here + INF_WARPS - 1) / INF_WARPS, (long long)s->sm_count * 6);
-        if (stats) cudaEventRecord(ev_k0, s->stream);
-        k_inflate<<<grid, INF_WARPS * 32, 0, s->stream>>>(U.d_comp[par], U.d_scratch[par], U.d_jobs[par], n_here,
-                                                          U.d_status + a, U.d_next + slab_no);
+        if (stats) cudaEventRecord(ev_k0, ks);
+        k_inflate<<<grid, INF_WARPS * 32, 0, ks>>>(d_comp[par], d_jobs[par], n_here, d_status + a, d_next + slab_no);
         if (stats) {
-            cudaEventRecord(ev_k1, s->stream);
+            cudaEventRecord(ev_k1, ks);
             cudaEventSynchronize(ev_k1);
             float ms = 0.f;
             cudaEventElapsedTime(&ms, ev_k0, ev_k1);
             t_kernels += ms;
         }
-        const long long per_chunk = (long long)chunk_rows * chunk_cols;
-        const dim3 sgrid((unsigned)std::min<long long>((per_chunk + 255) / 256, 64), (unsigned)n_here);
-        // (a failed chunk is scattered too and re-done by the caller: its rows are overwritten then)
-        if (pack_bits == 64)
-            k_scatter_chunks<uint64_t><<<sgrid, 256, 0, s->stream>>>(U.d_scratch[par], U.d_sjobs[par], s->d_mat, s->ld, s->col0,
-                                                                     s->n_cols, rows_total, s->k_total, (int)chunk_rows, chunk_cols);
-        else
-            k_scatter_chunks<uint32_t><<<sgrid, 256, 0, s->stream>>>(U.d_scratch[par], U.d_sjobs[par], s->d_mat, s->ld, s->col0,
-                                                                     s->n_cols, rows_total, s->k_total, (int)chunk_rows, chunk_cols);
-        count_launch(s, 2);
-        CU(cudaEventRecord(U.done[par], s->stream));
+        count_launch(s);
+        if (n_scr) {
+            // (a chunk the kernel rejected is scattered too: the caller re-does it on the host, overwriting its rows)
+            const long long per_chunk = (long long)chunk_rows * chunk_cols;
+            const dim3 sgrid((unsigned)std::min<long long>((per_chunk + 255) / 256, 64), (unsigned)n_scr);
+            if (pack_bits == 64)
+                k_scatter_chunks<uint64_t><<<sgrid, 256, 0, ks>>>(d_sjobs[par], s->d_mat, s->ld, s->col0, s->n_cols,
+                                                                  rows_total, s->k_total, (int)chunk_rows, chunk_cols);
+            else
+                k_scatter_chunks<uint32_t><<<sgrid, 256, 0, ks>>>(d_sjobs[par], s->d_mat, s->ld, s->col0, s->n_cols,
+                                                                  rows_total, s->k_total, (int)chunk_rows, chunk_cols);
+            count_launch(s);
+        }
+        CU(cudaEventRecord(done[par], ks));
     }
+    for (int i = 1; i < n_par; ++i) CU(cudaStreamSynchronize(k_stream[i]));
     static_assert(sizeof(int) == sizeof(int32_t), "status array");
-    CU(cudaMemcpyAsync(status, U.d_status, (size_t)n_chunks * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaMemcpyAsync(status, d_status, (size_t)n_chunks * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
     CU(cudaGetLastError());
     if (stats) {
         size_t comp = 0;
         for (int64_t q = 0; q < n_chunks; ++q) comp += (size_t)src_bytes[q];
-        fprintf(stderr, "kv_upload_deflate: %lld chunks (%.1f MB deflated -> %.1f MB), slabs of %lld: setup %.1f ms, "
-                        "gather %.1f ms, inflate kernels %.1f ms (serialised for this report), total %.1f ms\n",
-                (long long)n_chunks, comp / 1e6, (double)n_chunks * chunk_bytes / 1e6, (long long)slab, t_setup, t_gather,
-                t_kernels, ms_since(t_begin));
-        cudaEventDestroy(ev_k0);
-        cudaEventDestroy(ev_k1);
+        fprintf(stderr, "kv_upload_deflate: %lld chunks (%.1f MB deflated -> %.1f MB), slabs of %lld, %zu via scratch: setup "
+                        "%.1f ms, gather %.1f ms, inflate kernels %.1f ms (serialised for this report), total %.1f ms\n",
+                (long long)n_chunks, comp / 1e6, (double)n_chunks * chunk_bytes / 1e6, (long long)slab, max_scratch, t_setup,
+                t_gather, t_kernels, ms_since(t_begin));
     }
     return KV_OK;
 }

@@ -32,15 +32,15 @@ struct InflateJob {
     unsigned long long src_off;     // byte offset of the zlib stream in the compressed slab (16-byte aligned)
     unsigned int src_bytes;
     unsigned int dst_bytes;         // expected size after inflation
-    unsigned long long dst_off;     // byte offset in the scratch slab (16-byte aligned)
-};
+    unsigned char *dst;             // where the chunk inflates to (16-byte aligned): its row of the resident image when
+};                                  // the chunk lies wholly inside the shard, else a slot of the scratch slab
 
 static constexpr int INF_WARPS = 8;            // chunks decoded concurrently per CTA
 static constexpr int INF_LIT_BITS = 10, INF_DIST_BITS = 8;
 static constexpr int INF_STAGE = 128;          // literals staged per batch
 
 struct InflateWarp {                            // per-warp shared memory (~3.8 KB)
-    unsigned short lit_tab[1 << INF_LIT_BITS];  // (symbol << 4) | code length; 0 = longer code / unused
+    unsigned short lit_tab[1 << INF_LIT_BITS];  // (symbol << 4) | code length, bit 15 = literal; 0 = longer code / unused
     unsigned short dist_tab[1 << INF_DIST_BITS];
     unsigned short lit_sym[288], dist_sym[32];  // symbols in canonical order
     unsigned short lit_cnt[16], dist_cnt[16];   // codes per length
@@ -122,7 +122,7 @@ __device__ __forceinline__ int br_slow_symbol(BitReader &b, const unsigned short
 // Canonical Huffman set-up from code lengths (whole warp).  lens[n] -> cnt[16], sym[] (canonical order), primary table
 // tab[1 << bits].  Returns false for an over-subscribed set of lengths.
 __device__ __forceinline__ bool build_tables(const unsigned char *lens, int n, unsigned short *cnt, unsigned short *sym,
-                             unsigned short *tab, int bits, int lane) {
+                             unsigned short *tab, int bits, int lane, bool flag_literals) {
     __shared__ unsigned short s_first_code[INF_WARPS][16], s_first_idx[INF_WARPS][16];
     const int w = threadIdx.x >> 5;
     for (int i = lane; i < (1 << bits); i += 32) tab[i] = 0;
@@ -166,7 +166,8 @@ __device__ __forceinline__ bool build_tables(const unsigned char *lens, int n, u
         if (l > bits) continue;
         const unsigned int code = (unsigned int)s_first_code[w][l] + (unsigned int)(i - s_first_idx[w][l]);
         const unsigned int rev = __brev(code) >> (32 - l);
-        const unsigned short e = (unsigned short)((s << 4) | l);
+        // bit 15 marks a literal (symbol < 256) in the literal/length table: the symbol loop's fast path
+        const unsigned short e = (unsigned short)((s << 4) | l | ((flag_literals && s < 256) ? 0x8000 : 0));
         for (unsigned int j = rev; j < (1u << bits); j += (1u << l)) tab[j] = e;
     }
     __syncwarp();
@@ -280,9 +281,8 @@ __device__ __forceinline__ unsigned int warp_adler32(const unsigned char *dst, u
     return (unsigned int)((s2 << 16) | s1);
 }
 
-__global__ void __launch_bounds__(INF_WARPS * 32) k_inflate(const unsigned char *src_base, unsigned char *dst_base,
-                                                             const InflateJob *jobs, int n_jobs, int *status,
-                                                             unsigned int *next_job) {
+__global__ void __launch_bounds__(INF_WARPS * 32) k_inflate(const unsigned char *src_base, const InflateJob *jobs,
+                                                             int n_jobs, int *status, unsigned int *next_job) {
     __shared__ InflateWarp s_w[INF_WARPS];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     InflateWarp &S = s_w[wid];
@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(INF_WARPS * 32) k_inflate(const unsigned char 
         job = __shfl_sync(0xffffffffu, job, 0);
         if (job >= n_jobs) return;
         const InflateJob J = jobs[job];
-        unsigned char *dst = dst_base + J.dst_off;
+        unsigned char *dst = J.dst;
         BitReader b;
         b.words = reinterpret_cast<const unsigned int *>(src_base + J.src_off);
         b.n_words = (J.src_bytes + 3) / 4;
@@ -363,8 +363,8 @@ __global__ void __launch_bounds__(INF_WARPS * 32) k_inflate(const unsigned char 
                 if (st != INF_OK) break;
             }
             __syncwarp();
-            if (!build_tables(S.lens, hlit, S.lit_cnt, S.lit_sym, S.lit_tab, INF_LIT_BITS, lane) ||
-                !build_tables(S.lens + hlit, hdist, S.dist_cnt, S.dist_sym, S.dist_tab, INF_DIST_BITS, lane)) {
+            if (!build_tables(S.lens, hlit, S.lit_cnt, S.lit_sym, S.lit_tab, INF_LIT_BITS, lane, true) ||
+                !build_tables(S.lens + hlit, hdist, S.dist_cnt, S.dist_sym, S.dist_tab, INF_DIST_BITS, lane, false)) {
                 st = INF_BAD_LENGTHS;
                 break;
             }
@@ -374,9 +374,20 @@ __global__ void __launch_bounds__(INF_WARPS * 32) k_inflate(const unsigned char 
                 int nlit = 0, mlen = 0, mdist = 0;
                 if (lane == 0) {
 #pragma unroll 1
-                    while (nlit < INF_STAGE) {
-                        br_refill(b);
-                        unsigned int e = S.lit_tab[(unsigned int)b.buf & ((1u << INF_LIT_BITS) - 1u)];
+                    for (;;) {
+                        // tight loop over short literal codes (entry bit 15): refill, look up, consume, stage
+                        unsigned int e;
+#pragma unroll 1
+                        for (;;) {
+                            br_refill(b);
+                            e = S.lit_tab[(unsigned int)b.buf & ((1u << INF_LIT_BITS) - 1u)];
+                            if (!(e & 0x8000u)) break;
+                            b.buf >>= (e & 15u);
+                            b.cnt -= (int)(e & 15u);
+                            S.stage[nlit] = (unsigned char)(e >> 4);
+                            if (++nlit == INF_STAGE) break;
+                        }
+                        if (nlit == INF_STAGE) break;
                         int sym;
                         if (e & 15u) {
                             b.buf >>= (e & 15u);
@@ -389,8 +400,9 @@ __global__ void __launch_bounds__(INF_WARPS * 32) k_inflate(const unsigned char 
                                 break;
                             }
                         }
-                        if (sym < 256) {
-                            S.stage[nlit++] = (unsigned char)sym;
+                        if (sym < 256) {                          // a literal with a code longer than the table
+                            S.stage[nlit] = (unsigned char)sym;
+                            if (++nlit == INF_STAGE) break;
                             continue;
                         }
                         if (sym == 256) {
@@ -473,19 +485,17 @@ __global__ void __launch_bounds__(INF_WARPS * 32) k_inflate(const unsigned char 
 // starting at (row0, gcol0); only the part inside the dataset and inside this shard's columns is kept (HDF5 stores
 // edge chunks at full size; shards are cut on 512-column tiles, so a chunk can belong to two shards).
 struct ScatterJob {
-    unsigned long long src_off;     // in the scratch slab
+    const unsigned char *src;       // the inflated chunk in the scratch slab
     long long row0, gcol0;          // dataset coordinates of the chunk's first element (row in pack_bits units)
-    int ok;                         // 0: skip (the host re-does this chunk)
 };
 
 template <typename T>
-__global__ void __launch_bounds__(256) k_scatter_chunks(const unsigned char *scratch, const ScatterJob *jobs, uint64_t *mat,
+__global__ void __launch_bounds__(256) k_scatter_chunks(const ScatterJob *jobs, uint64_t *mat,
                                                          long long ld, long long shard_col0, long long shard_cols,
                                                          long long n_rows_total, long long n_cols_total,
                                                          int chunk_rows, long long chunk_cols) {
     const ScatterJob J = jobs[blockIdx.y];
-    if (!J.ok) return;
-    const T *src = reinterpret_cast<const T *>(scratch + J.src_off);
+    const T *src = reinterpret_cast<const T *>(J.src);
     const long long per_chunk = (long long)chunk_rows * chunk_cols;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < per_chunk; e += (long long)gridDim.x * blockDim.x) {
         const long long r = J.row0 + e / chunk_cols, c = J.gcol0 + e % chunk_cols;

@@ -96,7 +96,7 @@ def test_device_inflate_matches_host_path(tmp_path, monkeypatch, case, devices):
         rc.close()
         f.close()
         if mode == "1":
-            assert launches >= 2 * len(devices)               # the inflate + scatter kernels ran
+            assert launches >= len(devices)                   # the inflate kernel ran on every shard
     assert np.array_equal(images["1"], want)
     assert np.array_equal(images["0"], want)
 
