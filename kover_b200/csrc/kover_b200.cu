@@ -2489,7 +2489,12 @@ extern "C" int kv_upload_deflate(kv_shard *s, int pack_bits, int64_t n_chunks, c
         CU(cudaStreamWaitEvent(ks, copied[par], 0));
         const int grid = (int)std::min<long long>((n_here + INF_WARPS - 1) / INF_WARPS, (long long)s->sm_count * 6);
         if (stats) cudaEventRecord(ev_k0, ks);
-        k_inflate<<<grid, INF_WARPS * 32, 0, ks>>>(d_comp[par], d_jobs[par], n_here, d_status + a, d_next + slab_no);
+        // (KOVER_B200_INFLATE_V=1: the first decoder, one lane walking the whole stream -- kept for comparison)
+        const int inflate_v = getenv("KOVER_B200_INFLATE_V") ? atoi(getenv("KOVER_B200_INFLATE_V")) : 2;
+        if (inflate_v == 1)
+            k_inflate<<<grid, INF_WARPS * 32, 0, ks>>>(d_comp[par], d_jobs[par], n_here, d_status + a, d_next + slab_no);
+        else
+            k_inflate2<<<grid, INF_WARPS * 32, 0, ks>>>(d_comp[par], d_jobs[par], n_here, d_status + a, d_next + slab_no);
         if (stats) {
             cudaEventRecord(ev_k1, ks);
             cudaEventSynchronize(ev_k1);

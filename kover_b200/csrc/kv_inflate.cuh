@@ -481,6 +481,328 @@ __global__ void __launch_bounds__(INF_WARPS * 32) k_inflate(const unsigned char 
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// k_inflate2: the same decoder with the LITERAL RUNS decoded by the whole warp.
+//
+// In k_inflate one lane walks the Huffman stream: ~200 cycles per symbol, whatever else the GPU does (a dependent
+// chain with a shared-memory lookup and half a dozen branches).  Here the decoder state is just the bit position p,
+// identical in all lanes (no lane-0 section, no broadcasts), and a literal run is decoded speculatively: lane i looks
+// up the code that WOULD start at bit p + i; the codes that really are on the chain p -> p + len -> ... are found by
+// pointer doubling over the 32 candidates (each round: one redux.sync.or + one shuffle; ceil(log2(32 / shortest
+// code)) rounds, usually 3), their literals are written in parallel, and p advances past the whole run -- 4 to 6
+// symbols per iteration for ~8-bit codes.  Everything that is not a table-resident literal (length / distance pairs,
+// end of block, codes longer than the table) is decoded one symbol at a time, uniformly by all lanes, from a 64-bit
+// peek at p.  Block headers are parsed the same way.
+// ------------------------------------------------------------------------------------------------
+struct BitSrc {
+    const unsigned int *w;          // stream start, 4-byte aligned
+    unsigned int n_words;
+};
+__device__ __forceinline__ unsigned int src_word(const BitSrc &s, unsigned int i) { return i < s.n_words ? __ldg(s.w + i) : 0u; }
+__device__ __forceinline__ unsigned int peek32(const BitSrc &s, unsigned int pos) {          // 32 bits from bit `pos`
+    const unsigned int i = pos >> 5;
+    return __funnelshift_r(src_word(s, i), src_word(s, i + 1), pos & 31u);
+}
+__device__ __forceinline__ unsigned long long peek64(const BitSrc &s, unsigned int pos) {    // 64 bits from bit `pos`
+    const unsigned int i = pos >> 5, sh = pos & 31u;
+    const unsigned int w0 = src_word(s, i), w1 = src_word(s, i + 1), w2 = src_word(s, i + 2);
+    return (unsigned long long)__funnelshift_r(w0, w1, sh) | ((unsigned long long)__funnelshift_r(w1, w2, sh) << 32);
+}
+
+// dynamic block header at bit p (RFC 1951 3.2.7), executed identically by every lane; lane 0 stores the lengths
+__device__ __forceinline__ int read_dynamic_lengths2(const BitSrc &src, unsigned int &p, unsigned char *lens, int &hlit,
+                                                     int &hdist, int lane) {
+    unsigned int w = peek32(src, p);
+    hlit = (int)(w & 31u) + 257;
+    hdist = (int)((w >> 5) & 31u) + 1;
+    const int hclen = (int)((w >> 10) & 15u) + 4;
+    p += 14;
+    if (hlit > 286 || hdist > 30) return INF_BAD_LENGTHS;
+    unsigned char cl[19];
+#pragma unroll 1
+    for (int i = 0; i < 19; ++i) cl[i] = 0;
+    const unsigned long long q = peek64(src, p);                  // hclen * 3 <= 57 bits
+#pragma unroll 1
+    for (int i = 0; i < hclen; ++i) cl[c_clen_order[i]] = (unsigned char)((q >> (3 * i)) & 7ull);
+    p += 3u * (unsigned int)hclen;
+    unsigned short ccnt[16], csym[19];
+#pragma unroll 1
+    for (int l = 0; l < 16; ++l) ccnt[l] = 0;
+#pragma unroll 1
+    for (int s = 0; s < 19; ++s) ccnt[cl[s]]++;
+    ccnt[0] = 0;
+    {
+        int left = 1;
+#pragma unroll 1
+        for (int l = 1; l <= 7; ++l) {
+            left <<= 1;
+            left -= ccnt[l];
+            if (left < 0) return INF_BAD_LENGTHS;
+        }
+        unsigned short offs[16];
+        int idx = 0;
+#pragma unroll 1
+        for (int l = 1; l <= 15; ++l) {
+            offs[l] = (unsigned short)idx;
+            idx += ccnt[l];
+        }
+#pragma unroll 1
+        for (int s = 0; s < 19; ++s)
+            if (cl[s]) csym[offs[cl[s]]++] = (unsigned short)s;
+    }
+    int n = 0, prev = 0;
+    const int total = hlit + hdist;
+#pragma unroll 1
+    while (n < total) {
+        w = peek32(src, p);
+        const int r = slow_decode(w, ccnt, csym);
+        if (r < 0) return INF_BAD_CODE;
+        const int s = r & 0xFFFF, used = r >> 16;
+        w >>= used;
+        p += (unsigned int)used;
+        if (s < 16) {
+            if (lane == 0) lens[n] = (unsigned char)s;
+            ++n;
+            prev = s;
+            continue;
+        }
+        int rep, val = 0;
+        if (s == 16) {
+            if (n == 0) return INF_BAD_LENGTHS;
+            val = prev;
+            rep = 3 + (int)(w & 3u);
+            p += 2;
+        } else if (s == 17) {
+            rep = 3 + (int)(w & 7u);
+            p += 3;
+        } else {
+            rep = 11 + (int)(w & 127u);
+            p += 7;
+        }
+        if (n + rep > total) return INF_BAD_LENGTHS;
+        if (lane == 0)
+            for (int i = 0; i < rep; ++i) lens[n + i] = (unsigned char)val;
+        n += rep;
+        prev = val;
+    }
+    __syncwarp();
+    if (lens[256] == 0) return INF_BAD_LENGTHS;          // no end-of-block code
+    return INF_OK;
+}
+
+__global__ void __launch_bounds__(INF_WARPS * 32) k_inflate2(const unsigned char *src_base, const InflateJob *jobs,
+                                                              int n_jobs, int *status, unsigned int *next_job) {
+    __shared__ InflateWarp s_w[INF_WARPS];
+    const unsigned int full = 0xffffffffu;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    InflateWarp &S = s_w[wid];
+    for (;;) {
+        int job = 0;
+        if (lane == 0) job = (int)atomicAdd(next_job, 1u);
+        job = __shfl_sync(full, job, 0);
+        if (job >= n_jobs) return;
+        const InflateJob J = jobs[job];
+        unsigned char *dst = J.dst;
+        BitSrc src;
+        src.w = reinterpret_cast<const unsigned int *>(src_base + J.src_off);
+        src.n_words = (J.src_bytes + 3) / 4;
+        const unsigned int nbits = J.src_bytes * 8u;
+        int st = INF_OK;
+        unsigned int out = 0, p = 16;
+        {
+            const unsigned int w = peek32(src, 0);
+            const unsigned int cmf = w & 255u, flg = (w >> 8) & 255u;
+            if ((cmf & 15u) != 8u || (cmf >> 4) > 7u || ((cmf << 8) | flg) % 31u != 0u || (flg & 32u)) st = INF_BAD_HEADER;
+            if (J.src_bytes >= (1u << 28)) st = INF_IN_OVERRUN;            // bit positions are 32-bit
+        }
+        bool last = false;
+        while (st == INF_OK && !last) {
+            const unsigned int hw = peek32(src, p);
+            last = (hw & 1u) != 0;
+            const int btype = (int)((hw >> 1) & 3u);
+            p += 3;
+            if (btype == 0) {
+                p = (p + 7u) & ~7u;
+                const unsigned int lw = peek32(src, p);
+                const unsigned int len = lw & 0xFFFFu, nlen = lw >> 16;
+                p += 32;
+                const unsigned int byte_pos = p >> 3;
+                if ((len ^ nlen) != 0xFFFFu) st = INF_BAD_BLOCK;
+                else if (byte_pos + len > J.src_bytes) st = INF_IN_OVERRUN;
+                else if (out + len > J.dst_bytes) st = INF_OUT_OVERFLOW;
+                if (st != INF_OK) break;
+                const unsigned char *sb = src_base + J.src_off + byte_pos;
+                for (unsigned int i = lane; i < len; i += 32) dst[out + i] = sb[i];
+                out += len;
+                p += len * 8u;
+                __syncwarp();
+                continue;
+            }
+            if (btype == 3) {
+                st = INF_BAD_BLOCK;
+                break;
+            }
+            int hlit = 288, hdist = 30;
+            if (btype == 1) {
+                for (int i = lane; i < 288; i += 32) S.lens[i] = i < 144 ? 8 : (i < 256 ? 9 : (i < 280 ? 7 : 8));
+                for (int i = lane; i < 32; i += 32) S.lens[288 + i] = i < 30 ? 5 : 0;
+            } else {
+                st = read_dynamic_lengths2(src, p, S.lens, hlit, hdist, lane);
+                if (st != INF_OK) break;
+            }
+            __syncwarp();
+            if (!build_tables(S.lens, hlit, S.lit_cnt, S.lit_sym, S.lit_tab, INF_LIT_BITS, lane, true) ||
+                !build_tables(S.lens + hlit, hdist, S.dist_cnt, S.dist_sym, S.dist_tab, INF_DIST_BITS, lane, false)) {
+                st = INF_BAD_LENGTHS;
+                break;
+            }
+            // pointer-doubling rounds that cover the longest possible literal chain inside a 32-bit window
+            int minlen = 1;
+            while (minlen < 15 && S.lit_cnt[minlen] == 0) ++minlen;
+            int rounds = 1;
+            while ((1 << rounds) < 32 / minlen + 2) ++rounds;
+            // ---- symbols of the block
+            for (;;) {
+                // (1) the literal run that starts at p, all 32 candidate code starts at once
+                const unsigned int w = peek32(src, p + (unsigned int)lane);
+                const unsigned int e = S.lit_tab[w & ((1u << INF_LIT_BITS) - 1u)];
+                const bool lit = (e & 0x8000u) != 0;
+                const int nxt0 = lit ? lane + (int)(e & 15u) : 64;       // where the next code starts; 64 = not a literal
+                int jump = nxt0;
+                unsigned int reach = 1u;                                    // candidates on the chain from p (bit i = p + i)
+#pragma unroll 1
+                for (int r = 0; r < rounds; ++r) {
+                    const unsigned int add = (((reach >> lane) & 1u) && jump < 32) ? (1u << jump) : 0u;
+                    reach |= __reduce_or_sync(full, add);
+                    const int far = __shfl_sync(full, jump, jump & 31);
+                    jump = jump < 32 ? far : jump;
+                }
+                const unsigned int litmask = __ballot_sync(full, lit);
+                const unsigned int chain = reach & litmask, stop = reach & ~litmask;
+                const unsigned int count = __popc(chain);
+                if (out + count > J.dst_bytes) {
+                    st = INF_OUT_OVERFLOW;
+                    break;
+                }
+                if ((chain >> lane) & 1u) dst[out + __popc(chain & ((1u << lane) - 1u))] = (unsigned char)(e >> 4);
+                out += count;
+                if (!stop) {                                               // the run leaves the window: next window
+                    p += (unsigned int)__shfl_sync(full, nxt0, 31 - __clz(chain));
+                    if (p > nbits) {
+                        st = INF_IN_OVERRUN;
+                        break;
+                    }
+                    continue;
+                }
+                p += (unsigned int)(__ffs(stop) - 1);
+                // (2) the symbol at p is not a table-resident literal: one symbol, decoded identically by every lane
+                unsigned long long q = peek64(src, p);
+                unsigned int used;
+                int sym;
+                {
+                    const unsigned int e1 = S.lit_tab[(unsigned int)q & ((1u << INF_LIT_BITS) - 1u)];
+                    if (e1 & 15u) {
+                        used = e1 & 15u;
+                        sym = (int)((e1 >> 4) & 0x1FFu);
+                    } else {
+                        const int r = slow_decode((unsigned int)q, S.lit_cnt, S.lit_sym);
+                        if (r < 0) {
+                            st = INF_BAD_CODE;
+                            break;
+                        }
+                        used = (unsigned int)(r >> 16);
+                        sym = r & 0xFFFF;
+                    }
+                }
+                q >>= used;
+                if (sym < 256) {                                           // a literal with a code longer than the table
+                    if (out + 1 > J.dst_bytes) {
+                        st = INF_OUT_OVERFLOW;
+                        break;
+                    }
+                    if (lane == 0) dst[out] = (unsigned char)sym;
+                    out += 1;
+                    p += used;
+                    continue;
+                }
+                if (sym == 256) {
+                    p += used;
+                    break;                                                 // end of block
+                }
+                sym -= 257;
+                if (sym >= 29) {
+                    st = INF_BAD_CODE;
+                    break;
+                }
+                unsigned int eb = c_len_extra[sym];
+                const unsigned int mlen = c_len_base[sym] + ((unsigned int)q & ((1u << eb) - 1u));
+                q >>= eb;
+                used += eb;
+                int ds;
+                {
+                    const unsigned int e2 = S.dist_tab[(unsigned int)q & ((1u << INF_DIST_BITS) - 1u)];
+                    unsigned int dl;
+                    if (e2 & 15u) {
+                        dl = e2 & 15u;
+                        ds = (int)(e2 >> 4);
+                    } else {
+                        const int r = slow_decode((unsigned int)q, S.dist_cnt, S.dist_sym);
+                        if (r < 0) {
+                            st = INF_BAD_CODE;
+                            break;
+                        }
+                        dl = (unsigned int)(r >> 16);
+                        ds = r & 0xFFFF;
+                    }
+                    q >>= dl;
+                    used += dl;
+                }
+                if (ds >= 30) {
+                    st = INF_BAD_CODE;
+                    break;
+                }
+                eb = c_dist_extra[ds];
+                const unsigned int mdist = c_dist_base[ds] + ((unsigned int)q & ((1u << eb) - 1u));
+                used += eb;
+                p += used;
+                if (p > nbits) {
+                    st = INF_IN_OVERRUN;
+                    break;
+                }
+                if (mdist > out) {
+                    st = INF_BAD_DISTANCE;
+                    break;
+                }
+                if (out + mlen > J.dst_bytes) {
+                    st = INF_OUT_OVERFLOW;
+                    break;
+                }
+                __syncwarp();                                              // the match source may have just been written
+                const unsigned char *from = dst + out - mdist;
+                for (unsigned int i = lane; i < mlen; i += 32) dst[out + i] = from[i % mdist];
+                out += mlen;
+                __syncwarp();
+            }
+            if (p > nbits && st == INF_OK) st = INF_IN_OVERRUN;
+        }
+        // ---- trailer: Adler-32 of the output, big-endian, byte aligned
+        if (st == INF_OK) {
+            p = (p + 7u) & ~7u;
+            const unsigned int want = __byte_perm(peek32(src, p), 0, 0x0123);
+            p += 32;
+            if (p > nbits) st = INF_IN_OVERRUN;
+            else if (out != J.dst_bytes) st = INF_OUT_SHORT;
+            if (st == INF_OK) {
+                __syncwarp();
+                __threadfence_block();
+                if (warp_adler32(dst, J.dst_bytes, lane) != want) st = INF_BAD_CHECKSUM;
+            }
+        }
+        if (lane == 0) status[job] = st;
+        __syncwarp();
+    }
+}
+
 // Places the inflated chunks into the [W, ld] image.  A chunk holds chunk_rows x chunk_cols elements of the dataset
 // starting at (row0, gcol0); only the part inside the dataset and inside this shard's columns is kept (HDF5 stores
 // edge chunks at full size; shards are cut on 512-column tiles, so a chunk can belong to two shards).

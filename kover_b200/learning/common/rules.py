@@ -223,8 +223,14 @@ class KmerRuleClassifications(BaseRuleClassifications):
         if not all(hasattr(s, "upload_deflate") for s in self._group.shards):
             return False
         needed_rows = min(-(-int(self.dataset_initial_n_rows) // self.dataset_pack_size), int(ds.shape[0]))
+        stats = os.environ.get("KOVER_B200_INFLATE_STATS") is not None
+        import time
         for s in self._group.shards:
+            t0 = time.perf_counter()
             tab = table_of(0, needed_rows, s.col0, s.col0 + s.n_cols)
+            if stats:
+                import sys
+                sys.stderr.write("deflate_chunk_table: %.1f ms\n" % ((time.perf_counter() - t0) * 1e3))
             if tab is None:
                 return False
             cr, cc = tab["chunks"]

@@ -24,6 +24,10 @@ def matrix(seed, n_rows, n_cols, dtype, kind):
     if kind == "random":
         hi = rs.randint(0, 2 ** 32, size=(n_rows, n_cols), dtype=np.uint64)
         m = (hi << np.uint64(32) | rs.randint(0, 2 ** 32, size=(n_rows, n_cols), dtype=np.uint64)) if bits == 64 else hi
+    elif kind == "two_values":                   # bytes 0x00 (90 %) / 0xFF, and a few others: very short Huffman codes
+        b = np.where(rs.rand(n_rows, n_cols * (bits // 8)) < 0.9, 0, 255).astype(np.uint8)
+        b[rs.rand(*b.shape) < 0.01] = 7
+        m = b.view(np.uint64 if bits == 64 else np.uint32).astype(np.uint64)
     elif kind == "sparse":                       # k-mer-like: most words zero, runs of identical words
         m = np.zeros((n_rows, n_cols), dtype=np.uint64)
         idx = rs.rand(n_rows, n_cols) < 0.03
@@ -70,13 +74,17 @@ CASES = [
     ("multi_row_chunks", np.uint64, 9, 12_345, (2, 700), 4, "mixed"),
     ("pack32_gz4", np.uint32, 11, 33_333, (1, 5_000), 4, "mixed"),
     ("pack32_multi_row", np.uint32, 8, 9_999, (3, 1_000), 6, "sparse"),
+    # two byte values only, no matches: 1- and 2-bit literal codes, up to 32 symbols inside one 32-bit window
+    ("skewed_literals", np.uint64, 3, 16_000, (1, 8_000), raw_deflate(zlib.Z_HUFFMAN_ONLY), "two_values"),
 ]
 
 
 @pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
 @pytest.mark.parametrize("devices", [[0], [0, 0, 0]], ids=["1shard", "3shards"])
-def test_device_inflate_matches_host_path(tmp_path, monkeypatch, case, devices):
+@pytest.mark.parametrize("decoder", ["2", "1"], ids=["warp_parallel_literals", "single_lane"])
+def test_device_inflate_matches_host_path(tmp_path, monkeypatch, case, devices, decoder):
     name, dtype, n_rows, n_cols, chunks, compression, kind = case
+    monkeypatch.setenv("KOVER_B200_INFLATE_V", decoder)
     pack_bits = np.dtype(dtype).itemsize * 8
     M = matrix(len(name), n_rows, n_cols, dtype, kind)
     path = str(tmp_path / "m.h5")
@@ -122,10 +130,12 @@ def test_corrupt_stream_is_reported_through_the_host_path(tmp_path):
     f.close()
 
 
-def test_status_codes_of_malformed_streams():
+@pytest.mark.parametrize("decoder", ["2", "1"], ids=["warp_parallel_literals", "single_lane"])
+def test_status_codes_of_malformed_streams(monkeypatch, decoder):
     """kv_upload_deflate's per-chunk status on hand-made streams (C ABI level): good, truncated, wrong checksum,
     wrong size, bad header."""
     from kover_b200 import _native
+    monkeypatch.setenv("KOVER_B200_INFLATE_V", decoder)
     n_cols = 4096
     shard = _native.Shard(0, 64 * 8, n_cols)
     rs = np.random.RandomState(1)

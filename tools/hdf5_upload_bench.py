@@ -34,6 +34,13 @@ for mode, label in (("1", "device inflate"), ("0", "host inflate  "), ("1", "dev
     os.environ["KOVER_B200_DEVICE_INFLATE"] = mode
     f = hdf5_lite.File(path)
     d = f["kmer_matrix"]
+    if os.environ.get("KOVER_B200_INFLATE_STATS"):          # where the time of the constructor goes
+        from kover_b200 import _native
+        t0 = time.perf_counter()
+        sh_probe = _native.Shard(0, n, k)
+        t_create = time.perf_counter() - t0
+        sh_probe.close()
+        print("  (kv_create of a %d x %d shard alone: %.1f ms)" % (n, k, t_create * 1e3), flush=True)
     t0 = time.perf_counter()
     rc = KmerRuleClassifications(d, n, devices=[0])
     dt = time.perf_counter() - t0
