@@ -713,10 +713,11 @@ def run_ours(args):
     line["roofline"]["step_GBps"] = float(np.sum(alg_bytes) / (dev_ms * 1e-3) / 1e9)
     line["roofline"]["step_frac"] = line["roofline"]["step_GBps"] / peak
     if world > 1:
-        info_x = shard.info()
-        m = max(1, info_x.exch_steps)
-        line["exchange"] = {"steps": int(info_x.exch_steps), "publish_us": info_x.exch_publish_us / m,
-                            "wait_for_peers_us": info_x.exch_wait_us / m, "merge_and_result_us": info_x.exch_merge_us / m,
+        m = max(1, info_b.exch_steps - info_a.exch_steps)          # over the K timed steps
+        line["exchange"] = {"steps": int(info_b.exch_steps - info_a.exch_steps),
+                            "publish_us": (info_b.exch_publish_us - info_a.exch_publish_us) / m,
+                            "wait_for_peers_us": (info_b.exch_wait_us - info_a.exch_wait_us) / m,
+                            "merge_and_result_us": (info_b.exch_merge_us - info_a.exch_merge_us) / m,
                             "note": "rank 0, device clock of its last CTA, per step: packet stores into the peers' mailboxes; "
                                     "waiting for every peer's packet (NVLink latency + rank skew); merge + result to the host"}
     if rank == 0 and world == 1:

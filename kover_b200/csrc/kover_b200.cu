@@ -799,7 +799,52 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
     return t;
 }
 
-// the sequential block merge of scm.py:270-286 on n_blocks maxima (one thread); fills tol / sel, returns best
+// The block merge of scm.py:270-286 by ONE WARP (all 32 lanes call it with identical arguments).  The reference walks
+// the blocks in order; a block only matters when its maximum beats or is close to the running best -- a handful of
+// blocks out of hundreds on 8 GPUs -- so the lanes test 32 blocks at a time against the current best (ballot) and only
+// the hits are processed in order: the same decisions in the same order, without a 100-cycle dependent chain per block.
+// tol[b] = atol + rtol * |bm[b]| must be filled, sel[] is written for every block.  Returns best.
+__device__ __forceinline__ double block_merge_warp(const double *bm, const double *tol, uint8_t *sel, long long n_blocks) {
+    const int lane = threadIdx.x & 31;
+    for (long long b = lane; b < n_blocks; b += 32) sel[b] = 0;
+    __syncwarp();
+    double best = -INFINITY, best_tol = 0.0;        // best_tol: tolerance of isclose(x, best) = atol + rtol * |best|
+    long long first = 0, pos = 0;
+    while (pos < n_blocks) {
+        long long found = -1;
+        for (long long base = pos & ~31ll; base < n_blocks; base += 32) {
+            const long long b = base + lane;
+            bool hit = false;
+            if (b >= pos && b < n_blocks) {
+                const double m = bm[b];
+                // m > best or isclose(best, m): |best - m| <= tol(m) and isfinite(m), or best == m   (scm.py:271)
+                hit = (m > best) || (best == m) || (isfinite(m) && fabs(__dsub_rn(best, m)) <= tol[b]);
+            }
+            const unsigned mask = __ballot_sync(0xffffffffu, hit);
+            if (mask) {
+                found = base + (__ffs(mask) - 1);
+                break;
+            }
+        }
+        if (found < 0) break;
+        const double m = bm[found];
+        // isclose(m, best): |m - best| <= tol(best) and isfinite(best), or m == best   (scm.py:276)
+        const bool close = (m == best) || (isfinite(best) && fabs(__dsub_rn(m, best)) <= best_tol);
+        if (!close) {                                // a new best: everything selected so far is dropped (scm.py:282-286)
+            for (long long q = first + lane; q < found; q += 32) sel[q] = 0;
+            best = m;
+            best_tol = tol[found];
+            first = found;
+        }
+        if (lane == 0) sel[found] = 1;
+        __syncwarp();
+        pos = found + 1;
+    }
+    __syncwarp();
+    return best;
+}
+
+// the same, one thread (kept for k_scm_select's single-lane walk semantics in the unfused kernels)
 __device__ __forceinline__ double block_merge_seq(const double *bm, double *tol, uint8_t *sel, long long n_blocks) {
     double best = -INFINITY;
     long long first = 0;
@@ -874,15 +919,19 @@ __device__ void p2p_exchange_merge(const Scan2Params &P, double *s_bm, double *s
     const char *box = X.peer_box[X.rank] + (size_t)parity * world * X.slot_bytes;
     for (long long b = tid; b < F.n_blocks; b += NT) {
         double m = -INFINITY;
+#pragma unroll 4
         for (int r = 0; r < world; ++r) {
             const double v = __ldcv(reinterpret_cast<const double *>(box + (size_t)r * X.slot_bytes) + b);
             m = v > m ? v : m;
         }
         s_bm[b] = m;
+        s_tol[b] = np_tol_dev(m);
     }
     consumer_bar(NT);
-    if (tid == 0) {
-        s_best2 = block_merge_seq(s_bm, s_tol, s_sel, F.n_blocks);
+    if (tid < 32) {
+        const double best = block_merge_warp(s_bm, s_tol, s_sel, F.n_blocks);
+        if (tid == 0) s_best2 = best;
+    } else if (tid == 32) {
         for (int r = 0; r < world; ++r) {
             const PacketHeader *h = reinterpret_cast<const PacketHeader *>(box + (size_t)r * X.slot_bytes + nb_bytes);
             if ((long long)__ldcv(&h->count) > F.packet_cap && s_status == 0) s_status = 2;
@@ -958,16 +1007,22 @@ __device__ void scm_fused_tail(const Scan2Params &P, long long t0, long long t1,
     double *s_bm = reinterpret_cast<double *>(ring);
     double *s_tol = s_bm + F.n_blocks;
     uint8_t *s_sel = reinterpret_cast<uint8_t *>(s_tol + F.n_blocks);
-    for (long long b = tid; b < F.n_blocks; b += NT) s_bm[b] = dec_f64_max_dev(__ldcg(P.blockmax + b));
+    for (long long b = tid; b < F.n_blocks; b += NT) {
+        const double m = dec_f64_max_dev(__ldcg(P.blockmax + b));
+        s_bm[b] = m;
+        s_tol[b] = np_tol_dev(m);
+    }
     consumer_bar(NT);
-    if (tid == 0) {
+    if (tid < 32) {
         if (F.mode == 1) {
-            s_best = block_merge_seq(s_bm, s_tol, s_sel, F.n_blocks);       // scm.py:270-286
+            const double best = block_merge_warp(s_bm, s_tol, s_sel, F.n_blocks);       // scm.py:270-286
+            if (tid == 0) s_best = best;
         } else {
             // this rank only knows ITS maxima: superset threshold (see k_scm_select_local)
             double lmax = -INFINITY;
-            for (long long b = 0; b < F.n_blocks; ++b) lmax = fmax(lmax, s_bm[b]);
-            s_best = isfinite(lmax) ? lmax - 5.0 * np_tol_dev(lmax) : -INFINITY;
+            for (long long b = tid; b < F.n_blocks; b += 32) lmax = fmax(lmax, s_bm[b]);
+            lmax = warp_max(lmax);
+            if (tid == 0) s_best = isfinite(lmax) ? lmax - 5.0 * np_tol_dev(lmax) : -INFINITY;
         }
     }
     consumer_bar(NT);
