@@ -420,10 +420,10 @@ def measure_shape(name, n_genomes, k_local, world, rank, local_rank, comm, seed,
         call = lambda: rc.best_utility_rules(1.0, pos, neg, util_block_size=UTIL_BLOCK_SIZE)
         units = 2.0 * k_total
     else:
-        from oracle import kover_oracle as ko
+        from kover_b200.learning.learners.cart import _NodeImpurity
         ex = {0: neg, 1: pos}
-        n_total, altered = ko.cart_altered_priors(ex, {0: 1.0, 1: 1.0})
-        call = lambda: rc.gini_best_split(ex, altered, n_total)
+        impurity = _NodeImpurity(ex, {0: 1.0, 1: 1.0})                 # altered priors / class totals (cart.py:67-77)
+        call = lambda: rc.gini_best_split(ex, impurity.priors, impurity.n_total)
         units = 1.0 * k_total
     for _ in range(3):
         call()

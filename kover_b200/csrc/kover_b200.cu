@@ -22,12 +22,15 @@
 #include <cub/device/device_radix_sort.cuh>   // only to order LARGE tie lists (not on the scan path)
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <condition_variable>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <mutex>
 #include <numeric>
 #include <string>
 #include <thread>
@@ -2330,24 +2333,84 @@ extern "C" int kv_upload_block(kv_shard *s, int pack_bits, int64_t row0, int64_t
 #include "kv_inflate.cuh"
 
 namespace {
-// copy `n` byte ranges (src[i], bytes[i]) to dst + off[i] with a few threads (page cache -> pinned memory)
-void gather_streams(char *dst, const void *const *src, const int64_t *bytes, const size_t *off, int64_t n) {
-    const unsigned hw = std::thread::hardware_concurrency();
-    static const unsigned max_threads =
-        getenv("KOVER_B200_UPLOAD_THREADS") ? (unsigned)atoi(getenv("KOVER_B200_UPLOAD_THREADS")) : 16u;
-    size_t total = 0;
-    for (int64_t i = 0; i < n; ++i) total += (size_t)bytes[i];
-    const int n_threads = total < ((size_t)2 << 20) ? 1 : (int)std::max(1u, std::min(hw ? hw : 1u, std::max(1u, max_threads)));
-    auto work = [&](int t) {
-        for (int64_t i = t; i < n; i += n_threads) memcpy(dst + off[i], src[i], (size_t)bytes[i]);
-    };
-    if (n_threads == 1) {
-        work(0);
-        return;
+// Worker threads that copy byte ranges (page cache -> pinned memory), created once per upload call: spawning
+// threads per 16 MB slot cost more than the copies themselves (2 240 thread starts for a 2.2 GB file).
+class GatherPool {
+public:
+    explicit GatherPool(int n_threads) : n_(std::max(1, n_threads)) {
+        for (int t = 1; t < n_; ++t) workers_.emplace_back([this, t] { loop(t); });
     }
-    std::vector<std::thread> pool;
-    for (int t = 0; t < n_threads; ++t) pool.emplace_back(work, t);
-    for (auto &th : pool) th.join();
+    ~GatherPool() {
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            stop_ = true;
+            ++generation_;
+        }
+        cv_.notify_all();
+        for (auto &th : workers_) th.join();
+    }
+    // copy ranges i = 0 .. n-1: src[i] (bytes[i] bytes) -> dst + off[i]; returns when all are done
+    void run(char *dst, const void *const *src, const int64_t *bytes, const size_t *off, int64_t n) {
+        if (n_ == 1 || n < 2) {
+            for (int64_t i = 0; i < n; ++i) memcpy(dst + off[i], src[i], (size_t)bytes[i]);
+            return;
+        }
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            dst_ = dst; src_ = src; bytes_ = bytes; off_ = off; count_ = n;
+            next_.store(0);
+            pending_ = n_ - 1;
+            ++generation_;
+        }
+        cv_.notify_all();
+        work();
+        std::unique_lock<std::mutex> lk(m_);
+        done_.wait(lk, [this] { return pending_ == 0; });
+    }
+
+private:
+    void work() {
+        for (;;) {
+            const int64_t i = next_.fetch_add(1);
+            if (i >= count_) return;
+            memcpy(dst_ + off_[i], src_[i], (size_t)bytes_[i]);
+        }
+    }
+    void loop(int) {
+        unsigned long long seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [&] { return generation_ != seen; });
+                seen = generation_;
+                if (stop_) return;
+            }
+            work();
+            {
+                std::lock_guard<std::mutex> lk(m_);
+                if (--pending_ == 0) done_.notify_one();
+            }
+        }
+    }
+    int n_;
+    std::vector<std::thread> workers_;
+    std::mutex m_;
+    std::condition_variable cv_, done_;
+    unsigned long long generation_ = 0;
+    bool stop_ = false;
+    int pending_ = 0;
+    std::atomic<int64_t> next_{0};
+    char *dst_ = nullptr;
+    const void *const *src_ = nullptr;
+    const int64_t *bytes_ = nullptr;
+    const size_t *off_ = nullptr;
+    int64_t count_ = 0;
+};
+
+static int gather_threads() {
+    const unsigned hw = std::thread::hardware_concurrency();
+    const unsigned want = getenv("KOVER_B200_UPLOAD_THREADS") ? (unsigned)atoi(getenv("KOVER_B200_UPLOAD_THREADS")) : 16u;
+    return (int)std::max(1u, std::min(hw ? hw : 1u, std::max(1u, want)));
 }
 
 struct DevFree {                      // frees device buffers / events of one kv_upload_deflate call on every exit path
@@ -2432,7 +2495,7 @@ extern "C" int kv_upload_deflate(kv_shard *s, int pack_bits, int64_t n_chunks, c
     // lasts (time to stage the last slab) + (one slab's kernel): small uploads are cut into up to four slabs whose
     // kernels run concurrently on their own streams and start as soon as their streams have arrived.
     int64_t slab = std::min<int64_t>(n_chunks, 8192);
-    if (n_chunks <= 8192) slab = std::max<int64_t>(256, (n_chunks + 3) / 4);
+    if (n_chunks <= 8192 && !getenv("KOVER_B200_UPLOAD_ONE_SLAB")) slab = std::max<int64_t>(256, (n_chunks + 3) / 4);
     while (slab > 64 && (size_t)slab * chunk_stride * 4 > free_b / 4) slab /= 2;
     size_t max_comp = 0, max_scratch = 0, biggest = 0;
     for (int64_t a = 0; a < n_chunks; a += slab) {
@@ -2487,6 +2550,7 @@ extern "C" int kv_upload_deflate(kv_shard *s, int pack_bits, int64_t n_chunks, c
     CU(cudaMemsetAsync(d_status, 0xFF, (size_t)n_chunks * sizeof(int), s->stream));
     CU(cudaMemsetAsync(d_next, 0, n_slabs * sizeof(unsigned int), s->stream));
     CU(cudaStreamSynchronize(s->stream));
+    GatherPool pool(gather_threads());
     const double t_setup = ms_since(t_begin);
     std::vector<InflateJob> jobs((size_t)slab);
     std::vector<ScatterJob> sjobs(max_scratch);
@@ -2527,7 +2591,7 @@ extern "C" int kv_upload_deflate(kv_shard *s, int pack_bits, int64_t n_chunks, c
             std::vector<size_t> rel((size_t)(j - i));
             for (int64_t q = i; q < j; ++q) rel[(size_t)(q - i)] = off[(size_t)(q - a)] - base;
             const auto t_g = now();
-            gather_streams((char *)s->inf_pin[slot], src + i, src_bytes + i, rel.data(), j - i);
+            pool.run((char *)s->inf_pin[slot], src + i, src_bytes + i, rel.data(), j - i);
             t_gather += ms_since(t_g);
             const size_t span = (j < b ? off[(size_t)(j - a)] : c) - base;
             CU(cudaMemcpyAsync(d_comp[par] + base, s->inf_pin[slot], span, cudaMemcpyHostToDevice, s->inf_copy_stream));

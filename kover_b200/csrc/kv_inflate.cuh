@@ -46,6 +46,7 @@ struct InflateWarp {                            // per-warp shared memory (~3.8 
     unsigned short lit_cnt[16], dist_cnt[16];   // codes per length
     unsigned char lens[320];                    // code lengths of the block being set up
     unsigned char stage[INF_STAGE];
+    unsigned int run[256];                      // k_inflate2: per candidate bit position (next position << 8) | literal
 };
 
 __constant__ unsigned short c_len_base[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31,
@@ -485,14 +486,14 @@ __global__ void __launch_bounds__(INF_WARPS * 32) k_inflate(const unsigned char 
 // k_inflate2: the same decoder with the LITERAL RUNS decoded by the whole warp.
 //
 // In k_inflate one lane walks the Huffman stream: ~200 cycles per symbol, whatever else the GPU does (a dependent
-// chain with a shared-memory lookup and half a dozen branches).  Here the decoder state is just the bit position p,
-// identical in all lanes (no lane-0 section, no broadcasts), and a literal run is decoded speculatively: lane i looks
-// up the code that WOULD start at bit p + i; the codes that really are on the chain p -> p + len -> ... are found by
-// pointer doubling over the 32 candidates (each round: one redux.sync.or + one shuffle; ceil(log2(32 / shortest
-// code)) rounds, usually 3), their literals are written in parallel, and p advances past the whole run -- 4 to 6
-// symbols per iteration for ~8-bit codes.  Everything that is not a table-resident literal (length / distance pairs,
-// end of block, codes longer than the table) is decoded one symbol at a time, uniformly by all lanes, from a 64-bit
-// peek at p.  Block headers are parsed the same way.
+// chain of a refill, a shared-memory lookup and half a dozen branches at ~16 cycles per dependent instruction).  Here
+// the decoder state is just the bit position p, identical in all lanes (no lane-0 section, no broadcasts), and a
+// literal run is decoded speculatively: the lanes look up the codes that WOULD start at each of the next 256 bit
+// positions (eight per lane) and write {next position, literal} per position to shared memory; the codes that really
+// are on the chain p -> p + len -> ... are then found by walking that table, ONE dependent shared-memory load per
+// symbol, and up to 32 literals are written by the warp at once.  Everything that is not a table-resident literal
+// (length / distance pairs, end of block, codes longer than the table) is decoded one symbol at a time, uniformly by
+// all lanes, from a 64-bit peek at p.  Block headers are parsed the same way.
 // ------------------------------------------------------------------------------------------------
 struct BitSrc {
     const unsigned int *w;          // stream start, 4-byte aligned
@@ -656,45 +657,50 @@ __global__ void __launch_bounds__(INF_WARPS * 32) k_inflate2(const unsigned char
                 st = INF_BAD_LENGTHS;
                 break;
             }
-            // pointer-doubling rounds that cover the longest possible literal chain inside a 32-bit window
-            int minlen = 1;
-            while (minlen < 15 && S.lit_cnt[minlen] == 0) ++minlen;
-            int rounds = 1;
-            while ((1 << rounds) < 32 / minlen + 2) ++rounds;
             // ---- symbols of the block
             for (;;) {
-                // (1) the literal run that starts at p, all 32 candidate code starts at once
-                const unsigned int w = peek32(src, p + (unsigned int)lane);
-                const unsigned int e = S.lit_tab[w & ((1u << INF_LIT_BITS) - 1u)];
-                const bool lit = (e & 0x8000u) != 0;
-                const int nxt0 = lit ? lane + (int)(e & 15u) : 64;       // where the next code starts; 64 = not a literal
-                int jump = nxt0;
-                unsigned int reach = 1u;                                    // candidates on the chain from p (bit i = p + i)
-#pragma unroll 1
-                for (int r = 0; r < rounds; ++r) {
-                    const unsigned int add = (((reach >> lane) & 1u) && jump < 32) ? (1u << jump) : 0u;
-                    reach |= __reduce_or_sync(full, add);
-                    const int far = __shfl_sync(full, jump, jump & 31);
-                    jump = jump < 32 ? far : jump;
+                // (1) the literal run that starts at p.  Every lane decodes the codes that WOULD start at 8 of the next
+                // 256 bit positions (one 32-bit peek, eight table lookups) and leaves {next position, literal} per
+                // position in shared memory; the chain p -> p + len -> ... is then walked through that table -- one
+                // dependent shared-memory load per symbol instead of a refill + lookup + branch chain -- by all
+                // lanes alike; lane i keeps the i-th literal of the run and the warp writes up to 32 bytes at once.
+                {
+                    const unsigned int w = peek32(src, p + 8u * (unsigned int)lane);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const unsigned int e = S.lit_tab[(w >> j) & ((1u << INF_LIT_BITS) - 1u)];
+                        const unsigned int c = 8u * (unsigned int)lane + (unsigned int)j;
+                        S.run[c] = (e & 0x8000u) ? (((c + (e & 15u)) << 8) | ((e >> 4) & 0xFFu)) : 0xFFFFFFFFu;
+                    }
                 }
-                const unsigned int litmask = __ballot_sync(full, lit);
-                const unsigned int chain = reach & litmask, stop = reach & ~litmask;
-                const unsigned int count = __popc(chain);
-                if (out + count > J.dst_bytes) {
+                __syncwarp();
+                unsigned int pos = 0, n = 0, mine = 0;
+                bool stop = false;
+#pragma unroll 1
+                for (;;) {
+                    const unsigned int e = S.run[pos];
+                    if (e == 0xFFFFFFFFu) {                                // not a table-resident literal
+                        stop = true;
+                        break;
+                    }
+                    if (n == (unsigned int)lane) mine = e & 0xFFu;
+                    ++n;
+                    pos = e >> 8;
+                    if (pos >= 256u || n == 32u) break;
+                }
+                __syncwarp();                                              // (S.run is rewritten by the next iteration)
+                if (out + n > J.dst_bytes) {
                     st = INF_OUT_OVERFLOW;
                     break;
                 }
-                if ((chain >> lane) & 1u) dst[out + __popc(chain & ((1u << lane) - 1u))] = (unsigned char)(e >> 4);
-                out += count;
-                if (!stop) {                                               // the run leaves the window: next window
-                    p += (unsigned int)__shfl_sync(full, nxt0, 31 - __clz(chain));
-                    if (p > nbits) {
-                        st = INF_IN_OVERRUN;
-                        break;
-                    }
-                    continue;
+                if ((unsigned int)lane < n) dst[out + lane] = (unsigned char)mine;
+                out += n;
+                p += pos;
+                if (p > nbits) {
+                    st = INF_IN_OVERRUN;
+                    break;
                 }
-                p += (unsigned int)(__ffs(stop) - 1);
+                if (!stop) continue;                                       // the run goes on: next window
                 // (2) the symbol at p is not a table-resident literal: one symbol, decoded identically by every lane
                 unsigned long long q = peek64(src, p);
                 unsigned int used;

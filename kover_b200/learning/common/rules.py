@@ -406,6 +406,21 @@ class KmerRuleClassifications(BaseRuleClassifications):
             packed.append((float(p), mask_of(pos), mask_of(neg), pos.shape[0], neg.shape[0]))
         return self._group.scm_best_rules_grid(packed, int(util_block_size))
 
+    def best_utility_rules_grid_masks(self, jobs, rule_blacklist=(), util_block_size=1000000):
+        """``best_utility_rules_grid`` for jobs given as (p, positive row mask, negative row mask, n_pos, n_neg): the
+        lock-step learners keep their remaining examples as packed masks (learners.scm.fit_many)."""
+        self.set_rule_blacklist(rule_blacklist)
+        packed = [(float(p), pm, nm, int(n_pos), int(n_neg)) for p, pm, nm, n_pos, n_neg in jobs]
+        return self._group.scm_best_rules_grid(packed, int(util_block_size))
+
+    def packed_rule_columns(self, rule_indices):
+        """The packed matrix columns (uint64 [W] each, presence bits, nothing inverted) of the k-mers behind the given
+        rule indices, fetched with one gather -> list in the order asked."""
+        cols = np.asarray([int(r) % self._n_kmers for r in rule_indices], dtype=np.int64)
+        distinct, position = np.unique(cols, return_inverse=True)
+        packed = self._group.get_packed_columns(distinct)
+        return [packed[j] for j in position]
+
     def gini_best_split(self, example_idx, altered_priors, n_total_class_examples, rule_blacklist=()):
         """cart.py:112-161 + 231-238.  example_idx: dict class -> example indices of the node, iterated in
         dict order like the reference.  -> (min score, presence-rule indices achieving it, ascending)."""

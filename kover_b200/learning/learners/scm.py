@@ -61,23 +61,31 @@ class BaseSetCoveringMachine(object):
         answer = None
         while True:
             try:
-                pos_idx, neg_idx, blacklist, extra = steps.send(answer)
+                request = steps.send(answer)
             except StopIteration:
                 return
-            if neg_idx is None:                          # pos_idx is the device-resident greedy state
-                answer = pos_idx.scan(self.p, blacklist, UTIL_BLOCK_SIZE)
+            if request[0] == "state":                    # the device-resident greedy state
+                _, state, blacklist = request
+                answer = state.scan(self.p, blacklist, UTIL_BLOCK_SIZE)
             else:
+                _, pos_idx, neg_idx, blacklist, extra = request
                 answer = self._get_best_utility_rules(rule_classifications=rule_classifications,
                                                       positive_example_idx=pos_idx, negative_example_idx=neg_idx,
                                                       rule_blacklist=blacklist, **extra)
 
     def _fit_steps(self, rules, rule_classifications, positive_example_idx, negative_example_idx, rule_blacklist=[],
                    tiebreaker=None, iteration_callback=None, iteration_rule_importances=False, device_state=False,
-                   **kwargs):
-        """Generator: yields (positive_idx, negative_idx, blacklist, utility kwargs) whenever the greedy loop
-        needs the best-utility rules, and is sent the 4-tuple ``_get_best_utility_rules`` returns.
-        device_state: keep the remaining examples as masks on the device (rule_classifications.scm_state) and yield
-        (state, None, blacklist, kwargs) instead -- the index lists are then never filtered on the host."""
+                   host_masks=False, **kwargs):
+        """Generator of the greedy loop's requests; the caller answers each through ``send``:
+          ("idx", positive_idx, negative_idx, blacklist, utility kwargs) -> the 4-tuple of _get_best_utility_rules;
+          ("state", ScmGreedyState, blacklist)   -> the same 4-tuple   (device_state: the remaining examples live as
+                                                    masks on the device, rule_classifications.scm_state);
+          ("masks", pos_mask, neg_mask, n_pos, n_neg, blacklist) -> the same 4-tuple   (host_masks, used by fit_many:
+                                                    the remaining examples are two packed row masks of W words);
+          ("column", rule_idx)                   -> the packed matrix column of that rule's k-mer, uint64 [W]
+                                                    (host_masks only: fit_many fetches the columns of all learners
+                                                    of an iteration with one gather).
+        In the two mask modes the example index lists are never filtered on the host (scm.py:133-139)."""
         scan_kwargs = dict((name[len("utility__"):], value) for name, value in (kwargs or {}).items()
                            if name.startswith("utility__"))
         if len(positive_example_idx) == 0 or len(negative_example_idx) == 0:
@@ -97,15 +105,23 @@ class BaseSetCoveringMachine(object):
 
         all_training_idx = np.hstack((to_keep, to_cover))
         chosen, importances = [], []
-        state = None
+        state, keep_mask, cover_mask = None, None, None
         if device_state and not scan_kwargs and hasattr(rule_classifications, "scm_state"):
             state = rule_classifications.scm_state(to_keep, to_cover)
-        n_to_cover = len(to_cover)
+        elif host_masks and not scan_kwargs:
+            keep_mask = rule_classifications.row_mask(to_keep)
+            cover_mask = rule_classifications.row_mask(to_cover)
+        n_to_keep, n_to_cover = len(to_keep), len(to_cover)
+        n_kmers = n_rules // 2
         while n_to_cover > 0 and len(self.model) < self.max_rules:
             info = {"iteration_number": len(self.model) + 1}
-            best_utility, tied, tied_pos_errors, tied_neg_cover = \
-                yield ((state, None, rule_blacklist, scan_kwargs) if state is not None
-                       else (to_keep, to_cover, rule_blacklist, scan_kwargs))
+            if state is not None:
+                request = ("state", state, rule_blacklist)
+            elif keep_mask is not None:
+                request = ("masks", keep_mask, cover_mask, n_to_keep, n_to_cover, rule_blacklist)
+            else:
+                request = ("idx", to_keep, to_cover, rule_blacklist, scan_kwargs)
+            best_utility, tied, tied_pos_errors, tied_neg_cover = yield request
             info["utility_max"], info["utility_argmax"] = best_utility, tied
             logging.debug("Greatest utility is %.5f (%d rules)", best_utility, len(tied))
 
@@ -127,6 +143,13 @@ class BaseSetCoveringMachine(object):
             # examples the new rule rejects leave both sets (scm.py:133-139); the column spans ALL genomes
             if state is not None:
                 n_to_keep, n_to_cover = state.apply(selected)          # masks &= column, on the device
+            elif keep_mask is not None:
+                column = yield ("column", int(selected))               # uint64 [W]: the k-mer's packed presence column
+                accepted = ~column if selected >= n_kmers else column  # (padding bits are zero in the masks)
+                keep_mask = keep_mask & accepted
+                cover_mask = cover_mask & accepted
+                n_to_keep = int(np.bitwise_count(keep_mask).sum())
+                n_to_cover = int(np.bitwise_count(cover_mask).sum())
             else:
                 accepted = rule_classifications.get_columns(selected)
                 to_cover = to_cover[accepted[to_cover] != 0]
@@ -198,25 +221,48 @@ def fit_many(learners, fit_args, rule_classifications):
     coincide -- every p of the grid and both model types at iteration 1, and whenever they picked the same
     rules -- share one pass over the matrix.  Each learner ends in exactly the state its own ``fit`` would have
     produced (same scans, same order of operations per learner)."""
+    # remaining examples as packed row masks (W words per set) when the matrix can score masks directly: no index
+    # filtering per learner, and ONE column gather per iteration for all the learners' picks
+    masks_mode = hasattr(rule_classifications, "best_utility_rules_grid_masks") and \
+        not getattr(rule_classifications, "dataset_removed_rows", None)
     running = {}
     for i, (learner, kw) in enumerate(zip(learners, fit_args)):
-        gen = learner._fit_steps(rule_classifications=rule_classifications, **kw)
+        gen = learner._fit_steps(rule_classifications=rule_classifications, host_masks=masks_mode, **kw)
         try:
             running[i] = (gen, next(gen))
         except StopIteration:
             pass
     while running:
-        # one grid call per distinct blacklist (the experiments use a single blacklist for all fits)
+        # (1) learners that just picked a rule wait for its column: one gather for all of them
+        waiting = [i for i, (_, req) in running.items() if req[0] == "column"]
+        if waiting:
+            wanted = [running[i][1][1] for i in waiting]
+            columns = rule_classifications.packed_rule_columns(wanted)
+            for i, column in zip(waiting, columns):
+                gen = running[i][0]
+                try:
+                    running[i] = (gen, gen.send(column))
+                except StopIteration:
+                    del running[i]
+            continue
+        # (2) everybody is at a scan: one grid call per distinct blacklist (the experiments use a single blacklist)
         by_blacklist = {}
-        for i, (_, (pos_idx, neg_idx, blacklist, extra)) in running.items():
-            if extra:
+        for i, (_, req) in running.items():
+            if req[0] == "idx" and req[4]:
                 raise ValueError("fit_many does not support utility__ keyword arguments")
+            blacklist = req[5] if req[0] == "masks" else req[3]
             by_blacklist.setdefault(np.asarray(blacklist, dtype=np.int64).tobytes(), []).append(i)
         answers = {}
         for members in by_blacklist.values():
-            jobs = [(learners[i].p, running[i][1][0], running[i][1][1]) for i in members]
-            results = rule_classifications.best_utility_rules_grid(jobs, rule_blacklist=running[members[0]][1][2],
-                                                                   util_block_size=UTIL_BLOCK_SIZE)
+            first = running[members[0]][1]
+            if first[0] == "masks":
+                jobs = [(learners[i].p,) + tuple(running[i][1][1:5]) for i in members]
+                results = rule_classifications.best_utility_rules_grid_masks(jobs, rule_blacklist=first[5],
+                                                                             util_block_size=UTIL_BLOCK_SIZE)
+            else:
+                jobs = [(learners[i].p, running[i][1][1], running[i][1][2]) for i in members]
+                results = rule_classifications.best_utility_rules_grid(jobs, rule_blacklist=first[3],
+                                                                       util_block_size=UTIL_BLOCK_SIZE)
             answers.update(zip(members, results))
         still_running = {}
         for i, answer in answers.items():
