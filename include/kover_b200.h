@@ -98,6 +98,9 @@ int kv_upload_block(kv_shard *s, int pack_bits, int64_t row0, int64_t n_rows, in
 int kv_upload_deflate(kv_shard *s, int pack_bits, int64_t n_chunks, const void *const *src,
                       const int64_t *src_bytes, const int64_t *row0, const int64_t *gcol0,
                       int64_t chunk_rows, int64_t chunk_cols, int32_t *status);
+/* Host-clock phases of the last kv_upload_deflate on this shard (measurement aid): buffer set-up, gathering the
+ * streams into page-locked memory (overlaps the copies and the kernels), whole call. */
+int kv_upload_deflate_stats(kv_shard *s, double *setup_ms, double *gather_ms, double *total_ms);
 /* Fill the shard with the deterministic synthetic matrix of kover_b200/synthetic.py (bench and
  * full-size parity tests; the CPU twin regenerates any column slice). */
 int kv_generate_synthetic(kv_shard *s, uint64_t seed);

@@ -38,6 +38,8 @@ SYMBOLS = {
     "kv_get_info": (ctypes.c_int, [_c_p, ctypes.POINTER(ShardInfo)]),
     "kv_upload_block": (ctypes.c_int, [_c_p, ctypes.c_int, _c_i64, _c_i64, _c_i64, _c_i64, _c_p, _c_i64]),
     "kv_upload_deflate": (ctypes.c_int, [_c_p, ctypes.c_int, _c_i64, _c_p, _c_p, _c_p, _c_p, _c_i64, _c_i64, _c_p]),
+    "kv_upload_deflate_stats": (ctypes.c_int, [_c_p, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
+                                               ctypes.POINTER(ctypes.c_double)]),
     "kv_generate_synthetic": (ctypes.c_int, [_c_p, ctypes.c_uint64]),
     "kv_read_block": (ctypes.c_int, [_c_p, _c_i64, _c_i64, _c_i64, _c_i64, _c_p, _c_i64]),
     "kv_timer_start": (ctypes.c_int, [_c_p]),
@@ -271,6 +273,12 @@ class Shard(object):
         check(self._lib.kv_upload_deflate(self._h, int(pack_bits), n, ptr(addresses), ptr(nbytes), ptr(row0), ptr(gcol0),
                                           int(chunk_rows), int(chunk_cols), ptr(status)))
         return status
+
+    def upload_deflate_stats(self):
+        """{setup_ms, gather_ms, total_ms} of the last upload_deflate on this shard (host clock)."""
+        a, b, c = ctypes.c_double(0), ctypes.c_double(0), ctypes.c_double(0)
+        check(self._lib.kv_upload_deflate_stats(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
+        return {"setup_ms": a.value, "gather_ms": b.value, "total_ms": c.value}
 
     def generate_synthetic(self, seed):
         check(self._lib.kv_generate_synthetic(self._h, ctypes.c_uint64(int(seed))))

@@ -2056,6 +2056,7 @@ struct kv_shard {
     void *inf_pin[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t inf_pin_free[4] = {nullptr, nullptr, nullptr, nullptr};
     size_t inf_slot_bytes = 0;
+    double up_setup_ms = 0.0, up_gather_ms = 0.0, up_total_ms = 0.0;   // phases of the last kv_upload_deflate (host clock)
     DevBuf d_level;                           // kv_gini_level: per-node minima, counters, tie slots, segment minima
     std::vector<uint32_t *> occ_tables;       // kv_occ_table_set: k-mer occurrence counts of a training set, [ld] each
     int64_t *h_level = nullptr;               // pinned arena: the tie lists of the last kv_gini_level, node after node
@@ -2641,6 +2642,9 @@ extern "C" int kv_upload_deflate(kv_shard *s, int pack_bits, int64_t n_chunks, c
     CU(cudaMemcpyAsync(status, d_status, (size_t)n_chunks * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
     CU(cudaGetLastError());
+    s->up_setup_ms = t_setup;
+    s->up_gather_ms = t_gather;
+    s->up_total_ms = ms_since(t_begin);
     if (stats) {
         size_t comp = 0;
         for (int64_t q = 0; q < n_chunks; ++q) comp += (size_t)src_bytes[q];
@@ -2649,6 +2653,14 @@ extern "C" int kv_upload_deflate(kv_shard *s, int pack_bits, int64_t n_chunks, c
                 (long long)n_chunks, comp / 1e6, (double)n_chunks * chunk_bytes / 1e6, (long long)slab, max_scratch, t_setup,
                 t_gather, t_kernels, ms_since(t_begin));
     }
+    return KV_OK;
+}
+
+extern "C" int kv_upload_deflate_stats(kv_shard *s, double *setup_ms, double *gather_ms, double *total_ms) {
+    if (!s || !setup_ms || !gather_ms || !total_ms) return fail(KV_E_INVALID, "kv_upload_deflate_stats: null pointer");
+    *setup_ms = s->up_setup_ms;
+    *gather_ms = s->up_gather_ms;
+    *total_ms = s->up_total_ms;
     return KV_OK;
 }
 
