@@ -931,23 +931,26 @@ __device__ void p2p_exchange_merge(const Scan2Params &P, double *s_bm, double *s
         s_tol[b] = np_tol_dev(m);
     }
     consumer_bar(NT);
+    __shared__ long long s_cnt[P2P_MAX_WORLD];
     if (tid < 32) {
         const double best = block_merge_warp(s_bm, s_tol, s_sel, F.n_blocks);
         if (tid == 0) s_best2 = best;
-    } else if (tid == 32) {
-        for (int r = 0; r < world; ++r) {
-            const PacketHeader *h = reinterpret_cast<const PacketHeader *>(box + (size_t)r * X.slot_bytes + nb_bytes);
-            if ((long long)__ldcv(&h->count) > F.packet_cap && s_status == 0) s_status = 2;
-        }
+    } else if (tid - 32 < world) {               // every rank's candidate count, fetched in parallel
+        const int r = tid - 32;
+        const PacketHeader *h = reinterpret_cast<const PacketHeader *>(box + (size_t)r * X.slot_bytes + nb_bytes);
+        const long long c = (long long)__ldcv(&h->count);
+        s_cnt[r] = c;
+        if (c > F.packet_cap) atomicCAS(&s_status, 0, 2);
     }
     consumer_bar(NT);
     if (s_status == 0) {
         const double inv_ubs = 1.0 / (double)P.ubs;
-        for (int r = 0; r < world; ++r) {
+        // one warp per rank's packet (round robin), one lane per candidate: the packets are filtered side by side
+        for (int r = tid >> 5; r < world; r += NT / 32) {
             const PacketHeader *h = reinterpret_cast<const PacketHeader *>(box + (size_t)r * X.slot_bytes + nb_bytes);
-            const long long cnt = (long long)__ldcv(&h->count);
+            const long long cnt = s_cnt[r];
             const TieRec *recs = reinterpret_cast<const TieRec *>(h + 1);
-            for (long long i = tid; i < cnt; i += NT) {
+            for (long long i = tid & 31; i < cnt; i += 32) {
                 // (records are 8-byte aligned only: the packet head is n_blocks doubles + a 16-byte header)
                 const unsigned long long *rw = reinterpret_cast<const unsigned long long *>(recs + i);
                 long long idx = (long long)__ldcv(rw);

@@ -594,6 +594,19 @@ __device__ __forceinline__ int read_dynamic_lengths2(const BitSrc &src, unsigned
 __global__ void __launch_bounds__(INF_WARPS * 32) k_inflate2(const unsigned char *src_base, const InflateJob *jobs,
                                                               int n_jobs, int *status, unsigned int *next_job) {
     __shared__ InflateWarp s_w[INF_WARPS];
+    // length / distance code tables next to the decoder (constant-memory lookups with a data-dependent index cost a
+    // constant-cache round trip each, four per match)
+    __shared__ unsigned short s_len_base[29], s_dist_base[30];
+    __shared__ unsigned char s_len_extra[29], s_dist_extra[30];
+    if (threadIdx.x < 29) {
+        s_len_base[threadIdx.x] = c_len_base[threadIdx.x];
+        s_len_extra[threadIdx.x] = c_len_extra[threadIdx.x];
+    }
+    if (threadIdx.x < 30) {
+        s_dist_base[threadIdx.x] = c_dist_base[threadIdx.x];
+        s_dist_extra[threadIdx.x] = c_dist_extra[threadIdx.x];
+    }
+    __syncthreads();
     const unsigned int full = 0xffffffffu;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     InflateWarp &S = s_w[wid];
@@ -658,18 +671,29 @@ __global__ void __launch_bounds__(INF_WARPS * 32) k_inflate2(const unsigned char
                 break;
             }
             // ---- symbols of the block
+            bool wide = true;
             for (;;) {
                 // (1) the literal run that starts at p.  Every lane decodes the codes that WOULD start at 8 of the next
                 // 256 bit positions (one 32-bit peek, eight table lookups) and leaves {next position, literal} per
                 // position in shared memory; the chain p -> p + len -> ... is then walked through that table -- one
                 // dependent shared-memory load per symbol instead of a refill + lookup + branch chain -- by all
                 // lanes alike; lane i keeps the i-th literal of the run and the warp writes up to 32 bytes at once.
-                {
+                // (after a short run -- match-heavy data -- only 64 positions, two per lane, are looked up)
+                const unsigned int window = wide ? 256u : 64u;
+                if (wide) {
                     const unsigned int w = peek32(src, p + 8u * (unsigned int)lane);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const unsigned int e = S.lit_tab[(w >> j) & ((1u << INF_LIT_BITS) - 1u)];
                         const unsigned int c = 8u * (unsigned int)lane + (unsigned int)j;
+                        S.run[c] = (e & 0x8000u) ? (((c + (e & 15u)) << 8) | ((e >> 4) & 0xFFu)) : 0xFFFFFFFFu;
+                    }
+                } else {
+                    const unsigned int w = peek32(src, p + 2u * (unsigned int)lane);
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const unsigned int e = S.lit_tab[(w >> j) & ((1u << INF_LIT_BITS) - 1u)];
+                        const unsigned int c = 2u * (unsigned int)lane + (unsigned int)j;
                         S.run[c] = (e & 0x8000u) ? (((c + (e & 15u)) << 8) | ((e >> 4) & 0xFFu)) : 0xFFFFFFFFu;
                     }
                 }
@@ -686,8 +710,9 @@ __global__ void __launch_bounds__(INF_WARPS * 32) k_inflate2(const unsigned char
                     if (n == (unsigned int)lane) mine = e & 0xFFu;
                     ++n;
                     pos = e >> 8;
-                    if (pos >= 256u || n == 32u) break;
+                    if (pos >= window || n == 32u) break;
                 }
+                wide = n >= 8u;
                 __syncwarp();                                              // (S.run is rewritten by the next iteration)
                 if (out + n > J.dst_bytes) {
                     st = INF_OUT_OVERFLOW;
@@ -740,8 +765,8 @@ __global__ void __launch_bounds__(INF_WARPS * 32) k_inflate2(const unsigned char
                     st = INF_BAD_CODE;
                     break;
                 }
-                unsigned int eb = c_len_extra[sym];
-                const unsigned int mlen = c_len_base[sym] + ((unsigned int)q & ((1u << eb) - 1u));
+                unsigned int eb = s_len_extra[sym];
+                const unsigned int mlen = s_len_base[sym] + ((unsigned int)q & ((1u << eb) - 1u));
                 q >>= eb;
                 used += eb;
                 int ds;
@@ -767,8 +792,8 @@ __global__ void __launch_bounds__(INF_WARPS * 32) k_inflate2(const unsigned char
                     st = INF_BAD_CODE;
                     break;
                 }
-                eb = c_dist_extra[ds];
-                const unsigned int mdist = c_dist_base[ds] + ((unsigned int)q & ((1u << eb) - 1u));
+                eb = s_dist_extra[ds];
+                const unsigned int mdist = s_dist_base[ds] + ((unsigned int)q & ((1u << eb) - 1u));
                 used += eb;
                 p += used;
                 if (p > nbits) {
