@@ -61,6 +61,8 @@ typedef struct kv_shard_info {
     double exch_publish_us;  /* summed over those steps, device clock of the rank's last CTA: packet stores, */
     double exch_wait_us;     /* ... waiting for every peer's packet (rank skew + NVLink latency),          */
     double exch_merge_us;    /* ... merging the packets and publishing the result to the host              */
+    int64_t stream_steps;    /* fused SCM steps that streamed their candidates (no count arrays written)   */
+    int64_t stream_redos;    /* ... of which were redone with the count arrays (candidate / tie overflow)   */
 } kv_shard_info;
 
 const char *kv_last_error(void);

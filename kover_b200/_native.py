@@ -25,7 +25,7 @@ class ShardInfo(ctypes.Structure):
                 ("last_launches", _c_i64), ("total_launches", _c_i64), ("scan_ms_total", ctypes.c_double),
                 ("scan_calls", _c_i64), ("rescore_calls", _c_i64), ("exch_steps", _c_i64),
                 ("exch_publish_us", ctypes.c_double), ("exch_wait_us", ctypes.c_double),
-                ("exch_merge_us", ctypes.c_double)]
+                ("exch_merge_us", ctypes.c_double), ("stream_steps", _c_i64), ("stream_redos", _c_i64)]
 
 
 # every exported symbol with (restype, argtypes); tests/test_abi.py checks this table against the header

@@ -189,7 +189,10 @@ static constexpr int SCAN_INLINE_ROWS = 64;
 // Fused tail of an SCM scan (single-shard step in ONE launch): after its last tile every CTA arrives at a grid-wide
 // barrier, replays the block merge on the complete block maxima, collects the ties of ITS OWN tiles straight into
 // mapped page-locked host memory, and the last CTA to finish publishes {best utility, tie count, epoch flag} there.
-struct TieRec;
+struct TieRec {
+    long long idx;
+    uint32_t pe, nc;
+};
 struct FusedTail {
     int mode;                                   // 0 = off, 1 = exact ties
     unsigned long long *barrier, *done;         // monotonic device counters (never reset)
@@ -242,10 +245,20 @@ struct Scan2Params {
     // Gini epilogue (two classes = the two masks, in the caller's dict order): cart.py:71-77, 99-110
     double g_prior[2], g_ntot[2], g_nnode[2];
     unsigned long long *gmin;                 // enc_f64 of the minimum split score; segmax[0..ld/64) holds segment minima
+    // EPI_SCM_STREAM: candidate records per CTA, cand[blockIdx.x * cand_cap ...], and how many each CTA produced
+    TieRec *cand;
+    unsigned *cand_n;
+    int cand_cap;
     FusedTail tail;
 };
 
-enum { EPI_COUNTS = 0, EPI_SCM = 1, EPI_GINI2 = 2 };
+// EPI_SCM_STREAM = EPI_SCM without a single store to HBM inside the tile loop: no count arrays, no segment maxima.
+// A rule can only survive the merge if u >= best - 5 T(best) (the rank-local superset criterion of DESIGN section 7,
+// x - 5 T(x) increasing), and every running maximum is a lower bound of `best`, so each warp compares its utilities with
+// the threshold of the CTA's running maximum and appends the few that pass {rule, pos_err, neg_cover} to the CTA's
+// candidate list; the LAST CTA of the grid filters all the lists exactly.  At W = 32 the 83 MB of count / segment stores
+// cost 7 % of the scan (read / write turnarounds: profiles/r02_stream_vs_counts.log).
+enum { EPI_COUNTS = 0, EPI_SCM = 1, EPI_GINI2 = 2, EPI_SCM_STREAM = 3 };
 
 // _gini_rule_score for two classes (cart.py:112-161) in numpy's operation order; l0/l1 = examples of
 // class 0/1 WITH the k-mer.  Identical arithmetic to gini_score<2> below (k_gini), kept separate so the
@@ -374,6 +387,10 @@ __device__ __forceinline__ void accum_word(const unsigned char *p, uint64_t a, u
 
 template <int CW>
 __device__ void scm_fused_tail(const Scan2Params &P, long long t0, long long t1, unsigned char *ring);
+template <int CW>
+__device__ void scm_stream_tail(const Scan2Params &P, unsigned char *ring, unsigned n_cand);
+__device__ __forceinline__ double dec_f64_max_dev(unsigned long long v);
+__device__ __forceinline__ double np_tol_dev(double b);
 
 // GREC = true: the row records stay in global memory (read through L1) instead of being staged in shared memory --
 // the fallback for masks with more active packed rows than fit beside the ring (~5 000 rows = 320 000 genomes); the
@@ -384,6 +401,8 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) k_scan_tma(const Scan2Par
     constexpr int ROW_BYTES = CW * 32 * 16;
     constexpr int TC = CW * 64;                          // columns per tile
     __shared__ unsigned long long s_red[CW];
+    __shared__ unsigned long long s_cmax;                // EPI_SCM_STREAM: enc_f64 of the CTA's running maximum
+    __shared__ unsigned s_ncand;                         //                 candidates appended by this CTA
     const int n_act = P.n_act;
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_tma);
     uint64_t *empty = full + S;
@@ -415,6 +434,8 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) k_scan_tma(const Scan2Par
             mbar_init(empty + s, CW);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        s_cmax = 0ull;
+        s_ncand = 0u;
     }
     __syncthreads();
 
@@ -464,6 +485,8 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) k_scan_tma(const Scan2Par
     run[0].mx = run[1].mx = -INFINITY;
     const double neg_inf = -INFINITY;
     double gini_min = INFINITY;
+    double thr = -INFINITY;                              // EPI_SCM_STREAM: candidate threshold (warp-uniform)
+    TieRec *const my_cand = EPI == EPI_SCM_STREAM ? P.cand + (size_t)blockIdx.x * P.cand_cap : nullptr;
     const uint64_t pol_last = l2_policy_evict_last();
     int s = 0;
     uint32_t ph = 0;
@@ -486,7 +509,9 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) k_scan_tma(const Scan2Par
             if (++s == S) { s = 0; ph ^= 1; }
         }
         const long long col = tile * TC + 2 * (long long)threadIdx.x;
-        if (P.l2_hints & 2) {
+        if (EPI == EPI_SCM_STREAM) {
+            // nothing is stored
+        } else if (P.l2_hints & 2) {
             st_u32x2_hint(P.cnt0 + col, c0x, c0y, pol_last);
             if (P.cnt1) st_u32x2_hint(P.cnt1 + col, c1x, c1y, pol_last);
         } else {
@@ -505,7 +530,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) k_scan_tma(const Scan2Par
             if (lane == 0) P.segmax[col >> 6] = seg;
             gini_min = fmin(gini_min, sm);
         }
-        if (EPI == EPI_SCM) {
+        if (EPI == EPI_SCM || EPI == EPI_SCM_STREAM) {
             const bool vx = col < P.n_cols, vy = col + 1 < P.n_cols;
             uint32_t bp = 0, ba = 0;
             if (P.black_pres) {
@@ -525,9 +550,11 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) k_scan_tma(const Scan2Par
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const double um = fmax(ux[h], uy[h]);
-                // per-64-column segment maximum: lets k_scm_ties skip segments that cannot hold a tie
-                const unsigned long long seg = warp_max_enc(enc_f64(um));
-                if (lane == 0) P.segmax[(size_t)h * (P.ld >> 6) + (col >> 6)] = seg;
+                if (EPI == EPI_SCM) {
+                    // per-64-column segment maximum: lets k_scm_ties skip segments that cannot hold a tie
+                    const unsigned long long seg = warp_max_enc(enc_f64(um));
+                    if (lane == 0) P.segmax[(size_t)h * (P.ld >> 6) + (col >> 6)] = seg;
+                }
                 if (tile_n <= 0) continue;
                 RunMax &r = run[h];
                 const long long r0 = (long long)h * P.k_total + P.col0 + tile_c0;
@@ -551,12 +578,46 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) k_scan_tma(const Scan2Par
                     if (vy) atomicMax(P.blockmax + (rx + 1) / P.ubs, enc_f64(uy[h]));
                 }
             }
+            if (EPI == EPI_SCM_STREAM) {
+                const double um = fmax(fmax(ux[0], uy[0]), fmax(ux[1], uy[1]));
+                if (__any_sync(0xffffffffu, um >= thr)) {            // rare once the running maximum has settled
+                    // raise the CTA's running maximum, pick up what the other warps found, re-derive the threshold
+                    unsigned long long e = warp_max_enc(enc_f64(um));
+                    if (lane == 0) atomicMax(&s_cmax, e);
+                    __syncwarp();
+                    const unsigned long long ec = *reinterpret_cast<volatile unsigned long long *>(&s_cmax);
+                    const double cur = dec_f64_max_dev(ec > e ? ec : e);
+                    if (cur > -INFINITY) thr = __dsub_rn(cur, __dmul_rn(5.0, np_tol_dev(cur)));
+                    const long long rule = P.col0 + col;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int h = q >> 1, y = q & 1;
+                        const double u = y ? uy[h] : ux[h];
+                        if (u >= thr && u > -INFINITY) {
+                            const uint32_t c0 = y ? c0y : c0x, c1 = y ? c1y : c1x;
+                            const unsigned slot = atomicAdd(&s_ncand, 1u);
+                            if (slot < (unsigned)P.cand_cap) {
+                                TieRec r;
+                                r.idx = (long long)h * P.k_total + rule + y;
+                                r.pe = h ? c0 : P.n_pos - c0;
+                                r.nc = h ? c1 : P.n_neg - c1;
+                                my_cand[slot] = r;
+                            }
+                        }
+                    }
+                }
+            }
         }
     }
-    if (EPI == EPI_SCM) {
+    if (EPI == EPI_SCM || EPI == EPI_SCM_STREAM) {
         runmax_flush<CW>(run[0], P.blockmax, s_red);
         runmax_flush<CW>(run[1], P.blockmax, s_red);
-        if (P.tail.mode) scm_fused_tail<CW>(P, t0, t1, ring);      // (the ring is idle: every stage was consumed)
+        if (EPI == EPI_SCM_STREAM) {
+            consumer_bar(CW * 32);
+            scm_stream_tail<CW>(P, ring, s_ncand);
+        } else if (P.tail.mode) {
+            scm_fused_tail<CW>(P, t0, t1, ring);      // (the ring is idle: every stage was consumed)
+        }
     }
     if (EPI == EPI_GINI2) {
         const unsigned long long v = warp_min_enc(enc_f64(gini_min));
@@ -593,11 +654,6 @@ struct TieHeader {               // first 32 bytes of d_ties
     unsigned long long count;
     unsigned long long pad[2];
 };
-struct TieRec {
-    long long idx;
-    uint32_t pe, nc;
-};
-
 // Both select kernels run as ONE warp: the lanes fetch + decode the block maxima in parallel (and zero
 // the accumulators for the next scan), lane 0 then walks them in shared memory.
 static constexpr int SELECT_SMEM_BLOCKS = 2048;
@@ -1094,6 +1150,141 @@ __device__ void scm_fused_tail(const Scan2Params &P, long long t0, long long t1,
         }
         return;
     }
+    p2p_exchange_merge<NT>(P, s_bm, s_tol, s_sel, s_t_last);
+}
+
+// The tail of k_scan_tma<EPI_SCM_STREAM>: ONE synchronisation point.  Every CTA records how many candidates it appended
+// and takes a ticket; the last CTA of the grid owns the rest of the step: block merge (scm.py:270-286) on the complete
+// maxima, exact filter of ALL the candidate lists (a few thousand records in L2), result into mapped host memory
+// (mode 1) or packet -> exchange -> merge of the ranks' packets (mode 2).  No grid barrier, so no co-residency
+// requirement and nothing spins while the slowest CTA finishes.  A candidate list that overflowed, or a best utility of
+// -inf (every rule blacklisted: the tie set is the whole block), is reported as "more ties than the buffer holds" and
+// the caller redoes the step with the count arrays.
+template <int CW>
+__device__ void scm_stream_tail(const Scan2Params &P, unsigned char *ring, unsigned n_cand) {
+    const FusedTail &F = P.tail;
+    const int tid = threadIdx.x;
+    constexpr int NT = CW * 32;
+    __shared__ double s_best;               // mode 1: best utility; mode 2: the rank's candidate threshold
+    __shared__ int s_last;
+    __shared__ unsigned s_over;
+    __shared__ unsigned long long s_emit, s_t_last;
+    if (tid == 0) {
+        P.cand_n[blockIdx.x] = n_cand;
+        s_over = 0u;
+        s_emit = 0ull;
+        __threadfence();                         // this CTA's candidates and block maxima before its ticket
+        const unsigned long long ticket = atomicAdd(F.done, 1ull);
+        s_last = ticket + 1 == F.done_target;
+        __threadfence();
+    }
+    consumer_bar(NT);
+    if (!s_last) return;
+    if (tid == 0) s_t_last = globaltimer_ns();
+    const int G = (int)gridDim.x;
+    double *s_bm = reinterpret_cast<double *>(ring);
+    double *s_tol = s_bm + F.n_blocks;
+    uint8_t *s_sel = reinterpret_cast<uint8_t *>(s_tol + F.n_blocks);
+    unsigned *s_pre = reinterpret_cast<unsigned *>(ring + (((size_t)F.n_blocks * 17 + 63) / 16) * 16);   // [G + 1]
+    for (long long b = tid; b < F.n_blocks; b += NT) {
+        const double m = dec_f64_max_dev(__ldcg(P.blockmax + b));
+        s_bm[b] = m;
+        s_tol[b] = np_tol_dev(m);
+        F.zero_next[b] = 0ull;
+    }
+    for (int c = tid; c < G; c += NT) {
+        unsigned n = __ldcg(P.cand_n + c);
+        if (n > (unsigned)P.cand_cap) {
+            n = (unsigned)P.cand_cap;
+            s_over = 1u;
+        }
+        s_pre[c + 1] = n;
+    }
+    if (tid == 0) s_pre[0] = 0u;
+    consumer_bar(NT);
+    if (tid < 32) {
+        if (F.mode == 1) {
+            const double best = block_merge_warp(s_bm, s_tol, s_sel, F.n_blocks);
+            if (tid == 0) s_best = best;
+        } else {
+            double lmax = -INFINITY;
+            for (long long b = tid; b < F.n_blocks; b += 32) lmax = fmax(lmax, s_bm[b]);
+            lmax = warp_max(lmax);
+            if (tid == 0) s_best = isfinite(lmax) ? lmax - 5.0 * np_tol_dev(lmax) : -INFINITY;
+        }
+    } else if (tid < 64) {                       // inclusive scan of the list lengths, 32 at a time
+        const int lane = tid & 31;
+        unsigned carry = 0u;
+        for (int base = 0; base < G; base += 32) {
+            const int c = base + lane;
+            unsigned v = c < G ? s_pre[c + 1] : 0u;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned o = __shfl_up_sync(0xffffffffu, v, d);
+                if (lane >= d) v += o;
+            }
+            if (c < G) s_pre[c + 1] = v + carry;
+            carry += __shfl_sync(0xffffffffu, v, 31);
+        }
+    }
+    consumer_bar(NT);
+    const bool exact = F.mode == 1;
+    TieRec *out = exact ? F.out : reinterpret_cast<TieRec *>(F.packet + (size_t)F.n_blocks * 8 + sizeof(PacketHeader));
+    const long long cap = exact ? F.cap : F.packet_cap;
+    const unsigned total = s_pre[G];
+    const double inv_ubs = 1.0 / (double)P.ubs, thr = s_best;
+    for (unsigned i = tid; i < total; i += NT) {
+        int lo = 0, hi = G;                      // s_pre[lo] <= i < s_pre[hi]
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (s_pre[mid] <= i) lo = mid; else hi = mid;
+        }
+        const unsigned long long *rw =
+            reinterpret_cast<const unsigned long long *>(P.cand + (size_t)lo * P.cand_cap + (i - s_pre[lo]));
+        const long long idx = (long long)__ldcg(rw);
+        const unsigned long long cnts = __ldcg(rw + 1);
+        const uint32_t pe = (uint32_t)cnts, nc = (uint32_t)(cnts >> 32);
+        const double u = scm_utility(nc, pe, P.p);
+        bool keep;
+        if (exact) {
+            const long long b = fast_div(idx, P.ubs, inv_ubs);
+            keep = s_sel[b] && tie_close(u, s_bm[b], s_tol[b]);
+        } else {
+            keep = u >= thr;
+        }
+        if (keep) {
+            const unsigned long long slot = atomicAdd(&s_emit, 1ull);
+            if ((long long)slot < cap) {
+                TieRec o;
+                o.idx = idx; o.pe = pe; o.nc = nc;
+                out[slot] = o;
+            }
+        }
+    }
+    if (!exact) {                                // the head of the packet: block maxima + threshold
+        double *pk = reinterpret_cast<double *>(F.packet);
+        for (long long b = tid; b < F.n_blocks; b += NT) pk[b] = s_bm[b];
+    }
+    consumer_bar(NT);
+    const bool redo = s_over != 0u || !(s_best > -INFINITY);
+    if (exact) {
+        if (tid == 0) {
+            F.host[0] = (unsigned long long)__double_as_longlong(s_best);
+            F.host[1] = redo ? (unsigned long long)(F.cap + 1) : s_emit;
+            F.host[3] = redo ? 2ull : 0ull;
+            F.host[4] = s_t_last;
+            F.host[5] = F.host[6] = F.host[7] = globaltimer_ns();
+            __threadfence_system();
+            F.host[2] = F.epoch;
+        }
+        return;
+    }
+    if (tid == 0) {
+        PacketHeader *h = reinterpret_cast<PacketHeader *>(F.packet + (size_t)F.n_blocks * 8);
+        h->threshold = s_best;
+        h->count = redo ? (unsigned long long)(F.packet_cap + 1) : s_emit;
+    }
+    consumer_bar(NT);
     p2p_exchange_merge<NT>(P, s_bm, s_tol, s_sel, s_t_last);
 }
 
@@ -2046,6 +2237,15 @@ struct kv_shard {
     long long fused_n_blocks = -1;
     unsigned long long fused_epoch = 0, fused_barrier_total = 0, fused_done_total = 0;
     std::vector<uint64_t> h_masks;            // masks built from index arrays (kv_scm_best_rules_idx)
+    // candidate-streaming step (EPI_SCM_STREAM): no count arrays are written, so what later phases read from them
+    // (kv_scm_reuse_counts, kv_scm_ties) is produced on demand by one more scan of the same masks (scm_materialize)
+    int stream_cand = 1;                      // KOVER_B200_STREAM=0: always write the count arrays
+    int stream_backoff = 0, stream_backoff_len = 8;   // steps left on the counting path after a candidate overflow
+    TieRec *d_cand = nullptr;                 // [2 * sm_count][kCandCap]
+    unsigned *d_cand_n = nullptr;             // [2 * sm_count]
+    bool scm_lazy = false, lazy_from_state = false;
+    std::vector<uint64_t> lazy_masks;         // pos [W] | neg [W] of the last streamed step
+    long long stream_steps = 0, stream_redos = 0;
     // device-resident greedy state (kv_scm_state_set / kv_mask_and_column)
     uint64_t *d_state = nullptr;              // pos [W] | neg [W] | column words [W] | rec m0 [W] | rec m1 [W] | rec row u32 [W]
     void *h_state = nullptr;                  // mapped page-locked: 64-byte header + column words [W]
@@ -2151,6 +2351,7 @@ extern "C" int kv_create(int device, int64_t n_examples, int64_t n_kmers_total, 
     if (const char *v = getenv("KOVER_B200_L2HINT")) s->l2_hints = atoi(v);
     if (const char *v = getenv("KOVER_B200_FUSED")) s->fused = atoi(v);
     if (const char *v = getenv("KOVER_B200_COOP")) s->cooperative = atoi(v);
+    if (const char *v = getenv("KOVER_B200_STREAM")) s->stream_cand = atoi(v);
     if (const char *v = getenv("KOVER_B200_PROFILE")) s->profiling = atoi(v) != 0;
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
@@ -2198,6 +2399,8 @@ extern "C" int kv_destroy(kv_shard *s) {
     if (s->inf_copy_stream) cudaStreamDestroy(s->inf_copy_stream);
     if (s->d_state) cudaFree(s->d_state);
     if (s->d_fused_ctr) cudaFree(s->d_fused_ctr);
+    if (s->d_cand) cudaFree(s->d_cand);
+    if (s->d_cand_n) cudaFree(s->d_cand_n);
     if (s->d_fused_bm) cudaFree(s->d_fused_bm);
     for (int i = 0; i < 2; ++i) {
         if (s->h_up[i]) cudaFreeHost(s->h_up[i]);
@@ -2233,6 +2436,8 @@ extern "C" int kv_get_info(kv_shard *s, kv_shard_info *o) {
     o->exch_publish_us = s->exch_publish_us;
     o->exch_wait_us = s->exch_wait_us;
     o->exch_merge_us = s->exch_merge_us;
+    o->stream_steps = s->stream_steps;
+    o->stream_redos = s->stream_redos;
     return KV_OK;
 }
 
@@ -2858,22 +3063,23 @@ static int launch_scan_variant(kv_shard *s, const Scan2Params &P) {
     }
     const long long n_tiles = s->ld / (CW * 64);
     const int grid = (int)std::max(1ll, std::min<long long>((long long)s->sm_count * MINB, n_tiles));
-    if (EPI == EPI_SCM && P.tail.mode) {
+    if ((EPI == EPI_SCM || EPI == EPI_SCM_STREAM) && P.tail.mode) {
         // the tail's grid barrier needs every CTA resident: at most MINB CTAs per SM are launched (persistent grid)
-        // and a cooperative launch makes the driver verify it
-        if ((size_t)P.tail.n_blocks * 17 + 64 > (size_t)S * R * CW * 512)
+        // and a cooperative launch makes the driver verify it.  (The streaming tail has no barrier: plain launch.)
+        const size_t tables = ((size_t)P.tail.n_blocks * 17 + 63) / 16 * 16 + (EPI == EPI_SCM_STREAM ? (size_t)(grid + 1) * 4 : 0);
+        if (tables > (size_t)S * R * CW * 512)
             return fail(KV_E_INVALID, "fused scan: block tables do not fit the ring");
         Scan2Params Q = P;
         Q.tail.barrier_target = s->fused_barrier_total + (unsigned long long)grid;
         Q.tail.done_target = s->fused_done_total + (unsigned long long)grid;
-        if (s->cooperative) {
+        if (EPI == EPI_SCM && s->cooperative) {
             void *args[] = {(void *)&Q};
             CU(cudaLaunchCooperativeKernel((const void *)k_scan_tma<EPI, CW, R, S, MINB, GREC>, dim3(grid),
                                            dim3((CW + 1) * 32), args, smem, s->stream));
         } else {
             k_scan_tma<EPI, CW, R, S, MINB, GREC><<<grid, (CW + 1) * 32, smem, s->stream>>>(Q);
         }
-        s->fused_barrier_total += (unsigned long long)grid;
+        if (EPI == EPI_SCM) s->fused_barrier_total += (unsigned long long)grid;
         s->fused_done_total += (unsigned long long)grid;
         return KV_OK;
     }
@@ -2903,6 +3109,32 @@ static int launch_scan(kv_shard *s, const Scan2Params &P, int n_both) {
 #undef KV_CASE
         case 6: rc = launch_scan_variant<EPI, 16, 8, 3, 1, true>(s, P); break;
         default: return fail(KV_E_INVALID, "unknown scan variant");
+    }
+    KV_TRY(rc);
+    count_launch(s);
+    if (s->profiling) CU(cudaEventRecord(s->ev1, s->stream));
+    return KV_OK;
+}
+
+// The candidate-streaming step only exists for the default ring shapes (variants 1 / 5 / 6 of launch_scan, same
+// choice); a forced KOVER_B200_SCAN_VARIANT other than those keeps the counting kernel (-> false).
+static constexpr int kCandCap = 2048;                 // candidate records per CTA
+static bool stream_variant_ok(const kv_shard *s) {
+    const int v = s->scan_variant;
+    return v < 0 || v > kNumScanVariants || v == 1 || v == 5 || v == 6;
+}
+static int launch_scan_stream(kv_shard *s, const Scan2Params &P) {
+    int v = s->scan_variant;
+    if (v == 6 && P.inline_rec) v = -1;
+    if (v < 0 || v > kNumScanVariants) v = ((size_t)P.n_act * 20 > 30 * 1024) ? 5 : 1;
+    if (v == 5 && scan_smem_bytes<16, 4, 4>((size_t)P.n_act) > kSmemLimit) v = 6;
+    if (s->profiling) CU(cudaEventRecord(s->ev0, s->stream));
+    int rc;
+    switch (v) {
+        case 1: rc = launch_scan_variant<EPI_SCM_STREAM, 16, 8, 3, 1>(s, P); break;
+        case 5: rc = launch_scan_variant<EPI_SCM_STREAM, 16, 4, 4, 1>(s, P); break;
+        case 6: rc = launch_scan_variant<EPI_SCM_STREAM, 16, 8, 3, 1, true>(s, P); break;
+        default: return fail(KV_E_INVALID, "no streaming kernel for this scan variant");
     }
     KV_TRY(rc);
     count_launch(s);
@@ -3360,8 +3592,11 @@ static int ensure_ties(kv_shard *s, long long cap) {
     return ensure(s->d_ties, sizeof(TieHeader) + (size_t)std::max<long long>(cap, kTieFirstBatch) * sizeof(TieRec));
 }
 
+static int scm_materialize(kv_shard *s);
+
 static int scm_scan_async(kv_shard *s, const uint64_t *pos_mask, const uint64_t *neg_mask, int64_t n_pos, int64_t n_neg,
                           double p, int64_t ubs, int64_t n_blocks) {
+    if (s->reuse_armed && s->scm_valid && s->scm_lazy) KV_TRY(scm_materialize(s));   // (before d_misc is laid out below)
     if (n_pos < 0 || n_neg < 0 || n_pos > s->n_examples || n_neg > s->n_examples) {
         s->reuse_armed = false;
         return fail(KV_E_INVALID, "kv_scm_scan: n_pos / n_neg out of range");
@@ -3444,6 +3679,25 @@ static int scm_scan_async(kv_shard *s, const uint64_t *pos_mask, const uint64_t 
     s->scm_n_neg = n_neg;
     s->scm_ubs = ubs;
     s->scm_p = p;
+    return KV_OK;
+}
+
+// The last SCM step streamed its candidates and wrote no count arrays (EPI_SCM_STREAM): scan the same masks once more
+// with the counting kernel, so that the count arrays, segment maxima and scm_* bookkeeping are what a counting step
+// would have left.  Only the rare consumers of resident counts pay for it (kv_scm_reuse_counts, kv_scm_ties after a
+// packet overflow).
+static int scm_materialize(kv_shard *s) {
+    if (!s->scm_lazy) return KV_OK;
+    s->scm_lazy = false;
+    const bool armed = s->reuse_armed;
+    s->reuse_armed = false;
+    const uint64_t *pm = s->lazy_from_state ? nullptr : s->lazy_masks.data();
+    const uint64_t *nm = pm ? pm + s->W : nullptr;
+    const int64_t nb = kv_scm_n_blocks(s->k_total, s->scm_ubs);
+    KV_TRY(scm_scan_async(s, pm, nm, s->scm_n_pos, s->scm_n_neg, s->scm_p, s->scm_ubs, nb));
+    MiscLayout L = misc_layout(s->d_misc.p, nb);
+    CU(cudaMemsetAsync(L.blockmax, 0, (size_t)nb * 8, s->stream));    // nobody reads these maxima: leave the accumulators clean
+    s->reuse_armed = armed;
     return KV_OK;
 }
 
@@ -3609,6 +3863,7 @@ extern "C" int kv_scm_ties(kv_shard *s, const double *block_max, const uint8_t *
     if (capacity < 0) return fail(KV_E_INVALID, "kv_scm_ties: negative capacity");
     DeviceGuard g(s->device);
     s->last_launches = 0;
+    KV_TRY(scm_materialize(s));
     // merged block table (host) -> pinned -> device: bm | tol | sel are contiguous in d_misc
     MiscLayout L = misc_layout(s->d_misc.p, n_blocks);
     const size_t tab_bytes = (size_t)n_blocks * 16 + ((size_t)n_blocks + 15) / 16 * 16;
@@ -3645,6 +3900,10 @@ static int ensure_state(kv_shard *s) {
 // launch k_mask_and_column and wait for its epoch word; fills the shard's state counters
 static int run_mask_kernel(kv_shard *s, long long col, const uint64_t *d_words, int invert) {
     const long long W = s->W;
+    if (s->scm_lazy && s->lazy_from_state) {     // the masks of the last streamed step are about to change: its counts
+        s->scm_lazy = false;                     // can no longer be produced on demand
+        s->scm_valid = false;
+    }
     MaskColParams M;
     memset(&M, 0, sizeof M);
     M.mat = s->d_mat;
@@ -3784,10 +4043,22 @@ struct P2PTail {                 // what the multi-rank variant of the fused ste
 static int scm_best_rules_fused(kv_shard *s, const uint64_t *pos_mask, const uint64_t *neg_mask, int64_t n_pos,
                                 int64_t n_neg, double p, int64_t ubs, int64_t n_blocks, double *best_utility,
                                 int64_t capacity, int64_t *rule_idx, int64_t *pos_err, int64_t *neg_cover,
-                                int64_t *n_found, P2PTail *p2p_tail = nullptr) {
+                                int64_t *n_found, P2PTail *p2p_tail = nullptr, bool allow_stream = true) {
     if (n_pos < 0 || n_neg < 0 || n_pos > s->n_examples || n_neg > s->n_examples)
         return fail(KV_E_INVALID, "kv_scm_scan: n_pos / n_neg out of range");
     KV_TRY(ensure_fused(s, n_blocks));
+    // candidate streaming (EPI_SCM_STREAM) unless switched off, backing off after an overflow, or p is not finite
+    bool stream = allow_stream && s->stream_cand && std::isfinite(p) && stream_variant_ok(s);
+    if (stream && s->stream_backoff > 0) {
+        --s->stream_backoff;
+        stream = false;
+    }
+    if (stream && !s->d_cand) {
+        CU(cudaMalloc(&s->d_cand, (size_t)s->sm_count * 2 * kCandCap * sizeof(TieRec)));
+        CU(cudaMalloc(&s->d_cand_n, (size_t)s->sm_count * 2 * sizeof(unsigned)));
+    }
+    const uint64_t *const in_pos = pos_mask, *const in_neg = neg_mask;
+    const int64_t in_n_pos = n_pos, in_n_neg = n_neg;
     KV_TRY(ensure_counts(s, 2));
     if (!s->d_segmax) CU(cudaMalloc(&s->d_segmax, (size_t)(s->ld / 64) * 2 * 8));
     KV_TRY(ensure(s->d_misc, misc_layout(nullptr, n_blocks).bytes));
@@ -3846,7 +4117,21 @@ static int scm_best_rules_fused(kv_shard *s, const uint64_t *pos_mask, const uin
         F.host_bm = (double *)((char *)s->h_fused + kFusedHdrBytes + (size_t)kFusedCap * sizeof(TieRec));
         F.host_sel = (uint8_t *)(F.host_bm + FUSED_MAX_BLOCKS);
     }
-    KV_TRY(launch_scan<EPI_SCM>(s, P, n_both));
+    if (stream) {
+        P.cand = s->d_cand;
+        P.cand_n = s->d_cand_n;
+        P.cand_cap = kCandCap;
+        KV_TRY(launch_scan_stream(s, P));
+        s->lazy_from_state = in_pos == nullptr;
+        if (in_pos) {
+            s->lazy_masks.resize((size_t)s->W * 2);
+            memcpy(s->lazy_masks.data(), in_pos, (size_t)s->W * 8);
+            memcpy(s->lazy_masks.data() + s->W, in_neg, (size_t)s->W * 8);
+        }
+    } else {
+        KV_TRY(launch_scan<EPI_SCM>(s, P, n_both));
+    }
+    s->scm_lazy = stream;
     s->scm_cnt_a = s->d_cnt[0];
     s->scm_cnt_b = s->d_cnt[1];
     s->scm_swapped = false;
@@ -3882,6 +4167,27 @@ static int scm_best_rules_fused(kv_shard *s, const uint64_t *pos_mask, const uin
     if (s->profiling) {
         CU(cudaStreamSynchronize(s->stream));
         KV_TRY(finish_scan_timing(s));
+    }
+    if (stream) {
+        // a candidate list overflowed / every rule blacklisted / more ties than the result buffer holds: this step is
+        // redone with the count arrays (single shard: here; ranks: by the two-phase fallback through scm_materialize)
+        const bool redo = p2p_tail ? h[3] == 2ull : found > kFusedCap;
+        s->stream_steps += 1;
+        if (redo) {
+            s->stream_redos += 1;
+            s->stream_backoff = s->stream_backoff_len;
+            s->stream_backoff_len = std::min(s->stream_backoff_len * 2, 1024);
+            if (!p2p_tail) {
+                if (s->profiling) {
+                    CU(cudaStreamSynchronize(s->stream));
+                    KV_TRY(finish_scan_timing(s));
+                }
+                return scm_best_rules_fused(s, in_pos, in_neg, in_n_pos, in_n_neg, p, ubs, n_blocks, best_utility, capacity,
+                                            rule_idx, pos_err, neg_cover, n_found, nullptr, false);
+            }
+        } else {
+            s->stream_backoff_len = 8;
+        }
     }
     if (p2p_tail) {
         s->exch_publish_us += (double)(h[5] - h[4]) * 1e-3;      // device globaltimer stamps of the last CTA

@@ -240,14 +240,16 @@ def test_util_block_size_changes_between_calls(devices):
     rc.close()
 
 
-@pytest.mark.parametrize("fused,coop", [("1", "1"), ("1", "0"), ("0", "1")], ids=["fused-coop", "fused-plain", "unfused"])
-def test_single_launch_step_modes(monkeypatch, fused, coop):
+@pytest.mark.parametrize("fused,coop,stream", [("1", "1", "1"), ("1", "1", "0"), ("1", "0", "0"), ("0", "1", "0")],
+                         ids=["fused-stream", "fused-coop", "fused-plain", "unfused"])
+def test_single_launch_step_modes(monkeypatch, fused, coop, stream):
     """The single-shard step as ONE kernel (scan -> grid barrier -> block merge -> ties into mapped host memory,
     cooperative or plain launch) and as the scan + select + ties sequence: both against the checker, over repeated
     calls (the monotonic barrier / epoch counters and the parity-alternating accumulators), several block counts,
     few and thousands of ties, blacklists, through the mask and the index-array entry points."""
     monkeypatch.setenv("KOVER_B200_FUSED", fused)
     monkeypatch.setenv("KOVER_B200_COOP", coop)
+    monkeypatch.setenv("KOVER_B200_STREAM", stream)
     n, k, seed = 900, 200000, 12
     P = synthetic_block(seed, n, 0, k)
     P[:, 150000:150050] = P[:, 7:8]                    # 50 copies of one k-mer: equivalent rules
@@ -276,6 +278,90 @@ def test_single_launch_step_modes(monkeypatch, fused, coop):
         rc.best_utility_rules(1.0, np.array([0, n]), neg)
     with pytest.raises(IndexError):
         rc.best_utility_rules(1.0, pos, np.array([-1]))
+    info = shard.info()
+    if stream == "1":
+        assert info.stream_steps > 0 and info.stream_redos < info.stream_steps
+    else:
+        assert info.stream_steps == 0
+    rc.close()
+
+
+def test_candidate_streaming_step():
+    """The step that writes no count arrays (k_scan_tma<EPI_SCM_STREAM>: candidates streamed against the running
+    maximum, filtered by the grid's last CTA) against the checker where it has to give up and redo the step with the
+    counting kernel -- every rule blacklisted (best utility -inf), one CTA's candidate list overflowing (tens of
+    thousands of identical columns), more ties than the result buffer -- and where later calls want the counts it
+    did not write: kv_scm_reuse_counts (another p, exchanged roles) and kv_scm_ties produce them on demand."""
+    n, k, seed = 700, 120000, 5
+    P = synthetic_block(seed, n, 0, k)
+    y = synthetic_labels(seed, n, sorted_by_label=False)
+    pos, neg = np.where(y == 1)[0], np.where(y == 0)[0]
+    orc = ko.OracleKmerRuleClassifications(P, n, fast=True)
+    rc = KmerRuleClassifications(P, n, devices=[0])
+    shard = rc._group.shards[0]
+    none = np.zeros(2 * k, dtype=bool)
+
+    def want(p, a, b, blm=none, ubs=25000):
+        return ko.merge_utility_blocks(len(b) - orc.sum_rows(b), len(a) - orc.sum_rows(a), p, blm, block_size=ubs)
+
+    def same(got, w):
+        assert got[0] == w[0] and np.array_equal(got[1], np.asarray(w[1], dtype=np.int64))
+        assert np.array_equal(got[2], w[2]) and np.array_equal(got[3], w[3])
+
+    # plain streamed steps
+    for p in (0.1, 1.0, 999999.0):
+        same(rc.best_utility_rules(p, pos, neg, util_block_size=25000), want(p, pos, neg))
+    i0 = shard.info()
+    assert i0.stream_steps == 3 and i0.stream_redos == 0
+    # the counts of a streamed step on demand: another p from the "resident" counts, then with exchanged roles
+    mp, mn = rc.row_mask(pos), rc.row_mask(neg)
+    shard.scm_best_rules(mp, mn, len(pos), len(neg), 1.0, 25000)
+    shard.scm_reuse_counts(False)
+    same(shard.scm_best_rules(mp, mn, len(pos), len(neg), 2.5, 25000), want(2.5, pos, neg))
+    shard.scm_reuse_counts(True)
+    same(shard.scm_best_rules(mn, mp, len(neg), len(pos), 0.5, 9999), want(0.5, neg, pos, ubs=9999))
+    assert shard.info().rescore_calls == i0.rescore_calls + 2
+    # ... and the two-phase tie collection on the block table of the host
+    w = want(1.0, pos, neg)
+    shard.scm_best_rules(mp, mn, len(pos), len(neg), 1.0, 25000)
+    cnt_neg, cnt_pos = orc.sum_rows(neg), orc.sum_rows(pos)
+    u = np.concatenate([(len(neg) - cnt_neg) - 1.0 * (len(pos) - cnt_pos), cnt_neg - 1.0 * cnt_pos])
+    nb = (2 * k + 24999) // 25000
+    bm = np.array([u[b * 25000:(b + 1) * 25000].max() for b in range(nb)])
+    best, sel = _native.select_blocks(bm)
+    idx, pe, nc = shard.scm_ties(bm, sel)
+    assert best == w[0] and np.array_equal(idx, np.asarray(w[1], dtype=np.int64)) and np.array_equal(pe, w[2])
+    # every rule blacklisted: best utility -inf, every rule of the selected blocks ties
+    everything = np.arange(2 * k)
+    blm = np.ones(2 * k, dtype=bool)
+    r0 = shard.info().stream_redos
+    got = rc.best_utility_rules(1.0, pos, neg, rule_blacklist=everything, util_block_size=25000)
+    w = want(1.0, pos, neg, blm)
+    assert got[0] == w[0] == -np.inf and np.array_equal(got[1], np.asarray(w[1], dtype=np.int64))
+    assert shard.info().stream_redos == r0 + 1
+    same(rc.best_utility_rules(1.0, pos, neg, util_block_size=25000), want(1.0, pos, neg))   # (blacklist cleared)
+    rc.close()
+
+    # one k-mer copied 30 000 times next to each other: the candidate lists of the CTAs that hold the copies overflow
+    # (4 tiles = 8 192 rules per CTA against 2 048 candidate slots)
+    n, k = 300, 600000
+    P2 = synthetic_block(seed, n, 0, k)
+    P2[:, 200000:230000] = P2[:, 11:12]
+    y = synthetic_labels(seed, n, sorted_by_label=False)
+    pos, neg = np.where(y == 1)[0], np.where(y == 0)[0]
+    orc = ko.OracleKmerRuleClassifications(P2, n, fast=True)
+    rc = KmerRuleClassifications(P2, n, devices=[0])
+    shard = rc._group.shards[0]
+    none = np.zeros(2 * k, dtype=bool)
+    col = orc.get_columns(11).astype(bool)
+    a, b = pos[~col[pos]][:40], neg[col[neg]]          # the copied k-mer's absence rule is far ahead: 30 001 ties
+    w = want(1.0, a, b, none, 1000000)
+    assert len(w[1]) >= 30001
+    for it in range(12):                               # first call: redo; then the back-off window; then a new attempt
+        same(rc.best_utility_rules(1.0, a, b), w)
+    info = shard.info()
+    assert info.stream_redos == 2 and info.stream_steps == 2, (info.stream_steps, info.stream_redos)
+    same(rc.best_utility_rules(1.0, pos, neg), want(1.0, pos, neg, none, 1000000))
     rc.close()
 
 
