@@ -696,7 +696,10 @@ def run_ours(args):
         "dtype": "u64 popcount + f64 utility", "data": "synthetic (hash-generated on device, seed %d)" % SEED,
         "config": workload_config(world),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "traffic_source": traffic_src, "kernel": "k_scan_tma<EPI_SCM>",
+                     "traffic": traffic, "traffic_source": traffic_src,
+                     "kernel": "k_scan_tma<EPI_SCM_STREAM> (the whole step: scan + candidate filter + result)",
+                     "note": "peak = measured COPY bandwidth (half reads, half writes); this kernel only reads, so a "
+                             "fraction slightly above 1 is possible",
                      "peak_source": peak_src,
                      "bytes_per_launch": float(np.mean(alg_bytes)), "kernel_ms": float(np.mean(kernel_ms)),
                      "kernel_share_of_step": float(np.sum(kernel_ms) / dev_ms)},
@@ -710,6 +713,8 @@ def run_ours(args):
                 "api": "SetCoveringMachine._get_best_utility_rules(rule_classifications, pos_idx, neg_idx) with host "
                        "index arrays in, host tie arrays out; matrix resident (uploaded once per dataset)"},
         "gpu_launches": int(launches),
+        "steps_streamed": int(info_b.stream_steps - info_a.stream_steps),           # rank 0: steps that wrote no count
+        "steps_redone_with_counts": int(info_b.stream_redos - info_a.stream_redos),  # arrays / had to be redone with them
         "parity_checked": bool(parity_ok),
         "clocks": clocks.summary(),
         "wall_ms_per_step": 1e3 * wall_s / args.steps,
