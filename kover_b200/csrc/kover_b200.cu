@@ -2185,6 +2185,62 @@ struct DevBuf {
     size_t bytes = 0;
 };
 
+// Page-locked staging buffers outlive the shard that first needed them: pinning host memory costs ~1 ms per MB
+// (70 ms for the four 16 MB slots of the deflate upload, measured), which a process that opens one dataset after the
+// other (or one shard per device) would pay every time.  Buffers are handed back at kv_destroy and kept for the next
+// shard, up to kPinnedCacheBytes in total; portable, so any device's streams may use them.
+static constexpr size_t kPinnedCacheBytes = (size_t)512 << 20;
+struct PinnedCache {
+    struct Ent {
+        void *p;
+        size_t bytes;
+        bool busy;
+    };
+    std::mutex mu;
+    std::vector<Ent> ents;
+};
+static PinnedCache g_pinned;
+
+static cudaError_t pinned_borrow(void **out, size_t bytes) {
+    {
+        std::lock_guard<std::mutex> lock(g_pinned.mu);
+        PinnedCache::Ent *best = nullptr;
+        for (auto &e : g_pinned.ents)
+            if (!e.busy && e.bytes >= bytes && (!best || e.bytes < best->bytes)) best = &e;
+        if (best) {
+            best->busy = true;
+            *out = best->p;
+            return cudaSuccess;
+        }
+    }
+    void *p = nullptr;
+    const cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocPortable);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lock(g_pinned.mu);
+    g_pinned.ents.push_back({p, bytes, true});
+    *out = p;
+    return cudaSuccess;
+}
+
+static void pinned_return(void *p) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lock(g_pinned.mu);
+    size_t idle = 0;
+    for (auto &e : g_pinned.ents)
+        if (!e.busy) idle += e.bytes;
+    for (size_t i = 0; i < g_pinned.ents.size(); ++i) {
+        if (g_pinned.ents[i].p != p) continue;
+        if (idle + g_pinned.ents[i].bytes > kPinnedCacheBytes) {
+            cudaFreeHost(p);
+            g_pinned.ents.erase(g_pinned.ents.begin() + (long)i);
+        } else {
+            g_pinned.ents[i].busy = false;
+        }
+        return;
+    }
+    cudaFreeHost(p);                             // (not one of ours)
+}
+
 struct kv_p2p;
 static void p2p_destroy(kv_p2p *m);
 struct kv_shard;
@@ -2393,7 +2449,7 @@ extern "C" int kv_destroy(kv_shard *s) {
     if (s->h_fused) cudaFreeHost(s->h_fused);
     if (s->h_state) cudaFreeHost(s->h_state);
     for (int i = 0; i < 4; ++i) {
-        if (s->inf_pin[i]) cudaFreeHost(s->inf_pin[i]);
+        pinned_return(s->inf_pin[i]);
         if (s->inf_pin_free[i]) cudaEventDestroy(s->inf_pin_free[i]);
     }
     if (s->inf_copy_stream) cudaStreamDestroy(s->inf_copy_stream);
@@ -2403,7 +2459,7 @@ extern "C" int kv_destroy(kv_shard *s) {
     if (s->d_cand_n) cudaFree(s->d_cand_n);
     if (s->d_fused_bm) cudaFree(s->d_fused_bm);
     for (int i = 0; i < 2; ++i) {
-        if (s->h_up[i]) cudaFreeHost(s->h_up[i]);
+        pinned_return(s->h_up[i]);
         if (s->ev_up[i]) cudaEventDestroy(s->ev_up[i]);
     }
     if (s->ev0) cudaEventDestroy(s->ev0);
@@ -2449,7 +2505,7 @@ static int ensure_upload_ring(kv_shard *s) {
     s->h_up_bytes = (size_t)32 << 20;
     if (const char *v = getenv("KOVER_B200_UPLOAD_SLOT_MB")) s->h_up_bytes = (size_t)std::max(1, atoi(v)) << 20;
     for (int i = 0; i < 2; ++i) {
-        CU(cudaMallocHost(&s->h_up[i], s->h_up_bytes));
+        CU(pinned_borrow(&s->h_up[i], s->h_up_bytes));
         CU(cudaEventCreateWithFlags(&s->ev_up[i], cudaEventDisableTiming));
     }
     return KV_OK;
@@ -2641,9 +2697,9 @@ static int ensure_inflate_staging(kv_shard *s, size_t slot_bytes) {
     if (!s->inf_copy_stream) CU(cudaStreamCreateWithFlags(&s->inf_copy_stream, cudaStreamNonBlocking));
     if (s->inf_slot_bytes >= slot_bytes) return KV_OK;
     for (int i = 0; i < kInflateSlots; ++i) {
-        if (s->inf_pin[i]) cudaFreeHost(s->inf_pin[i]);
+        pinned_return(s->inf_pin[i]);
         s->inf_pin[i] = nullptr;
-        CU(cudaMallocHost(&s->inf_pin[i], slot_bytes));
+        CU(pinned_borrow(&s->inf_pin[i], slot_bytes));
         if (!s->inf_pin_free[i]) CU(cudaEventCreateWithFlags(&s->inf_pin_free[i], cudaEventDisableTiming));
     }
     s->inf_slot_bytes = slot_bytes;
