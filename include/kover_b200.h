@@ -63,6 +63,8 @@ typedef struct kv_shard_info {
     double exch_merge_us;    /* ... merging the packets and publishing the result to the host              */
     int64_t stream_steps;    /* fused SCM steps that streamed their candidates (no count arrays written)   */
     int64_t stream_redos;    /* ... of which were redone with the count arrays (candidate / tie overflow)   */
+    int64_t level_nodes_counted;  /* kv_gini_level: nodes whose class masks went through a matrix pass ...          */
+    int64_t level_nodes_derived;  /* ... and nodes whose counts were parent - sibling (kv_gini_level_family)        */
 } kv_shard_info;
 
 const char *kv_last_error(void);
@@ -302,6 +304,16 @@ int kv_gini_best_split(kv_shard *s, int n_classes, const uint64_t *class_masks, 
 int kv_gini_level(kv_shard *s, int64_t n_nodes, const uint64_t *class_masks, const double *altered_prior,
                   const double *n_total, const int64_t *n_node, const int32_t *occ_table, double *min_score,
                   int64_t *n_found, uint32_t *occ_max);
+/* Sibling subtraction across tree levels.  The children of a split partition their parent's examples
+ * (cart.py:300-312: rule true / rule false), so the class counts of one child are the parent's minus the other
+ * child's.  kv_gini_level_family arms the NEXT kv_gini_level call: node_key[i] >= 0 names node i, parent_key[i] the
+ * node it was split from (-1: none; parent_key may be NULL).  The counts of the armed call's nodes stay resident
+ * (slots of one arena sized from the free memory; nodes that find no slot are simply not remembered); when two nodes
+ * of the next armed call name the same resident parent and their n_node add up to the parent's, only the SMALLER one
+ * is counted in the matrix pass and the other one's counts are computed as parent - sibling (exact: integers).
+ * Results are identical with or without the arming; an unarmed kv_gini_level ends the family.  n_nodes = 0 forgets
+ * the resident level, n_nodes < 0 also frees the arena.  KOVER_B200_LEVEL_SUB=0 disables the subtraction. */
+int kv_gini_level_family(kv_shard *s, int64_t n_nodes, const int64_t *node_key, const int64_t *parent_key);
 /* The reference's CART tiebreaker on the device (experiment_cart.py:82-94, 264: among the best splits keep the
  * k-mers whose occurrence count in the tree's training set is numpy.isclose to the largest one).
  * kv_occ_table_set(table 0..63, mask) computes the presence counts of the shard's k-mers under `mask` into a

@@ -25,7 +25,8 @@ class ShardInfo(ctypes.Structure):
                 ("last_launches", _c_i64), ("total_launches", _c_i64), ("scan_ms_total", ctypes.c_double),
                 ("scan_calls", _c_i64), ("rescore_calls", _c_i64), ("exch_steps", _c_i64),
                 ("exch_publish_us", ctypes.c_double), ("exch_wait_us", ctypes.c_double),
-                ("exch_merge_us", ctypes.c_double), ("stream_steps", _c_i64), ("stream_redos", _c_i64)]
+                ("exch_merge_us", ctypes.c_double), ("stream_steps", _c_i64), ("stream_redos", _c_i64),
+                ("level_nodes_counted", _c_i64), ("level_nodes_derived", _c_i64)]
 
 
 # every exported symbol with (restype, argtypes); tests/test_abi.py checks this table against the header
@@ -97,6 +98,7 @@ SYMBOLS = {
     "kv_gini_level": (ctypes.c_int, [_c_p, _c_i64, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p]),
     "kv_occ_table_set": (ctypes.c_int, [_c_p, ctypes.c_int, _c_p]),
     "kv_occ_table_gather": (ctypes.c_int, [_c_p, ctypes.c_int, _c_p, _c_i64, _c_p]),
+    "kv_gini_level_family": (ctypes.c_int, [_c_p, _c_i64, _c_p, _c_p]),
     "kv_gini_level_fetch": (ctypes.c_int, [_c_p, _c_i64, _c_p, _c_i64]),
     "kv_gini_level_result": (ctypes.c_int, [_c_p, _c_i64, ctypes.POINTER(ctypes.POINTER(ctypes.c_int64)),
                                             ctypes.POINTER(_c_i64)]),
@@ -645,13 +647,29 @@ class Shard(object):
         check(self._lib.kv_occ_table_gather(self._h, int(table), ptr(idx), idx.shape[0], ptr(out)))
         return out
 
-    def gini_level(self, node_masks, altered_prior, n_total, n_node, occ_tables=None):
+    def gini_level_family(self, node_keys=None, parent_keys=None, free=False):
+        """Arms the next gini_level (kv_gini_level_family): sibling nodes whose parent was searched by the previous
+        armed call are counted once -- the smaller one -- and the other is parent - sibling.  No keys: forget the
+        resident level (free=True also returns the arena's memory)."""
+        if node_keys is None:
+            check(self._lib.kv_gini_level_family(self._h, -1 if free else 0, None, None))
+            return
+        keys = np.ascontiguousarray(node_keys, dtype=np.int64)
+        parents = np.ascontiguousarray(parent_keys, dtype=np.int64)
+        assert keys.shape == parents.shape and keys.ndim == 1
+        check(self._lib.kv_gini_level_family(self._h, keys.shape[0], ptr(keys), ptr(parents)))
+
+    def gini_level(self, node_masks, altered_prior, n_total, n_node, occ_tables=None, family=None):
         """Split search of several two-class nodes, up to 8 nodes per matrix pass.  node_masks [n_nodes, 2, W],
         n_node [n_nodes, 2] -> [(min score over this shard, rule indices achieving it, ascending)] per node.
         occ_tables [n_nodes] (table id per node, -1 = none): the occurrence tiebreaker is applied on the device; the
-        result entries then carry a third element, the largest occurrence among the node's ties on this shard."""
+        result entries then carry a third element, the largest occurrence among the node's ties on this shard.
+        family = (node keys, parent keys): see gini_level_family."""
         masks = np.ascontiguousarray(node_masks, dtype=np.uint64)
         assert masks.ndim == 3 and masks.shape[1] == 2 and masks.shape[2] == self.n_words
+        if family is not None:
+            assert len(family[0]) == masks.shape[0]
+            self.gini_level_family(family[0], family[1])
         nn = np.ascontiguousarray(n_node, dtype=np.int64)
         # priors / class totals: one pair for all the nodes (one tree) or one pair per node (several trees)
         pri = np.ascontiguousarray(np.broadcast_to(np.asarray(altered_prior, dtype=np.float64), nn.shape))

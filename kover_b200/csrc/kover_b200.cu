@@ -34,6 +34,7 @@
 #include <numeric>
 #include <string>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 // ------------------------------------------------------------------------------------------------
@@ -1961,6 +1962,18 @@ __global__ void __launch_bounds__(256) k_gini2_counts(const GiniParams P, unsign
     }
 }
 
+// class counts of a tree node = its parent's - its sibling's (the children partition the parent's examples)
+__global__ void __launch_bounds__(256) k_sub_counts(const uint4 *__restrict__ par0, const uint4 *__restrict__ par1,
+                                                    const uint4 *__restrict__ sib0, const uint4 *__restrict__ sib1,
+                                                    uint4 *__restrict__ out0, uint4 *__restrict__ out1, long long n4) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const uint4 a = par0[i], b = sib0[i], c = par1[i], d = sib1[i];
+        out0[i] = make_uint4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w);
+        out1[i] = make_uint4(c.x - d.x, c.y - d.y, c.z - d.z, c.w - d.w);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // small kernels
 // ------------------------------------------------------------------------------------------------
@@ -2318,6 +2331,16 @@ struct kv_shard {
     double up_setup_ms = 0.0, up_gather_ms = 0.0, up_total_ms = 0.0;   // phases of the last kv_upload_deflate (host clock)
     DevBuf d_level;                           // kv_gini_level: per-node minima, counters, tie slots, segment minima
     std::vector<uint32_t *> occ_tables;       // kv_occ_table_set: k-mer occurrence counts of a training set, [ld] each
+    // kv_gini_level_family: the class counts of the previous tree level's nodes stay resident (slots of one arena) so
+    // that of two sibling nodes only the smaller is counted and the other one is parent - sibling
+    uint32_t *d_fam_arena = nullptr;          // [fam_slots][2][ld]
+    int fam_slots = 0;
+    bool fam_tried = false;
+    std::vector<int> fam_free;
+    struct FamNode { int slot; long long n[2]; };
+    std::unordered_map<long long, FamNode> fam_prev;
+    std::vector<long long> fam_key, fam_parent;   // armed for the next kv_gini_level
+    long long level_nodes_counted = 0, level_nodes_derived = 0;
     int64_t *h_level = nullptr;               // pinned arena: the tie lists of the last kv_gini_level, node after node
     size_t h_level_cap = 0, h_level_used = 0; // in entries
     std::vector<std::pair<size_t, size_t>> level_span;   // (offset, count) of every node in the arena
@@ -2439,6 +2462,7 @@ extern "C" int kv_destroy(kv_shard *s) {
     for (auto p : s->d_cnt) cudaFree(p);
     for (auto p : s->occ_tables)
         if (p) cudaFree(p);
+    if (s->d_fam_arena) cudaFree(s->d_fam_arena);
     for (DevBuf *b : {&s->d_rec, &s->d_misc, &s->d_ties, &s->d_stage, &s->d_sort_tmp, &s->d_sort_io, &s->d_queue, &s->d_level, &s->d_qmisc, &s->d_qseg})
         if (b->p) cudaFree(b->p);
     if (s->d_black_pres) cudaFree(s->d_black_pres);
@@ -2494,6 +2518,8 @@ extern "C" int kv_get_info(kv_shard *s, kv_shard_info *o) {
     o->exch_merge_us = s->exch_merge_us;
     o->stream_steps = s->stream_steps;
     o->stream_redos = s->stream_redos;
+    o->level_nodes_counted = s->level_nodes_counted;
+    o->level_nodes_derived = s->level_nodes_derived;
     return KV_OK;
 }
 
@@ -5253,6 +5279,67 @@ extern "C" int kv_occ_table_gather(kv_shard *s, int table, const int64_t *rule_i
     return KV_OK;
 }
 
+// ---- sibling subtraction (kv_gini_level_family) --------------------------------------------------------------------
+static void fam_release_prev(kv_shard *s) {
+    for (auto &kv : s->fam_prev) s->fam_free.push_back(kv.second.slot);
+    s->fam_prev.clear();
+}
+
+// one arena for the node count slots, sized once from the memory that is free at the first armed level search
+static void fam_arena_init(kv_shard *s) {
+    if (s->fam_tried) return;
+    s->fam_tried = true;
+    if (const char *v = getenv("KOVER_B200_LEVEL_SUB"))
+        if (atoi(v) == 0) return;
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) {
+        cudaGetLastError();
+        return;
+    }
+    double frac = 0.25;
+    long long cap = 320;
+    if (const char *v = getenv("KOVER_B200_LEVEL_POOL_FRAC")) frac = std::min(0.8, std::max(0.0, atof(v)));
+    if (const char *v = getenv("KOVER_B200_LEVEL_POOL_SLOTS")) cap = std::max(0, atoi(v));
+    const size_t slot_bytes = (size_t)2 * s->ld * sizeof(uint32_t);
+    const long long n = std::min<long long>(cap, (long long)(frac * (double)free_b / (double)slot_bytes));
+    if (n < 3) return;
+    if (cudaMalloc(&s->d_fam_arena, (size_t)n * slot_bytes) != cudaSuccess) {
+        cudaGetLastError();
+        s->d_fam_arena = nullptr;
+        return;
+    }
+    s->fam_slots = (int)n;
+    for (int i = (int)n - 1; i >= 0; --i) s->fam_free.push_back(i);
+}
+
+// Arms the NEXT kv_gini_level call of the shard: node_key[i] >= 0 names node i (unique over the life of the shard's
+// current trees), parent_key[i] the node it was split from (-1: none).  Two nodes of the call with the same parent whose
+// counts are still resident (it was searched by the previous armed call) are siblings: only the smaller one is counted
+// in the matrix pass, the other one's class counts are parent - sibling.  n_nodes = 0 forgets the resident level,
+// n_nodes < 0 also returns the arena's memory.
+extern "C" int kv_gini_level_family(kv_shard *s, int64_t n_nodes, const int64_t *node_key, const int64_t *parent_key) {
+    if (!s) return fail(KV_E_INVALID, "kv_gini_level_family: null shard");
+    s->fam_key.clear();
+    s->fam_parent.clear();
+    if (n_nodes <= 0 || !node_key) {
+        fam_release_prev(s);
+        if (n_nodes < 0 && s->d_fam_arena) {
+            DeviceGuard g(s->device);
+            CU(cudaStreamSynchronize(s->stream));
+            cudaFree(s->d_fam_arena);
+            s->d_fam_arena = nullptr;
+            s->fam_slots = 0;
+            s->fam_free.clear();
+            s->fam_tried = false;
+        }
+        return KV_OK;
+    }
+    s->fam_key.assign(node_key, node_key + n_nodes);
+    if (parent_key) s->fam_parent.assign(parent_key, parent_key + n_nodes);
+    else s->fam_parent.assign((size_t)n_nodes, -1);
+    return KV_OK;
+}
+
 extern "C" int kv_gini_level(kv_shard *s, int64_t n_nodes, const uint64_t *class_masks, const double *altered_prior,
                              const double *n_total, const int64_t *n_node, const int32_t *occ_table, double *min_score,
                              int64_t *n_found, uint32_t *occ_max) {
@@ -5266,56 +5353,139 @@ extern "C" int kv_gini_level(kv_shard *s, int64_t n_nodes, const uint64_t *class
     DeviceGuard g(s->device);
     s->last_launches = 0;
     s->scm_valid = s->gini_valid = false;
-    s->level_span.clear();
+    s->level_span.assign((size_t)n_nodes, std::pair<size_t, size_t>(0, 0));
     s->h_level_used = 0;
     const int per = std::max(1, std::min(kLevelNodesPerPass, max_masks_per_pass(s->W) / 2));
+    const int per2 = 2 * per;                 // nodes per batch: up to `per` counted + their derived siblings
     const long long W = s->W, n_seg_ld = s->ld / 64;
+
+    // ---- plan: which nodes are counted, which are parent - sibling, where the counts of each node go ----
+    std::vector<long long> key, parent;
+    const bool armed = (int64_t)s->fam_key.size() == n_nodes;
+    if (armed) {
+        key.swap(s->fam_key);
+        parent.swap(s->fam_parent);
+        fam_arena_init(s);
+    } else {
+        fam_release_prev(s);                  // an unarmed search ends the family: nothing refers to the old level any more
+    }
+    s->fam_key.clear();
+    s->fam_parent.clear();
+    std::vector<int> slot((size_t)n_nodes, -1), derived_sib((size_t)n_nodes, -1), parent_slot((size_t)n_nodes, -1);
+    std::vector<char> is_derived((size_t)n_nodes, 0);
+    if (armed && s->fam_slots) {
+        std::unordered_map<long long, std::vector<int>> kids;
+        for (int64_t i = 0; i < n_nodes; ++i)
+            if (key[i] >= 0 && parent[i] >= 0 && s->fam_prev.count(parent[i])) kids[parent[i]].push_back((int)i);
+        for (int64_t i = 0; i < n_nodes; ++i) {                    // (node order: which pairs get the last slots is deterministic)
+            if (parent[i] < 0) continue;
+            auto it = kids.find(parent[i]);
+            if (it == kids.end() || it->second.size() != 2 || it->second[0] != (int)i) continue;
+            const int a = it->second[0], b = it->second[1];
+            const kv_shard::FamNode &pn = s->fam_prev[parent[i]];
+            if (pn.n[0] != n_node[a * 2] + n_node[b * 2] || pn.n[1] != n_node[a * 2 + 1] + n_node[b * 2 + 1]) continue;
+            if (s->fam_free.empty()) break;
+            const long long na = n_node[a * 2] + n_node[a * 2 + 1], nb_ = n_node[b * 2] + n_node[b * 2 + 1];
+            const int cnt = na <= nb_ ? a : b, der = na <= nb_ ? b : a;
+            slot[der] = s->fam_free.back();
+            s->fam_free.pop_back();
+            is_derived[der] = 1;
+            derived_sib[cnt] = der;
+            parent_slot[der] = pn.slot;
+        }
+        for (int64_t i = 0; i < n_nodes && !s->fam_free.empty(); ++i)
+            if (!is_derived[i] && key[i] >= 0) {
+                slot[i] = s->fam_free.back();
+                s->fam_free.pop_back();
+            }
+    }
+    struct SlotGuard {                        // an error return gives the slots taken above back
+        kv_shard *s;
+        std::vector<int> *slot;
+        bool keep = false;
+        ~SlotGuard() {
+            if (!keep)
+                for (int sl : *slot)
+                    if (sl >= 0) s->fam_free.push_back(sl);
+        }
+    } slot_guard{s, &slot};
+    std::vector<int> counted;
+    for (int64_t i = 0; i < n_nodes; ++i)
+        if (!is_derived[i]) counted.push_back((int)i);
+    auto slot_ptr = [&](int sl, int c) { return s->d_fam_arena + ((size_t)sl * 2 + c) * (size_t)s->ld; };
+
     KV_TRY(ensure_counts(s, 2 + 2 * per));
-    // d_level: min enc [per] | counter [per] | ties [per][kLevelSlotIdx] | segmin [per][ld/64] | score tables [per][4096]
-    //          | occurrence maxima u32 [2 * per]
-    const size_t level_bytes = (size_t)per * 16 + (size_t)per * kLevelSlotIdx * 8 + (size_t)per * n_seg_ld * 8 +
-                               (size_t)per * GINI2_TABLE_MAX * 8 + (size_t)per * 8;
+    // d_level: min enc [per2] | counter [per2] | ties [per2][kLevelSlotIdx] | segmin [per2][ld/64] | score tables
+    //          [per2][4096] | occurrence maxima u32 [2 * per2]
+    const size_t level_bytes = (size_t)per2 * 16 + (size_t)per2 * kLevelSlotIdx * 8 + (size_t)per2 * n_seg_ld * 8 +
+                               (size_t)per2 * GINI2_TABLE_MAX * 8 + (size_t)per2 * 8;
     KV_TRY(ensure(s->d_level, level_bytes));
-    unsigned long long *d_min = (unsigned long long *)s->d_level.p, *d_cntr = d_min + per;
-    long long *d_ties = (long long *)(d_cntr + per);
-    unsigned long long *d_segmin = (unsigned long long *)(d_ties + (size_t)per * kLevelSlotIdx);
-    double *d_tables = (double *)(d_segmin + (size_t)per * n_seg_ld);
-    unsigned int *d_occmax = (unsigned int *)(d_tables + (size_t)per * GINI2_TABLE_MAX);
-    const size_t hdr_bytes = (size_t)per * 16 + (size_t)per * kLevelSlotIdx * 8;
-    KV_TRY(ensure_pinned(s, count_batch_stride(W) + hdr_bytes + (size_t)per * 8));
+    unsigned long long *d_min = (unsigned long long *)s->d_level.p, *d_cntr = d_min + per2;
+    long long *d_ties = (long long *)(d_cntr + per2);
+    unsigned long long *d_segmin = (unsigned long long *)(d_ties + (size_t)per2 * kLevelSlotIdx);
+    double *d_tables = (double *)(d_segmin + (size_t)per2 * n_seg_ld);
+    unsigned int *d_occmax = (unsigned int *)(d_tables + (size_t)per2 * GINI2_TABLE_MAX);
+    const size_t hdr_bytes = (size_t)per2 * 16 + (size_t)per2 * kLevelSlotIdx * 8;
+    KV_TRY(ensure_pinned(s, count_batch_stride(W) + hdr_bytes + (size_t)per2 * 8));
     CU(cudaStreamSynchronize(s->stream));
     char *pin_rec = (char *)s->h_pin;
     const unsigned long long *h_hdr = (const unsigned long long *)((char *)s->h_pin + count_batch_stride(W));
     const long long n_seg = (s->n_cols + 63) / 64;
     const unsigned grid_score = (unsigned)std::max<long long>(1, std::min<long long>((n_seg + 7) / 8, (long long)s->sm_count * 8));
     const unsigned grid_ties = (unsigned)std::max<long long>(1, std::min<long long>((n_seg + 255) / 256, (long long)s->sm_count * 4));
+    const unsigned grid_sub = (unsigned)std::max<long long>(1, std::min<long long>((s->ld / 4 + 255) / 256, (long long)s->sm_count * 8));
     float scan_ms = 0;
-    for (int64_t b0 = 0; b0 < n_nodes; b0 += per) {
-        const int nb = (int)std::min<int64_t>(per, n_nodes - b0);
+    for (size_t b0 = 0; b0 < counted.size(); b0 += (size_t)per) {
+        const int nc = (int)std::min<size_t>((size_t)per, counted.size() - b0);
+        // the batch's nodes: the counted ones, then the siblings derived from them
+        std::vector<int> node;
+        std::vector<int> from;                                       // derived: batch index of the counted sibling; else -1
         std::vector<const uint64_t *> ptrs;
         std::vector<uint32_t *> dst;
-        for (int i = 0; i < nb; ++i) {
-            const uint64_t *m = class_masks + (size_t)(b0 + i) * 2 * W;
+        for (int i = 0; i < nc; ++i) {
+            const int nd = counted[b0 + i];
+            node.push_back(nd);
+            from.push_back(-1);
+            const uint64_t *m = class_masks + (size_t)nd * 2 * W;
             ptrs.push_back(m);
             ptrs.push_back(m + W);
-            dst.push_back(s->d_cnt[2 + 2 * i]);
-            dst.push_back(s->d_cnt[3 + 2 * i]);
+            dst.push_back(slot[nd] >= 0 ? slot_ptr(slot[nd], 0) : s->d_cnt[2 + 2 * i]);
+            dst.push_back(slot[nd] >= 0 ? slot_ptr(slot[nd], 1) : s->d_cnt[3 + 2 * i]);
         }
-        KV_TRY(count_masks_async(s, 2 * nb, ptrs.data(), dst.data(), pin_rec));
+        for (int i = 0; i < nc; ++i)
+            if (derived_sib[node[i]] >= 0) {
+                const int nd = derived_sib[node[i]];
+                node.push_back(nd);
+                from.push_back(i);
+                dst.push_back(slot_ptr(slot[nd], 0));
+                dst.push_back(slot_ptr(slot[nd], 1));
+            }
+        const int nb = (int)node.size();
+        KV_TRY(count_masks_async(s, 2 * nc, ptrs.data(), dst.data(), pin_rec));
         s->scan_calls += 1;
-        CU(cudaMemsetAsync(d_min, 0xFF, (size_t)per * 8, s->stream));
-        CU(cudaMemsetAsync(d_cntr, 0, (size_t)per * 8, s->stream));
-        CU(cudaMemsetAsync(d_occmax, 0, (size_t)per * 8, s->stream));
+        s->level_nodes_counted += nc;
+        s->level_nodes_derived += nb - nc;
+        CU(cudaMemsetAsync(d_min, 0xFF, (size_t)per2 * 8, s->stream));
+        CU(cudaMemsetAsync(d_cntr, 0, (size_t)per2 * 8, s->stream));
+        CU(cudaMemsetAsync(d_occmax, 0, (size_t)per2 * 8, s->stream));
         std::vector<GiniParams> params((size_t)nb);
         for (int i = 0; i < nb; ++i) {
+            const int nd = node[i];
+            if (from[i] >= 0) {
+                k_sub_counts<<<grid_sub, 256, 0, s->stream>>>(
+                    (const uint4 *)slot_ptr(parent_slot[nd], 0), (const uint4 *)slot_ptr(parent_slot[nd], 1),
+                    (const uint4 *)dst[2 * from[i]], (const uint4 *)dst[2 * from[i] + 1], (uint4 *)dst[2 * i],
+                    (uint4 *)dst[2 * i + 1], s->ld / 4);
+                count_launch(s);
+            }
             GiniParams &G = params[i];
             memset(&G, 0, sizeof G);
             G.n_classes = 2;
             for (int c = 0; c < 2; ++c) {
                 G.cnt[c] = dst[2 * i + c];
-                G.prior[c] = altered_prior[(b0 + i) * 2 + c];
-                G.n_total[c] = n_total[(b0 + i) * 2 + c];
-                G.n_node[c] = (double)n_node[(b0 + i) * 2 + c];
+                G.prior[c] = altered_prior[nd * 2 + c];
+                G.n_total[c] = n_total[nd * 2 + c];
+                G.n_node[c] = (double)n_node[nd * 2 + c];
             }
             G.n_cols = s->n_cols;
             G.col0 = s->col0;
@@ -5326,17 +5496,17 @@ extern "C" int kv_gini_level(kv_shard *s, int64_t n_nodes, const uint64_t *class
             G.segmin = d_segmin + (size_t)i * n_seg_ld;
             G.out_idx = d_ties + (size_t)i * kLevelSlotIdx;
             G.cap = kLevelSlotIdx;
-            const long long pairs = (n_node[(b0 + i) * 2] + 1) * (n_node[(b0 + i) * 2 + 1] + 1);
+            const long long pairs = (n_node[nd * 2] + 1) * (n_node[nd * 2 + 1] + 1);
             if (pairs <= GINI2_TABLE_MAX) {
-                G.table_stride = (int)n_node[(b0 + i) * 2 + 1] + 1;
+                G.table_stride = (int)n_node[nd * 2 + 1] + 1;
                 k_gini2_table<<<(unsigned)((pairs + 255) / 256), 256, 0, s->stream>>>(G, d_tables + (size_t)i * GINI2_TABLE_MAX);
                 count_launch(s);
                 G.table = d_tables + (size_t)i * GINI2_TABLE_MAX;
             }
             k_gini2_counts<<<grid_score, 256, 0, s->stream>>>(G, d_segmin + (size_t)i * n_seg_ld);
-            if (occ_table && occ_table[b0 + i] >= 0) {
+            if (occ_table && occ_table[nd] >= 0) {
                 // the reference's tiebreaker on the device: largest occurrence among the ties, then the survivors
-                G.occ = s->occ_tables[occ_table[b0 + i]];
+                G.occ = s->occ_tables[occ_table[nd]];
                 G.occ_max = d_occmax + i;
                 k_gini2_ties_occmax<<<grid_ties, 256, 0, s->stream>>>(G);
                 k_gini2_ties_occ<<<grid_ties, 256, 0, s->stream>>>(G);
@@ -5348,27 +5518,28 @@ extern "C" int kv_gini_level(kv_shard *s, int64_t n_nodes, const uint64_t *class
         }
         CU(cudaMemcpyAsync((void *)h_hdr, d_min, hdr_bytes, cudaMemcpyDeviceToHost, s->stream));
         unsigned int *h_occmax = (unsigned int *)((char *)s->h_pin + count_batch_stride(W) + hdr_bytes);
-        CU(cudaMemcpyAsync(h_occmax, d_occmax, (size_t)per * 4, cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaMemcpyAsync(h_occmax, d_occmax, (size_t)per2 * 4, cudaMemcpyDeviceToHost, s->stream));
         CU(stream_sync_spin(s->stream));
         CU(cudaGetLastError());
         float ms = 0;
         if (s->profiling && cudaEventElapsedTime(&ms, s->ev0, s->ev1) == cudaSuccess) scan_ms += ms;
-        const long long *h_ties = (const long long *)(h_hdr + 2 * per);
+        const long long *h_ties = (const long long *)(h_hdr + 2 * per2);
         size_t batch_total = 0, biggest = 0;
         for (int i = 0; i < nb; ++i) {
-            batch_total += (size_t)h_hdr[per + i];
-            if ((long long)h_hdr[per + i] > kLevelSlotIdx) biggest = std::max(biggest, (size_t)h_hdr[per + i]);
+            batch_total += (size_t)h_hdr[per2 + i];
+            if ((long long)h_hdr[per2 + i] > kLevelSlotIdx) biggest = std::max(biggest, (size_t)h_hdr[per2 + i]);
         }
         KV_TRY(level_arena_reserve(s, s->h_level_used + batch_total));
         if (biggest * 16 > s->d_sort_io.bytes) KV_TRY(ensure(s->d_sort_io, std::max(biggest * 16, s->d_sort_io.bytes * 2)));
         bool pending = false;
         for (int i = 0; i < nb; ++i) {
-            const long long found = (long long)h_hdr[per + i];
-            min_score[b0 + i] = dec_f64_min(h_hdr[i]);
-            n_found[b0 + i] = found;
-            if (occ_max) occ_max[b0 + i] = h_occmax[i];
+            const int nd = node[i];
+            const long long found = (long long)h_hdr[per2 + i];
+            min_score[nd] = dec_f64_min(h_hdr[i]);
+            n_found[nd] = found;
+            if (occ_max) occ_max[nd] = h_occmax[i];
             int64_t *out = s->h_level + s->h_level_used;
-            s->level_span.emplace_back(s->h_level_used, (size_t)found);
+            s->level_span[(size_t)nd] = std::pair<size_t, size_t>(s->h_level_used, (size_t)found);
             s->h_level_used += (size_t)found;
             if (found == 0) continue;
             if (found <= kLevelSlotIdx) {
@@ -5395,6 +5566,19 @@ extern "C" int kv_gini_level(kv_shard *s, int64_t n_nodes, const uint64_t *class
             CU(cudaGetLastError());
         }
     }
+    // the previous level's counts are not needed any more; this level's become the resident generation
+    fam_release_prev(s);
+    slot_guard.keep = true;
+    if (armed)
+        for (int64_t i = 0; i < n_nodes; ++i)
+            if (slot[i] >= 0) {
+                auto it = s->fam_prev.find(key[i]);
+                if (it != s->fam_prev.end()) {                      // a repeated key: the later node wins
+                    s->fam_free.push_back(it->second.slot);
+                    s->fam_prev.erase(it);
+                }
+                s->fam_prev[key[i]] = kv_shard::FamNode{slot[i], {n_node[i * 2], n_node[i * 2 + 1]}};
+            }
     s->last_kernel_ms = scan_ms;
     s->scan_ms_total += scan_ms;
     return KV_OK;

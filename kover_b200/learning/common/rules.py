@@ -10,6 +10,7 @@ kernel over that resident image instead of a loop of h5py chunk reads + Cython p
 Additions the learners of this package use (not in the reference): ``best_utility_rules`` (the
 fused SCM scan, scm.py:238-288) and ``gini_best_split`` (cart.py:112-161, 231-238).
 """
+import itertools
 import os
 
 import numpy as np
@@ -77,6 +78,22 @@ class BaseRuleClassifications(object):
 
     def sum_rows(self, rows):
         raise NotImplementedError()
+
+
+_level_keys = itertools.count(1)
+
+
+class NodeExamples(dict):
+    """class -> example indices of a tree node, tagged for the level search: ``level_key`` names the node,
+    ``parent_key`` the node it was split from (-1: the root).  The children of a split partition their parent's
+    examples (cart.py:300-312), which is what allows parent - sibling (kv_gini_level_family)."""
+
+    def __init__(self, members, parent=None):
+        dict.__init__(self, members)
+        self.level_key = next(_level_keys)
+        self.parent_key = getattr(parent, "level_key", None)
+        if self.parent_key is None:
+            self.parent_key = -1
 
 
 class DeviceOccurrences(object):
@@ -449,7 +466,13 @@ class KmerRuleClassifications(BaseRuleClassifications):
         tables = list(tie_tables) if tie_tables is not None else [None] * len(nodes)
         any_table = any(t is not None for t in tables)
         two_class = all(len(ex) == 2 and list(ex.keys()) == list(nodes[0].keys()) for ex in nodes)
-        on_device = two_class and (len(nodes) > 1 or any_table) and \
+        # nodes that carry a (level_key, parent_key) -- the tree learner's NodeExamples -- let the level search count only
+        # the smaller of two siblings and derive the other one from the parent's resident counts
+        family = None
+        if all(getattr(ex, "level_key", None) is not None for ex in nodes):
+            family = (np.array([ex.level_key for ex in nodes], dtype=np.int64),
+                      np.array([ex.parent_key for ex in nodes], dtype=np.int64))
+        on_device = two_class and (len(nodes) > 1 or any_table or family is not None) and \
             (not any_table or self._group.occurrence_table_supported())
         if not on_device:
             found = [self.gini_best_split(ex, pr, tt, rule_blacklist) for ex, pr, tt in zip(nodes, priors, totals)]
@@ -467,7 +490,7 @@ class KmerRuleClassifications(BaseRuleClassifications):
         total = np.array([[tt[c] for c in classes] for tt in totals], dtype=np.float64)
         n_node = np.array([[len(ex[c]) for c in classes] for ex in nodes], dtype=np.int64)
         occ_ids = np.array([-1 if t is None else t.table for t in tables], dtype=np.int32) if any_table else None
-        return self._group.gini_best_splits(masks, prior, total, n_node, occ_ids)
+        return self._group.gini_best_splits(masks, prior, total, n_node, occ_ids, family=family)
 
     def occurrence_table(self, rows):
         """Occurrence counts of every k-mer in the genomes ``rows`` (= ``sum_rows(rows)[:K]``), kept on the device

@@ -14,6 +14,7 @@ from copy import deepcopy
 
 import numpy as np
 
+from ..common.rules import NodeExamples
 from ..common.tree import ProbabilisticTreeNode
 
 UTIL_BLOCK_SIZE = 1000000
@@ -134,7 +135,9 @@ class DecisionTreeClassifier(object):
                                          criterion_value=node_criterion(counts), class_priors=impurity.priors,
                                          total_n_examples_by_class=impurity.n_total)
 
-        root = new_node(example_idx, 0, counts=impurity.n_total)
+        # (NodeExamples: the dicts carry node / parent keys so that the level search can derive the larger of two
+        #  siblings from their parent's resident counts instead of counting it)
+        root = new_node(NodeExamples(example_idx), 0, counts=impurity.n_total)
         # Breadth first, one level at a time (the reference pops a FIFO queue, cart.py:260-339: same visiting
         # order).  The nodes of a level are independent, so their split searches are issued together and share
         # matrix passes; everything else -- callbacks, tiebreaker calls, child creation -- runs in node order.
@@ -163,8 +166,8 @@ class DecisionTreeClassifier(object):
                     equivalent = np.array(equivalent)  # candidates may be a view of a buffer the next level reuses
                 chosen = equivalent[0]
                 has_kmer = rule_classifications.get_columns(chosen)
-                left = dict((c, members[c][has_kmer[members[c]] == 1]) for c in members.keys())     # rule true
-                right = dict((c, members[c][has_kmer[members[c]] == 0]) for c in members.keys())    # rule false
+                left = NodeExamples(((c, members[c][has_kmer[members[c]] == 1]) for c in members.keys()), members)   # rule true
+                right = NodeExamples(((c, members[c][has_kmer[members[c]] == 0]) for c in members.keys()), members)  # rule false
 
                 node.rule = rules[chosen]
                 node.rule_idx = chosen

@@ -432,22 +432,24 @@ class ShardGroup(object):
         for s in self.shards:
             s.occ_table_set(table, mask)
 
-    def gini_best_splits(self, node_masks, altered_prior, n_total, n_node, occ_tables=None):
+    def gini_best_splits(self, node_masks, altered_prior, n_total, n_node, occ_tables=None, family=None):
         """gini_best_split for several two-class nodes (a tree level): node_masks [n_nodes, 2, W], n_node
         [n_nodes, 2].  Every shard counts the class masks of up to 8 nodes per matrix pass (kv_gini_level); the
         minima are merged over shards / ranks and the tie lists of the shards that hold a node's minimum are
         concatenated in column order.  occ_tables [n_nodes] (local shards only): the reference's occurrence
-        tiebreaker (experiment_cart.py:82-94) is applied on the device, the lists hold its survivors."""
+        tiebreaker (experiment_cart.py:82-94) is applied on the device, the lists hold its survivors.
+        family = (node keys, parent keys) [n_nodes] each: sibling subtraction across levels (kv_gini_level_family)."""
         n_node = np.asarray(n_node, dtype=np.int64)
         altered_prior = np.broadcast_to(np.asarray(altered_prior, dtype=np.float64), n_node.shape)
         n_total = np.broadcast_to(np.asarray(n_total, dtype=np.float64), n_node.shape)
         if not hasattr(self.shards[0], "gini_level"):
             assert occ_tables is None
             return [self.gini_best_split(m, pr, tt, nn) for m, pr, tt, nn in zip(node_masks, altered_prior, n_total, n_node)]
+        fam = {"family": family} if family is not None and hasattr(self.shards[0], "gini_level_family") else {}
         if occ_tables is not None and self.comm is not None:
-            return self._gini_best_splits_ranks_tiebroken(node_masks, altered_prior, n_total, n_node, occ_tables)
+            return self._gini_best_splits_ranks_tiebroken(node_masks, altered_prior, n_total, n_node, occ_tables, fam)
         if occ_tables is not None:
-            per_shard = [s.gini_level(node_masks, altered_prior, n_total, n_node, occ_tables) for s in self.shards]
+            per_shard = [s.gini_level(node_masks, altered_prior, n_total, n_node, occ_tables, **fam) for s in self.shards]
             if self._single:
                 return [(m, idx) for m, idx, _ in per_shard[0]]
             out = []
@@ -470,7 +472,7 @@ class ShardGroup(object):
                         parts.append(np.array(idx)[np.abs(o - float(g)) <= tol])
                 out.append((float(m), np.sort(np.concatenate(parts))))
             return out
-        per_shard = [s.gini_level(node_masks, altered_prior, n_total, n_node) for s in self.shards]
+        per_shard = [s.gini_level(node_masks, altered_prior, n_total, n_node, **fam) for s in self.shards]
         if self._single:
             return per_shard[0]         # (the tie lists are read-only views, valid until the next level search)
         n_nodes = len(per_shard[0])
@@ -495,13 +497,13 @@ class ShardGroup(object):
             out.append((float(mins[i]), np.sort(np.concatenate(parts))))
         return out
 
-    def _gini_best_splits_ranks_tiebroken(self, node_masks, altered_prior, n_total, n_node, occ_tables):
+    def _gini_best_splits_ranks_tiebroken(self, node_masks, altered_prior, n_total, n_node, occ_tables, fam={}):
         """One process per GPU, occurrence tiebreaker on the device: every rank reports, per node, its minimum, the
         largest occurrence among ITS ties and the ties that survive relative to that; two small reductions find the
         global minimum and the global largest occurrence, the ranks whose survivors stand send them in one exchange
         for the whole level -- the millions of ties of small nodes never cross NVLink."""
         shard = self.shards[0]
-        res = shard.gini_level(node_masks, altered_prior, n_total, n_node, occ_tables)
+        res = shard.gini_level(node_masks, altered_prior, n_total, n_node, occ_tables, **fam)
         n_nodes = len(res)
         local_min = np.array([r[0] for r in res], dtype=np.float64)
         mins = self.comm.allreduce_min(local_min)

@@ -738,6 +738,78 @@ def test_level_search_matches_per_node_search(devices, sorted_labels):
     rc.close()
 
 
+@pytest.mark.parametrize("devices", [[0], [0, 0, 0]], ids=["1shard", "3shards"])
+@pytest.mark.parametrize("slots", [None, "3", "0"], ids=["arena", "3slots", "off"])
+def test_level_sibling_subtraction(devices, slots, monkeypatch):
+    """kv_gini_level_family: of two sibling nodes only the smaller is counted in the matrix pass, the other one's class
+    counts are parent - sibling.  Three levels of a hand-made family (a root, its two children, grandchildren incl. a
+    lone child, a pair whose sizes do not add up to the parent's, an unrelated node) searched armed == the same nodes
+    searched unarmed, with blacklist and the device tiebreaker; the number of derived nodes is what the arena allows."""
+    from kover_b200.learning.common.rules import NodeExamples
+    from kover_b200.learning.experiments import experiment_cart as cexp
+    if slots == "0":
+        monkeypatch.setenv("KOVER_B200_LEVEL_SUB", "0")
+    elif slots is not None:
+        monkeypatch.setenv("KOVER_B200_LEVEL_POOL_SLOTS", slots)
+    seed, n, k = 31, 1100, 70000
+    P = synthetic_block(seed, n, 0, k)
+    y = synthetic_labels(seed, n, sorted_by_label=False)
+    rs = np.random.RandomState(seed)
+    rc = KmerRuleClassifications(P, n, devices=devices)
+    train = np.sort(rs.choice(n, size=900, replace=False))
+    tb = cexp.OccurrenceTiebreaker(rc, train)
+    n_total = {0: float((y[train] == 0).sum()), 1: float((y[train] == 1).sum())}
+    priors = {0: 0.45, 1: 0.55}
+    bl = rs.choice(k, size=200, replace=False)
+
+    def node(members, parent=None):
+        members = np.sort(members)
+        return NodeExamples({0: members[y[members] == 0], 1: members[y[members] == 1]}, parent)
+
+    def split(ex, frac):
+        members = np.concatenate([ex[0], ex[1]])
+        take = rs.rand(len(members)) < frac
+        return node(members[take], ex), node(members[~take], ex)
+
+    root = node(train)
+    a, b = split(root, 0.3)
+    a1, a2 = split(a, 0.5)
+    b1, b2 = split(b, 0.9)
+    stranger = node(rs.choice(train, size=50, replace=False))
+    c1, c2 = split(a1, 0.4)
+    d1, d2 = split(b1, 0.02)                            # a tiny node next to a large one
+    wrong1, wrong2 = split(b2, 0.5)
+    wrong2 = node(np.concatenate([wrong2[0], wrong2[1]])[:-3], b2)       # sizes no longer add up: both are counted
+    levels = [[root], [a, b], [a1, a2, b1, stranger, b2], [c1, c2, d2, d1, wrong1, wrong2, node(np.concatenate([a2[0], a2[1]])[::2], a2)]]
+    tables = tb.device_occurrences
+    derived0 = [s_.info().level_nodes_derived for s_ in rc._group.shards]
+    for use_table in (False, True):
+        for lv in levels:
+            assert all(len(ex[0]) and len(ex[1]) for ex in lv)
+            kw = dict(tie_tables=[tables] * len(lv)) if use_table else {}
+            got = [(m, np.array(c)) for m, c in rc.gini_best_splits(lv, priors, n_total, rule_blacklist=bl, **kw)]
+            plain = [dict(ex) for ex in lv]             # the same nodes without keys: every node counted
+            want = rc.gini_best_splits(plain, priors, n_total, rule_blacklist=bl, **kw)
+            if len(lv) == 1 and not use_table:
+                want = [rc.gini_best_split(plain[0], priors, n_total, rule_blacklist=bl)]
+            for (gm, gc), (wm, wc) in zip(got, want):
+                assert gm == wm and np.array_equal(gc, np.asarray(wc))
+            # (the unarmed search ended the family: arm this level again so that the next one finds its parents)
+            rc.gini_best_splits(lv, priors, n_total, rule_blacklist=bl, **kw)
+    derived = [s_.info().level_nodes_derived - d0 for s_, d0 in zip(rc._group.shards, derived0)]
+    # per sweep: level 1 -> (a, b); level 2 -> (a1, a2), b1 + b2 straddle the stranger; level 3 -> (c1, c2), (d1, d2)
+    # (only the first, compared search of a level finds its parents resident: the unarmed one in between ends the family)
+    full = 2 * (1 + 2 + 2)
+    if slots is None:
+        assert derived == [full] * len(devices), derived
+    elif slots == "0":
+        assert derived == [0] * len(devices)
+    else:
+        assert all(0 < d < full for d in derived), derived
+    tb.release()
+    rc.close()
+
+
 @pytest.mark.parametrize("seed", range(12))
 def test_randomized_trees_vs_checker(seed):
     """Whole trees on random small / ragged shapes: level-batched split search + occurrence tiebreaker on the device,
