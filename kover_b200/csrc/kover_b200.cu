@@ -1723,6 +1723,7 @@ struct GiniParams {
     // two classes, small node: score of every (count 0, count 1) pair, [n_node0 + 1][table_stride], or null
     const double *table;
     int table_stride;
+    int table_global;               // the table is too large for shared memory: looked up where it is (L2-resident)
     // occurrence tiebreak on the device (experiment_cart.py:82-94): k-mer occurrence counts of the tree's training
     // set, and the maximum occurrence among the node's ties
     const uint32_t *occ;
@@ -1824,10 +1825,13 @@ __global__ void __launch_bounds__(256) k_gini(const GiniParams P) {
 // per column -- is then tabulated once per node (k_gini2_table) and looked up.  Same values bit for bit: the table
 // entries are computed by the same gini_score arithmetic.
 static constexpr int GINI2_TABLE_MAX = 4096;
+// Larger nodes: the table stays in device memory (a few MB, L2-resident) as long as tabulating is cheaper than scoring
+// every column -- at most GINI2_GTABLE_MAX pairs and at most half as many pairs as columns.
+static constexpr long long GINI2_GTABLE_MAX = 4ll << 20;
 
 __global__ void __launch_bounds__(256) k_gini2_table(const GiniParams P, double *table) {
-    const int n0 = (int)P.n_node[0] + 1, stride = P.table_stride;
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n0 * stride; e += gridDim.x * blockDim.x) {
+    const long long n0 = (long long)P.n_node[0] + 1, stride = P.table_stride;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n0 * stride; e += (long long)gridDim.x * blockDim.x) {
         const double l[2] = {(double)(e / stride), (double)(e % stride)};
         const double r[2] = {P.n_node[0] - l[0], P.n_node[1] - l[1]};
         double v = INFINITY;                                           // cart.py:158-159
@@ -1837,7 +1841,7 @@ __global__ void __launch_bounds__(256) k_gini2_table(const GiniParams P, double 
 }
 
 __device__ __forceinline__ void gini2_table_load(const GiniParams &P, double *s_tab) {
-    if (P.table) {
+    if (P.table && !P.table_global) {
         const int n = ((int)P.n_node[0] + 1) * P.table_stride;
         for (int e = threadIdx.x; e < n; e += blockDim.x) s_tab[e] = P.table[e];
         __syncthreads();
@@ -1847,7 +1851,22 @@ __device__ __forceinline__ void gini2_table_load(const GiniParams &P, double *s_
 __device__ __forceinline__ double gini2_score_any(long long col, const GiniParams &P, const double *s_tab) {
     if (!P.table) return gini_score<2>(col, P);
     if (P.black_pres && ((P.black_pres[col >> 5] >> (col & 31)) & 1u)) return INFINITY;   // cart.py:231
-    return s_tab[P.cnt[0][col] * (uint32_t)P.table_stride + P.cnt[1][col]];
+    const uint32_t e = P.cnt[0][col] * (uint32_t)P.table_stride + P.cnt[1][col];
+    return P.table_global ? __ldg(P.table + e) : s_tab[e];
+}
+
+// the same score from counts already in registers (lets the callers issue the loads of several columns up front)
+__device__ __forceinline__ double gini2_score_cnt(uint32_t c0, uint32_t c1, bool blacklisted, const GiniParams &P,
+                                                  const double *s_tab) {
+    if (blacklisted) return INFINITY;                                                      // cart.py:231
+    if (P.table) {
+        const uint32_t e = c0 * (uint32_t)P.table_stride + c1;
+        return P.table_global ? __ldg(P.table + e) : s_tab[e];
+    }
+    const double l[2] = {(double)c0, (double)c1};
+    const double r[2] = {P.n_node[0] - l[0], P.n_node[1] - l[1]};
+    if (l[0] + l[1] == 0.0 || r[0] + r[1] == 0.0) return INFINITY;                         // cart.py:158-159
+    return __dadd_rn(gini_child<2>(l, P, 2), gini_child<2>(r, P, 2));
 }
 
 // Tie collection when the scan left exact per-segment minima: one lane screens one 64-column segment
@@ -1857,9 +1876,8 @@ __device__ __forceinline__ double gini2_score_any(long long col, const GiniParam
 // numpy.isclose(o, o.max()): |o - max| <= 1e-8 + 1e-5 * |max|) -- pass 1 finds the maximum, pass 2 emits the survivors.
 // A node with few examples ties on millions of k-mers, of which the tiebreaker keeps a handful: filtering here
 // removes their sort and their trip to the host.
-template <int OCC>
-__device__ __forceinline__ void gini2_ties_body(const GiniParams &P, double *s_tab) {
-    gini2_table_load(P, s_tab);
+template <int OCC, int NSEG>
+__device__ __forceinline__ void gini2_ties_walk(const GiniParams &P, const double *s_tab) {
     double target = P.min_score;
     if (P.min_ptr) {
         const unsigned long long v = *reinterpret_cast<const unsigned long long *>(P.min_ptr);
@@ -1884,29 +1902,62 @@ __device__ __forceinline__ void gini2_ties_body(const GiniParams &P, double *s_t
             cand = v != ~0ull && dec_f64_max_dev(v) == target;
         }
         unsigned todo = __ballot_sync(0xffffffffu, cand);
+        // NSEG candidate segments (2 NSEG columns per lane) at a time, every load issued before the first use: a node with
+        // few examples ties on most of the k-mers and this loop then walks nearly every segment
         while (todo) {
-            const int src = __ffs(todo) - 1;
-            todo &= todo - 1;
+            constexpr int NE = 2 * NSEG;
+            long long col[NE];
+            uint32_t c0[NE], c1[NE], oc[NE], bw[NE];
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const long long col = ((sb + src) << 6) + lane + 32 * j;
-                if (col >= P.n_cols) continue;
-                bool hit = gini2_score_any(col, P, s_tab) == target;
+            for (int q = 0; q < NSEG; ++q) {
+                const int src = todo ? __ffs(todo) - 1 : -1;
+                todo &= todo - 1;                       // (0 & anything stays 0)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const long long c = ((sb + src) << 6) + lane + 32 * j;
+                    col[q * 2 + j] = (src >= 0 && c < P.n_cols) ? c : -1;
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < NE; ++e) {
+                const bool v = col[e] >= 0;
+                c0[e] = v ? P.cnt[0][col[e]] : 0u;
+                c1[e] = v ? P.cnt[1][col[e]] : 0u;
+                bw[e] = (v && P.black_pres) ? P.black_pres[col[e] >> 5] : 0u;
+                oc[e] = (OCC != 0 && v) ? P.occ[col[e]] : 0u;
+            }
+            unsigned mine = 0;                          // bit e: column e of this lane is a tie (that survives)
+#pragma unroll
+            for (int e = 0; e < NE; ++e) {
+                if (col[e] < 0) continue;
+                bool hit = gini2_score_cnt(c0[e], c1[e], (bw[e] >> (col[e] & 31)) & 1u, P, s_tab) == target;
                 if (OCC == 1) {
-                    if (hit) occ_run = max(occ_run, P.occ[col]);
+                    if (hit) occ_run = max(occ_run, oc[e]);
                     continue;
                 }
-                if (OCC == 2 && hit) hit = fabs(__dsub_rn((double)P.occ[col], occ_best)) <= occ_tol;
-                // one atomic per warp: a node with few examples can tie on most of the k-mers
-                const unsigned hits = __ballot_sync(__activemask(), hit);
-                if (hit) {
-                    const int leader = __ffs(hits) - 1;
-                    unsigned long long base = 0;
-                    if (lane == leader) base = atomicAdd(P.counter, (unsigned long long)__popc(hits));
-                    base = __shfl_sync(hits, base, leader);
-                    const unsigned long long slot = base + __popc(hits & ((1u << lane) - 1u));
-                    if ((long long)slot < P.cap) P.out_idx[slot] = P.col0 + col;
-                }
+                if (OCC == 2 && hit) hit = fabs(__dsub_rn((double)oc[e], occ_best)) <= occ_tol;
+                if (hit) mine |= 1u << e;
+            }
+            if (OCC == 1) continue;
+            // one atomic per warp and group
+            const unsigned n_mine = __popc(mine);
+            unsigned incl = n_mine;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned t = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += t;
+            }
+            const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+            if (total) {
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(P.counter, (unsigned long long)total);
+                base = __shfl_sync(0xffffffffu, base, 0) + (incl - n_mine);
+#pragma unroll
+                for (int e = 0; e < NE; ++e)
+                    if ((mine >> e) & 1u) {
+                        if ((long long)base < P.cap) P.out_idx[base] = P.col0 + col[e];
+                        ++base;
+                    }
             }
         }
     }
@@ -1914,6 +1965,15 @@ __device__ __forceinline__ void gini2_ties_body(const GiniParams &P, double *s_t
         occ_run = __reduce_max_sync(0xffffffffu, occ_run);
         if (lane == 0 && occ_run) atomicMax(P.occ_max, occ_run);
     }
+}
+
+// small nodes (score table; they are the ones that tie on millions of k-mers): four segments per step; large nodes score
+// with eight IEEE divisions per column and tie on few: one segment per step keeps the code small
+template <int OCC>
+__device__ __forceinline__ void gini2_ties_body(const GiniParams &P, double *s_tab) {
+    gini2_table_load(P, s_tab);
+    if (P.table) gini2_ties_walk<OCC, 4>(P, s_tab);
+    else gini2_ties_walk<OCC, 1>(P, s_tab);
 }
 
 __global__ void __launch_bounds__(256) k_gini2_ties_seg(const GiniParams P) {
@@ -1938,19 +1998,40 @@ __global__ void __launch_bounds__(256) k_gini2_counts(const GiniParams P, unsign
     gini2_table_load(P, s_tab);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long n_seg = (P.n_cols + 63) >> 6;
+    const long long n_span = (P.n_cols + 255) >> 8;                    // 256 columns = 4 segments per warp and iteration
     const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
     double mn = INFINITY;
-    for (long long g = warp0; g < n_seg; g += n_warps) {
-        double sm = INFINITY;
+    // lane l: columns 4l .. 4l+3 of the span's first and second half (two 128-bit loads per count array, all four issued
+    // before the first score: the kernel used to be bound by the latency of one dependent load chain per segment); the
+    // count arrays are [ld] long, ld a multiple of 1024, so the vector loads stay inside them
+    for (long long sp = warp0; sp < n_span; sp += n_warps) {
+        const long long cbase[2] = {(sp << 8) + 4 * lane, (sp << 8) + 128 + 4 * lane};
+        uint4 a[2], b[2];
+        uint32_t bl[2];
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const long long col = (g << 6) + lane + 32 * j;
-            if (col < P.n_cols) sm = fmin(sm, gini2_score_any(col, P, s_tab));
+        for (int h = 0; h < 2; ++h) {
+            a[h] = *reinterpret_cast<const uint4 *>(P.cnt[0] + cbase[h]);
+            b[h] = *reinterpret_cast<const uint4 *>(P.cnt[1] + cbase[h]);
+            bl[h] = P.black_pres ? (P.black_pres[cbase[h] >> 5] >> (cbase[h] & 31)) & 15u : 0u;
         }
-        const unsigned long long seg = warp_min_enc(enc_f64(sm));
-        if (lane == 0) segmin_out[g] = seg;
-        mn = fmin(mn, sm);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const uint32_t c0[4] = {a[h].x, a[h].y, a[h].z, a[h].w}, c1[4] = {b[h].x, b[h].y, b[h].z, b[h].w};
+            double sm = INFINITY;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (cbase[h] + q < P.n_cols) sm = fmin(sm, gini2_score_cnt(c0[q], c1[q], (bl[h] >> q) & 1u, P, s_tab));
+            mn = fmin(mn, sm);
+            unsigned long long seg = enc_f64(sm);                          // minimum of the 16 lanes that share a segment
+#pragma unroll
+            for (int d = 8; d >= 1; d >>= 1) {
+                const unsigned long long o = __shfl_xor_sync(0xffffffffu, seg, d);
+                seg = o < seg ? o : seg;
+            }
+            const long long g = (sp << 2) + 2 * h + (lane >> 4);
+            if ((lane & 15) == 0 && g < n_seg) segmin_out[g] = seg;
+        }
     }
     const unsigned long long v = warp_min_enc(enc_f64(mn));
     if (lane == 0) s_red[warp] = v;
@@ -2329,6 +2410,7 @@ struct kv_shard {
     cudaEvent_t inf_pin_free[4] = {nullptr, nullptr, nullptr, nullptr};
     size_t inf_slot_bytes = 0;
     double up_setup_ms = 0.0, up_gather_ms = 0.0, up_total_ms = 0.0;   // phases of the last kv_upload_deflate (host clock)
+    DevBuf d_gtables;                         // kv_gini_level: score tables of nodes too large for shared memory
     DevBuf d_level;                           // kv_gini_level: per-node minima, counters, tie slots, segment minima
     std::vector<uint32_t *> occ_tables;       // kv_occ_table_set: k-mer occurrence counts of a training set, [ld] each
     // kv_gini_level_family: the class counts of the previous tree level's nodes stay resident (slots of one arena) so
@@ -2463,7 +2545,7 @@ extern "C" int kv_destroy(kv_shard *s) {
     for (auto p : s->occ_tables)
         if (p) cudaFree(p);
     if (s->d_fam_arena) cudaFree(s->d_fam_arena);
-    for (DevBuf *b : {&s->d_rec, &s->d_misc, &s->d_ties, &s->d_stage, &s->d_sort_tmp, &s->d_sort_io, &s->d_queue, &s->d_level, &s->d_qmisc, &s->d_qseg})
+    for (DevBuf *b : {&s->d_rec, &s->d_misc, &s->d_ties, &s->d_stage, &s->d_sort_tmp, &s->d_sort_io, &s->d_queue, &s->d_level, &s->d_gtables, &s->d_qmisc, &s->d_qseg})
         if (b->p) cudaFree(b->p);
     if (s->d_black_pres) cudaFree(s->d_black_pres);
     if (s->d_black_abs) cudaFree(s->d_black_abs);
@@ -5433,6 +5515,8 @@ extern "C" int kv_gini_level(kv_shard *s, int64_t n_nodes, const uint64_t *class
     const long long n_seg = (s->n_cols + 63) / 64;
     const unsigned grid_score = (unsigned)std::max<long long>(1, std::min<long long>((n_seg + 7) / 8, (long long)s->sm_count * 8));
     const unsigned grid_ties = (unsigned)std::max<long long>(1, std::min<long long>((n_seg + 255) / 256, (long long)s->sm_count * 4));
+    long long gtable_max = std::min<long long>(GINI2_GTABLE_MAX, s->n_cols / 2);
+    if (const char *v = getenv("KOVER_B200_GINI_GTABLE")) gtable_max = std::min<long long>(gtable_max, atoll(v));
     const unsigned grid_sub = (unsigned)std::max<long long>(1, std::min<long long>((s->ld / 4 + 255) / 256, (long long)s->sm_count * 8));
     float scan_ms = 0;
     for (size_t b0 = 0; b0 < counted.size(); b0 += (size_t)per) {
@@ -5502,6 +5586,15 @@ extern "C" int kv_gini_level(kv_shard *s, int64_t n_nodes, const uint64_t *class
                 k_gini2_table<<<(unsigned)((pairs + 255) / 256), 256, 0, s->stream>>>(G, d_tables + (size_t)i * GINI2_TABLE_MAX);
                 count_launch(s);
                 G.table = d_tables + (size_t)i * GINI2_TABLE_MAX;
+            } else if (pairs <= gtable_max) {
+                if (!s->d_gtables.p || s->d_gtables.bytes < (size_t)per2 * gtable_max * 8)
+                    KV_TRY(ensure(s->d_gtables, (size_t)per2 * gtable_max * 8));
+                double *gt = (double *)s->d_gtables.p + (size_t)i * gtable_max;
+                G.table_stride = (int)n_node[nd * 2 + 1] + 1;
+                k_gini2_table<<<(unsigned)std::min<long long>((pairs + 255) / 256, (long long)s->sm_count * 16), 256, 0, s->stream>>>(G, gt);
+                count_launch(s);
+                G.table = gt;
+                G.table_global = 1;
             }
             k_gini2_counts<<<grid_score, 256, 0, s->stream>>>(G, d_segmin + (size_t)i * n_seg_ld);
             if (occ_table && occ_table[nd] >= 0) {

@@ -157,7 +157,15 @@ class DecisionTreeClassifier(object):
             if splittable:
                 found = yield ([node.class_examples_idx for node in splittable], impurity, rule_blacklist, tie_table)
             next_level = []
-            for node, (best_score, candidates) in zip(splittable, found):
+            # with the tiebreaker already applied by the search, the chosen rules of the whole level are known here:
+            # their columns come back in ONE get_columns call (one gather kernel / one exchange instead of one per node)
+            fetched = {}
+            if tie_table is not None:
+                picks = [(j, cand[0]) for j, (score, cand) in enumerate(found) if score != np.inf]
+                if len(picks) > 1:
+                    columns = rule_classifications.get_columns([c for _, c in picks])
+                    fetched = dict((j, columns[:, t]) for t, (j, _) in enumerate(picks))
+            for j, (node, (best_score, candidates)) in enumerate(zip(splittable, found)):
                 if best_score == np.inf:
                     continue                           # no rule separates the node into two non-empty children
                 members = node.class_examples_idx
@@ -165,7 +173,7 @@ class DecisionTreeClassifier(object):
                 if np.may_share_memory(equivalent, candidates):
                     equivalent = np.array(equivalent)  # candidates may be a view of a buffer the next level reuses
                 chosen = equivalent[0]
-                has_kmer = rule_classifications.get_columns(chosen)
+                has_kmer = fetched[j] if j in fetched else rule_classifications.get_columns(chosen)
                 left = NodeExamples(((c, members[c][has_kmer[members[c]] == 1]) for c in members.keys()), members)   # rule true
                 right = NodeExamples(((c, members[c][has_kmer[members[c]] == 0]) for c in members.keys()), members)  # rule false
 

@@ -53,7 +53,8 @@ import cProfile
 import pstats
 res = {}
 DecisionTreeClassifier("gini", 4, 2, {0: 1.0, 1: 1.0}).fit(rules, rc, ex, tiebreaker=tiebreaker)     # warm-up: allocations
-for mode in (("level",) if "--level-only" in sys.argv else ("level+device tiebreak", "level", "per-node")):
+for mode in (("level",) if "--level-only" in sys.argv else ("level+device tiebreak",) if "--device-only" in sys.argv
+             else ("level+device tiebreak", "level", "per-node")):
     if mode == "per-node":
         rc.gini_best_splits = lambda nodes, pri, tot, bl=(): [rc.gini_best_split(e, pri, tot, bl) for e in nodes]
     t = DecisionTreeClassifier("gini", depth, 2, {0: 1.0, 1: 1.0})
