@@ -1402,6 +1402,10 @@ struct RescoreMultiParams {
     double p[QUEUE_BATCH];
     double n_pos[QUEUE_BATCH], n_neg[QUEUE_BATCH];
     unsigned long long *blockmax[QUEUE_BATCH], *segmax[QUEUE_BATCH];
+    // every job of the launch counts its examples over the same mask pair (|first mask| = dn_a, |second| = dn_b; the
+    // swapped jobs with exchanged roles): the p-independent halves of the utilities are then formed once per column
+    int hoist;
+    double dn_a, dn_b;
 };
 
 // 2 048 columns per CTA: every warp owns 256 consecutive columns, every lane eight of them (two 128-bit loads per
@@ -1475,7 +1479,48 @@ __device__ __forceinline__ void rescore_job(const RescoreMultiParams &P, int j, 
     rescore_half<1>(P, j, L, ua, s_red);
 }
 
-__global__ void __launch_bounds__(256) k_scm_rescore_multi(const __grid_constant__ RescoreMultiParams P) {
+// The same with the p-independent terms hoisted out of the job loop: A = |negatives| - cn (negatives the presence rule
+// covers), B = |positives| - cp (positives it errs on); plain jobs: presence A - p B, absence cn - p cp; swapped jobs
+// (roles of the two masks exchanged): presence B - p A, absence cp - p cn.  Bit-identical to rescore_job: the same
+// rounded operations on the same operands, only formed once.  DEAD (warp-uniform): some lane holds a padding column or
+// a blacklisted rule.
+template <bool DEAD>
+__device__ __forceinline__ void rescore_job_hoisted(const RescoreMultiParams &P, int j, const RescoreLane &L,
+                                                    const double (&a)[8], const double (&b)[8], const double (&cn)[8],
+                                                    const double (&cp)[8], unsigned long long (*s_red)[2][8]) {
+    const double p = P.p[j];
+    double up[8], ua[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        up[q] = __dsub_rn(a[q], __dmul_rn(p, b[q]));
+        ua[q] = __dsub_rn(cn[q], __dmul_rn(p, cp[q]));
+    }
+    if (DEAD) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            if ((L.dead_p >> q) & 1u) up[q] = -INFINITY;
+            if ((L.dead_a >> q) & 1u) ua[q] = -INFINITY;
+        }
+    }
+    rescore_half<0>(P, j, L, up, s_red);
+    rescore_half<1>(P, j, L, ua, s_red);
+}
+
+template <bool DEAD>
+__device__ __forceinline__ void rescore_jobs_hoisted(const RescoreMultiParams &P, const RescoreLane &L,
+                                                     unsigned long long (*s_red)[2][8]) {
+    double a[8], b[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        a[q] = __dsub_rn(P.dn_b, L.cn[q]);
+        b[q] = __dsub_rn(P.dn_a, L.cp[q]);
+    }
+    for (int j = 0; j < P.n_plain; ++j) rescore_job_hoisted<DEAD>(P, j, L, a, b, L.cn, L.cp, s_red);
+    for (int j = P.n_plain; j < P.n_jobs; ++j) rescore_job_hoisted<DEAD>(P, j, L, b, a, L.cp, L.cn, s_red);
+}
+
+template <bool HOIST>
+__global__ void __launch_bounds__(256, 2) k_scm_rescore_multi(const __grid_constant__ RescoreMultiParams P) {
     __shared__ unsigned long long s_red[QUEUE_BATCH][2][8];
     RescoreLane L;
     L.lane = threadIdx.x & 31;
@@ -1516,14 +1561,19 @@ __global__ void __launch_bounds__(256) k_scm_rescore_multi(const __grid_constant
         L.dead_p |= (bp | pad) << (4 * g);
         L.dead_a |= (ba | pad) << (4 * g);
     }
-    for (int j = 0; j < P.n_plain; ++j) rescore_job(P, j, L, s_red);
+    if (HOIST) {
+        if (__any_sync(0xffffffffu, (L.dead_p | L.dead_a) != 0u)) rescore_jobs_hoisted<true>(P, L, s_red);
+        else rescore_jobs_hoisted<false>(P, L, s_red);
+    } else {
+        for (int j = 0; j < P.n_plain; ++j) rescore_job(P, j, L, s_red);
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {                               // swapped jobs: the two count arrays exchange roles
-        const double t = L.cp[q];
-        L.cp[q] = L.cn[q];
-        L.cn[q] = t;
+        for (int q = 0; q < 8; ++q) {                           // swapped jobs: the two count arrays exchange roles
+            const double t = L.cp[q];
+            L.cp[q] = L.cn[q];
+            L.cn[q] = t;
+        }
+        for (int j = P.n_plain; j < P.n_jobs; ++j) rescore_job(P, j, L, s_red);
     }
-    for (int j = P.n_plain; j < P.n_jobs; ++j) rescore_job(P, j, L, s_red);
     __syncthreads();
     if (threadIdx.x < 2 * P.n_jobs) {
         const int j = threadIdx.x >> 1, h = threadIdx.x & 1;
@@ -4611,7 +4661,20 @@ static int queue_score_group(kv_shard *s, const uint32_t *cnt_a, const uint32_t 
                 t.cap = packet_capacity;
             }
         }
-        k_scm_rescore_multi<<<(unsigned)((s->ld + 2047) / 2048), 256, 0, s->stream>>>(R);
+        {   // one mask pair behind all the jobs?  (always, for the queue's own grouping; checked because the sizes are the caller's)
+            const bool first_plain = R.n_plain > 0;
+            R.dn_a = first_plain ? R.n_pos[0] : R.n_neg[0];
+            R.dn_b = first_plain ? R.n_neg[0] : R.n_pos[0];
+            R.hoist = 1;
+            for (int i = 0; i < nb; ++i) {
+                const bool plain = i < R.n_plain;
+                if ((plain ? R.n_pos[i] : R.n_neg[i]) != R.dn_a || (plain ? R.n_neg[i] : R.n_pos[i]) != R.dn_b) R.hoist = 0;
+            }
+            if (const char *v = getenv("KOVER_B200_RESCORE_HOIST")) R.hoist = R.hoist && atoi(v) != 0;
+        }
+        const unsigned grid_rescore = (unsigned)((s->ld + 2047) / 2048);
+        if (R.hoist) k_scm_rescore_multi<true><<<grid_rescore, 256, 0, s->stream>>>(R);
+        else k_scm_rescore_multi<false><<<grid_rescore, 256, 0, s->stream>>>(R);
         if (d_packets) k_scm_select_local_multi<<<nb, 32, 0, s->stream>>>(SL);
         else k_scm_select_multi<<<nb, 32, 0, s->stream>>>(S);
         k_scm_ties_multi<<<dim3(grid_ties, nb), 256, 0, s->stream>>>(T);

@@ -157,6 +157,48 @@ def test_kmer_risk_tables(world):
             assert w.dtype == g.dtype and np.array_equal(w, g)
 
 
+def test_whole_tree_with_sibling_subtraction(world):
+    """A whole Gini tree (depth 6, occurrence tiebreaker on the device, blacklist) grown level by level with the counts
+    of every larger sibling derived as parent - smaller sibling (kv_gini_level_family) == the checker's tree, one node
+    at a time with the host tiebreaker; 1 and 3 shards."""
+    if world.n > 20000:
+        pytest.skip("the checker's tree takes minutes at this size; W = 79 and 313 cover the path")
+    from kover_b200.learning.common.rules import LazyKmerRuleList
+    from kover_b200.learning.experiments.experiment_cart import OccurrenceTiebreaker
+    from kover_b200.learning.learners.cart import DecisionTreeClassifier
+    pos, neg = world.sets["interleaved"]
+    ex = {0: neg, 1: pos}
+    train = np.sort(np.concatenate([pos, neg]))
+    rs = np.random.RandomState(world.seed)
+    blacklist = np.unique(rs.randint(0, world.k, size=500))
+    occ = world.orc.sum_rows(train)
+    imp = {0: 1.0, 1: 1.5}
+    want = ko.cart_fit(world.orc, ex, "gini", 6, 2, imp, rule_blacklist=list(blacklist),
+                       tiebreaker=lambda idx: ko.cart_tiebreaker(idx, occ))
+    rules = LazyKmerRuleList(np.arange(world.k), np.arange(world.k))
+
+    def same(a, b):
+        assert (a.rule is None) == b.is_leaf
+        assert [len(v) for v in a.class_examples_idx.values()] == [len(v) for v in b.class_examples_idx.values()]
+        if a.rule is not None:
+            assert int(a.rule_idx) == int(b.rule_idx) and float(a.criterion_value) == float(b.criterion_value)
+            assert np.array_equal(np.asarray(a.equivalent_rules_idx), np.asarray(b.equivalent_rules_idx))
+            same(a.left_child, b.left_child)
+            same(a.right_child, b.right_child)
+
+    for n_shards in (1, 3):
+        rc = world.rc(n_shards)
+        derived0 = [s_.info().level_nodes_derived for s_ in rc._group.shards]
+        tb = OccurrenceTiebreaker(rc, train)
+        try:
+            t = DecisionTreeClassifier("gini", 6, 2, imp)
+            t.fit(rules, rc, ex, rule_blacklist=list(blacklist), tiebreaker=tb)
+        finally:
+            tb.release()
+        same(t.decision_tree, want)
+        assert all(s_.info().level_nodes_derived - d0 >= 5 for s_, d0 in zip(rc._group.shards, derived0))
+
+
 # ------------------------------------------------------------------------------------------------ beyond the staging limits
 def _check_all_paths(n, k, seed, rc, orc):
     y = synthetic_labels(seed, n, sorted_by_label=False)
