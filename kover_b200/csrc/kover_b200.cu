@@ -233,6 +233,7 @@ struct Scan2Params {
     int n_act;
     int inline_rec;                   // 1: the records travel in the kernel parameters (n_act <= SCAN_INLINE_ROWS)
     int l2_hints;                     // bit 0: evict-first matrix loads, bit 1: evict-last count stores
+    int csa;                          // carry-save popcounts over groups of four rows (KOVER_B200_SCAN_CSA, default on)
     uint64_t inl_m0[SCAN_INLINE_ROWS], inl_m1[SCAN_INLINE_ROWS];
     uint32_t inl_row[SCAN_INLINE_ROWS];
     uint32_t *cnt0, *cnt1;            // [ld] each; cnt1 may be null (single-mask scan)
@@ -373,6 +374,59 @@ __device__ __forceinline__ void runmax_flush(RunMax &r, unsigned long long *bloc
     }
 }
 
+// 3:2 carry-save compressor on 32 bit lanes: a + b + d = s + 2 c, two LOP3
+__device__ __forceinline__ void csa32(uint32_t &s, uint32_t &c, uint32_t a, uint32_t b, uint32_t d) {
+    s = a ^ b ^ d;
+    c = (a & b) | (d & (a ^ b));
+}
+// popcount(a) + popcount(b) + popcount(c) + popcount(d) of four (already masked) 64-bit words with 4 POPC instead
+// of 8: the eight 32-bit halves go through four carry-save compressors (8 LOP3 on the ALU pipe, which idles
+// while the 16-lane POPC pipe is the bottleneck), leaving two words of weight 1, one of weight 2, one of weight 4.
+__device__ __forceinline__ uint32_t popc4x64_csa(uint64_t a, uint64_t b, uint64_t c, uint64_t d) {
+    uint32_t s1, c1, s2, c2, s3, c3, s4, c4;
+    csa32(s1, c1, (uint32_t)a, (uint32_t)(a >> 32), (uint32_t)b);
+    csa32(s2, c2, (uint32_t)(b >> 32), (uint32_t)c, (uint32_t)(c >> 32));
+    csa32(s3, c3, s1, s2, (uint32_t)d);
+    csa32(s4, c4, c1, c2, c3);
+    return (__popc(s3) + __popc((uint32_t)(d >> 32))) + 2 * (__popc(s4) + 2 * __popc(c4));
+}
+
+// Four rows of a ring stage at once.  Whenever a mask is non-zero on all four rows (warp-uniform: the mask words are per
+// row) its four masked words per column go through the carry-save compressors: with interleaved labels both masks touch
+// every packed row, 4 POPC per streamed word, and the 16-lane POPC pipe -- not HBM -- bounded the scan (72 % busy at
+// 6.0 TB/s); the compressors move half of that work to the idle ALU pipe.
+__device__ __forceinline__ void accum_rows4(const unsigned char *p, int row_bytes, const uint64_t *m0, const uint64_t *m1,
+                                            uint32_t &c0x, uint32_t &c0y, uint32_t &c1x, uint32_t &c1y) {
+    const ulonglong2 v0 = *reinterpret_cast<const ulonglong2 *>(p);
+    const ulonglong2 v1 = *reinterpret_cast<const ulonglong2 *>(p + row_bytes);
+    const ulonglong2 v2 = *reinterpret_cast<const ulonglong2 *>(p + 2 * row_bytes);
+    const ulonglong2 v3 = *reinterpret_cast<const ulonglong2 *>(p + 3 * row_bytes);
+    {
+        const uint64_t a0 = m0[0], a1 = m0[1], a2 = m0[2], a3 = m0[3];
+        if (a0 && a1 && a2 && a3) {
+            c0x += popc4x64_csa(v0.x & a0, v1.x & a1, v2.x & a2, v3.x & a3);
+            c0y += popc4x64_csa(v0.y & a0, v1.y & a1, v2.y & a2, v3.y & a3);
+        } else {
+            if (a0) { c0x += __popcll(v0.x & a0); c0y += __popcll(v0.y & a0); }
+            if (a1) { c0x += __popcll(v1.x & a1); c0y += __popcll(v1.y & a1); }
+            if (a2) { c0x += __popcll(v2.x & a2); c0y += __popcll(v2.y & a2); }
+            if (a3) { c0x += __popcll(v3.x & a3); c0y += __popcll(v3.y & a3); }
+        }
+    }
+    {
+        const uint64_t b0 = m1[0], b1 = m1[1], b2 = m1[2], b3 = m1[3];
+        if (b0 && b1 && b2 && b3) {
+            c1x += popc4x64_csa(v0.x & b0, v1.x & b1, v2.x & b2, v3.x & b3);
+            c1y += popc4x64_csa(v0.y & b0, v1.y & b1, v2.y & b2, v3.y & b3);
+        } else {
+            if (b0) { c1x += __popcll(v0.x & b0); c1y += __popcll(v0.y & b0); }
+            if (b1) { c1x += __popcll(v1.x & b1); c1y += __popcll(v1.y & b1); }
+            if (b2) { c1x += __popcll(v2.x & b2); c1y += __popcll(v2.y & b2); }
+            if (b3) { c1x += __popcll(v3.x & b3); c1y += __popcll(v3.y & b3); }
+        }
+    }
+}
+
 __device__ __forceinline__ void accum_word(const unsigned char *p, uint64_t a, uint64_t m, uint32_t &c0x, uint32_t &c0y,
                                            uint32_t &c1x, uint32_t &c1y) {
     const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(p);
@@ -497,7 +551,11 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) k_scan_tma(const Scan2Par
             const int rows_here = min(R, n_act - b * R);
             mbar_wait(full + s, ph);
             const unsigned char *st = ring + (size_t)s * R * ROW_BYTES + threadIdx.x * 16;
-            if (rows_here == R) {
+            if (R % 4 == 0 && rows_here == R && P.csa) {      // (row groups of four must not straddle ring stages)
+#pragma unroll
+                for (int r = 0; r + 3 < R; r += 4)
+                    accum_rows4(st + r * ROW_BYTES, ROW_BYTES, s_m0 + b * R + r, s_m1 + b * R + r, c0x, c0y, c1x, c1y);
+            } else if (rows_here == R) {
 #pragma unroll
                 for (int r = 0; r < R; ++r)
                     accum_word(st + r * ROW_BYTES, s_m0[b * R + r], s_m1[b * R + r], c0x, c0y, c1x, c1y);
@@ -1619,23 +1677,6 @@ struct CountParams {
     uint32_t *cnt[MAX_MULTI];     // [ld] each; null = discard (padding mask)
 };
 
-// 3:2 carry-save compressor on 32 bit lanes: a + b + d = s + 2 c, two LOP3
-__device__ __forceinline__ void csa32(uint32_t &s, uint32_t &c, uint32_t a, uint32_t b, uint32_t d) {
-    s = a ^ b ^ d;
-    c = (a & b) | (d & (a ^ b));
-}
-// popcount(a) + popcount(b) + popcount(c) + popcount(d) of four (already masked) 64-bit words with 4 POPC instead
-// of 8: the eight 32-bit halves go through four carry-save compressors (8 LOP3 on the ALU pipe, which idles
-// while the 16-lane POPC pipe is the bottleneck), leaving two words of weight 1, one of weight 2, one of weight 4.
-__device__ __forceinline__ uint32_t popc4x64_csa(uint64_t a, uint64_t b, uint64_t c, uint64_t d) {
-    uint32_t s1, c1, s2, c2, s3, c3, s4, c4;
-    csa32(s1, c1, (uint32_t)a, (uint32_t)(a >> 32), (uint32_t)b);
-    csa32(s2, c2, (uint32_t)(b >> 32), (uint32_t)c, (uint32_t)(c >> 32));
-    csa32(s3, c3, s1, s2, (uint32_t)d);
-    csa32(s4, c4, c1, c2, c3);
-    return (__popc(s3) + __popc((uint32_t)(d >> 32))) + 2 * (__popc(s4) + 2 * __popc(c4));
-}
-
 // Mask staging: [group of 4 consecutive active rows][NM][4] so that a (group, mask) needs two 128-bit broadcast
 // reads; s_nz[group] has bit m set when mask m is non-zero on any of the group's rows.
 template <int NM, int CW, int R, int S, bool CSA>
@@ -2400,6 +2441,7 @@ struct kv_shard {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
     int scan_ctas_per_sm = 4;
+    int scan_csa = 1;                         // KOVER_B200_SCAN_CSA=0: plain popcounts in k_scan_tma
     int l2_hints = 0;                         // KOVER_B200_L2HINT (bit 0 loads evict-first, bit 1 count stores evict-last)
     int scan_variant = -1;                    // -1: choose per call; >= 0: forced (KOVER_B200_SCAN_VARIANT)
 
@@ -2560,6 +2602,7 @@ extern "C" int kv_create(int device, int64_t n_examples, int64_t n_kmers_total, 
     s->n_tiles = s->ld / TILE_COLS;
     if (const char *v = getenv("KOVER_B200_SCAN_VARIANT")) s->scan_variant = atoi(v);
     if (const char *v = getenv("KOVER_B200_L2HINT")) s->l2_hints = atoi(v);
+    if (const char *v = getenv("KOVER_B200_SCAN_CSA")) s->scan_csa = atoi(v);
     if (const char *v = getenv("KOVER_B200_FUSED")) s->fused = atoi(v);
     if (const char *v = getenv("KOVER_B200_COOP")) s->cooperative = atoi(v);
     if (const char *v = getenv("KOVER_B200_STREAM")) s->stream_cand = atoi(v);
@@ -3226,6 +3269,7 @@ static void fill_scan2(kv_shard *s, Scan2Params &P, int n_act) {
     P.k_total = s->k_total;
     P.n_act = n_act;
     P.l2_hints = s->l2_hints;
+    P.csa = s->scan_csa;
     if (n_act <= SCAN_INLINE_ROWS) {
         const uint64_t *pm0 = (const uint64_t *)s->h_pin, *pm1 = pm0 + n_act;
         const uint32_t *prow = (const uint32_t *)(pm1 + n_act);
@@ -4211,6 +4255,7 @@ static void fill_scan2_state(kv_shard *s, Scan2Params &P) {
     P.k_total = s->k_total;
     P.n_act = s->state_n_act;
     P.l2_hints = s->l2_hints;
+    P.csa = s->scan_csa;
     P.inline_rec = 0;
     P.rec_m0 = s->d_state + 3 * W;
     P.rec_m1 = s->d_state + 4 * W;
