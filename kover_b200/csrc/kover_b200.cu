@@ -5065,6 +5065,7 @@ struct kv_p2p {
     char *d_packet = nullptr;              // local packet staging
     int *d_error = nullptr;
     unsigned long long seq = 0;
+    unsigned long long timeout_ns = 20ull * 1000 * 1000 * 1000;   // waiting for a peer's packet (KOVER_B200_P2P_TIMEOUT_MS)
     void *h_rows = nullptr;                // pinned: gathered rows of one parity
     P2PDev *d_dev = nullptr;               // the peer table for the fused step (device copy)
 };
@@ -5076,6 +5077,8 @@ extern "C" int kv_p2p_create(kv_shard *s, int rank, int world, int64_t slot_byte
     DeviceGuard g(s->device);
     if (s->p2p) return fail(KV_E_INVALID, "kv_p2p_create: mailbox already exists");
     kv_p2p *m = new kv_p2p();
+    if (const char *v = getenv("KOVER_B200_P2P_TIMEOUT_MS"))
+        if (atoll(v) > 0) m->timeout_ns = (unsigned long long)atoll(v) * 1000ull * 1000ull;
     m->rank = rank;
     m->world = world;
     m->slot_bytes = ((size_t)slot_bytes + 255) / 256 * 256;
@@ -5162,7 +5165,7 @@ extern "C" int kv_scm_best_rules_p2p(kv_shard *s, const uint64_t *pos_mask, cons
         P2PTail t;
         t.dev = m->d_dev;
         t.seq = ++m->seq;
-        t.timeout_ns = 20ull * 1000 * 1000 * 1000;
+        t.timeout_ns = m->timeout_ns;
         t.packet = m->d_packet;
         t.packet_cap = packet_capacity;
         *overflowed = 0;
@@ -5197,7 +5200,7 @@ extern "C" int kv_scm_best_rules_p2p(kv_shard *s, const uint64_t *pos_mask, cons
     P.packet = m->d_packet;
     P.packet_capacity = packet_capacity;
     P.error = m->d_error;
-    P.timeout_ns = 20ull * 1000 * 1000 * 1000;
+    P.timeout_ns = m->timeout_ns;
     k_p2p_publish_wait<<<1, 256, 0, s->stream>>>(P);
     count_launch(s);
     const int parity = (int)(P.seq & 1ull);

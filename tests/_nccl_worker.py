@@ -147,6 +147,28 @@ def main():
         walk_eq(t.decision_tree, root)
         stats = dict(rc._group.exchange_stats)
         rc.close()
+    # a peer that never publishes its packet: the waiting rank gives up after the timeout and reports it (both the
+    # one-kernel exchange and k_p2p_publish_wait), instead of hanging the GPU
+    import time
+    os.environ["KOVER_B200_P2P"] = "1"
+    os.environ["KOVER_B200_P2P_TIMEOUT_MS"] = "400"
+    for fused in ("1", "0"):
+        os.environ["KOVER_B200_FUSED"] = fused
+        rc = KmerRuleClassifications(P, n, devices=[lr], comm=comm)
+        assert rc._group.p2p_slot_bytes > 0
+        if comm.rank == 0:
+            t0 = time.perf_counter()
+            try:
+                rc.best_utility_rules(1.0, pos, neg, util_block_size=1000000)
+                message = "no error"
+            except RuntimeError as e:
+                message = str(e)
+            waited = time.perf_counter() - t0
+            assert "timed out waiting for a peer" in message, message
+            assert 0.3 < waited < 10.0, waited
+        comm.barrier()
+        rc.close()
+    del os.environ["KOVER_B200_P2P_TIMEOUT_MS"]
     comm.barrier()
     if comm.rank == 0:
         print("NCCL_WORKER_OK p2p_used=%s nccl_used=%s stats=%s" % (used["1"], not used["0"], stats))
