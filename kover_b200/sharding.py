@@ -59,21 +59,28 @@ class Comm(object):
         return t.cpu().numpy()
 
     def allgather_concat(self, a):
-        """Concatenate 1-D int64 arrays of different lengths from every rank, in rank order."""
+        """Concatenate 1-D int64 arrays of different lengths from every rank, in rank order.  ONE collective in the usual
+        case: every rank sends [its length, its data] padded to a shared capacity; only when some rank's array does not
+        fit -- every rank sees the same lengths, so all of them decide alike -- the capacity grows (it is remembered) and
+        the gather is repeated."""
         a = np.ascontiguousarray(a, dtype=np.int64)
-        n = self._t(np.array([a.shape[0]], dtype=np.int64))
-        sizes = [self._torch.zeros_like(n) for _ in range(self.world_size)]
-        self._dist.all_gather(sizes, n, group=self.group)
-        sizes = [int(s.item()) for s in sizes]
-        m = max(sizes)
-        if m == 0:
-            return np.zeros(0, dtype=np.int64)
-        pad = np.zeros(m, dtype=np.int64)
-        pad[:a.shape[0]] = a
-        t = self._t(pad)
-        out = [self._torch.zeros_like(t) for _ in range(self.world_size)]
-        self._dist.all_gather(out, t, group=self.group)
-        return np.concatenate([o.cpu().numpy()[:s] for o, s in zip(out, sizes)])
+        cap = self.__dict__.get("_concat_capacity", 1024)
+        while True:
+            buf = np.zeros(cap + 1, dtype=np.int64)
+            buf[0] = a.shape[0]
+            buf[1:1 + min(a.shape[0], cap)] = a[:cap]
+            t = self._t(buf)
+            out = [self._torch.empty_like(t) for _ in range(self.world_size)]
+            self._dist.all_gather(out, t, group=self.group)
+            rows = self._torch.stack(out).cpu().numpy()
+            sizes = rows[:, 0]
+            largest = int(sizes.max())
+            # the next call starts from twice what this one needed (tie lists of a tree's small nodes run to millions,
+            # those of the next fit to a handful)
+            self._concat_capacity = max(1024, 1 << max(0, 2 * largest - 1).bit_length())
+            if largest <= cap:
+                return np.concatenate([rows[r, 1:1 + int(sizes[r])] for r in range(self.world_size)])
+            cap = self._concat_capacity
 
     def byte_buffers(self, nbytes):
         """(local [nbytes], gathered [world, nbytes]) uint8 tensors on the collective's device, cached by size."""
