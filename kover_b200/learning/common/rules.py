@@ -80,6 +80,34 @@ class BaseRuleClassifications(object):
         raise NotImplementedError()
 
 
+def _raw_chunk_view(dataset):
+    """The dataset as something that can hand out the RAW gzip streams of its chunks (``deflate_chunk_table``), or None.
+    hdf5_lite datasets do so themselves.  An h5py dataset -- what a Kover installation passes in (utils.py:58-73,
+    experiment_scm.py:830) -- inflates every chunk on one host core inside ``dataset[...]`` (rules.py:253); the same file
+    is therefore opened a second time, read-only, with the built-in reader, which only parses the chunk index (the
+    reference writes its files with h5py's default "earliest" format: version-0 superblock, version-1 object headers,
+    version-1 chunk B-tree).  Anything the reader does not understand -- or a dataset that does not look like the same
+    object -- falls back to reading through the caller's dataset."""
+    if getattr(dataset, "deflate_chunk_table", None) is not None:
+        return dataset
+    try:
+        path, name = dataset.file.filename, dataset.name
+    except AttributeError:
+        return None
+    if not isinstance(path, str) or not isinstance(name, str) or getattr(dataset, "chunks", None) is None:
+        return None
+    try:
+        from ...dataset import hdf5_lite
+        twin = hdf5_lite.File(path, "r")[name]
+        if getattr(twin, "deflate_chunk_table", None) is None:
+            return None
+        same = (tuple(twin.shape) == tuple(dataset.shape) and np.dtype(twin.dtype) == np.dtype(dataset.dtype)
+                and tuple(twin.chunks or ()) == tuple(dataset.chunks))
+        return twin if same else None
+    except Exception:                       # (NotImplementedError for newer file formats, OSError, KeyError, ...)
+        return None
+
+
 _level_keys = itertools.count(1)
 
 
@@ -233,10 +261,12 @@ class KmerRuleClassifications(BaseRuleClassifications):
         KOVER_B200_DEVICE_INFLATE=0 switches it off.  A chunk the device rejects (malformed stream) or that was stored
         unfiltered is read through the host path, which raises the proper error if it really is corrupt.
         -> False when this path does not apply."""
-        ds = self.dataset
-        table_of = getattr(ds, "deflate_chunk_table", None)
-        if table_of is None or os.environ.get("KOVER_B200_DEVICE_INFLATE", "1") == "0":
+        if os.environ.get("KOVER_B200_DEVICE_INFLATE", "1") == "0":
             return False
+        ds = _raw_chunk_view(self.dataset)
+        if ds is None:
+            return False
+        table_of = ds.deflate_chunk_table
         if not all(hasattr(s, "upload_deflate") for s in self._group.shards):
             return False
         needed_rows = min(-(-int(self.dataset_initial_n_rows) // self.dataset_pack_size), int(ds.shape[0]))

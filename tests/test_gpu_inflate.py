@@ -109,6 +109,28 @@ def test_device_inflate_matches_host_path(tmp_path, monkeypatch, case, devices, 
     assert np.array_equal(images["0"], want)
 
 
+def test_h5py_like_dataset_takes_the_device_inflate_path(tmp_path, monkeypatch):
+    """A dataset object in h5py's style (shape / dtype / chunks / name / file.filename, slicing inflates on the host) --
+    what a Kover installation passes to KmerRuleClassifications -- is uploaded through the raw chunks of its file and
+    the device decoder, without a single read through the object itself; with the device path switched off the same
+    object is read slab by slab.  Both images equal the written matrix."""
+    from h5py_like import H5pyLikeDataset
+    M = matrix(5, 6, 120_000, np.uint64, "mixed")
+    path = str(tmp_path / "m.h5")
+    with Writer(path) as w:
+        w.create_dataset("kmer_matrix", M, chunks=(1, 50_000), compression=4)
+    n_genomes = 6 * 64 - 5
+    for mode, devices in (("1", [0]), ("1", [0, 0, 0]), ("0", [0])):
+        monkeypatch.setenv("KOVER_B200_DEVICE_INFLATE", mode)
+        like = H5pyLikeDataset(path, "kmer_matrix")
+        rc = KmerRuleClassifications(like, n_genomes, devices=devices)
+        assert (like.reads == 0) == (mode == "1")
+        if mode == "1":
+            assert all(s.upload_deflate_stats()["total_ms"] > 0 for s in rc._group.shards)
+        assert np.array_equal(resident(rc, 6), M)
+        rc.close()
+
+
 def test_corrupt_stream_is_reported_through_the_host_path(tmp_path):
     """A flipped byte inside one chunk: the device marks the chunk (bad code / distance / checksum), the host path
     re-inflates it and raises zlib's own error; the other chunks are unaffected."""

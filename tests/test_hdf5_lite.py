@@ -237,3 +237,34 @@ def test_version_2_object_header_is_not_implemented(tmp_path):
     with pytest.raises(NotImplementedError, match="version-2 object headers"):
         f["kmer_matrix"]
     assert np.array_equal(f["phenotype"][...], np.array([0, 0, 1, 1, 0, 1], dtype=np.uint8))
+
+
+def test_raw_chunk_view_of_an_h5py_like_dataset(tmp_path):
+    """rules._raw_chunk_view: an h5py-style dataset (file name + object name, no raw-chunk access) is opened a second
+    time with the built-in reader so that its gzip chunks can go to the device as they are; anything that does not
+    look like the same dataset, or that the reader cannot parse, falls back to reading through the caller's object."""
+    from h5py_like import H5pyLikeDataset
+    from kover_b200.learning.common.rules import _raw_chunk_view
+    rs = np.random.RandomState(8)
+    M = rs.randint(0, 2 ** 62, size=(5, 2300)).astype(np.uint64)
+    path = str(tmp_path / "k.h5")
+    with Writer(path) as w:
+        w.create_dataset("kmer_matrix", M, chunks=(1, 1000), compression=4)
+        w.create_dataset("plain", M)                                   # contiguous: no chunks to hand out
+    like = H5pyLikeDataset(path, "kmer_matrix")
+    twin = _raw_chunk_view(like)
+    assert twin is not None and twin is not like and tuple(twin.shape) == M.shape
+    tab = twin.deflate_chunk_table(0, 5, 0, 2300)
+    assert tab is not None and tab["address"].shape[0] == 5 * 3 and np.array_equal(twin[...], M)
+    direct = hdf5_lite.File(path)["kmer_matrix"]
+    assert _raw_chunk_view(direct) is direct                           # the built-in reader's own datasets: as they are
+    assert _raw_chunk_view(M) is None                                  # numpy arrays / memmaps: nothing to open
+    assert _raw_chunk_view(H5pyLikeDataset(path, "kmer_matrix", shape=(5, 2299))) is None      # not the same object
+    assert _raw_chunk_view(H5pyLikeDataset(path, "plain")) is None
+    gone = H5pyLikeDataset(path, "kmer_matrix")
+    gone.file.filename = str(tmp_path / "moved_away.h5")
+    assert _raw_chunk_view(gone) is None
+    with open(str(tmp_path / "not.h5"), "wb") as f:
+        f.write(b"definitely not HDF5" * 100)
+    gone.file.filename = str(tmp_path / "not.h5")
+    assert _raw_chunk_view(gone) is None
