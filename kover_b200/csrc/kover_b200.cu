@@ -3075,11 +3075,20 @@ extern "C" int kv_upload_deflate(kv_shard *s, int pack_bits, int64_t n_chunks, c
         const int grid = (int)std::min<long long>((n_here + INF_WARPS - 1) / INF_WARPS, (long long)s->sm_count * 6);
         if (stats) cudaEventRecord(ev_k0, ks);
         // (KOVER_B200_INFLATE_V=1: the first decoder, one lane walking the whole stream -- kept for comparison)
-        const int inflate_v = getenv("KOVER_B200_INFLATE_V") ? atoi(getenv("KOVER_B200_INFLATE_V")) : 2;
-        if (inflate_v == 1)
+        // =2: the chain walk of one code per dependent load and global-memory peeks (before k_inflate3)
+        const int inflate_v = getenv("KOVER_B200_INFLATE_V") ? atoi(getenv("KOVER_B200_INFLATE_V")) : 3;
+        if (inflate_v == 1) {
             k_inflate<<<grid, INF_WARPS * 32, 0, ks>>>(d_comp[par], d_jobs[par], n_here, d_status + a, d_next + slab_no);
-        else
+        } else if (inflate_v == 2) {
             k_inflate2<<<grid, INF_WARPS * 32, 0, ks>>>(d_comp[par], d_jobs[par], n_here, d_status + a, d_next + slab_no);
+        } else {
+            constexpr size_t smem3 = sizeof(InflateWarp3) * INF_WARPS;
+            static std::atomic<bool> armed[64];
+            if (s->device < 64 && !armed[s->device].exchange(true))
+                CU(cudaFuncSetAttribute(k_inflate3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+            const int grid3 = std::min(grid, s->sm_count * 4);
+            k_inflate3<<<grid3, INF_WARPS * 32, smem3, ks>>>(d_comp[par], d_jobs[par], n_here, d_status + a, d_next + slab_no);
+        }
         if (stats) {
             cudaEventRecord(ev_k1, ks);
             cudaEventSynchronize(ev_k1);

@@ -248,18 +248,15 @@ __device__ __forceinline__ unsigned int warp_adler32(const unsigned char *dst, u
     unsigned long long s1 = 0, s2 = 0;
     const unsigned int n16 = n / 16;
     const uint4 *v = reinterpret_cast<const uint4 *>(dst);
-    for (unsigned int i = lane; i < n16; i += 32) {
+#pragma unroll 4
+    for (unsigned int i = lane; i < n16; i += 32) {        // (unrolled: four independent 16-byte loads in flight)
         const uint4 q = __ldcg(v + i);
         const unsigned int w[4] = {q.x, q.y, q.z, q.w};
         unsigned int a = 0, wsum = 0;                      // a = sum b_j, wsum = sum j * b_j over the 16 bytes
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const unsigned int byte = (w[k] >> (8 * j)) & 0xFFu;
-                a += byte;
-                wsum += (unsigned int)(k * 4 + j) * byte;
-            }
+        for (int k = 0; k < 4; ++k) {                      // byte-wise dot products: weights 1,1,1,1 and 4k .. 4k+3
+            a = __dp4a(w[k], 0x01010101u, a);
+            wsum = __dp4a(w[k], 0x03020100u + 0x04040404u * (unsigned int)k, wsum);
         }
         const unsigned long long base = (unsigned long long)n - (unsigned long long)i * 16ull;   // weight of byte 0
         s1 += a;
@@ -811,6 +808,377 @@ __global__ void __launch_bounds__(INF_WARPS * 32) k_inflate2(const unsigned char
                 __syncwarp();                                              // the match source may have just been written
                 const unsigned char *from = dst + out - mdist;
                 for (unsigned int i = lane; i < mlen; i += 32) dst[out + i] = from[i % mdist];
+                out += mlen;
+                __syncwarp();
+            }
+            if (p > nbits && st == INF_OK) st = INF_IN_OVERRUN;
+        }
+        // ---- trailer: Adler-32 of the output, big-endian, byte aligned
+        if (st == INF_OK) {
+            p = (p + 7u) & ~7u;
+            const unsigned int want = __byte_perm(peek32(src, p), 0, 0x0123);
+            p += 32;
+            if (p > nbits) st = INF_IN_OVERRUN;
+            else if (out != J.dst_bytes) st = INF_OUT_SHORT;
+            if (st == INF_OK) {
+                __syncwarp();
+                __threadfence_block();
+                if (warp_adler32(dst, J.dst_bytes, lane) != want) st = INF_BAD_CHECKSUM;
+            }
+        }
+        if (lane == 0) status[job] = st;
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_inflate3: k_inflate2 with a shorter critical path per literal run (a chunk's latency, not the GPU's throughput, bounds
+// uploads of a few GB: DESIGN.md section 4.7).
+//   * the compressed stream is read through a REGISTER WINDOW: lane l holds words base + l and base + 32 + l, refilled
+//     one line ahead, and a 32- / 64-bit peek is two / three pairs of shuffles -- no global load on the dependent path;
+//   * the chain p -> p + len -> ... is walked TWO codes per dependent shared-memory load: after the per-position
+//     entries E1[c] = {where the code starting at c leads, its literal} every lane composes E2[c] = {E1[c], E1[next(c)]}
+//     for its positions (one more parallel round), and a chain step is then LDS.64 -> LOP -> LDS.64: the low 18 bits
+//     of the loaded word ARE the shared-memory address of the next load.  Entries that are not table-resident literals
+//     (STOP) or lie beyond the window (END) point at themselves, so the walk needs no test inside a group of four
+//     steps.  Short runs (match-heavy data) keep the one-code walk over a 64-position window.
+// Same LSU instruction count per run as k_inflate2 (the decoder is also bound by shared-memory instructions once
+// every SM holds dozens of chunks), half the dependent loads.
+// ------------------------------------------------------------------------------------------------
+static constexpr unsigned int INF_E_STOP = 0x80000000u, INF_E_END = 0x40000000u;
+
+struct InflateWarp3 {                           // per-warp shared memory (6 848 B), dynamic
+    unsigned short lit_tab[1 << INF_LIT_BITS];
+    unsigned short dist_tab[1 << INF_DIST_BITS];
+    unsigned short lit_sym[288], dist_sym[32];
+    unsigned short lit_cnt[16], dist_cnt[16];
+    unsigned char lens[320];
+    unsigned int e1[256 + 16];                  // address of E2[next] | literal << 18 | flags
+    uint2 e2[256 + 16];                         // {E1[c], E1[next(c)]}
+};
+
+struct BitWindow {                              // identical control flow in all lanes; p only moves forward
+    BitSrc s;
+    unsigned int base, a, b;
+    int lane;
+    __device__ __forceinline__ void start(const BitSrc &src, int l) {
+        s = src;
+        lane = l;
+        base = 0;
+        a = src_word(s, (unsigned int)l);
+        b = src_word(s, 32u + (unsigned int)l);
+    }
+    // afterwards the word that holds bit p is one of the first 32 of the window (p is warp-uniform)
+    __device__ __forceinline__ void seek(unsigned int p) {
+        const unsigned int wi = p >> 5;
+        if (wi - base >= 64u) {
+            base = wi & ~31u;
+            a = src_word(s, base + (unsigned int)lane);
+            b = src_word(s, base + 32u + (unsigned int)lane);
+        } else if (wi - base >= 32u) {
+            a = b;
+            base += 32u;
+            b = src_word(s, base + 32u + (unsigned int)lane);
+        }
+    }
+    __device__ __forceinline__ unsigned int word(unsigned int wi) const {      // wi - base < 64, any lane pattern
+        const unsigned int r = wi - base;
+        const unsigned int x = __shfl_sync(0xffffffffu, a, (int)(r & 31u)), y = __shfl_sync(0xffffffffu, b, (int)(r & 31u));
+        return r < 32u ? x : y;
+    }
+    __device__ __forceinline__ unsigned int peek32(unsigned int pos) const {
+        const unsigned int i = pos >> 5;
+        return __funnelshift_r(word(i), word(i + 1), pos & 31u);
+    }
+    __device__ __forceinline__ unsigned long long peek64(unsigned int pos) const {
+        const unsigned int i = pos >> 5, sh = pos & 31u;
+        const unsigned int w0 = word(i), w1 = word(i + 1), w2 = word(i + 2);
+        return (unsigned long long)__funnelshift_r(w0, w1, sh) | ((unsigned long long)__funnelshift_r(w1, w2, sh) << 32);
+    }
+};
+
+__global__ void __launch_bounds__(INF_WARPS * 32) k_inflate3(const unsigned char *src_base, const InflateJob *jobs,
+                                                              int n_jobs, int *status, unsigned int *next_job) {
+    extern __shared__ __align__(16) unsigned char s_dyn[];
+    InflateWarp3 *s_w = reinterpret_cast<InflateWarp3 *>(s_dyn);
+    // length / distance code tables next to the decoder (constant-memory lookups with a data-dependent index cost a
+    // constant-cache round trip each, four per match)
+    __shared__ unsigned short s_len_base[29], s_dist_base[30];
+    __shared__ unsigned char s_len_extra[29], s_dist_extra[30];
+    if (threadIdx.x < 29) {
+        s_len_base[threadIdx.x] = c_len_base[threadIdx.x];
+        s_len_extra[threadIdx.x] = c_len_extra[threadIdx.x];
+    }
+    if (threadIdx.x < 30) {
+        s_dist_base[threadIdx.x] = c_dist_base[threadIdx.x];
+        s_dist_extra[threadIdx.x] = c_dist_extra[threadIdx.x];
+    }
+    __syncthreads();
+    const unsigned int full = 0xffffffffu;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    InflateWarp3 &S = s_w[wid];
+    const unsigned int e1_base = (unsigned int)__cvta_generic_to_shared(S.e1);
+    const unsigned int e2_base = (unsigned int)__cvta_generic_to_shared(S.e2);
+    for (;;) {
+        int job = 0;
+        if (lane == 0) job = (int)atomicAdd(next_job, 1u);
+        job = __shfl_sync(full, job, 0);
+        if (job >= n_jobs) return;
+        const InflateJob J = jobs[job];
+        unsigned char *dst = J.dst;
+        BitSrc src;
+        src.w = reinterpret_cast<const unsigned int *>(src_base + J.src_off);
+        src.n_words = (J.src_bytes + 3) / 4;
+        const unsigned int nbits = J.src_bytes * 8u;
+        int st = INF_OK;
+        unsigned int out = 0, p = 16;
+        BitWindow win;
+        win.start(src, lane);
+        {
+            const unsigned int w = peek32(src, 0);
+            const unsigned int cmf = w & 255u, flg = (w >> 8) & 255u;
+            if ((cmf & 15u) != 8u || (cmf >> 4) > 7u || ((cmf << 8) | flg) % 31u != 0u || (flg & 32u)) st = INF_BAD_HEADER;
+            if (J.src_bytes >= (1u << 28)) st = INF_IN_OVERRUN;            // bit positions are 32-bit
+        }
+        bool last = false;
+        while (st == INF_OK && !last) {
+            const unsigned int hw = peek32(src, p);
+            last = (hw & 1u) != 0;
+            const int btype = (int)((hw >> 1) & 3u);
+            p += 3;
+            if (btype == 0) {
+                p = (p + 7u) & ~7u;
+                const unsigned int lw = peek32(src, p);
+                const unsigned int len = lw & 0xFFFFu, nlen = lw >> 16;
+                p += 32;
+                const unsigned int byte_pos = p >> 3;
+                if ((len ^ nlen) != 0xFFFFu) st = INF_BAD_BLOCK;
+                else if (byte_pos + len > J.src_bytes) st = INF_IN_OVERRUN;
+                else if (out + len > J.dst_bytes) st = INF_OUT_OVERFLOW;
+                if (st != INF_OK) break;
+                const unsigned char *sb = src_base + J.src_off + byte_pos;
+                for (unsigned int i = lane; i < len; i += 32) dst[out + i] = sb[i];
+                out += len;
+                p += len * 8u;
+                __syncwarp();
+                continue;
+            }
+            if (btype == 3) {
+                st = INF_BAD_BLOCK;
+                break;
+            }
+            int hlit = 288, hdist = 30;
+            if (btype == 1) {
+                for (int i = lane; i < 288; i += 32) S.lens[i] = i < 144 ? 8 : (i < 256 ? 9 : (i < 280 ? 7 : 8));
+                for (int i = lane; i < 32; i += 32) S.lens[288 + i] = i < 30 ? 5 : 0;
+            } else {
+                st = read_dynamic_lengths2(src, p, S.lens, hlit, hdist, lane);
+                if (st != INF_OK) break;
+            }
+            __syncwarp();
+            if (!build_tables(S.lens, hlit, S.lit_cnt, S.lit_sym, S.lit_tab, INF_LIT_BITS, lane, true) ||
+                !build_tables(S.lens + hlit, hdist, S.dist_cnt, S.dist_sym, S.dist_tab, INF_DIST_BITS, lane, false)) {
+                st = INF_BAD_LENGTHS;
+                break;
+            }
+            // ---- symbols of the block
+            int mode = 2;
+            for (;;) {
+                // (1) the literal run that starts at p.  Every lane decodes the codes that WOULD start at 8 of the next
+                // 256 bit positions (one 32-bit peek, eight table lookups) and leaves {next position, literal} per
+                // position in shared memory; the chain p -> p + len -> ... is then walked through that table -- one
+                // dependent shared-memory load per symbol instead of a refill + lookup + branch chain -- by all
+                // lanes alike; lane i keeps the i-th literal of the run and the warp writes up to 32 bytes at once.
+                // (after a short run -- match-heavy data -- only 64 positions, two per lane, are looked up)
+                // mode 0: 64 positions, one code per step (after a short run: match-heavy data); mode 1: 256 positions,
+                // one code per step; mode 2 (after a run of >= 24 literals): 256 positions, two codes per step
+                const unsigned int window = mode ? 256u : 64u;
+                win.seek(p);
+                // E1[c], c < window + 16: the literal of the code that WOULD start at bit p + c and the shared-memory
+                // address of the entry it leads to (of E2 in mode 2, of E1 otherwise); flagged STOP when it is not a
+                // table-resident literal, END beyond the window -- flagged entries point at themselves
+                const unsigned int nbase = mode == 2 ? e2_base : e1_base, nshift = mode == 2 ? 3u : 2u;
+                if (mode) {
+                    const unsigned int w = win.peek32(p + 8u * (unsigned int)lane);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const unsigned int e = S.lit_tab[(w >> j) & ((1u << INF_LIT_BITS) - 1u)];
+                        const unsigned int c = 8u * (unsigned int)lane + (unsigned int)j;
+                        S.e1[c] = (e & 0x8000u) ? ((nbase + ((c + (e & 15u)) << nshift)) | (((e >> 4) & 0xFFu) << 18))
+                                                : ((nbase + (c << nshift)) | INF_E_STOP);
+                    }
+                } else {
+                    const unsigned int w = win.peek32(p + 2u * (unsigned int)lane);
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const unsigned int e = S.lit_tab[(w >> j) & ((1u << INF_LIT_BITS) - 1u)];
+                        const unsigned int c = 2u * (unsigned int)lane + (unsigned int)j;
+                        S.e1[c] = (e & 0x8000u) ? ((nbase + ((c + (e & 15u)) << nshift)) | (((e >> 4) & 0xFFu) << 18))
+                                                : ((nbase + (c << nshift)) | INF_E_STOP);
+                    }
+                }
+                if (lane < 16) S.e1[window + (unsigned int)lane] = (nbase + ((window + (unsigned int)lane) << nshift)) | INF_E_END;
+                __syncwarp();
+                unsigned int pos = 0, n = 0, mine = 0;
+                if (mode == 2) {
+                    // E2[c] = {E1[c], E1[next(c)]}: the chain is then walked TWO codes per dependent shared-memory load,
+                    // and the load address is the low 18 bits of the loaded word itself (one LOP between two loads)
+                    for (unsigned int c = (unsigned int)lane; c < 256u + 16u; c += 32u) {
+                        const unsigned int a1 = S.e1[c];
+                        const unsigned int a2 = S.e1[((a1 & 0x3FFFFu) - e2_base) >> 3];
+                        S.e2[c] = make_uint2(a1, a2);
+                    }
+                    __syncwarp();
+                    unsigned int addr = e2_base, mlo = INF_E_STOP, mhi = INF_E_STOP;
+#pragma unroll
+                    for (int s2 = 0; s2 < 16; ++s2) {
+                        unsigned int lo, hi;
+                        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(addr) : "memory");
+                        if ((lane >> 1) == s2) {
+                            mlo = lo;
+                            mhi = hi;
+                        }
+                        addr = hi & 0x3FFFFu;
+                        if ((s2 & 3) == 3 && (hi >> 30)) break;            // (uniform) the run has ended
+                    }
+                    const unsigned int e = (lane & 1) ? mhi : mlo;
+                    n = (unsigned int)__popc(__ballot_sync(full, (e >> 30) == 0u));
+                    mine = (e >> 18) & 0xFFu;
+                    pos = (addr - e2_base) >> 3;
+                } else {
+                    unsigned int addr = e1_base;
+#pragma unroll 1
+                    for (;;) {
+                        unsigned int e;
+                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(addr) : "memory");
+                        if (e >> 30) break;
+                        if (n == (unsigned int)lane) mine = (e >> 18) & 0xFFu;
+                        addr = e & 0x3FFFFu;
+                        if (++n == 32u) break;
+                    }
+                    pos = (addr - e1_base) >> 2;
+                }
+                const bool stop = (S.e1[pos] & INF_E_STOP) != 0u;
+                mode = n < 8u ? 0 : (n < 24u ? 1 : 2);
+                __syncwarp();                                              // (E1 / E2 are rewritten by the next iteration)
+                if (out + n > J.dst_bytes) {
+                    st = INF_OUT_OVERFLOW;
+                    break;
+                }
+                if ((unsigned int)lane < n) dst[out + lane] = (unsigned char)mine;
+                out += n;
+                p += pos;
+                if (p > nbits) {
+                    st = INF_IN_OVERRUN;
+                    break;
+                }
+                if (!stop) continue;                                       // the run goes on: next window
+                // (2) the symbol at p is not a table-resident literal: one symbol, decoded identically by every lane
+                unsigned long long q = win.peek64(p);
+                unsigned int used;
+                int sym;
+                {
+                    const unsigned int e1 = S.lit_tab[(unsigned int)q & ((1u << INF_LIT_BITS) - 1u)];
+                    if (e1 & 15u) {
+                        used = e1 & 15u;
+                        sym = (int)((e1 >> 4) & 0x1FFu);
+                    } else {
+                        const int r = slow_decode((unsigned int)q, S.lit_cnt, S.lit_sym);
+                        if (r < 0) {
+                            st = INF_BAD_CODE;
+                            break;
+                        }
+                        used = (unsigned int)(r >> 16);
+                        sym = r & 0xFFFF;
+                    }
+                }
+                q >>= used;
+                if (sym < 256) {                                           // a literal with a code longer than the table
+                    if (out + 1 > J.dst_bytes) {
+                        st = INF_OUT_OVERFLOW;
+                        break;
+                    }
+                    if (lane == 0) dst[out] = (unsigned char)sym;
+                    out += 1;
+                    p += used;
+                    continue;
+                }
+                if (sym == 256) {
+                    p += used;
+                    break;                                                 // end of block
+                }
+                sym -= 257;
+                if (sym >= 29) {
+                    st = INF_BAD_CODE;
+                    break;
+                }
+                unsigned int eb = s_len_extra[sym];
+                const unsigned int mlen = s_len_base[sym] + ((unsigned int)q & ((1u << eb) - 1u));
+                q >>= eb;
+                used += eb;
+                int ds;
+                {
+                    const unsigned int e2 = S.dist_tab[(unsigned int)q & ((1u << INF_DIST_BITS) - 1u)];
+                    unsigned int dl;
+                    if (e2 & 15u) {
+                        dl = e2 & 15u;
+                        ds = (int)(e2 >> 4);
+                    } else {
+                        const int r = slow_decode((unsigned int)q, S.dist_cnt, S.dist_sym);
+                        if (r < 0) {
+                            st = INF_BAD_CODE;
+                            break;
+                        }
+                        dl = (unsigned int)(r >> 16);
+                        ds = r & 0xFFFF;
+                    }
+                    q >>= dl;
+                    used += dl;
+                }
+                if (ds >= 30) {
+                    st = INF_BAD_CODE;
+                    break;
+                }
+                eb = s_dist_extra[ds];
+                const unsigned int mdist = s_dist_base[ds] + ((unsigned int)q & ((1u << eb) - 1u));
+                used += eb;
+                p += used;
+                if (p > nbits) {
+                    st = INF_IN_OVERRUN;
+                    break;
+                }
+                if (mdist > out) {
+                    st = INF_BAD_DISTANCE;
+                    break;
+                }
+                if (out + mlen > J.dst_bytes) {
+                    st = INF_OUT_OVERFLOW;
+                    break;
+                }
+                __syncwarp();                                              // the match source may have just been written
+                const unsigned char *from = dst + out - mdist;
+                unsigned char *to = dst + out;
+                if (mdist == 1u) {
+                    // a run of one byte value (the zero runs of a sparse k-mer matrix): aligned 32-bit stores
+                    const unsigned int b = from[0], b4 = b * 0x01010101u;
+                    const unsigned int head = min(mlen, (4u - ((unsigned int)(size_t)to & 3u)) & 3u);
+                    const unsigned int nw = (mlen - head) >> 2, tail0 = head + (nw << 2);
+                    if ((unsigned int)lane < head) to[lane] = (unsigned char)b;
+                    unsigned int *tw = reinterpret_cast<unsigned int *>(to + head);
+                    for (unsigned int i = lane; i < nw; i += 32) tw[i] = b4;
+                    if (tail0 + (unsigned int)lane < mlen) to[tail0 + lane] = (unsigned char)b;
+                } else if (mdist >= mlen) {
+                    for (unsigned int i = lane; i < mlen; i += 32) to[i] = from[i];
+                } else {
+                    // overlapping copy = the last mdist bytes repeated; i % mdist kept incrementally
+                    unsigned int j = (unsigned int)lane % mdist;
+                    const unsigned int step = 32u % mdist;
+                    for (unsigned int i = lane; i < mlen; i += 32) {
+                        to[i] = from[j];
+                        j += step;
+                        if (j >= mdist) j -= mdist;
+                    }
+                }
                 out += mlen;
                 __syncwarp();
             }

@@ -31,6 +31,9 @@ def streams(data, level=4, strategy=zlib.Z_DEFAULT_STRATEGY):
 cases = [("bench matrix, gzip 4", streams(rows, 4)), ("bench matrix, gzip 1", streams(rows, 1)),
          ("bench matrix, gzip 9", streams(rows, 9)), ("bench matrix, literals only", streams(rows, 6, zlib.Z_HUFFMAN_ONLY)),
          ("bench matrix, stored", streams(rows, 0)), ("sparse (2 % non-zero words), gzip 4", streams(sparse, 4))]
+only = os.environ.get("KV_CASES")                                 # e.g. KV_CASES="sparse" or "gzip 4,literals"
+if only:
+    cases = [c for c in cases if any(k.strip() in c[0] for k in only.split(","))]
 shard = _native.Shard(0, 64 * n_chunks, cols)
 for name, ss in cases:
     bufs = [np.frombuffer(s + b"\x00" * 8, dtype=np.uint8).copy() for s in ss]
