@@ -834,8 +834,8 @@ __global__ void __launch_bounds__(INF_WARPS * 32) k_inflate2(const unsigned char
 // ------------------------------------------------------------------------------------------------
 // k_inflate3: k_inflate2 with a shorter critical path per literal run (a chunk's latency, not the GPU's throughput, bounds
 // uploads of a few GB: DESIGN.md section 4.7).
-//   * the compressed stream is read through a REGISTER WINDOW: lane l holds words base + l and base + 32 + l, refilled
-//     one line ahead, and a 32- / 64-bit peek is two / three pairs of shuffles -- no global load on the dependent path;
+//   * the next 128-byte line of the compressed stream is prefetched into L1 when the decoder enters a line (a register
+//     window read with shuffles was tried: as fast alone, slower with 18 chunks per SM -- shuffles share the LSU pipe);
 //   * the chain p -> p + len -> ... is walked TWO codes per dependent shared-memory load: after the per-position
 //     entries E1[c] = {where the code starting at c leads, its literal} every lane composes E2[c] = {E1[c], E1[next(c)]}
 //     for its positions (one more parallel round), and a chain step is then LDS.64 -> LOP -> LDS.64: the low 18 bits
@@ -855,46 +855,6 @@ struct InflateWarp3 {                           // per-warp shared memory (6 848
     unsigned char lens[320];
     unsigned int e1[256 + 16];                  // address of E2[next] | literal << 18 | flags
     uint2 e2[256 + 16];                         // {E1[c], E1[next(c)]}
-};
-
-struct BitWindow {                              // identical control flow in all lanes; p only moves forward
-    BitSrc s;
-    unsigned int base, a, b;
-    int lane;
-    __device__ __forceinline__ void start(const BitSrc &src, int l) {
-        s = src;
-        lane = l;
-        base = 0;
-        a = src_word(s, (unsigned int)l);
-        b = src_word(s, 32u + (unsigned int)l);
-    }
-    // afterwards the word that holds bit p is one of the first 32 of the window (p is warp-uniform)
-    __device__ __forceinline__ void seek(unsigned int p) {
-        const unsigned int wi = p >> 5;
-        if (wi - base >= 64u) {
-            base = wi & ~31u;
-            a = src_word(s, base + (unsigned int)lane);
-            b = src_word(s, base + 32u + (unsigned int)lane);
-        } else if (wi - base >= 32u) {
-            a = b;
-            base += 32u;
-            b = src_word(s, base + 32u + (unsigned int)lane);
-        }
-    }
-    __device__ __forceinline__ unsigned int word(unsigned int wi) const {      // wi - base < 64, any lane pattern
-        const unsigned int r = wi - base;
-        const unsigned int x = __shfl_sync(0xffffffffu, a, (int)(r & 31u)), y = __shfl_sync(0xffffffffu, b, (int)(r & 31u));
-        return r < 32u ? x : y;
-    }
-    __device__ __forceinline__ unsigned int peek32(unsigned int pos) const {
-        const unsigned int i = pos >> 5;
-        return __funnelshift_r(word(i), word(i + 1), pos & 31u);
-    }
-    __device__ __forceinline__ unsigned long long peek64(unsigned int pos) const {
-        const unsigned int i = pos >> 5, sh = pos & 31u;
-        const unsigned int w0 = word(i), w1 = word(i + 1), w2 = word(i + 2);
-        return (unsigned long long)__funnelshift_r(w0, w1, sh) | ((unsigned long long)__funnelshift_r(w1, w2, sh) << 32);
-    }
 };
 
 __global__ void __launch_bounds__(INF_WARPS * 32) k_inflate3(const unsigned char *src_base, const InflateJob *jobs,
@@ -932,8 +892,7 @@ __global__ void __launch_bounds__(INF_WARPS * 32) k_inflate3(const unsigned char
         const unsigned int nbits = J.src_bytes * 8u;
         int st = INF_OK;
         unsigned int out = 0, p = 16;
-        BitWindow win;
-        win.start(src, lane);
+        unsigned int pf_line = 0xFFFFFFFFu;                          // last 128-byte line of the stream that was prefetched
         {
             const unsigned int w = peek32(src, 0);
             const unsigned int cmf = w & 255u, flg = (w >> 8) & 255u;
@@ -993,13 +952,17 @@ __global__ void __launch_bounds__(INF_WARPS * 32) k_inflate3(const unsigned char
                 // mode 0: 64 positions, one code per step (after a short run: match-heavy data); mode 1: 256 positions,
                 // one code per step; mode 2 (after a run of >= 24 literals): 256 positions, two codes per step
                 const unsigned int window = mode ? 256u : 64u;
-                win.seek(p);
+                if ((p >> 10) != pf_line) {                            // entering a new 128-byte line: fetch the next one into L1
+                    pf_line = p >> 10;
+                    const unsigned int nw = (pf_line + 1u) << 5;
+                    if (nw < src.n_words) asm volatile("prefetch.global.L1 [%0];" ::"l"(src.w + nw));
+                }
                 // E1[c], c < window + 16: the literal of the code that WOULD start at bit p + c and the shared-memory
                 // address of the entry it leads to (of E2 in mode 2, of E1 otherwise); flagged STOP when it is not a
                 // table-resident literal, END beyond the window -- flagged entries point at themselves
                 const unsigned int nbase = mode == 2 ? e2_base : e1_base, nshift = mode == 2 ? 3u : 2u;
                 if (mode) {
-                    const unsigned int w = win.peek32(p + 8u * (unsigned int)lane);
+                    const unsigned int w = peek32(src, p + 8u * (unsigned int)lane);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const unsigned int e = S.lit_tab[(w >> j) & ((1u << INF_LIT_BITS) - 1u)];
@@ -1008,7 +971,7 @@ __global__ void __launch_bounds__(INF_WARPS * 32) k_inflate3(const unsigned char
                                                 : ((nbase + (c << nshift)) | INF_E_STOP);
                     }
                 } else {
-                    const unsigned int w = win.peek32(p + 2u * (unsigned int)lane);
+                    const unsigned int w = peek32(src, p + 2u * (unsigned int)lane);
 #pragma unroll
                     for (int j = 0; j < 2; ++j) {
                         const unsigned int e = S.lit_tab[(w >> j) & ((1u << INF_LIT_BITS) - 1u)];
@@ -1074,7 +1037,7 @@ __global__ void __launch_bounds__(INF_WARPS * 32) k_inflate3(const unsigned char
                 }
                 if (!stop) continue;                                       // the run goes on: next window
                 // (2) the symbol at p is not a table-resident literal: one symbol, decoded identically by every lane
-                unsigned long long q = win.peek64(p);
+                unsigned long long q = peek64(src, p);
                 unsigned int used;
                 int sym;
                 {
