@@ -3075,12 +3075,20 @@ extern "C" int kv_upload_deflate(kv_shard *s, int pack_bits, int64_t n_chunks, c
         const int grid = (int)std::min<long long>((n_here + INF_WARPS - 1) / INF_WARPS, (long long)s->sm_count * 6);
         if (stats) cudaEventRecord(ev_k0, ks);
         // (KOVER_B200_INFLATE_V=1: the first decoder, one lane walking the whole stream -- kept for comparison)
-        // =2: the chain walk of one code per dependent load and global-memory peeks (before k_inflate3)
-        const int inflate_v = getenv("KOVER_B200_INFLATE_V") ? atoi(getenv("KOVER_B200_INFLATE_V")) : 3;
+        // default 4: every symbol of a window decoded speculatively (best on compressible = realistic k-mer matrices);
+        // =3: literal runs two codes per dependent load (best on literal-only streams); =2 / =1: the earlier decoders
+        const int inflate_v = getenv("KOVER_B200_INFLATE_V") ? atoi(getenv("KOVER_B200_INFLATE_V")) : 4;
         if (inflate_v == 1) {
             k_inflate<<<grid, INF_WARPS * 32, 0, ks>>>(d_comp[par], d_jobs[par], n_here, d_status + a, d_next + slab_no);
         } else if (inflate_v == 2) {
             k_inflate2<<<grid, INF_WARPS * 32, 0, ks>>>(d_comp[par], d_jobs[par], n_here, d_status + a, d_next + slab_no);
+        } else if (inflate_v != 3) {
+            constexpr size_t smem4 = sizeof(InflateWarp4) * INF_WARPS;
+            static std::atomic<bool> armed4[64];
+            if (s->device < 64 && !armed4[s->device].exchange(true))
+                CU(cudaFuncSetAttribute(k_inflate4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
+            const int grid4 = std::min(grid, s->sm_count * 4);
+            k_inflate4<<<grid4, INF_WARPS * 32, smem4, ks>>>(d_comp[par], d_jobs[par], n_here, d_status + a, d_next + slab_no);
         } else {
             constexpr size_t smem3 = sizeof(InflateWarp3) * INF_WARPS;
             static std::atomic<bool> armed[64];

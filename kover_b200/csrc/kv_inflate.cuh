@@ -1165,6 +1165,378 @@ __global__ void __launch_bounds__(INF_WARPS * 32) k_inflate3(const unsigned char
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// k_inflate4: EVERY symbol of a 256-bit window is decoded speculatively, length / distance pairs included.
+//
+// Source-level stall samples of k_inflate3 on the dense bench matrix (short matches every few literals) are flat: ~460
+// cycles per symbol spread over ~100 dependent instructions -- a serial program, one warp, 4 - 6 cycles per dependent
+// issue.  The cure is fewer SERIAL instructions per symbol.  Here the lanes decode, for each of the next 256 bit
+// positions, the complete symbol that would start there (literal, or length code + extra bits + distance code + extra
+// bits, at most 48 bits, from one 64-bit peek); the real symbols are then found by the chain walk (one dependent 64-bit
+// shared-memory load each), their output offsets by a warp prefix sum, literals are written at once, short matches whose
+// source precedes the batch are copied by their own lanes, and only the remaining matches (long, or reading what the
+// batch itself produces: the distance-1 zero runs of a sparse matrix) are copied one after the other by the whole warp.
+// Positions that do not hold a valid table-resident symbol stop the chain and take k_inflate2's one-symbol path.
+// ------------------------------------------------------------------------------------------------
+static constexpr unsigned int INF4_STOP = 0x80000000u, INF4_END = 0x40000000u, INF4_MATCH = 0x20000000u;
+
+struct InflateWarp4 {                           // per-warp shared memory (6 016 B), dynamic
+    unsigned short lit_tab[1 << INF_LIT_BITS];
+    unsigned short dist_tab[1 << INF_DIST_BITS];
+    unsigned short lit_sym[288], dist_sym[32];
+    unsigned short lit_cnt[16], dist_cnt[16];
+    unsigned char lens[320];
+    uint2 sym[256 + 48];                        // .x = address of the next entry | literal << 18 | flags, .y = length | distance << 16
+};
+
+__global__ void __launch_bounds__(INF_WARPS * 32) k_inflate4(const unsigned char *src_base, const InflateJob *jobs,
+                                                              int n_jobs, int *status, unsigned int *next_job) {
+    extern __shared__ __align__(16) unsigned char s_dyn[];
+    InflateWarp4 *s_w = reinterpret_cast<InflateWarp4 *>(s_dyn);
+    // length / distance code tables next to the decoder (constant-memory lookups with a data-dependent index cost a
+    // constant-cache round trip each, four per match)
+    __shared__ unsigned short s_len_base[29], s_dist_base[30];
+    __shared__ unsigned char s_len_extra[29], s_dist_extra[30];
+    __shared__ unsigned int s_lenx[32], s_distx[32];              // base | extra bits << 16, one lookup instead of two
+    if (threadIdx.x < 32) {
+        s_lenx[threadIdx.x] = threadIdx.x < 29 ? (unsigned int)c_len_base[threadIdx.x] | ((unsigned int)c_len_extra[threadIdx.x] << 16) : 0u;
+        s_distx[threadIdx.x] = threadIdx.x < 30 ? (unsigned int)c_dist_base[threadIdx.x] | ((unsigned int)c_dist_extra[threadIdx.x] << 16) : 0u;
+    }
+    if (threadIdx.x < 29) {
+        s_len_base[threadIdx.x] = c_len_base[threadIdx.x];
+        s_len_extra[threadIdx.x] = c_len_extra[threadIdx.x];
+    }
+    if (threadIdx.x < 30) {
+        s_dist_base[threadIdx.x] = c_dist_base[threadIdx.x];
+        s_dist_extra[threadIdx.x] = c_dist_extra[threadIdx.x];
+    }
+    __syncthreads();
+    const unsigned int full = 0xffffffffu;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    InflateWarp4 &S = s_w[wid];
+    const unsigned int sym_base = (unsigned int)__cvta_generic_to_shared(S.sym);
+    for (;;) {
+        int job = 0;
+        if (lane == 0) job = (int)atomicAdd(next_job, 1u);
+        job = __shfl_sync(full, job, 0);
+        if (job >= n_jobs) return;
+        const InflateJob J = jobs[job];
+        unsigned char *dst = J.dst;
+        BitSrc src;
+        src.w = reinterpret_cast<const unsigned int *>(src_base + J.src_off);
+        src.n_words = (J.src_bytes + 3) / 4;
+        const unsigned int nbits = J.src_bytes * 8u;
+        int st = INF_OK;
+        unsigned int out = 0, p = 16;
+        unsigned int pf_line = 0xFFFFFFFFu;                          // last 128-byte line of the stream that was prefetched
+        {
+            const unsigned int w = peek32(src, 0);
+            const unsigned int cmf = w & 255u, flg = (w >> 8) & 255u;
+            if ((cmf & 15u) != 8u || (cmf >> 4) > 7u || ((cmf << 8) | flg) % 31u != 0u || (flg & 32u)) st = INF_BAD_HEADER;
+            if (J.src_bytes >= (1u << 28)) st = INF_IN_OVERRUN;            // bit positions are 32-bit
+        }
+        bool last = false;
+        while (st == INF_OK && !last) {
+            const unsigned int hw = peek32(src, p);
+            last = (hw & 1u) != 0;
+            const int btype = (int)((hw >> 1) & 3u);
+            p += 3;
+            if (btype == 0) {
+                p = (p + 7u) & ~7u;
+                const unsigned int lw = peek32(src, p);
+                const unsigned int len = lw & 0xFFFFu, nlen = lw >> 16;
+                p += 32;
+                const unsigned int byte_pos = p >> 3;
+                if ((len ^ nlen) != 0xFFFFu) st = INF_BAD_BLOCK;
+                else if (byte_pos + len > J.src_bytes) st = INF_IN_OVERRUN;
+                else if (out + len > J.dst_bytes) st = INF_OUT_OVERFLOW;
+                if (st != INF_OK) break;
+                const unsigned char *sb = src_base + J.src_off + byte_pos;
+                for (unsigned int i = lane; i < len; i += 32) dst[out + i] = sb[i];
+                out += len;
+                p += len * 8u;
+                __syncwarp();
+                continue;
+            }
+            if (btype == 3) {
+                st = INF_BAD_BLOCK;
+                break;
+            }
+            int hlit = 288, hdist = 30;
+            if (btype == 1) {
+                for (int i = lane; i < 288; i += 32) S.lens[i] = i < 144 ? 8 : (i < 256 ? 9 : (i < 280 ? 7 : 8));
+                for (int i = lane; i < 32; i += 32) S.lens[288 + i] = i < 30 ? 5 : 0;
+            } else {
+                st = read_dynamic_lengths2(src, p, S.lens, hlit, hdist, lane);
+                if (st != INF_OK) break;
+            }
+            __syncwarp();
+            if (!build_tables(S.lens, hlit, S.lit_cnt, S.lit_sym, S.lit_tab, INF_LIT_BITS, lane, true) ||
+                !build_tables(S.lens + hlit, hdist, S.dist_cnt, S.dist_sym, S.dist_tab, INF_DIST_BITS, lane, false)) {
+                st = INF_BAD_LENGTHS;
+                break;
+            }
+            // ---- symbols of the block
+            for (;;) {
+                // (1) every symbol that starts inside the next 256 bits -- literals AND length / distance pairs -- is decoded
+                // speculatively: lane l decodes the symbols that WOULD start at bit p + 8 l + j (j < 8) from one 64-bit
+                // peek (a symbol is at most 15 + 5 + 15 + 13 = 48 bits) and leaves {where it leads, literal | length,
+                // distance} per position; positions that do not hold a table-resident, valid symbol (end of block, codes
+                // longer than the tables, bad codes) are STOP entries and go through the one-symbol path (2) below.
+                if ((p >> 10) != pf_line) {                            // entering a new 128-byte line: fetch the next one into L1
+                    pf_line = p >> 10;
+                    const unsigned int nw = (pf_line + 1u) << 5;
+                    if (nw < src.n_words) asm volatile("prefetch.global.L1 [%0];" ::"l"(src.w + nw));
+                }
+                {
+                    const unsigned long long w = peek64(src, p + 8u * (unsigned int)lane);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const unsigned long long wj = w >> j;
+                        const unsigned int c = 8u * (unsigned int)lane + (unsigned int)j;
+                        const unsigned int e = S.lit_tab[(unsigned int)wj & ((1u << INF_LIT_BITS) - 1u)];
+                        unsigned int lo = (sym_base + (c << 3)) | INF4_STOP, hi = 0u;
+                        unsigned int used = e & 15u;
+                        if (e & 0x8000u) {                                             // literal
+                            lo = (sym_base + ((c + used) << 3)) | (((e >> 4) & 0xFFu) << 18);
+                        } else if (used != 0u) {
+                            const unsigned int ls = ((e >> 4) & 0x1FFu) - 257u;        // (256 = end of block wraps to a large value)
+                            if (ls < 29u) {
+                                const unsigned int lx = s_lenx[ls];
+                                unsigned int eb = lx >> 16;
+                                const unsigned int mlen = (lx & 0xFFFFu) + ((unsigned int)(wj >> used) & ((1u << eb) - 1u));
+                                used += eb;
+                                const unsigned int e2 = S.dist_tab[(unsigned int)(wj >> used) & ((1u << INF_DIST_BITS) - 1u)];
+                                const unsigned int dl = e2 & 15u, ds = e2 >> 4;
+                                if (dl != 0u && ds < 30u) {
+                                    const unsigned int dx = s_distx[ds];
+                                    eb = dx >> 16;
+                                    used += dl;
+                                    const unsigned int mdist = (dx & 0xFFFFu) + ((unsigned int)(wj >> used) & ((1u << eb) - 1u));
+                                    used += eb;
+                                    lo = (sym_base + ((c + used) << 3)) | INF4_MATCH;
+                                    hi = mlen | (mdist << 16);
+                                }
+                            }
+                        }
+                        S.sym[c] = make_uint2(lo, hi);
+                    }
+                }
+                for (unsigned int c = 256u + (unsigned int)lane; c < 256u + 48u; c += 32u)
+                    S.sym[c] = make_uint2((sym_base + (c << 3)) | INF4_END, 0u);
+                __syncwarp();
+                // the chain p -> next -> ...: one dependent 64-bit shared-memory load per symbol; lane k keeps symbol k
+                unsigned int n = 0, mlo = INF4_STOP, mhi = 0u, addr = sym_base;
+#pragma unroll 1
+                for (;;) {
+                    unsigned int lo, hi;
+                    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(addr) : "memory");
+                    if (lo & (INF4_STOP | INF4_END)) break;
+                    if (n == (unsigned int)lane) {
+                        mlo = lo;
+                        mhi = hi;
+                    }
+                    addr = lo & 0x3FFFFu;
+                    if (++n == 32u) break;
+                }
+                const unsigned int pos = (addr - sym_base) >> 3;
+                const bool stop = (S.sym[pos].x & INF4_STOP) != 0u;
+                __syncwarp();                                              // (S.sym is rewritten by the next iteration)
+                // where every symbol's output goes: exclusive prefix sum of the output lengths
+                const bool have = (unsigned int)lane < n, is_match = have && (mlo & INF4_MATCH) != 0u;
+                const unsigned int s_len = mhi & 0xFFFFu, s_dist = mhi >> 16;
+                const unsigned int mylen = have ? (is_match ? s_len : 1u) : 0u;
+                unsigned int incl = mylen;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const unsigned int t = __shfl_up_sync(full, incl, d);
+                    if (lane >= d) incl += t;
+                }
+                const unsigned int total = __shfl_sync(full, incl, 31), off = incl - mylen;
+                if (out + total > J.dst_bytes) {
+                    st = INF_OUT_OVERFLOW;
+                    break;
+                }
+                if (__any_sync(full, is_match && s_dist > out + off)) {
+                    st = INF_BAD_DISTANCE;
+                    break;
+                }
+                if (have && !is_match) dst[out + off] = (unsigned char)((mlo >> 18) & 0xFFu);
+                // matches whose source lies wholly before this batch's output and that are short: every lane copies its own
+                const bool indep = is_match && s_dist >= off + s_len && s_len <= 16u;
+                if (indep) {
+                    const unsigned char *from = dst + out + off - s_dist;
+                    unsigned char *to = dst + out + off;
+                    for (unsigned int i = 0; i < s_len; ++i) to[i] = from[i];
+                }
+                // the others in symbol order, copied by the whole warp (they may read what earlier symbols of the batch wrote)
+                unsigned int todo = __ballot_sync(full, is_match && !indep);
+                while (todo) {
+                    const int k = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const unsigned int koff = __shfl_sync(full, off, k), khi = __shfl_sync(full, mhi, k);
+                    const unsigned int klen = khi & 0xFFFFu, kdist = khi >> 16;
+                    __syncwarp();                                          // the match source may have just been written
+                    const unsigned char *from = dst + out + koff - kdist;
+                    unsigned char *to = dst + out + koff;
+                    if (kdist == 1u) {
+                        // a run of one byte value (the zero runs of a sparse k-mer matrix): aligned 32-bit stores
+                        const unsigned int b = from[0], b4 = b * 0x01010101u;
+                        const unsigned int head = min(klen, (4u - ((unsigned int)(size_t)to & 3u)) & 3u);
+                        const unsigned int nw = (klen - head) >> 2, tail0 = head + (nw << 2);
+                        if ((unsigned int)lane < head) to[lane] = (unsigned char)b;
+                        unsigned int *tw = reinterpret_cast<unsigned int *>(to + head);
+                        for (unsigned int i = lane; i < nw; i += 32) tw[i] = b4;
+                        if (tail0 + (unsigned int)lane < klen) to[tail0 + lane] = (unsigned char)b;
+                    } else if (kdist >= klen) {
+                        for (unsigned int i = lane; i < klen; i += 32) to[i] = from[i];
+                    } else {
+                        unsigned int jj = (unsigned int)lane % kdist;
+                        const unsigned int step = 32u % kdist;
+                        for (unsigned int i = lane; i < klen; i += 32) {
+                            to[i] = from[jj];
+                            jj += step;
+                            if (jj >= kdist) jj -= kdist;
+                        }
+                    }
+                }
+                __syncwarp();
+                out += total;
+                p += pos;
+                if (p > nbits) {
+                    st = INF_IN_OVERRUN;
+                    break;
+                }
+                if (!stop) continue;                                       // the run goes on: next window
+                // (2) the symbol at p is not a table-resident literal: one symbol, decoded identically by every lane
+                unsigned long long q = peek64(src, p);
+                unsigned int used;
+                int sym;
+                {
+                    const unsigned int e1 = S.lit_tab[(unsigned int)q & ((1u << INF_LIT_BITS) - 1u)];
+                    if (e1 & 15u) {
+                        used = e1 & 15u;
+                        sym = (int)((e1 >> 4) & 0x1FFu);
+                    } else {
+                        const int r = slow_decode((unsigned int)q, S.lit_cnt, S.lit_sym);
+                        if (r < 0) {
+                            st = INF_BAD_CODE;
+                            break;
+                        }
+                        used = (unsigned int)(r >> 16);
+                        sym = r & 0xFFFF;
+                    }
+                }
+                q >>= used;
+                if (sym < 256) {                                           // a literal with a code longer than the table
+                    if (out + 1 > J.dst_bytes) {
+                        st = INF_OUT_OVERFLOW;
+                        break;
+                    }
+                    if (lane == 0) dst[out] = (unsigned char)sym;
+                    out += 1;
+                    p += used;
+                    continue;
+                }
+                if (sym == 256) {
+                    p += used;
+                    break;                                                 // end of block
+                }
+                sym -= 257;
+                if (sym >= 29) {
+                    st = INF_BAD_CODE;
+                    break;
+                }
+                unsigned int eb = s_len_extra[sym];
+                const unsigned int mlen = s_len_base[sym] + ((unsigned int)q & ((1u << eb) - 1u));
+                q >>= eb;
+                used += eb;
+                int ds;
+                {
+                    const unsigned int e2 = S.dist_tab[(unsigned int)q & ((1u << INF_DIST_BITS) - 1u)];
+                    unsigned int dl;
+                    if (e2 & 15u) {
+                        dl = e2 & 15u;
+                        ds = (int)(e2 >> 4);
+                    } else {
+                        const int r = slow_decode((unsigned int)q, S.dist_cnt, S.dist_sym);
+                        if (r < 0) {
+                            st = INF_BAD_CODE;
+                            break;
+                        }
+                        dl = (unsigned int)(r >> 16);
+                        ds = r & 0xFFFF;
+                    }
+                    q >>= dl;
+                    used += dl;
+                }
+                if (ds >= 30) {
+                    st = INF_BAD_CODE;
+                    break;
+                }
+                eb = s_dist_extra[ds];
+                const unsigned int mdist = s_dist_base[ds] + ((unsigned int)q & ((1u << eb) - 1u));
+                used += eb;
+                p += used;
+                if (p > nbits) {
+                    st = INF_IN_OVERRUN;
+                    break;
+                }
+                if (mdist > out) {
+                    st = INF_BAD_DISTANCE;
+                    break;
+                }
+                if (out + mlen > J.dst_bytes) {
+                    st = INF_OUT_OVERFLOW;
+                    break;
+                }
+                __syncwarp();                                              // the match source may have just been written
+                const unsigned char *from = dst + out - mdist;
+                unsigned char *to = dst + out;
+                if (mdist == 1u) {
+                    // a run of one byte value (the zero runs of a sparse k-mer matrix): aligned 32-bit stores
+                    const unsigned int b = from[0], b4 = b * 0x01010101u;
+                    const unsigned int head = min(mlen, (4u - ((unsigned int)(size_t)to & 3u)) & 3u);
+                    const unsigned int nw = (mlen - head) >> 2, tail0 = head + (nw << 2);
+                    if ((unsigned int)lane < head) to[lane] = (unsigned char)b;
+                    unsigned int *tw = reinterpret_cast<unsigned int *>(to + head);
+                    for (unsigned int i = lane; i < nw; i += 32) tw[i] = b4;
+                    if (tail0 + (unsigned int)lane < mlen) to[tail0 + lane] = (unsigned char)b;
+                } else if (mdist >= mlen) {
+                    for (unsigned int i = lane; i < mlen; i += 32) to[i] = from[i];
+                } else {
+                    // overlapping copy = the last mdist bytes repeated; i % mdist kept incrementally
+                    unsigned int j = (unsigned int)lane % mdist;
+                    const unsigned int step = 32u % mdist;
+                    for (unsigned int i = lane; i < mlen; i += 32) {
+                        to[i] = from[j];
+                        j += step;
+                        if (j >= mdist) j -= mdist;
+                    }
+                }
+                out += mlen;
+                __syncwarp();
+            }
+            if (p > nbits && st == INF_OK) st = INF_IN_OVERRUN;
+        }
+        // ---- trailer: Adler-32 of the output, big-endian, byte aligned
+        if (st == INF_OK) {
+            p = (p + 7u) & ~7u;
+            const unsigned int want = __byte_perm(peek32(src, p), 0, 0x0123);
+            p += 32;
+            if (p > nbits) st = INF_IN_OVERRUN;
+            else if (out != J.dst_bytes) st = INF_OUT_SHORT;
+            if (st == INF_OK) {
+                __syncwarp();
+                __threadfence_block();
+                if (warp_adler32(dst, J.dst_bytes, lane) != want) st = INF_BAD_CHECKSUM;
+            }
+        }
+        if (lane == 0) status[job] = st;
+        __syncwarp();
+    }
+}
+
 // Places the inflated chunks into the [W, ld] image.  A chunk holds chunk_rows x chunk_cols elements of the dataset
 // starting at (row0, gcol0); only the part inside the dataset and inside this shard's columns is kept (HDF5 stores
 // edge chunks at full size; shards are cut on 512-column tiles, so a chunk can belong to two shards).

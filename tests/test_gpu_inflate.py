@@ -81,7 +81,7 @@ CASES = [
 
 @pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
 @pytest.mark.parametrize("devices", [[0], [0, 0, 0]], ids=["1shard", "3shards"])
-@pytest.mark.parametrize("decoder", ["3", "2", "1"], ids=["two_codes_per_load", "warp_parallel_literals", "single_lane"])
+@pytest.mark.parametrize("decoder", ["4", "3", "2", "1"], ids=["all_symbols_speculative", "two_codes_per_load", "warp_parallel_literals", "single_lane"])
 def test_device_inflate_matches_host_path(tmp_path, monkeypatch, case, devices, decoder):
     name, dtype, n_rows, n_cols, chunks, compression, kind = case
     monkeypatch.setenv("KOVER_B200_INFLATE_V", decoder)
@@ -152,7 +152,7 @@ def test_corrupt_stream_is_reported_through_the_host_path(tmp_path):
     f.close()
 
 
-@pytest.mark.parametrize("decoder", ["3", "2", "1"], ids=["two_codes_per_load", "warp_parallel_literals", "single_lane"])
+@pytest.mark.parametrize("decoder", ["4", "3", "2", "1"], ids=["all_symbols_speculative", "two_codes_per_load", "warp_parallel_literals", "single_lane"])
 def test_status_codes_of_malformed_streams(monkeypatch, decoder):
     """kv_upload_deflate's per-chunk status on hand-made streams (C ABI level): good, truncated, wrong checksum,
     wrong size, bad header."""
