@@ -180,3 +180,81 @@ def test_status_codes_of_malformed_streams(monkeypatch, decoder):
     for r in (0, 1, 7):
         assert np.array_equal(img[r], rows[r])
     shard.close()
+
+
+def _fuzz_row(rs, n_bytes):
+    """One chunk of a random character: the byte statistics and match structure DEFLATE sees vary from pure noise to
+    long runs, short and long match distances, skewed alphabets (long Huffman codes) and periodic patterns."""
+    kind = rs.randint(0, 9)
+    if kind == 0:
+        b = rs.randint(0, 256, size=n_bytes)
+    elif kind == 1:                                  # long zero runs broken by noise
+        b = np.where(rs.rand(n_bytes) < rs.choice([0.001, 0.02, 0.2]), rs.randint(0, 256, size=n_bytes), 0)
+    elif kind == 2:                                  # a periodic pattern (period 1 .. 40) with mutations: overlapping matches
+        period = rs.randint(1, 41)
+        b = np.tile(rs.randint(0, 256, size=period), n_bytes // period + 1)[:n_bytes]
+        b = np.where(rs.rand(n_bytes) < 0.01, rs.randint(0, 256, size=n_bytes), b)
+    elif kind == 3:                                  # skewed alphabet: geometric byte frequencies -> codes of 1 .. 15 bits
+        b = np.minimum(rs.geometric(rs.choice([0.5, 0.2, 0.05]), size=n_bytes) - 1, 255)
+    elif kind == 4:                                  # far matches: copies of earlier segments at distances up to 32 KB
+        b = rs.randint(0, 256, size=n_bytes)
+        for _ in range(n_bytes // 300):
+            ln, dist = rs.randint(3, 300), rs.randint(1, 32768)
+            at = rs.randint(0, n_bytes - ln)
+            if at - dist >= 0:
+                b[at:at + ln] = b[at - dist:at - dist + ln]
+    elif kind == 5:                                  # k-mer-like packed words: rare / core / mid densities
+        dens = rs.choice([0.01, 0.5, 0.99], size=n_bytes // 8 + 1, p=[0.6, 0.3, 0.1])
+        bits = rs.rand(n_bytes // 8 + 1, 64) < dens[:, None]
+        b = np.packbits(bits, axis=1).reshape(-1)[:n_bytes]
+    elif kind == 6:
+        b = np.full(n_bytes, rs.randint(0, 256))     # one byte value
+    elif kind == 7:                                  # few distinct values
+        b = rs.choice(rs.randint(0, 256, size=rs.randint(2, 6)), size=n_bytes)
+    else:                                            # text-like
+        words = [bytes(rs.randint(97, 123, size=rs.randint(2, 9)).astype(np.uint8)) for _ in range(50)]
+        b = np.frombuffer(b" ".join(words[i] for i in rs.randint(0, 50, size=n_bytes // 3)), dtype=np.uint8)[:n_bytes]
+        b = np.concatenate([b, np.zeros(n_bytes - b.shape[0], dtype=np.uint8)])
+    return np.asarray(b, dtype=np.uint8)
+
+
+@pytest.mark.parametrize("decoder", ["4", "3", "2"], ids=["all_symbols_speculative", "two_codes_per_load", "warp_parallel_literals"])
+@pytest.mark.parametrize("n_cols", [1000, 40000], ids=["8KB", "320KB"])
+def test_randomized_streams_against_zlib(monkeypatch, decoder, n_cols):
+    """64 chunks of random character x every zlib level / strategy / window size / memory level, inflated on the device
+    straight into the image: bit-identical to the bytes zlib compressed, status 0 for every chunk.  (zlib.decompress of
+    the same streams is the oracle: the reference inflates through libhdf5 -> zlib, rules.py:253.)"""
+    from kover_b200 import _native
+    monkeypatch.setenv("KOVER_B200_INFLATE_V", decoder)
+    rs = np.random.RandomState(1234 + n_cols)
+    n_chunks = 64
+    shard = _native.Shard(0, 64 * n_chunks, n_cols)
+    rows, streams = [], []
+    strategies = [zlib.Z_DEFAULT_STRATEGY, zlib.Z_FILTERED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE, zlib.Z_FIXED]
+    for i in range(n_chunks):
+        raw = _fuzz_row(rs, n_cols * 8)
+        level = int(rs.randint(0, 10))
+        c = zlib.compressobj(level, zlib.DEFLATED, int(rs.choice([9, 12, 15])), int(rs.randint(1, 10)),
+                             strategies[rs.randint(0, len(strategies))])
+        parts = []
+        at = 0
+        while at < raw.shape[0]:                     # a few sync flushes: empty stored blocks inside the stream
+            step = int(rs.randint(1, raw.shape[0] + 1))
+            parts.append(c.compress(raw[at:at + step].tobytes()))
+            at += step
+            if at < raw.shape[0] and rs.rand() < 0.5:
+                parts.append(c.flush(zlib.Z_SYNC_FLUSH if rs.rand() < 0.7 else zlib.Z_FULL_FLUSH))
+        parts.append(c.flush())
+        stream = b"".join(parts)
+        assert zlib.decompress(stream) == raw.tobytes()
+        rows.append(raw.view(np.uint64))
+        streams.append(stream)
+    bufs = [np.frombuffer(st + b"\x00" * 8, dtype=np.uint8).copy() for st in streams]
+    addr = np.array([b.ctypes.data for b in bufs], dtype=np.uint64)
+    nbytes = np.array([len(st) for st in streams], dtype=np.int64)
+    status = shard.upload_deflate(64, addr, nbytes, np.arange(n_chunks), np.zeros(n_chunks, dtype=np.int64), 1, n_cols)
+    assert not status.any(), status
+    img = shard.read_block(0, n_chunks, 0, n_cols)
+    for r in range(n_chunks):
+        assert np.array_equal(img[r], rows[r]), r
+    shard.close()
