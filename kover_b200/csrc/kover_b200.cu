@@ -2930,6 +2930,7 @@ extern "C" int kv_upload_deflate(kv_shard *s, int pack_bits, int64_t n_chunks, c
     s->last_launches = 0;
     s->scm_valid = s->gini_valid = false;
     static const bool stats = getenv("KOVER_B200_INFLATE_STATS") != nullptr;      // phase times on stderr
+    static const bool trace = getenv("KOVER_B200_UPLOAD_TRACE") != nullptr;       // when each slab reached the device
     const auto now = [] { return std::chrono::steady_clock::now(); };
     const auto ms_since = [](std::chrono::steady_clock::time_point t0) {
         return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
@@ -3071,6 +3072,7 @@ extern "C" int kv_upload_deflate(kv_shard *s, int pack_bits, int64_t n_chunks, c
             CU(cudaMemcpyAsync(d_sjobs[par], sjobs.data(), n_scr * sizeof(ScatterJob), cudaMemcpyHostToDevice, s->inf_copy_stream));
         CU(cudaEventRecord(copied[par], s->inf_copy_stream));
         CU(cudaStreamSynchronize(s->inf_copy_stream));           // `jobs` / `sjobs` are reused by the next slab
+        if (trace) fprintf(stderr, "  slab %lld staged at %.1f ms (gather so far %.1f ms)\n", (long long)slab_no, ms_since(t_begin), t_gather);
         CU(cudaStreamWaitEvent(ks, copied[par], 0));
         const int grid = (int)std::min<long long>((n_here + INF_WARPS - 1) / INF_WARPS, (long long)s->sm_count * 6);
         if (stats) cudaEventRecord(ev_k0, ks);

@@ -1290,11 +1290,15 @@ __global__ void __launch_bounds__(INF_WARPS * 32) k_inflate4(const unsigned char
                 }
                 {
                     const unsigned long long w = peek64(src, p + 8u * (unsigned int)lane);
+                    const unsigned int wlo = (unsigned int)w, whi = (unsigned int)(w >> 32);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        const unsigned long long wj = w >> j;
+                        // 32-bit views only (64-bit variable shifts cost two or three instructions each): a = bits
+                        // [j, j + 32) of the peek, ah = bits [j + 32, 64); after the length code and its extra bits
+                        // (<= 20 bits) t = the next 32 bits, enough for the distance code and its extra bits (<= 28)
+                        const unsigned int a = __funnelshift_r(wlo, whi, j), ah = whi >> j;
                         const unsigned int c = 8u * (unsigned int)lane + (unsigned int)j;
-                        const unsigned int e = S.lit_tab[(unsigned int)wj & ((1u << INF_LIT_BITS) - 1u)];
+                        const unsigned int e = S.lit_tab[a & ((1u << INF_LIT_BITS) - 1u)];
                         unsigned int lo = (sym_base + (c << 3)) | INF4_STOP, hi = 0u;
                         unsigned int used = e & 15u;
                         if (e & 0x8000u) {                                             // literal
@@ -1304,16 +1308,16 @@ __global__ void __launch_bounds__(INF_WARPS * 32) k_inflate4(const unsigned char
                             if (ls < 29u) {
                                 const unsigned int lx = s_lenx[ls];
                                 unsigned int eb = lx >> 16;
-                                const unsigned int mlen = (lx & 0xFFFFu) + ((unsigned int)(wj >> used) & ((1u << eb) - 1u));
+                                const unsigned int mlen = (lx & 0xFFFFu) + ((a >> used) & ((1u << eb) - 1u));
                                 used += eb;
-                                const unsigned int e2 = S.dist_tab[(unsigned int)(wj >> used) & ((1u << INF_DIST_BITS) - 1u)];
+                                const unsigned int t = __funnelshift_r(a, ah, used);
+                                const unsigned int e2 = S.dist_tab[t & ((1u << INF_DIST_BITS) - 1u)];
                                 const unsigned int dl = e2 & 15u, ds = e2 >> 4;
                                 if (dl != 0u && ds < 30u) {
                                     const unsigned int dx = s_distx[ds];
                                     eb = dx >> 16;
-                                    used += dl;
-                                    const unsigned int mdist = (dx & 0xFFFFu) + ((unsigned int)(wj >> used) & ((1u << eb) - 1u));
-                                    used += eb;
+                                    const unsigned int mdist = (dx & 0xFFFFu) + ((t >> dl) & ((1u << eb) - 1u));
+                                    used += dl + eb;
                                     lo = (sym_base + ((c + used) << 3)) | INF4_MATCH;
                                     hi = mlen | (mdist << 16);
                                 }
