@@ -145,6 +145,21 @@ def main():
                 walk_eq(a.left_child, b.left_child)
                 walk_eq(a.right_child, b.right_child)
         walk_eq(t.decision_tree, root)
+        # the same with the experiments' occurrence tiebreaker applied on every rank's device (two small reductions + one
+        # exchange per level) and the larger sibling of every split derived from its parent's resident counts
+        from kover_b200.learning.experiments.experiment_cart import OccurrenceTiebreaker
+        occ = orc.sum_rows(train)
+        tb = OccurrenceTiebreaker(rc, train)
+        on_device = tb.device_occurrences is not None
+        try:
+            t2 = kcart.DecisionTreeClassifier("gini", 5, 2, {0: 1.0, 1: 2.0})
+            t2.fit(rules, rc, {0: neg, 1: pos}, rule_blacklist=blacklist[:1], tiebreaker=tb)
+        finally:
+            tb.release()
+        root2 = ko.cart_fit(orc, {0: neg, 1: pos}, "gini", 5, 2, {0: 1.0, 1: 2.0}, rule_blacklist=blacklist[:1],
+                            tiebreaker=lambda idx: ko.cart_tiebreaker(idx, occ))
+        walk_eq(t2.decision_tree, root2)
+        assert on_device and shard.info().level_nodes_derived > 0
         stats = dict(rc._group.exchange_stats)
         rc.close()
     # a peer that never publishes its packet: the waiting rank gives up after the timeout and reports it (both the
