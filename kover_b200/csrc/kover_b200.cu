@@ -3398,7 +3398,7 @@ static int launch_scan(kv_shard *s, const Scan2Params &P, int n_both) {
 static constexpr int kCandCap = 2048;                 // candidate records per CTA
 static bool stream_variant_ok(const kv_shard *s) {
     const int v = s->scan_variant;
-    return v < 0 || v > kNumScanVariants || v == 1 || v == 5 || v == 6;
+    return v < 0 || v > kNumScanVariants || v == 1 || v == 4 || v == 5 || v == 6;
 }
 static int launch_scan_stream(kv_shard *s, const Scan2Params &P) {
     int v = s->scan_variant;
@@ -3409,6 +3409,7 @@ static int launch_scan_stream(kv_shard *s, const Scan2Params &P) {
     int rc;
     switch (v) {
         case 1: rc = launch_scan_variant<EPI_SCM_STREAM, 16, 8, 3, 1>(s, P); break;
+        case 4: rc = launch_scan_variant<EPI_SCM_STREAM, 16, 4, 6, 1>(s, P); break;
         case 5: rc = launch_scan_variant<EPI_SCM_STREAM, 16, 4, 4, 1>(s, P); break;
         case 6: rc = launch_scan_variant<EPI_SCM_STREAM, 16, 8, 3, 1, true>(s, P); break;
         default: return fail(KV_E_INVALID, "no streaming kernel for this scan variant");
