@@ -466,7 +466,12 @@ def measure_shape(name, n_genomes, k_local, world, rank, local_rank, comm, seed,
             tb.release()
             out["depth10_fit_s" if attempt == "steady" else "depth10_first_fit_s"] = _t.perf_counter() - t0
         out["depth10_split_nodes"] = len(t.decision_tree.rules)
-        out["depth10_matrix_passes"] = shard.info().scan_calls - ia.scan_calls
+        ib = shard.info()
+        out["depth10_matrix_passes"] = ib.scan_calls - ia.scan_calls
+        # sibling subtraction (kv_gini_level_family): nodes whose class masks went through a matrix pass / nodes whose
+        # counts were parent - sibling
+        out["depth10_nodes_counted"] = ib.level_nodes_counted - ia.level_nodes_counted
+        out["depth10_nodes_derived"] = ib.level_nodes_derived - ia.level_nodes_derived
     rc.close()
     return out
 
