@@ -226,6 +226,7 @@ class Shard(object):
         # reusable output buffers of the per-step calls (their contents are copied out before returning)
         self._tie_cap = 1 << 16
         self._tie_buf = [np.empty(self._tie_cap, dtype=np.int64) for _ in range(3)]
+        self._tie_ptr = [a.ctypes.data for a in self._tie_buf]      # (.ctypes builds an object per access: cached)
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
@@ -431,19 +432,21 @@ class Shard(object):
     def scm_best_rules_p2p_idx(self, pos_idx, neg_idx, p, util_block_size, packet_capacity):
         """The multi-rank step from example index arrays (int64, contiguous) -> the 4-tuple, or None when a packet or
         the merged result overflowed (the caller redoes the step through the mask path and its two-phase fallback)."""
-        nb = n_utility_blocks(self.n_kmers_total, util_block_size)
-        if getattr(self, "_p2p_nb", None) != nb:
-            self._p2p_nb, self._p2p_bm, self._p2p_sel = nb, np.empty(nb, dtype=np.float64), np.empty(nb, dtype=np.uint8)
-        capacity, (idx, pe, nc) = self._tie_cap, self._tie_buf
+        if getattr(self, "_p2p_ubs", None) != util_block_size:         # (per util_block_size: block tables of the merge)
+            nb = n_utility_blocks(self.n_kmers_total, util_block_size)
+            self._p2p_ubs, self._p2p_bm, self._p2p_sel = util_block_size, np.empty(nb, dtype=np.float64), np.empty(nb, dtype=np.uint8)
+            self._p2p_ptr = (self._p2p_bm.ctypes.data, self._p2p_sel.ctypes.data)
+        capacity, (idx, pe, nc), (p_idx, p_pe, p_nc) = self._tie_cap, self._tie_buf, self._tie_ptr
         best, n, over = ctypes.c_double(0.0), _c_i64(0), ctypes.c_int(0)
-        rc = self._lib.kv_scm_best_rules_p2p_idx(self._h, pos_idx.ctypes.data, pos_idx.shape[0], neg_idx.ctypes.data,
-                                                 neg_idx.shape[0], float(p), int(util_block_size), int(packet_capacity),
-                                                 ctypes.byref(best), capacity, idx.ctypes.data, pe.ctypes.data,
-                                                 nc.ctypes.data, ctypes.byref(n), self._p2p_bm.ctypes.data,
-                                                 self._p2p_sel.ctypes.data, ctypes.byref(over))
+        rc = self._lib.kv_scm_best_rules_p2p_idx(self._h, pos_idx.__array_interface__["data"][0], pos_idx.shape[0],
+                                                 neg_idx.__array_interface__["data"][0], neg_idx.shape[0], p,
+                                                 util_block_size, packet_capacity, ctypes.byref(best), capacity, p_idx,
+                                                 p_pe, p_nc, ctypes.byref(n), self._p2p_ptr[0], self._p2p_ptr[1],
+                                                 ctypes.byref(over))
         if rc == KV_E_OVERFLOW or (rc == KV_OK and over.value):
             return None
-        check(rc)
+        if rc:
+            check(rc)
         m = n.value
         return best.value, idx[:m].copy(), pe[:m].copy(), nc[:m].copy()
 
@@ -523,15 +526,18 @@ class Shard(object):
 
     def scm_best_rules_idx(self, pos_idx, neg_idx, p, util_block_size):
         """scm_best_rules from example index arrays (int64, contiguous): the row masks are built in the library."""
-        capacity, (idx, pe, nc) = self._tie_cap, self._tie_buf
+        capacity, (idx, pe, nc), (p_idx, p_pe, p_nc) = self._tie_cap, self._tie_buf, self._tie_ptr
         best = ctypes.c_double(0.0)
         n = _c_i64(0)
-        rc = self._lib.kv_scm_best_rules_idx(self._h, pos_idx.ctypes.data, pos_idx.shape[0], neg_idx.ctypes.data,
-                                             neg_idx.shape[0], float(p), int(util_block_size), ctypes.byref(best),
-                                             capacity, idx.ctypes.data, pe.ctypes.data, nc.ctypes.data, ctypes.byref(n))
+        # (the per-iteration call of the SCM: pointers straight from the array interface, no ctypes objects)
+        rc = self._lib.kv_scm_best_rules_idx(self._h, pos_idx.__array_interface__["data"][0], pos_idx.shape[0],
+                                             neg_idx.__array_interface__["data"][0], neg_idx.shape[0], p,
+                                             util_block_size, ctypes.byref(best), capacity, p_idx, p_pe, p_nc,
+                                             ctypes.byref(n))
         if rc == KV_E_OVERFLOW:
             return None
-        check(rc)
+        if rc:
+            check(rc)
         m = n.value
         return best.value, idx[:m].copy(), pe[:m].copy(), nc[:m].copy()
 

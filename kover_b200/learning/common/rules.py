@@ -80,6 +80,13 @@ class BaseRuleClassifications(object):
         raise NotImplementedError()
 
 
+def _flat_int64(a):
+    """a as a contiguous 1-D int64 array -- itself when it already is one (the learners' index arrays)."""
+    if a.dtype == np.int64 and a.ndim == 1 and a.flags.c_contiguous:
+        return a
+    return np.ascontiguousarray(a, dtype=np.int64).reshape(-1)
+
+
 def _raw_chunk_view(dataset):
     """The dataset as something that can hand out the RAW gzip streams of its chunks (``deflate_chunk_table``), or None.
     hdf5_lite datasets do so themselves.  An h5py dataset -- what a Kover installation passes in (utils.py:58-73,
@@ -419,8 +426,7 @@ class KmerRuleClassifications(BaseRuleClassifications):
         self.set_rule_blacklist(rule_blacklist)
         if not self.dataset_removed_rows:
             # index arrays straight into the library (masks built there): one kernel launch per call and rank
-            out = self._group.scm_best_rules_idx(np.ascontiguousarray(positive_example_idx, dtype=np.int64).reshape(-1),
-                                                 np.ascontiguousarray(negative_example_idx, dtype=np.int64).reshape(-1),
+            out = self._group.scm_best_rules_idx(_flat_int64(positive_example_idx), _flat_int64(negative_example_idx),
                                                  float(p), int(util_block_size))
             if out is not None:
                 return out

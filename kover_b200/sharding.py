@@ -294,8 +294,11 @@ class ShardGroup(object):
                 return shard.scm_best_rules_idx(pos_idx, neg_idx, p, util_block_size)
             return None
         if self.comm is not None and len(self.shards) == 1 and hasattr(shard, "scm_best_rules_p2p_idx"):
-            nb = _native.n_utility_blocks(self.n_kmers, util_block_size)
-            if self.p2p_slot_bytes >= _native.packet_bytes(nb, self.PACKET_CAPACITY):
+            fits = self.__dict__.setdefault("_p2p_fits", {})          # (two library calls per step otherwise)
+            if util_block_size not in fits:
+                nb = _native.n_utility_blocks(self.n_kmers, util_block_size)
+                fits[util_block_size] = self.p2p_slot_bytes >= _native.packet_bytes(nb, self.PACKET_CAPACITY)
+            if fits[util_block_size]:
                 out = shard.scm_best_rules_p2p_idx(pos_idx, neg_idx, p, util_block_size, self.PACKET_CAPACITY)
                 if out is not None:
                     self.exchange_stats["one_exchange"] += 1
