@@ -411,6 +411,8 @@ class KmerRuleClassifications(BaseRuleClassifications):
 
     # ------------------------------------------------------------------ fused scans (this package's learners)
     def set_rule_blacklist(self, rule_blacklist):
+        if self._blacklist_key == b"" and isinstance(rule_blacklist, (list, tuple, np.ndarray)) and len(rule_blacklist) == 0:
+            return                                   # (the per-iteration call with nothing blacklisted, still nothing)
         bl = np.asarray(rule_blacklist, dtype=np.int64).reshape(-1)
         key = bl.tobytes()
         if key != self._blacklist_key:
