@@ -36,10 +36,6 @@ class _NodeImpurity(object):
     def _posterior(self, n_by_class):
         joint = dict((c, 1.0 * self.priors[c] * n_by_class[c] / self.n_total[c]) for c in n_by_class.keys())
         p_node = sum(joint.values())
-        if p_node != 0 and all(type(v) is float for v in joint.values()):
-            # scalar counts of a non-empty node (every node the learner creates): the same IEEE divisions without the
-            # errstate context and the numpy scalar round trips -- two of these run per created node
-            return dict((c, np.float64(joint[c] / p_node)) for c in joint.keys()), p_node
         with np.errstate(divide="ignore", invalid="ignore"):
             return dict((c, np.divide(joint[c], p_node)) for c in joint.keys()), p_node
 
