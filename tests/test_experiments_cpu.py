@@ -87,3 +87,44 @@ def test_first_hp_scoring_exactly_one_selects_nothing_like_python2():
         assert better(0.5, ("disjunction", 1.0, 3), 0.5, chosen) is True          # same score and size, p closer to 1
         assert better(0.5, ("disjunction", 10.0, 3), 0.5, chosen) is False
         assert better(0.6, ("disjunction", 1.0, 1), 0.5, chosen) is False
+
+
+def _tree_dict(node):
+    d = {"depth": node.depth, "criterion_value": float(node.criterion_value),
+         "n_by_class": {int(c): int(len(v)) for c, v in node.class_examples_idx.items()}}
+    if node.rule is not None:
+        d["rule_idx"] = int(node.rule.kmer_index)
+        d["equivalent_rules_idx"] = [int(x) for x in node.equivalent_rules_idx]
+        d["importance"] = float(node.rule.importance)
+        d["left"], d["right"] = _tree_dict(node.left_child), _tree_dict(node.right_child)
+    return d
+
+
+@pytest.mark.parametrize("case", list(cases.CART_CASES) + list(cases.CART_CE_CASES),
+                         ids=[c[0] for c in list(cases.CART_CASES) + list(cases.CART_CE_CASES)])
+def test_tree_learner_host_logic(golden_dir, case):
+    """kover_b200's DecisionTreeClassifier itself -- the breadth-first growth, the level batching with node / parent
+    keys, the cross-entropy formula evaluated on the host (cart.py:167-207) -- over checker-backed shards (no GPU)
+    against the REAL reference's trees: Gini bit-exact, cross-entropy to 4 ulp (np.log)."""
+    import json
+    from kover_b200.learning.common.rules import LazyKmerRuleList
+    from kover_b200.learning.learners.cart import DecisionTreeClassifier
+    from oracle import kover_oracle as ko
+    from test_oracle_golden import load, tree_equal
+    name, mname, lname, max_depth, mss, class_importance, tb, subset_seed = case
+    want = json.loads(str(load(golden_dir, name)["tree_json"]))
+    X, P, n, chunks = cases.matrix(mname)
+    y = cases.labels(lname)
+    k = P.shape[1]
+    rc = make_rc(P, n, chunks)
+    train = cases.train_subset(n, subset_seed)
+    example_idx = {c: train[y[train] == c] for c in sorted(class_importance.keys())}
+    tiebreaker = None
+    if tb == "occurrence":
+        occ = rc.sum_rows(train)
+        tiebreaker = lambda idx: ko.cart_tiebreaker(idx, occ)
+    criterion = "cross-entropy" if case in cases.CART_CE_CASES else "gini"
+    t = DecisionTreeClassifier(criterion, max_depth, mss, class_importance)
+    t.fit(LazyKmerRuleList(["K%d" % i for i in range(k)], np.arange(k)), rc, example_idx, rule_blacklist=[],
+          tiebreaker=tiebreaker)
+    tree_equal(_tree_dict(t.decision_tree), want, rtol=1e-15 if criterion == "cross-entropy" else 0.0)
