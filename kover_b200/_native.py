@@ -459,24 +459,24 @@ class Shard(object):
         -> [(best, idx, pos_err, neg_cover)] in job order."""
         n = len(jobs)
         r = self.QUEUE_SLOT_RECS
-        masks = np.empty((n, 2, self.n_words), dtype=np.uint64)
-        for j, job in enumerate(jobs):
-            masks[j, 0], masks[j, 1] = job[1], job[2]
-        n_pos = np.array([job[3] for job in jobs], dtype=np.int64)
-        n_neg = np.array([job[4] for job in jobs], dtype=np.int64)
-        ps = np.array([job[0] for job in jobs], dtype=np.float64)
-        reuse = np.array([job[5] for job in jobs], dtype=np.int32)
+        masks = _stack_job_masks(jobs, self.n_words)
+        ps, _, _, n_pos, n_neg, reuse = zip(*jobs) if n else ((), (), (), (), (), ())
+        n_pos, n_neg = np.array(n_pos, dtype=np.int64), np.array(n_neg, dtype=np.int64)
+        ps, reuse = np.array(ps, dtype=np.float64), np.array(reuse, dtype=np.int32)
         best, found = np.empty(n, dtype=np.float64), np.empty(n, dtype=np.int64)
         idx, pe, nc = (np.empty((n, r), dtype=np.int64) for _ in range(3))
         check(self._lib.kv_scm_queue_run(self._h, n, ptr(masks), ptr(n_pos), ptr(n_neg), ptr(ps), ptr(reuse),
                                          int(util_block_size), ptr(best), ptr(found), ptr(idx), ptr(pe), ptr(nc)))
+        # (the result arrays are this call's own: the per-job results are views into them, not copies)
+        best_l, found_l = best.tolist(), found.tolist()
         out = []
-        for j, (p, pm, nm, n_pos, n_neg, reuse) in enumerate(jobs):
-            m = int(found[j])
+        for j in range(n):
+            m = found_l[j]
             if m > r:
-                out.append(self.scm_best_rules(pm, nm, n_pos, n_neg, p, util_block_size, capacity=m))
+                p, pm, nm, jp, jn, _ = jobs[j]
+                out.append(self.scm_best_rules(pm, nm, jp, jn, p, util_block_size, capacity=m))
             else:
-                out.append((float(best[j]), idx[j, :m].copy(), pe[j, :m].copy(), nc[j, :m].copy()))
+                out.append((best_l[j], idx[j, :m], pe[j, :m], nc[j, :m]))
         return out
 
     def scm_queue_packets(self, jobs, util_block_size, capacity, packets):
@@ -484,9 +484,7 @@ class Shard(object):
         numpy uint8 array or a torch uint8 tensor on this shard's GPU of n_jobs * packet_bytes bytes, filled with one
         packet per job."""
         n = len(jobs)
-        masks = np.empty((n, 2, self.n_words), dtype=np.uint64)
-        for j, job in enumerate(jobs):
-            masks[j, 0], masks[j, 1] = job[1], job[2]
+        masks = _stack_job_masks(jobs, self.n_words)
         n_pos = np.array([job[3] for job in jobs], dtype=np.int64)
         n_neg = np.array([job[4] for job in jobs], dtype=np.int64)
         ps = np.array([job[0] for job in jobs], dtype=np.float64)
@@ -708,6 +706,27 @@ class Shard(object):
         out = np.empty(self.n_cols, dtype=np.float64)
         check(self._lib.kv_gini_scores(self._h, ptr(out)))
         return out
+
+
+def _stack_job_masks(jobs, n_words):
+    """uint64 [n_jobs, 2, W] of the jobs' (positive, negative) row masks; the jobs of a grid share a handful of mask
+    arrays, which are stacked once and gathered by index."""
+    n = len(jobs)
+    slot, distinct = {}, []
+    index = np.empty((n, 2), dtype=np.intp)
+    for j, job in enumerate(jobs):
+        for h in (0, 1):
+            a = job[1 + h]
+            k = slot.get(id(a))
+            if k is None:
+                k = slot[id(a)] = len(distinct)
+                distinct.append(a)
+            index[j, h] = k
+    if not distinct:
+        return np.empty((0, 2, n_words), dtype=np.uint64)
+    table = np.ascontiguousarray(np.stack(distinct), dtype=np.uint64)
+    assert table.shape[1] == n_words
+    return table[index]
 
 
 def n_utility_blocks(n_kmers_total, util_block_size):

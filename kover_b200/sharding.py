@@ -349,9 +349,15 @@ class ShardGroup(object):
         matrix is scanned once per DISTINCT unordered mask pair; every other job re-scores the counts that scan
         left on the device (kv_scm_reuse_counts: another p, or positives and negatives exchanged as the
         disjunction does, scm.py:69-73).  Results in job order, each as scm_best_rules returns it."""
-        groups = {}
+        groups, content = {}, {}
+
+        def content_of(mask):            # (the jobs of a grid share a handful of mask arrays: one tobytes per array)
+            b = content.get(id(mask))
+            if b is None:
+                b = content[id(mask)] = mask.tobytes()
+            return b
         for i, (p, pm, nm, n_pos, n_neg) in enumerate(jobs):
-            key = (pm.tobytes(), nm.tobytes())
+            key = (content_of(pm), content_of(nm))
             if key in groups:
                 groups[key].append((i, False))
             elif (key[1], key[0]) in groups:
