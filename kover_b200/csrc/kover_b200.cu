@@ -2426,6 +2426,76 @@ static void pinned_return(void *p) {
     cudaFreeHost(p);                             // (not one of ours)
 }
 
+// The same for the device scratch of the deflate upload (compressed slabs, job lists): cudaMalloc of a few hundred MB
+// costs 2 ms on some boxes and 20 ms on others (measured: `setup` of kv_upload_deflate), as much as inflating a sparse
+// matrix takes.  Per device; at most kDevCacheBytes idle in total and kDevCacheEntry per buffer -- larger ones are freed.
+static constexpr size_t kDevCacheBytes = (size_t)3 << 30, kDevCacheEntry = (size_t)1 << 30;
+struct DevCache {
+    struct Ent {
+        void *p;
+        size_t bytes;
+        int device;
+        bool busy;
+    };
+    std::mutex mu;
+    std::vector<Ent> ents;
+};
+static DevCache g_devcache;
+
+static cudaError_t dev_borrow(void **out, size_t bytes, int device) {
+    {
+        std::lock_guard<std::mutex> lock(g_devcache.mu);
+        DevCache::Ent *best = nullptr;
+        for (auto &e : g_devcache.ents)
+            if (!e.busy && e.device == device && e.bytes >= bytes && e.bytes <= 2 * bytes + (1 << 20) &&
+                (!best || e.bytes < best->bytes))
+                best = &e;
+        if (best) {
+            best->busy = true;
+            *out = best->p;
+            return cudaSuccess;
+        }
+    }
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) {                      // memory pressure: give the idle cache back and try once more
+        cudaGetLastError();
+        {
+            std::lock_guard<std::mutex> lock(g_devcache.mu);
+            for (size_t i = g_devcache.ents.size(); i-- > 0;)
+                if (!g_devcache.ents[i].busy && g_devcache.ents[i].device == device) {
+                    cudaFree(g_devcache.ents[i].p);
+                    g_devcache.ents.erase(g_devcache.ents.begin() + (long)i);
+                }
+        }
+        e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) return e;
+    }
+    std::lock_guard<std::mutex> lock(g_devcache.mu);
+    g_devcache.ents.push_back({p, bytes, device, true});
+    *out = p;
+    return cudaSuccess;
+}
+
+static void dev_return(void *p) {                // (the caller has synchronised the streams that used the buffer)
+    if (!p) return;
+    std::lock_guard<std::mutex> lock(g_devcache.mu);
+    size_t idle = 0;
+    for (auto &e : g_devcache.ents)
+        if (!e.busy) idle += e.bytes;
+    for (size_t i = 0; i < g_devcache.ents.size(); ++i) {
+        if (g_devcache.ents[i].p != p) continue;
+        if (g_devcache.ents[i].bytes > kDevCacheEntry || idle + g_devcache.ents[i].bytes > kDevCacheBytes) {
+            cudaFree(p);
+            g_devcache.ents.erase(g_devcache.ents.begin() + (long)i);
+        } else {
+            g_devcache.ents[i].busy = false;
+        }
+        return;
+    }
+    cudaFree(p);
+}
+
 struct kv_p2p;
 static void p2p_destroy(kv_p2p *m);
 struct kv_shard;
@@ -2882,9 +2952,10 @@ static int gather_threads() {
 struct DevFree {                      // frees device buffers / events of one kv_upload_deflate call on every exit path
     std::vector<void *> bufs;
     std::vector<cudaEvent_t> events;
+    bool idle = false;                // every stream that touched the buffers has been synchronised
     ~DevFree() {
-        for (void *p : bufs)
-            if (p) cudaFree(p);
+        if (!idle) cudaDeviceSynchronize();          // (error exit: kernels of the call may still be running)
+        for (void *p : bufs) dev_return(p);          // back to the process-wide cache (dev_borrow)
         for (cudaEvent_t e : events)
             if (e) cudaEventDestroy(e);
     }
@@ -2993,15 +3064,15 @@ extern "C" int kv_upload_deflate(kv_shard *s, int pack_bits, int64_t n_chunks, c
     } stream_free{k_stream};
     for (int i = 1; i < n_par; ++i) CU(cudaStreamCreateWithFlags(&k_stream[i], cudaStreamNonBlocking));
     for (int i = 0; i < n_par; ++i) {
-        CU(cudaMalloc(&d_comp[i], max_comp + 64));
+        CU(dev_borrow((void **)&d_comp[i], max_comp + 64, s->device));
         F.bufs.push_back(d_comp[i]);
         if (max_scratch) {
-            CU(cudaMalloc(&d_scratch[i], max_scratch * chunk_stride));
+            CU(dev_borrow((void **)&d_scratch[i], max_scratch * chunk_stride, s->device));
             F.bufs.push_back(d_scratch[i]);
-            CU(cudaMalloc(&d_sjobs[i], max_scratch * sizeof(ScatterJob)));
+            CU(dev_borrow((void **)&d_sjobs[i], max_scratch * sizeof(ScatterJob), s->device));
             F.bufs.push_back(d_sjobs[i]);
         }
-        CU(cudaMalloc(&d_jobs[i], (size_t)slab * sizeof(InflateJob)));
+        CU(dev_borrow((void **)&d_jobs[i], (size_t)slab * sizeof(InflateJob), s->device));
         F.bufs.push_back(d_jobs[i]);
         CU(cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming));
         F.events.push_back(copied[i]);
@@ -3010,9 +3081,9 @@ extern "C" int kv_upload_deflate(kv_shard *s, int pack_bits, int64_t n_chunks, c
     }
     int *d_status = nullptr;
     unsigned int *d_next = nullptr;
-    CU(cudaMalloc(&d_status, (size_t)n_chunks * sizeof(int)));
+    CU(dev_borrow((void **)&d_status, (size_t)n_chunks * sizeof(int), s->device));
     F.bufs.push_back(d_status);
-    CU(cudaMalloc(&d_next, n_slabs * sizeof(unsigned int)));
+    CU(dev_borrow((void **)&d_next, n_slabs * sizeof(unsigned int), s->device));
     F.bufs.push_back(d_next);
     CU(cudaMemsetAsync(d_status, 0xFF, (size_t)n_chunks * sizeof(int), s->stream));
     CU(cudaMemsetAsync(d_next, 0, n_slabs * sizeof(unsigned int), s->stream));
@@ -3126,6 +3197,7 @@ extern "C" int kv_upload_deflate(kv_shard *s, int pack_bits, int64_t n_chunks, c
     CU(cudaMemcpyAsync(status, d_status, (size_t)n_chunks * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
     CU(cudaGetLastError());
+    F.idle = true;                                  // (every kernel stream and the copy stream were synchronised above)
     s->up_setup_ms = t_setup;
     s->up_gather_ms = t_gather;
     s->up_total_ms = ms_since(t_begin);
